@@ -1,0 +1,362 @@
+"""TEST INFRASTRUCTURE — CPU restatement (numpy) of the CUP2D hot path on a uniform grid.
+
+This module is the *checker*.  Only tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline/reference leg may import it; the product path (cup2d_b200/) never does.
+
+Parity status: PINNED.  Every function below is checked in tests/test_oracle_golden.py against
+outputs of the unmodified reference (oracle/_ref/ref_harness = /root/reference/main.cpp compiled as
+is, driven through oracle/shim/), committed as fixtures under tests/golden/ together with the
+script that generated them (tests/golden/make_golden.py).  The reference ships no tests or golden
+vectors of its own.
+
+All citations are file:line in /root/reference.  Fields are held as GLOBAL 2-D arrays
+a[iy, ix] (row-major, N = 8*2^L cells per side, h = extent/N); `to_blocks/from_blocks` convert
+to the reference's memory layout (8x8 blocks concatenated in Hilbert order, vectors interleaved
+u,v per cell: main.cpp:6517, 5467-5468).
+"""
+import numpy as np
+
+BS = 8  # _BS_, Makefile:12
+
+
+# --------------------------------------------------------------------------------------------
+# Space-filling curve (main.cpp:342-446) — regular case bpdx == bpdy == 2^k
+# --------------------------------------------------------------------------------------------
+def hilbert_xy2d(b, x, y):
+    """SpaceCurve::AxestoTranspose (main.cpp:347-359): index of block (x,y) on a 2^b x 2^b curve."""
+    n = 1 << b
+    d = 0
+    s = n // 2
+    while s > 0:
+        rx = 1 if (x & s) > 0 else 0
+        ry = 1 if (y & s) > 0 else 0
+        d += s * s * ((3 * rx) ^ ry)
+        # rot (main.cpp:374-384) with n = full size
+        if ry == 0:
+            if rx == 1:
+                x = n - 1 - x
+                y = n - 1 - y
+            x, y = y, x
+        s //= 2
+    return d
+
+
+def hilbert_d2xy(b, d):
+    """SpaceCurve::TransposetoAxes (main.cpp:360-373)."""
+    n = 1 << b
+    x = y = 0
+    t = d
+    s = 1
+    while s < n:
+        rx = 1 & (t // 2)
+        ry = 1 & (t ^ rx)
+        if ry == 0:
+            if rx == 1:
+                x = s - 1 - x
+                y = s - 1 - y
+            x, y = y, x
+        x += s * rx
+        y += s * ry
+        t //= 4
+        s *= 2
+    return x, y
+
+
+def block_order(L):
+    """(i, j) of every block of a uniform level-L grid (bpdx=bpdy=1) in reference `infos` order:
+    blocks are sorted by the Hilbert key (main.cpp:1550-1562, 6519-6537); returns int array (4^L, 2)."""
+    nb = 1 << L
+    out = np.empty((nb * nb, 2), dtype=np.int32)
+    for d in range(nb * nb):
+        out[d] = hilbert_d2xy(L, d)
+    return out
+
+
+def to_blocks(a, order, dim=1):
+    """global field(s) -> reference block layout, flat.  dim=2: a = (u, v) interleaved per cell."""
+    nblk = len(order)
+    out = np.empty((nblk, BS, BS, dim))
+    comps = (a,) if dim == 1 else a
+    for k, (i, j) in enumerate(order):
+        for c in range(dim):
+            out[k, :, :, c] = comps[c][j * BS:(j + 1) * BS, i * BS:(i + 1) * BS]
+    return out.reshape(-1)
+
+
+def from_blocks(flat, order, dim=1):
+    nblk = len(order)
+    nb = int(round(np.sqrt(nblk)))
+    blk = np.asarray(flat).reshape(nblk, BS, BS, dim)
+    outs = [np.empty((nb * BS, nb * BS)) for _ in range(dim)]
+    for k, (i, j) in enumerate(order):
+        for c in range(dim):
+            outs[c][j * BS:(j + 1) * BS, i * BS:(i + 1) * BS] = blk[k, :, :, c]
+    return outs[0] if dim == 1 else tuple(outs)
+
+
+# --------------------------------------------------------------------------------------------
+# Ghost cells at the domain edge (what BlockLab + _apply_bc produce on a uniform grid)
+# --------------------------------------------------------------------------------------------
+def pad_vector(u, v, g):
+    """VectorLab::applyBCface (main.cpp:3131-3154): every ghost layer takes the wall-adjacent cell,
+    normal component negated, tangential copied (free-slip).  Corner ghosts are not used by any
+    hot-path stencil (all are cross-shaped)."""
+    up = np.pad(u, g, mode="edge")
+    vp = np.pad(v, g, mode="edge")
+    up[:, :g] *= -1.0  # x faces: u is normal
+    up[:, -g:] *= -1.0
+    vp[:g, :] *= -1.0  # y faces: v is normal
+    vp[-g:, :] *= -1.0
+    return up, vp
+
+
+def pad_scalar(p, g):
+    """ScalarLab::Neumann2D (main.cpp:3210-3245): constant extrapolation."""
+    return np.pad(p, g, mode="edge")
+
+
+# --------------------------------------------------------------------------------------------
+# WENO5 (main.cpp:162-208)
+# --------------------------------------------------------------------------------------------
+def _betas(um2, um1, u, up1, up2):
+    b1 = 13.0 / 12.0 * ((um2 + u) - 2 * um1) ** 2 + 0.25 * ((um2 + 3 * u) - 4 * um1) ** 2
+    b2 = 13.0 / 12.0 * ((um1 + up1) - 2 * u) ** 2 + 0.25 * (um1 - up1) ** 2
+    b3 = 13.0 / 12.0 * ((u + up2) - 2 * up1) ** 2 + 0.25 * ((3 * u + up2) - 4 * up1) ** 2
+    return b1, b2, b3
+
+
+def weno5_plus(um2, um1, u, up1, up2):
+    """main.cpp:162-181"""
+    e = 1e-6
+    b1, b2, b3 = _betas(um2, um1, u, up1, up2)
+    g1, g2, g3 = 0.1, 0.6, 0.3
+    what1 = g1 / (b1 + e) ** 2
+    what2 = g2 / (b2 + e) ** 2
+    what3 = g3 / (b3 + e) ** 2
+    aux = 1.0 / ((what1 + what3) + what2)
+    w1, w2, w3 = what1 * aux, what2 * aux, what3 * aux
+    f1 = (11.0 / 6.0) * u + ((1.0 / 3.0) * um2 - (7.0 / 6.0) * um1)
+    f2 = (5.0 / 6.0) * u + ((-1.0 / 6.0) * um1 + (1.0 / 3.0) * up1)
+    f3 = (1.0 / 3.0) * u + ((+5.0 / 6.0) * up1 - (1.0 / 6.0) * up2)
+    return (w1 * f1 + w3 * f3) + w2 * f2
+
+
+def weno5_minus(um2, um1, u, up1, up2):
+    """main.cpp:182-201"""
+    e = 1e-6
+    b1, b2, b3 = _betas(um2, um1, u, up1, up2)
+    g1, g2, g3 = 0.3, 0.6, 0.1
+    what1 = g1 / (b1 + e) ** 2
+    what2 = g2 / (b2 + e) ** 2
+    what3 = g3 / (b3 + e) ** 2
+    aux = 1.0 / ((what1 + what3) + what2)
+    w1, w2, w3 = what1 * aux, what2 * aux, what3 * aux
+    f1 = (1.0 / 3.0) * u + ((-1.0 / 6.0) * um2 + (5.0 / 6.0) * um1)
+    f2 = (5.0 / 6.0) * u + ((1.0 / 3.0) * um1 - (1.0 / 6.0) * up1)
+    f3 = (11.0 / 6.0) * u + ((-7.0 / 6.0) * up1 + (1.0 / 3.0) * up2)
+    return (w1 * f1 + w3 * f3) + w2 * f2
+
+
+def derivative(U, um3, um2, um1, u, up1, up2, up3):
+    """main.cpp:202-208"""
+    plus = weno5_plus(um2, um1, u, up1, up2) - weno5_plus(um3, um2, um1, u, up1)
+    minus = weno5_minus(um1, u, up1, up2, up3) - weno5_minus(um2, um1, u, up1, up2)
+    return np.where(U > 0, plus, minus)
+
+
+# --------------------------------------------------------------------------------------------
+# Operators
+# --------------------------------------------------------------------------------------------
+def advect_diffuse(u, v, h, nu, dt):
+    """KernelAdvectDiffuse::operator() (main.cpp:5441-5503): undivided RHS written to tmpV."""
+    g = 3
+    N = u.shape[0]
+    up, vp = pad_vector(u, v, g)
+    dfac = nu * dt
+    afac = -dt * h
+
+    def sx(a, k):  # a(ix+k, iy)
+        return a[g:g + N, g + k:g + k + N]
+
+    def sy(a, k):  # a(ix, iy+k)
+        return a[g + k:g + k + N, g:g + N]
+
+    dudx = derivative(u, sx(up, -3), sx(up, -2), sx(up, -1), u, sx(up, 1), sx(up, 2), sx(up, 3))
+    dudy = derivative(v, sy(up, -3), sy(up, -2), sy(up, -1), u, sy(up, 1), sy(up, 2), sy(up, 3))
+    dvdx = derivative(u, sx(vp, -3), sx(vp, -2), sx(vp, -1), v, sx(vp, 1), sx(vp, 2), sx(vp, 3))
+    dvdy = derivative(v, sy(vp, -3), sy(vp, -2), sy(vp, -1), v, sy(vp, 1), sy(vp, 2), sy(vp, 3))
+    tu = afac * (u * dudx + v * dudy) + dfac * (sx(up, 1) + sx(up, -1) + sy(up, 1) + sy(up, -1) - 4 * u)
+    tv = afac * (u * dvdx + v * dvdy) + dfac * (sx(vp, 1) + sx(vp, -1) + sy(vp, 1) + sy(vp, -1) - 4 * v)
+    return tu, tv
+
+
+def compute_dt(u, v, h, nu, cfl):
+    """main.cpp:6579-6595"""
+    umax = max(np.abs(u).max(), np.abs(v).max())
+    dt_diff = 0.25 * h * h / (nu + 0.25 * h * umax)
+    dt_adv = h / (umax + 1e-8)
+    return min(dt_diff, cfl * dt_adv)
+
+
+def rk2(u, v, h, nu, dt):
+    """main.cpp:6607-6642: vold=vel; V=Vold+0.5*K(V)/h^2; V=Vold+K(V)/h^2."""
+    uo, vo = u.copy(), v.copy()
+    tu, tv = advect_diffuse(u, v, h, nu, dt)
+    ih2 = 0.5 / (h * h)
+    u1, v1 = uo + tu * ih2, vo + tv * ih2
+    tu, tv = advect_diffuse(u1, v1, h, nu, dt)
+    ih2 = 1.0 / (h * h)
+    return uo + tu * ih2, vo + tv * ih2
+
+
+def pressure_rhs(u, v, udu, udv, chi, h, dt):
+    """pressure_rhs::operator() (main.cpp:6105-6139)"""
+    N = u.shape[0]
+    up, vp = pad_vector(u, v, 1)
+    dup, dvp = pad_vector(udu, udv, 1)
+    fac = 0.5 * h / dt
+    c = slice(1, 1 + N)
+    div_v = up[c, 2:] - up[c, :-2] + vp[2:, c] - vp[:-2, c]
+    div_u = dup[c, 2:] - dup[c, :-2] + dvp[2:, c] - dvp[:-2, c]
+    return fac * div_v - fac * chi * div_u
+
+
+def laplacian_neumann(p):
+    """5-point undivided Laplacian with constant-extrapolation ghosts = the Poisson matrix rows of
+    main.cpp:7074-7107 (interior: +1,+1,-4,+1,+1; domain edge: missing neighbour omitted, diagonal
+    = -(number of neighbours)) and pressure_rhs1's stencil (main.cpp:6209-6230)."""
+    N = p.shape[0]
+    pp = pad_scalar(p, 1)
+    c = slice(1, 1 + N)
+    return pp[c, :-2] + pp[c, 2:] + pp[:-2, c] + pp[2:, c] - 4 * p
+
+
+def pressure_rhs1(tmp, pold):
+    """main.cpp:6209-6230: tmp -= lap(pold)"""
+    return tmp - laplacian_neumann(pold)
+
+
+def grad_p(p, h, dt):
+    """pressureCorrectionKernel::operator() (main.cpp:6021-6043)"""
+    N = p.shape[0]
+    pp = pad_scalar(p, 1)
+    pfac = -0.5 * dt * h
+    c = slice(1, 1 + N)
+    return pfac * (pp[c, 2:] - pp[c, :-2]), pfac * (pp[2:, c] - pp[:-2, c])
+
+
+# --------------------------------------------------------------------------------------------
+# Poisson: block-Jacobi preconditioned BiCGSTAB (cuda.cu:403-548), matrix-free on a uniform grid
+# --------------------------------------------------------------------------------------------
+def build_P_inv():
+    """main.cpp:46-57 (getA_local) + 6451-6488: P_inv = -(A_loc)^-1 via dense Cholesky."""
+    n = BS * BS
+    A = np.zeros((n, n))
+    for I1 in range(n):
+        j1, i1 = divmod(I1, BS)
+        for I2 in range(n):
+            j2, i2 = divmod(I2, BS)
+            if I1 == I2:
+                A[I1, I2] = 4.0
+            elif abs(i1 - i2) + abs(j1 - j2) == 1:
+                A[I1, I2] = -1.0
+    Lc = np.linalg.cholesky(A)
+    Linv = np.linalg.solve(Lc, np.eye(n))
+    return -(Linv.T @ Linv)
+
+
+_P_INV = None
+
+
+def precond(v):
+    """cuda.cu:484-486: z_blk = P_inv^T v_blk for every 8x8 block (within-block index 8*iy+ix)."""
+    global _P_INV
+    if _P_INV is None:
+        _P_INV = build_P_inv()
+    N = v.shape[0]
+    nb = N // BS
+    blk = v.reshape(nb, BS, nb, BS).transpose(0, 2, 1, 3).reshape(nb, nb, BS * BS)
+    z = blk @ _P_INV.T
+    return z.reshape(nb, nb, BS, BS).transpose(0, 2, 1, 3).reshape(N, N)
+
+
+def bicgstab(b, x0, max_error=0.0, max_rel_error=0.0, max_restarts=0, max_iter=1000,
+             A=laplacian_neumann, M=precond):
+    """BiCGSTABSolver::main (cuda.cu:403-548), same operation order, eps guards and stopping rule.
+    Returns (x_opt, iterations, error_opt)."""
+    eps = 1e-21
+    alpha = beta = omega = rho_prev = rho_curr = 1.0
+    x = x0.copy()
+    r = b - A(x)                                   # cuda.cu:412-415
+    error = error_init = error_opt = np.abs(r).max()  # 420-430
+    x_opt = x.copy()
+    rhat = r.copy()
+    nu = np.zeros_like(b)
+    p = np.zeros_like(b)
+    restarts = 0
+    k = 0
+    while k < max_iter:                            # cuda.cu:438
+        rho_curr = float(np.vdot(rhat, r))         # 440
+        nr2 = float(np.vdot(r, r))
+        nrh2 = float(np.vdot(rhat, rhat))
+        breakdown = rho_curr * rho_curr < 1e-16 * nr2 * nrh2   # 452-454
+        beta = (rho_curr / (rho_prev + eps)) * (alpha / (omega + eps))  # 315-318
+        if breakdown and max_restarts > 0:         # 457-477
+            restarts += 1
+            if restarts >= max_restarts:
+                break
+            rhat = r.copy()
+            rho_curr = float(np.vdot(rhat, rhat))
+            nu[:] = 0
+            p[:] = 0
+            rho_prev = alpha = omega = 1.0
+            beta = (rho_curr / (rho_prev + eps)) * (alpha / (omega + eps))
+        p = beta * (p - omega * nu) + r            # 478-483
+        z = M(p)                                   # 484
+        nu = A(z)                                  # 487
+        alpha = rho_curr / (float(np.vdot(rhat, nu)) + eps)  # 488-496
+        x = x + alpha * z                          # 498
+        r = r - alpha * nu                         # 502
+        z = M(r)                                   # 503
+        t = A(z)                                   # 506
+        omega = float(np.vdot(t, r)) / (float(np.vdot(t, t)) + eps)  # 507-518
+        x = x + omega * z                          # 520
+        r = r - omega * t                          # 524
+        error = np.abs(r).max()                    # 525-534
+        k += 1
+        if error < error_opt:                      # 535-541
+            error_opt = error
+            x_opt = x.copy()
+            if error <= max_error or error / error_init <= max_rel_error:
+                break
+        rho_prev = rho_curr                        # 325-327
+    return x_opt, k, error_opt
+
+
+# --------------------------------------------------------------------------------------------
+# One full time step of the hot path without bodies (main.cpp:6576-7187 minus the OUT-of-scope parts)
+# --------------------------------------------------------------------------------------------
+def step(u, v, pres, nu, cfl, extent=1.0, kiter=1000, tol=0.0, tol_rel=0.0, max_restarts=100,
+         chi=None, udef=None, dt=None):
+    """Returns dict(dt, u, v, p, b, x, iters)."""
+    N = u.shape[0]
+    h = extent / N
+    if dt is None:
+        dt = compute_dt(u, v, h, nu, cfl)
+    u, v = rk2(u, v, h, nu, dt)
+    if chi is None:
+        chi = np.zeros_like(u)
+    if udef is None:
+        udef = (np.zeros_like(u), np.zeros_like(u))
+    tmp = pressure_rhs(u, v, udef[0], udef[1], chi, h, dt)   # main.cpp:7011
+    pold = pres.copy()                                        # 7016-7021
+    tmp = pressure_rhs1(tmp, pold)                            # 7026
+    x, iters, err = bicgstab(tmp, np.zeros_like(tmp), tol, tol_rel, max_restarts, kiter)  # 7114-7118
+    # main.cpp:7120-7173 (uniform h: the h^2 weights cancel)
+    p = x - x.sum() / x.size
+    p = p + (pold - p.sum() / p.size)
+    gu, gv = grad_p(p, h, dt)                                 # 7178
+    ih2 = 1.0 / h / h                                         # 7180-7187
+    u = u + gu * ih2
+    v = v + gv * ih2
+    return dict(dt=dt, u=u, v=v, p=p, b=tmp, x=x, iters=iters, err=err)

@@ -1,0 +1,295 @@
+// TEST INFRASTRUCTURE (oracle) — not part of the product path.
+//
+// Operator-level harness around the UNMODIFIED reference translation unit.  It includes
+// /root/reference/main.cpp verbatim (only `main` is renamed by a macro), lets the
+// reference's own init code build a uniform 2^L x 2^L-block grid
+// (-bpdx 1 -bpdy 1 -levelStart L -levelMax L+1 -Ctol 0), and takes control
+// at the first MPI_Allreduce(MPI_MAX) of the time loop (main.cpp:6592) through the hook of
+// oracle/shim/mpi.h.  From there it calls the reference's own operators
+// (computeA<VectorLab>(KernelAdvectDiffuse(), ...) etc., main.cpp:6616, 7011, 7026, 7178)
+// on seeded fields, or lets the reference time loop run and records every step.
+//
+// All files are raw little-endian doubles in GLOBAL row-major cell order
+// (index = iy*N + ix, N = 8*2^L), so they do not depend on the block ordering.
+//
+//   ref_harness order L out.bin
+//        out: int32 pairs (i,j) of every block in reference `infos` order (Hilbert id order)
+//   ref_harness ops   L nu dt in.bin out.bin
+//        in : u v p chi udef_u udef_v            (6 N^2 doubles)
+//        out: K(vel)_u K(vel)_v  rhs  rhs1  gradp_u gradp_v   (6 N^2 doubles)
+//             K = KernelAdvectDiffuse output tmpV (undivided), rhs = pressure_rhs(vel,udef,chi),
+//             rhs1 = rhs - lap(p) (pressure_rhs1 with pold = p), gradp = pressureCorrectionKernel(p)
+//   ref_harness steps L nu cfl nsteps kiter in.bin out.bin
+//        in : as above (udef ignored: no shapes => udef = 0, chi = 0 ; p = initial pres)
+//        out: per step: dt, then u v p  b x   (1 + 5 N^2 doubles), b/x = Poisson rhs / solution
+//   ref_harness time  L reps kiter
+//        prints one JSON line with per-operator CPU times (seconds, median of reps)
+#define CUP2D_REF_HOOK_TU 1
+#define main ref_main
+#include "main.cpp" // resolved with -I/root/reference
+#undef main
+#include <chrono>
+
+extern int cup2d_ref_last_iters;
+extern double cup2d_ref_last_err;
+extern int cup2d_ref_force_iters;
+
+namespace {
+enum Mode { ORDER, OPS, STEPS, TIME } g_mode;
+int g_L, g_N, g_nsteps, g_reps, g_kiter;
+double g_nu, g_dt, g_cfl;
+std::string g_in, g_out;
+int g_calls = 0;
+std::vector<double> g_input;
+FILE *g_fout = nullptr;
+
+double now() {
+  return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+void read_input(int nfields) {
+  g_input.resize((size_t)nfields * g_N * g_N);
+  FILE *f = fopen(g_in.c_str(), "rb");
+  if (!f || fread(g_input.data(), sizeof(double), g_input.size(), f) != g_input.size()) {
+    fprintf(stderr, "ref_harness: cannot read %s\n", g_in.c_str());
+    exit(2);
+  }
+  fclose(f);
+}
+// scatter a global row-major field into a reference grid (dim 1 or 2 components)
+void scatter(Grid *g, int dim, const double *c0, const double *c1) {
+  for (auto &info : g->infos) {
+    const int bi = info.index[0], bj = info.index[1];
+    for (int iy = 0; iy < _BS_; iy++)
+      for (int ix = 0; ix < _BS_; ix++) {
+        size_t gidx = (size_t)(bj * _BS_ + iy) * g_N + (bi * _BS_ + ix);
+        info.block[dim * (_BS_ * iy + ix)] = c0[gidx];
+        if (dim == 2) info.block[dim * (_BS_ * iy + ix) + 1] = c1[gidx];
+      }
+  }
+}
+void gather(Grid *g, int dim, double *c0, double *c1) {
+  for (auto &info : g->infos) {
+    const int bi = info.index[0], bj = info.index[1];
+    for (int iy = 0; iy < _BS_; iy++)
+      for (int ix = 0; ix < _BS_; ix++) {
+        size_t gidx = (size_t)(bj * _BS_ + iy) * g_N + (bi * _BS_ + ix);
+        c0[gidx] = info.block[dim * (_BS_ * iy + ix)];
+        if (dim == 2) c1[gidx] = info.block[dim * (_BS_ * iy + ix) + 1];
+      }
+  }
+}
+void write_field(Grid *g, int dim) {
+  std::vector<double> a((size_t)g_N * g_N), b((size_t)g_N * g_N);
+  gather(g, dim, a.data(), b.data());
+  fwrite(a.data(), sizeof(double), a.size(), g_fout);
+  if (dim == 2) fwrite(b.data(), sizeof(double), b.size(), g_fout);
+}
+void write_vec(const std::vector<double> &x) {
+  // solver vectors are block-major in `infos` order (main.cpp:5753-5771): back to global order
+  std::vector<double> a((size_t)g_N * g_N);
+  auto &infos = var.tmp->infos;
+  for (size_t i = 0; i < infos.size(); i++) {
+    const int bi = infos[i].index[0], bj = infos[i].index[1];
+    for (int iy = 0; iy < _BS_; iy++)
+      for (int ix = 0; ix < _BS_; ix++)
+        a[(size_t)(bj * _BS_ + iy) * g_N + (bi * _BS_ + ix)] = x[i * _BS_ * _BS_ + iy * _BS_ + ix];
+  }
+  fwrite(a.data(), sizeof(double), a.size(), g_fout);
+}
+double field_umax() {
+  double umax = 0;
+  for (auto &info : var.vel->infos)
+    for (int j = 0; j < 2 * _BS_ * _BS_; j++) umax = std::max(umax, std::fabs(info.block[j]));
+  return umax;
+}
+// the reference's own calling sequences (main.cpp:6611-6617, 7007-7013, 7022-7027, 7174-7179)
+void call_advect() {
+  if (var.tmpV->UpdateFluxCorrection) {
+    prepare0(var.buf2, &var.tmpV->infos, &var.tmpV->all, &var.tmpV->tree, 2);
+    var.tmpV->UpdateFluxCorrection = false;
+  }
+  computeA<VectorLab>(KernelAdvectDiffuse(), var.vel, 2);
+  fillcases(var.buf2, &var.tmpV->tree, 2);
+}
+void call_rhs() {
+  if (var.tmp->UpdateFluxCorrection) {
+    prepare0(var.buf1, &var.tmp->infos, &var.tmp->all, &var.tmp->tree, 1);
+    var.tmp->UpdateFluxCorrection = false;
+  }
+  computeB<pressure_rhs, VectorLab, VectorLab>(pressure_rhs(), var.vel, 2, var.tmpV, 2);
+  fillcases(var.buf1, &var.tmp->tree, 1);
+}
+void call_rhs1() {
+  if (var.tmp->UpdateFluxCorrection) {
+    prepare0(var.buf1, &var.tmp->infos, &var.tmp->all, &var.tmp->tree, 1);
+    var.tmp->UpdateFluxCorrection = false;
+  }
+  computeA<ScalarLab>(pressure_rhs1(), var.pold, 1);
+  fillcases(var.buf1, &var.tmp->tree, 1);
+}
+void call_gradp() {
+  if (var.tmp->UpdateFluxCorrection) {
+    prepare0(var.buf1, &var.tmp->infos, &var.tmp->all, &var.tmp->tree, 1);
+    var.tmp->UpdateFluxCorrection = false;
+  }
+  computeA<ScalarLab>(pressureCorrectionKernel(), var.pres, 1);
+  fillcases(var.buf1, &var.tmp->tree, 1);
+}
+void rk_update(double c) { // main.cpp:6618-6626 / 6634-6642
+  auto &velInfo = var.vel->infos;
+#pragma omp parallel for
+  for (size_t i = 0; i < velInfo.size(); i++) {
+    Real *V = velInfo[i].block, *Vold = var.vold->infos[i].block, *tmpV = var.tmpV->infos[i].block;
+    Real ih2 = c / (velInfo[i].h * velInfo[i].h);
+    for (int j = 0; j < 2 * _BS_ * _BS_; j++) V[j] = Vold[j] + tmpV[j] * ih2;
+  }
+}
+void corr_update() { // main.cpp:7180-7187
+  auto &velInfo = var.vel->infos;
+#pragma omp parallel for
+  for (size_t i = 0; i < velInfo.size(); i++) {
+    Real ih2 = 1.0 / velInfo[i].h / velInfo[i].h;
+    Real *V = velInfo[i].block, *tmpV = var.tmpV->infos[i].block;
+    for (int j = 0; j < 2 * _BS_ * _BS_; j++) V[j] += tmpV[j] * ih2;
+  }
+}
+void seed_taylor_green() {
+  const size_t n2 = (size_t)g_N * g_N;
+  g_input.assign(6 * n2, 0.0);
+  for (int iy = 0; iy < g_N; iy++)
+    for (int ix = 0; ix < g_N; ix++) {
+      double x = (ix + 0.5) / g_N, y = (iy + 0.5) / g_N;
+      g_input[0 * n2 + (size_t)iy * g_N + ix] = sin(2 * M_PI * x) * cos(2 * M_PI * y);
+      g_input[1 * n2 + (size_t)iy * g_N + ix] = -cos(2 * M_PI * x) * sin(2 * M_PI * y);
+      g_input[2 * n2 + (size_t)iy * g_N + ix] = cos(2 * M_PI * x) * cos(2 * M_PI * y);
+    }
+}
+template <class F> double median_time(int reps, F f) {
+  std::vector<double> t;
+  f(); // warm-up (also builds the cached sync plan, excluded as BASELINE.md §3 says)
+  for (int r = 0; r < reps; r++) {
+    double t0 = now();
+    f();
+    t.push_back(now() - t0);
+  }
+  std::sort(t.begin(), t.end());
+  return t[t.size() / 2];
+}
+
+void do_order() {
+  FILE *f = fopen(g_out.c_str(), "wb");
+  for (auto &info : var.vel->infos) {
+    int ij[2] = {info.index[0], info.index[1]};
+    fwrite(ij, sizeof(int), 2, f);
+  }
+  fclose(f);
+}
+void do_ops() {
+  const size_t n2 = (size_t)g_N * g_N;
+  read_input(6);
+  const double *in = g_input.data();
+  sim.nu = g_nu;
+  sim.dt = g_dt;
+  g_fout = fopen(g_out.c_str(), "wb");
+  scatter(var.vel, 2, in, in + n2);
+  call_advect();
+  write_field(var.tmpV, 2);
+  scatter(var.tmpV, 2, in + 4 * n2, in + 5 * n2);
+  scatter(var.chi, 1, in + 3 * n2, nullptr);
+  call_rhs();
+  write_field(var.tmp, 1);
+  scatter(var.pold, 1, in + 2 * n2, nullptr);
+  call_rhs1();
+  write_field(var.tmp, 1);
+  scatter(var.pres, 1, in + 2 * n2, nullptr);
+  call_gradp();
+  write_field(var.tmpV, 2);
+  fclose(g_fout);
+}
+void do_time() {
+  seed_taylor_green();
+  const size_t n2 = (size_t)g_N * g_N;
+  const double *in = g_input.data();
+  scatter(var.vel, 2, in, in + n2);
+  scatter(var.vold, 2, in, in + n2);
+  scatter(var.pres, 1, in + 2 * n2, nullptr);
+  scatter(var.pold, 1, in + 2 * n2, nullptr);
+  double h = var.vel->infos[0].h, umax = field_umax();
+  sim.nu = 1e-3;
+  sim.dt = std::min(0.25 * h * h / (sim.nu + 0.25 * h * umax), 0.5 * h / (umax + 1e-8));
+  double t_stage = median_time(g_reps, [] { call_advect(); rk_update(0.5); scatter(var.vel, 2, g_input.data(), g_input.data() + (size_t)g_N * g_N); });
+  double t_scatter = median_time(g_reps, [] { scatter(var.vel, 2, g_input.data(), g_input.data() + (size_t)g_N * g_N); });
+  t_stage -= t_scatter;
+  double t_rhs = median_time(g_reps, [] { call_rhs(); call_rhs1(); });
+  double t_corr = median_time(g_reps, [] { call_gradp(); corr_update(); });
+  int nthreads = 1;
+#ifdef _OPENMP
+  nthreads = omp_get_max_threads();
+#endif
+  printf("{\"L\": %d, \"N\": %d, \"cells\": %zu, \"threads\": %d, \"t_stage\": %.6e, \"t_rhs\": %.6e, "
+         "\"t_correct\": %.6e}\n",
+         g_L, g_N, n2, nthreads, t_stage, t_rhs, t_corr);
+}
+} // namespace
+
+void cup2d_ref_hook(int op, void *buf, int count) {
+  if (op != MPI_MAX || count != 1) return;
+  const int call = g_calls++;
+  if (g_mode == ORDER) { do_order(); exit(0); }
+  if (g_mode == OPS) { do_ops(); exit(0); }
+  if (g_mode == TIME) { do_time(); exit(0); }
+  // STEPS: call 0 = before step 0 (seed), call k = after k steps (record)
+  const size_t n2 = (size_t)g_N * g_N;
+  if (call == 0) {
+    read_input(6);
+    const double *in = g_input.data();
+    scatter(var.vel, 2, in, in + n2);
+    scatter(var.pres, 1, in + 2 * n2, nullptr);
+    *(double *)buf = field_umax(); // umax feeds dt (main.cpp:6593-6595)
+    g_fout = fopen(g_out.c_str(), "wb");
+    return;
+  }
+  fwrite(&sim.dt, sizeof(double), 1, g_fout);
+  write_field(var.vel, 2);
+  write_field(var.pres, 1);
+  write_vec(sim.mat->get_b());
+  write_vec(sim.mat->get_x());
+  fprintf(stderr, "ref_harness: step %d dt %.17g poisson iters %d err %.3e\n", call - 1, sim.dt,
+          cup2d_ref_last_iters, cup2d_ref_last_err);
+  if (call == g_nsteps) {
+    fclose(g_fout);
+    exit(0);
+  }
+}
+
+int main(int argc, char **argv) {
+  if (argc < 3) {
+    fprintf(stderr, "usage: ref_harness order|ops|steps|time L ...\n");
+    return 2;
+  }
+  std::string mode = argv[1];
+  g_L = atoi(argv[2]);
+  g_N = _BS_ << g_L;
+  g_nu = 1e-3;
+  g_cfl = 0.5;
+  if (mode == "order" && argc == 4) { g_mode = ORDER; g_out = argv[3]; }
+  else if (mode == "ops" && argc == 7) { g_mode = OPS; g_nu = atof(argv[3]); g_dt = atof(argv[4]); g_in = argv[5]; g_out = argv[6]; }
+  else if (mode == "steps" && argc == 9) {
+    g_mode = STEPS; g_nu = atof(argv[3]); g_cfl = atof(argv[4]); g_nsteps = atoi(argv[5]);
+    g_kiter = atoi(argv[6]); g_in = argv[7]; g_out = argv[8];
+    cup2d_ref_force_iters = g_kiter;
+  } else if (mode == "time" && argc == 5) { g_mode = TIME; g_reps = atoi(argv[3]); g_kiter = atoi(argv[4]); }
+  else { fprintf(stderr, "ref_harness: bad arguments\n"); return 2; }
+  char a_ls[32], a_lm[32], a_nu[64], a_cfl[64];
+  snprintf(a_ls, sizeof a_ls, "%d", g_L);
+  snprintf(a_lm, sizeof a_lm, "%d", g_L + 1);
+  snprintf(a_nu, sizeof a_nu, "%.17g", g_nu);
+  snprintf(a_cfl, sizeof a_cfl, "%.17g", g_cfl);
+  const char *args[] = {"ref_main", "-AdaptSteps", "1000000", "-bpdx", "1", "-bpdy", "1", "-CFL", a_cfl,
+                        "-Ctol", "0", "-extent", "1", "-lambda", "1e7", "-levelMax", a_lm, "-levelStart", a_ls,
+                        "-maxPoissonIterations", "1000", "-maxPoissonRestarts", "0", "-nu", a_nu,
+                        "-poissonTol", "0", "-poissonTolRel", "0", "-Rtol", "1e300", "-tdump", "0",
+                        "-tend", "1e300", "-shapes", ""};
+  int n = sizeof args / sizeof *args;
+  return ref_main(n, (char **)args);
+}

@@ -1,0 +1,218 @@
+// TEST INFRASTRUCTURE (oracle) — not part of the product path.
+//
+// CPU restatement of the reference's device Krylov solver, linked IN PLACE OF cuda.cu
+// when the unmodified reference main.cpp is built into oracle/_ref/ref_harness, so the
+// reference time loop can run in a container without a GPU.  Single rank only.
+//
+// Follows, operation by operation (same order, same epsilons, same stopping rule):
+//   container      : /root/reference/cuda.cu:549-699  (reserve/cooPushBack*/make/solve*)
+//   BiCGSTAB main  : /root/reference/cuda.cu:403-548
+//   scalar kernels : /root/reference/cuda.cu:303-330  (set_beta/alpha/omega/rho, breakdown_update)
+//   SpMV           : /root/reference/cuda.cu:344-402  (COO y = A z; bd part empty at size 1)
+//   preconditioner : /root/reference/cuda.cu:484-486,503-505  z_blk = P_inv^T v_blk
+// Reductions (cublasDdot/Dnrm2/Idamax there) are plain sequential loops here: their
+// order is implementation-defined in the reference, so parity is to rounding.
+//
+// The class declaration comes from the reference's own header at build time
+// (-I/root/reference); nothing from the reference is copied into this repository.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <map>
+#include <memory>
+#include <mpi.h>
+#include <set>
+#include <vector>
+#include "cuda.h"
+
+class BiCGSTABSolver {
+public:
+  BiCGSTABSolver(LocalSpMatDnVec &ls, int blen, const std::vector<double> &P_inv)
+      : ls_(ls), blen_(blen), P_inv_(P_inv) {}
+  void run(double max_error, double max_rel_error, int max_restarts);
+  int last_iters = 0;
+  double last_err = 0;
+
+private:
+  void spmv(const std::vector<double> &z, std::vector<double> &y) const;
+  void precond(const std::vector<double> &v, std::vector<double> &z) const;
+  LocalSpMatDnVec &ls_;
+  int blen_;
+  std::vector<double> P_inv_;
+};
+
+// exported so the harness can report iteration counts
+int cup2d_ref_last_iters = 0;
+double cup2d_ref_last_err = 0;
+int cup2d_ref_force_iters = -1; // >=0: cap the loop at this many iterations (harness timing/parity)
+
+void BiCGSTABSolver::spmv(const std::vector<double> &z, std::vector<double> &y) const {
+  // cuda.cu:361-363  y = A_loc z   (COO is row-sorted: rows are pushed in order, main.cpp:7051-7111)
+  const int nnz = ls_.loc_nnz_;
+  const int m = ls_.m_;
+  const double *val = ls_.loc_cooValA_.data();
+  const int *row = ls_.loc_cooRowA_int_.data();
+  const int *col = ls_.loc_cooColA_int_.data();
+  for (int i = 0; i < m; i++) y[i] = 0;
+  for (int k = 0; k < nnz; k++) y[row[k]] += val[k] * z[col[k]];
+}
+
+void BiCGSTABSolver::precond(const std::vector<double> &v, std::vector<double> &z) const {
+  // cuda.cu:484-486: Dgemm(OP_T, OP_N, BLEN, m/BLEN, BLEN, 1, P_inv, BLEN, v, BLEN, 0, z, BLEN)
+  // column-major P_inv^T(i,j) = P_inv[i*BLEN + j]
+  const int B = blen_, nb = ls_.m_ / B;
+#pragma omp parallel for
+  for (int b = 0; b < nb; b++)
+    for (int i = 0; i < B; i++) {
+      double s = 0;
+      for (int j = 0; j < B; j++) s += P_inv_[i * B + j] * v[b * B + j];
+      z[b * B + i] = s;
+    }
+}
+
+static double dot(const std::vector<double> &a, const std::vector<double> &b, int m) {
+  double s = 0;
+  for (int i = 0; i < m; i++) s += a[i] * b[i];
+  return s;
+}
+static double amax(const std::vector<double> &a, int m) {
+  double s = 0;
+  for (int i = 0; i < m; i++) s = std::max(s, std::fabs(a[i]));
+  return s;
+}
+
+void BiCGSTABSolver::run(double max_error, double max_rel_error, int max_restarts) {
+  const int m = ls_.m_;
+  std::vector<double> &x = ls_.x_;
+  std::vector<double> r(ls_.b_), x_opt(m), rhat(m), p(m, 0.), nu(m, 0.), t(m), z(m);
+  // cuda.cu:409 scalars {alpha, beta, omega, eps, rho_prev, rho_curr, buff_1, buff_2}
+  double alpha = 1, beta = 1, omega = 1, rho_prev = 1, rho_curr = 1;
+  const double eps = 1e-21;
+  double error, error_init, error_opt;
+  int restarts = 0;
+  // cuda.cu:412-415  r = b - A x0
+  z = x;
+  spmv(z, nu);
+  for (int i = 0; i < m; i++) r[i] -= nu[i];
+  // cuda.cu:416-430
+  error = amax(r, m);
+  error_init = error;
+  error_opt = error;
+  x_opt = x;
+  rhat = r;
+  std::fill(nu.begin(), nu.end(), 0.);
+  std::fill(p.begin(), p.end(), 0.);
+  size_t max_iter = 1000; // cuda.cu:438
+  if (cup2d_ref_force_iters >= 0) max_iter = cup2d_ref_force_iters;
+  size_t k = 0;
+  for (; k < max_iter; k++) {
+    rho_curr = dot(rhat, r, m);                     // cuda.cu:440
+    double nr2 = dot(r, r, m), nrh2 = dot(rhat, rhat, m); // cuda.cu:441-447 (nrm2 squared)
+    const bool serious_breakdown = rho_curr * rho_curr < 1e-16 * nr2 * nrh2; // cuda.cu:452-454
+    beta = (rho_curr / (rho_prev + eps)) * (alpha / (omega + eps));          // set_beta 315-318
+    if (serious_breakdown && max_restarts > 0) { // cuda.cu:457-477
+      restarts++;
+      if (restarts >= max_restarts) break;
+      rhat = r;
+      rho_curr = dot(rhat, rhat, m);
+      std::fill(nu.begin(), nu.end(), 0.);
+      std::fill(p.begin(), p.end(), 0.);
+      rho_prev = 1; alpha = 1; omega = 1;           // breakdown_update 308-314
+      beta = (rho_curr / (rho_prev + eps)) * (alpha / (omega + eps));
+    }
+    for (int i = 0; i < m; i++) {                   // cuda.cu:478-483
+      double pi = p[i] + (-omega) * nu[i];
+      pi = beta * pi;
+      p[i] = pi + r[i];
+    }
+    precond(p, z);                                  // 484
+    spmv(z, nu);                                    // 487
+    double rhat_nu = dot(rhat, nu, m);              // 488
+    alpha = rho_curr / (rhat_nu + eps);             // set_alpha 319-321
+    for (int i = 0; i < m; i++) x[i] += alpha * z[i];   // 498
+    for (int i = 0; i < m; i++) r[i] += (-alpha) * nu[i]; // 499-502
+    precond(r, z);                                  // 503
+    spmv(z, t);                                     // 506
+    double tr = dot(t, r, m), tt = dot(t, t, m);    // 507-516
+    omega = tr / (tt + eps);                        // set_omega 322-324
+    for (int i = 0; i < m; i++) x[i] += omega * z[i];   // 520
+    for (int i = 0; i < m; i++) r[i] += (-omega) * t[i]; // 521-524
+    error = amax(r, m);                             // 525-534
+    if (error < error_opt) {                        // 535-541
+      error_opt = error;
+      x_opt = x;
+      if ((error <= max_error) || (error / error_init <= max_rel_error)) { k++; break; }
+    }
+    rho_prev = rho_curr;                            // set_rho 325-327
+  }
+  last_iters = (int)k;
+  last_err = error_opt;
+  cup2d_ref_last_iters = last_iters;
+  cup2d_ref_last_err = last_err;
+  x = x_opt;                                        // cuda.cu:546-547
+}
+
+// ---- container (cuda.cu:549-699), single rank -------------------------------------------
+LocalSpMatDnVec::LocalSpMatDnVec(MPI_Comm m_comm, const int BLEN, const bool bMeanConstraint,
+                                 const std::vector<double> &P_inv)
+    : m_comm_(m_comm), BLEN_(BLEN) {
+  MPI_Comm_rank(m_comm_, &rank_);
+  MPI_Comm_size(m_comm_, &comm_size_);
+  if (comm_size_ != 1 || bMeanConstraint) {
+    fprintf(stderr, "ref_spmat_cpu: single rank, bMeanConstraint=0 only\n");
+    abort();
+  }
+  bd_recv_set_.resize(comm_size_);
+  solver_ = std::make_unique<BiCGSTABSolver>(*this, BLEN, P_inv);
+}
+LocalSpMatDnVec::~LocalSpMatDnVec() {}
+void LocalSpMatDnVec::reserve(const int N) { // cuda.cu:567-587
+  m_ = N;
+  bMeanRow_ = -1;
+  loc_cooValA_.clear();
+  loc_cooRowA_long_.clear();
+  loc_cooColA_long_.clear();
+  loc_cooValA_.reserve(6 * (size_t)N);
+  loc_cooRowA_long_.reserve(6 * (size_t)N);
+  loc_cooColA_long_.reserve(6 * (size_t)N);
+  x_.resize(N);
+  b_.resize(N);
+  h2_.resize(N / BLEN_);
+}
+void LocalSpMatDnVec::cooPushBackVal(const double val, const long long row, const long long col) {
+  loc_cooValA_.push_back(val); // cuda.cu:588-593
+  loc_cooRowA_long_.push_back(row);
+  loc_cooColA_long_.push_back(col);
+}
+void LocalSpMatDnVec::cooPushBackRow(const SpRowInfo &row) { // cuda.cu:594-610
+  for (const auto &i : row.loc_colval_) {
+    loc_cooValA_.push_back(i.second);
+    loc_cooRowA_long_.push_back(row.idx_);
+    loc_cooColA_long_.push_back(i.first);
+  }
+  if (!row.neirank_cols_.empty()) {
+    fprintf(stderr, "ref_spmat_cpu: boundary columns at size 1\n");
+    abort();
+  }
+}
+void LocalSpMatDnVec::make(const std::vector<long long> &Nrows_xcumsum) { // cuda.cu:611-689
+  loc_nnz_ = (int)loc_cooValA_.size();
+  bd_nnz_ = 0;
+  halo_ = 0;
+  const long long shift = -Nrows_xcumsum[rank_];
+  loc_cooRowA_int_.resize(loc_nnz_);
+  loc_cooColA_int_.resize(loc_nnz_);
+  for (int i = 0; i < loc_nnz_; i++) {
+    loc_cooRowA_int_[i] = (int)(loc_cooRowA_long_[i] + shift);
+    loc_cooColA_int_[i] = (int)(loc_cooColA_long_[i] + shift);
+  }
+}
+void LocalSpMatDnVec::solveWithUpdate(const double max_error, const double max_rel_error,
+                                      const int max_restarts) {
+  solver_->run(max_error, max_rel_error, max_restarts);
+}
+void LocalSpMatDnVec::solveNoUpdate(const double max_error, const double max_rel_error,
+                                    const int max_restarts) {
+  solver_->run(max_error, max_rel_error, max_restarts);
+}

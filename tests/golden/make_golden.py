@@ -1,0 +1,104 @@
+"""Generate the golden fixtures in this directory from the UNMODIFIED reference.
+
+Run in the build container (needs /root/reference, which does not exist on the GPU box):
+
+    make -C oracle ref && python tests/golden/make_golden.py
+
+Every fixture is the output of oracle/_ref/ref_harness (= /root/reference/main.cpp compiled as is;
+see oracle/ref_harness.cpp for the modes) on seeded inputs.  Inputs are stored alongside outputs so
+the tests never need the reference at run time.  All arrays are global row-major a[iy, ix].
+"""
+import os
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+HARNESS = os.path.join(ROOT, "oracle", "_ref", "ref_harness")
+
+
+def run(*args):
+    subprocess.run([HARNESS, *map(str, args)], check=True, stderr=subprocess.DEVNULL)
+
+
+def taylor_green(N):
+    x = (np.arange(N) + 0.5) / N
+    X, Y = np.meshgrid(x, x)  # X[iy, ix]
+    u = np.sin(2 * np.pi * X) * np.cos(2 * np.pi * Y)
+    v = -np.cos(2 * np.pi * X) * np.sin(2 * np.pi * Y)
+    p = np.cos(2 * np.pi * X) * np.cos(2 * np.pi * Y)
+    return u, v, p
+
+
+def make_inputs(kind, L, seed):
+    N = 8 << L
+    rng = np.random.default_rng(seed)
+    if kind == "random":
+        u, v, p = (rng.uniform(-1, 1, (N, N)) for _ in range(3))
+        chi = rng.uniform(0, 1, (N, N))
+        udu, udv = (rng.uniform(-1, 1, (N, N)) for _ in range(2))
+    else:
+        u, v, p = taylor_green(N)
+        # small seeded perturbation so that no symmetry hides an indexing error
+        u = u + 0.05 * rng.uniform(-1, 1, (N, N))
+        v = v + 0.05 * rng.uniform(-1, 1, (N, N))
+        x = (np.arange(N) + 0.5) / N
+        X, Y = np.meshgrid(x, x)
+        chi = np.exp(-((X - 0.4) ** 2 + (Y - 0.55) ** 2) / 0.02)
+        udu, udv = 0.3 * np.sin(3 * X + Y), 0.2 * np.cos(2 * Y - X)
+    return [np.ascontiguousarray(a, dtype=np.float64) for a in (u, v, p, chi, udu, udv)]
+
+
+def gen_order(tmp):
+    for L in (0, 1, 2, 3, 4, 5):
+        out = os.path.join(tmp, "order.bin")
+        run("order", L, out)
+        o = np.fromfile(out, dtype=np.int32).reshape(-1, 2)
+        np.save(os.path.join(HERE, f"order_L{L}.npy"), o)
+        print("order", L, o.shape)
+
+
+def gen_ops(tmp, kind, L, seed, nu, dt):
+    N = 8 << L
+    ins = make_inputs(kind, L, seed)
+    fin, fout = os.path.join(tmp, "in.bin"), os.path.join(tmp, "out.bin")
+    np.concatenate([a.ravel() for a in ins]).tofile(fin)
+    run("ops", L, repr(nu), repr(dt), fin, fout)
+    o = np.fromfile(fout).reshape(6, N, N)
+    np.savez_compressed(
+        os.path.join(HERE, f"ops_L{L}_{kind}.npz"), nu=nu, dt=dt, L=L,
+        u=ins[0], v=ins[1], p=ins[2], chi=ins[3], udef_u=ins[4], udef_v=ins[5],
+        adv_u=o[0], adv_v=o[1], rhs=o[2], rhs1=o[3], gradp_u=o[4], gradp_v=o[5])
+    print("ops", kind, L, float(np.abs(o).max()))
+
+
+def gen_steps(tmp, kind, L, seed, nu, cfl, nsteps, kiter):
+    N = 8 << L
+    ins = make_inputs(kind, L, seed)
+    fin, fout = os.path.join(tmp, "in.bin"), os.path.join(tmp, "out.bin")
+    np.concatenate([a.ravel() for a in ins]).tofile(fin)
+    run("steps", L, repr(nu), repr(cfl), nsteps, kiter, fin, fout)
+    raw = np.fromfile(fout).reshape(nsteps, 1 + 5 * N * N)
+    dts = raw[:, 0].copy()
+    f = raw[:, 1:].reshape(nsteps, 5, N, N)
+    np.savez_compressed(
+        os.path.join(HERE, f"steps_L{L}_{kind}_k{kiter}.npz"), nu=nu, cfl=cfl, L=L, kiter=kiter,
+        u0=ins[0], v0=ins[1], p0=ins[2], dt=dts,
+        u=f[:, 0], v=f[:, 1], p=f[:, 2], b=f[:, 3], x=f[:, 4])
+    print("steps", kind, L, dts)
+
+
+if __name__ == "__main__":
+    if not os.path.exists(HARNESS):
+        sys.exit("build oracle/_ref/ref_harness first: make -C oracle ref")
+    with tempfile.TemporaryDirectory() as tmp:
+        gen_order(tmp)
+        gen_ops(tmp, "random", 2, 1234, 1e-3, 2.5e-3)
+        gen_ops(tmp, "tg", 3, 4321, 1e-3, 1.2e-3)
+        gen_steps(tmp, "tg", 2, 777, 1e-3, 0.5, 3, 12)
+        gen_steps(tmp, "random", 2, 778, 1e-2, 0.4, 2, 8)
+        gen_steps(tmp, "tg", 3, 779, 1e-3, 0.5, 2, 40)
+        gen_steps(tmp, "tg", 3, 779, 1e-3, 0.5, 2, 15)
