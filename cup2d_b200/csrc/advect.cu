@@ -1,0 +1,306 @@
+// Fused advection-diffusion RK stage:  out = old + coef * K(in) / h^2
+//
+// K is the reference's KernelAdvectDiffuse (main.cpp:5441-5503): WENO5 upwind differences
+// (main.cpp:162-208) of both velocity components + 5-point diffusion, undivided.  The Lab assembly
+// (BlockLab::load, main.cpp:2270-2440) and the free-slip ghost fill (VectorLab::applyBCface,
+// main.cpp:3131-3154) become the tile loader of this kernel; the RK update loops
+// (main.cpp:6618-6626, 6634-6642) are fused into the store.
+//
+// One CTA = one tile of 4x4 blocks (32x32 cells).  Data path:
+//   HBM --cp.async.bulk (1-D TMA, one 1 KB copy per 8x8 block, mbarrier complete_tx)--> staging smem
+//   staging (AoS, block layout) --repack + ghost synthesis--> padded SoA planes su/sv (38x38, +3 ring)
+//   x pass (lanes = rows, thread = 8 cells of a row)    -> partial result planes Ru/Rv in smem
+//   y pass (lanes = columns, thread = 8 cells of a column) -> + old, 128-bit coalesced stores
+//
+// Arithmetic (all FP64).  Per line the WENO fluxes are shared between neighbouring cells and only
+// the upwind family that some cell needs is evaluated; written in differences D[k] = q[k+1]-q[k]:
+//   beta1 = 13/12 D2(w-1)^2 + 1/4 (3 D[w-1] - D[w-2])^2,  beta2 = 13/12 D2(w)^2 + 1/4 (D[w-1]+D[w])^2,
+//   beta3 = 13/12 D2(w+1)^2 + 1/4 (3 D[w] - D[w+1])^2        (D2(k) = D[k]-D[k-1])
+//   flux(w) = q[w] + (sum_k a_k phi_k)/(sum_k a_k),  a_k = gamma_k (B_j B_l)^2,  B = beta + 1e-6
+// which is the reference's w_k = (gamma_k/B_k^2)/sum with numerator and denominator multiplied by
+// (B1 B2 B3)^2: one division per flux instead of four.  Same real-number result; rounding differs
+// from the reference's CPU evaluation at the 1e-16 relative level (tests bound it at 1e-12).
+#include "sim.h"
+
+namespace cup2d {
+
+constexpr int TC = 32;          // tile cells per side
+constexpr int GH = 3;           // ghost width (stencil -3..+3, main.cpp:5442)
+constexpr int TW = TC + 2 * GH; // 38
+constexpr int SP = 39;          // plane row stride (odd: conflict-free for lanes along y)
+constexpr int RP = 33;          // partial-result plane stride
+constexpr int NT_ADV = 128;
+constexpr int STG_BYTES = 24 * 1024 + 8 * 384; // 16 interior + 4 W + 4 E blocks, 4 S + 4 N 3-row strips
+constexpr int OFF_SU = STG_BYTES;
+constexpr int OFF_SV = OFF_SU + TW * SP * 8;
+constexpr int OFF_RU = OFF_SV + TW * SP * 8;
+constexpr int OFF_RV = OFF_RU + TC * RP * 8;
+constexpr int OFF_BAR = OFF_RV + TC * RP * 8;
+constexpr int OFF_SLOTS = OFF_BAR + 16;
+constexpr int ADV_SMEM = OFF_SLOTS + TILE_SLOTS * 4;
+
+struct LineState {
+  double dm2, dm1, d0, dp1; // D[w-2..w+1]
+  double Gm1, G0, Gp1;      // 13/12 D2^2 + eps at w-1, w, w+1
+  double qlast;             // q[w+2]
+  double rP1, rP2, rM1;     // ratioP(w-1), ratioP(w-2), ratioM(w-1)
+};
+
+__device__ __forceinline__ double Gfun(double D2) {
+  const double c = 13.0 / 12.0;
+  return fma(c * D2, D2, 1e-6);
+}
+__device__ __forceinline__ void line_init(LineState &s, const double *q, int es) {
+  double q0 = q[0], q1 = q[es], q2 = q[2 * es], q3 = q[3 * es], q4 = q[4 * es];
+  double D0 = q1 - q0;
+  s.dm2 = D0;        // w = 2: D[0]
+  s.dm1 = q2 - q1;   // D[1]
+  s.d0 = q3 - q2;    // D[2]
+  s.dp1 = q4 - q3;   // D[3]
+  s.Gm1 = Gfun(s.dm1 - s.dm2);
+  s.G0 = Gfun(s.d0 - s.dm1);
+  s.Gp1 = Gfun(s.dp1 - s.d0);
+  s.qlast = q4;
+  s.rP1 = s.rP2 = s.rM1 = 0.0;
+}
+__device__ __forceinline__ void line_betas(const LineState &s, double &s1, double &s2, double &s3) {
+  double e1 = fma(3.0, s.dm1, -s.dm2);
+  double e2 = s.dm1 + s.d0;
+  double e3 = fma(3.0, s.d0, -s.dp1);
+  double B1 = fma(0.25 * e1, e1, s.Gm1);
+  double B2 = fma(0.25 * e2, e2, s.G0);
+  double B3 = fma(0.25 * e3, e3, s.Gp1);
+  double q1 = B2 * B3, q2 = B1 * B3, q3 = B1 * B2;
+  s1 = q1 * q1;
+  s2 = q2 * q2;
+  s3 = q3 * q3;
+}
+// upwind-from-the-left flux ratio at face w+1/2  (weno5_plus, main.cpp:162-181)
+__device__ __forceinline__ double ratio_plus(const LineState &s, double s1, double s2, double s3) {
+  double a1 = 0.1 * s1, a2 = 0.6 * s2, a3 = 0.3 * s3;
+  double den = (a1 + a3) + a2;
+  double p1 = fma(5.0 / 6.0, s.dm1, (-1.0 / 3.0) * s.dm2);
+  double p2 = fma(1.0 / 6.0, s.dm1, (1.0 / 3.0) * s.d0);
+  double p3 = fma(2.0 / 3.0, s.d0, (-1.0 / 6.0) * s.dp1);
+  double num = fma(a1, p1, fma(a3, p3, a2 * p2));
+  return num * fast_rcp_pos(den);
+}
+// upwind-from-the-right flux ratio at face w-1/2  (weno5_minus, main.cpp:182-201)
+__device__ __forceinline__ double ratio_minus(const LineState &s, double s1, double s2, double s3) {
+  double a1 = 0.3 * s1, a2 = 0.6 * s2, a3 = 0.1 * s3;
+  double den = (a1 + a3) + a2;
+  double p1 = fma(-2.0 / 3.0, s.dm1, (1.0 / 6.0) * s.dm2);
+  double p2 = fma(-1.0 / 3.0, s.dm1, (-1.0 / 6.0) * s.d0);
+  double p3 = fma(-5.0 / 6.0, s.d0, (1.0 / 3.0) * s.dp1);
+  double num = fma(a1, p1, fma(a3, p3, a2 * p2));
+  return num * fast_rcp_pos(den);
+}
+__device__ __forceinline__ void line_advance(LineState &s, double qn, double rP, double rM) {
+  s.rP2 = s.rP1;
+  s.rP1 = rP;
+  s.rM1 = rM;
+  s.dm2 = s.dm1;
+  s.dm1 = s.d0;
+  s.d0 = s.dp1;
+  s.dp1 = qn - s.qlast;
+  s.qlast = qn;
+  s.Gm1 = s.G0;
+  s.G0 = s.Gp1;
+  s.Gp1 = Gfun(s.dp1 - s.d0);
+}
+
+// Upwind WENO5 differences of both components along one line of 8 cells (window of 14 values per
+// component, element stride ES).  qa = advecting component (sign + multiplier), qb = the other one.
+// emit(c, U, da, db, D2a, D2b) is called once per cell c = 0..7 with the undivided differences
+// (reference `derivative`, main.cpp:202-208) and the second differences (for the diffusion term).
+template <int ES, class Emit>
+__device__ __forceinline__ void weno_line(const double *__restrict__ qa,
+                                          const double *__restrict__ qb, Emit emit) {
+  LineState A, B;
+  line_init(A, qa, ES);
+  line_init(B, qb, ES);
+  double Um1 = qa[ES], U0 = qa[2 * ES], Up1 = qa[3 * ES];
+#pragma unroll 1
+  for (int w = 2; w <= 11; ++w) {
+    const bool vc = (unsigned)(w - 3) < 8u, vn = (unsigned)(w - 2) < 8u, vp = (unsigned)(w - 4) < 8u;
+    const bool posc = is_pos(U0), posn = is_pos(Up1), posp = is_pos(Um1);
+    const bool needP = (vc && posc) || (vn && posn);
+    const bool needM = (vc && !posc) || (vp && !posp);
+    double a1, a2, a3, b1, b2, b3;
+    line_betas(A, a1, a2, a3);
+    line_betas(B, b1, b2, b3);
+    double rPa = 0, rPb = 0, rMa = 0, rMb = 0;
+    if (needP) {
+      rPa = ratio_plus(A, a1, a2, a3);
+      rPb = ratio_plus(B, b1, b2, b3);
+    }
+    if (needM) {
+      rMa = ratio_minus(A, a1, a2, a3);
+      rMb = ratio_minus(B, b1, b2, b3);
+    }
+    if (vp) { // finalize cell c = w-4 (window index w-1)
+      double da, db;
+      if (posp) {
+        da = A.dm2 + (A.rP1 - A.rP2);
+        db = B.dm2 + (B.rP1 - B.rP2);
+      } else {
+        da = A.dm1 + (rMa - A.rM1);
+        db = B.dm1 + (rMb - B.rM1);
+      }
+      emit(w - 4, Um1, da, db, A.dm1 - A.dm2, B.dm1 - B.dm2);
+    }
+    if (w < 11) {
+      double qna = qa[(w + 3) * ES], qnb = qb[(w + 3) * ES];
+      Um1 = U0;
+      U0 = Up1;
+      Up1 = A.qlast;
+      line_advance(A, qna, rPa, rMa);
+      line_advance(B, qnb, rPb, rMb);
+    }
+  }
+}
+
+template <bool RAW, bool OLD_IS_IN>
+__global__ void __launch_bounds__(NT_ADV, 3)
+advect_stage_kernel(const double *__restrict__ in, const double *__restrict__ old,
+                    double *__restrict__ out, const int *__restrict__ tiles,
+                    const int *__restrict__ tile_org, int nbx, int nby, int nloc, double afac,
+                    double dfac, double ofac) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  double2 *stg = reinterpret_cast<double2 *>(smem);
+  double *su = reinterpret_cast<double *>(smem + OFF_SU);
+  double *sv = reinterpret_cast<double *>(smem + OFF_SV);
+  double *Ru = reinterpret_cast<double *>(smem + OFF_RU);
+  double *Rv = reinterpret_cast<double *>(smem + OFF_RV);
+  uint64_t *bar = reinterpret_cast<uint64_t *>(smem + OFF_BAR);
+  int *s_slots = reinterpret_cast<int *>(smem + OFF_SLOTS);
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tile = blockIdx.x;
+  if (tid < TILE_SLOTS) s_slots[tid] = tiles[tile * TILE_SLOTS + tid];
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+
+  // ---- stage 0: TMA bulk loads, one per block / strip, issued by the lanes of warp 0 ----
+  if (warp == 0) {
+    const int slot = s_slots[lane];
+    const uint32_t bytes = slot >= 0 ? (lane < 24 ? 1024u : 384u) : 0u;
+    uint32_t tot = bytes;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+    if (lane == 0) mbar_arrive_expect_tx(bar, tot);
+    __syncwarp();
+    if (slot >= 0) {
+      const unsigned char *src = reinterpret_cast<const unsigned char *>(in + (size_t)slot * 128);
+      if (lane >= 24 && lane < 28) src += 5 * 128; // S strip = rows 5..7 of the block below
+      unsigned char *dst = smem + (lane < 24 ? lane * 1024 : 24 * 1024 + (lane - 24) * 384);
+      tma_load_1d(dst, src, bytes, bar);
+    }
+  }
+  const int gx0 = tile_org[2 * tile] * CUP2D_BS, gy0 = tile_org[2 * tile + 1] * CUP2D_BS;
+  const int NX = nbx * CUP2D_BS, NY = nby * CUP2D_BS;
+  mbar_wait(bar, 0);
+
+  // ---- stage 1: repack AoS blocks -> padded SoA planes, synthesising wall ghosts ----
+  // (VectorLab::applyBCface main.cpp:3131-3154: ghost = wall-adjacent cell, normal component negated)
+  for (int idx = tid; idx < TW * TW; idx += NT_ADV) {
+    const int ty = idx / TW, tx = idx - ty * TW;
+    const int lx = tx - GH, ly = ty - GH;
+    const bool xin = (unsigned)lx < (unsigned)TC, yin = (unsigned)ly < (unsigned)TC;
+    if (!xin && !yin) continue; // corner ghosts are never read (cross-shaped stencil)
+    int gx = gx0 + lx, gy = gy0 + ly;
+    double sgu = 1.0, sgv = 1.0;
+    if (gx < 0) { gx = 0; sgu = -1.0; } else if (gx >= NX) { gx = NX - 1; sgu = -1.0; }
+    if (gy < 0) { gy = 0; sgv = -1.0; } else if (gy >= NY) { gy = NY - 1; sgv = -1.0; }
+    const int cx = gx - gx0, cy = gy - gy0; // clamped, tile-local
+    int o;
+    if ((unsigned)cx < (unsigned)TC && (unsigned)cy < (unsigned)TC)
+      o = ((cy >> 3) * 4 + (cx >> 3)) * 64 + (cy & 7) * 8 + (cx & 7);
+    else if (cx < 0)
+      o = (16 + (cy >> 3)) * 64 + (cy & 7) * 8 + (8 + cx);
+    else if (cx >= TC)
+      o = (20 + (cy >> 3)) * 64 + (cy & 7) * 8 + (cx - TC);
+    else if (cy < 0)
+      o = 24 * 64 + (cx >> 3) * 24 + (3 + cy) * 8 + (cx & 7);
+    else
+      o = 24 * 64 + 4 * 24 + (cx >> 3) * 24 + (cy - TC) * 8 + (cx & 7);
+    const double2 v = stg[o];
+    su[ty * SP + tx] = sgu * v.x;
+    sv[ty * SP + tx] = sgv * v.y;
+  }
+  __syncthreads();
+
+  // ---- stage 2: x pass. lanes = rows; thread = 8 consecutive cells of one row ----
+  {
+    const int r = lane, xs = warp;
+    const double *qa = su + (r + GH) * SP + 8 * xs; // window index 0 <-> cell x0-3
+    const double *qb = sv + (r + GH) * SP + 8 * xs;
+    double *ru = Ru + r * RP + 8 * xs, *rv = Rv + r * RP + 8 * xs;
+    weno_line<1>(qa, qb, [&](int c, double U, double du, double dv, double D2u, double D2v) {
+      const double aU = afac * U;
+      ru[c] = fma(aU, du, dfac * D2u); // afac*u*dudx + dfac*(u_E + u_W - 2u)
+      rv[c] = fma(aU, dv, dfac * D2v);
+    });
+  }
+  __syncthreads();
+
+  // ---- stage 3: y pass. lanes = columns; thread = 8 consecutive cells of one column = one block ----
+  {
+    const int x = lane, ys = warp;
+    const double *qa = sv + (8 * ys) * SP + (x + GH); // advecting component is v
+    const double *qb = su + (8 * ys) * SP + (x + GH);
+    const int b = ys * 4 + (x >> 3);
+    const int slot = s_slots[b];
+    const bool store = slot >= 0 && slot < nloc;
+    const double2 *oldp = OLD_IS_IN ? (stg + b * 64 + (x & 7))
+                                    : (reinterpret_cast<const double2 *>(old) + (size_t)(store ? slot : 0) * 64 + (x & 7));
+    double2 *outp = reinterpret_cast<double2 *>(out) + (size_t)(store ? slot : 0) * 64 + (x & 7);
+    const double *ru = Ru + (8 * ys) * RP + x, *rv = Rv + (8 * ys) * RP + x;
+    weno_line<SP>(qa, qb, [&](int c, double V, double dv, double du, double D2v, double D2u) {
+      const double aV = afac * V;
+      const double tu = ru[c * RP] + fma(aV, du, dfac * D2u);
+      const double tv = rv[c * RP] + fma(aV, dv, dfac * D2v);
+      if (store) {
+        double2 o;
+        if (RAW) {
+          o.x = tu;
+          o.y = tv;
+        } else {
+          const double2 ov = oldp[c * 8];
+          o.x = fma(ofac, tu, ov.x); // V = Vold + coef*tmpV/h^2, main.cpp:6618-6626
+          o.y = fma(ofac, tv, ov.y);
+        }
+        outp[c * 8] = o;
+      }
+    });
+  }
+}
+
+int launch_advect(cup2d_sim *s, const double *in, const double *old, double *out, double coef,
+                  double dt, bool raw) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    CUP2D_CUDA(cudaFuncSetAttribute(advect_stage_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ADV_SMEM));
+    CUP2D_CUDA(cudaFuncSetAttribute(advect_stage_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ADV_SMEM));
+    CUP2D_CUDA(cudaFuncSetAttribute(advect_stage_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ADV_SMEM));
+    attr_set = true;
+  }
+  const double afac = -dt * s->h;    // main.cpp:5447
+  const double dfac = s->nu * dt;    // main.cpp:5446
+  const double ofac = coef / (s->h * s->h);
+  dim3 grid(s->ntiles), block(NT_ADV);
+  if (raw)
+    advect_stage_kernel<true, true><<<grid, block, ADV_SMEM, s->stream>>>(in, in, out, s->d_tiles, s->d_tile_org, s->nbx, s->nby, (int)s->nloc, afac, dfac, ofac);
+  else if (old == in)
+    advect_stage_kernel<false, true><<<grid, block, ADV_SMEM, s->stream>>>(in, in, out, s->d_tiles, s->d_tile_org, s->nbx, s->nby, (int)s->nloc, afac, dfac, ofac);
+  else
+    advect_stage_kernel<false, false><<<grid, block, ADV_SMEM, s->stream>>>(in, old, out, s->d_tiles, s->d_tile_org, s->nbx, s->nby, (int)s->nloc, afac, dfac, ofac);
+  s->launches++;
+  CUP2D_CUDA(cudaGetLastError());
+  return CUP2D_OK;
+}
+
+} // namespace cup2d

@@ -1,0 +1,464 @@
+// C ABI of libcup2d_b200.so (include/cup2d_b200.h): context creation, topology tables, field
+// transfer, the C++ host driver of one time step, and the NVLink peer-memory halo exchange.
+#include "sim.h"
+#include <algorithm>
+#include <cstring>
+#include <map>
+#include <mutex>
+
+namespace cup2d {
+
+static thread_local std::string g_err;
+void set_error(const std::string &msg) { g_err = msg; }
+int dim_of(int field) { return (field == CUP2D_VEL || field == CUP2D_VOLD || field == CUP2D_TMPV) ? 2 : 1; }
+
+#define CUP2D_REQUIRE(cond, msg)                                                                  \
+  do {                                                                                            \
+    if (!(cond)) {                                                                                \
+      cup2d::set_error(msg);                                                                      \
+      return CUP2D_EINVAL;                                                                        \
+    }                                                                                             \
+  } while (0)
+
+// ---- space-filling curve: host restatement of SpaceCurve (main.cpp:342-446, init 6342-6376) ------
+static long long hilbert_xy2d(int b, int x, int y) { // AxestoTranspose, main.cpp:347-359
+  const int n = 1 << b;
+  long long d = 0;
+  for (int s = n / 2; s > 0; s /= 2) {
+    const int rx = (x & s) > 0, ry = (y & s) > 0;
+    d += (long long)s * s * ((3 * rx) ^ ry);
+    if (ry == 0) { // rot, main.cpp:374-384
+      if (rx == 1) {
+        x = n - 1 - x;
+        y = n - 1 - y;
+      }
+      std::swap(x, y);
+    }
+  }
+  return d;
+}
+static void hilbert_d2xy(int b, long long d, int *xo, int *yo) { // TransposetoAxes, main.cpp:360-373
+  const int n = 1 << b;
+  int x = 0, y = 0;
+  long long t = d;
+  for (long long s = 1; s < n; s *= 2) {
+    const long long rx = 1 & (t / 2), ry = 1 & (t ^ rx);
+    if (ry == 0) {
+      if (rx == 1) {
+        x = (int)s - 1 - x;
+        y = (int)s - 1 - y;
+      }
+      std::swap(x, y);
+    }
+    x += (int)(s * rx);
+    y += (int)(s * ry);
+    t /= 4;
+  }
+  *xo = x;
+  *yo = y;
+}
+
+} // namespace cup2d
+
+using namespace cup2d;
+
+extern "C" {
+
+const char *cup2d_last_error(void) { return g_err.c_str(); }
+int cup2d_version(void) { return 100; }
+
+int cup2d_block_order(int32_t bpdx, int32_t bpdy, int32_t level, int32_t *out) {
+  CUP2D_REQUIRE(bpdx > 0 && bpdy > 0 && level >= 0 && out, "cup2d_block_order: bad arguments");
+  // base curve over the bpdx x bpdy coarse blocks, compacted when the bounding 2^b square is not
+  // filled (main.cpp:6342-6376)
+  int base_level = 0;
+  while ((1 << base_level) < std::max(bpdx, bpdy)) base_level++;
+  std::vector<long long> zsave((size_t)bpdx * bpdy);
+  bool regular = true;
+  {
+    const int n = 1 << base_level;
+    std::vector<char> inside((size_t)n * n, 0);
+    std::vector<long long> before((size_t)n * n + 1, 0);
+    for (long long d = 0; d < (long long)n * n; d++) {
+      int x, y;
+      hilbert_d2xy(base_level, d, &x, &y);
+      inside[d] = (x < bpdx && y < bpdy);
+      before[d + 1] = before[d] + (inside[d] ? 0 : 1);
+    }
+    for (int j = 0; j < bpdy; j++)
+      for (int i = 0; i < bpdx; i++) {
+        long long idx = hilbert_xy2d(base_level, i, j);
+        if (before[idx] > 0) regular = false;
+        zsave[(size_t)j * bpdx + i] = idx - before[idx];
+      }
+  }
+  const int nbx = bpdx << level, nby = bpdy << level;
+  const long long aux = 1LL << level;
+  std::vector<std::pair<long long, int>> keyed((size_t)nbx * nby);
+  for (int j = 0; j < nby; j++)
+    for (int i = 0; i < nbx; i++) {
+      long long z;
+      if (regular)
+        z = hilbert_xy2d(level + base_level, i, j); // forward(), main.cpp:385-400
+      else {
+        const int I = (int)(i / aux), J = (int)(j / aux);
+        z = hilbert_xy2d(level, (int)(i - I * aux), (int)(j - J * aux)) + zsave[(size_t)J * bpdx + I] * aux * aux;
+      }
+      keyed[(size_t)j * nbx + i] = {z, j * nbx + i};
+    }
+  std::sort(keyed.begin(), keyed.end());
+  for (size_t k = 0; k < keyed.size(); k++) {
+    out[2 * k] = keyed[k].second % nbx;
+    out[2 * k + 1] = keyed[k].second / nbx;
+  }
+  return CUP2D_OK;
+}
+
+static int build_tables(cup2d_sim *s) {
+  const int nbx = s->nbx, nby = s->nby;
+  const int64_t nloc = s->nloc, gb = s->gbegin, ge = s->gbegin + s->nloc;
+  std::vector<int32_t> gid_of((size_t)nbx * nby, -1);
+  for (int64_t g = 0; g < s->nglobal; g++) {
+    const int i = s->ij[2 * g], j = s->ij[2 * g + 1];
+    CUP2D_REQUIRE(i >= 0 && i < nbx && j >= 0 && j < nby, "cup2d_create: block index outside the grid");
+    CUP2D_REQUIRE(gid_of[(size_t)j * nbx + i] < 0, "cup2d_create: duplicate block index");
+    gid_of[(size_t)j * nbx + i] = (int32_t)g;
+  }
+  auto gid_at = [&](int i, int j) -> int32_t {
+    if (i < 0 || i >= nbx || j < 0 || j >= nby) return -1;
+    return gid_of[(size_t)j * nbx + i];
+  };
+  // halo = non-local face neighbours of local blocks (the hot-path stencils are cross-shaped)
+  std::vector<int32_t> halo;
+  static const int di[4] = {-1, 1, 0, 0}, dj[4] = {0, 0, -1, 1};
+  for (int64_t g = gb; g < ge; g++) {
+    const int i = s->ij[2 * g], j = s->ij[2 * g + 1];
+    for (int k = 0; k < 4; k++) {
+      const int32_t n = gid_at(i + di[k], j + dj[k]);
+      if (n >= 0 && (n < gb || n >= ge)) halo.push_back(n);
+    }
+  }
+  std::sort(halo.begin(), halo.end());
+  halo.erase(std::unique(halo.begin(), halo.end()), halo.end());
+  s->halo_gid = halo;
+  s->nhalo = (int64_t)halo.size();
+  s->nslots = nloc + s->nhalo;
+  s->halo_owner.resize(halo.size());
+  for (size_t k = 0; k < halo.size(); k++) {
+    int r = 0;
+    while (!(halo[k] >= s->rank_begin[r] && halo[k] < s->rank_begin[r + 1])) r++;
+    s->halo_owner[k] = r;
+  }
+  auto slot_of = [&](int32_t g) -> int {
+    if (g < 0) return -1;
+    if (g >= gb && g < ge) return (int)(g - gb);
+    auto it = std::lower_bound(halo.begin(), halo.end(), g);
+    if (it != halo.end() && *it == g) return (int)(nloc + (it - halo.begin()));
+    return -1;
+  };
+  // per-block neighbour table W,E,S,N
+  std::vector<int> nbr((size_t)nloc * 4);
+  for (int64_t g = gb; g < ge; g++) {
+    const int i = s->ij[2 * g], j = s->ij[2 * g + 1];
+    for (int k = 0; k < 4; k++) nbr[(size_t)(g - gb) * 4 + k] = slot_of(gid_at(i + di[k], j + dj[k]));
+  }
+  // advect tiles: aligned 4x4 block groups that contain at least one local block, in SFC order of
+  // first appearance (keeps neighbouring tiles close in launch order => L2 reuse of ring blocks)
+  std::map<std::pair<int, int>, int> tile_id;
+  std::vector<std::pair<int, int>> tiles;
+  for (int64_t g = gb; g < ge; g++) {
+    std::pair<int, int> key(s->ij[2 * g] / TILE_B, s->ij[2 * g + 1] / TILE_B);
+    if (tile_id.emplace(key, (int)tiles.size()).second) tiles.push_back(key);
+  }
+  s->ntiles = (int)tiles.size();
+  std::vector<int> tslots((size_t)s->ntiles * TILE_SLOTS), torg((size_t)s->ntiles * 2);
+  for (int t = 0; t < s->ntiles; t++) {
+    const int bi0 = tiles[t].first * TILE_B, bj0 = tiles[t].second * TILE_B;
+    torg[2 * t] = bi0;
+    torg[2 * t + 1] = bj0;
+    int *ts = &tslots[(size_t)t * TILE_SLOTS];
+    for (int by = 0; by < 4; by++)
+      for (int bx = 0; bx < 4; bx++) ts[by * 4 + bx] = slot_of(gid_at(bi0 + bx, bj0 + by));
+    for (int k = 0; k < 4; k++) {
+      ts[16 + k] = slot_of(gid_at(bi0 - 1, bj0 + k)); // W
+      ts[20 + k] = slot_of(gid_at(bi0 + 4, bj0 + k)); // E
+      ts[24 + k] = slot_of(gid_at(bi0 + k, bj0 - 1)); // S
+      ts[28 + k] = slot_of(gid_at(bi0 + k, bj0 + 4)); // N
+    }
+  }
+  CUP2D_CUDA(cudaMalloc(&s->d_nbr, std::max<size_t>(nbr.size(), 4) * sizeof(int)));
+  CUP2D_CUDA(cudaMemcpy(s->d_nbr, nbr.data(), nbr.size() * sizeof(int), cudaMemcpyHostToDevice));
+  CUP2D_CUDA(cudaMalloc(&s->d_tiles, tslots.size() * sizeof(int)));
+  CUP2D_CUDA(cudaMemcpy(s->d_tiles, tslots.data(), tslots.size() * sizeof(int), cudaMemcpyHostToDevice));
+  CUP2D_CUDA(cudaMalloc(&s->d_tile_org, torg.size() * sizeof(int)));
+  CUP2D_CUDA(cudaMemcpy(s->d_tile_org, torg.data(), torg.size() * sizeof(int), cudaMemcpyHostToDevice));
+  // halo source table: (owner rank, slot on the owner)
+  if (s->nhalo > 0) {
+    std::vector<int> src((size_t)s->nhalo * 2);
+    for (int64_t k = 0; k < s->nhalo; k++) {
+      src[2 * k] = s->halo_owner[k];
+      src[2 * k + 1] = (int)(halo[k] - s->rank_begin[s->halo_owner[k]]);
+    }
+    CUP2D_CUDA(cudaMalloc(&s->d_halo_src, src.size() * sizeof(int)));
+    CUP2D_CUDA(cudaMemcpy(s->d_halo_src, src.data(), src.size() * sizeof(int), cudaMemcpyHostToDevice));
+  }
+  return CUP2D_OK;
+}
+
+int cup2d_create(const cup2d_config *cfg, cup2d_sim **out) {
+  CUP2D_REQUIRE(cfg && out, "cup2d_create: null argument");
+  CUP2D_REQUIRE(cfg->nbx > 0 && cfg->nby > 0 && cfg->nblocks_global == (int64_t)cfg->nbx * cfg->nby,
+                "cup2d_create: nblocks_global must equal nbx*nby (uniform level)");
+  CUP2D_REQUIRE(cfg->nranks >= 1 && cfg->nranks <= MAX_RANKS && cfg->rank >= 0 && cfg->rank < cfg->nranks,
+                "cup2d_create: bad rank/nranks (1..8 ranks)");
+  CUP2D_REQUIRE(cfg->block_ij && cfg->rank_begin, "cup2d_create: missing tables");
+  CUP2D_REQUIRE(cfg->h > 0, "cup2d_create: h must be positive");
+  CUP2D_REQUIRE(cfg->nblocks_global * 64 < (1LL << 31), "cup2d_create: more than 2^31 cells per field");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    set_error("cup2d_create: no CUDA device visible; this library has no CPU fallback");
+    return CUP2D_ENOGPU;
+  }
+  CUP2D_REQUIRE(cfg->device >= 0 && cfg->device < ndev, "cup2d_create: bad device ordinal");
+  CUP2D_CUDA(cudaSetDevice(cfg->device));
+  cudaDeviceProp prop;
+  CUP2D_CUDA(cudaGetDeviceProperties(&prop, cfg->device));
+  if (prop.major != 10) {
+    set_error(std::string("cup2d_create: device '") + prop.name + "' is not sm_100 (compiled for sm_100a only)");
+    return CUP2D_ENOGPU;
+  }
+  cup2d_sim *s = new cup2d_sim;
+  s->nbx = cfg->nbx;
+  s->nby = cfg->nby;
+  s->nglobal = cfg->nblocks_global;
+  s->rank = cfg->rank;
+  s->nranks = cfg->nranks;
+  s->device = cfg->device;
+  s->h = cfg->h;
+  s->nu = cfg->nu;
+  s->cfl = cfg->cfl;
+  s->num_sms = prop.multiProcessorCount;
+  s->ij.assign(cfg->block_ij, cfg->block_ij + 2 * cfg->nblocks_global);
+  s->rank_begin.assign(cfg->rank_begin, cfg->rank_begin + cfg->nranks + 1);
+  if (!(s->rank_begin[0] == 0 && s->rank_begin[cfg->nranks] == s->nglobal)) {
+    delete s;
+    set_error("cup2d_create: rank_begin must span [0, nblocks_global]");
+    return CUP2D_EINVAL;
+  }
+  s->gbegin = s->rank_begin[s->rank];
+  s->nloc = s->rank_begin[s->rank + 1] - s->gbegin;
+  if (s->nloc <= 0) {
+    delete s;
+    set_error("cup2d_create: rank owns no blocks");
+    return CUP2D_EINVAL;
+  }
+  int rc = build_tables(s);
+  if (rc) {
+    cup2d_destroy(s);
+    return rc;
+  }
+  CUP2D_CUDA(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+  for (int f = 0; f < CUP2D_NFIELDS; f++) {
+    const size_t bytes = (size_t)s->nslots * 64 * dim_of(f) * sizeof(double);
+    CUP2D_CUDA(cudaMalloc(&s->f[f], bytes));
+    CUP2D_CUDA(cudaMemset(s->f[f], 0, bytes));
+  }
+  const size_t vb = (size_t)s->nslots * 64 * sizeof(double);
+  double **kv[] = {&s->kx[0], &s->kx[1], &s->kx[2], &s->kr, &s->krhat, &s->kp, &s->knu, &s->kt, &s->kz};
+  for (auto p : kv) {
+    CUP2D_CUDA(cudaMalloc(p, vb));
+    CUP2D_CUDA(cudaMemset(*p, 0, vb));
+  }
+  CUP2D_CUDA(cudaMalloc(&s->d_state, sizeof(KrylovState)));
+  CUP2D_CUDA(cudaMemset(s->d_state, 0, sizeof(KrylovState)));
+  CUP2D_CUDA(cudaMallocHost(&s->h_state, sizeof(KrylovState)));
+  memset(s->h_state, 0, sizeof(KrylovState));
+  CUP2D_CUDA(cudaMalloc(&s->d_partials, (size_t)RED_MAX_CTAS * RED_SLOTS * sizeof(double)));
+  CUP2D_CUDA(cudaMalloc(&s->d_counter, sizeof(unsigned int)));
+  CUP2D_CUDA(cudaMemset(s->d_counter, 0, sizeof(unsigned int)));
+  CUP2D_CUDA(cudaMalloc(&s->d_scal, 16 * sizeof(double)));
+  CUP2D_CUDA(cudaMallocHost(&s->h_scal, 16 * sizeof(double)));
+  CUP2D_CUDA(cudaMalloc(&s->d_mailbox, 4096));
+  CUP2D_CUDA(cudaMemset(s->d_mailbox, 0, 4096));
+  s->comm.rank = s->rank;
+  s->comm.nranks = 1; // raised to nranks by cup2d_peer_attach
+  s->comm.mb[s->rank] = s->d_mailbox;
+  CUP2D_CUDA(cudaDeviceSynchronize());
+  *out = s;
+  return CUP2D_OK;
+}
+
+void cup2d_destroy(cup2d_sim *s) {
+  if (!s) return;
+  cudaSetDevice(s->device);
+  if (s->stream) cudaStreamSynchronize(s->stream);
+  if (s->peers_attached) {
+    for (int r = 0; r < s->nranks; r++) {
+      if (r == s->rank) continue;
+      for (auto p : s->peer_base[r])
+        if (p) cudaIpcCloseMemHandle(p);
+      if (s->peer_mailbox[r]) cudaIpcCloseMemHandle(s->peer_mailbox[r]);
+    }
+  }
+  for (auto p : s->f) cudaFree(p);
+  for (auto p : s->kx) cudaFree(p);
+  cudaFree(s->kr); cudaFree(s->krhat); cudaFree(s->kp); cudaFree(s->knu); cudaFree(s->kt); cudaFree(s->kz);
+  cudaFree(s->d_nbr); cudaFree(s->d_tiles); cudaFree(s->d_tile_org); cudaFree(s->d_halo_src);
+  cudaFree(s->d_state); cudaFree(s->d_partials); cudaFree(s->d_counter); cudaFree(s->d_scal);
+  cudaFree(s->d_mailbox); cudaFree(s->d_peer_ptrs);
+  if (s->h_state) cudaFreeHost(s->h_state);
+  if (s->h_scal) cudaFreeHost(s->h_scal);
+  if (s->stream) cudaStreamDestroy(s->stream);
+  delete s;
+}
+
+int64_t cup2d_nblocks_local(const cup2d_sim *s) { return s ? s->nloc : 0; }
+int64_t cup2d_nblocks_halo(const cup2d_sim *s) { return s ? s->nhalo : 0; }
+int64_t cup2d_launch_count(const cup2d_sim *s) { return s ? s->launches : 0; }
+void *cup2d_stream(cup2d_sim *s) { return s ? (void *)s->stream : nullptr; }
+
+#define CHECK_SIM(s) CUP2D_REQUIRE((s) != nullptr, "null cup2d_sim")
+#define CHECK_FIELD(f) CUP2D_REQUIRE((f) >= 0 && (f) < CUP2D_NFIELDS, "bad field id")
+
+int cup2d_field_upload(cup2d_sim *s, int field, const double *host) {
+  CHECK_SIM(s); CHECK_FIELD(field);
+  CUP2D_REQUIRE(host, "null host pointer");
+  CUP2D_CUDA(cudaSetDevice(s->device));
+  CUP2D_CUDA(cudaMemcpyAsync(s->f[field], host, (size_t)s->nloc * 64 * dim_of(field) * sizeof(double),
+                             cudaMemcpyHostToDevice, s->stream));
+  return CUP2D_OK;
+}
+int cup2d_field_download(cup2d_sim *s, int field, double *host) {
+  CHECK_SIM(s); CHECK_FIELD(field);
+  CUP2D_REQUIRE(host, "null host pointer");
+  CUP2D_CUDA(cudaSetDevice(s->device));
+  CUP2D_CUDA(cudaMemcpyAsync(host, s->f[field], (size_t)s->nloc * 64 * dim_of(field) * sizeof(double),
+                             cudaMemcpyDeviceToHost, s->stream));
+  CUP2D_CUDA(cudaStreamSynchronize(s->stream));
+  return CUP2D_OK;
+}
+int cup2d_field_fill(cup2d_sim *s, int field, double value) {
+  CHECK_SIM(s); CHECK_FIELD(field);
+  CUP2D_REQUIRE(value == 0.0, "cup2d_field_fill: only 0 is supported");
+  CUP2D_CUDA(cudaMemsetAsync(s->f[field], 0, (size_t)s->nslots * 64 * dim_of(field) * sizeof(double), s->stream));
+  return CUP2D_OK;
+}
+void *cup2d_field_device_ptr(cup2d_sim *s, int field) {
+  if (!s || field < 0 || field >= CUP2D_NFIELDS) return nullptr;
+  return s->f[field];
+}
+int cup2d_sync(cup2d_sim *s) {
+  CHECK_SIM(s);
+  CUP2D_CUDA(cudaStreamSynchronize(s->stream));
+  return CUP2D_OK;
+}
+
+static int need_peers(cup2d_sim *s) {
+  if (s->nranks > 1 && !s->peers_attached) {
+    set_error("multi-rank operator called before cup2d_peer_attach");
+    return CUP2D_ESTATE;
+  }
+  return CUP2D_OK;
+}
+
+int cup2d_compute_dt(cup2d_sim *s, double *umax_out, double *dt_out) {
+  CHECK_SIM(s);
+  CUP2D_CUDA(cudaSetDevice(s->device));
+  double umax = 0;
+  int rc = launch_umax(s, &umax);
+  if (rc) return rc;
+  // umax is already global: the reduction's finalizer all-reduces over the peers (common.cuh)
+  const double h = s->h;
+  const double dt_diff = 0.25 * h * h / (s->nu + 0.25 * h * umax); // main.cpp:6593
+  const double dt_adv = h / (umax + 1e-8);                          // main.cpp:6594
+  if (umax_out) *umax_out = umax;
+  if (dt_out) *dt_out = std::min(dt_diff, s->cfl * dt_adv);
+  return CUP2D_OK;
+}
+
+int cup2d_advect_diffuse_stage(cup2d_sim *s, int in_f, int old_f, int out_f, double coef, double dt) {
+  CHECK_SIM(s);
+  CUP2D_REQUIRE(in_f >= 0 && in_f < 3 && old_f >= 0 && old_f < 3 && out_f >= 0 && out_f < 3, "advect: vector field ids only");
+  CUP2D_REQUIRE(out_f != in_f, "advect: out must differ from in (halo cells of in are read by other tiles)");
+  CUP2D_CUDA(cudaSetDevice(s->device));
+  int rc = need_peers(s);
+  if (rc) return rc;
+  if (s->nranks > 1 && (rc = halo_exchange_ptr(s, s->f[in_f], 2, in_f))) return rc;
+  return launch_advect(s, s->f[in_f], s->f[old_f], s->f[out_f], coef, dt, false);
+}
+int cup2d_advect_diffuse_rhs(cup2d_sim *s, int in_f, int out_f, double dt) {
+  CHECK_SIM(s);
+  CUP2D_REQUIRE(in_f >= 0 && in_f < 3 && out_f >= 0 && out_f < 3 && in_f != out_f, "advect_rhs: bad field ids");
+  CUP2D_CUDA(cudaSetDevice(s->device));
+  int rc = need_peers(s);
+  if (rc) return rc;
+  if (s->nranks > 1 && (rc = halo_exchange_ptr(s, s->f[in_f], 2, in_f))) return rc;
+  return launch_advect(s, s->f[in_f], s->f[in_f], s->f[out_f], 1.0, dt, true);
+}
+int cup2d_advect_diffuse_rk2(cup2d_sim *s, double dt) {
+  CHECK_SIM(s);
+  CUP2D_CUDA(cudaSetDevice(s->device));
+  int rc = need_peers(s);
+  if (rc) return rc;
+  // vold <- vel is a pointer swap (main.cpp:6607-6610 copies); stage 1 reads vold, writes tmpV-as-V1;
+  // stage 2 reads V1, adds to vold, writes vel.  No copy kernel: 80 B/cell/step -> 64 B/cell/step.
+  swap_fields(s, CUP2D_VEL, CUP2D_VOLD);
+  if (s->nranks > 1) {
+    if ((rc = halo_exchange_ptr(s, s->f[CUP2D_VOLD], 2, CUP2D_VOLD))) return rc;
+  }
+  if ((rc = launch_advect(s, s->f[CUP2D_VOLD], s->f[CUP2D_VOLD], s->f[CUP2D_TMPV], 0.5, dt, false))) return rc;
+  if (s->nranks > 1) {
+    if ((rc = halo_exchange_ptr(s, s->f[CUP2D_TMPV], 2, CUP2D_TMPV))) return rc;
+  }
+  return launch_advect(s, s->f[CUP2D_TMPV], s->f[CUP2D_VOLD], s->f[CUP2D_VEL], 1.0, dt, false);
+}
+int cup2d_pressure_rhs(cup2d_sim *s, double dt) {
+  CHECK_SIM(s);
+  CUP2D_REQUIRE(dt > 0, "pressure_rhs: dt must be positive");
+  CUP2D_CUDA(cudaSetDevice(s->device));
+  int rc = need_peers(s);
+  if (rc) return rc;
+  return launch_pressure_rhs(s, dt);
+}
+int cup2d_poisson_solve(cup2d_sim *s, double tol_abs, double tol_rel, int max_restarts, int max_iter,
+                        int *iters, double *err) {
+  CHECK_SIM(s);
+  CUP2D_CUDA(cudaSetDevice(s->device));
+  int rc = need_peers(s);
+  if (rc) return rc;
+  rc = poisson_solve(s, tol_abs, tol_rel, max_restarts, max_iter, iters, err);
+  if (rc) return rc;
+  CUP2D_CUDA(cudaMemcpyAsync(s->f[CUP2D_PRES], s->kx[s->h_state->opt], (size_t)s->nloc * 64 * sizeof(double),
+                             cudaMemcpyDeviceToDevice, s->stream));
+  return CUP2D_OK;
+}
+int cup2d_pressure_correct(cup2d_sim *s, double dt) {
+  CHECK_SIM(s);
+  CUP2D_CUDA(cudaSetDevice(s->device));
+  int rc = need_peers(s);
+  if (rc) return rc;
+  return launch_pressure_correct(s, dt);
+}
+
+int cup2d_step(cup2d_sim *s, double dt_in, int keep_udef, double tol_abs, double tol_rel,
+               int max_restarts, int max_iter, double *dt_out, int *iters_out, double *err_out) {
+  CHECK_SIM(s);
+  CUP2D_CUDA(cudaSetDevice(s->device));
+  int rc = need_peers(s);
+  if (rc) return rc;
+  double dt = dt_in;
+  if (!(dt > 0)) {
+    double umax;
+    if ((rc = cup2d_compute_dt(s, &umax, &dt))) return rc;
+  }
+  if ((rc = cup2d_advect_diffuse_rk2(s, dt))) return rc;
+  if (!keep_udef) // no bodies: sum of u_def is zero (main.cpp:6980-6983)
+    CUP2D_CUDA(cudaMemsetAsync(s->f[CUP2D_TMPV], 0, (size_t)s->nslots * 128 * sizeof(double), s->stream));
+  if ((rc = launch_pressure_rhs(s, dt))) return rc;
+  if ((rc = poisson_solve(s, tol_abs, tol_rel, max_restarts, max_iter, iters_out, err_out))) return rc;
+  if ((rc = launch_pressure_correct(s, dt))) return rc;
+  if (dt_out) *dt_out = dt;
+  return CUP2D_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,229 @@
+// Internal helpers shared by the kernels of libcup2d_b200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+
+#define CUP2D_BS 8
+#define CUP2D_BS2 64
+
+namespace cup2d {
+
+// ---- error plumbing ------------------------------------------------------------------------
+void set_error(const std::string &msg);
+#define CUP2D_CUDA(call)                                                                         \
+  do {                                                                                           \
+    cudaError_t _e = (call);                                                                     \
+    if (_e != cudaSuccess) {                                                                     \
+      cup2d::set_error(std::string(#call) + ": " + cudaGetErrorString(_e) + " (" + __FILE__ +    \
+                       ":" + std::to_string(__LINE__) + ")");                                    \
+      return CUP2D_ECUDA;                                                                        \
+    }                                                                                            \
+  } while (0)
+
+// ---- mbarrier + 1-D TMA bulk copy (cp.async.bulk: SASS UBLKCP) -----------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_mbar_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  asm volatile("{\n"
+               ".reg .pred p;\n"
+               "WAIT_%=:\n"
+               "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+               "@p bra DONE_%=;\n"
+               "bra WAIT_%=;\n"
+               "DONE_%=:\n"
+               "}" ::"r"(smem_u32(bar)),
+               "r"(parity)
+               : "memory");
+}
+// global -> shared bulk copy; bytes % 16 == 0, both addresses 16-byte aligned
+__device__ __forceinline__ void tma_load_1d(void *smem_dst, const void *gmem_src, uint32_t bytes,
+                                            uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+                   "r"(smem_u32(smem_dst)),
+               "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+// ---- numerics ------------------------------------------------------------------------------
+// U > 0 for finite doubles without touching the FP64 pipe (NaN is treated as > 0)
+__device__ __forceinline__ bool is_pos(double x) {
+  int hi = __double2hiint(x), lo = __double2loint(x);
+  return hi >= 0 && (hi | lo) != 0;
+}
+// reciprocal of a positive normal double: MUFU.RCP64H seed + 2 Newton steps (~1 ulp)
+__device__ __forceinline__ double fast_rcp_pos(double x) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  double e = fma(-x, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-x, r, 1.0);
+  r = fma(r, e, r);
+  return r;
+}
+
+// ---- cross-GPU plumbing over NVLink peer memory ---------------------------------------------------
+// One process per GPU; every rank maps every peer's mailbox (CUDA IPC).  Mailbox layout (u64 words):
+//   [0..8)   halo READY epochs, one per source rank      [8..16) halo DONE epochs
+//   [16 + (src*2 + parity)*8 ...]  reduction slot: flag(epoch), v0..v5
+//   [496]    this rank's reduction epoch counter (local use only)
+constexpr int MB_READY = 0, MB_DONE = 8, MB_RED = 16, MB_RED_STRIDE = 8, MB_EPOCH = 496, MB_WORDS = 512;
+constexpr int COMM_MAX_RANKS = 8;
+struct Comm {
+  int rank, nranks;
+  unsigned long long *mb[COMM_MAX_RANKS]; // mb[r] = rank r's mailbox (mb[rank] is local memory)
+};
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_relaxed_sys(unsigned long long *p, unsigned long long v) {
+  asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_relaxed_sys(const unsigned long long *p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+// All-reduce of NS sums + 1 max across ranks, executed by ONE thread per rank (the finalizer of a
+// grid reduction).  Every rank writes its values into every peer's mailbox over NVLink, then combines
+// all contributions in rank order, so the result is bitwise identical on all ranks.
+template <int NS>
+__device__ __forceinline__ void peer_allreduce(const Comm &c, double (&tot)[NS], double &mx) {
+  static_assert(NS + 1 <= MB_RED_STRIDE - 1, "reduction slot too small");
+  if (c.nranks <= 1) return;
+  unsigned long long *mine = c.mb[c.rank];
+  const unsigned long long ep = ld_relaxed_sys(mine + MB_EPOCH) + 1;
+  st_relaxed_sys(mine + MB_EPOCH, ep);
+  const int slot = MB_RED + (c.rank * 2 + (int)(ep & 1)) * MB_RED_STRIDE;
+  for (int r = 0; r < c.nranks; r++) {
+    unsigned long long *dst = c.mb[r] + slot;
+#pragma unroll
+    for (int k = 0; k < NS; k++) st_relaxed_sys(dst + 1 + k, (unsigned long long)__double_as_longlong(tot[k]));
+    st_relaxed_sys(dst + 1 + NS, (unsigned long long)__double_as_longlong(mx));
+    __threadfence_system();
+    st_release_sys(dst, ep);
+  }
+  double acc[NS];
+#pragma unroll
+  for (int k = 0; k < NS; k++) acc[k] = 0;
+  double am = 0;
+  for (int r = 0; r < c.nranks; r++) {
+    const unsigned long long *src = mine + MB_RED + (r * 2 + (int)(ep & 1)) * MB_RED_STRIDE;
+    while (ld_acquire_sys(src) < ep) { }
+#pragma unroll
+    for (int k = 0; k < NS; k++) acc[k] += __longlong_as_double((long long)ld_relaxed_sys(src + 1 + k));
+    am = fmax(am, __longlong_as_double((long long)ld_relaxed_sys(src + 1 + NS)));
+  }
+#pragma unroll
+  for (int k = 0; k < NS; k++) tot[k] = acc[k];
+  mx = am;
+}
+
+// ---- block reductions -----------------------------------------------------------------------
+template <int N> __device__ __forceinline__ void warp_sum(double (&v)[N]) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+    for (int k = 0; k < N; k++) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// Deterministic grid reduction: every CTA writes its partial (NS sums + 1 max) to
+// partials[blockIdx.x]; the CTA that finishes last re-reduces all partials in a fixed order and
+// calls fin(sums, max).  Result is independent of CTA scheduling.  `counter` must be 0 on entry and
+// is reset to 0 by the last CTA.  With more than one rank the finalizer first all-reduces the local
+// totals over NVLink peer memory (peer_allreduce), so fin sees global values on every rank.
+template <int NS, int NT, class Fin>
+__device__ __forceinline__ void grid_reduce(double (&sums)[NS], double mx, double *partials,
+                                            unsigned int *counter, const Comm &comm, Fin fin) {
+  __shared__ double s_red[(NS + 1) * (NT / 32)];
+  __shared__ bool s_last;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  warp_sum<NS>(sums);
+  mx = warp_max(mx);
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < NS; k++) s_red[k * (NT / 32) + warp] = sums[k];
+    s_red[NS * (NT / 32) + warp] = mx;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double *out = partials + (size_t)blockIdx.x * (NS + 1);
+#pragma unroll
+    for (int k = 0; k < NS; k++) {
+      double a = 0;
+      for (int w = 0; w < NT / 32; w++) a += s_red[k * (NT / 32) + w];
+      out[k] = a;
+    }
+    double m = 0;
+    for (int w = 0; w < NT / 32; w++) m = fmax(m, s_red[NS * (NT / 32) + w]);
+    out[NS] = m;
+    __threadfence();
+    unsigned int done = atomicAdd(counter, 1u);
+    s_last = (done == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  // last CTA: fixed-order re-reduction over all CTA partials
+  double acc[NS];
+#pragma unroll
+  for (int k = 0; k < NS; k++) acc[k] = 0;
+  double am = 0;
+  for (unsigned int b = threadIdx.x; b < gridDim.x; b += NT) {
+    const volatile double *in = partials + (size_t)b * (NS + 1);
+#pragma unroll
+    for (int k = 0; k < NS; k++) acc[k] += in[k];
+    am = fmax(am, in[NS]);
+  }
+  __syncthreads(); // s_red reuse
+  warp_sum<NS>(acc);
+  am = warp_max(am);
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < NS; k++) s_red[k * (NT / 32) + warp] = acc[k];
+    s_red[NS * (NT / 32) + warp] = am;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double tot[NS];
+#pragma unroll
+    for (int k = 0; k < NS; k++) {
+      double a = 0;
+      for (int w = 0; w < NT / 32; w++) a += s_red[k * (NT / 32) + w];
+      tot[k] = a;
+    }
+    double m = 0;
+    for (int w = 0; w < NT / 32; w++) m = fmax(m, s_red[NS * (NT / 32) + w]);
+    *counter = 0;
+    peer_allreduce<NS>(comm, tot, m);
+    fin(tot, m);
+    __threadfence();
+  }
+}
+
+} // namespace cup2d

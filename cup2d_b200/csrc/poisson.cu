@@ -1,0 +1,424 @@
+// Pressure-Poisson solve: block-Jacobi preconditioned BiCGSTAB, matrix-free, device-resident control.
+//
+// Restates BiCGSTABSolver::main (cuda.cu:403-548) — same recurrence, same operation order, same
+// 1e-21 guards (cuda.cu:315-326), same breakdown/restart rule (cuda.cu:452-477), same L-inf stopping
+// rule with best-iterate tracking (cuda.cu:525-541) — but
+//   * A is applied matrix-free from the block neighbour table (the COO of main.cpp:7074-7107 on a
+//     uniform level is the undivided 5-point Laplacian with Neumann walls), instead of cusparseSpMV;
+//   * the preconditioner P_inv = -(A_loc)^-1 (main.cpp:6451-6488; cublasDgemm at cuda.cu:484,503) is
+//     applied by fast diagonalisation: A_loc = T (x) I + I (x) T, T = tridiag(-1,2,-1) = Q L Q^T with
+//     Q[j][k] = sqrt(2/9) sin((j+1)(k+1)pi/9), so z = -(Q(x)Q) diag(1/(l_i+l_j)) (Q(x)Q)^T v:
+//     four 8x8 transforms per block (32 FMA/cell) instead of a 64x64 product (64 FMA/cell);
+//   * the ~25 launches + 4 host syncs per iteration of the reference become 5 fused kernels and no
+//     host sync: dots are reduced deterministically on the device, the scalar recurrences
+//     (set_alpha/beta/omega/rho, cuda.cu:303-330) run in the last CTA of the producing kernel, the
+//     x_opt snapshot (cuda.cu:537) is a rotation among three x buffers, and convergence is a device
+//     flag that turns the remaining launches into no-ops.
+// Traffic per iteration: 25 doubles/cell = 200 B/cell.
+#include "sim.h"
+#include <cmath>
+
+namespace cup2d {
+
+constexpr int NT = 256;
+constexpr double EPS21 = 1e-21; // cuda.cu:409
+
+__constant__ double cQ[64];   // Q[i*8+k]
+__constant__ double cIL[64];  // -1/(lambda_m + lambda_k)
+
+static bool g_consts_ready = false;
+static int init_consts() {
+  if (g_consts_ready) return CUP2D_OK;
+  double Q[64], IL[64], lam[8];
+  const double pi = 3.14159265358979323846;
+  for (int k = 0; k < 8; k++) lam[k] = 2.0 - 2.0 * std::cos((k + 1) * pi / 9.0);
+  for (int i = 0; i < 8; i++)
+    for (int k = 0; k < 8; k++) Q[i * 8 + k] = std::sqrt(2.0 / 9.0) * std::sin((i + 1) * (k + 1) * pi / 9.0);
+  for (int m = 0; m < 8; m++)
+    for (int k = 0; k < 8; k++) IL[m * 8 + k] = -1.0 / (lam[m] + lam[k]);
+  CUP2D_CUDA(cudaMemcpyToSymbol(cQ, Q, sizeof Q));
+  CUP2D_CUDA(cudaMemcpyToSymbol(cIL, IL, sizeof IL));
+  g_consts_ready = true;
+  return CUP2D_OK;
+}
+
+__device__ __forceinline__ void load_row(const double *__restrict__ f, int slot, int y, double (&c)[8]) {
+  const double4 *p = reinterpret_cast<const double4 *>(f + (size_t)slot * 64 + y * 8);
+  double4 a = p[0], b = p[1];
+  c[0] = a.x; c[1] = a.y; c[2] = a.z; c[3] = a.w;
+  c[4] = b.x; c[5] = b.y; c[6] = b.z; c[7] = b.w;
+}
+__device__ __forceinline__ void store_row(double *__restrict__ f, int slot, int y, const double (&c)[8]) {
+  double4 *p = reinterpret_cast<double4 *>(f + (size_t)slot * 64 + y * 8);
+  p[0] = make_double4(c[0], c[1], c[2], c[3]);
+  p[1] = make_double4(c[4], c[5], c[6], c[7]);
+}
+
+// y = A z on one block row: neighbours S,W,C,E,N (main.cpp:7075-7087); at a wall the missing
+// neighbour is omitted and the diagonal is -(number of neighbours) (main.cpp:7100-7107), i.e. the
+// ghost equals the cell itself.
+__device__ __forceinline__ void lap_row(const double *__restrict__ z, int slot, int y, const int4 nb,
+                                        double (&out)[8]) {
+  double c[8], up[8], dn[8];
+  load_row(z, slot, y, c);
+  const double gW = nb.x >= 0 ? z[(size_t)nb.x * 64 + y * 8 + 7] : c[0];
+  const double gE = nb.y >= 0 ? z[(size_t)nb.y * 64 + y * 8 + 0] : c[7];
+  if (y < 7) load_row(z, slot, y + 1, up);
+  else if (nb.w >= 0) load_row(z, nb.w, 0, up);
+  else {
+#pragma unroll
+    for (int i = 0; i < 8; i++) up[i] = c[i];
+  }
+  if (y > 0) load_row(z, slot, y - 1, dn);
+  else if (nb.z >= 0) load_row(z, nb.z, 7, dn);
+  else {
+#pragma unroll
+    for (int i = 0; i < 8; i++) dn[i] = c[i];
+  }
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    const double e = i < 7 ? c[i + 1] : gE;
+    const double w = i > 0 ? c[i - 1] : gW;
+    out[i] = (((dn[i] + w) + e) + up[i]) - 4.0 * c[i];
+  }
+}
+
+// z_blk = P_inv v_blk for the block whose row `y` this lane holds (8 lanes = one block).
+// sw: per-warp scratch of 4*72 doubles.  All 32 lanes must call.
+__device__ __forceinline__ void precond_row(double (&v)[8], double *sw, int lane) {
+  const int y = lane & 7, bl = lane >> 3;
+  double *sb = sw + bl * 72;
+  double a[8];
+#pragma unroll
+  for (int k = 0; k < 8; k++) {
+    double s = cQ[k] * v[0];
+#pragma unroll
+    for (int i = 1; i < 8; i++) s = fma(cQ[i * 8 + k], v[i], s);
+    a[k] = s;
+  }
+  __syncwarp();
+#pragma unroll
+  for (int k = 0; k < 8; k++) sb[y * 9 + k] = a[k];
+  __syncwarp();
+  double b[8];
+#pragma unroll
+  for (int yy = 0; yy < 8; yy++) b[yy] = sb[yy * 9 + y]; // lane now owns x-mode kx = y
+#pragma unroll
+  for (int m = 0; m < 8; m++) {
+    double s = cQ[m] * b[0];
+#pragma unroll
+    for (int yy = 1; yy < 8; yy++) s = fma(cQ[yy * 8 + m], b[yy], s);
+    a[m] = s * cIL[m * 8 + y];
+  }
+#pragma unroll
+  for (int yy = 0; yy < 8; yy++) {
+    double s = cQ[yy * 8] * a[0];
+#pragma unroll
+    for (int m = 1; m < 8; m++) s = fma(cQ[yy * 8 + m], a[m], s);
+    b[yy] = s;
+  }
+  __syncwarp();
+#pragma unroll
+  for (int yy = 0; yy < 8; yy++) sb[yy * 9 + y] = b[yy];
+  __syncwarp();
+#pragma unroll
+  for (int k = 0; k < 8; k++) a[k] = sb[y * 9 + k];
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    double s = cQ[i * 8] * a[0];
+#pragma unroll
+    for (int k = 1; k < 8; k++) s = fma(cQ[i * 8 + k], a[k], s);
+    v[i] = s;
+  }
+}
+
+__device__ __forceinline__ int next_buf(int cur, int opt) { return cur != opt ? 3 - cur - opt : (cur + 1) % 3; }
+
+// decisions taken at the top of the reference loop (cuda.cu:440-477), given rho' = rhat.r and |r|^2
+__device__ void prepare_iteration(KrylovState *st, double rho_new, double nr2) {
+  st->rho_curr = rho_new;
+  st->nr2 = nr2;
+  const bool breakdown = rho_new * rho_new < 1e-16 * nr2 * st->nrh2;                        // 452-454
+  st->beta = (st->rho_curr / (st->rho_prev + EPS21)) * (st->alpha / (st->omega + EPS21));   // set_beta
+  st->restart_now = 0;
+  if (breakdown && st->max_restarts > 0) {                                                  // 457-477
+    st->restarts++;
+    if (st->restarts >= st->max_restarts) {
+      st->done = 1;
+      return;
+    }
+    st->restart_now = 1;   // K1: rhat = r, p = r (p = nu = 0 then p = beta*0 + r)
+    st->rho_curr = nr2;    // nrm2(rhat)^2 with rhat = r
+    st->nrh2 = nr2;
+    st->rho_prev = 1.0;    // breakdown_update, cuda.cu:308-314
+    st->alpha = 1.0;
+    st->omega = 1.0;
+    st->beta = (st->rho_curr / (st->rho_prev + EPS21)) * (st->alpha / (st->omega + EPS21));
+  }
+}
+
+// ---- K0: r = b - A x0 ; rhat = r ; p = nu = 0 ; x[0] = x0 ; err0, |r|^2, sum(x0) -----------------
+__global__ void __launch_bounds__(NT)
+k_init(const double *__restrict__ b, const double *__restrict__ x0, double *__restrict__ x,
+       double *__restrict__ r, double *__restrict__ rhat, double *__restrict__ p,
+       double *__restrict__ nu, const int4 *__restrict__ nbr, int nrows, KrylovState *st,
+       double *partials, unsigned int *counter, Comm comm) {
+  double sums[2] = {0, 0}; // |r|^2, sum x0
+  double mx = 0;
+  for (int row = blockIdx.x * NT + threadIdx.x; row < nrows; row += gridDim.x * NT) {
+    const int slot = row >> 3, y = row & 7;
+    const int4 nb = nbr[slot];
+    double ax[8], bb[8], xx[8], zero[8];
+    lap_row(x0, slot, y, nb, ax);
+    load_row(b, slot, y, bb);
+    load_row(x0, slot, y, xx);
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      bb[i] -= ax[i];
+      sums[0] = fma(bb[i], bb[i], sums[0]);
+      sums[1] += xx[i];
+      mx = fmax(mx, fabs(bb[i]));
+      zero[i] = 0.0;
+    }
+    store_row(r, slot, y, bb);
+    store_row(rhat, slot, y, bb);
+    store_row(x, slot, y, xx);
+    store_row(p, slot, y, zero);
+    store_row(nu, slot, y, zero);
+  }
+  grid_reduce<2, NT>(sums, mx, partials, counter, comm, [=](const double *t, double m) {
+    st->err = st->err_init = st->err_opt = m;   // cuda.cu:428-430
+    st->xsum = t[1];
+    st->nrh2 = t[0];
+    st->iter = 0;
+    if (st->max_iter <= 0) st->done = 1;
+    prepare_iteration(st, t[0], t[0]);
+  });
+}
+
+// ---- K1: p = r + beta (p - omega nu) ; z = M p    (cuda.cu:478-486) -------------------------------
+__global__ void __launch_bounds__(NT)
+k_pupdate(const double *__restrict__ r, double *__restrict__ rhat, double *__restrict__ p,
+          const double *__restrict__ nu, double *__restrict__ z, int nrows,
+          const KrylovState *__restrict__ st) {
+  __shared__ double s_tr[(NT / 32) * 288];
+  if (st->done) return;
+  const double beta = st->beta, nomega = -st->omega;
+  const bool restart = st->restart_now != 0;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double *sw = s_tr + warp * 288;
+  for (int base = blockIdx.x * NT + warp * 32; base < nrows; base += gridDim.x * NT) {
+    const int row = base + lane;
+    const bool act = row < nrows;
+    const int slot = row >> 3, y = row & 7;
+    double pp[8];
+    if (act) {
+      double rr[8];
+      load_row(r, slot, y, rr);
+      if (restart) {
+        store_row(rhat, slot, y, rr);
+#pragma unroll
+        for (int i = 0; i < 8; i++) pp[i] = rr[i];
+      } else {
+        double nn[8];
+        load_row(p, slot, y, pp);
+        load_row(nu, slot, y, nn);
+#pragma unroll
+        for (int i = 0; i < 8; i++) pp[i] = fma(beta, fma(nomega, nn[i], pp[i]), rr[i]);
+      }
+      store_row(p, slot, y, pp);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; i++) pp[i] = 0.0;
+    }
+    precond_row(pp, sw, lane);
+    if (act) store_row(z, slot, y, pp);
+  }
+}
+
+// ---- K2 / K4: y = A z with one or two dots against `d` and y -------------------------------------
+//   MODE 0 (K2): nu = A z ; rhat.nu             -> alpha = rho/(rhat.nu + eps)   (cuda.cu:487-496)
+//   MODE 1 (K4): t  = A z ; t.r, t.t            -> omega = t.r/(t.t + eps)       (cuda.cu:506-518)
+template <int MODE>
+__global__ void __launch_bounds__(NT)
+k_spmv(const double *__restrict__ z, const double *__restrict__ d, double *__restrict__ yout,
+       const int4 *__restrict__ nbr, int nrows, KrylovState *st, double *partials,
+       unsigned int *counter, Comm comm) {
+  if (st->done) return;
+  double sums[2] = {0, 0};
+  for (int row = blockIdx.x * NT + threadIdx.x; row < nrows; row += gridDim.x * NT) {
+    const int slot = row >> 3, y = row & 7;
+    const int4 nb = nbr[slot];
+    double az[8], dd[8];
+    lap_row(z, slot, y, nb, az);
+    load_row(d, slot, y, dd);
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      sums[0] = fma(az[i], dd[i], sums[0]);
+      if (MODE == 1) sums[1] = fma(az[i], az[i], sums[1]);
+    }
+    store_row(yout, slot, y, az);
+  }
+  grid_reduce<2, NT>(sums, 0.0, partials, counter, comm, [=](const double *t, double) {
+    if (MODE == 0) {
+      st->rhat_nu = t[0];
+      st->alpha = st->rho_curr / (t[0] + EPS21); // set_alpha
+      st->restart_now = 0;
+    } else {
+      st->tr = t[0];
+      st->tt = t[1];
+      st->omega = t[0] / (t[1] + EPS21);         // set_omega
+    }
+  });
+}
+
+// ---- K3: x' = x + alpha z ; r -= alpha nu ; z = M r     (cuda.cu:498-505) -------------------------
+__global__ void __launch_bounds__(NT)
+k_xr_update(double *x0, double *x1, double *x2, const double *zin,
+            double *__restrict__ r, const double *__restrict__ nu, double *zout,
+            int nrows, const KrylovState *__restrict__ st) {
+  __shared__ double s_tr[(NT / 32) * 288];
+  if (st->done) return;
+  const double alpha = st->alpha;
+  const int cur = st->cur, nxt = next_buf(st->cur, st->opt);
+  const double *xc = cur == 0 ? x0 : (cur == 1 ? x1 : x2);
+  double *xn = nxt == 0 ? x0 : (nxt == 1 ? x1 : x2);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double *sw = s_tr + warp * 288;
+  for (int base = blockIdx.x * NT + warp * 32; base < nrows; base += gridDim.x * NT) {
+    const int row = base + lane;
+    const bool act = row < nrows;
+    const int slot = row >> 3, y = row & 7;
+    double rr[8];
+    if (act) {
+      double xx[8], zz[8], nn[8];
+      load_row(xc, slot, y, xx);
+      load_row(zin, slot, y, zz);
+      load_row(r, slot, y, rr);
+      load_row(nu, slot, y, nn);
+#pragma unroll
+      for (int i = 0; i < 8; i++) {
+        xx[i] = fma(alpha, zz[i], xx[i]);
+        rr[i] = fma(-alpha, nn[i], rr[i]);
+      }
+      store_row(xn, slot, y, xx);
+      store_row(r, slot, y, rr);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; i++) rr[i] = 0.0;
+    }
+    precond_row(rr, sw, lane);
+    if (act) store_row(zout, slot, y, rr);
+  }
+}
+
+// ---- K5: x += omega z ; r -= omega t ; err, rhat.r, |r|^2, sum(x) ; end-of-iteration logic --------
+__global__ void __launch_bounds__(NT)
+k_final(double *x0, double *x1, double *x2, const double *__restrict__ z, double *__restrict__ r,
+        const double *__restrict__ t, const double *__restrict__ rhat, int nrows, KrylovState *st,
+        double *partials, unsigned int *counter, Comm comm) {
+  if (st->done) return;
+  const double omega = st->omega;
+  const int nxt = next_buf(st->cur, st->opt);
+  double *xn = nxt == 0 ? x0 : (nxt == 1 ? x1 : x2);
+  double sums[3] = {0, 0, 0}; // rhat.r, r.r, sum x
+  double mx = 0;
+  for (int row = blockIdx.x * NT + threadIdx.x; row < nrows; row += gridDim.x * NT) {
+    const int slot = row >> 3, y = row & 7;
+    double xx[8], zz[8], rr[8], tt[8], hh[8];
+    load_row(xn, slot, y, xx);
+    load_row(z, slot, y, zz);
+    load_row(r, slot, y, rr);
+    load_row(t, slot, y, tt);
+    load_row(rhat, slot, y, hh);
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      xx[i] = fma(omega, zz[i], xx[i]);       // cuda.cu:520
+      rr[i] = fma(-omega, tt[i], rr[i]);      // cuda.cu:524
+      sums[0] = fma(hh[i], rr[i], sums[0]);
+      sums[1] = fma(rr[i], rr[i], sums[1]);
+      sums[2] += xx[i];
+      mx = fmax(mx, fabs(rr[i]));
+    }
+    store_row(xn, slot, y, xx);
+    store_row(r, slot, y, rr);
+  }
+  grid_reduce<3, NT>(sums, mx, partials, counter, comm, [=](const double *tsum, double m) {
+    st->iter++;
+    st->err = m;
+    st->cur = nxt;
+    if (m < st->err_opt) {                                            // cuda.cu:535-541
+      st->err_opt = m;
+      st->opt = nxt;
+      st->xsum = tsum[2];
+      if (m <= st->tol_abs || m / st->err_init <= st->tol_rel) {
+        st->done = 1;
+        return;
+      }
+    }
+    st->rho_prev = st->rho_curr;                                      // set_rho
+    if (st->iter >= st->max_iter) {                                   // cuda.cu:438
+      st->done = 1;
+      return;
+    }
+    prepare_iteration(st, tsum[0], tsum[1]);
+  });
+}
+
+static inline int red_grid(const cup2d_sim *s, int nrows) {
+  int g = (nrows + NT - 1) / NT;
+  int cap = s->num_sms * 8;
+  if (cap > RED_MAX_CTAS) cap = RED_MAX_CTAS;
+  return g < cap ? g : cap;
+}
+
+int poisson_solve(cup2d_sim *s, double tol_abs, double tol_rel, int max_restarts, int max_iter,
+                  int *iters, double *err) {
+  int rc = init_consts();
+  if (rc) return rc;
+  const int nrows = (int)s->nloc * 8;
+  const int grid = red_grid(s, nrows);
+  const int4 *nbr = reinterpret_cast<const int4 *>(s->d_nbr);
+  KrylovState *h = s->h_state;
+  *h = KrylovState{};
+  h->alpha = h->omega = h->rho_prev = h->rho_curr = 1.0; // cuda.cu:409
+  h->tol_abs = tol_abs;
+  h->tol_rel = tol_rel;
+  h->max_restarts = max_restarts;
+  h->max_iter = max_iter;
+  CUP2D_CUDA(cudaMemcpyAsync(s->d_state, h, sizeof *h, cudaMemcpyHostToDevice, s->stream));
+  if (s->nranks > 1 && (rc = halo_exchange_ptr(s, s->f[CUP2D_PRES], 1, CUP2D_PRES))) return rc;
+  k_init<<<grid, NT, 0, s->stream>>>(s->f[CUP2D_TMP], s->f[CUP2D_PRES], s->kx[0], s->kr, s->krhat,
+                                     s->kp, s->knu, nbr, nrows, s->d_state, s->d_partials, s->d_counter, s->comm);
+  s->launches++;
+  const int check_every = (tol_abs > 0 || tol_rel > 0) ? 8 : 64;
+  int launched = 0;
+  bool done = max_iter <= 0;
+  while (!done) {
+    int batch = max_iter - launched < check_every ? max_iter - launched : check_every;
+    for (int k = 0; k < batch; k++) {
+      k_pupdate<<<grid, NT, 0, s->stream>>>(s->kr, s->krhat, s->kp, s->knu, s->kz, nrows, s->d_state);
+      if (s->nranks > 1 && (rc = halo_exchange_ptr(s, s->kz, 1, CUP2D_NFIELDS))) return rc;
+      k_spmv<0><<<grid, NT, 0, s->stream>>>(s->kz, s->krhat, s->knu, nbr, nrows, s->d_state, s->d_partials, s->d_counter, s->comm);
+      k_xr_update<<<grid, NT, 0, s->stream>>>(s->kx[0], s->kx[1], s->kx[2], s->kz, s->kr, s->knu, s->kz, nrows, s->d_state);
+      if (s->nranks > 1 && (rc = halo_exchange_ptr(s, s->kz, 1, CUP2D_NFIELDS))) return rc;
+      k_spmv<1><<<grid, NT, 0, s->stream>>>(s->kz, s->kr, s->kt, nbr, nrows, s->d_state, s->d_partials, s->d_counter, s->comm);
+      k_final<<<grid, NT, 0, s->stream>>>(s->kx[0], s->kx[1], s->kx[2], s->kz, s->kr, s->kt, s->krhat, nrows, s->d_state, s->d_partials, s->d_counter, s->comm);
+      s->launches += 5;
+    }
+    launched += batch;
+    CUP2D_CUDA(cudaGetLastError());
+    CUP2D_CUDA(cudaMemcpyAsync(h, s->d_state, sizeof *h, cudaMemcpyDeviceToHost, s->stream));
+    CUP2D_CUDA(cudaStreamSynchronize(s->stream));
+    done = h->done || launched >= max_iter;
+  }
+  if (max_iter <= 0) {
+    CUP2D_CUDA(cudaMemcpyAsync(h, s->d_state, sizeof *h, cudaMemcpyDeviceToHost, s->stream));
+    CUP2D_CUDA(cudaStreamSynchronize(s->stream));
+  }
+  if (iters) *iters = h->iter;
+  if (err) *err = h->err_opt;
+  return CUP2D_OK;
+}
+
+} // namespace cup2d

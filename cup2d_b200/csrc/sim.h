@@ -1,0 +1,96 @@
+// Internal state of one cup2d_sim (one process <-> one GPU <-> one contiguous SFC range of blocks).
+#pragma once
+#include "../../include/cup2d_b200.h"
+#include "common.cuh"
+#include <vector>
+
+namespace cup2d {
+
+constexpr int TILE_B = 4;                 // advect tile = 4x4 blocks = 32x32 cells
+constexpr int TILE_SLOTS = 32;            // 16 interior + 4 W + 4 E + 4 S + 4 N
+constexpr int MAX_RANKS = 8;
+constexpr int RED_MAX_CTAS = 4096;        // upper bound on reduction grid size
+constexpr int RED_SLOTS = 8;              // doubles per CTA partial
+
+// Device-resident scalars of the Krylov recurrence (cuda.cu:24-34 BiCGSTABScalars, plus the host
+// variables of cuda.cu:405-408 moved to the device so that no host sync is needed per iteration).
+struct KrylovState {
+  double alpha, omega, rho_prev, rho_curr; // recurrence scalars
+  double beta;                             // beta for the next p-update
+  double nr2, nrh2;                        // |r|^2, |rhat|^2 (breakdown test, cuda.cu:452-454)
+  double rhat_nu;                          // rhat . nu
+  double tr, tt;                           // t.r, t.t
+  double err, err_init, err_opt;           // ||r||_inf now / initially / best
+  double xsum;                             // sum of the returned iterate (pressure mean, main.cpp:7126-7148)
+  double tol_abs, tol_rel;
+  int max_restarts, max_iter;
+  int iter;                                // completed iterations
+  int restarts;
+  int done;                                // 1: stop (converged / restart cap / max_iter)
+  int restart_now;                         // 1: next p-update performs the restart of cuda.cu:457-477
+  int cur, opt;                            // which of the 3 x buffers holds x / x_opt
+  int pad;
+};
+
+struct PeerBlob { // what every rank publishes to the others (cup2d_peer_export)
+  cudaIpcMemHandle_t field[CUP2D_NFIELDS];
+  cudaIpcMemHandle_t kz, kx[3];
+  cudaIpcMemHandle_t mailbox;
+  int64_t nloc;
+  int32_t rank, device;
+};
+
+} // namespace cup2d
+
+struct cup2d_sim {
+  // topology
+  int nbx = 0, nby = 0;
+  int64_t nglobal = 0, gbegin = 0, nloc = 0, nhalo = 0, nslots = 0;
+  int rank = 0, nranks = 1, device = 0;
+  double h = 0, nu = 0, cfl = 0;
+  std::vector<int32_t> ij;             // global (i,j) table
+  std::vector<int64_t> rank_begin;
+  std::vector<int32_t> halo_gid;       // global id of every halo slot (slot = nloc + k), sorted
+  std::vector<int32_t> halo_owner;     // owning rank per halo slot
+  cudaStream_t stream = nullptr;
+  // device tables
+  int *d_nbr = nullptr;                // [nloc][4] slots of W,E,S,N neighbours, -1 = wall
+  int *d_tiles = nullptr;              // [ntiles][TILE_SLOTS]
+  int *d_tile_org = nullptr;           // [ntiles][2] tile origin in blocks
+  int ntiles = 0;
+  // fields (dim*64*nslots doubles each)
+  double *f[CUP2D_NFIELDS] = {};
+  // Krylov vectors (64*nslots)
+  double *kx[3] = {}, *kr = nullptr, *krhat = nullptr, *kp = nullptr, *knu = nullptr, *kt = nullptr,
+         *kz = nullptr;
+  cup2d::KrylovState *d_state = nullptr, *h_state = nullptr;
+  // reductions
+  double *d_partials = nullptr;
+  unsigned int *d_counter = nullptr;
+  double *d_scal = nullptr, *h_scal = nullptr; // small scalar mailbox (umax, sums)
+  int num_sms = 0;
+  // multi-GPU (peer memory over NVLink)
+  bool peers_attached = false;
+  void *peer_base[cup2d::MAX_RANKS][CUP2D_NFIELDS + 4] = {};
+  int *d_halo_src = nullptr;           // [nhalo][2] = (owner rank, slot on owner)
+  unsigned long long *d_mailbox = nullptr;       // this rank's flag/scalar mailbox (peer-writable)
+  unsigned long long *peer_mailbox[cup2d::MAX_RANKS] = {};
+  unsigned long long epoch = 0;
+  cup2d::Comm comm = {};               // by-value kernel argument of every reducing kernel
+  double **d_peer_ptrs = nullptr;      // device copy of peer_base
+  int64_t launches = 0;
+};
+
+namespace cup2d {
+int dim_of(int field);
+// operators (host-side launchers; all on s->stream)
+int launch_advect(cup2d_sim *s, const double *in, const double *old, double *out, double coef,
+                  double dt, bool raw);
+int launch_umax(cup2d_sim *s, double *umax_out);
+int launch_pressure_rhs(cup2d_sim *s, double dt);
+int launch_pressure_correct(cup2d_sim *s, double dt);
+int poisson_solve(cup2d_sim *s, double tol_abs, double tol_rel, int max_restarts, int max_iter,
+                  int *iters, double *err);
+int halo_exchange_ptr(cup2d_sim *s, double *base, int dim, int peer_index);
+void swap_fields(cup2d_sim *s, int a, int b); // pointer swap, mirrored on the peer mappings
+} // namespace cup2d

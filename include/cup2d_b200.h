@@ -1,0 +1,131 @@
+/* cup2d_b200 — C ABI of the B200-native CUP2D hot path (libcup2d_b200.so).
+ *
+ * Plain pointers and sizes only; no C++/torch types cross this boundary.  Every entry point
+ * returns 0 on success and a negative CUP2D_E* code on failure; cup2d_last_error() gives the
+ * message (the reference itself has no error convention: CUDA errors are swallowed, cuda.cu:358;
+ * this library fails loudly instead).
+ *
+ * What each group replaces in the reference (/root/reference, file:line):
+ *   grid / fields   Grid, Info, var.{vel,vold,tmpV,chi,pres,pold,tmp}     main.cpp:504-512, 2193-2201, 3264-3278, 6508-6541
+ *   compute_dt      umax reduction + dt rule                              main.cpp:6579-6595
+ *   advect_diffuse  computeA<VectorLab>(KernelAdvectDiffuse) + RK2 loops  main.cpp:5441-5503, 6607-6642, 162-208
+ *   pressure_rhs    computeB<pressure_rhs> + pold/pres swap + pressure_rhs1  main.cpp:6105-6139, 6209-6230, 7011-7027
+ *   poisson_solve   Solver::getVec + LocalSpMatDnVec::solve* (BiCGSTAB)   main.cpp:5998-6019, 7031-7118; cuda.cu:403-548
+ *   pressure_correct mean removal + pressureCorrectionKernel + V update   main.cpp:6021-6043, 7120-7187
+ *   halo exchange   sync1/Setup/pack/unpack_subregion                     main.cpp:1971-2142, 909-1380, 58-110
+ *
+ * Memory layout (kept from the reference so the host driver can hand blocks over unchanged):
+ * a field is nblocks_local consecutive 8x8 blocks in the caller's block order (the reference's
+ * Hilbert-sorted `infos[]`); cell (ix,iy) component c of block k is at
+ *   k*dim*64 + dim*(8*iy+ix) + c        (dim = 2 for vel/vold/tmpV interleaved u,v; 1 otherwise)
+ * exactly main.cpp:6517 + 5467-5468.  All arithmetic is FP64 (main.cpp:24 `typedef double Real`).
+ */
+#ifndef CUP2D_B200_H
+#define CUP2D_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CUP2D_BS 8 /* _BS_, reference Makefile:12 */
+
+enum {
+  CUP2D_OK = 0,
+  CUP2D_EINVAL = -1,  /* bad argument / unsupported topology */
+  CUP2D_ECUDA = -2,   /* CUDA runtime error (message in cup2d_last_error) */
+  CUP2D_ENOGPU = -3,  /* no usable sm_100 device: there is NO CPU fallback */
+  CUP2D_ESTATE = -4   /* call made in the wrong state (e.g. multi-rank step before peers attached) */
+};
+
+/* field ids (var.* of main.cpp:3264-3278) */
+enum {
+  CUP2D_VEL = 0,  /* dim 2 */
+  CUP2D_VOLD = 1, /* dim 2 */
+  CUP2D_TMPV = 2, /* dim 2 : RK scratch, then sum of u_def (main.cpp:6980-7006) */
+  CUP2D_CHI = 3,  /* dim 1 */
+  CUP2D_PRES = 4, /* dim 1 */
+  CUP2D_POLD = 5, /* dim 1 */
+  CUP2D_TMP = 6,  /* dim 1 : Poisson right-hand side */
+  CUP2D_NFIELDS = 7
+};
+
+typedef struct cup2d_sim cup2d_sim;
+
+typedef struct {
+  int32_t nbx, nby;          /* blocks per direction of the (uniform-level) grid: bpd << level */
+  int64_t nblocks_global;    /* == nbx*nby */
+  const int32_t *block_ij;   /* [2*nblocks_global]: (i,j) = Info::index of every block, in GLOBAL id
+                                order (rank 0's infos[], then rank 1's, ... : main.cpp:6494-6504) */
+  int32_t rank, nranks;      /* this process / number of processes (one per GPU) */
+  const int64_t *rank_begin; /* [nranks+1]: rank r owns global block ids [rank_begin[r], rank_begin[r+1]) */
+  double h;                  /* cell size (Info::h) */
+  double nu;                 /* sim.nu */
+  double cfl;                /* sim.CFL */
+  int32_t device;            /* CUDA device ordinal for this process */
+  int32_t reserved;
+} cup2d_config;
+
+/* ---- lifetime ---- */
+int cup2d_create(const cup2d_config *cfg, cup2d_sim **out);
+void cup2d_destroy(cup2d_sim *s);
+const char *cup2d_last_error(void);
+int cup2d_version(void);
+int64_t cup2d_nblocks_local(const cup2d_sim *s);
+int64_t cup2d_nblocks_halo(const cup2d_sim *s);
+
+/* host helper mirroring SpaceCurve (main.cpp:342-446) for bpdx x bpdy base blocks at `level`:
+ * writes (i,j) of all (bpdx<<level)*(bpdy<<level) blocks in the reference's Hilbert id order. */
+int cup2d_block_order(int32_t bpdx, int32_t bpdy, int32_t level, int32_t *block_ij_out);
+
+/* ---- fields: host <-> device in the reference block layout (local blocks only) ---- */
+int cup2d_field_upload(cup2d_sim *s, int field, const double *host_blocks);
+int cup2d_field_download(cup2d_sim *s, int field, double *host_blocks);
+int cup2d_field_fill(cup2d_sim *s, int field, double value);
+void *cup2d_field_device_ptr(cup2d_sim *s, int field); /* device pointer, same layout (+halo slots after) */
+int cup2d_sync(cup2d_sim *s);                          /* cudaStreamSynchronize on the sim's stream */
+void *cup2d_stream(cup2d_sim *s);                      /* cudaStream_t all work is launched on */
+
+/* ---- operators; everything stays on the device ---- */
+/* umax = max|vel| (all components), dt = min(0.25 h^2/(nu+0.25 h umax), cfl*h/(umax+1e-8)). main.cpp:6579-6595 */
+int cup2d_compute_dt(cup2d_sim *s, double *umax_out, double *dt_out);
+/* one fused RK stage: out = old + coef * K(in)/h^2, K = KernelAdvectDiffuse (main.cpp:5441-5503).
+ * in/old/out are vector field ids; out must differ from in (old may equal in). */
+int cup2d_advect_diffuse_stage(cup2d_sim *s, int in_field, int old_field, int out_field, double coef,
+                               double dt);
+/* raw K(vel) -> tmpV, undivided, exactly what the reference kernel writes (for operator parity tests). */
+int cup2d_advect_diffuse_rhs(cup2d_sim *s, int in_field, int out_field, double dt);
+/* vold = vel; vel = vold + 0.5 K(vel)/h^2; vel = vold + K(vel)/h^2.  main.cpp:6607-6642 */
+int cup2d_advect_diffuse_rk2(cup2d_sim *s, double dt);
+/* tmp = (0.5 h/dt)(div vel - chi div tmpV); pold = pres; pres = 0; tmp -= lap(pold).  main.cpp:7011-7027 */
+int cup2d_pressure_rhs(cup2d_sim *s, double dt);
+/* Solve A x = tmp (A = undivided 5-point Laplacian, Neumann walls), x0 = pres, result -> pres.
+ * Block-Jacobi preconditioned BiCGSTAB with the reference's operation order, epsilons, restart and
+ * stopping rules (cuda.cu:403-548).  max_iter: cuda.cu:438 hard-codes 1000.  iters/err may be NULL. */
+int cup2d_poisson_solve(cup2d_sim *s, double tol_abs, double tol_rel, int max_restarts, int max_iter,
+                        int *iters_out, double *err_out);
+/* pres = pres - mean(pres); pres += pold - mean(pres); tmpV = -0.5 dt h grad(pres) (undivided);
+ * vel += tmpV/h^2.  main.cpp:7120-7187 */
+int cup2d_pressure_correct(cup2d_sim *s, double dt);
+/* One full time step of the hot path (no bodies): compute_dt (unless dt>0 is given), rk2, tmpV=0
+ * (or kept if keep_udef), pressure_rhs, poisson_solve, pressure_correct.  Returns dt used. */
+int cup2d_step(cup2d_sim *s, double dt_in, int keep_udef, double tol_abs, double tol_rel,
+               int max_restarts, int max_iter, double *dt_out, int *iters_out, double *err_out);
+
+/* ---- multi-GPU (one process per GPU; peers on the same NVSwitch node) ---- */
+/* Size in bytes of the opaque per-rank handle blob exchanged by the launcher (torch.distributed). */
+int cup2d_peer_blob_size(void);
+/* Fill `blob` (cup2d_peer_blob_size() bytes) with this rank's CUDA IPC handles. */
+int cup2d_peer_export(cup2d_sim *s, void *blob);
+/* all_blobs = nranks blobs in rank order (all-gathered by the caller). Opens peer mappings. */
+int cup2d_peer_attach(cup2d_sim *s, const void *all_blobs);
+/* Explicit halo refresh of one field (normally implicit inside the operators). */
+int cup2d_halo_exchange(cup2d_sim *s, int field);
+
+/* ---- instrumentation ---- */
+/* number of kernels this library has launched since creation (bench.py's gpu_launches) */
+int64_t cup2d_launch_count(const cup2d_sim *s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,59 @@
+"""CPU-side checks of the C-ABI library: it loads, exports every symbol the header declares, mirrors
+the reference's block ordering, and refuses to run without a GPU (no CPU fallback)."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+import cup2d_b200
+from cup2d_b200 import lib as L
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = cup2d_b200.load_library()
+    hdr = open(os.path.join(ROOT, "include", "cup2d_b200.h")).read()
+    declared = sorted(set(re.findall(r"\b(cup2d_[a-z0-9_]+)\s*\(", hdr)))
+    assert declared, "no declarations parsed"
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/cup2d_b200.h but not exported"
+    assert sorted(L.SYMBOLS) == declared
+    assert lib.cup2d_version() >= 100
+
+
+@pytest.mark.parametrize("lvl", range(6))
+def test_block_order_matches_reference_golden(golden_dir, lvl):
+    g = np.load(os.path.join(golden_dir, f"order_L{lvl}.npy"))
+    assert np.array_equal(cup2d_b200.block_order(1, 1, lvl), g)
+
+
+def test_block_order_rectangular_is_a_permutation_with_face_adjacency():
+    # 2x1 base blocks (run.sh geometry): every block exactly once; consecutive blocks inside one base
+    # block are face neighbours (Hilbert property)
+    o = cup2d_b200.block_order(2, 1, 3)
+    assert len({(i, j) for i, j in o}) == 16 * 8
+    d = np.abs(np.diff(o, axis=0)).sum(axis=1)
+    assert (d == 1).sum() >= len(o) - 2
+
+
+def test_blocks_roundtrip_layout():
+    lvl = 2
+    N = 8 << lvl
+    rng = np.random.default_rng(0)
+    u, v = rng.normal(size=(N, N)), rng.normal(size=(N, N))
+    order = cup2d_b200.block_order(1, 1, lvl)
+    flat = cup2d_b200.to_blocks((u, v), order, 1 << lvl)
+    i, j = order[5]
+    assert flat[5 * 128 + 2 * (8 * 3 + 2) + 1] == v[j * 8 + 3, i * 8 + 2]  # main.cpp:5467-5468
+    u2, v2 = cup2d_b200.from_blocks(flat, order, 1 << lvl, 1 << lvl, 2)
+    assert np.array_equal(u, u2) and np.array_equal(v, v2)
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(cup2d_b200.Cup2dError, match="no CPU fallback"):
+        cup2d_b200.Simulation(2)
