@@ -1,0 +1,348 @@
+#!/usr/bin/env python
+"""bench.py — CUP2D hot path on B200: Mcell-updates/s (advect+diffuse+Poisson iter) at 8192^2.
+
+One "step" = one full time step of the hot path on a uniform grid without bodies:
+    dt control (umax reduction) -> RK2 (two fused WENO5 advect-diffuse stages) -> Poisson RHS ->
+    K BiCGSTAB iterations (K fixed, tolerance 0, like the reference's first 10 steps with its
+    hard-coded cap, main.cpp:7028-7030 / cuda.cu:438) -> pressure correction.
+cell-updates per step = cells * (2 stage sweeps + K Poisson iterations)   [the metric's own definition]
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--level L] [--poisson-iters K] [--impl reference]
+
+N > 1: launched by torchrun, one rank per GPU; the 8192^2 grid is split into contiguous Hilbert ranges
+(strong scaling); halos and Krylov dots go over NVLink peer memory inside the library's kernels.
+`--impl reference` times the reference's own CPU code (oracle/_ref/ref_harness: unmodified main.cpp
+operators under OpenMP on all host cores; its GPU-only Poisson solver is replaced by the CPU restatement
+of cuda.cu) on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+HARNESS = os.path.join(ROOT, "oracle", "_ref", "ref_harness")
+
+# algorithmic bytes per cell per launch (DESIGN.md "Kernels")
+ALG_BYTES = {
+    "advect_stage_kernel": 48.0,      # read V_in 16 + read V_old 16 + write V_out 16 (stage 1 aliases in/old: 32)
+    "umax_kernel": 16.0,
+    "pressure_rhs_kernel": 64.0,      # vel 16 + udef 16 + chi 8 + pold 8 read; tmp 8 + pres 8 written
+    "pressure_correct_kernel": 56.0,  # x 8 + pold 8 + vel 16 read; pres 8 + vel 16 written
+    "k_init": 56.0,                   # b, x0 read; x, r, rhat, p, nu written
+    "k_pupdate": 40.0,                # r, p, nu read; p, z written
+    "k_spmv<0>": 24.0,                # z, rhat read; nu written
+    "k_xr_update": 56.0,              # x, z, r, nu read; x, r, z written
+    "k_spmv<1>": 24.0,                # z, r read; t written
+    "k_final": 56.0,                  # x, z, r, t, rhat read; x, r written
+    "memset(udef)": 16.0,
+}
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows = []
+        self.proc = None
+        self.idx = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.idx), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def run_harness_time(level, reps, kiter, threads):
+    env = dict(os.environ, OMP_NUM_THREADS=str(threads), OMP_PROC_BIND="close")
+    out = subprocess.run([HARNESS, "time", str(level), str(reps), str(kiter)], env=env, check=True,
+                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True).stdout
+    return json.loads(out.strip().splitlines()[-1])
+
+
+def cpu_composite(level, reps, kiter):
+    """Reference CPU path on a bounded sample: cells*(2+K) / (2 t_stage + t_rhs + K t_iter + t_correct)."""
+    threads = os.cpu_count() or 1
+    t = run_harness_time(level, reps, kiter, threads)
+    step_s = 2 * t["t_stage"] + t["t_rhs"] + kiter * t["t_poisson_iter"] + t["t_correct"]
+    val = t["cells"] * (2 + kiter) / step_s / 1e6
+    N = t["N"]
+    return {
+        "value": val, "unit": "Mcell-updates/s", "cores": t["threads"], "kind": "reference",
+        "sample": f"{N}x{N} uniform grid (L={level}), Taylor-Green, median of {reps} reps per operator; "
+                  f"operators = unmodified reference main.cpp under OpenMP; Poisson iteration = CPU restatement "
+                  f"of cuda.cu (the reference has no CPU solver); composite = 2 stages + RHS + {kiter} iterations + correction",
+        "ms_per_step": step_s * 1e3,
+        "stage_Mcells_s": t["cells"] / t["t_stage"] / 1e6,
+        "poisson_iter_Mcells_s": t["cells"] / t["t_poisson_iter"] / 1e6 if t["t_poisson_iter"] > 0 else None,
+    }
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--level", type=int, default=10, help="uniform level: grid = (8*2^L)^2; 10 = 8192^2")
+    ap.add_argument("--poisson-iters", type=int, default=10)
+    ap.add_argument("--impl", default="cup2d_b200", choices=["cup2d_b200", "reference"])
+    ap.add_argument("--cpu-level", type=int, default=8, help="grid level of the bounded CPU sample (8 = 2048^2)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    K = args.poisson_iters
+    L = args.level
+    N = 8 << L
+    cells = N * N
+    config = {"workload": f"{N}x{N} uniform block grid (level {L}, {(1 << L) ** 2} blocks of 8x8, Hilbert order), "
+                          f"Taylor-Green + seeded perturbation, nu=1e-4, CFL=0.5, free-slip box, no bodies",
+              "step": f"dt control + RK2 WENO5 advect-diffuse + Poisson RHS + {K} BiCGSTAB iterations (tol 0) + pressure correction",
+              "cell_updates_per_step": f"cells*(2+{K})", "poisson_iters": K,
+              "partition": f"{world} contiguous Hilbert range(s), halo + dots over NVLink peer memory" if world > 1 else "single GPU",
+              "cache": "inputs larger than L2 (each field >= 0.5 GB vs 126 MB L2)" if L >= 9 else "L2-resident at this size"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        reps = max(3, args.steps)
+        cb = cpu_composite(args.cpu_level, reps, K)
+        line = {"impl": "reference", "metric": "Mcell-updates/s (advect+diffuse+Poisson iter)", "value": cb["value"],
+                "unit": "Mcell-updates/s", "n_gpus": 0, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": cb["ms_per_step"], "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
+                "cpu_baseline": cb,
+                "e2e": {"value": cb["value"], "unit": "Mcell-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    import numpy as np
+    import torch
+    import cup2d_b200
+
+    if not torch.cuda.is_available():
+        sys.exit("bench.py: no CUDA device; cup2d_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    # ---- synthetic input (host, reference block layout) -------------------------------------------
+    sim = cup2d_b200.Simulation(L, nu=1e-4, cfl=0.5, device=local_rank, rank=rank, nranks=world)
+    if world > 1:
+        sim.attach_peers(dist)
+    order = sim.local_order
+    bi = order[:, 0].astype(np.float64)[:, None, None]
+    bj = order[:, 1].astype(np.float64)[:, None, None]
+    ix = np.arange(8, dtype=np.float64)[None, None, :]
+    iy = np.arange(8, dtype=np.float64)[None, :, None]
+    X = (bi * 8 + ix + 0.5) / N
+    Y = (bj * 8 + iy + 0.5) / N
+    rng = np.random.default_rng(1234 + rank)
+    nloc = len(order)
+    vel_h = torch.empty(nloc * 128, dtype=torch.float64).pin_memory()
+    pres_h = torch.empty(nloc * 64, dtype=torch.float64).pin_memory()
+    v = vel_h.numpy().reshape(nloc, 8, 8, 2)
+    v[..., 0] = np.sin(2 * np.pi * X) * np.cos(2 * np.pi * Y) + 0.01 * rng.uniform(-1, 1, (nloc, 8, 8))
+    v[..., 1] = -np.cos(2 * np.pi * X) * np.sin(2 * np.pi * Y) + 0.01 * rng.uniform(-1, 1, (nloc, 8, 8))
+    pres_h.numpy().reshape(nloc, 8, 8)[:] = 0.0
+    vel_out = torch.empty_like(vel_h).pin_memory()
+    pres_out = torch.empty_like(pres_h).pin_memory()
+    del X, Y
+
+    lib = sim.lib
+    from cup2d_b200 import lib as _l
+    H = sim._h
+    stream = torch.cuda.ExternalStream(sim.stream, device=torch.device("cuda", local_rank))
+
+    def upload():
+        _l.check(lib.cup2d_field_upload(H, 0, vel_h.data_ptr()))
+        _l.check(lib.cup2d_field_upload(H, 4, pres_h.data_ptr()))
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # dt: fixed from the initial field so that every step does identical work on every rank
+    upload()
+    sim.sync()
+    umax, dt = sim.compute_dt()
+
+    def step():
+        sim.step(dt=dt, max_iter=K, max_restarts=0)
+
+    # ---- device-resident timing (`value`) ------------------------------------------------------------
+    for _ in range(max(3, args.warmup)):
+        step()
+    barrier()
+    l0 = sim.launch_count()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    sim.profile(True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        step()
+    e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    prof = sim.profile_read()
+    sim.profile(False)
+    clocks = sampler.stop() if rank == 0 else None
+    launches = sim.launch_count() - l0
+    if dist is not None:
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    ms_per_step = ms / args.steps
+    value = cells * (2 + K) / (ms_per_step * 1e-3) / 1e6
+
+    # ---- end-to-end through the C ABI with host buffers (`e2e`) -----------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        def e2e_step():
+            upload()                                   # H2D from pinned memory: vel + pres
+            step()
+            _l.check(lib.cup2d_field_download(H, 0, vel_out.data_ptr()))   # D2H (synchronises the stream)
+            _l.check(lib.cup2d_field_download(H, 4, pres_out.data_ptr()))
+        for _ in range(2):
+            e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        e0.record(stream)
+        for _ in range(args.steps):
+            e2e_step()
+        e1.record(stream)
+        barrier()
+        ms_e = e0.elapsed_time(e1)
+        wall = (time.perf_counter() - t0) * 1e3
+        if dist is not None:
+            t = torch.tensor([ms_e], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms_e = float(t.item())
+        ms_e /= args.steps
+        e2e = {"value": cells * (2 + K) / (ms_e * 1e-3) / 1e6, "unit": "Mcell-updates/s",
+               "h2d_bytes_per_step": int((vel_h.numel() + pres_h.numel()) * 8 * world),
+               "d2h_bytes_per_step": int((vel_out.numel() + pres_out.numel()) * 8 * world),
+               "ms_per_step": ms_e, "wall_ms_per_step": wall / args.steps,
+               "note": "per step: pinned-host vel+pres -> device, one full step, vel+pres -> pinned host"}
+
+    # ---- per-kernel roofline from the CUDA events recorded inside the timed region ---------------------
+    peak, peak_src = load_peaks()
+    cells_loc = nloc * 64
+    kernels = []
+    for name, (tot_ms, n) in prof.items():
+        per = tot_ms / n
+        ab = ALG_BYTES.get(name)
+        gbs = cells_loc * ab / (per * 1e-3) / 1e9 if ab else None
+        kernels.append({"kernel": name, "launches_per_step": n / args.steps, "ms_per_launch": per,
+                        "share_of_step": tot_ms / (ms_per_step * args.steps),
+                        "alg_bytes_per_cell": ab, "achieved_GBs": gbs, "frac_hbm": gbs / peak if gbs else None})
+    kernels.sort(key=lambda k: -k["share_of_step"])
+    adv = next((k for k in kernels if k["kernel"] == "advect_stage_kernel"), None)
+    top = kernels[0] if kernels else None
+    roofline = None
+    if top:
+        roofline = {"kernel": top["kernel"], "bound": "hbm", "achieved": top["achieved_GBs"], "peak": peak,
+                    "unit": "GB/s", "frac": top["frac_hbm"], "traffic": None, "peak_source": peak_src,
+                    "ms_per_launch": top["ms_per_launch"], "share_of_step": top["share_of_step"]}
+    extra = {}
+    if adv:
+        # the north-star kernel: HBM fraction and the FP64-pipe bound it actually sits under
+        gcell = cells_loc / (adv["ms_per_launch"] * 1e-3) / 1e9
+        extra["advect_stage"] = {"Gcell_per_s": gcell, "achieved_GBs": adv["achieved_GBs"], "frac_hbm": adv["frac_hbm"],
+                                 "ms_per_launch": adv["ms_per_launch"], "alg_bytes_per_cell": 48.0,
+                                 "note": "FP64-pipe-bound (~230 DFMA-class instr/cell vs 64 lanes/clk/SM): see DESIGN.md"}
+    it_ms = sum(k["ms_per_launch"] * k["launches_per_step"] for k in kernels
+                if k["kernel"] in ("k_pupdate", "k_spmv<0>", "k_xr_update", "k_spmv<1>", "k_final")) / max(K, 1)
+    if it_ms > 0:
+        gbs = cells_loc * 200.0 / (it_ms * 1e-3) / 1e9
+        extra["poisson_iteration"] = {"ms_per_iteration": it_ms, "Gcell_iter_per_s": cells_loc / (it_ms * 1e-3) / 1e9,
+                                      "alg_bytes_per_cell": 200.0, "achieved_GBs": gbs, "frac_hbm": gbs / peak}
+
+    if rank != 0:
+        if dist is not None:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline and os.path.exists(HARNESS):
+        try:
+            cpu = cpu_composite(args.cpu_level, 3, K)
+        except Exception as ex:  # the baseline is a reported figure, not a gate
+            cpu = {"error": str(ex)}
+
+    line = {"metric": "Mcell-updates/s (advect+diffuse+Poisson iter)", "value": value, "unit": "Mcell-updates/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_per_step,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": config, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+            "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu, "dt": dt, "umax": umax}
+    line.update(extra)
+    print(json.dumps(line))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

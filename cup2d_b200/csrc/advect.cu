@@ -292,6 +292,7 @@ int launch_advect(cup2d_sim *s, const double *in, const double *old, double *out
   const double dfac = s->nu * dt;    // main.cpp:5446
   const double ofac = coef / (s->h * s->h);
   dim3 grid(s->ntiles), block(NT_ADV);
+  ProfScope prof(s, KC_ADVECT);
   if (raw)
     advect_stage_kernel<true, true><<<grid, block, ADV_SMEM, s->stream>>>(in, in, out, s->d_tiles, s->d_tile_org, s->nbx, s->nby, (int)s->nloc, afac, dfac, ofac);
   else if (old == in)

@@ -315,6 +315,37 @@ void cup2d_destroy(cup2d_sim *s) {
 int64_t cup2d_nblocks_local(const cup2d_sim *s) { return s ? s->nloc : 0; }
 int64_t cup2d_nblocks_halo(const cup2d_sim *s) { return s ? s->nhalo : 0; }
 int64_t cup2d_launch_count(const cup2d_sim *s) { return s ? s->launches : 0; }
+
+static const char *kclass_name[KC_COUNT] = {"advect_stage_kernel", "umax_kernel", "pressure_rhs_kernel",
+    "pressure_correct_kernel", "k_init", "k_pupdate", "k_spmv<0>", "k_xr_update", "k_spmv<1>", "k_final",
+    "halo_pull_kernel", "memset(udef)"};
+int cup2d_profile_enable(cup2d_sim *s, int on) {
+  if (!s) return CUP2D_EINVAL;
+  for (auto &r : s->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+  s->prof.clear();
+  s->prof_on = on != 0;
+  return CUP2D_OK;
+}
+int cup2d_profile_read(cup2d_sim *s, int max_entries, char *names, double *total_ms, int64_t *launches) {
+  if (!s || !names || !total_ms || !launches) return CUP2D_EINVAL;
+  if (cudaStreamSynchronize(s->stream) != cudaSuccess) return CUP2D_ECUDA;
+  double ms[KC_COUNT] = {};
+  int64_t n[KC_COUNT] = {};
+  for (auto &r : s->prof) {
+    float t = 0;
+    if (cudaEventElapsedTime(&t, r.a, r.b) == cudaSuccess) { ms[r.cls] += t; n[r.cls]++; }
+  }
+  int k = 0;
+  for (int c = 0; c < KC_COUNT && k < max_entries; c++) {
+    if (!n[c]) continue;
+    strncpy(names + 32 * k, kclass_name[c], 31);
+    names[32 * k + 31] = 0;
+    total_ms[k] = ms[c];
+    launches[k] = n[c];
+    k++;
+  }
+  return k;
+}
 void *cup2d_stream(cup2d_sim *s) { return s ? (void *)s->stream : nullptr; }
 
 #define CHECK_SIM(s) CUP2D_REQUIRE((s) != nullptr, "null cup2d_sim")
@@ -452,8 +483,10 @@ int cup2d_step(cup2d_sim *s, double dt_in, int keep_udef, double tol_abs, double
     if ((rc = cup2d_compute_dt(s, &umax, &dt))) return rc;
   }
   if ((rc = cup2d_advect_diffuse_rk2(s, dt))) return rc;
-  if (!keep_udef) // no bodies: sum of u_def is zero (main.cpp:6980-6983)
+  if (!keep_udef) { // no bodies: sum of u_def is zero (main.cpp:6980-6983)
+    ProfScope prof(s, KC_MEMSET);
     CUP2D_CUDA(cudaMemsetAsync(s->f[CUP2D_TMPV], 0, (size_t)s->nslots * 128 * sizeof(double), s->stream));
+  }
   if ((rc = launch_pressure_rhs(s, dt))) return rc;
   if ((rc = poisson_solve(s, tol_abs, tol_rel, max_restarts, max_iter, iters_out, err_out))) return rc;
   if ((rc = launch_pressure_correct(s, dt))) return rc;

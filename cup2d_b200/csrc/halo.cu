@@ -78,6 +78,7 @@ int halo_exchange_ptr(cup2d_sim *s, double *base, int dim, int peer_index) {
   int grid = (int)((s->nhalo * 32 + 255) / 256);
   if (grid > s->num_sms) grid = s->num_sms;
   if (grid < 1) grid = 1;
+  ProfScope prof(s, KC_HALO);
   halo_pull_kernel<<<grid, 256, 0, s->stream>>>(base, pa, s->comm, reinterpret_cast<const int2 *>(s->d_halo_src),
                                                 (int)s->nhalo, (int)s->nloc, 64 * dim, s->epoch, s->d_counter);
   s->launches++;

@@ -388,8 +388,11 @@ int poisson_solve(cup2d_sim *s, double tol_abs, double tol_rel, int max_restarts
   h->max_iter = max_iter;
   CUP2D_CUDA(cudaMemcpyAsync(s->d_state, h, sizeof *h, cudaMemcpyHostToDevice, s->stream));
   if (s->nranks > 1 && (rc = halo_exchange_ptr(s, s->f[CUP2D_PRES], 1, CUP2D_PRES))) return rc;
+  {
+  ProfScope prof(s, KC_KINIT);
   k_init<<<grid, NT, 0, s->stream>>>(s->f[CUP2D_TMP], s->f[CUP2D_PRES], s->kx[0], s->kr, s->krhat,
                                      s->kp, s->knu, nbr, nrows, s->d_state, s->d_partials, s->d_counter, s->comm);
+  }
   s->launches++;
   const int check_every = (tol_abs > 0 || tol_rel > 0) ? 8 : 64;
   int launched = 0;
@@ -397,13 +400,18 @@ int poisson_solve(cup2d_sim *s, double tol_abs, double tol_rel, int max_restarts
   while (!done) {
     int batch = max_iter - launched < check_every ? max_iter - launched : check_every;
     for (int k = 0; k < batch; k++) {
-      k_pupdate<<<grid, NT, 0, s->stream>>>(s->kr, s->krhat, s->kp, s->knu, s->kz, nrows, s->d_state);
+      { ProfScope prof(s, KC_PUPDATE);
+      k_pupdate<<<grid, NT, 0, s->stream>>>(s->kr, s->krhat, s->kp, s->knu, s->kz, nrows, s->d_state); }
       if (s->nranks > 1 && (rc = halo_exchange_ptr(s, s->kz, 1, CUP2D_NFIELDS))) return rc;
-      k_spmv<0><<<grid, NT, 0, s->stream>>>(s->kz, s->krhat, s->knu, nbr, nrows, s->d_state, s->d_partials, s->d_counter, s->comm);
-      k_xr_update<<<grid, NT, 0, s->stream>>>(s->kx[0], s->kx[1], s->kx[2], s->kz, s->kr, s->knu, s->kz, nrows, s->d_state);
+      { ProfScope prof(s, KC_SPMV_NU);
+      k_spmv<0><<<grid, NT, 0, s->stream>>>(s->kz, s->krhat, s->knu, nbr, nrows, s->d_state, s->d_partials, s->d_counter, s->comm); }
+      { ProfScope prof(s, KC_XRUPDATE);
+      k_xr_update<<<grid, NT, 0, s->stream>>>(s->kx[0], s->kx[1], s->kx[2], s->kz, s->kr, s->knu, s->kz, nrows, s->d_state); }
       if (s->nranks > 1 && (rc = halo_exchange_ptr(s, s->kz, 1, CUP2D_NFIELDS))) return rc;
-      k_spmv<1><<<grid, NT, 0, s->stream>>>(s->kz, s->kr, s->kt, nbr, nrows, s->d_state, s->d_partials, s->d_counter, s->comm);
-      k_final<<<grid, NT, 0, s->stream>>>(s->kx[0], s->kx[1], s->kx[2], s->kz, s->kr, s->kt, s->krhat, nrows, s->d_state, s->d_partials, s->d_counter, s->comm);
+      { ProfScope prof(s, KC_SPMV_T);
+      k_spmv<1><<<grid, NT, 0, s->stream>>>(s->kz, s->kr, s->kt, nbr, nrows, s->d_state, s->d_partials, s->d_counter, s->comm); }
+      { ProfScope prof(s, KC_FINAL);
+      k_final<<<grid, NT, 0, s->stream>>>(s->kx[0], s->kx[1], s->kx[2], s->kz, s->kr, s->kt, s->krhat, nrows, s->d_state, s->d_partials, s->d_counter, s->comm); }
       s->launches += 5;
     }
     launched += batch;

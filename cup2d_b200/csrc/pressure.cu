@@ -51,7 +51,10 @@ __global__ void __launch_bounds__(NT) umax_kernel(const double *__restrict__ vel
 int launch_umax(cup2d_sim *s, double *umax_out) {
   const size_t n4 = (size_t)s->nloc * 128 / 4;
   int grid = s->num_sms * 4;
+  {
+  ProfScope prof(s, KC_UMAX);
   umax_kernel<<<grid, NT, 0, s->stream>>>(s->f[CUP2D_VEL], n4, s->d_partials, s->d_counter, s->comm, s->d_scal);
+  }
   s->launches++;
   CUP2D_CUDA(cudaGetLastError());
   CUP2D_CUDA(cudaMemcpyAsync(s->h_scal, s->d_scal, sizeof(double), cudaMemcpyDeviceToHost, s->stream));
@@ -155,6 +158,7 @@ int launch_pressure_rhs(cup2d_sim *s, double dt) {
   const int nrows = (int)s->nloc * 8;
   const int grid = min((nrows + NT - 1) / NT, s->num_sms * 8);
   const double fac = 0.5 * s->h / dt; // main.cpp:6119
+  ProfScope prof(s, KC_RHS);
   pressure_rhs_kernel<<<grid, NT, 0, s->stream>>>(s->f[CUP2D_VEL], s->f[CUP2D_TMPV], s->f[CUP2D_CHI],
                                                   s->f[CUP2D_POLD], s->f[CUP2D_TMP], s->f[CUP2D_PRES],
                                                   reinterpret_cast<const int4 *>(s->d_nbr), nrows, fac);
@@ -242,6 +246,7 @@ int launch_pressure_correct(cup2d_sim *s, double dt) {
   const int grid = min((nrows + NT - 1) / NT, s->num_sms * 8);
   const double pfac = -0.5 * dt * s->h;          // main.cpp:6028
   const double ih2 = 1.0 / s->h / s->h;          // main.cpp:7182
+  ProfScope prof(s, KC_CORRECT);
   pressure_correct_kernel<<<grid, NT, 0, s->stream>>>(
       x, s->f[CUP2D_POLD], s->f[CUP2D_PRES], s->f[CUP2D_VEL], reinterpret_cast<const int4 *>(s->d_nbr),
       nrows, &s->d_state->xsum, 1.0 / ((double)s->nglobal * 64.0), pfac * ih2);

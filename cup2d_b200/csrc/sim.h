@@ -79,9 +79,33 @@ struct cup2d_sim {
   cup2d::Comm comm = {};               // by-value kernel argument of every reducing kernel
   double **d_peer_ptrs = nullptr;      // device copy of peer_base
   int64_t launches = 0;
+  // optional per-kernel-class CUDA-event instrumentation (cup2d_profile_*)
+  bool prof_on = false;
+  struct ProfRec { int cls; cudaEvent_t a, b; };
+  std::vector<ProfRec> prof;
 };
 
 namespace cup2d {
+enum KClass { KC_ADVECT = 0, KC_UMAX, KC_RHS, KC_CORRECT, KC_KINIT, KC_PUPDATE, KC_SPMV_NU, KC_XRUPDATE,
+              KC_SPMV_T, KC_FINAL, KC_HALO, KC_MEMSET, KC_COUNT };
+// bracket one launch with events when profiling is on (no-op otherwise)
+struct ProfScope {
+  cup2d_sim *s;
+  int idx = -1;
+  ProfScope(cup2d_sim *sim, int cls) : s(sim) {
+    if (!s->prof_on) return;
+    cup2d_sim::ProfRec r;
+    r.cls = cls;
+    cudaEventCreate(&r.a);
+    cudaEventCreate(&r.b);
+    cudaEventRecord(r.a, s->stream);
+    s->prof.push_back(r);
+    idx = (int)s->prof.size() - 1;
+  }
+  ~ProfScope() {
+    if (idx >= 0) cudaEventRecord(s->prof[idx].b, s->stream);
+  }
+};
 int dim_of(int field);
 // operators (host-side launchers; all on s->stream)
 int launch_advect(cup2d_sim *s, const double *in, const double *old, double *out, double coef,

@@ -156,6 +156,20 @@ class Simulation:
     def launch_count(self):
         return self.lib.cup2d_launch_count(self._h)
 
+    def profile(self, on):
+        _l.check(self.lib.cup2d_profile_enable(self._h, int(on)))
+
+    def profile_read(self):
+        """-> {kernel class: (total ms, launches)} since profile(True)."""
+        n = 16
+        names = C.create_string_buffer(32 * n)
+        ms = (C.c_double * n)()
+        cnt = (C.c_int64 * n)()
+        k = self.lib.cup2d_profile_read(self._h, n, names, ms, cnt)
+        if k < 0:
+            _l.check(k)
+        return {names.raw[32 * i:32 * i + 32].split(b"\0")[0].decode(): (ms[i], cnt[i]) for i in range(k)}
+
     @property
     def stream(self):
         return self.lib.cup2d_stream(self._h)

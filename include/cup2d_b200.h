@@ -124,6 +124,11 @@ int cup2d_halo_exchange(cup2d_sim *s, int field);
 /* ---- instrumentation ---- */
 /* number of kernels this library has launched since creation (bench.py's gpu_launches) */
 int64_t cup2d_launch_count(const cup2d_sim *s);
+/* per-kernel-class timing with CUDA events on the launching stream (bench.py's roofline leg).
+ * enable(1) starts a fresh recording, enable(0) stops.  read() synchronises the stream and returns the
+ * number of classes written: names[k*32..] (NUL-terminated), summed milliseconds and launch counts. */
+int cup2d_profile_enable(cup2d_sim *s, int on);
+int cup2d_profile_read(cup2d_sim *s, int max_entries, char *names, double *total_ms, int64_t *launches);
 
 #ifdef __cplusplus
 }

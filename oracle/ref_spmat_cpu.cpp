@@ -31,6 +31,8 @@ public:
   BiCGSTABSolver(LocalSpMatDnVec &ls, int blen, const std::vector<double> &P_inv)
       : ls_(ls), blen_(blen), P_inv_(P_inv) {}
   void run(double max_error, double max_rel_error, int max_restarts);
+  void build_rowptr();
+  std::vector<int> rowptr_;
   int last_iters = 0;
   double last_err = 0;
 
@@ -49,13 +51,31 @@ int cup2d_ref_force_iters = -1; // >=0: cap the loop at this many iterations (ha
 
 void BiCGSTABSolver::spmv(const std::vector<double> &z, std::vector<double> &y) const {
   // cuda.cu:361-363  y = A_loc z   (COO is row-sorted: rows are pushed in order, main.cpp:7051-7111)
-  const int nnz = ls_.loc_nnz_;
+  // Rows are contiguous in the COO, so row i owns entries [rowptr[i], rowptr[i+1]) in push order;
+  // the loop over rows is threaded (the CPU baseline uses every host core, like the operators do).
   const int m = ls_.m_;
   const double *val = ls_.loc_cooValA_.data();
-  const int *row = ls_.loc_cooRowA_int_.data();
   const int *col = ls_.loc_cooColA_int_.data();
-  for (int i = 0; i < m; i++) y[i] = 0;
-  for (int k = 0; k < nnz; k++) y[row[k]] += val[k] * z[col[k]];
+  const int *rp = rowptr_.data();
+#pragma omp parallel for schedule(static)
+  for (int i = 0; i < m; i++) {
+    double s = 0;
+    for (int k = rp[i]; k < rp[i + 1]; k++) s += val[k] * z[col[k]];
+    y[i] = s;
+  }
+}
+void BiCGSTABSolver::build_rowptr() {
+  const int m = ls_.m_, nnz = ls_.loc_nnz_;
+  const int *row = ls_.loc_cooRowA_int_.data();
+  rowptr_.assign(m + 1, 0);
+  for (int k = 0; k < nnz; k++) {
+    if (k > 0 && row[k] < row[k - 1]) {
+      fprintf(stderr, "ref_spmat_cpu: COO not row-sorted\n");
+      abort();
+    }
+    rowptr_[row[k] + 1]++;
+  }
+  for (int i = 0; i < m; i++) rowptr_[i + 1] += rowptr_[i];
 }
 
 void BiCGSTABSolver::precond(const std::vector<double> &v, std::vector<double> &z) const {
@@ -73,11 +93,13 @@ void BiCGSTABSolver::precond(const std::vector<double> &v, std::vector<double> &
 
 static double dot(const std::vector<double> &a, const std::vector<double> &b, int m) {
   double s = 0;
+#pragma omp parallel for reduction(+ : s) schedule(static)
   for (int i = 0; i < m; i++) s += a[i] * b[i];
   return s;
 }
 static double amax(const std::vector<double> &a, int m) {
   double s = 0;
+#pragma omp parallel for reduction(max : s) schedule(static)
   for (int i = 0; i < m; i++) s = std::max(s, std::fabs(a[i]));
   return s;
 }
@@ -121,6 +143,7 @@ void BiCGSTABSolver::run(double max_error, double max_rel_error, int max_restart
       rho_prev = 1; alpha = 1; omega = 1;           // breakdown_update 308-314
       beta = (rho_curr / (rho_prev + eps)) * (alpha / (omega + eps));
     }
+#pragma omp parallel for schedule(static)
     for (int i = 0; i < m; i++) {                   // cuda.cu:478-483
       double pi = p[i] + (-omega) * nu[i];
       pi = beta * pi;
@@ -130,14 +153,20 @@ void BiCGSTABSolver::run(double max_error, double max_rel_error, int max_restart
     spmv(z, nu);                                    // 487
     double rhat_nu = dot(rhat, nu, m);              // 488
     alpha = rho_curr / (rhat_nu + eps);             // set_alpha 319-321
-    for (int i = 0; i < m; i++) x[i] += alpha * z[i];   // 498
-    for (int i = 0; i < m; i++) r[i] += (-alpha) * nu[i]; // 499-502
+#pragma omp parallel for schedule(static)
+    for (int i = 0; i < m; i++) {
+      x[i] += alpha * z[i];      // 498
+      r[i] += (-alpha) * nu[i];  // 499-502
+    }
     precond(r, z);                                  // 503
     spmv(z, t);                                     // 506
     double tr = dot(t, r, m), tt = dot(t, t, m);    // 507-516
     omega = tr / (tt + eps);                        // set_omega 322-324
-    for (int i = 0; i < m; i++) x[i] += omega * z[i];   // 520
-    for (int i = 0; i < m; i++) r[i] += (-omega) * t[i]; // 521-524
+#pragma omp parallel for schedule(static)
+    for (int i = 0; i < m; i++) {
+      x[i] += omega * z[i];      // 520
+      r[i] += (-omega) * t[i];   // 521-524
+    }
     error = amax(r, m);                             // 525-534
     if (error < error_opt) {                        // 535-541
       error_opt = error;
@@ -207,6 +236,7 @@ void LocalSpMatDnVec::make(const std::vector<long long> &Nrows_xcumsum) { // cud
     loc_cooRowA_int_[i] = (int)(loc_cooRowA_long_[i] + shift);
     loc_cooColA_int_[i] = (int)(loc_cooColA_long_[i] + shift);
   }
+  solver_->build_rowptr();
 }
 void LocalSpMatDnVec::solveWithUpdate(const double max_error, const double max_rel_error,
                                       const int max_restarts) {
