@@ -6,21 +6,24 @@
 // main.cpp:3131-3154) become the tile loader of this kernel; the RK update loops
 // (main.cpp:6618-6626, 6634-6642) are fused into the store.
 //
-// One CTA = one tile of 4x4 blocks (32x32 cells).  Data path:
+// One CTA = one tile of 4x4 blocks (32x32 cells), 128 threads, 4 CTAs per SM.  Data path:
 //   HBM --cp.async.bulk (1-D TMA, one 1 KB copy per 8x8 block, mbarrier complete_tx)--> staging smem
 //   staging (AoS, block layout) --repack + ghost synthesis--> padded SoA planes su/sv (38x38, +3 ring)
-//   x pass (lanes = rows, thread = 8 cells of a row)    -> partial result planes Ru/Rv in smem
+//   x pass (lanes = rows, thread = 8 cells of a row)    -> partial result planes Ru/Rv (alias staging)
 //   y pass (lanes = columns, thread = 8 cells of a column) -> + old, 128-bit coalesced stores
 //
-// Arithmetic (all FP64).  Per line the WENO fluxes are shared between neighbouring cells and only
-// the upwind family that some cell needs is evaluated; written in differences D[k] = q[k+1]-q[k]:
-//   beta1 = 13/12 D2(w-1)^2 + 1/4 (3 D[w-1] - D[w-2])^2,  beta2 = 13/12 D2(w)^2 + 1/4 (D[w-1]+D[w])^2,
-//   beta3 = 13/12 D2(w+1)^2 + 1/4 (3 D[w] - D[w+1])^2        (D2(k) = D[k]-D[k-1])
-//   flux(w) = q[w] + (sum_k a_k phi_k)/(sum_k a_k),  a_k = gamma_k (B_j B_l)^2,  B = beta + 1e-6
-// which is the reference's w_k = (gamma_k/B_k^2)/sum with numerator and denominator multiplied by
-// (B1 B2 B3)^2: one division per flux instead of four.  Same real-number result; rounding differs
+// Arithmetic (all FP64; this kernel is bound by the FP64 pipe, not by HBM — see DESIGN.md).  Per line
+// the WENO fluxes are shared between neighbouring cells and only the upwind family that some cell needs
+// is evaluated.  In differences D[k] = q[k+1]-q[k], D2(k) = D[k]-D[k-1], with every smoothness indicator
+// scaled by 4 (the weights are ratios, so a common factor cancels):
+//   B1 = 13/3 D2(w-1)^2 + (3 D[w-1] - D[w-2])^2 + 4e-6,   B2 = 13/3 D2(w)^2 + (D[w-1]+D[w])^2 + 4e-6,
+//   B3 = 13/3 D2(w+1)^2 + (3 D[w] - D[w+1])^2 + 4e-6                      ( = 4 (beta_k + 1e-6) )
+//   flux(w) = q[w] + (sum_k s_k gamma_k phi_k)/(sum_k gamma_k s_k),   s_k = (B_j B_l)^2
+// which is the reference's w_k = (gamma_k/(beta_k+eps)^2)/sum with numerator and denominator multiplied
+// by (B1 B2 B3)^2: one division per flux instead of four.  Same real-number result; rounding differs
 // from the reference's CPU evaluation at the 1e-16 relative level (tests bound it at 1e-12).
 #include "sim.h"
+#include <cstdlib>
 
 namespace cup2d {
 
@@ -31,32 +34,30 @@ constexpr int SP = 39;          // plane row stride (odd: conflict-free for lane
 constexpr int RP = 33;          // partial-result plane stride
 constexpr int NT_ADV = 128;
 constexpr int STG_BYTES = 24 * 1024 + 8 * 384; // 16 interior + 4 W + 4 E blocks, 4 S + 4 N 3-row strips
+constexpr int OFF_RU = 0;                      // Ru/Rv alias the staging area (dead after the repack)
+constexpr int OFF_RV = OFF_RU + TC * RP * 8;
+static_assert(OFF_RV + TC * RP * 8 <= STG_BYTES, "R planes must fit in the staging area");
 constexpr int OFF_SU = STG_BYTES;
 constexpr int OFF_SV = OFF_SU + TW * SP * 8;
-constexpr int OFF_RU = OFF_SV + TW * SP * 8;
-constexpr int OFF_RV = OFF_RU + TC * RP * 8;
-constexpr int OFF_BAR = OFF_RV + TC * RP * 8;
+constexpr int OFF_BAR = OFF_SV + TW * SP * 8;
 constexpr int OFF_SLOTS = OFF_BAR + 16;
-constexpr int ADV_SMEM = OFF_SLOTS + TILE_SLOTS * 4;
+constexpr int ADV_SMEM = OFF_SLOTS + TILE_SLOTS * 4; // 51.5 KB -> 4 CTAs/SM
 
 struct LineState {
   double dm2, dm1, d0, dp1; // D[w-2..w+1]
-  double Gm1, G0, Gp1;      // 13/12 D2^2 + eps at w-1, w, w+1
+  double Gm1, G0, Gp1;      // 13/3 D2^2 + 4e-6 at w-1, w, w+1
   double qlast;             // q[w+2]
   double rP1, rP2, rM1;     // ratioP(w-1), ratioP(w-2), ratioM(w-1)
 };
 
-__device__ __forceinline__ double Gfun(double D2) {
-  const double c = 13.0 / 12.0;
-  return fma(c * D2, D2, 1e-6);
-}
+__device__ __forceinline__ double Gfun(double D2) { return fma((13.0 / 3.0) * D2, D2, 4e-6); }
+
 __device__ __forceinline__ void line_init(LineState &s, const double *q, int es) {
   double q0 = q[0], q1 = q[es], q2 = q[2 * es], q3 = q[3 * es], q4 = q[4 * es];
-  double D0 = q1 - q0;
-  s.dm2 = D0;        // w = 2: D[0]
-  s.dm1 = q2 - q1;   // D[1]
-  s.d0 = q3 - q2;    // D[2]
-  s.dp1 = q4 - q3;   // D[3]
+  s.dm2 = q1 - q0; // w = 2: D[0]
+  s.dm1 = q2 - q1; // D[1]
+  s.d0 = q3 - q2;  // D[2]
+  s.dp1 = q4 - q3; // D[3]
   s.Gm1 = Gfun(s.dm1 - s.dm2);
   s.G0 = Gfun(s.d0 - s.dm1);
   s.Gp1 = Gfun(s.dp1 - s.d0);
@@ -64,36 +65,47 @@ __device__ __forceinline__ void line_init(LineState &s, const double *q, int es)
   s.rP1 = s.rP2 = s.rM1 = 0.0;
 }
 __device__ __forceinline__ void line_betas(const LineState &s, double &s1, double &s2, double &s3) {
-  double e1 = fma(3.0, s.dm1, -s.dm2);
-  double e2 = s.dm1 + s.d0;
-  double e3 = fma(3.0, s.d0, -s.dp1);
-  double B1 = fma(0.25 * e1, e1, s.Gm1);
-  double B2 = fma(0.25 * e2, e2, s.G0);
-  double B3 = fma(0.25 * e3, e3, s.Gp1);
-  double q1 = B2 * B3, q2 = B1 * B3, q3 = B1 * B2;
+  const double e1 = fma(3.0, s.dm1, -s.dm2);
+  const double e2 = s.dm1 + s.d0;
+  const double e3 = fma(3.0, s.d0, -s.dp1);
+  const double B1 = fma(e1, e1, s.Gm1);
+  const double B2 = fma(e2, e2, s.G0);
+  const double B3 = fma(e3, e3, s.Gp1);
+  const double q1 = B2 * B3, q2 = B1 * B3, q3 = B1 * B2;
   s1 = q1 * q1;
   s2 = q2 * q2;
   s3 = q3 * q3;
 }
-// upwind-from-the-left flux ratio at face w+1/2  (weno5_plus, main.cpp:162-181)
-__device__ __forceinline__ double ratio_plus(const LineState &s, double s1, double s2, double s3) {
-  double a1 = 0.1 * s1, a2 = 0.6 * s2, a3 = 0.3 * s3;
-  double den = (a1 + a3) + a2;
-  double p1 = fma(5.0 / 6.0, s.dm1, (-1.0 / 3.0) * s.dm2);
-  double p2 = fma(1.0 / 6.0, s.dm1, (1.0 / 3.0) * s.d0);
-  double p3 = fma(2.0 / 3.0, s.d0, (-1.0 / 6.0) * s.dp1);
-  double num = fma(a1, p1, fma(a3, p3, a2 * p2));
-  return num * fast_rcp_pos(den);
+template <int NEWTON> __device__ __forceinline__ double rcp_pos(double x) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x)); // MUFU.RCP64H seed
+#pragma unroll
+  for (int i = 0; i < NEWTON; i++) {
+    const double e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+  }
+  return r;
 }
-// upwind-from-the-right flux ratio at face w-1/2  (weno5_minus, main.cpp:182-201)
+// upwind-from-the-left flux ratio at face w+1/2 (weno5_plus, main.cpp:162-181; gammas .1,.6,.3 folded
+// into the phi coefficients)
+template <int NEWTON>
+__device__ __forceinline__ double ratio_plus(const LineState &s, double s1, double s2, double s3) {
+  const double den = fma(0.1, s1, fma(0.3, s3, 0.6 * s2));
+  const double p1 = fma(0.1 * 5.0 / 6.0, s.dm1, (-0.1 / 3.0) * s.dm2);
+  const double p2 = fma(0.6 / 6.0, s.dm1, (0.6 / 3.0) * s.d0);
+  const double p3 = fma(0.3 * 2.0 / 3.0, s.d0, (-0.3 / 6.0) * s.dp1);
+  const double num = fma(s1, p1, fma(s3, p3, s2 * p2));
+  return num * rcp_pos<NEWTON>(den);
+}
+// upwind-from-the-right flux ratio at face w-1/2 (weno5_minus, main.cpp:182-201; gammas .3,.6,.1)
+template <int NEWTON>
 __device__ __forceinline__ double ratio_minus(const LineState &s, double s1, double s2, double s3) {
-  double a1 = 0.3 * s1, a2 = 0.6 * s2, a3 = 0.1 * s3;
-  double den = (a1 + a3) + a2;
-  double p1 = fma(-2.0 / 3.0, s.dm1, (1.0 / 6.0) * s.dm2);
-  double p2 = fma(-1.0 / 3.0, s.dm1, (-1.0 / 6.0) * s.d0);
-  double p3 = fma(-5.0 / 6.0, s.d0, (1.0 / 3.0) * s.dp1);
-  double num = fma(a1, p1, fma(a3, p3, a2 * p2));
-  return num * fast_rcp_pos(den);
+  const double den = fma(0.3, s1, fma(0.1, s3, 0.6 * s2));
+  const double p1 = fma(-0.3 * 2.0 / 3.0, s.dm1, (0.3 / 6.0) * s.dm2);
+  const double p2 = fma(-0.6 / 3.0, s.dm1, (-0.6 / 6.0) * s.d0);
+  const double p3 = fma(-0.1 * 5.0 / 6.0, s.d0, (0.1 / 3.0) * s.dp1);
+  const double num = fma(s1, p1, fma(s3, p3, s2 * p2));
+  return num * rcp_pos<NEWTON>(den);
 }
 __device__ __forceinline__ void line_advance(LineState &s, double qn, double rP, double rM) {
   s.rP2 = s.rP1;
@@ -111,19 +123,24 @@ __device__ __forceinline__ void line_advance(LineState &s, double qn, double rP,
 
 // Upwind WENO5 differences of both components along one line of 8 cells (window of 14 values per
 // component, element stride ES).  qa = advecting component (sign + multiplier), qb = the other one.
-// emit(c, U, da, db, D2a, D2b) is called once per cell c = 0..7 with the undivided differences
-// (reference `derivative`, main.cpp:202-208) and the second differences (for the diffusion term).
-template <int ES, class Emit>
+// emit(c, Ua, Ub, da, db, D2a, D2b) is called once per cell c = 0..7 with the cell values, the undivided
+// differences (reference `derivative`, main.cpp:202-208) and the second differences (diffusion term).
+template <int ES, int UNR, int NEWTON, class Emit>
 __device__ __forceinline__ void weno_line(const double *__restrict__ qa,
                                           const double *__restrict__ qb, Emit emit) {
   LineState A, B;
   line_init(A, qa, ES);
   line_init(B, qb, ES);
-  double Um1 = qa[ES], U0 = qa[2 * ES], Up1 = qa[3 * ES];
-#pragma unroll 1
+  // sign of the advecting velocity at window indices 2..12 (bit k <-> index k), one pass, no FP64 pipe
+  unsigned pos = 0;
+#pragma unroll
+  for (int k = 2; k <= 12; k++) pos |= is_pos(qa[k * ES]) ? (1u << k) : 0u;
+  double Ubm1 = qb[2 * ES]; // qb at window index w-1 (cell value of the other component)
+  double Uam1 = qa[2 * ES];
+#pragma unroll UNR
   for (int w = 2; w <= 11; ++w) {
     const bool vc = (unsigned)(w - 3) < 8u, vn = (unsigned)(w - 2) < 8u, vp = (unsigned)(w - 4) < 8u;
-    const bool posc = is_pos(U0), posn = is_pos(Up1), posp = is_pos(Um1);
+    const bool posc = (pos >> w) & 1u, posn = (pos >> (w + 1)) & 1u, posp = (pos >> (w - 1)) & 1u;
     const bool needP = (vc && posc) || (vn && posn);
     const bool needM = (vc && !posc) || (vp && !posp);
     double a1, a2, a3, b1, b2, b3;
@@ -131,12 +148,12 @@ __device__ __forceinline__ void weno_line(const double *__restrict__ qa,
     line_betas(B, b1, b2, b3);
     double rPa = 0, rPb = 0, rMa = 0, rMb = 0;
     if (needP) {
-      rPa = ratio_plus(A, a1, a2, a3);
-      rPb = ratio_plus(B, b1, b2, b3);
+      rPa = ratio_plus<NEWTON>(A, a1, a2, a3);
+      rPb = ratio_plus<NEWTON>(B, b1, b2, b3);
     }
     if (needM) {
-      rMa = ratio_minus(A, a1, a2, a3);
-      rMb = ratio_minus(B, b1, b2, b3);
+      rMa = ratio_minus<NEWTON>(A, a1, a2, a3);
+      rMb = ratio_minus<NEWTON>(B, b1, b2, b3);
     }
     if (vp) { // finalize cell c = w-4 (window index w-1)
       double da, db;
@@ -147,21 +164,22 @@ __device__ __forceinline__ void weno_line(const double *__restrict__ qa,
         da = A.dm1 + (rMa - A.rM1);
         db = B.dm1 + (rMb - B.rM1);
       }
-      emit(w - 4, Um1, da, db, A.dm1 - A.dm2, B.dm1 - B.dm2);
+      emit(w - 4, Uam1, Ubm1, da, db, A.dm1 - A.dm2, B.dm1 - B.dm2);
     }
     if (w < 11) {
-      double qna = qa[(w + 3) * ES], qnb = qb[(w + 3) * ES];
-      Um1 = U0;
-      U0 = Up1;
-      Up1 = A.qlast;
+      // q[w] of both components = q[w+1] - D[w]; cheaper: reload from shared memory
+      Uam1 = qa[w * ES];
+      Ubm1 = qb[w * ES];
+      const double qna = qa[(w + 3) * ES], qnb = qb[(w + 3) * ES];
       line_advance(A, qna, rPa, rMa);
       line_advance(B, qnb, rPb, rMb);
     }
   }
 }
 
-template <bool RAW, bool OLD_IS_IN>
-__global__ void __launch_bounds__(NT_ADV, 3)
+// MODE 0: out = tot (raw K, undivided)   1: old == in (stage 1)   2: old is a separate field (stage 2)
+template <int MODE, int UNR, int NEWTON>
+__global__ void __launch_bounds__(NT_ADV, 4)
 advect_stage_kernel(const double *__restrict__ in, const double *__restrict__ old,
                     double *__restrict__ out, const int *__restrict__ tiles,
                     const int *__restrict__ tile_org, int nbx, int nby, int nloc, double afac,
@@ -200,6 +218,17 @@ advect_stage_kernel(const double *__restrict__ in, const double *__restrict__ ol
       tma_load_1d(dst, src, bytes, bar);
     }
   }
+  // y-pass ownership (known now, so the `old` loads of stage 2 can be in flight during everything else)
+  const int yx = lane, ys = warp;
+  const int yb = ys * 4 + (yx >> 3);
+  const int yslot = s_slots[yb];
+  const bool store = yslot >= 0 && yslot < nloc;
+  double2 oldv[8];
+  if (MODE == 2) {
+    const double2 *oldp = reinterpret_cast<const double2 *>(old) + (size_t)(store ? yslot : 0) * 64 + (yx & 7);
+#pragma unroll
+    for (int c = 0; c < 8; c++) oldv[c] = store ? oldp[c * 8] : make_double2(0.0, 0.0);
+  }
   const int gx0 = tile_org[2 * tile] * CUP2D_BS, gy0 = tile_org[2 * tile + 1] * CUP2D_BS;
   const int NX = nbx * CUP2D_BS, NY = nby * CUP2D_BS;
   mbar_wait(bar, 0);
@@ -231,7 +260,7 @@ advect_stage_kernel(const double *__restrict__ in, const double *__restrict__ ol
     su[ty * SP + tx] = sgu * v.x;
     sv[ty * SP + tx] = sgv * v.y;
   }
-  __syncthreads();
+  __syncthreads(); // staging is dead from here on: Ru/Rv reuse it
 
   // ---- stage 2: x pass. lanes = rows; thread = 8 consecutive cells of one row ----
   {
@@ -239,7 +268,7 @@ advect_stage_kernel(const double *__restrict__ in, const double *__restrict__ ol
     const double *qa = su + (r + GH) * SP + 8 * xs; // window index 0 <-> cell x0-3
     const double *qb = sv + (r + GH) * SP + 8 * xs;
     double *ru = Ru + r * RP + 8 * xs, *rv = Rv + r * RP + 8 * xs;
-    weno_line<1>(qa, qb, [&](int c, double U, double du, double dv, double D2u, double D2v) {
+    weno_line<1, UNR, NEWTON>(qa, qb, [&](int c, double U, double, double du, double dv, double D2u, double D2v) {
       const double aU = afac * U;
       ru[c] = fma(aU, du, dfac * D2u); // afac*u*dudx + dfac*(u_E + u_W - 2u)
       rv[c] = fma(aU, dv, dfac * D2v);
@@ -249,29 +278,25 @@ advect_stage_kernel(const double *__restrict__ in, const double *__restrict__ ol
 
   // ---- stage 3: y pass. lanes = columns; thread = 8 consecutive cells of one column = one block ----
   {
-    const int x = lane, ys = warp;
-    const double *qa = sv + (8 * ys) * SP + (x + GH); // advecting component is v
-    const double *qb = su + (8 * ys) * SP + (x + GH);
-    const int b = ys * 4 + (x >> 3);
-    const int slot = s_slots[b];
-    const bool store = slot >= 0 && slot < nloc;
-    const double2 *oldp = OLD_IS_IN ? (stg + b * 64 + (x & 7))
-                                    : (reinterpret_cast<const double2 *>(old) + (size_t)(store ? slot : 0) * 64 + (x & 7));
-    double2 *outp = reinterpret_cast<double2 *>(out) + (size_t)(store ? slot : 0) * 64 + (x & 7);
-    const double *ru = Ru + (8 * ys) * RP + x, *rv = Rv + (8 * ys) * RP + x;
-    weno_line<SP>(qa, qb, [&](int c, double V, double dv, double du, double D2v, double D2u) {
+    const double *qa = sv + (8 * ys) * SP + (yx + GH); // advecting component is v
+    const double *qb = su + (8 * ys) * SP + (yx + GH);
+    double2 *outp = reinterpret_cast<double2 *>(out) + (size_t)(store ? yslot : 0) * 64 + (yx & 7);
+    const double *ru = Ru + (8 * ys) * RP + yx, *rv = Rv + (8 * ys) * RP + yx;
+    weno_line<SP, UNR, NEWTON>(qa, qb, [&](int c, double V, double Uc, double dv, double du, double D2v, double D2u) {
       const double aV = afac * V;
       const double tu = ru[c * RP] + fma(aV, du, dfac * D2u);
       const double tv = rv[c * RP] + fma(aV, dv, dfac * D2v);
       if (store) {
         double2 o;
-        if (RAW) {
+        if (MODE == 0) {
           o.x = tu;
           o.y = tv;
+        } else if (MODE == 1) { // old == in: the cell values are already in registers
+          o.x = fma(ofac, tu, Uc);
+          o.y = fma(ofac, tv, V);
         } else {
-          const double2 ov = oldp[c * 8];
-          o.x = fma(ofac, tu, ov.x); // V = Vold + coef*tmpV/h^2, main.cpp:6618-6626
-          o.y = fma(ofac, tv, ov.y);
+          o.x = fma(ofac, tu, oldv[c].x); // V = Vold + coef*tmpV/h^2, main.cpp:6618-6626
+          o.y = fma(ofac, tv, oldv[c].y);
         }
         outp[c * 8] = o;
       }
@@ -279,26 +304,57 @@ advect_stage_kernel(const double *__restrict__ in, const double *__restrict__ ol
   }
 }
 
+typedef void (*adv_fn)(const double *, const double *, double *, const int *, const int *, int, int, int,
+                       double, double, double);
+template <int UNR, int NEWTON> static adv_fn pick_mode(int mode) {
+  switch (mode) {
+  case 0: return advect_stage_kernel<0, UNR, NEWTON>;
+  case 1: return advect_stage_kernel<1, UNR, NEWTON>;
+  default: return advect_stage_kernel<2, UNR, NEWTON>;
+  }
+}
+static adv_fn pick(int mode, int unr, int newton) {
+  if (newton == 1) {
+    switch (unr) {
+    case 1: return pick_mode<1, 1>(mode);
+    case 2: return pick_mode<2, 1>(mode);
+    case 5: return pick_mode<5, 1>(mode);
+    default: return pick_mode<10, 1>(mode);
+    }
+  }
+  switch (unr) {
+  case 1: return pick_mode<1, 2>(mode);
+  case 2: return pick_mode<2, 2>(mode);
+  case 5: return pick_mode<5, 2>(mode);
+  default: return pick_mode<10, 2>(mode);
+  }
+}
+
 int launch_advect(cup2d_sim *s, const double *in, const double *old, double *out, double coef,
                   double dt, bool raw) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    CUP2D_CUDA(cudaFuncSetAttribute(advect_stage_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ADV_SMEM));
-    CUP2D_CUDA(cudaFuncSetAttribute(advect_stage_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ADV_SMEM));
-    CUP2D_CUDA(cudaFuncSetAttribute(advect_stage_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ADV_SMEM));
-    attr_set = true;
+  // tuning knobs (profiles/README.md records the sweep): loop unroll factor and Newton steps of the
+  // reciprocal; the defaults are the measured best
+  static int unr = -1, newton = -1;
+  if (unr < 0) {
+    const char *e = getenv("CUP2D_ADV_UNROLL");
+    unr = e ? atoi(e) : 10;
+    e = getenv("CUP2D_ADV_NEWTON");
+    newton = e ? atoi(e) : 2;
   }
-  const double afac = -dt * s->h;    // main.cpp:5447
-  const double dfac = s->nu * dt;    // main.cpp:5446
+  const int mode = raw ? 0 : (old == in ? 1 : 2);
+  adv_fn fn = pick(mode, unr, newton);
+  static bool configured[3] = {false, false, false};
+  if (!configured[mode]) {
+    CUP2D_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, ADV_SMEM));
+    configured[mode] = true;
+  }
+  const double afac = -dt * s->h; // main.cpp:5447
+  const double dfac = s->nu * dt; // main.cpp:5446
   const double ofac = coef / (s->h * s->h);
   dim3 grid(s->ntiles), block(NT_ADV);
   ProfScope prof(s, KC_ADVECT);
-  if (raw)
-    advect_stage_kernel<true, true><<<grid, block, ADV_SMEM, s->stream>>>(in, in, out, s->d_tiles, s->d_tile_org, s->nbx, s->nby, (int)s->nloc, afac, dfac, ofac);
-  else if (old == in)
-    advect_stage_kernel<false, true><<<grid, block, ADV_SMEM, s->stream>>>(in, in, out, s->d_tiles, s->d_tile_org, s->nbx, s->nby, (int)s->nloc, afac, dfac, ofac);
-  else
-    advect_stage_kernel<false, false><<<grid, block, ADV_SMEM, s->stream>>>(in, old, out, s->d_tiles, s->d_tile_org, s->nbx, s->nby, (int)s->nloc, afac, dfac, ofac);
+  fn<<<grid, block, ADV_SMEM, s->stream>>>(in, old, out, s->d_tiles, s->d_tile_org, s->nbx, s->nby,
+                                           (int)s->nloc, afac, dfac, ofac);
   s->launches++;
   CUP2D_CUDA(cudaGetLastError());
   return CUP2D_OK;

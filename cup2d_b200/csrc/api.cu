@@ -449,7 +449,7 @@ int cup2d_pressure_rhs(cup2d_sim *s, double dt) {
   CUP2D_CUDA(cudaSetDevice(s->device));
   int rc = need_peers(s);
   if (rc) return rc;
-  return launch_pressure_rhs(s, dt);
+  return launch_pressure_rhs(s, dt, true);
 }
 int cup2d_poisson_solve(cup2d_sim *s, double tol_abs, double tol_rel, int max_restarts, int max_iter,
                         int *iters, double *err) {
@@ -483,11 +483,10 @@ int cup2d_step(cup2d_sim *s, double dt_in, int keep_udef, double tol_abs, double
     if ((rc = cup2d_compute_dt(s, &umax, &dt))) return rc;
   }
   if ((rc = cup2d_advect_diffuse_rk2(s, dt))) return rc;
-  if (!keep_udef) { // no bodies: sum of u_def is zero (main.cpp:6980-6983)
-    ProfScope prof(s, KC_MEMSET);
-    CUP2D_CUDA(cudaMemsetAsync(s->f[CUP2D_TMPV], 0, (size_t)s->nslots * 128 * sizeof(double), s->stream));
-  }
-  if ((rc = launch_pressure_rhs(s, dt))) return rc;
+  // keep_udef = 0: no bodies, the sum of u_def is identically zero (main.cpp:6980-6983), so the RHS
+  // kernel skips the chi*div(u_def) term instead of reading a zeroed field (tmpV keeps RK scratch).
+  // keep_udef = 1: the caller uploaded chi and the summed u_def into tmpV after the RK2 stages.
+  if ((rc = launch_pressure_rhs(s, dt, keep_udef != 0))) return rc;
   if ((rc = poisson_solve(s, tol_abs, tol_rel, max_restarts, max_iter, iters_out, err_out))) return rc;
   if ((rc = launch_pressure_correct(s, dt))) return rc;
   if (dt_out) *dt_out = dt;

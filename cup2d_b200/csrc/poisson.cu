@@ -15,16 +15,20 @@
 //     x_opt snapshot (cuda.cu:537) is a rotation among three x buffers, and convergence is a device
 //     flag that turns the remaining launches into no-ops.
 // Traffic per iteration: 25 doubles/cell = 200 B/cell.
+// Memory access: warp-cooperative coalesced rows through padded shared memory (rows.cuh).
+#include "rows.cuh"
 #include "sim.h"
 #include <cmath>
 
 namespace cup2d {
 
 constexpr int NT = 256;
-constexpr double EPS21 = 1e-21; // cuda.cu:409
+constexpr int WPB = NT / 32;
+constexpr int SCR1 = 32 * RS1 * 2; // per-warp scratch (doubles) for scalar rows; >= 288 (preconditioner)
+constexpr double EPS21 = 1e-21;    // cuda.cu:409
 
-__constant__ double cQ[64];   // Q[i*8+k]
-__constant__ double cIL[64];  // -1/(lambda_m + lambda_k)
+__constant__ double cQ[64];  // Q[i*8+k]
+__constant__ double cIL[64]; // -1/(lambda_m + lambda_k)
 
 static bool g_consts_ready = false;
 static int init_consts() {
@@ -42,49 +46,8 @@ static int init_consts() {
   return CUP2D_OK;
 }
 
-__device__ __forceinline__ void load_row(const double *__restrict__ f, int slot, int y, double (&c)[8]) {
-  const double4 *p = reinterpret_cast<const double4 *>(f + (size_t)slot * 64 + y * 8);
-  double4 a = p[0], b = p[1];
-  c[0] = a.x; c[1] = a.y; c[2] = a.z; c[3] = a.w;
-  c[4] = b.x; c[5] = b.y; c[6] = b.z; c[7] = b.w;
-}
-__device__ __forceinline__ void store_row(double *__restrict__ f, int slot, int y, const double (&c)[8]) {
-  double4 *p = reinterpret_cast<double4 *>(f + (size_t)slot * 64 + y * 8);
-  p[0] = make_double4(c[0], c[1], c[2], c[3]);
-  p[1] = make_double4(c[4], c[5], c[6], c[7]);
-}
-
-// y = A z on one block row: neighbours S,W,C,E,N (main.cpp:7075-7087); at a wall the missing
-// neighbour is omitted and the diagonal is -(number of neighbours) (main.cpp:7100-7107), i.e. the
-// ghost equals the cell itself.
-__device__ __forceinline__ void lap_row(const double *__restrict__ z, int slot, int y, const int4 nb,
-                                        double (&out)[8]) {
-  double c[8], up[8], dn[8];
-  load_row(z, slot, y, c);
-  const double gW = nb.x >= 0 ? z[(size_t)nb.x * 64 + y * 8 + 7] : c[0];
-  const double gE = nb.y >= 0 ? z[(size_t)nb.y * 64 + y * 8 + 0] : c[7];
-  if (y < 7) load_row(z, slot, y + 1, up);
-  else if (nb.w >= 0) load_row(z, nb.w, 0, up);
-  else {
-#pragma unroll
-    for (int i = 0; i < 8; i++) up[i] = c[i];
-  }
-  if (y > 0) load_row(z, slot, y - 1, dn);
-  else if (nb.z >= 0) load_row(z, nb.z, 7, dn);
-  else {
-#pragma unroll
-    for (int i = 0; i < 8; i++) dn[i] = c[i];
-  }
-#pragma unroll
-  for (int i = 0; i < 8; i++) {
-    const double e = i < 7 ? c[i + 1] : gE;
-    const double w = i > 0 ? c[i - 1] : gW;
-    out[i] = (((dn[i] + w) + e) + up[i]) - 4.0 * c[i];
-  }
-}
-
 // z_blk = P_inv v_blk for the block whose row `y` this lane holds (8 lanes = one block).
-// sw: per-warp scratch of 4*72 doubles.  All 32 lanes must call.
+// sw: per-warp scratch (>= 4*72 doubles).  All 32 lanes must call.
 __device__ __forceinline__ void precond_row(double (&v)[8], double *sw, int lane) {
   const int y = lane & 7, bl = lane >> 3;
   double *sb = sw + bl * 72;
@@ -138,24 +101,29 @@ __device__ __forceinline__ int next_buf(int cur, int opt) { return cur != opt ? 
 __device__ void prepare_iteration(KrylovState *st, double rho_new, double nr2) {
   st->rho_curr = rho_new;
   st->nr2 = nr2;
-  const bool breakdown = rho_new * rho_new < 1e-16 * nr2 * st->nrh2;                        // 452-454
-  st->beta = (st->rho_curr / (st->rho_prev + EPS21)) * (st->alpha / (st->omega + EPS21));   // set_beta
+  const bool breakdown = rho_new * rho_new < 1e-16 * nr2 * st->nrh2;                      // 452-454
+  st->beta = (st->rho_curr / (st->rho_prev + EPS21)) * (st->alpha / (st->omega + EPS21)); // set_beta
   st->restart_now = 0;
-  if (breakdown && st->max_restarts > 0) {                                                  // 457-477
+  if (breakdown && st->max_restarts > 0) { // 457-477
     st->restarts++;
     if (st->restarts >= st->max_restarts) {
       st->done = 1;
       return;
     }
-    st->restart_now = 1;   // K1: rhat = r, p = r (p = nu = 0 then p = beta*0 + r)
-    st->rho_curr = nr2;    // nrm2(rhat)^2 with rhat = r
+    st->restart_now = 1; // K1: rhat = r, p = r (p = nu = 0 then p = beta*0 + r)
+    st->rho_curr = nr2;  // nrm2(rhat)^2 with rhat = r
     st->nrh2 = nr2;
-    st->rho_prev = 1.0;    // breakdown_update, cuda.cu:308-314
+    st->rho_prev = 1.0;  // breakdown_update, cuda.cu:308-314
     st->alpha = 1.0;
     st->omega = 1.0;
     st->beta = (st->rho_curr / (st->rho_prev + EPS21)) * (st->alpha / (st->omega + EPS21));
   }
 }
+
+#define CHUNK_LOOP()                                                                              \
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;                                     \
+  double *sw = s_scr + warp * SCR1;                                                               \
+  for (int row0 = (blockIdx.x * WPB + warp) * 32; row0 < nrows; row0 += gridDim.x * WPB * 32)
 
 // ---- K0: r = b - A x0 ; rhat = r ; p = nu = 0 ; x[0] = x0 ; err0, |r|^2, sum(x0) -----------------
 __global__ void __launch_bounds__(NT)
@@ -163,15 +131,14 @@ k_init(const double *__restrict__ b, const double *__restrict__ x0, double *__re
        double *__restrict__ r, double *__restrict__ rhat, double *__restrict__ p,
        double *__restrict__ nu, const int4 *__restrict__ nbr, int nrows, KrylovState *st,
        double *partials, unsigned int *counter, Comm comm) {
+  __shared__ double s_scr[WPB * SCR1];
   double sums[2] = {0, 0}; // |r|^2, sum x0
   double mx = 0;
-  for (int row = blockIdx.x * NT + threadIdx.x; row < nrows; row += gridDim.x * NT) {
-    const int slot = row >> 3, y = row & 7;
-    const int4 nb = nbr[slot];
-    double ax[8], bb[8], xx[8], zero[8];
-    lap_row(x0, slot, y, nb, ax);
-    load_row(b, slot, y, bb);
-    load_row(x0, slot, y, xx);
+  CHUNK_LOOP() {
+    const int nv = min(32, nrows - row0);
+    double xx[8], ax[8], bb[8], zero[8];
+    rows_lap(x0, row0, nv, nbr, sw, lane, xx, ax);
+    rows_load1(b, row0, nv, sw, lane, bb);
 #pragma unroll
     for (int i = 0; i < 8; i++) {
       bb[i] -= ax[i];
@@ -180,14 +147,14 @@ k_init(const double *__restrict__ b, const double *__restrict__ x0, double *__re
       mx = fmax(mx, fabs(bb[i]));
       zero[i] = 0.0;
     }
-    store_row(r, slot, y, bb);
-    store_row(rhat, slot, y, bb);
-    store_row(x, slot, y, xx);
-    store_row(p, slot, y, zero);
-    store_row(nu, slot, y, zero);
+    rows_store1(r, row0, nv, sw, lane, bb);
+    rows_store1(rhat, row0, nv, sw, lane, bb);
+    rows_store1(x, row0, nv, sw, lane, xx);
+    rows_store1(p, row0, nv, sw, lane, zero);
+    rows_store1(nu, row0, nv, sw, lane, zero);
   }
   grid_reduce<2, NT>(sums, mx, partials, counter, comm, [=](const double *t, double m) {
-    st->err = st->err_init = st->err_opt = m;   // cuda.cu:428-430
+    st->err = st->err_init = st->err_opt = m; // cuda.cu:428-430
     st->xsum = t[1];
     st->nrh2 = t[0];
     st->iter = 0;
@@ -201,38 +168,28 @@ __global__ void __launch_bounds__(NT)
 k_pupdate(const double *__restrict__ r, double *__restrict__ rhat, double *__restrict__ p,
           const double *__restrict__ nu, double *__restrict__ z, int nrows,
           const KrylovState *__restrict__ st) {
-  __shared__ double s_tr[(NT / 32) * 288];
+  __shared__ double s_scr[WPB * SCR1];
   if (st->done) return;
   const double beta = st->beta, nomega = -st->omega;
   const bool restart = st->restart_now != 0;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  double *sw = s_tr + warp * 288;
-  for (int base = blockIdx.x * NT + warp * 32; base < nrows; base += gridDim.x * NT) {
-    const int row = base + lane;
-    const bool act = row < nrows;
-    const int slot = row >> 3, y = row & 7;
-    double pp[8];
-    if (act) {
-      double rr[8];
-      load_row(r, slot, y, rr);
-      if (restart) {
-        store_row(rhat, slot, y, rr);
+  CHUNK_LOOP() {
+    const int nv = min(32, nrows - row0);
+    double pp[8], rr[8];
+    rows_load1(r, row0, nv, sw, lane, rr);
+    if (restart) {
+      rows_store1(rhat, row0, nv, sw, lane, rr);
 #pragma unroll
-        for (int i = 0; i < 8; i++) pp[i] = rr[i];
-      } else {
-        double nn[8];
-        load_row(p, slot, y, pp);
-        load_row(nu, slot, y, nn);
-#pragma unroll
-        for (int i = 0; i < 8; i++) pp[i] = fma(beta, fma(nomega, nn[i], pp[i]), rr[i]);
-      }
-      store_row(p, slot, y, pp);
+      for (int i = 0; i < 8; i++) pp[i] = rr[i];
     } else {
+      double nn[8];
+      rows_load1(p, row0, nv, sw, lane, pp);
+      rows_load1(nu, row0, nv, sw, lane, nn);
 #pragma unroll
-      for (int i = 0; i < 8; i++) pp[i] = 0.0;
+      for (int i = 0; i < 8; i++) pp[i] = fma(beta, fma(nomega, nn[i], pp[i]), rr[i]);
     }
+    rows_store1(p, row0, nv, sw, lane, pp);
     precond_row(pp, sw, lane);
-    if (act) store_row(z, slot, y, pp);
+    rows_store1(z, row0, nv, sw, lane, pp);
   }
 }
 
@@ -244,20 +201,20 @@ __global__ void __launch_bounds__(NT)
 k_spmv(const double *__restrict__ z, const double *__restrict__ d, double *__restrict__ yout,
        const int4 *__restrict__ nbr, int nrows, KrylovState *st, double *partials,
        unsigned int *counter, Comm comm) {
+  __shared__ double s_scr[WPB * SCR1];
   if (st->done) return;
   double sums[2] = {0, 0};
-  for (int row = blockIdx.x * NT + threadIdx.x; row < nrows; row += gridDim.x * NT) {
-    const int slot = row >> 3, y = row & 7;
-    const int4 nb = nbr[slot];
-    double az[8], dd[8];
-    lap_row(z, slot, y, nb, az);
-    load_row(d, slot, y, dd);
+  CHUNK_LOOP() {
+    const int nv = min(32, nrows - row0);
+    double zz[8], az[8], dd[8];
+    rows_lap(z, row0, nv, nbr, sw, lane, zz, az);
+    rows_load1(d, row0, nv, sw, lane, dd);
 #pragma unroll
     for (int i = 0; i < 8; i++) {
       sums[0] = fma(az[i], dd[i], sums[0]);
       if (MODE == 1) sums[1] = fma(az[i], az[i], sums[1]);
     }
-    store_row(yout, slot, y, az);
+    rows_store1(yout, row0, nv, sw, lane, az);
   }
   grid_reduce<2, NT>(sums, 0.0, partials, counter, comm, [=](const double *t, double) {
     if (MODE == 0) {
@@ -267,48 +224,37 @@ k_spmv(const double *__restrict__ z, const double *__restrict__ d, double *__res
     } else {
       st->tr = t[0];
       st->tt = t[1];
-      st->omega = t[0] / (t[1] + EPS21);         // set_omega
+      st->omega = t[0] / (t[1] + EPS21); // set_omega
     }
   });
 }
 
 // ---- K3: x' = x + alpha z ; r -= alpha nu ; z = M r     (cuda.cu:498-505) -------------------------
 __global__ void __launch_bounds__(NT)
-k_xr_update(double *x0, double *x1, double *x2, const double *zin,
-            double *__restrict__ r, const double *__restrict__ nu, double *zout,
-            int nrows, const KrylovState *__restrict__ st) {
-  __shared__ double s_tr[(NT / 32) * 288];
+k_xr_update(double *x0, double *x1, double *x2, const double *zin, double *__restrict__ r,
+            const double *__restrict__ nu, double *zout, int nrows,
+            const KrylovState *__restrict__ st) {
+  __shared__ double s_scr[WPB * SCR1];
   if (st->done) return;
   const double alpha = st->alpha;
   const int cur = st->cur, nxt = next_buf(st->cur, st->opt);
   const double *xc = cur == 0 ? x0 : (cur == 1 ? x1 : x2);
   double *xn = nxt == 0 ? x0 : (nxt == 1 ? x1 : x2);
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  double *sw = s_tr + warp * 288;
-  for (int base = blockIdx.x * NT + warp * 32; base < nrows; base += gridDim.x * NT) {
-    const int row = base + lane;
-    const bool act = row < nrows;
-    const int slot = row >> 3, y = row & 7;
-    double rr[8];
-    if (act) {
-      double xx[8], zz[8], nn[8];
-      load_row(xc, slot, y, xx);
-      load_row(zin, slot, y, zz);
-      load_row(r, slot, y, rr);
-      load_row(nu, slot, y, nn);
+  CHUNK_LOOP() {
+    const int nv = min(32, nrows - row0);
+    double xx[8], zz[8], rr[8], nn[8];
+    rows_load1(xc, row0, nv, sw, lane, xx);
+    rows_load1(zin, row0, nv, sw, lane, zz);
 #pragma unroll
-      for (int i = 0; i < 8; i++) {
-        xx[i] = fma(alpha, zz[i], xx[i]);
-        rr[i] = fma(-alpha, nn[i], rr[i]);
-      }
-      store_row(xn, slot, y, xx);
-      store_row(r, slot, y, rr);
-    } else {
+    for (int i = 0; i < 8; i++) xx[i] = fma(alpha, zz[i], xx[i]);
+    rows_store1(xn, row0, nv, sw, lane, xx);
+    rows_load1(r, row0, nv, sw, lane, rr);
+    rows_load1(nu, row0, nv, sw, lane, nn);
 #pragma unroll
-      for (int i = 0; i < 8; i++) rr[i] = 0.0;
-    }
+    for (int i = 0; i < 8; i++) rr[i] = fma(-alpha, nn[i], rr[i]);
+    rows_store1(r, row0, nv, sw, lane, rr);
     precond_row(rr, sw, lane);
-    if (act) store_row(zout, slot, y, rr);
+    rows_store1(zout, row0, nv, sw, lane, rr);
   }
 }
 
@@ -317,37 +263,41 @@ __global__ void __launch_bounds__(NT)
 k_final(double *x0, double *x1, double *x2, const double *__restrict__ z, double *__restrict__ r,
         const double *__restrict__ t, const double *__restrict__ rhat, int nrows, KrylovState *st,
         double *partials, unsigned int *counter, Comm comm) {
+  __shared__ double s_scr[WPB * SCR1];
   if (st->done) return;
   const double omega = st->omega;
   const int nxt = next_buf(st->cur, st->opt);
   double *xn = nxt == 0 ? x0 : (nxt == 1 ? x1 : x2);
   double sums[3] = {0, 0, 0}; // rhat.r, r.r, sum x
   double mx = 0;
-  for (int row = blockIdx.x * NT + threadIdx.x; row < nrows; row += gridDim.x * NT) {
-    const int slot = row >> 3, y = row & 7;
-    double xx[8], zz[8], rr[8], tt[8], hh[8];
-    load_row(xn, slot, y, xx);
-    load_row(z, slot, y, zz);
-    load_row(r, slot, y, rr);
-    load_row(t, slot, y, tt);
-    load_row(rhat, slot, y, hh);
+  CHUNK_LOOP() {
+    const int nv = min(32, nrows - row0);
+    double xx[8], zz[8], rr[8], tt[8];
+    rows_load1(xn, row0, nv, sw, lane, xx);
+    rows_load1(z, row0, nv, sw, lane, zz);
 #pragma unroll
     for (int i = 0; i < 8; i++) {
-      xx[i] = fma(omega, zz[i], xx[i]);       // cuda.cu:520
-      rr[i] = fma(-omega, tt[i], rr[i]);      // cuda.cu:524
-      sums[0] = fma(hh[i], rr[i], sums[0]);
-      sums[1] = fma(rr[i], rr[i], sums[1]);
+      xx[i] = fma(omega, zz[i], xx[i]); // cuda.cu:520
       sums[2] += xx[i];
+    }
+    rows_store1(xn, row0, nv, sw, lane, xx);
+    rows_load1(r, row0, nv, sw, lane, rr);
+    rows_load1(t, row0, nv, sw, lane, tt);
+    rows_load1(rhat, row0, nv, sw, lane, zz);
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      rr[i] = fma(-omega, tt[i], rr[i]); // cuda.cu:524
+      sums[0] = fma(zz[i], rr[i], sums[0]);
+      sums[1] = fma(rr[i], rr[i], sums[1]);
       mx = fmax(mx, fabs(rr[i]));
     }
-    store_row(xn, slot, y, xx);
-    store_row(r, slot, y, rr);
+    rows_store1(r, row0, nv, sw, lane, rr);
   }
   grid_reduce<3, NT>(sums, mx, partials, counter, comm, [=](const double *tsum, double m) {
     st->iter++;
     st->err = m;
     st->cur = nxt;
-    if (m < st->err_opt) {                                            // cuda.cu:535-541
+    if (m < st->err_opt) { // cuda.cu:535-541
       st->err_opt = m;
       st->opt = nxt;
       st->xsum = tsum[2];
@@ -356,8 +306,8 @@ k_final(double *x0, double *x1, double *x2, const double *__restrict__ z, double
         return;
       }
     }
-    st->rho_prev = st->rho_curr;                                      // set_rho
-    if (st->iter >= st->max_iter) {                                   // cuda.cu:438
+    st->rho_prev = st->rho_curr; // set_rho
+    if (st->iter >= st->max_iter) { // cuda.cu:438
       st->done = 1;
       return;
     }
@@ -389,9 +339,10 @@ int poisson_solve(cup2d_sim *s, double tol_abs, double tol_rel, int max_restarts
   CUP2D_CUDA(cudaMemcpyAsync(s->d_state, h, sizeof *h, cudaMemcpyHostToDevice, s->stream));
   if (s->nranks > 1 && (rc = halo_exchange_ptr(s, s->f[CUP2D_PRES], 1, CUP2D_PRES))) return rc;
   {
-  ProfScope prof(s, KC_KINIT);
-  k_init<<<grid, NT, 0, s->stream>>>(s->f[CUP2D_TMP], s->f[CUP2D_PRES], s->kx[0], s->kr, s->krhat,
-                                     s->kp, s->knu, nbr, nrows, s->d_state, s->d_partials, s->d_counter, s->comm);
+    ProfScope prof(s, KC_KINIT);
+    k_init<<<grid, NT, 0, s->stream>>>(s->f[CUP2D_TMP], s->f[CUP2D_PRES], s->kx[0], s->kr, s->krhat,
+                                       s->kp, s->knu, nbr, nrows, s->d_state, s->d_partials,
+                                       s->d_counter, s->comm);
   }
   s->launches++;
   const int check_every = (tol_abs > 0 || tol_rel > 0) ? 8 : 64;
@@ -400,18 +351,33 @@ int poisson_solve(cup2d_sim *s, double tol_abs, double tol_rel, int max_restarts
   while (!done) {
     int batch = max_iter - launched < check_every ? max_iter - launched : check_every;
     for (int k = 0; k < batch; k++) {
-      { ProfScope prof(s, KC_PUPDATE);
-      k_pupdate<<<grid, NT, 0, s->stream>>>(s->kr, s->krhat, s->kp, s->knu, s->kz, nrows, s->d_state); }
+      {
+        ProfScope prof(s, KC_PUPDATE);
+        k_pupdate<<<grid, NT, 0, s->stream>>>(s->kr, s->krhat, s->kp, s->knu, s->kz, nrows, s->d_state);
+      }
       if (s->nranks > 1 && (rc = halo_exchange_ptr(s, s->kz, 1, CUP2D_NFIELDS))) return rc;
-      { ProfScope prof(s, KC_SPMV_NU);
-      k_spmv<0><<<grid, NT, 0, s->stream>>>(s->kz, s->krhat, s->knu, nbr, nrows, s->d_state, s->d_partials, s->d_counter, s->comm); }
-      { ProfScope prof(s, KC_XRUPDATE);
-      k_xr_update<<<grid, NT, 0, s->stream>>>(s->kx[0], s->kx[1], s->kx[2], s->kz, s->kr, s->knu, s->kz, nrows, s->d_state); }
+      {
+        ProfScope prof(s, KC_SPMV_NU);
+        k_spmv<0><<<grid, NT, 0, s->stream>>>(s->kz, s->krhat, s->knu, nbr, nrows, s->d_state,
+                                              s->d_partials, s->d_counter, s->comm);
+      }
+      {
+        ProfScope prof(s, KC_XRUPDATE);
+        k_xr_update<<<grid, NT, 0, s->stream>>>(s->kx[0], s->kx[1], s->kx[2], s->kz, s->kr, s->knu,
+                                                s->kz, nrows, s->d_state);
+      }
       if (s->nranks > 1 && (rc = halo_exchange_ptr(s, s->kz, 1, CUP2D_NFIELDS))) return rc;
-      { ProfScope prof(s, KC_SPMV_T);
-      k_spmv<1><<<grid, NT, 0, s->stream>>>(s->kz, s->kr, s->kt, nbr, nrows, s->d_state, s->d_partials, s->d_counter, s->comm); }
-      { ProfScope prof(s, KC_FINAL);
-      k_final<<<grid, NT, 0, s->stream>>>(s->kx[0], s->kx[1], s->kx[2], s->kz, s->kr, s->kt, s->krhat, nrows, s->d_state, s->d_partials, s->d_counter, s->comm); }
+      {
+        ProfScope prof(s, KC_SPMV_T);
+        k_spmv<1><<<grid, NT, 0, s->stream>>>(s->kz, s->kr, s->kt, nbr, nrows, s->d_state,
+                                              s->d_partials, s->d_counter, s->comm);
+      }
+      {
+        ProfScope prof(s, KC_FINAL);
+        k_final<<<grid, NT, 0, s->stream>>>(s->kx[0], s->kx[1], s->kx[2], s->kz, s->kr, s->kt,
+                                            s->krhat, nrows, s->d_state, s->d_partials, s->d_counter,
+                                            s->comm);
+      }
       s->launches += 5;
     }
     launched += batch;

@@ -1,0 +1,161 @@
+// Warp-cooperative row access for the block-structured kernels.
+//
+// Compute mapping: one lane owns one row of 8 cells of one 8x8 block (8 lanes = one block, one warp =
+// 4 consecutive blocks = 32 rows = 2 KB (scalar) / 4 KB (vector) of CONTIGUOUS memory).  If every lane
+// read its own row with 128-bit loads, each load instruction would touch 16-32 different 128-B lines
+// and the kernels become L1/TEX-bound (measured: 78-98 % l1tex throughput, profiles/r01_summary.md).
+// Instead the warp loads its 2/4 KB chunk with fully coalesced 128-bit accesses, parks it in a
+// per-warp shared-memory scratch whose rows are padded (80 B / 144 B stride: conflict-free for the
+// transposed read), and every lane then reads its row — and, for stencils, the rows of lanes +-1 —
+// from shared memory.  Stores go the same way in reverse.
+#pragma once
+#include "common.cuh"
+
+namespace cup2d {
+
+constexpr int RS1 = 5;                 // scalar row stride in double2 (4 used + 1 pad = 80 B)
+constexpr int RS2 = 9;                 // vector row stride in double2 (8 used + 1 pad = 144 B)
+constexpr int ROWS_SCRATCH = 32 * RS2 * 2; // doubles per warp (4608 B); scalar users need 32*RS1*2
+
+// rows [row0, row0+nvalid) of a scalar field -> lane l gets row row0+l in c (zeros when l >= nvalid)
+__device__ __forceinline__ void rows_load1(const double *__restrict__ f, int row0, int nvalid,
+                                           double *sw, int lane, double (&c)[8]) {
+  const double2 *src = reinterpret_cast<const double2 *>(f) + (size_t)row0 * 4;
+  double2 *s2 = reinterpret_cast<double2 *>(sw);
+  __syncwarp();
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    const int i = j * 32 + lane;
+    if ((i >> 2) < nvalid) s2[(i >> 2) * RS1 + (i & 3)] = src[i];
+  }
+  __syncwarp();
+  if (lane < nvalid) {
+#pragma unroll
+    for (int p = 0; p < 4; p++) {
+      const double2 v = s2[lane * RS1 + p];
+      c[2 * p] = v.x;
+      c[2 * p + 1] = v.y;
+    }
+  } else {
+#pragma unroll
+    for (int p = 0; p < 8; p++) c[p] = 0.0;
+  }
+}
+// row of another lane of the chunk currently parked in the scratch (call between rows_load1 and the
+// next primitive)
+__device__ __forceinline__ void rows_peek1(const double *sw, int r, double (&c)[8]) {
+  const double2 *s2 = reinterpret_cast<const double2 *>(sw);
+#pragma unroll
+  for (int p = 0; p < 4; p++) {
+    const double2 v = s2[r * RS1 + p];
+    c[2 * p] = v.x;
+    c[2 * p + 1] = v.y;
+  }
+}
+__device__ __forceinline__ void rows_store1(double *__restrict__ f, int row0, int nvalid, double *sw,
+                                            int lane, const double (&c)[8]) {
+  double2 *dst = reinterpret_cast<double2 *>(f) + (size_t)row0 * 4;
+  double2 *s2 = reinterpret_cast<double2 *>(sw);
+  __syncwarp();
+#pragma unroll
+  for (int p = 0; p < 4; p++) s2[lane * RS1 + p] = make_double2(c[2 * p], c[2 * p + 1]);
+  __syncwarp();
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    const int i = j * 32 + lane;
+    if ((i >> 2) < nvalid) dst[i] = s2[(i >> 2) * RS1 + (i & 3)];
+  }
+}
+// vector field (u,v interleaved): lane l gets row row0+l as 8 double2
+__device__ __forceinline__ void rows_load2(const double *__restrict__ f, int row0, int nvalid,
+                                           double *sw, int lane, double2 (&c)[8]) {
+  const double2 *src = reinterpret_cast<const double2 *>(f) + (size_t)row0 * 8;
+  double2 *s2 = reinterpret_cast<double2 *>(sw);
+  __syncwarp();
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    const int i = j * 32 + lane;
+    if ((i >> 3) < nvalid) s2[(i >> 3) * RS2 + (i & 7)] = src[i];
+  }
+  __syncwarp();
+  if (lane < nvalid) {
+#pragma unroll
+    for (int p = 0; p < 8; p++) c[p] = s2[lane * RS2 + p];
+  } else {
+#pragma unroll
+    for (int p = 0; p < 8; p++) c[p] = make_double2(0.0, 0.0);
+  }
+}
+__device__ __forceinline__ void rows_peek2(const double *sw, int r, double2 (&c)[8]) {
+  const double2 *s2 = reinterpret_cast<const double2 *>(sw);
+#pragma unroll
+  for (int p = 0; p < 8; p++) c[p] = s2[r * RS2 + p];
+}
+__device__ __forceinline__ void rows_store2(double *__restrict__ f, int row0, int nvalid, double *sw,
+                                            int lane, const double2 (&c)[8]) {
+  double2 *dst = reinterpret_cast<double2 *>(f) + (size_t)row0 * 8;
+  double2 *s2 = reinterpret_cast<double2 *>(sw);
+  __syncwarp();
+#pragma unroll
+  for (int p = 0; p < 8; p++) s2[lane * RS2 + p] = c[p];
+  __syncwarp();
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    const int i = j * 32 + lane;
+    if ((i >> 3) < nvalid) dst[i] = s2[(i >> 3) * RS2 + (i & 7)];
+  }
+}
+// plain per-lane global row access (used only by the few lanes that touch a NEIGHBOUR block's edge row)
+__device__ __forceinline__ void grow_load1(const double *__restrict__ f, int slot, int y, double (&c)[8]) {
+  const double2 *p = reinterpret_cast<const double2 *>(f + (size_t)slot * 64 + y * 8);
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    const double2 v = p[k];
+    c[2 * k] = v.x;
+    c[2 * k + 1] = v.y;
+  }
+}
+__device__ __forceinline__ void grow_load2(const double *__restrict__ f, int slot, int y, double2 (&c)[8]) {
+  const double2 *p = reinterpret_cast<const double2 *>(f + (size_t)slot * 128 + y * 16);
+#pragma unroll
+  for (int k = 0; k < 8; k++) c[k] = p[k];
+}
+
+// Undivided 5-point Laplacian rows of a scalar field for the warp's 32 rows, ghost = the cell itself at
+// a domain wall (Neumann rows of main.cpp:7100-7107 / ScalarLab::Neumann2D main.cpp:3210-3245).
+// Returns the own row in c and the Laplacian in out.  Summation order S,W,E,N then -4C.
+__device__ __forceinline__ void rows_lap(const double *__restrict__ z, int row0, int nvalid,
+                                         const int4 *__restrict__ nbr, double *sw, int lane,
+                                         double (&c)[8], double (&out)[8]) {
+  rows_load1(z, row0, nvalid, sw, lane, c);
+  const int row = row0 + lane, slot = row >> 3, y = row & 7;
+  if (lane < nvalid) {
+    const int4 nb = nbr[slot];
+    double up[8], dn[8];
+    if (y < 7) rows_peek1(sw, lane + 1, up);
+    else if (nb.w >= 0) grow_load1(z, nb.w, 0, up);
+    else {
+#pragma unroll
+      for (int i = 0; i < 8; i++) up[i] = c[i];
+    }
+    if (y > 0) rows_peek1(sw, lane - 1, dn);
+    else if (nb.z >= 0) grow_load1(z, nb.z, 7, dn);
+    else {
+#pragma unroll
+      for (int i = 0; i < 8; i++) dn[i] = c[i];
+    }
+    const double gW = nb.x >= 0 ? z[(size_t)nb.x * 64 + y * 8 + 7] : c[0];
+    const double gE = nb.y >= 0 ? z[(size_t)nb.y * 64 + y * 8 + 0] : c[7];
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      const double e = i < 7 ? c[i + 1] : gE;
+      const double w = i > 0 ? c[i - 1] : gW;
+      out[i] = (((dn[i] + w) + e) + up[i]) - 4.0 * c[i];
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; i++) out[i] = 0.0;
+  }
+}
+
+} // namespace cup2d

@@ -111,7 +111,7 @@ int dim_of(int field);
 int launch_advect(cup2d_sim *s, const double *in, const double *old, double *out, double coef,
                   double dt, bool raw);
 int launch_umax(cup2d_sim *s, double *umax_out);
-int launch_pressure_rhs(cup2d_sim *s, double dt);
+int launch_pressure_rhs(cup2d_sim *s, double dt, bool has_udef);
 int launch_pressure_correct(cup2d_sim *s, double dt);
 int poisson_solve(cup2d_sim *s, double tol_abs, double tol_rel, int max_restarts, int max_iter,
                   int *iters, double *err);
