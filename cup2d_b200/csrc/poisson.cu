@@ -131,7 +131,7 @@ k_init(const double *__restrict__ b, const double *__restrict__ x0, double *__re
        double *__restrict__ r, double *__restrict__ rhat, double *__restrict__ p,
        double *__restrict__ nu, const int4 *__restrict__ nbr, int nrows, KrylovState *st,
        double *partials, unsigned int *counter, Comm comm) {
-  __shared__ double s_scr[WPB * SCR1];
+  __shared__ __align__(16) double s_scr[WPB * SCR1];
   double sums[2] = {0, 0}; // |r|^2, sum x0
   double mx = 0;
   CHUNK_LOOP() {
@@ -168,7 +168,7 @@ __global__ void __launch_bounds__(NT)
 k_pupdate(const double *__restrict__ r, double *__restrict__ rhat, double *__restrict__ p,
           const double *__restrict__ nu, double *__restrict__ z, int nrows,
           const KrylovState *__restrict__ st) {
-  __shared__ double s_scr[WPB * SCR1];
+  __shared__ __align__(16) double s_scr[WPB * SCR1];
   if (st->done) return;
   const double beta = st->beta, nomega = -st->omega;
   const bool restart = st->restart_now != 0;
@@ -201,7 +201,7 @@ __global__ void __launch_bounds__(NT)
 k_spmv(const double *__restrict__ z, const double *__restrict__ d, double *__restrict__ yout,
        const int4 *__restrict__ nbr, int nrows, KrylovState *st, double *partials,
        unsigned int *counter, Comm comm) {
-  __shared__ double s_scr[WPB * SCR1];
+  __shared__ __align__(16) double s_scr[WPB * SCR1];
   if (st->done) return;
   double sums[2] = {0, 0};
   CHUNK_LOOP() {
@@ -234,7 +234,7 @@ __global__ void __launch_bounds__(NT)
 k_xr_update(double *x0, double *x1, double *x2, const double *zin, double *__restrict__ r,
             const double *__restrict__ nu, double *zout, int nrows,
             const KrylovState *__restrict__ st) {
-  __shared__ double s_scr[WPB * SCR1];
+  __shared__ __align__(16) double s_scr[WPB * SCR1];
   if (st->done) return;
   const double alpha = st->alpha;
   const int cur = st->cur, nxt = next_buf(st->cur, st->opt);
@@ -263,7 +263,7 @@ __global__ void __launch_bounds__(NT)
 k_final(double *x0, double *x1, double *x2, const double *__restrict__ z, double *__restrict__ r,
         const double *__restrict__ t, const double *__restrict__ rhat, int nrows, KrylovState *st,
         double *partials, unsigned int *counter, Comm comm) {
-  __shared__ double s_scr[WPB * SCR1];
+  __shared__ __align__(16) double s_scr[WPB * SCR1];
   if (st->done) return;
   const double omega = st->omega;
   const int nxt = next_buf(st->cur, st->opt);

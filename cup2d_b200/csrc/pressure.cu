@@ -106,7 +106,7 @@ pressure_rhs_kernel(const double *__restrict__ vel, const double *__restrict__ u
                     const double *__restrict__ chi, const double *__restrict__ pold,
                     double *__restrict__ tmp, double *__restrict__ pres, const int4 *__restrict__ nbr,
                     int nrows, double fac) {
-  __shared__ double s_scr[WPB * ROWS_SCRATCH];
+  __shared__ __align__(16) double s_scr[WPB * ROWS_SCRATCH];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   double *sw = s_scr + warp * ROWS_SCRATCH;
   for (int row0 = (blockIdx.x * WPB + warp) * 32; row0 < nrows; row0 += gridDim.x * WPB * 32) {
@@ -214,7 +214,7 @@ pressure_correct_kernel(const double *__restrict__ x, const double *__restrict__
                         double *__restrict__ pres, double *__restrict__ vel,
                         const int4 *__restrict__ nbr, int nrows, const double *__restrict__ xsum,
                         double inv_ncells, double pfac_ih2) {
-  __shared__ double s_scr[WPB * ROWS_SCRATCH];
+  __shared__ __align__(16) double s_scr[WPB * ROWS_SCRATCH];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   double *sw = s_scr + warp * ROWS_SCRATCH;
   const double avg = xsum[0] * inv_ncells;
