@@ -33,7 +33,7 @@ HARNESS = os.path.join(ROOT, "oracle", "_ref", "ref_harness")
 ALG_BYTES = {
     "advect_stage_kernel": 48.0,      # read V_in 16 + read V_old 16 + write V_out 16 (stage 1 aliases in/old: 32)
     "umax_kernel": 16.0,
-    "pressure_rhs_kernel": 64.0,      # vel 16 + udef 16 + chi 8 + pold 8 read; tmp 8 + pres 8 written
+    "pressure_rhs_kernel": 40.0,      # no bodies: vel 16 + pold 8 read; tmp 8 + pres 8 written (+ udef 16 + chi 8 with bodies)
     "pressure_correct_kernel": 56.0,  # x 8 + pold 8 + vel 16 read; pres 8 + vel 16 written
     "k_init": 56.0,                   # b, x0 read; x, r, rhat, p, nu written
     "k_pupdate": 40.0,                # r, p, nu read; p, z written

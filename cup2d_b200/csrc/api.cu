@@ -186,26 +186,33 @@ static int build_tables(cup2d_sim *s) {
       ts[28 + k] = slot_of(gid_at(bi0 + k, bj0 + 4)); // N
     }
   }
-  CUP2D_CUDA(cudaMalloc(&s->d_nbr, std::max<size_t>(nbr.size(), 4) * sizeof(int)));
-  CUP2D_CUDA(cudaMemcpy(s->d_nbr, nbr.data(), nbr.size() * sizeof(int), cudaMemcpyHostToDevice));
-  CUP2D_CUDA(cudaMalloc(&s->d_tiles, tslots.size() * sizeof(int)));
-  CUP2D_CUDA(cudaMemcpy(s->d_tiles, tslots.data(), tslots.size() * sizeof(int), cudaMemcpyHostToDevice));
-  CUP2D_CUDA(cudaMalloc(&s->d_tile_org, torg.size() * sizeof(int)));
-  CUP2D_CUDA(cudaMemcpy(s->d_tile_org, torg.data(), torg.size() * sizeof(int), cudaMemcpyHostToDevice));
+  s->h_nbr = nbr;
+  s->h_tiles = tslots;
+  s->h_torg = torg;
   // halo source table: (owner rank, slot on the owner)
-  if (s->nhalo > 0) {
-    std::vector<int> src((size_t)s->nhalo * 2);
-    for (int64_t k = 0; k < s->nhalo; k++) {
-      src[2 * k] = s->halo_owner[k];
-      src[2 * k + 1] = (int)(halo[k] - s->rank_begin[s->halo_owner[k]]);
-    }
-    CUP2D_CUDA(cudaMalloc(&s->d_halo_src, src.size() * sizeof(int)));
-    CUP2D_CUDA(cudaMemcpy(s->d_halo_src, src.data(), src.size() * sizeof(int), cudaMemcpyHostToDevice));
+  s->h_halo_src.assign((size_t)s->nhalo * 2, 0);
+  for (int64_t k = 0; k < s->nhalo; k++) {
+    s->h_halo_src[2 * k] = s->halo_owner[k];
+    s->h_halo_src[2 * k + 1] = (int)(halo[k] - s->rank_begin[s->halo_owner[k]]);
   }
   return CUP2D_OK;
 }
 
-int cup2d_create(const cup2d_config *cfg, cup2d_sim **out) {
+static int upload_tables(cup2d_sim *s) {
+  auto up = [](int **d, const std::vector<int> &h) -> cudaError_t {
+    cudaError_t e = cudaMalloc(d, std::max<size_t>(h.size(), 4) * sizeof(int));
+    if (e != cudaSuccess) return e;
+    return cudaMemcpy(*d, h.data(), h.size() * sizeof(int), cudaMemcpyHostToDevice);
+  };
+  CUP2D_CUDA(up(&s->d_nbr, s->h_nbr));
+  CUP2D_CUDA(up(&s->d_tiles, s->h_tiles));
+  CUP2D_CUDA(up(&s->d_tile_org, s->h_torg));
+  if (s->nhalo > 0) CUP2D_CUDA(up(&s->d_halo_src, s->h_halo_src));
+  return CUP2D_OK;
+}
+
+// fills the topology part of a context from a config (no CUDA calls)
+static int init_topology(const cup2d_config *cfg, cup2d_sim **out) {
   CUP2D_REQUIRE(cfg && out, "cup2d_create: null argument");
   CUP2D_REQUIRE(cfg->nbx > 0 && cfg->nby > 0 && cfg->nblocks_global == (int64_t)cfg->nbx * cfg->nby,
                 "cup2d_create: nblocks_global must equal nbx*nby (uniform level)");
@@ -214,6 +221,64 @@ int cup2d_create(const cup2d_config *cfg, cup2d_sim **out) {
   CUP2D_REQUIRE(cfg->block_ij && cfg->rank_begin, "cup2d_create: missing tables");
   CUP2D_REQUIRE(cfg->h > 0, "cup2d_create: h must be positive");
   CUP2D_REQUIRE(cfg->nblocks_global * 64 < (1LL << 31), "cup2d_create: more than 2^31 cells per field");
+  cup2d_sim *s = new cup2d_sim;
+  s->nbx = cfg->nbx;
+  s->nby = cfg->nby;
+  s->nglobal = cfg->nblocks_global;
+  s->rank = cfg->rank;
+  s->nranks = cfg->nranks;
+  s->device = cfg->device;
+  s->h = cfg->h;
+  s->nu = cfg->nu;
+  s->cfl = cfg->cfl;
+  s->ij.assign(cfg->block_ij, cfg->block_ij + 2 * cfg->nblocks_global);
+  s->rank_begin.assign(cfg->rank_begin, cfg->rank_begin + cfg->nranks + 1);
+  bool ok = s->rank_begin[0] == 0 && s->rank_begin[cfg->nranks] == s->nglobal;
+  for (int r = 0; ok && r < cfg->nranks; r++) ok = s->rank_begin[r + 1] > s->rank_begin[r];
+  if (!ok) {
+    delete s;
+    set_error("cup2d_create: rank_begin must be increasing and span [0, nblocks_global] (every rank owns blocks)");
+    return CUP2D_EINVAL;
+  }
+  s->gbegin = s->rank_begin[s->rank];
+  s->nloc = s->rank_begin[s->rank + 1] - s->gbegin;
+  int rc = build_tables(s);
+  if (rc) {
+    delete s;
+    return rc;
+  }
+  *out = s;
+  return CUP2D_OK;
+}
+
+int cup2d_plan_create(const cup2d_config *cfg, cup2d_sim **out) {
+  cup2d_sim *s = nullptr;
+  int rc = init_topology(cfg, &s);
+  if (rc) return rc;
+  s->plan_only = true;
+  *out = s;
+  return CUP2D_OK;
+}
+
+int64_t cup2d_plan_table(const cup2d_sim *s, int which, int32_t *out) {
+  if (!s) return CUP2D_EINVAL;
+  const std::vector<int> *v = nullptr;
+  std::vector<int> tmp;
+  switch (which) {
+  case 0: tmp.assign(s->halo_gid.begin(), s->halo_gid.end()); v = &tmp; break;
+  case 1: tmp.assign(s->halo_owner.begin(), s->halo_owner.end()); v = &tmp; break;
+  case 2: tmp.resize(s->nhalo); for (int64_t k = 0; k < s->nhalo; k++) tmp[k] = s->h_halo_src[2 * k + 1]; v = &tmp; break;
+  case 3: v = &s->h_nbr; break;
+  case 4: v = &s->h_tiles; break;
+  case 5: v = &s->h_torg; break;
+  default: set_error("cup2d_plan_table: unknown table"); return CUP2D_EINVAL;
+  }
+  if (out) memcpy(out, v->data(), v->size() * sizeof(int));
+  return (int64_t)v->size();
+}
+
+int cup2d_create(const cup2d_config *cfg, cup2d_sim **out) {
+  CUP2D_REQUIRE(cfg && out, "cup2d_create: null argument");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
     set_error("cup2d_create: no CUDA device visible; this library has no CPU fallback");
@@ -227,32 +292,11 @@ int cup2d_create(const cup2d_config *cfg, cup2d_sim **out) {
     set_error(std::string("cup2d_create: device '") + prop.name + "' is not sm_100 (compiled for sm_100a only)");
     return CUP2D_ENOGPU;
   }
-  cup2d_sim *s = new cup2d_sim;
-  s->nbx = cfg->nbx;
-  s->nby = cfg->nby;
-  s->nglobal = cfg->nblocks_global;
-  s->rank = cfg->rank;
-  s->nranks = cfg->nranks;
-  s->device = cfg->device;
-  s->h = cfg->h;
-  s->nu = cfg->nu;
-  s->cfl = cfg->cfl;
+  cup2d_sim *s = nullptr;
+  int rc = init_topology(cfg, &s);
+  if (rc) return rc;
   s->num_sms = prop.multiProcessorCount;
-  s->ij.assign(cfg->block_ij, cfg->block_ij + 2 * cfg->nblocks_global);
-  s->rank_begin.assign(cfg->rank_begin, cfg->rank_begin + cfg->nranks + 1);
-  if (!(s->rank_begin[0] == 0 && s->rank_begin[cfg->nranks] == s->nglobal)) {
-    delete s;
-    set_error("cup2d_create: rank_begin must span [0, nblocks_global]");
-    return CUP2D_EINVAL;
-  }
-  s->gbegin = s->rank_begin[s->rank];
-  s->nloc = s->rank_begin[s->rank + 1] - s->gbegin;
-  if (s->nloc <= 0) {
-    delete s;
-    set_error("cup2d_create: rank owns no blocks");
-    return CUP2D_EINVAL;
-  }
-  int rc = build_tables(s);
+  rc = upload_tables(s);
   if (rc) {
     cup2d_destroy(s);
     return rc;
@@ -290,6 +334,10 @@ int cup2d_create(const cup2d_config *cfg, cup2d_sim **out) {
 
 void cup2d_destroy(cup2d_sim *s) {
   if (!s) return;
+  if (s->plan_only) {
+    delete s;
+    return;
+  }
   cudaSetDevice(s->device);
   if (s->stream) cudaStreamSynchronize(s->stream);
   if (s->peers_attached) {
@@ -348,7 +396,7 @@ int cup2d_profile_read(cup2d_sim *s, int max_entries, char *names, double *total
 }
 void *cup2d_stream(cup2d_sim *s) { return s ? (void *)s->stream : nullptr; }
 
-#define CHECK_SIM(s) CUP2D_REQUIRE((s) != nullptr, "null cup2d_sim")
+#define CHECK_SIM(s) CUP2D_REQUIRE((s) != nullptr && !(s)->plan_only, "null or plan-only cup2d_sim (plan-only contexts have no device state)")
 #define CHECK_FIELD(f) CUP2D_REQUIRE((f) >= 0 && (f) < CUP2D_NFIELDS, "bad field id")
 
 int cup2d_field_upload(cup2d_sim *s, int field, const double *host) {

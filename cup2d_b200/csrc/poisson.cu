@@ -24,7 +24,6 @@ namespace cup2d {
 
 constexpr int NT = 256;
 constexpr int WPB = NT / 32;
-constexpr int SCR1 = 32 * RS1 * 2; // per-warp scratch (doubles) for scalar rows; >= 288 (preconditioner)
 constexpr double EPS21 = 1e-21;    // cuda.cu:409
 
 __constant__ double cQ[64];  // Q[i*8+k]
@@ -174,20 +173,27 @@ k_pupdate(const double *__restrict__ r, double *__restrict__ rhat, double *__res
   const bool restart = st->restart_now != 0;
   CHUNK_LOOP() {
     const int nv = min(32, nrows - row0);
-    double pp[8], rr[8];
-    rows_load1(r, row0, nv, sw, lane, rr);
+    // element-wise part in chunk layout (coalesced, no shared memory)
+    double2 cp[4], cr[4];
+    chunk_ld(r, row0, nv, lane, cr);
     if (restart) {
-      rows_store1(rhat, row0, nv, sw, lane, rr);
+      chunk_st(rhat, row0, nv, lane, cr);
 #pragma unroll
-      for (int i = 0; i < 8; i++) pp[i] = rr[i];
+      for (int j = 0; j < 4; j++) cp[j] = cr[j];
     } else {
-      double nn[8];
-      rows_load1(p, row0, nv, sw, lane, pp);
-      rows_load1(nu, row0, nv, sw, lane, nn);
+      double2 cn[4];
+      chunk_ld(p, row0, nv, lane, cp);
+      chunk_ld(nu, row0, nv, lane, cn);
 #pragma unroll
-      for (int i = 0; i < 8; i++) pp[i] = fma(beta, fma(nomega, nn[i], pp[i]), rr[i]);
+      for (int j = 0; j < 4; j++) {
+        cp[j].x = fma(beta, fma(nomega, cn[j].x, cp[j].x), cr[j].x);
+        cp[j].y = fma(beta, fma(nomega, cn[j].y, cp[j].y), cr[j].y);
+      }
     }
-    rows_store1(p, row0, nv, sw, lane, pp);
+    chunk_st(p, row0, nv, lane, cp);
+    // block preconditioner in row layout
+    double pp[8];
+    chunk_to_rows(sw, lane, cp, pp);
     precond_row(pp, sw, lane);
     rows_store1(z, row0, nv, sw, lane, pp);
   }
@@ -206,15 +212,22 @@ k_spmv(const double *__restrict__ z, const double *__restrict__ d, double *__res
   double sums[2] = {0, 0};
   CHUNK_LOOP() {
     const int nv = min(32, nrows - row0);
-    double zz[8], az[8], dd[8];
+    double zz[8], az[8];
     rows_lap(z, row0, nv, nbr, sw, lane, zz, az);
-    rows_load1(d, row0, nv, sw, lane, dd);
+    // back to chunk layout: the dots and the store are element-wise
+    double2 ca[4], cd[4];
+    chunk_ld(d, row0, nv, lane, cd);
+    rows_to_chunk(sw, lane, az, ca);
 #pragma unroll
-    for (int i = 0; i < 8; i++) {
-      sums[0] = fma(az[i], dd[i], sums[0]);
-      if (MODE == 1) sums[1] = fma(az[i], az[i], sums[1]);
+    for (int j = 0; j < 4; j++) {
+      sums[0] = fma(ca[j].x, cd[j].x, sums[0]);
+      sums[0] = fma(ca[j].y, cd[j].y, sums[0]);
+      if (MODE == 1) {
+        sums[1] = fma(ca[j].x, ca[j].x, sums[1]);
+        sums[1] = fma(ca[j].y, ca[j].y, sums[1]);
+      }
     }
-    rows_store1(yout, row0, nv, sw, lane, az);
+    chunk_st(yout, row0, nv, lane, ca);
   }
   grid_reduce<2, NT>(sums, 0.0, partials, counter, comm, [=](const double *t, double) {
     if (MODE == 0) {
@@ -242,17 +255,24 @@ k_xr_update(double *x0, double *x1, double *x2, const double *zin, double *__res
   double *xn = nxt == 0 ? x0 : (nxt == 1 ? x1 : x2);
   CHUNK_LOOP() {
     const int nv = min(32, nrows - row0);
-    double xx[8], zz[8], rr[8], nn[8];
-    rows_load1(xc, row0, nv, sw, lane, xx);
-    rows_load1(zin, row0, nv, sw, lane, zz);
+    // element-wise part in chunk layout (coalesced, no shared memory)
+    double2 cx[4], cz[4], cr[4], cn[4];
+    chunk_ld(xc, row0, nv, lane, cx);
+    chunk_ld(zin, row0, nv, lane, cz);
+    chunk_ld(r, row0, nv, lane, cr);
+    chunk_ld(nu, row0, nv, lane, cn);
 #pragma unroll
-    for (int i = 0; i < 8; i++) xx[i] = fma(alpha, zz[i], xx[i]);
-    rows_store1(xn, row0, nv, sw, lane, xx);
-    rows_load1(r, row0, nv, sw, lane, rr);
-    rows_load1(nu, row0, nv, sw, lane, nn);
-#pragma unroll
-    for (int i = 0; i < 8; i++) rr[i] = fma(-alpha, nn[i], rr[i]);
-    rows_store1(r, row0, nv, sw, lane, rr);
+    for (int j = 0; j < 4; j++) {
+      cx[j].x = fma(alpha, cz[j].x, cx[j].x);
+      cx[j].y = fma(alpha, cz[j].y, cx[j].y);
+      cr[j].x = fma(-alpha, cn[j].x, cr[j].x);
+      cr[j].y = fma(-alpha, cn[j].y, cr[j].y);
+    }
+    chunk_st(xn, row0, nv, lane, cx);
+    chunk_st(r, row0, nv, lane, cr);
+    // block preconditioner in row layout
+    double rr[8];
+    chunk_to_rows(sw, lane, cr, rr);
     precond_row(rr, sw, lane);
     rows_store1(zout, row0, nv, sw, lane, rr);
   }
@@ -263,35 +283,37 @@ __global__ void __launch_bounds__(NT)
 k_final(double *x0, double *x1, double *x2, const double *__restrict__ z, double *__restrict__ r,
         const double *__restrict__ t, const double *__restrict__ rhat, int nrows, KrylovState *st,
         double *partials, unsigned int *counter, Comm comm) {
-  __shared__ __align__(16) double s_scr[WPB * SCR1];
   if (st->done) return;
   const double omega = st->omega;
   const int nxt = next_buf(st->cur, st->opt);
   double *xn = nxt == 0 ? x0 : (nxt == 1 ? x1 : x2);
   double sums[3] = {0, 0, 0}; // rhat.r, r.r, sum x
   double mx = 0;
-  CHUNK_LOOP() {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int row0 = (blockIdx.x * WPB + warp) * 32; row0 < nrows; row0 += gridDim.x * WPB * 32) {
     const int nv = min(32, nrows - row0);
-    double xx[8], zz[8], rr[8], tt[8];
-    rows_load1(xn, row0, nv, sw, lane, xx);
-    rows_load1(z, row0, nv, sw, lane, zz);
+    // purely element-wise: chunk layout only, no shared memory
+    double2 cx[4], cz[4], cr[4], ct[4], ch[4];
+    chunk_ld(xn, row0, nv, lane, cx);
+    chunk_ld(z, row0, nv, lane, cz);
+    chunk_ld(r, row0, nv, lane, cr);
+    chunk_ld(t, row0, nv, lane, ct);
+    chunk_ld(rhat, row0, nv, lane, ch);
 #pragma unroll
-    for (int i = 0; i < 8; i++) {
-      xx[i] = fma(omega, zz[i], xx[i]); // cuda.cu:520
-      sums[2] += xx[i];
+    for (int j = 0; j < 4; j++) {
+      cx[j].x = fma(omega, cz[j].x, cx[j].x); // cuda.cu:520
+      cx[j].y = fma(omega, cz[j].y, cx[j].y);
+      cr[j].x = fma(-omega, ct[j].x, cr[j].x); // cuda.cu:524
+      cr[j].y = fma(-omega, ct[j].y, cr[j].y);
+      sums[0] = fma(ch[j].x, cr[j].x, sums[0]);
+      sums[0] = fma(ch[j].y, cr[j].y, sums[0]);
+      sums[1] = fma(cr[j].x, cr[j].x, sums[1]);
+      sums[1] = fma(cr[j].y, cr[j].y, sums[1]);
+      sums[2] += cx[j].x + cx[j].y;
+      mx = fmax(mx, fmax(fabs(cr[j].x), fabs(cr[j].y)));
     }
-    rows_store1(xn, row0, nv, sw, lane, xx);
-    rows_load1(r, row0, nv, sw, lane, rr);
-    rows_load1(t, row0, nv, sw, lane, tt);
-    rows_load1(rhat, row0, nv, sw, lane, zz);
-#pragma unroll
-    for (int i = 0; i < 8; i++) {
-      rr[i] = fma(-omega, tt[i], rr[i]); // cuda.cu:524
-      sums[0] = fma(zz[i], rr[i], sums[0]);
-      sums[1] = fma(rr[i], rr[i], sums[1]);
-      mx = fmax(mx, fabs(rr[i]));
-    }
-    rows_store1(r, row0, nv, sw, lane, rr);
+    chunk_st(xn, row0, nv, lane, cx);
+    chunk_st(r, row0, nv, lane, cr);
   }
   grid_reduce<3, NT>(sums, mx, partials, counter, comm, [=](const double *tsum, double m) {
     st->iter++;

@@ -1,72 +1,100 @@
 // Warp-cooperative row access for the block-structured kernels.
 //
-// Compute mapping: one lane owns one row of 8 cells of one 8x8 block (8 lanes = one block, one warp =
-// 4 consecutive blocks = 32 rows = 2 KB (scalar) / 4 KB (vector) of CONTIGUOUS memory).  If every lane
-// read its own row with 128-bit loads, each load instruction would touch 16-32 different 128-B lines
-// and the kernels become L1/TEX-bound (measured: 78-98 % l1tex throughput, profiles/r01_summary.md).
-// Instead the warp loads its 2/4 KB chunk with fully coalesced 128-bit accesses, parks it in a
-// per-warp shared-memory scratch whose rows are padded (80 B / 144 B stride: conflict-free for the
-// transposed read), and every lane then reads its row — and, for stencils, the rows of lanes +-1 —
-// from shared memory.  Stores go the same way in reverse.
+// Compute mapping ("row layout"): one lane owns one row of 8 cells of one 8x8 block (8 lanes = one
+// block, one warp = 4 consecutive blocks = 32 rows = one CHUNK of 2 KB (scalar) / 4 KB (vector) of
+// CONTIGUOUS memory).  If every lane read its own row with 128-bit loads, each load instruction would
+// touch 16-32 different 128-B lines and the kernels become L1/TEX-bound (measured: 78-98 % l1tex
+// throughput, profiles/r01_summary.md).  So global memory is only ever touched in "chunk layout": lane
+// l holds the 16-byte pieces j*32+l (j = 0..3) of the chunk, i.e. fully coalesced 128-bit accesses.
+// Element-wise work (axpy, dots, norms) is done directly in chunk layout; only stencils and the block
+// preconditioner need row layout, and the two layouts are converted through a per-warp shared-memory
+// scratch.  The scratch is unpadded and XOR-swizzled: piece p of row r lives at 16-byte slot
+// 4r + (p ^ ((r>>1)&3)), which is bank-conflict-free both for the coalesced side (8 lanes = 2 rows x 4
+// pieces) and for the row side (8 lanes = 8 consecutive rows, same piece).
 #pragma once
 #include "common.cuh"
 
 namespace cup2d {
 
-constexpr int RS1 = 5;                 // scalar row stride in double2 (4 used + 1 pad = 80 B)
-constexpr int RS2 = 9;                 // vector row stride in double2 (8 used + 1 pad = 144 B)
-constexpr int ROWS_SCRATCH = 32 * RS2 * 2; // doubles per warp (4608 B); scalar users need 32*RS1*2
+constexpr int RS2 = 9;                     // vector row stride in double2 (8 used + 1 pad = 144 B)
+constexpr int ROWS_SCRATCH = 32 * RS2 * 2; // doubles per warp for kernels that touch vector fields
+constexpr int SCR1 = 288;                  // doubles per warp for scalar-only kernels (preconditioner: 4*72)
 
-// rows [row0, row0+nvalid) of a scalar field -> lane l gets row row0+l in c (zeros when l >= nvalid)
-__device__ __forceinline__ void rows_load1(const double *__restrict__ f, int row0, int nvalid,
-                                           double *sw, int lane, double (&c)[8]) {
+__device__ __forceinline__ int swz(int r, int p) { return r * 4 + (p ^ ((r >> 1) & 3)); }
+
+// ---- chunk layout <-> global ------------------------------------------------------------------
+__device__ __forceinline__ void chunk_ld(const double *__restrict__ f, int row0, int nvalid, int lane,
+                                         double2 (&c)[4]) {
   const double2 *src = reinterpret_cast<const double2 *>(f) + (size_t)row0 * 4;
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    const int i = j * 32 + lane;
+    c[j] = (i >> 2) < nvalid ? src[i] : make_double2(0.0, 0.0);
+  }
+}
+__device__ __forceinline__ void chunk_st(double *__restrict__ f, int row0, int nvalid, int lane,
+                                         const double2 (&c)[4]) {
+  double2 *dst = reinterpret_cast<double2 *>(f) + (size_t)row0 * 4;
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    const int i = j * 32 + lane;
+    if ((i >> 2) < nvalid) dst[i] = c[j];
+  }
+}
+// ---- chunk layout <-> row layout through the scratch -----------------------------------------------
+// after chunk_to_rows the whole chunk stays parked in the scratch (rows_peek1 may read other rows)
+__device__ __forceinline__ void chunk_to_rows(double *sw, int lane, const double2 (&c)[4], double (&r)[8]) {
   double2 *s2 = reinterpret_cast<double2 *>(sw);
   __syncwarp();
 #pragma unroll
   for (int j = 0; j < 4; j++) {
     const int i = j * 32 + lane;
-    if ((i >> 2) < nvalid) s2[(i >> 2) * RS1 + (i & 3)] = src[i];
+    s2[swz(i >> 2, i & 3)] = c[j];
   }
   __syncwarp();
-  if (lane < nvalid) {
 #pragma unroll
-    for (int p = 0; p < 4; p++) {
-      const double2 v = s2[lane * RS1 + p];
-      c[2 * p] = v.x;
-      c[2 * p + 1] = v.y;
-    }
-  } else {
-#pragma unroll
-    for (int p = 0; p < 8; p++) c[p] = 0.0;
+  for (int p = 0; p < 4; p++) {
+    const double2 v = s2[swz(lane, p)];
+    r[2 * p] = v.x;
+    r[2 * p + 1] = v.y;
   }
 }
-// row of another lane of the chunk currently parked in the scratch (call between rows_load1 and the
-// next primitive)
+__device__ __forceinline__ void rows_to_chunk(double *sw, int lane, const double (&r)[8], double2 (&c)[4]) {
+  double2 *s2 = reinterpret_cast<double2 *>(sw);
+  __syncwarp();
+#pragma unroll
+  for (int p = 0; p < 4; p++) s2[swz(lane, p)] = make_double2(r[2 * p], r[2 * p + 1]);
+  __syncwarp();
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    const int i = j * 32 + lane;
+    c[j] = s2[swz(i >> 2, i & 3)];
+  }
+}
 __device__ __forceinline__ void rows_peek1(const double *sw, int r, double (&c)[8]) {
   const double2 *s2 = reinterpret_cast<const double2 *>(sw);
 #pragma unroll
   for (int p = 0; p < 4; p++) {
-    const double2 v = s2[r * RS1 + p];
+    const double2 v = s2[swz(r, p)];
     c[2 * p] = v.x;
     c[2 * p + 1] = v.y;
   }
 }
+// convenience: rows [row0, row0+nvalid) of a scalar field -> lane l gets row row0+l (zeros beyond)
+__device__ __forceinline__ void rows_load1(const double *__restrict__ f, int row0, int nvalid,
+                                           double *sw, int lane, double (&c)[8]) {
+  double2 t[4];
+  chunk_ld(f, row0, nvalid, lane, t);
+  chunk_to_rows(sw, lane, t, c);
+}
 __device__ __forceinline__ void rows_store1(double *__restrict__ f, int row0, int nvalid, double *sw,
                                             int lane, const double (&c)[8]) {
-  double2 *dst = reinterpret_cast<double2 *>(f) + (size_t)row0 * 4;
-  double2 *s2 = reinterpret_cast<double2 *>(sw);
-  __syncwarp();
-#pragma unroll
-  for (int p = 0; p < 4; p++) s2[lane * RS1 + p] = make_double2(c[2 * p], c[2 * p + 1]);
-  __syncwarp();
-#pragma unroll
-  for (int j = 0; j < 4; j++) {
-    const int i = j * 32 + lane;
-    if ((i >> 2) < nvalid) dst[i] = s2[(i >> 2) * RS1 + (i & 3)];
-  }
+  double2 t[4];
+  rows_to_chunk(sw, lane, c, t);
+  chunk_st(f, row0, nvalid, lane, t);
 }
-// vector field (u,v interleaved): lane l gets row row0+l as 8 double2
+
+// ---- vector field (u,v interleaved): lane l gets row row0+l as 8 double2 (padded scratch) -----------
 __device__ __forceinline__ void rows_load2(const double *__restrict__ f, int row0, int nvalid,
                                            double *sw, int lane, double2 (&c)[8]) {
   const double2 *src = reinterpret_cast<const double2 *>(f) + (size_t)row0 * 8;

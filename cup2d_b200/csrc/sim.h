@@ -52,6 +52,8 @@ struct cup2d_sim {
   std::vector<int64_t> rank_begin;
   std::vector<int32_t> halo_gid;       // global id of every halo slot (slot = nloc + k), sorted
   std::vector<int32_t> halo_owner;     // owning rank per halo slot
+  std::vector<int> h_nbr, h_tiles, h_torg, h_halo_src; // host copies of the device tables
+  bool plan_only = false;              // created by cup2d_plan_create: topology only, no CUDA state
   cudaStream_t stream = nullptr;
   // device tables
   int *d_nbr = nullptr;                // [nloc][4] slots of W,E,S,N neighbours, -1 = wall

@@ -121,6 +121,17 @@ int cup2d_peer_attach(cup2d_sim *s, const void *all_blobs);
 /* Explicit halo refresh of one field (normally implicit inside the operators). */
 int cup2d_halo_exchange(cup2d_sim *s, int field);
 
+/* ---- host-side topology plan (no GPU needed; used by the CPU tests of the multi-rank logic) ---- */
+/* Same config as cup2d_create, but builds only the host tables: SFC-range partition, halo plan
+ * (which face-neighbour blocks this rank pulls from which owner), neighbour table, advect tiles.
+ * The context accepts only cup2d_plan_table / cup2d_nblocks_* / cup2d_destroy. */
+int cup2d_plan_create(const cup2d_config *cfg, cup2d_sim **out);
+/* which: 0 halo global block ids [nhalo] (halo slot k = nblocks_local + k), 1 halo owner ranks [nhalo],
+ * 2 halo source slots on the owner [nhalo], 3 neighbour slots W,E,S,N per local block [4*nblocks_local]
+ * (-1 = wall), 4 advect tile slots [32*ntiles], 5 tile origins in blocks [2*ntiles].
+ * Returns the number of int32 entries (out may be NULL to query). */
+int64_t cup2d_plan_table(const cup2d_sim *s, int which, int32_t *out);
+
 /* ---- instrumentation ---- */
 /* number of kernels this library has launched since creation (bench.py's gpu_launches) */
 int64_t cup2d_launch_count(const cup2d_sim *s);
