@@ -43,6 +43,23 @@ constexpr int OFF_BAR = OFF_SV + TW * SP * 8;
 constexpr int OFF_SLOTS = OFF_BAR + 16;
 constexpr int ADV_SMEM = OFF_SLOTS + TILE_SLOTS * 4; // 51.5 KB -> 4 CTAs/SM
 
+// WENO constants.  With CM (constant memory) they are DFMA constant-bank operands; otherwise the
+// compiler materialises each 64-bit literal with a pair of UMOVs (36 UMOV per cell in the r01c profile).
+enum { K_G = 0, K_EPS, K_D1, K_D2, K_D3,            // 13/3, 4e-6, den weights .1 .6 .3
+       K_PA1, K_PB1, K_PA2, K_PB2, K_PA3, K_PB3,    // plus-flux phi coefficients (gamma folded in)
+       K_MA1, K_MB1, K_MA2, K_MB2, K_MA3, K_MB3, K_N };
+__constant__ double cW[K_N];
+static const double hW[K_N] = {13.0 / 3.0, 4e-6, 0.1, 0.6, 0.3,
+                               0.1 * 5.0 / 6.0, -0.1 / 3.0, 0.6 / 6.0, 0.6 / 3.0, 0.3 * 2.0 / 3.0, -0.3 / 6.0,
+                               -0.3 * 2.0 / 3.0, 0.3 / 6.0, -0.6 / 3.0, -0.6 / 6.0, -0.1 * 5.0 / 6.0, 0.1 / 3.0};
+template <bool CM, int I> __device__ __forceinline__ double KW() {
+  if (CM) return cW[I];
+  constexpr double v[K_N] = {13.0 / 3.0, 4e-6, 0.1, 0.6, 0.3,
+                             0.1 * 5.0 / 6.0, -0.1 / 3.0, 0.6 / 6.0, 0.6 / 3.0, 0.3 * 2.0 / 3.0, -0.3 / 6.0,
+                             -0.3 * 2.0 / 3.0, 0.3 / 6.0, -0.6 / 3.0, -0.6 / 6.0, -0.1 * 5.0 / 6.0, 0.1 / 3.0};
+  return v[I];
+}
+
 struct LineState {
   double dm2, dm1, d0, dp1; // D[w-2..w+1]
   double Gm1, G0, Gp1;      // 13/3 D2^2 + 4e-6 at w-1, w, w+1
@@ -50,17 +67,18 @@ struct LineState {
   double rP1, rP2, rM1;     // ratioP(w-1), ratioP(w-2), ratioM(w-1)
 };
 
-__device__ __forceinline__ double Gfun(double D2) { return fma((13.0 / 3.0) * D2, D2, 4e-6); }
-
-__device__ __forceinline__ void line_init(LineState &s, const double *q, int es) {
+template <bool CM> __device__ __forceinline__ double Gfun(double D2) {
+  return fma(KW<CM, K_G>() * D2, D2, KW<CM, K_EPS>());
+}
+template <bool CM> __device__ __forceinline__ void line_init(LineState &s, const double *q, int es) {
   double q0 = q[0], q1 = q[es], q2 = q[2 * es], q3 = q[3 * es], q4 = q[4 * es];
   s.dm2 = q1 - q0; // w = 2: D[0]
   s.dm1 = q2 - q1; // D[1]
   s.d0 = q3 - q2;  // D[2]
   s.dp1 = q4 - q3; // D[3]
-  s.Gm1 = Gfun(s.dm1 - s.dm2);
-  s.G0 = Gfun(s.d0 - s.dm1);
-  s.Gp1 = Gfun(s.dp1 - s.d0);
+  s.Gm1 = Gfun<CM>(s.dm1 - s.dm2);
+  s.G0 = Gfun<CM>(s.d0 - s.dm1);
+  s.Gp1 = Gfun<CM>(s.dp1 - s.d0);
   s.qlast = q4;
   s.rP1 = s.rP2 = s.rM1 = 0.0;
 }
@@ -86,28 +104,27 @@ template <int NEWTON> __device__ __forceinline__ double rcp_pos(double x) {
   }
   return r;
 }
-// upwind-from-the-left flux ratio at face w+1/2 (weno5_plus, main.cpp:162-181; gammas .1,.6,.3 folded
-// into the phi coefficients)
-template <int NEWTON>
+// upwind-from-the-left flux ratio at face w+1/2 (weno5_plus, main.cpp:162-181; gammas .1,.6,.3)
+template <bool CM, int NEWTON>
 __device__ __forceinline__ double ratio_plus(const LineState &s, double s1, double s2, double s3) {
-  const double den = fma(0.1, s1, fma(0.3, s3, 0.6 * s2));
-  const double p1 = fma(0.1 * 5.0 / 6.0, s.dm1, (-0.1 / 3.0) * s.dm2);
-  const double p2 = fma(0.6 / 6.0, s.dm1, (0.6 / 3.0) * s.d0);
-  const double p3 = fma(0.3 * 2.0 / 3.0, s.d0, (-0.3 / 6.0) * s.dp1);
+  const double den = fma(KW<CM, K_D1>(), s1, fma(KW<CM, K_D3>(), s3, KW<CM, K_D2>() * s2));
+  const double p1 = fma(KW<CM, K_PA1>(), s.dm1, KW<CM, K_PB1>() * s.dm2);
+  const double p2 = fma(KW<CM, K_PA2>(), s.dm1, KW<CM, K_PB2>() * s.d0);
+  const double p3 = fma(KW<CM, K_PA3>(), s.d0, KW<CM, K_PB3>() * s.dp1);
   const double num = fma(s1, p1, fma(s3, p3, s2 * p2));
   return num * rcp_pos<NEWTON>(den);
 }
 // upwind-from-the-right flux ratio at face w-1/2 (weno5_minus, main.cpp:182-201; gammas .3,.6,.1)
-template <int NEWTON>
+template <bool CM, int NEWTON>
 __device__ __forceinline__ double ratio_minus(const LineState &s, double s1, double s2, double s3) {
-  const double den = fma(0.3, s1, fma(0.1, s3, 0.6 * s2));
-  const double p1 = fma(-0.3 * 2.0 / 3.0, s.dm1, (0.3 / 6.0) * s.dm2);
-  const double p2 = fma(-0.6 / 3.0, s.dm1, (-0.6 / 6.0) * s.d0);
-  const double p3 = fma(-0.1 * 5.0 / 6.0, s.d0, (0.1 / 3.0) * s.dp1);
+  const double den = fma(KW<CM, K_D3>(), s1, fma(KW<CM, K_D1>(), s3, KW<CM, K_D2>() * s2));
+  const double p1 = fma(KW<CM, K_MA1>(), s.dm1, KW<CM, K_MB1>() * s.dm2);
+  const double p2 = fma(KW<CM, K_MA2>(), s.dm1, KW<CM, K_MB2>() * s.d0);
+  const double p3 = fma(KW<CM, K_MA3>(), s.d0, KW<CM, K_MB3>() * s.dp1);
   const double num = fma(s1, p1, fma(s3, p3, s2 * p2));
   return num * rcp_pos<NEWTON>(den);
 }
-__device__ __forceinline__ void line_advance(LineState &s, double qn, double rP, double rM) {
+template <bool CM> __device__ __forceinline__ void line_advance(LineState &s, double qn, double rP, double rM) {
   s.rP2 = s.rP1;
   s.rP1 = rP;
   s.rM1 = rM;
@@ -118,25 +135,25 @@ __device__ __forceinline__ void line_advance(LineState &s, double qn, double rP,
   s.qlast = qn;
   s.Gm1 = s.G0;
   s.G0 = s.Gp1;
-  s.Gp1 = Gfun(s.dp1 - s.d0);
+  s.Gp1 = Gfun<CM>(s.dp1 - s.d0);
 }
 
 // Upwind WENO5 differences of both components along one line of 8 cells (window of 14 values per
-// component, element stride ES).  qa = advecting component (sign + multiplier), qb = the other one.
+// component, element stride es).  qa = advecting component (sign + multiplier), qb = the other one.
 // emit(c, Ua, Ub, da, db, D2a, D2b) is called once per cell c = 0..7 with the cell values, the undivided
 // differences (reference `derivative`, main.cpp:202-208) and the second differences (diffusion term).
-template <int ES, int UNR, int NEWTON, class Emit>
-__device__ __forceinline__ void weno_line(const double *__restrict__ qa,
-                                          const double *__restrict__ qb, Emit emit) {
+template <int UNR, int NEWTON, bool CM, class Emit>
+__device__ __forceinline__ void weno_line(const double *__restrict__ qa, const double *__restrict__ qb,
+                                          const int es, Emit emit) {
   LineState A, B;
-  line_init(A, qa, ES);
-  line_init(B, qb, ES);
+  line_init<CM>(A, qa, es);
+  line_init<CM>(B, qb, es);
   // sign of the advecting velocity at window indices 2..12 (bit k <-> index k), one pass, no FP64 pipe
   unsigned pos = 0;
 #pragma unroll
-  for (int k = 2; k <= 12; k++) pos |= is_pos(qa[k * ES]) ? (1u << k) : 0u;
-  double Ubm1 = qb[2 * ES]; // qb at window index w-1 (cell value of the other component)
-  double Uam1 = qa[2 * ES];
+  for (int k = 2; k <= 12; k++) pos |= is_pos(qa[k * es]) ? (1u << k) : 0u;
+  double Ubm1 = qb[2 * es]; // qb at window index w-1 (cell value of the other component)
+  double Uam1 = qa[2 * es];
 #pragma unroll UNR
   for (int w = 2; w <= 11; ++w) {
     const bool vc = (unsigned)(w - 3) < 8u, vn = (unsigned)(w - 2) < 8u, vp = (unsigned)(w - 4) < 8u;
@@ -148,12 +165,12 @@ __device__ __forceinline__ void weno_line(const double *__restrict__ qa,
     line_betas(B, b1, b2, b3);
     double rPa = 0, rPb = 0, rMa = 0, rMb = 0;
     if (needP) {
-      rPa = ratio_plus<NEWTON>(A, a1, a2, a3);
-      rPb = ratio_plus<NEWTON>(B, b1, b2, b3);
+      rPa = ratio_plus<CM, NEWTON>(A, a1, a2, a3);
+      rPb = ratio_plus<CM, NEWTON>(B, b1, b2, b3);
     }
     if (needM) {
-      rMa = ratio_minus<NEWTON>(A, a1, a2, a3);
-      rMb = ratio_minus<NEWTON>(B, b1, b2, b3);
+      rMa = ratio_minus<CM, NEWTON>(A, a1, a2, a3);
+      rMb = ratio_minus<CM, NEWTON>(B, b1, b2, b3);
     }
     if (vp) { // finalize cell c = w-4 (window index w-1)
       double da, db;
@@ -167,18 +184,19 @@ __device__ __forceinline__ void weno_line(const double *__restrict__ qa,
       emit(w - 4, Uam1, Ubm1, da, db, A.dm1 - A.dm2, B.dm1 - B.dm2);
     }
     if (w < 11) {
-      // q[w] of both components = q[w+1] - D[w]; cheaper: reload from shared memory
-      Uam1 = qa[w * ES];
-      Ubm1 = qb[w * ES];
-      const double qna = qa[(w + 3) * ES], qnb = qb[(w + 3) * ES];
-      line_advance(A, qna, rPa, rMa);
-      line_advance(B, qnb, rPb, rMb);
+      Uam1 = qa[w * es];
+      Ubm1 = qb[w * es];
+      const double qna = qa[(w + 3) * es], qnb = qb[(w + 3) * es];
+      line_advance<CM>(A, qna, rPa, rMa);
+      line_advance<CM>(B, qnb, rPb, rMb);
     }
   }
 }
 
 // MODE 0: out = tot (raw K, undivided)   1: old == in (stage 1)   2: old is a separate field (stage 2)
-template <int MODE, int UNR, int NEWTON>
+// ONE: both passes run through ONE copy of the unrolled line code (a 2-trip loop with run-time strides)
+//      instead of two specialised copies: halves the instruction footprint (I-cache).
+template <int MODE, int UNR, int NEWTON, bool CM, bool ONE>
 __global__ void __launch_bounds__(NT_ADV, 4)
 advect_stage_kernel(const double *__restrict__ in, const double *__restrict__ old,
                     double *__restrict__ out, const int *__restrict__ tiles,
@@ -262,87 +280,84 @@ advect_stage_kernel(const double *__restrict__ in, const double *__restrict__ ol
   }
   __syncthreads(); // staging is dead from here on: Ru/Rv reuse it
 
-  // ---- stage 2: x pass. lanes = rows; thread = 8 consecutive cells of one row ----
-  {
-    const int r = lane, xs = warp;
-    const double *qa = su + (r + GH) * SP + 8 * xs; // window index 0 <-> cell x0-3
-    const double *qb = sv + (r + GH) * SP + 8 * xs;
-    double *ru = Ru + r * RP + 8 * xs, *rv = Rv + r * RP + 8 * xs;
-    weno_line<1, UNR, NEWTON>(qa, qb, [&](int c, double U, double, double du, double dv, double D2u, double D2v) {
-      const double aU = afac * U;
-      ru[c] = fma(aU, du, dfac * D2u); // afac*u*dudx + dfac*(u_E + u_W - 2u)
-      rv[c] = fma(aU, dv, dfac * D2v);
-    });
-  }
-  __syncthreads();
-
-  // ---- stage 3: y pass. lanes = columns; thread = 8 consecutive cells of one column = one block ----
-  {
-    const double *qa = sv + (8 * ys) * SP + (yx + GH); // advecting component is v
-    const double *qb = su + (8 * ys) * SP + (yx + GH);
-    double2 *outp = reinterpret_cast<double2 *>(out) + (size_t)(store ? yslot : 0) * 64 + (yx & 7);
+  double2 *outp = reinterpret_cast<double2 *>(out) + (size_t)(store ? yslot : 0) * 64 + (yx & 7);
+  // x pass: lanes = rows, thread = 8 consecutive cells of one row (advecting component u)
+  // y pass: lanes = columns, thread = 8 consecutive cells of one column = one block (advecting v)
+  auto emit_x = [&](int c, double U, double, double du, double dv, double D2u, double D2v) {
+    double *ru = Ru + lane * RP + 8 * warp, *rv = Rv + lane * RP + 8 * warp;
+    const double aU = afac * U;
+    ru[c] = fma(aU, du, dfac * D2u); // afac*u*dudx + dfac*(u_E + u_W - 2u)
+    rv[c] = fma(aU, dv, dfac * D2v);
+  };
+  auto emit_y = [&](int c, double V, double Uc, double dv, double du, double D2v, double D2u) {
     const double *ru = Ru + (8 * ys) * RP + yx, *rv = Rv + (8 * ys) * RP + yx;
-    weno_line<SP, UNR, NEWTON>(qa, qb, [&](int c, double V, double Uc, double dv, double du, double D2v, double D2u) {
-      const double aV = afac * V;
-      const double tu = ru[c * RP] + fma(aV, du, dfac * D2u);
-      const double tv = rv[c * RP] + fma(aV, dv, dfac * D2v);
-      if (store) {
-        double2 o;
-        if (MODE == 0) {
-          o.x = tu;
-          o.y = tv;
-        } else if (MODE == 1) { // old == in: the cell values are already in registers
-          o.x = fma(ofac, tu, Uc);
-          o.y = fma(ofac, tv, V);
-        } else {
-          o.x = fma(ofac, tu, oldv[c].x); // V = Vold + coef*tmpV/h^2, main.cpp:6618-6626
-          o.y = fma(ofac, tv, oldv[c].y);
-        }
-        outp[c * 8] = o;
+    const double aV = afac * V;
+    const double tu = ru[c * RP] + fma(aV, du, dfac * D2u);
+    const double tv = rv[c * RP] + fma(aV, dv, dfac * D2v);
+    if (store) {
+      double2 o;
+      if (MODE == 0) {
+        o.x = tu;
+        o.y = tv;
+      } else if (MODE == 1) { // old == in: the cell values are already in registers
+        o.x = fma(ofac, tu, Uc);
+        o.y = fma(ofac, tv, V);
+      } else {
+        o.x = fma(ofac, tu, oldv[c].x); // V = Vold + coef*tmpV/h^2, main.cpp:6618-6626
+        o.y = fma(ofac, tv, oldv[c].y);
       }
-    });
+      outp[c * 8] = o;
+    }
+  };
+  if (ONE) {
+#pragma unroll 1
+    for (int pass = 0; pass < 2; pass++) {
+      const double *qa = pass == 0 ? su + (lane + GH) * SP + 8 * warp : sv + (8 * ys) * SP + (yx + GH);
+      const double *qb = pass == 0 ? sv + (lane + GH) * SP + 8 * warp : su + (8 * ys) * SP + (yx + GH);
+      const int es = pass == 0 ? 1 : SP;
+      weno_line<UNR, NEWTON, CM>(qa, qb, es, [&](int c, double Ua, double Ub, double da, double db, double D2a, double D2b) {
+        if (pass == 0) emit_x(c, Ua, Ub, da, db, D2a, D2b);
+        else emit_y(c, Ua, Ub, da, db, D2a, D2b);
+      });
+      __syncthreads();
+    }
+  } else {
+    weno_line<UNR, NEWTON, CM>(su + (lane + GH) * SP + 8 * warp, sv + (lane + GH) * SP + 8 * warp, 1, emit_x);
+    __syncthreads();
+    weno_line<UNR, NEWTON, CM>(sv + (8 * ys) * SP + (yx + GH), su + (8 * ys) * SP + (yx + GH), SP, emit_y);
   }
 }
 
 typedef void (*adv_fn)(const double *, const double *, double *, const int *, const int *, int, int, int,
                        double, double, double);
-template <int UNR, int NEWTON> static adv_fn pick_mode(int mode) {
+template <int UNR, bool CM, bool ONE> static adv_fn pick_mode(int mode) {
   switch (mode) {
-  case 0: return advect_stage_kernel<0, UNR, NEWTON>;
-  case 1: return advect_stage_kernel<1, UNR, NEWTON>;
-  default: return advect_stage_kernel<2, UNR, NEWTON>;
+  case 0: return advect_stage_kernel<0, UNR, 2, CM, ONE>;
+  case 1: return advect_stage_kernel<1, UNR, 2, CM, ONE>;
+  default: return advect_stage_kernel<2, UNR, 2, CM, ONE>;
   }
 }
-static adv_fn pick(int mode, int unr, int newton) {
-  if (newton == 1) {
-    switch (unr) {
-    case 1: return pick_mode<1, 1>(mode);
-    case 2: return pick_mode<2, 1>(mode);
-    case 5: return pick_mode<5, 1>(mode);
-    default: return pick_mode<10, 1>(mode);
-    }
-  }
-  switch (unr) {
-  case 1: return pick_mode<1, 2>(mode);
-  case 2: return pick_mode<2, 2>(mode);
-  case 5: return pick_mode<5, 2>(mode);
-  default: return pick_mode<10, 2>(mode);
-  }
+template <int UNR> static adv_fn pick_flags(int mode, bool cm, bool one) {
+  if (cm) return one ? pick_mode<UNR, true, true>(mode) : pick_mode<UNR, true, false>(mode);
+  return one ? pick_mode<UNR, false, true>(mode) : pick_mode<UNR, false, false>(mode);
 }
 
 int launch_advect(cup2d_sim *s, const double *in, const double *old, double *out, double coef,
                   double dt, bool raw) {
-  // tuning knobs (profiles/README.md records the sweep): loop unroll factor and Newton steps of the
-  // reciprocal; the defaults are the measured best
-  static int unr = -1, newton = -1;
+  // tuning knobs (profiles/ records the sweeps): loop unroll factor, constants from constant memory,
+  // one shared code copy for both passes; the defaults are the measured best
+  static int unr = -1, cm = 1, one = 1;
   if (unr < 0) {
     const char *e = getenv("CUP2D_ADV_UNROLL");
     unr = e ? atoi(e) : 10;
-    e = getenv("CUP2D_ADV_NEWTON");
-    newton = e ? atoi(e) : 2;
+    e = getenv("CUP2D_ADV_CONSTMEM");
+    cm = e ? atoi(e) : 1;
+    e = getenv("CUP2D_ADV_ONECOPY");
+    one = e ? atoi(e) : 1;
+    CUP2D_CUDA(cudaMemcpyToSymbol(cW, hW, sizeof hW));
   }
   const int mode = raw ? 0 : (old == in ? 1 : 2);
-  adv_fn fn = pick(mode, unr, newton);
+  adv_fn fn = unr == 5 ? pick_flags<5>(mode, cm, one) : pick_flags<10>(mode, cm, one);
   static bool configured[3] = {false, false, false};
   if (!configured[mode]) {
     CUP2D_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, ADV_SMEM));

@@ -48,6 +48,7 @@ private:
 int cup2d_ref_last_iters = 0;
 double cup2d_ref_last_err = 0;
 int cup2d_ref_force_iters = -1; // >=0: cap the loop at this many iterations (harness timing/parity)
+int cup2d_ref_fixed_iters = -1; // the real cuda.cu always runs 1000 (ref_gpu_glue.cpp)
 
 void BiCGSTABSolver::spmv(const std::vector<double> &z, std::vector<double> &y) const {
   // cuda.cu:361-363  y = A_loc z   (COO is row-sorted: rows are pushed in order, main.cpp:7051-7111)

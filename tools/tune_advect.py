@@ -1,4 +1,4 @@
-"""GPU-box sweep of the advect-stage tuning knobs (CUP2D_ADV_UNROLL x CUP2D_ADV_NEWTON).
+"""GPU-box sweep of the advect-stage tuning knobs (CUP2D_ADV_UNROLL x CUP2D_ADV_CONSTMEM x CUP2D_ADV_ONECOPY).
 Each variant runs in its own process (the knobs are read once); reports ms per stage launch at 8192^2
 for both stage kinds and the parity error against the numpy oracle at 256^2."""
 import json
@@ -48,18 +48,19 @@ for name, args in (("stage1", ("vel", "vel", "tmpV", 0.5)), ("stage2", ("tmpV", 
     p = sim.profile_read(); sim.profile(False)
     ms, n = p["advect_stage_kernel"]; res[name] = ms / n
     sim.upload_blocks("vel", blk.reshape(-1))
-print(json.dumps({"unroll": os.environ.get("CUP2D_ADV_UNROLL"), "newton": os.environ.get("CUP2D_ADV_NEWTON"),
+print(json.dumps({"unroll": os.environ.get("CUP2D_ADV_UNROLL"), "constmem": os.environ.get("CUP2D_ADV_CONSTMEM"), "onecopy": os.environ.get("CUP2D_ADV_ONECOPY"),
                   "ms_stage1": res["stage1"], "ms_stage2": res["stage2"], "rel_err": errs,
                   "Gcell_s_stage1": N*N/res["stage1"]/1e6, "Gcell_s_stage2": N*N/res["stage2"]/1e6}))
 '''
 out = []
-for unr in (1, 2, 5, 10):
-    for nw in (1, 2):
-        env = dict(os.environ, CUP2D_ADV_UNROLL=str(unr), CUP2D_ADV_NEWTON=str(nw))
-        r = subprocess.run([sys.executable, "-c", CHILD % {"root": ROOT}], env=env, stdout=subprocess.PIPE,
-                           stderr=subprocess.PIPE, text=True)
-        line = r.stdout.strip().splitlines()[-1] if r.stdout.strip() else json.dumps({"unroll": unr, "newton": nw, "error": r.stderr[-400:]})
-        print(line, flush=True)
-        out.append(line)
+for unr in (5, 10):
+    for cm in (0, 1):
+        for one in (0, 1):
+            env = dict(os.environ, CUP2D_ADV_UNROLL=str(unr), CUP2D_ADV_CONSTMEM=str(cm), CUP2D_ADV_ONECOPY=str(one))
+            r = subprocess.run([sys.executable, "-c", CHILD % {"root": ROOT}], env=env, stdout=subprocess.PIPE,
+                               stderr=subprocess.PIPE, text=True)
+            line = r.stdout.strip().splitlines()[-1] if r.stdout.strip() else json.dumps({"unroll": unr, "cm": cm, "one": one, "error": r.stderr[-400:]})
+            print(line, flush=True)
+            out.append(line)
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
 open(os.path.join(ROOT, "gpurun_out", "tune_advect.jsonl"), "w").write("\n".join(out) + "\n")
