@@ -27,7 +27,8 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-HARNESS = os.path.join(ROOT, "oracle", "_ref", "ref_harness")
+HARNESS = os.path.join(ROOT, "oracle", "_ref", "ref_harness")          # main.cpp + CPU restatement of cuda.cu
+HARNESS_GPU = os.path.join(ROOT, "oracle", "_ref", "ref_harness_gpu")  # main.cpp + the reference's own cuda.cu
 
 # algorithmic bytes per cell per launch (DESIGN.md "Kernels")
 ALG_BYTES = {
@@ -43,6 +44,12 @@ ALG_BYTES = {
     "k_final": 56.0,                  # x, z, r, t, rhat read; x, r written
     "memset(udef)": 16.0,
 }
+
+
+def load_traffic():
+    """measured DRAM bytes per cell per launch of each kernel (ncu --set full, profiles/traffic.json)"""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    return json.load(open(p)) if os.path.exists(p) else {}
 
 
 def load_peaks():
@@ -105,28 +112,40 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def run_harness_time(level, reps, kiter, threads):
+def gpu_visible():
+    try:
+        return subprocess.run(["nvidia-smi", "-L"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL).returncode == 0
+    except Exception:
+        return False
+
+
+def run_harness_time(binary, level, reps, kiter, threads):
     env = dict(os.environ, OMP_NUM_THREADS=str(threads), OMP_PROC_BIND="close")
-    out = subprocess.run([HARNESS, "time", str(level), str(reps), str(kiter)], env=env, check=True,
+    out = subprocess.run([binary, "time", str(level), str(reps), str(kiter)], env=env, check=True,
                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True).stdout
     return json.loads(out.strip().splitlines()[-1])
 
 
 def cpu_composite(level, reps, kiter):
-    """Reference CPU path on a bounded sample: cells*(2+K) / (2 t_stage + t_rhs + K t_iter + t_correct)."""
+    """The reference's own path on a bounded sample: cells*(2+K) / (2 t_stage + t_rhs + K t_iter + t_correct).
+    Operators = unmodified main.cpp under OpenMP on all host cores.  Poisson iteration = the reference's own
+    cuda.cu (cuSPARSE/cuBLAS, its only solver) when a GPU is visible, else the CPU restatement of it."""
     threads = os.cpu_count() or 1
-    t = run_harness_time(level, reps, kiter, threads)
+    use_gpu = os.path.exists(HARNESS_GPU) and gpu_visible()
+    t = run_harness_time(HARNESS_GPU if use_gpu else HARNESS, level, reps, kiter, threads)
     step_s = 2 * t["t_stage"] + t["t_rhs"] + kiter * t["t_poisson_iter"] + t["t_correct"]
     val = t["cells"] * (2 + kiter) / step_s / 1e6
     N = t["N"]
     return {
         "value": val, "unit": "Mcell-updates/s", "cores": t["threads"], "kind": "reference",
         "sample": f"{N}x{N} uniform grid (L={level}), Taylor-Green, median of {reps} reps per operator; "
-                  f"operators = unmodified reference main.cpp under OpenMP; Poisson iteration = CPU restatement "
-                  f"of cuda.cu (the reference has no CPU solver); composite = 2 stages + RHS + {kiter} iterations + correction",
+                  f"operators = unmodified reference main.cpp under OpenMP on {t['threads']} threads; "
+                  f"Poisson iteration = {t.get('poisson_solver', 'CPU restatement of cuda.cu')}; "
+                  f"composite = 2 stages + RHS + {kiter} iterations + correction",
         "ms_per_step": step_s * 1e3,
         "stage_Mcells_s": t["cells"] / t["t_stage"] / 1e6,
         "poisson_iter_Mcells_s": t["cells"] / t["t_poisson_iter"] / 1e6 if t["t_poisson_iter"] > 0 else None,
+        "poisson_solver": t.get("poisson_solver"),
     }
 
 
@@ -302,8 +321,11 @@ def main():
     top = kernels[0] if kernels else None
     roofline = None
     if top:
+        tr = load_traffic().get(top["kernel"])
         roofline = {"kernel": top["kernel"], "bound": "hbm", "achieved": top["achieved_GBs"], "peak": peak,
-                    "unit": "GB/s", "frac": top["frac_hbm"], "traffic": None, "peak_source": peak_src,
+                    "unit": "GB/s", "frac": top["frac_hbm"],
+                    "traffic": tr * cells_loc if tr else None, "traffic_unit": "bytes per launch (ncu dram read+write, profiles/)",
+                    "peak_source": peak_src,
                     "ms_per_launch": top["ms_per_launch"], "share_of_step": top["share_of_step"]}
     extra = {}
     if adv:

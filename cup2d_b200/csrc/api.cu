@@ -114,6 +114,8 @@ int cup2d_block_order(int32_t bpdx, int32_t bpdy, int32_t level, int32_t *out) {
   return CUP2D_OK;
 }
 
+static int alloc_device_state(cup2d_sim *s);
+
 static int build_tables(cup2d_sim *s) {
   const int nbx = s->nbx, nby = s->nby;
   const int64_t nloc = s->nloc, gb = s->gbegin, ge = s->gbegin + s->nloc;
@@ -296,11 +298,55 @@ int cup2d_create(const cup2d_config *cfg, cup2d_sim **out) {
   int rc = init_topology(cfg, &s);
   if (rc) return rc;
   s->num_sms = prop.multiProcessorCount;
-  rc = upload_tables(s);
+  rc = alloc_device_state(s);
   if (rc) {
     cup2d_destroy(s);
     return rc;
   }
+  *out = s;
+  return CUP2D_OK;
+}
+
+// Poisson-only context from a bare block neighbour table (what the LocalSpMatDnVec adapter derives from
+// the reference's COO pushes, dropin/local_spmat_adapter.cpp): no (i,j) geometry, no advect tiles.
+int cup2d_poisson_create(int64_t nblocks, const int32_t *nbr, int32_t device, cup2d_sim **out) {
+  CUP2D_REQUIRE(nblocks > 0 && nbr && out, "cup2d_poisson_create: bad arguments");
+  CUP2D_REQUIRE(nblocks * 64 < (1LL << 31), "cup2d_poisson_create: more than 2^31 rows");
+  for (int64_t k = 0; k < 4 * nblocks; k++)
+    CUP2D_REQUIRE(nbr[k] >= -1 && nbr[k] < nblocks, "cup2d_poisson_create: neighbour slot out of range");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    set_error("cup2d_poisson_create: no CUDA device visible; this library has no CPU fallback");
+    return CUP2D_ENOGPU;
+  }
+  CUP2D_REQUIRE(device >= 0 && device < ndev, "cup2d_poisson_create: bad device ordinal");
+  CUP2D_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CUP2D_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) {
+    set_error(std::string("cup2d_poisson_create: device '") + prop.name + "' is not sm_100");
+    return CUP2D_ENOGPU;
+  }
+  cup2d_sim *s = new cup2d_sim;
+  s->nglobal = s->nloc = s->nslots = nblocks;
+  s->device = device;
+  s->h = 1.0;
+  s->poisson_only = true;
+  s->rank_begin = {0, nblocks};
+  s->h_nbr.assign(nbr, nbr + 4 * nblocks);
+  s->num_sms = prop.multiProcessorCount;
+  int rc = alloc_device_state(s);
+  if (rc) {
+    cup2d_destroy(s);
+    return rc;
+  }
+  *out = s;
+  return CUP2D_OK;
+}
+
+static int alloc_device_state(cup2d_sim *s) {
+  int rc = upload_tables(s);
+  if (rc) return rc;
   CUP2D_CUDA(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
   for (int f = 0; f < CUP2D_NFIELDS; f++) {
     const size_t bytes = (size_t)s->nslots * 64 * dim_of(f) * sizeof(double);
@@ -328,7 +374,6 @@ int cup2d_create(const cup2d_config *cfg, cup2d_sim **out) {
   s->comm.nranks = 1; // raised to nranks by cup2d_peer_attach
   s->comm.mb[s->rank] = s->d_mailbox;
   CUP2D_CUDA(cudaDeviceSynchronize());
-  *out = s;
   return CUP2D_OK;
 }
 
@@ -459,6 +504,7 @@ int cup2d_advect_diffuse_stage(cup2d_sim *s, int in_f, int old_f, int out_f, dou
   CHECK_SIM(s);
   CUP2D_REQUIRE(in_f >= 0 && in_f < 3 && old_f >= 0 && old_f < 3 && out_f >= 0 && out_f < 3, "advect: vector field ids only");
   CUP2D_REQUIRE(out_f != in_f, "advect: out must differ from in (halo cells of in are read by other tiles)");
+  CUP2D_REQUIRE(!s->poisson_only, "advect: Poisson-only context (cup2d_poisson_create) has no grid geometry");
   CUP2D_CUDA(cudaSetDevice(s->device));
   int rc = need_peers(s);
   if (rc) return rc;
@@ -468,6 +514,7 @@ int cup2d_advect_diffuse_stage(cup2d_sim *s, int in_f, int old_f, int out_f, dou
 int cup2d_advect_diffuse_rhs(cup2d_sim *s, int in_f, int out_f, double dt) {
   CHECK_SIM(s);
   CUP2D_REQUIRE(in_f >= 0 && in_f < 3 && out_f >= 0 && out_f < 3 && in_f != out_f, "advect_rhs: bad field ids");
+  CUP2D_REQUIRE(!s->poisson_only, "advect: Poisson-only context (cup2d_poisson_create) has no grid geometry");
   CUP2D_CUDA(cudaSetDevice(s->device));
   int rc = need_peers(s);
   if (rc) return rc;
@@ -476,6 +523,7 @@ int cup2d_advect_diffuse_rhs(cup2d_sim *s, int in_f, int out_f, double dt) {
 }
 int cup2d_advect_diffuse_rk2(cup2d_sim *s, double dt) {
   CHECK_SIM(s);
+  CUP2D_REQUIRE(!s->poisson_only, "advect: Poisson-only context (cup2d_poisson_create) has no grid geometry");
   CUP2D_CUDA(cudaSetDevice(s->device));
   int rc = need_peers(s);
   if (rc) return rc;

@@ -53,6 +53,7 @@ struct cup2d_sim {
   std::vector<int32_t> halo_gid;       // global id of every halo slot (slot = nloc + k), sorted
   std::vector<int32_t> halo_owner;     // owning rank per halo slot
   std::vector<int> h_nbr, h_tiles, h_torg, h_halo_src; // host copies of the device tables
+  bool poisson_only = false;           // created by cup2d_poisson_create: neighbour table only, no tiles
   bool plan_only = false;              // created by cup2d_plan_create: topology only, no CUDA state
   cudaStream_t stream = nullptr;
   // device tables

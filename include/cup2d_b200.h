@@ -121,6 +121,13 @@ int cup2d_peer_attach(cup2d_sim *s, const void *all_blobs);
 /* Explicit halo refresh of one field (normally implicit inside the operators). */
 int cup2d_halo_exchange(cup2d_sim *s, int field);
 
+/* ---- Poisson-only context (the LocalSpMatDnVec boundary, cuda.h:26-79) ---- */
+/* nbr[4*k..4*k+3] = block indices of the W,E,S,N neighbours of block k on the same level, -1 = wall
+ * (what the reference's COO rows main.cpp:7074-7107 encode on a uniform level).  The context supports
+ * field upload/download of CUP2D_TMP (b) and CUP2D_PRES (x0 / x) and cup2d_poisson_solve; rows are
+ * numbered block-major, row = 64*k + 8*iy + ix, exactly like Solver::CellIndexer (main.cpp:5753-5771). */
+int cup2d_poisson_create(int64_t nblocks, const int32_t *nbr, int32_t device, cup2d_sim **out);
+
 /* ---- host-side topology plan (no GPU needed; used by the CPU tests of the multi-rank logic) ---- */
 /* Same config as cup2d_create, but builds only the host tables: SFC-range partition, halo plan
  * (which face-neighbour blocks this rank pulls from which owner), neighbour table, advect tiles.
