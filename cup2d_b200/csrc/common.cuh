@@ -104,35 +104,48 @@ __device__ __forceinline__ unsigned long long ld_relaxed_sys(const unsigned long
   asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
 }
-// All-reduce of NS sums + 1 max across ranks, executed by ONE thread per rank (the finalizer of a
-// grid reduction).  Every rank writes its values into every peer's mailbox over NVLink, then combines
-// all contributions in rank order, so the result is bitwise identical on all ranks.
+// All-reduce of NS sums + 1 max across ranks, executed by ONE WARP per rank (warp 0 of the last CTA of a
+// grid reduction; every lane enters with the same local totals).  Lane r < nranks writes this rank's
+// values into rank r's mailbox over NVLink (one peer per lane: one NVLink round trip in total, not one
+// per peer), then waits for rank r's contribution in the local mailbox; the contributions are combined
+// in rank order with shuffles, so the result is bitwise identical on every lane and on every rank.
 template <int NS>
-__device__ __forceinline__ void peer_allreduce(const Comm &c, double (&tot)[NS], double &mx) {
+__device__ __forceinline__ void peer_allreduce(const Comm &c, double (&tot)[NS], double &mx, int lane) {
   static_assert(NS + 1 <= MB_RED_STRIDE - 1, "reduction slot too small");
   if (c.nranks <= 1) return;
   unsigned long long *mine = c.mb[c.rank];
-  const unsigned long long ep = ld_relaxed_sys(mine + MB_EPOCH) + 1;
-  st_relaxed_sys(mine + MB_EPOCH, ep);
-  const int slot = MB_RED + (c.rank * 2 + (int)(ep & 1)) * MB_RED_STRIDE;
-  for (int r = 0; r < c.nranks; r++) {
-    unsigned long long *dst = c.mb[r] + slot;
+  unsigned long long ep = 0;
+  if (lane == 0) {
+    ep = ld_relaxed_sys(mine + MB_EPOCH) + 1;
+    st_relaxed_sys(mine + MB_EPOCH, ep);
+  }
+  ep = __shfl_sync(0xffffffffu, ep, 0);
+  const int par = (int)(ep & 1);
+  if (lane < c.nranks) {
+    unsigned long long *dst = c.mb[lane] + MB_RED + (c.rank * 2 + par) * MB_RED_STRIDE;
 #pragma unroll
     for (int k = 0; k < NS; k++) st_relaxed_sys(dst + 1 + k, (unsigned long long)__double_as_longlong(tot[k]));
     st_relaxed_sys(dst + 1 + NS, (unsigned long long)__double_as_longlong(mx));
     __threadfence_system();
     st_release_sys(dst, ep);
   }
+  double v[NS + 1];
+#pragma unroll
+  for (int k = 0; k <= NS; k++) v[k] = 0.0;
+  if (lane < c.nranks) {
+    const unsigned long long *src = mine + MB_RED + (lane * 2 + par) * MB_RED_STRIDE;
+    while (ld_acquire_sys(src) < ep) { }
+#pragma unroll
+    for (int k = 0; k <= NS; k++) v[k] = __longlong_as_double((long long)ld_relaxed_sys(src + 1 + k));
+  }
   double acc[NS];
 #pragma unroll
   for (int k = 0; k < NS; k++) acc[k] = 0;
   double am = 0;
   for (int r = 0; r < c.nranks; r++) {
-    const unsigned long long *src = mine + MB_RED + (r * 2 + (int)(ep & 1)) * MB_RED_STRIDE;
-    while (ld_acquire_sys(src) < ep) { }
 #pragma unroll
-    for (int k = 0; k < NS; k++) acc[k] += __longlong_as_double((long long)ld_relaxed_sys(src + 1 + k));
-    am = fmax(am, __longlong_as_double((long long)ld_relaxed_sys(src + 1 + NS)));
+    for (int k = 0; k < NS; k++) acc[k] += __shfl_sync(0xffffffffu, v[k], r);
+    am = fmax(am, __shfl_sync(0xffffffffu, v[NS], r));
   }
 #pragma unroll
   for (int k = 0; k < NS; k++) tot[k] = acc[k];
@@ -209,20 +222,22 @@ __device__ __forceinline__ void grid_reduce(double (&sums)[NS], double mx, doubl
     s_red[NS * (NT / 32) + warp] = am;
   }
   __syncthreads();
-  if (threadIdx.x == 0) {
+  if (warp == 0) { // warp 0 finishes: lane 0 sums the warps in order, the warp all-reduces across GPUs
     double tot[NS];
+    double m = 0;
 #pragma unroll
     for (int k = 0; k < NS; k++) {
       double a = 0;
       for (int w = 0; w < NT / 32; w++) a += s_red[k * (NT / 32) + w];
       tot[k] = a;
     }
-    double m = 0;
     for (int w = 0; w < NT / 32; w++) m = fmax(m, s_red[NS * (NT / 32) + w]);
-    *counter = 0;
-    peer_allreduce<NS>(comm, tot, m);
-    fin(tot, m);
-    __threadfence();
+    peer_allreduce<NS>(comm, tot, m, lane);
+    if (lane == 0) {
+      *counter = 0;
+      fin(tot, m);
+      __threadfence();
+    }
   }
 }
 
