@@ -85,9 +85,10 @@ def to_blocks(a, order, dim=1):
 
 def from_blocks(flat, order, dim=1):
     nblk = len(order)
-    nb = int(round(np.sqrt(nblk)))
+    order = np.asarray(order)
+    nbx, nby = int(order[:, 0].max()) + 1, int(order[:, 1].max()) + 1
     blk = np.asarray(flat).reshape(nblk, BS, BS, dim)
-    outs = [np.empty((nb * BS, nb * BS)) for _ in range(dim)]
+    outs = [np.empty((nby * BS, nbx * BS)) for _ in range(dim)]
     for k, (i, j) in enumerate(order):
         for c in range(dim):
             outs[c][j * BS:(j + 1) * BS, i * BS:(i + 1) * BS] = blk[k, :, :, c]
@@ -170,16 +171,16 @@ def derivative(U, um3, um2, um1, u, up1, up2, up3):
 def advect_diffuse(u, v, h, nu, dt):
     """KernelAdvectDiffuse::operator() (main.cpp:5441-5503): undivided RHS written to tmpV."""
     g = 3
-    N = u.shape[0]
+    NY, NX = u.shape
     up, vp = pad_vector(u, v, g)
     dfac = nu * dt
     afac = -dt * h
 
     def sx(a, k):  # a(ix+k, iy)
-        return a[g:g + N, g + k:g + k + N]
+        return a[g:g + NY, g + k:g + k + NX]
 
     def sy(a, k):  # a(ix, iy+k)
-        return a[g + k:g + k + N, g:g + N]
+        return a[g + k:g + k + NY, g:g + NX]
 
     dudx = derivative(u, sx(up, -3), sx(up, -2), sx(up, -1), u, sx(up, 1), sx(up, 2), sx(up, 3))
     dudy = derivative(v, sy(up, -3), sy(up, -2), sy(up, -1), u, sy(up, 1), sy(up, 2), sy(up, 3))
@@ -211,13 +212,13 @@ def rk2(u, v, h, nu, dt):
 
 def pressure_rhs(u, v, udu, udv, chi, h, dt):
     """pressure_rhs::operator() (main.cpp:6105-6139)"""
-    N = u.shape[0]
+    NY, NX = u.shape
     up, vp = pad_vector(u, v, 1)
     dup, dvp = pad_vector(udu, udv, 1)
     fac = 0.5 * h / dt
-    c = slice(1, 1 + N)
-    div_v = up[c, 2:] - up[c, :-2] + vp[2:, c] - vp[:-2, c]
-    div_u = dup[c, 2:] - dup[c, :-2] + dvp[2:, c] - dvp[:-2, c]
+    cy, cx = slice(1, 1 + NY), slice(1, 1 + NX)
+    div_v = up[cy, 2:] - up[cy, :-2] + vp[2:, cx] - vp[:-2, cx]
+    div_u = dup[cy, 2:] - dup[cy, :-2] + dvp[2:, cx] - dvp[:-2, cx]
     return fac * div_v - fac * chi * div_u
 
 
@@ -225,10 +226,10 @@ def laplacian_neumann(p):
     """5-point undivided Laplacian with constant-extrapolation ghosts = the Poisson matrix rows of
     main.cpp:7074-7107 (interior: +1,+1,-4,+1,+1; domain edge: missing neighbour omitted, diagonal
     = -(number of neighbours)) and pressure_rhs1's stencil (main.cpp:6209-6230)."""
-    N = p.shape[0]
+    NY, NX = p.shape
     pp = pad_scalar(p, 1)
-    c = slice(1, 1 + N)
-    return pp[c, :-2] + pp[c, 2:] + pp[:-2, c] + pp[2:, c] - 4 * p
+    cy, cx = slice(1, 1 + NY), slice(1, 1 + NX)
+    return pp[cy, :-2] + pp[cy, 2:] + pp[:-2, cx] + pp[2:, cx] - 4 * p
 
 
 def pressure_rhs1(tmp, pold):
@@ -238,11 +239,11 @@ def pressure_rhs1(tmp, pold):
 
 def grad_p(p, h, dt):
     """pressureCorrectionKernel::operator() (main.cpp:6021-6043)"""
-    N = p.shape[0]
+    NY, NX = p.shape
     pp = pad_scalar(p, 1)
     pfac = -0.5 * dt * h
-    c = slice(1, 1 + N)
-    return pfac * (pp[c, 2:] - pp[c, :-2]), pfac * (pp[2:, c] - pp[:-2, c])
+    cy, cx = slice(1, 1 + NY), slice(1, 1 + NX)
+    return pfac * (pp[cy, 2:] - pp[cy, :-2]), pfac * (pp[2:, cx] - pp[:-2, cx])
 
 
 # --------------------------------------------------------------------------------------------
@@ -273,11 +274,11 @@ def precond(v):
     global _P_INV
     if _P_INV is None:
         _P_INV = build_P_inv()
-    N = v.shape[0]
-    nb = N // BS
-    blk = v.reshape(nb, BS, nb, BS).transpose(0, 2, 1, 3).reshape(nb, nb, BS * BS)
+    NY, NX = v.shape
+    nby, nbx = NY // BS, NX // BS
+    blk = v.reshape(nby, BS, nbx, BS).transpose(0, 2, 1, 3).reshape(nby, nbx, BS * BS)
     z = blk @ _P_INV.T
-    return z.reshape(nb, nb, BS, BS).transpose(0, 2, 1, 3).reshape(N, N)
+    return z.reshape(nby, nbx, BS, BS).transpose(0, 2, 1, 3).reshape(NY, NX)
 
 
 def bicgstab(b, x0, max_error=0.0, max_rel_error=0.0, max_restarts=0, max_iter=1000,
@@ -339,7 +340,7 @@ def bicgstab(b, x0, max_error=0.0, max_rel_error=0.0, max_restarts=0, max_iter=1
 def step(u, v, pres, nu, cfl, extent=1.0, kiter=1000, tol=0.0, tol_rel=0.0, max_restarts=100,
          chi=None, udef=None, dt=None):
     """Returns dict(dt, u, v, p, b, x, iters)."""
-    N = u.shape[0]
+    N = max(u.shape)  # h0 = extent / max(bpdx, bpdy) / 8 / 2^level  (main.cpp:6338)
     h = extent / N
     if dt is None:
         dt = compute_dt(u, v, h, nu, cfl)

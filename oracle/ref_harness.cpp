@@ -37,7 +37,7 @@ extern int cup2d_ref_fixed_iters;
 
 namespace {
 enum Mode { ORDER, OPS, STEPS, TIME } g_mode;
-int g_L, g_N, g_nsteps, g_reps, g_kiter;
+int g_L, g_N, g_NY, g_bx = 1, g_by = 1, g_nsteps, g_reps, g_kiter;
 double g_nu, g_dt, g_cfl;
 std::string g_in, g_out;
 int g_calls = 0;
@@ -48,7 +48,7 @@ double now() {
   return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
 void read_input(int nfields) {
-  g_input.resize((size_t)nfields * g_N * g_N);
+  g_input.resize((size_t)nfields * g_N * g_NY);
   FILE *f = fopen(g_in.c_str(), "rb");
   if (!f || fread(g_input.data(), sizeof(double), g_input.size(), f) != g_input.size()) {
     fprintf(stderr, "ref_harness: cannot read %s\n", g_in.c_str());
@@ -80,14 +80,14 @@ void gather(Grid *g, int dim, double *c0, double *c1) {
   }
 }
 void write_field(Grid *g, int dim) {
-  std::vector<double> a((size_t)g_N * g_N), b((size_t)g_N * g_N);
+  std::vector<double> a((size_t)g_N * g_NY), b((size_t)g_N * g_NY);
   gather(g, dim, a.data(), b.data());
   fwrite(a.data(), sizeof(double), a.size(), g_fout);
   if (dim == 2) fwrite(b.data(), sizeof(double), b.size(), g_fout);
 }
 void write_vec(const std::vector<double> &x) {
   // solver vectors are block-major in `infos` order (main.cpp:5753-5771): back to global order
-  std::vector<double> a((size_t)g_N * g_N);
+  std::vector<double> a((size_t)g_N * g_NY);
   auto &infos = var.tmp->infos;
   for (size_t i = 0; i < infos.size(); i++) {
     const int bi = infos[i].index[0], bj = infos[i].index[1];
@@ -155,11 +155,11 @@ void corr_update() { // main.cpp:7180-7187
   }
 }
 void seed_taylor_green() {
-  const size_t n2 = (size_t)g_N * g_N;
+  const size_t n2 = (size_t)g_N * g_NY;
   g_input.assign(6 * n2, 0.0);
-  for (int iy = 0; iy < g_N; iy++)
+  for (int iy = 0; iy < g_NY; iy++)
     for (int ix = 0; ix < g_N; ix++) {
-      double x = (ix + 0.5) / g_N, y = (iy + 0.5) / g_N;
+      double x = (ix + 0.5) / g_N, y = (iy + 0.5) / g_NY;
       g_input[0 * n2 + (size_t)iy * g_N + ix] = sin(2 * M_PI * x) * cos(2 * M_PI * y);
       g_input[1 * n2 + (size_t)iy * g_N + ix] = -cos(2 * M_PI * x) * sin(2 * M_PI * y);
       g_input[2 * n2 + (size_t)iy * g_N + ix] = cos(2 * M_PI * x) * cos(2 * M_PI * y);
@@ -186,7 +186,7 @@ void do_order() {
   fclose(f);
 }
 void do_ops() {
-  const size_t n2 = (size_t)g_N * g_N;
+  const size_t n2 = (size_t)g_N * g_NY;
   read_input(6);
   const double *in = g_input.data();
   sim.nu = g_nu;
@@ -209,7 +209,7 @@ void do_ops() {
 }
 void do_time() {
   seed_taylor_green();
-  const size_t n2 = (size_t)g_N * g_N;
+  const size_t n2 = (size_t)g_N * g_NY;
   const double *in = g_input.data();
   scatter(var.vel, 2, in, in + n2);
   scatter(var.vold, 2, in, in + n2);
@@ -218,8 +218,8 @@ void do_time() {
   double h = var.vel->infos[0].h, umax = field_umax();
   sim.nu = 1e-3;
   sim.dt = std::min(0.25 * h * h / (sim.nu + 0.25 * h * umax), 0.5 * h / (umax + 1e-8));
-  double t_stage = median_time(g_reps, [] { call_advect(); rk_update(0.5); scatter(var.vel, 2, g_input.data(), g_input.data() + (size_t)g_N * g_N); });
-  double t_scatter = median_time(g_reps, [] { scatter(var.vel, 2, g_input.data(), g_input.data() + (size_t)g_N * g_N); });
+  double t_stage = median_time(g_reps, [] { call_advect(); rk_update(0.5); scatter(var.vel, 2, g_input.data(), g_input.data() + (size_t)g_N * g_NY); });
+  double t_scatter = median_time(g_reps, [] { scatter(var.vel, 2, g_input.data(), g_input.data() + (size_t)g_N * g_NY); });
   t_stage -= t_scatter;
   double t_rhs = median_time(g_reps, [] { call_rhs(); call_rhs1(); });
   double t_corr = median_time(g_reps, [] { call_gradp(); corr_update(); });
@@ -253,7 +253,7 @@ void cup2d_ref_hook(int op, void *buf, int count) {
     // Poisson matrix); call 1: time the operators on the state after that step.
     if (call == 0) {
       seed_taylor_green();
-      const size_t n2t = (size_t)g_N * g_N;
+      const size_t n2t = (size_t)g_N * g_NY;
       scatter(var.vel, 2, g_input.data(), g_input.data() + n2t);
       *(double *)buf = field_umax();
       cup2d_ref_force_iters = 2;
@@ -263,7 +263,7 @@ void cup2d_ref_hook(int op, void *buf, int count) {
     exit(0);
   }
   // STEPS: call 0 = before step 0 (seed), call k = after k steps (record)
-  const size_t n2 = (size_t)g_N * g_N;
+  const size_t n2 = (size_t)g_N * g_NY;
   if (call == 0) {
     read_input(6);
     const double *in = g_input.data();
@@ -293,7 +293,10 @@ int main(int argc, char **argv) {
   }
   std::string mode = argv[1];
   g_L = atoi(argv[2]);
-  g_N = _BS_ << g_L;
+  g_bx = getenv("CUP2D_REF_BPDX") ? atoi(getenv("CUP2D_REF_BPDX")) : 1;
+  g_by = getenv("CUP2D_REF_BPDY") ? atoi(getenv("CUP2D_REF_BPDY")) : 1;
+  g_N = (_BS_ << g_L) * g_bx;   // cells per row; g_NY rows
+  g_NY = (_BS_ << g_L) * g_by;
   g_nu = 1e-3;
   g_cfl = 0.5;
   if (mode == "order" && argc == 4) { g_mode = ORDER; g_out = argv[3]; }
@@ -309,7 +312,10 @@ int main(int argc, char **argv) {
   snprintf(a_lm, sizeof a_lm, "%d", g_L + 1);
   snprintf(a_nu, sizeof a_nu, "%.17g", g_nu);
   snprintf(a_cfl, sizeof a_cfl, "%.17g", g_cfl);
-  const char *args[] = {"ref_main", "-AdaptSteps", "1000000", "-bpdx", "1", "-bpdy", "1", "-CFL", a_cfl,
+  char a_bx[16], a_by[16];
+  snprintf(a_bx, sizeof a_bx, "%d", g_bx);
+  snprintf(a_by, sizeof a_by, "%d", g_by);
+  const char *args[] = {"ref_main", "-AdaptSteps", "1000000", "-bpdx", a_bx, "-bpdy", a_by, "-CFL", a_cfl,
                         "-Ctol", "0", "-extent", "1", "-lambda", "1e7", "-levelMax", a_lm, "-levelStart", a_ls,
                         "-maxPoissonIterations", "1000", "-maxPoissonRestarts", "0", "-nu", a_nu,
                         "-poissonTol", "0", "-poissonTolRel", "0", "-Rtol", "1e300", "-tdump", "0",

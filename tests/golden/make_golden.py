@@ -20,8 +20,11 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 HARNESS = os.path.join(ROOT, "oracle", "_ref", "ref_harness")
 
 
-def run(*args):
-    subprocess.run([HARNESS, *map(str, args)], check=True, stderr=subprocess.DEVNULL)
+def run(*args, bpd=(1, 1)):
+    # one OpenMP thread: the threaded dot products of the CPU solver restatement are then summed in a fixed
+    # order and the fixtures regenerate bit-identically
+    env = dict(os.environ, CUP2D_REF_BPDX=str(bpd[0]), CUP2D_REF_BPDY=str(bpd[1]), OMP_NUM_THREADS="1")
+    subprocess.run([HARNESS, *map(str, args)], check=True, stderr=subprocess.DEVNULL, env=env)
 
 
 def taylor_green(N):
@@ -50,6 +53,41 @@ def make_inputs(kind, L, seed):
         chi = np.exp(-((X - 0.4) ** 2 + (Y - 0.55) ** 2) / 0.02)
         udu, udv = 0.3 * np.sin(3 * X + Y), 0.2 * np.cos(2 * Y - X)
     return [np.ascontiguousarray(a, dtype=np.float64) for a in (u, v, p, chi, udu, udv)]
+
+
+def gen_rect(tmp):
+    """rectangular domains (bpdx != bpdy): the non-regular branch of the space-filling curve
+    (main.cpp:6358-6376) and operators / steps on a 2x1 box (h0 = extent/max(bpdx,bpdy)/8)."""
+    for bx, by, L in ((2, 1, 2), (3, 2, 1), (1, 2, 2)):
+        out = os.path.join(tmp, "order.bin")
+        run("order", L, out, bpd=(bx, by))
+        np.save(os.path.join(HERE, f"order_{bx}x{by}_L{L}.npy"), np.fromfile(out, dtype=np.int32).reshape(-1, 2))
+    bx, by, L = 2, 1, 2
+    NX, NY = (8 << L) * bx, (8 << L) * by
+    rng = np.random.default_rng(99)
+    x = (np.arange(NX) + 0.5) / NX
+    y = (np.arange(NY) + 0.5) / NY
+    X, Y = np.meshgrid(x, y)
+    u = np.sin(2 * np.pi * X) * np.cos(2 * np.pi * Y) + 0.05 * rng.uniform(-1, 1, (NY, NX))
+    v = -np.cos(2 * np.pi * X) * np.sin(2 * np.pi * Y) + 0.05 * rng.uniform(-1, 1, (NY, NX))
+    p = np.cos(2 * np.pi * X) * np.cos(2 * np.pi * Y)
+    chi = np.exp(-((X - 0.4) ** 2 + (Y - 0.55) ** 2) / 0.02)
+    udu, udv = 0.3 * np.sin(3 * X + Y), 0.2 * np.cos(2 * Y - X)
+    ins = [np.ascontiguousarray(a) for a in (u, v, p, chi, udu, udv)]
+    fin, fout = os.path.join(tmp, "in.bin"), os.path.join(tmp, "out.bin")
+    np.concatenate([a.ravel() for a in ins]).tofile(fin)
+    nu, dt = 1e-3, 2e-3
+    run("ops", L, repr(nu), repr(dt), fin, fout, bpd=(bx, by))
+    o = np.fromfile(fout).reshape(6, NY, NX)
+    nsteps, kiter, cfl = 2, 10, 0.5
+    run("steps", L, repr(nu), repr(cfl), nsteps, kiter, fin, fout, bpd=(bx, by))
+    raw = np.fromfile(fout).reshape(nsteps, 1 + 5 * NX * NY)
+    f = raw[:, 1:].reshape(nsteps, 5, NY, NX)
+    np.savez_compressed(os.path.join(HERE, "rect_2x1_L2.npz"), nu=nu, dt=dt, L=L, bpdx=bx, bpdy=by, cfl=cfl, kiter=kiter,
+                        u=ins[0], v=ins[1], p=ins[2], chi=ins[3], udef_u=ins[4], udef_v=ins[5],
+                        adv_u=o[0], adv_v=o[1], rhs=o[2], rhs1=o[3], gradp_u=o[4], gradp_v=o[5],
+                        step_dt=raw[:, 0].copy(), step_u=f[:, 0], step_v=f[:, 1], step_p=f[:, 2])
+    print("rect 2x1", raw[:, 0])
 
 
 def gen_order(tmp):
@@ -95,6 +133,7 @@ if __name__ == "__main__":
     if not os.path.exists(HARNESS):
         sys.exit("build oracle/_ref/ref_harness first: make -C oracle ref")
     with tempfile.TemporaryDirectory() as tmp:
+        gen_rect(tmp)
         gen_order(tmp)
         gen_ops(tmp, "random", 2, 1234, 1e-3, 2.5e-3)
         gen_ops(tmp, "tg", 3, 4321, 1e-3, 1.2e-3)

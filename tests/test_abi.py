@@ -57,3 +57,10 @@ def test_no_cpu_fallback():
         pytest.skip("GPU present")
     with pytest.raises(cup2d_b200.Cup2dError, match="no CPU fallback"):
         cup2d_b200.Simulation(2)
+
+
+@pytest.mark.parametrize("bx,by,lvl", [(2, 1, 2), (3, 2, 1), (1, 2, 2)])
+def test_block_order_rectangular_matches_reference_golden(golden_dir, bx, by, lvl):
+    """non-regular space-filling curve (bounding square not filled, main.cpp:6358-6376)"""
+    g = np.load(os.path.join(golden_dir, f"order_{bx}x{by}_L{lvl}.npy"))
+    assert np.array_equal(cup2d_b200.block_order(bx, by, lvl), g)

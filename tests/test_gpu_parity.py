@@ -255,3 +255,29 @@ def test_reference_driver_with_adapter_matches_reference_gpu_solver(tmp_path):
     f0, f1 = outs[0][:, 1:].reshape(2, 5, N, N), outs[1][:, 1:].reshape(2, 5, N, N)
     # contract: L-inf(u,v,p) < 1e-6; observed ~1e-12 (u,v) / 1e-10 (p) after 1000 Krylov iterations
     assert np.abs(f0[:, :3] - f1[:, :3]).max() < 1e-8
+
+
+def test_rectangular_domain_vs_reference_golden(golden_dir):
+    """2x1 base blocks, level 2 (64x32 cells): operators and two full steps against the reference."""
+    d = np.load(os.path.join(golden_dir, "rect_2x1_L2.npz"))
+    nu, dt, K = float(d["nu"]), float(d["dt"]), int(d["kiter"])
+    sim = cup2d_b200.Simulation(int(d["L"]), bpdx=2, bpdy=1, nu=nu, cfl=float(d["cfl"]))
+    assert abs(sim.h - 1.0 / d["u"].shape[1]) < 1e-18
+    sim.upload("vel", d["u"], d["v"])
+    sim.advect_diffuse_rhs(dt)
+    au, av = sim.download("tmpV")
+    assert rel(au, d["adv_u"]) < 1e-12 and rel(av, d["adv_v"]) < 1e-12
+    sim.upload("tmpV", d["udef_u"], d["udef_v"])
+    sim.upload("chi", d["chi"])
+    sim.upload("pres", d["p"])
+    sim.pressure_rhs(dt)
+    assert rel(sim.download("tmp"), d["rhs1"]) < 1e-13
+    sim.upload("vel", d["u"], d["v"])
+    sim.upload("pres", d["p"])
+    for s in range(len(d["step_dt"])):
+        dts, it, err = sim.step(max_iter=K)
+        assert abs(dts - d["step_dt"][s]) < 1e-15 and it == K
+        u, v = sim.download("vel")
+        assert np.abs(u - d["step_u"][s]).max() < 1e-9 and np.abs(v - d["step_v"][s]).max() < 1e-9
+        assert np.abs(sim.download("pres") - d["step_p"][s]).max() < 1e-9
+    sim.close()
