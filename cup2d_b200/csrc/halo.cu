@@ -11,7 +11,9 @@
 //      loads into the local halo slots (whole 8x8 blocks: 512 B / 1 KB, so the stencil kernels see
 //      remote neighbours exactly like local ones),
 //   4. publishes "done reading" and waits for every peer's "done", so that when the kernel retires
-//      the owners may overwrite the buffer (WAR safety without any host involvement).
+//      the owners may overwrite the buffer (WAR safety without any host involvement).  Inside the
+//      Krylov loop step 4 is skipped: the all-reduce fused into the SpMV kernel that consumes the halo
+//      completes only after every rank finished its pull, and the owner's next write comes after it.
 // No pack/unpack buffers, no host staging, no NCCL call on the critical path.  Payload at 8192^2 on
 // 8 GPUs: ~1500 perimeter blocks -> 1.5 MB (velocity) / 0.75 MB (scalar) per refresh: latency-bound.
 #include "sim.h"
@@ -25,7 +27,7 @@ struct PullArgs {
 __global__ void __launch_bounds__(256)
 halo_pull_kernel(double *__restrict__ dst, PullArgs pa, Comm comm, const int2 *__restrict__ src,
                  int nhalo, int nloc, int blk_doubles, unsigned long long epoch,
-                 unsigned int *counter) {
+                 unsigned int *counter, int done_barrier) {
   __shared__ bool s_last;
   unsigned long long *mine = comm.mb[comm.rank];
   const int tid = threadIdx.x;
@@ -50,6 +52,7 @@ halo_pull_kernel(double *__restrict__ dst, PullArgs pa, Comm comm, const int2 *_
       to[i] = v;
     }
   }
+  if (!done_barrier) return; // the caller guarantees a later all-reduce orders the owners' next write
   __syncthreads();
   if (tid == 0) {
     __threadfence();
@@ -65,7 +68,7 @@ halo_pull_kernel(double *__restrict__ dst, PullArgs pa, Comm comm, const int2 *_
   if (tid == 0) *counter = 0;
 }
 
-int halo_exchange_ptr(cup2d_sim *s, double *base, int dim, int peer_index) {
+int halo_exchange_ptr(cup2d_sim *s, double *base, int dim, int peer_index, bool done_barrier) {
   if (s->nranks == 1) return CUP2D_OK;
   if (!s->peers_attached) {
     set_error("halo exchange before cup2d_peer_attach");
@@ -80,7 +83,7 @@ int halo_exchange_ptr(cup2d_sim *s, double *base, int dim, int peer_index) {
   if (grid < 1) grid = 1;
   ProfScope prof(s, KC_HALO);
   halo_pull_kernel<<<grid, 256, 0, s->stream>>>(base, pa, s->comm, reinterpret_cast<const int2 *>(s->d_halo_src),
-                                                (int)s->nhalo, (int)s->nloc, 64 * dim, s->epoch, s->d_counter);
+                                                (int)s->nhalo, (int)s->nloc, 64 * dim, s->epoch, s->d_counter, done_barrier ? 1 : 0);
   s->launches++;
   CUP2D_CUDA(cudaGetLastError());
   return CUP2D_OK;

@@ -377,7 +377,7 @@ int poisson_solve(cup2d_sim *s, double tol_abs, double tol_rel, int max_restarts
         ProfScope prof(s, KC_PUPDATE);
         k_pupdate<<<grid, NT, 0, s->stream>>>(s->kr, s->krhat, s->kp, s->knu, s->kz, nrows, s->d_state);
       }
-      if (s->nranks > 1 && (rc = halo_exchange_ptr(s, s->kz, 1, CUP2D_NFIELDS))) return rc;
+      if (s->nranks > 1 && (rc = halo_exchange_ptr(s, s->kz, 1, CUP2D_NFIELDS, false))) return rc;
       {
         ProfScope prof(s, KC_SPMV_NU);
         k_spmv<0><<<grid, NT, 0, s->stream>>>(s->kz, s->krhat, s->knu, nbr, nrows, s->d_state,
@@ -388,7 +388,7 @@ int poisson_solve(cup2d_sim *s, double tol_abs, double tol_rel, int max_restarts
         k_xr_update<<<grid, NT, 0, s->stream>>>(s->kx[0], s->kx[1], s->kx[2], s->kz, s->kr, s->knu,
                                                 s->kz, nrows, s->d_state);
       }
-      if (s->nranks > 1 && (rc = halo_exchange_ptr(s, s->kz, 1, CUP2D_NFIELDS))) return rc;
+      if (s->nranks > 1 && (rc = halo_exchange_ptr(s, s->kz, 1, CUP2D_NFIELDS, false))) return rc;
       {
         ProfScope prof(s, KC_SPMV_T);
         k_spmv<1><<<grid, NT, 0, s->stream>>>(s->kz, s->kr, s->kt, nbr, nrows, s->d_state,

@@ -118,6 +118,6 @@ int launch_pressure_rhs(cup2d_sim *s, double dt, bool has_udef);
 int launch_pressure_correct(cup2d_sim *s, double dt);
 int poisson_solve(cup2d_sim *s, double tol_abs, double tol_rel, int max_restarts, int max_iter,
                   int *iters, double *err);
-int halo_exchange_ptr(cup2d_sim *s, double *base, int dim, int peer_index);
+int halo_exchange_ptr(cup2d_sim *s, double *base, int dim, int peer_index, bool done_barrier = true);
 void swap_fields(cup2d_sim *s, int a, int b); // pointer swap, mirrored on the peer mappings
 } // namespace cup2d
