@@ -344,6 +344,51 @@ int cup2d_poisson_create(int64_t nblocks, const int32_t *nbr, int32_t device, cu
   return CUP2D_OK;
 }
 
+// Poisson-only context whose matrix is "same-level stencil from nbr[] + general CSR rows that override
+// it".  irr_rows (sorted, unique) are row indices 64*block + 8*iy + ix; their complete rows are given
+// in CSR (rowptr has n_irr+1 entries).  nbr faces that are covered by general rows must be -1.
+int cup2d_poisson_create_general(int64_t nblocks, const int32_t *nbr, int64_t n_irr, const int32_t *irr_rows,
+                                 const int32_t *irr_rowptr, const int32_t *irr_col, const double *irr_val,
+                                 int32_t device, cup2d_sim **out) {
+  int rc = cup2d_poisson_create(nblocks, nbr, device, out);
+  if (rc || n_irr <= 0) return rc;
+  cup2d_sim *s = *out;
+  auto bail = [&](const char *msg) {
+    set_error(msg);
+    cup2d_destroy(s);
+    *out = nullptr;
+    return CUP2D_EINVAL;
+  };
+  if (!irr_rows || !irr_rowptr || !irr_col || !irr_val) return bail("cup2d_poisson_create_general: null table");
+  std::vector<int> blk(nblocks, -1), tab;
+  int nirrblk = 0;
+  for (int64_t k = 0; k < n_irr; k++) {
+    const int r = irr_rows[k];
+    if (r < 0 || r >= nblocks * 64 || (k > 0 && irr_rows[k - 1] >= r)) return bail("cup2d_poisson_create_general: irr_rows must be sorted, unique, in range");
+    const int b = r / 64;
+    if (blk[b] < 0) {
+      blk[b] = nirrblk++;
+      tab.resize((size_t)nirrblk * 64, -1);
+    }
+    tab[(size_t)blk[b] * 64 + r % 64] = (int)k;
+  }
+  const int nnz = irr_rowptr[n_irr];
+  for (int j = 0; j < nnz; j++)
+    if (irr_col[j] < 0 || irr_col[j] >= nblocks * 64) return bail("cup2d_poisson_create_general: column out of range");
+  auto up = [](void **d, const void *h, size_t bytes) -> cudaError_t {
+    cudaError_t e = cudaMalloc(d, bytes ? bytes : 8);
+    if (e != cudaSuccess) return e;
+    return cudaMemcpy(*d, h, bytes, cudaMemcpyHostToDevice);
+  };
+  CUP2D_CUDA(up((void **)&s->d_irr_blk, blk.data(), blk.size() * sizeof(int)));
+  CUP2D_CUDA(up((void **)&s->d_irr_tab, tab.data(), tab.size() * sizeof(int)));
+  CUP2D_CUDA(up((void **)&s->d_irr_rowptr, irr_rowptr, (size_t)(n_irr + 1) * sizeof(int)));
+  CUP2D_CUDA(up((void **)&s->d_irr_col, irr_col, (size_t)nnz * sizeof(int)));
+  CUP2D_CUDA(up((void **)&s->d_irr_val, irr_val, (size_t)nnz * sizeof(double)));
+  s->n_irr_rows = n_irr;
+  return CUP2D_OK;
+}
+
 static int alloc_device_state(cup2d_sim *s) {
   int rc = upload_tables(s);
   if (rc) return rc;
@@ -399,6 +444,7 @@ void cup2d_destroy(cup2d_sim *s) {
   cudaFree(s->d_nbr); cudaFree(s->d_tiles); cudaFree(s->d_tile_org); cudaFree(s->d_halo_src);
   cudaFree(s->d_state); cudaFree(s->d_partials); cudaFree(s->d_counter); cudaFree(s->d_scal);
   cudaFree(s->d_mailbox); cudaFree(s->d_peer_ptrs);
+  cudaFree(s->d_irr_blk); cudaFree(s->d_irr_tab); cudaFree(s->d_irr_rowptr); cudaFree(s->d_irr_col); cudaFree(s->d_irr_val);
   if (s->h_state) cudaFreeHost(s->h_state);
   if (s->h_scal) cudaFreeHost(s->h_scal);
   if (s->stream) cudaStreamDestroy(s->stream);

@@ -129,14 +129,14 @@ __global__ void __launch_bounds__(NT)
 k_init(const double *__restrict__ b, const double *__restrict__ x0, double *__restrict__ x,
        double *__restrict__ r, double *__restrict__ rhat, double *__restrict__ p,
        double *__restrict__ nu, const int4 *__restrict__ nbr, int nrows, KrylovState *st,
-       double *partials, unsigned int *counter, Comm comm) {
+       double *partials, unsigned int *counter, Comm comm, IrrView irr) {
   __shared__ __align__(16) double s_scr[WPB * SCR1];
   double sums[2] = {0, 0}; // |r|^2, sum x0
   double mx = 0;
   CHUNK_LOOP() {
     const int nv = min(32, nrows - row0);
     double xx[8], ax[8], bb[8], zero[8];
-    rows_lap(x0, row0, nv, nbr, sw, lane, xx, ax);
+    rows_lap(x0, row0, nv, nbr, sw, lane, xx, ax, irr);
     rows_load1(b, row0, nv, sw, lane, bb);
 #pragma unroll
     for (int i = 0; i < 8; i++) {
@@ -206,14 +206,14 @@ template <int MODE>
 __global__ void __launch_bounds__(NT)
 k_spmv(const double *__restrict__ z, const double *__restrict__ d, double *__restrict__ yout,
        const int4 *__restrict__ nbr, int nrows, KrylovState *st, double *partials,
-       unsigned int *counter, Comm comm) {
+       unsigned int *counter, Comm comm, IrrView irr) {
   __shared__ __align__(16) double s_scr[WPB * SCR1];
   if (st->done) return;
   double sums[2] = {0, 0};
   CHUNK_LOOP() {
     const int nv = min(32, nrows - row0);
     double zz[8], az[8];
-    rows_lap(z, row0, nv, nbr, sw, lane, zz, az);
+    rows_lap(z, row0, nv, nbr, sw, lane, zz, az, irr);
     // back to chunk layout: the dots and the store are element-wise
     double2 ca[4], cd[4];
     chunk_ld(d, row0, nv, lane, cd);
@@ -364,7 +364,7 @@ int poisson_solve(cup2d_sim *s, double tol_abs, double tol_rel, int max_restarts
     ProfScope prof(s, KC_KINIT);
     k_init<<<grid, NT, 0, s->stream>>>(s->f[CUP2D_TMP], s->f[CUP2D_PRES], s->kx[0], s->kr, s->krhat,
                                        s->kp, s->knu, nbr, nrows, s->d_state, s->d_partials,
-                                       s->d_counter, s->comm);
+                                       s->d_counter, s->comm, irr_view(s));
   }
   s->launches++;
   const int check_every = (tol_abs > 0 || tol_rel > 0) ? 8 : 64;
@@ -381,7 +381,7 @@ int poisson_solve(cup2d_sim *s, double tol_abs, double tol_rel, int max_restarts
       {
         ProfScope prof(s, KC_SPMV_NU);
         k_spmv<0><<<grid, NT, 0, s->stream>>>(s->kz, s->krhat, s->knu, nbr, nrows, s->d_state,
-                                              s->d_partials, s->d_counter, s->comm);
+                                              s->d_partials, s->d_counter, s->comm, irr_view(s));
       }
       {
         ProfScope prof(s, KC_XRUPDATE);
@@ -392,7 +392,7 @@ int poisson_solve(cup2d_sim *s, double tol_abs, double tol_rel, int max_restarts
       {
         ProfScope prof(s, KC_SPMV_T);
         k_spmv<1><<<grid, NT, 0, s->stream>>>(s->kz, s->kr, s->kt, nbr, nrows, s->d_state,
-                                              s->d_partials, s->d_counter, s->comm);
+                                              s->d_partials, s->d_counter, s->comm, irr_view(s));
       }
       {
         ProfScope prof(s, KC_FINAL);

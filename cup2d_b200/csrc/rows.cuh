@@ -149,12 +149,24 @@ __device__ __forceinline__ void grow_load2(const double *__restrict__ f, int slo
   for (int k = 0; k < 8; k++) c[k] = p[k];
 }
 
+// Rows of the Poisson matrix that are NOT the same-level 5-point stencil (coarse-fine interpolation rows
+// of main.cpp:5915-5997 pushed through cooPushBackRow).  They live in a small
+// CSR side table and override the stencil result of the cells they belong to: blk[slot] = -1 (block is
+// fully regular) or k, tab[k*64 + cell] = -1 or the CSR row index.
+struct IrrView {
+  const int *blk = nullptr;
+  const int *tab = nullptr;
+  const int *rowptr = nullptr;
+  const int *col = nullptr;
+  const double *val = nullptr;
+};
+
 // Undivided 5-point Laplacian rows of a scalar field for the warp's 32 rows, ghost = the cell itself at
 // a domain wall (Neumann rows of main.cpp:7100-7107 / ScalarLab::Neumann2D main.cpp:3210-3245).
 // Returns the own row in c and the Laplacian in out.  Summation order S,W,E,N then -4C.
 __device__ __forceinline__ void rows_lap(const double *__restrict__ z, int row0, int nvalid,
                                          const int4 *__restrict__ nbr, double *sw, int lane,
-                                         double (&c)[8], double (&out)[8]) {
+                                         double (&c)[8], double (&out)[8], const IrrView irr = IrrView()) {
   rows_load1(z, row0, nvalid, sw, lane, c);
   const int row = row0 + lane, slot = row >> 3, y = row & 7;
   if (lane < nvalid) {
@@ -179,6 +191,20 @@ __device__ __forceinline__ void rows_lap(const double *__restrict__ z, int row0,
       const double e = i < 7 ? c[i + 1] : gE;
       const double w = i > 0 ? c[i - 1] : gW;
       out[i] = (((dn[i] + w) + e) + up[i]) - 4.0 * c[i];
+    }
+    if (irr.blk) { // general rows override the stencil (rare: block faces at coarse-fine interfaces)
+      const int k = irr.blk[slot];
+      if (k >= 0) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+          const int idx = irr.tab[k * 64 + y * 8 + i];
+          if (idx >= 0) {
+            double acc = 0.0;
+            for (int j = irr.rowptr[idx]; j < irr.rowptr[idx + 1]; j++) acc = fma(irr.val[j], z[irr.col[j]], acc);
+            out[i] = acc;
+          }
+        }
+      }
     }
   } else {
 #pragma unroll

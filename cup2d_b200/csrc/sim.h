@@ -2,6 +2,7 @@
 #pragma once
 #include "../../include/cup2d_b200.h"
 #include "common.cuh"
+#include "rows.cuh"
 #include <vector>
 
 namespace cup2d {
@@ -81,6 +82,10 @@ struct cup2d_sim {
   unsigned long long epoch = 0;
   cup2d::Comm comm = {};               // by-value kernel argument of every reducing kernel
   double **d_peer_ptrs = nullptr;      // device copy of peer_base
+  // general (non-stencil) Poisson rows: CSR side table (cup2d_poisson_create_general)
+  int *d_irr_blk = nullptr, *d_irr_tab = nullptr, *d_irr_rowptr = nullptr, *d_irr_col = nullptr;
+  double *d_irr_val = nullptr;
+  int64_t n_irr_rows = 0;
   int64_t launches = 0;
   // optional per-kernel-class CUDA-event instrumentation (cup2d_profile_*)
   bool prof_on = false;
@@ -110,6 +115,13 @@ struct ProfScope {
   }
 };
 int dim_of(int field);
+inline IrrView irr_view(const cup2d_sim *s) {
+  IrrView v;
+  if (s->n_irr_rows > 0) {
+    v.blk = s->d_irr_blk; v.tab = s->d_irr_tab; v.rowptr = s->d_irr_rowptr; v.col = s->d_irr_col; v.val = s->d_irr_val;
+  }
+  return v;
+}
 // operators (host-side launchers; all on s->stream)
 int launch_advect(cup2d_sim *s, const double *in, const double *old, double *out, double coef,
                   double dt, bool raw);

@@ -127,6 +127,13 @@ int cup2d_halo_exchange(cup2d_sim *s, int field);
  * field upload/download of CUP2D_TMP (b) and CUP2D_PRES (x0 / x) and cup2d_poisson_solve; rows are
  * numbered block-major, row = 64*k + 8*iy + ix, exactly like Solver::CellIndexer (main.cpp:5753-5771). */
 int cup2d_poisson_create(int64_t nblocks, const int32_t *nbr, int32_t device, cup2d_sim **out);
+/* General variant: rows that are not the same-level stencil (the coarse-fine interpolation rows of
+ * main.cpp:5915-5997 on AMR grids, or anything else) are given completely in CSR and override the
+ * stencil for their cells: irr_rows[n_irr] sorted unique row indices, irr_rowptr[n_irr+1], irr_col/irr_val.
+ * Faces covered by such rows must have nbr = -1.  With n_irr = 0 this is cup2d_poisson_create. */
+int cup2d_poisson_create_general(int64_t nblocks, const int32_t *nbr, int64_t n_irr, const int32_t *irr_rows,
+                                 const int32_t *irr_rowptr, const int32_t *irr_col, const double *irr_val,
+                                 int32_t device, cup2d_sim **out);
 
 /* ---- host-side topology plan (no GPU needed; used by the CPU tests of the multi-rank logic) ---- */
 /* Same config as cup2d_create, but builds only the host tables: SFC-range partition, halo plan

@@ -22,6 +22,9 @@
 //   ref_harness steps L nu cfl nsteps kiter in.bin out.bin
 //        in : as above (udef ignored: no shapes => udef = 0, chi = 0 ; p = initial pres)
 //        out: per step: dt, then u v p  b x   (1 + 5 N^2 doubles), b/x = Poisson rhs / solution
+//   ref_harness amr   levelMax nsteps kiter out.bin
+//        the reference's own run.sh case (2 fish, AMR from level 5 to levelMax-1); per step:
+//        int64 nrows, int64 nblocks, double dt, b[nrows], x[nrows], int32 (level,i,j)[nblocks]
 //   ref_harness time  L reps kiter
 //        prints one JSON line with per-operator CPU times (seconds, median of reps)
 #define CUP2D_REF_HOOK_TU 1
@@ -36,7 +39,7 @@ extern int cup2d_ref_force_iters;
 extern int cup2d_ref_fixed_iters;
 
 namespace {
-enum Mode { ORDER, OPS, STEPS, TIME } g_mode;
+enum Mode { ORDER, OPS, STEPS, TIME, AMR } g_mode;
 int g_L, g_N, g_NY, g_bx = 1, g_by = 1, g_nsteps, g_reps, g_kiter;
 double g_nu, g_dt, g_cfl;
 std::string g_in, g_out;
@@ -262,6 +265,33 @@ void cup2d_ref_hook(int op, void *buf, int count) {
     do_time();
     exit(0);
   }
+  if (g_mode == AMR) {
+    // the reference's own run.sh case (2 fish, AMR levels 5..8): record the Poisson system of every step
+    // as raw block-ordered vectors: int64 nrows, int64 nblocks, double dt, b[nrows], x[nrows],
+    // int32 (level,i,j)[nblocks]
+    if (call == 0) {
+      g_fout = fopen(g_out.c_str(), "wb");
+      return;
+    }
+    const std::vector<double> &b = sim.mat->get_b(), &x = sim.mat->get_x();
+    long long nrows = (long long)b.size(), nblk = (long long)var.tmp->infos.size();
+    fwrite(&nrows, sizeof nrows, 1, g_fout);
+    fwrite(&nblk, sizeof nblk, 1, g_fout);
+    fwrite(&sim.dt, sizeof(double), 1, g_fout);
+    fwrite(b.data(), sizeof(double), b.size(), g_fout);
+    fwrite(x.data(), sizeof(double), x.size(), g_fout);
+    for (auto &info : var.tmp->infos) {
+      int lij[3] = {info.level, info.index[0], info.index[1]};
+      fwrite(lij, sizeof(int), 3, g_fout);
+    }
+    fprintf(stderr, "ref_harness: amr step %d dt %.6e blocks %lld iters %d err %.3e\n", call - 1, sim.dt, nblk,
+            cup2d_ref_last_iters, cup2d_ref_last_err);
+    if (call == g_nsteps) {
+      fclose(g_fout);
+      exit(0);
+    }
+    return;
+  }
   // STEPS: call 0 = before step 0 (seed), call k = after k steps (record)
   const size_t n2 = (size_t)g_N * g_NY;
   if (call == 0) {
@@ -306,6 +336,20 @@ int main(int argc, char **argv) {
     g_kiter = atoi(argv[6]); g_in = argv[7]; g_out = argv[8];
     cup2d_ref_force_iters = g_kiter;
   } else if (mode == "time" && argc == 5) { g_mode = TIME; g_reps = atoi(argv[3]); g_kiter = atoi(argv[4]); }
+  else if (mode == "amr" && argc == 6) {
+    // ref_harness amr <levelMax> <nsteps> <kiter> <out.bin>   (argv[2] is parsed as g_L = levelMax here)
+    g_mode = AMR; g_nsteps = atoi(argv[3]); g_kiter = atoi(argv[4]); g_out = argv[5];
+    cup2d_ref_force_iters = g_kiter;
+    char a_lmax[16];
+    snprintf(a_lmax, sizeof a_lmax, "%d", g_L);
+    // run.sh:1-22 verbatim except levelMax (argument) and tdump 0 (no output files)
+    const char *args[] = {"ref_main", "-AdaptSteps", "20", "-bpdx", "2", "-bpdy", "1", "-CFL", "0.5", "-Ctol", "1",
+                          "-extent", "4", "-lambda", "1e7", "-levelMax", a_lmax, "-levelStart", "5",
+                          "-maxPoissonIterations", "1000", "-maxPoissonRestarts", "0", "-nu", "0.00004",
+                          "-poissonTol", "1e-3", "-poissonTolRel", "1e-2", "-Rtol", "2", "-tdump", "0", "-tend", "10.0",
+                          "-shapes", "angle=0 L=0.2 xpos=1.8 ypos=0.8\n angle=180 L=0.2 xpos=1.6 ypos=0.8"};
+    return ref_main(sizeof args / sizeof *args, (char **)args);
+  }
   else { fprintf(stderr, "ref_harness: bad arguments\n"); return 2; }
   char a_ls[32], a_lm[32], a_nu[64], a_cfl[64];
   snprintf(a_ls, sizeof a_ls, "%d", g_L);

@@ -1,0 +1,61 @@
+"""GPU box only: the reference's own run.sh case (2 fish, block-AMR, levels 5..7) driven by the UNMODIFIED
+main.cpp, once with the reference's cuda.cu and once with dropin/local_spmat_adapter.cpp + libcup2d_b200.so
+(general rows through the CSR side table).  Compares, step by step, the grid (level,i,j of every block), the
+Poisson right-hand side and the returned solution."""
+import json
+import os
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def read_records(path):
+    raw = open(path, "rb").read()
+    off, recs = 0, []
+    while off < len(raw):
+        nrows, nblk = np.frombuffer(raw, dtype=np.int64, count=2, offset=off)
+        off += 16
+        dt = np.frombuffer(raw, dtype=np.float64, count=1, offset=off)[0]
+        off += 8
+        b = np.frombuffer(raw, dtype=np.float64, count=nrows, offset=off)
+        off += 8 * nrows
+        x = np.frombuffer(raw, dtype=np.float64, count=nrows, offset=off)
+        off += 8 * nrows
+        lij = np.frombuffer(raw, dtype=np.int32, count=3 * nblk, offset=off).reshape(-1, 3)
+        off += 12 * nblk
+        recs.append(dict(dt=dt, b=b, x=x, lij=lij))
+    return recs
+
+
+def compare(nsteps=12, level_max=8, names=("ref_harness_gpu", "ref_harness_b200")):
+    out = {}
+    with tempfile.TemporaryDirectory() as tmp:
+        recs = {}
+        for n in names:
+            f = os.path.join(tmp, n + ".bin")
+            subprocess.run([os.path.join(ROOT, "oracle", "_ref", n), "amr", str(level_max), str(nsteps), "1000", f],
+                           check=True, stderr=subprocess.DEVNULL, env=dict(os.environ, OMP_NUM_THREADS="8"))
+            recs[n] = read_records(f)
+    a, b = recs[names[0]], recs[names[1]]
+    rows = []
+    for s in range(min(len(a), len(b))):
+        same_grid = a[s]["lij"].shape == b[s]["lij"].shape and bool((a[s]["lij"] == b[s]["lij"]).all())
+        row = {"step": s, "blocks": int(len(a[s]["lij"])), "levels": sorted(set(a[s]["lij"][:, 0].tolist())),
+               "same_grid": same_grid, "dt_diff": float(abs(a[s]["dt"] - b[s]["dt"]))}
+        if same_grid:
+            scale = max(float(np.abs(a[s]["x"]).max()), 1e-300)
+            row["b_Linf"] = float(np.abs(a[s]["b"] - b[s]["b"]).max())
+            row["x_Linf"] = float(np.abs(a[s]["x"] - b[s]["x"]).max())
+            row["x_scale"] = scale
+        rows.append(row)
+    out["steps"] = rows
+    return out
+
+
+if __name__ == "__main__":
+    n = int(sys.argv[1]) if len(sys.argv) > 1 else 12
+    print(json.dumps(compare(n)))
