@@ -157,9 +157,11 @@ __device__ __forceinline__ void weno_line(const double *__restrict__ qa, const d
 #pragma unroll UNR
   for (int w = 2; w <= 11; ++w) {
     const bool vc = (unsigned)(w - 3) < 8u, vn = (unsigned)(w - 2) < 8u, vp = (unsigned)(w - 4) < 8u;
-    const bool posc = (pos >> w) & 1u, posn = (pos >> (w + 1)) & 1u, posp = (pos >> (w - 1)) & 1u;
-    const bool needP = (vc && posc) || (vn && posn);
-    const bool needM = (vc && !posc) || (vp && !posp);
+    const unsigned pw = pos >> (w - 1); // bit 0: cell w-1, bit 1: cell w, bit 2: cell w+1
+    const bool posp = pw & 1u;
+    // flux families needed at this window position (masks are compile-time after unrolling)
+    const bool needP = (pw & ((vc ? 2u : 0u) | (vn ? 4u : 0u))) != 0u;
+    const bool needM = (~pw & ((vc ? 2u : 0u) | (vp ? 1u : 0u))) != 0u;
     double a1, a2, a3, b1, b2, b3;
     line_betas(A, a1, a2, a3);
     line_betas(B, b1, b2, b3);
@@ -249,7 +251,8 @@ advect_stage_kernel(const double *__restrict__ in, const double *__restrict__ ol
   }
   const int gx0 = tile_org[2 * tile] * CUP2D_BS, gy0 = tile_org[2 * tile + 1] * CUP2D_BS;
   const int NX = nbx * CUP2D_BS, NY = nby * CUP2D_BS;
-  mbar_wait(bar, 0);
+  if (warp == 0) mbar_wait(bar, 0); // one warp polls the mbarrier; the others park at the CTA barrier
+  __syncthreads();
 
   // ---- stage 1: repack AoS blocks -> padded SoA planes, synthesising wall ghosts ----
   // (VectorLab::applyBCface main.cpp:3131-3154: ghost = wall-adjacent cell, normal component negated)

@@ -2,7 +2,7 @@
 # Run on the GPU box (via gpurun): bench line + ncu launch list + ncu full captures of the top kernels.
 # Outputs land in gpurun_out/ (scratch); summaries worth judging are copied to profiles/ by hand.
 set -u
-TAG=${1:-r01}
+TAG=${1:-r01f}
 OUT=gpurun_out
 mkdir -p $OUT
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $OUT/smi_$TAG.txt 2>&1
@@ -19,4 +19,7 @@ ncu --set full --clock-control none --import-source on -k regex:'k_pupdate|k_spm
     python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-e2e > $OUT/ncu_kry_$TAG.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:'pressure_rhs|pressure_correct|umax' -s 3 -c 3 -o $OUT/press_$TAG -f \
     python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-e2e > $OUT/ncu_prs_$TAG.log 2>&1
+timeout 300 python tools/ref_gpu_compare_amr.py 14 2>/dev/null | tail -1 > $OUT/amr_compare_$TAG.json
+(time timeout 600 python -m pytest tests -m gpu -x -q) > $OUT/pytest_gpu_$TAG.log 2>&1
+tail -5 $OUT/pytest_gpu_$TAG.log
 ls -la $OUT | tail -20
