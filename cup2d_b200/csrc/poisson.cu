@@ -125,6 +125,7 @@ __device__ void prepare_iteration(KrylovState *st, double rho_new, double nr2) {
   for (int row0 = (blockIdx.x * WPB + warp) * 32; row0 < nrows; row0 += gridDim.x * WPB * 32)
 
 // ---- K0: r = b - A x0 ; rhat = r ; p = nu = 0 ; x[0] = x0 ; err0, |r|^2, sum(x0) -----------------
+template <bool IRR>
 __global__ void __launch_bounds__(NT)
 k_init(const double *__restrict__ b, const double *__restrict__ x0, double *__restrict__ x,
        double *__restrict__ r, double *__restrict__ rhat, double *__restrict__ p,
@@ -136,7 +137,7 @@ k_init(const double *__restrict__ b, const double *__restrict__ x0, double *__re
   CHUNK_LOOP() {
     const int nv = min(32, nrows - row0);
     double xx[8], ax[8], bb[8], zero[8];
-    rows_lap(x0, row0, nv, nbr, sw, lane, xx, ax, irr);
+    rows_lap(x0, row0, nv, nbr, sw, lane, xx, ax, IRR ? irr : IrrView());
     rows_load1(b, row0, nv, sw, lane, bb);
 #pragma unroll
     for (int i = 0; i < 8; i++) {
@@ -202,7 +203,7 @@ k_pupdate(const double *__restrict__ r, double *__restrict__ rhat, double *__res
 // ---- K2 / K4: y = A z with one or two dots against `d` and y -------------------------------------
 //   MODE 0 (K2): nu = A z ; rhat.nu             -> alpha = rho/(rhat.nu + eps)   (cuda.cu:487-496)
 //   MODE 1 (K4): t  = A z ; t.r, t.t            -> omega = t.r/(t.t + eps)       (cuda.cu:506-518)
-template <int MODE>
+template <int MODE, bool IRR>
 __global__ void __launch_bounds__(NT)
 k_spmv(const double *__restrict__ z, const double *__restrict__ d, double *__restrict__ yout,
        const int4 *__restrict__ nbr, int nrows, KrylovState *st, double *partials,
@@ -213,7 +214,7 @@ k_spmv(const double *__restrict__ z, const double *__restrict__ d, double *__res
   CHUNK_LOOP() {
     const int nv = min(32, nrows - row0);
     double zz[8], az[8];
-    rows_lap(z, row0, nv, nbr, sw, lane, zz, az, irr);
+    rows_lap(z, row0, nv, nbr, sw, lane, zz, az, IRR ? irr : IrrView());
     // back to chunk layout: the dots and the store are element-wise
     double2 ca[4], cd[4];
     chunk_ld(d, row0, nv, lane, cd);
@@ -351,6 +352,7 @@ int poisson_solve(cup2d_sim *s, double tol_abs, double tol_rel, int max_restarts
   const int nrows = (int)s->nloc * 8;
   const int grid = red_grid(s, nrows);
   const int4 *nbr = reinterpret_cast<const int4 *>(s->d_nbr);
+  const bool has_irr = s->n_irr_rows > 0; // general rows present: kernels with the CSR override compiled in
   KrylovState *h = s->h_state;
   *h = KrylovState{};
   h->alpha = h->omega = h->rho_prev = h->rho_curr = 1.0; // cuda.cu:409
@@ -362,9 +364,14 @@ int poisson_solve(cup2d_sim *s, double tol_abs, double tol_rel, int max_restarts
   if (s->nranks > 1 && (rc = halo_exchange_ptr(s, s->f[CUP2D_PRES], 1, CUP2D_PRES))) return rc;
   {
     ProfScope prof(s, KC_KINIT);
-    k_init<<<grid, NT, 0, s->stream>>>(s->f[CUP2D_TMP], s->f[CUP2D_PRES], s->kx[0], s->kr, s->krhat,
-                                       s->kp, s->knu, nbr, nrows, s->d_state, s->d_partials,
-                                       s->d_counter, s->comm, irr_view(s));
+    if (has_irr)
+      k_init<true><<<grid, NT, 0, s->stream>>>(s->f[CUP2D_TMP], s->f[CUP2D_PRES], s->kx[0], s->kr, s->krhat, s->kp,
+                                               s->knu, nbr, nrows, s->d_state, s->d_partials, s->d_counter,
+                                               s->comm, irr_view(s));
+    else
+      k_init<false><<<grid, NT, 0, s->stream>>>(s->f[CUP2D_TMP], s->f[CUP2D_PRES], s->kx[0], s->kr, s->krhat, s->kp,
+                                                s->knu, nbr, nrows, s->d_state, s->d_partials, s->d_counter,
+                                                s->comm, irr_view(s));
   }
   s->launches++;
   const int check_every = (tol_abs > 0 || tol_rel > 0) ? 8 : 64;
@@ -380,8 +387,12 @@ int poisson_solve(cup2d_sim *s, double tol_abs, double tol_rel, int max_restarts
       if (s->nranks > 1 && (rc = halo_exchange_ptr(s, s->kz, 1, CUP2D_NFIELDS, false))) return rc;
       {
         ProfScope prof(s, KC_SPMV_NU);
-        k_spmv<0><<<grid, NT, 0, s->stream>>>(s->kz, s->krhat, s->knu, nbr, nrows, s->d_state,
-                                              s->d_partials, s->d_counter, s->comm, irr_view(s));
+        if (has_irr)
+          k_spmv<0, true><<<grid, NT, 0, s->stream>>>(s->kz, s->krhat, s->knu, nbr, nrows, s->d_state,
+                                                      s->d_partials, s->d_counter, s->comm, irr_view(s));
+        else
+          k_spmv<0, false><<<grid, NT, 0, s->stream>>>(s->kz, s->krhat, s->knu, nbr, nrows, s->d_state,
+                                                       s->d_partials, s->d_counter, s->comm, irr_view(s));
       }
       {
         ProfScope prof(s, KC_XRUPDATE);
@@ -391,8 +402,12 @@ int poisson_solve(cup2d_sim *s, double tol_abs, double tol_rel, int max_restarts
       if (s->nranks > 1 && (rc = halo_exchange_ptr(s, s->kz, 1, CUP2D_NFIELDS, false))) return rc;
       {
         ProfScope prof(s, KC_SPMV_T);
-        k_spmv<1><<<grid, NT, 0, s->stream>>>(s->kz, s->kr, s->kt, nbr, nrows, s->d_state,
-                                              s->d_partials, s->d_counter, s->comm, irr_view(s));
+        if (has_irr)
+          k_spmv<1, true><<<grid, NT, 0, s->stream>>>(s->kz, s->kr, s->kt, nbr, nrows, s->d_state,
+                                                      s->d_partials, s->d_counter, s->comm, irr_view(s));
+        else
+          k_spmv<1, false><<<grid, NT, 0, s->stream>>>(s->kz, s->kr, s->kt, nbr, nrows, s->d_state,
+                                                       s->d_partials, s->d_counter, s->comm, irr_view(s));
       }
       {
         ProfScope prof(s, KC_FINAL);

@@ -297,5 +297,22 @@ def test_reference_amr_case_through_adapter():
     assert len(res["steps"]) == 2
     for row in res["steps"]:
         assert row["same_grid"] and len(row["levels"]) >= 2     # really multi-level
-        assert row["dt_diff"] < 1e-12
-        assert row["x_Linf"] < 1e-6
+        assert row["dt_diff"] < 1e-7
+        assert row["b_Linf"] < 1e-6 * max(1.0, row["b_scale"])
+        assert row["x_Linf"] < 1e-6          # mean-free solution (the constant mode of the singular system is free)
+
+
+def test_two_ranks_on_two_gpus_match_the_oracle():
+    """N>1 path on real GPUs (skipped on a single-GPU box): NVLink peer halo + all-reduce, 2 ranks, vs oracle."""
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29577",
+                        os.path.join(root, "tools", "multi_gpu_check.py")], stdout=subprocess.PIPE,
+                       stderr=subprocess.STDOUT, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-2000:]
+    assert '"check": "parity_256"' in r.stdout
