@@ -24,6 +24,7 @@
 // from the reference's CPU evaluation at the 1e-16 relative level (tests bound it at 1e-12).
 #include "sim.h"
 #include <cstdlib>
+#include <vector>
 
 namespace cup2d {
 
@@ -58,6 +59,18 @@ template <bool CM, int I> __device__ __forceinline__ double KW() {
                              0.1 * 5.0 / 6.0, -0.1 / 3.0, 0.6 / 6.0, 0.6 / 3.0, 0.3 * 2.0 / 3.0, -0.3 / 6.0,
                              -0.3 * 2.0 / 3.0, 0.3 / 6.0, -0.6 / 3.0, -0.6 / 6.0, -0.1 * 5.0 / 6.0, 0.1 / 3.0};
   return v[I];
+}
+
+constexpr int ADV_LUT_N = TW * TW - 4 * GH * GH; // 1408 cells of the cross-shaped footprint = 11 * 128
+static_assert(ADV_LUT_N % NT_ADV == 0, "table must divide evenly among the threads");
+// staging slot (in double2 units) of tile-local cell (cx,cy), -3 <= cx,cy < 35, not a corner
+__host__ __device__ __forceinline__ int adv_src_slot(int cx, int cy) {
+  if ((unsigned)cx < (unsigned)TC && (unsigned)cy < (unsigned)TC)
+    return ((cy >> 3) * 4 + (cx >> 3)) * 64 + (cy & 7) * 8 + (cx & 7);
+  if (cx < 0) return (16 + (cy >> 3)) * 64 + (cy & 7) * 8 + (8 + cx);
+  if (cx >= TC) return (20 + (cy >> 3)) * 64 + (cy & 7) * 8 + (cx - TC);
+  if (cy < 0) return 24 * 64 + (cx >> 3) * 24 + (3 + cy) * 8 + (cx & 7);
+  return 24 * 64 + 4 * 24 + (cx >> 3) * 24 + (cy - TC) * 8 + (cx & 7);
 }
 
 struct LineState {
@@ -202,8 +215,8 @@ template <int MODE, int UNR, int NEWTON, bool CM, bool ONE>
 __global__ void __launch_bounds__(NT_ADV, 4)
 advect_stage_kernel(const double *__restrict__ in, const double *__restrict__ old,
                     double *__restrict__ out, const int *__restrict__ tiles,
-                    const int *__restrict__ tile_org, int nbx, int nby, int nloc, double afac,
-                    double dfac, double ofac) {
+                    const int *__restrict__ tile_org, const unsigned *__restrict__ lut, int nbx, int nby,
+                    int nloc, int prefetch_dist, double afac, double dfac, double ofac) {
   extern __shared__ __align__(128) unsigned char smem[];
   double2 *stg = reinterpret_cast<double2 *>(smem);
   double *su = reinterpret_cast<double *>(smem + OFF_SU);
@@ -237,6 +250,16 @@ advect_stage_kernel(const double *__restrict__ in, const double *__restrict__ ol
       unsigned char *dst = smem + (lane < 24 ? lane * 1024 : 24 * 1024 + (lane - 24) * 384);
       tma_load_1d(dst, src, bytes, bar);
     }
+    // warm L2 for the tile that the CTA scheduled one resident wave later will ask for
+    const int nt = tile + prefetch_dist;
+    if (nt < (int)gridDim.x) {
+      const int ns = tiles[nt * TILE_SLOTS + lane];
+      if (ns >= 0) {
+        const unsigned char *nsrc = reinterpret_cast<const unsigned char *>(in + (size_t)ns * 128);
+        if (lane >= 24 && lane < 28) nsrc += 5 * 128;
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(nsrc), "r"(lane < 24 ? 1024u : 384u) : "memory");
+      }
+    }
   }
   // y-pass ownership (known now, so the `old` loads of stage 2 can be in flight during everything else)
   const int yx = lane, ys = warp;
@@ -255,31 +278,33 @@ advect_stage_kernel(const double *__restrict__ in, const double *__restrict__ ol
   __syncthreads();
 
   // ---- stage 1: repack AoS blocks -> padded SoA planes, synthesising wall ghosts ----
-  // (VectorLab::applyBCface main.cpp:3131-3154: ghost = wall-adjacent cell, normal component negated)
-  for (int idx = tid; idx < TW * TW; idx += NT_ADV) {
-    const int ty = idx / TW, tx = idx - ty * TW;
-    const int lx = tx - GH, ly = ty - GH;
-    const bool xin = (unsigned)lx < (unsigned)TC, yin = (unsigned)ly < (unsigned)TC;
-    if (!xin && !yin) continue; // corner ghosts are never read (cross-shaped stencil)
-    int gx = gx0 + lx, gy = gy0 + ly;
-    double sgu = 1.0, sgv = 1.0;
-    if (gx < 0) { gx = 0; sgu = -1.0; } else if (gx >= NX) { gx = NX - 1; sgu = -1.0; }
-    if (gy < 0) { gy = 0; sgv = -1.0; } else if (gy >= NY) { gy = NY - 1; sgv = -1.0; }
-    const int cx = gx - gx0, cy = gy - gy0; // clamped, tile-local
-    int o;
-    if ((unsigned)cx < (unsigned)TC && (unsigned)cy < (unsigned)TC)
-      o = ((cy >> 3) * 4 + (cx >> 3)) * 64 + (cy & 7) * 8 + (cx & 7);
-    else if (cx < 0)
-      o = (16 + (cy >> 3)) * 64 + (cy & 7) * 8 + (8 + cx);
-    else if (cx >= TC)
-      o = (20 + (cy >> 3)) * 64 + (cy & 7) * 8 + (cx - TC);
-    else if (cy < 0)
-      o = 24 * 64 + (cx >> 3) * 24 + (3 + cy) * 8 + (cx & 7);
-    else
-      o = 24 * 64 + 4 * 24 + (cx >> 3) * 24 + (cy - TC) * 8 + (cx & 7);
-    const double2 v = stg[o];
-    su[ty * SP + tx] = sgu * v.x;
-    sv[ty * SP + tx] = sgv * v.y;
+  // Tiles whose ghost ring lies inside the domain (all but the perimeter tiles) use a precomputed table
+  // (source slot in the staging area, destination in the planes) for the 1408 cells of the cross-shaped
+  // footprint: 11 table entries per thread.  Index arithmetic used to be 29 % of the kernel's instructions.
+  const bool edge = gx0 < GH || gy0 < GH || gx0 + TC + GH > NX || gy0 + TC + GH > NY;
+  if (!edge) {
+#pragma unroll
+    for (int k = 0; k < ADV_LUT_N / NT_ADV; k++) {
+      const unsigned e = __ldg(lut + k * NT_ADV + tid);
+      const double2 v = stg[e & 0xffffu];
+      su[e >> 16] = v.x;
+      sv[e >> 16] = v.y;
+    }
+  } else {
+    // (VectorLab::applyBCface main.cpp:3131-3154: ghost = wall-adjacent cell, normal component negated)
+    for (int idx = tid; idx < TW * TW; idx += NT_ADV) {
+      const int ty = idx / TW, tx = idx - ty * TW;
+      const int lx = tx - GH, ly = ty - GH;
+      const bool xin = (unsigned)lx < (unsigned)TC, yin = (unsigned)ly < (unsigned)TC;
+      if (!xin && !yin) continue; // corner ghosts are never read (cross-shaped stencil)
+      int gx = gx0 + lx, gy = gy0 + ly;
+      double sgu = 1.0, sgv = 1.0;
+      if (gx < 0) { gx = 0; sgu = -1.0; } else if (gx >= NX) { gx = NX - 1; sgu = -1.0; }
+      if (gy < 0) { gy = 0; sgv = -1.0; } else if (gy >= NY) { gy = NY - 1; sgv = -1.0; }
+      const double2 v = stg[adv_src_slot(gx - gx0, gy - gy0)];
+      su[ty * SP + tx] = sgu * v.x;
+      sv[ty * SP + tx] = sgv * v.y;
+    }
   }
   __syncthreads(); // staging is dead from here on: Ru/Rv reuse it
 
@@ -331,8 +356,8 @@ advect_stage_kernel(const double *__restrict__ in, const double *__restrict__ ol
   }
 }
 
-typedef void (*adv_fn)(const double *, const double *, double *, const int *, const int *, int, int, int,
-                       double, double, double);
+typedef void (*adv_fn)(const double *, const double *, double *, const int *, const int *, const unsigned *, int,
+                       int, int, int, double, double, double);
 template <int UNR, bool CM, bool ONE> static adv_fn pick_mode(int mode) {
   switch (mode) {
   case 0: return advect_stage_kernel<0, UNR, 2, CM, ONE>;
@@ -359,6 +384,17 @@ int launch_advect(cup2d_sim *s, const double *in, const double *old, double *out
     one = e ? atoi(e) : 1;
     CUP2D_CUDA(cudaMemcpyToSymbol(cW, hW, sizeof hW));
   }
+  if (!s->d_adv_lut) { // repack table of interior tiles: (destination in the planes) << 16 | source slot
+    std::vector<unsigned> lut;
+    for (int ty = 0; ty < TW; ty++)
+      for (int tx = 0; tx < TW; tx++) {
+        const int lx = tx - GH, ly = ty - GH;
+        if (!((unsigned)lx < (unsigned)TC) && !((unsigned)ly < (unsigned)TC)) continue;
+        lut.push_back((unsigned)(ty * SP + tx) << 16 | (unsigned)adv_src_slot(lx, ly));
+      }
+    CUP2D_CUDA(cudaMalloc(&s->d_adv_lut, lut.size() * sizeof(unsigned)));
+    CUP2D_CUDA(cudaMemcpy(s->d_adv_lut, lut.data(), lut.size() * sizeof(unsigned), cudaMemcpyHostToDevice));
+  }
   const int mode = raw ? 0 : (old == in ? 1 : 2);
   adv_fn fn = unr == 5 ? pick_flags<5>(mode, cm, one) : pick_flags<10>(mode, cm, one);
   static bool configured[3] = {false, false, false};
@@ -371,8 +407,10 @@ int launch_advect(cup2d_sim *s, const double *in, const double *old, double *out
   const double ofac = coef / (s->h * s->h);
   dim3 grid(s->ntiles), block(NT_ADV);
   ProfScope prof(s, KC_ADVECT);
-  fn<<<grid, block, ADV_SMEM, s->stream>>>(in, old, out, s->d_tiles, s->d_tile_org, s->nbx, s->nby,
-                                           (int)s->nloc, afac, dfac, ofac);
+  static const int pf = getenv("CUP2D_ADV_PREFETCH") ? atoi(getenv("CUP2D_ADV_PREFETCH")) : 1;
+  const int prefetch_dist = pf ? s->num_sms * 4 : (1 << 30); // one resident wave ahead (4 CTAs per SM)
+  fn<<<grid, block, ADV_SMEM, s->stream>>>(in, old, out, s->d_tiles, s->d_tile_org, s->d_adv_lut, s->nbx,
+                                           s->nby, (int)s->nloc, prefetch_dist, afac, dfac, ofac);
   s->launches++;
   CUP2D_CUDA(cudaGetLastError());
   return CUP2D_OK;

@@ -19,6 +19,7 @@
 #include "rows.cuh"
 #include "sim.h"
 #include <cmath>
+#include <cstdlib>
 
 namespace cup2d {
 
@@ -137,8 +138,11 @@ k_init(const double *__restrict__ b, const double *__restrict__ x0, double *__re
   CHUNK_LOOP() {
     const int nv = min(32, nrows - row0);
     double xx[8], ax[8], bb[8], zero[8];
-    rows_lap(x0, row0, nv, nbr, sw, lane, xx, ax, IRR ? irr : IrrView());
-    rows_load1(b, row0, nv, sw, lane, bb);
+    double2 cx0[4], cb[4];
+    chunk_ld(x0, row0, nv, lane, cx0);
+    chunk_ld(b, row0, nv, lane, cb);
+    rows_lap_c(cx0, x0, row0, nv, nbr, sw, lane, xx, ax, IRR ? irr : IrrView());
+    chunk_to_rows(sw, lane, cb, bb);
 #pragma unroll
     for (int i = 0; i < 8; i++) {
       bb[i] -= ax[i];
@@ -203,8 +207,8 @@ k_pupdate(const double *__restrict__ r, double *__restrict__ rhat, double *__res
 // ---- K2 / K4: y = A z with one or two dots against `d` and y -------------------------------------
 //   MODE 0 (K2): nu = A z ; rhat.nu             -> alpha = rho/(rhat.nu + eps)   (cuda.cu:487-496)
 //   MODE 1 (K4): t  = A z ; t.r, t.t            -> omega = t.r/(t.t + eps)       (cuda.cu:506-518)
-template <int MODE, bool IRR>
-__global__ void __launch_bounds__(NT)
+template <int MODE, bool IRR, bool HOIST>
+__global__ void __launch_bounds__(NT, 3)
 k_spmv(const double *__restrict__ z, const double *__restrict__ d, double *__restrict__ yout,
        const int4 *__restrict__ nbr, int nrows, KrylovState *st, double *partials,
        unsigned int *counter, Comm comm, IrrView irr) {
@@ -213,11 +217,14 @@ k_spmv(const double *__restrict__ z, const double *__restrict__ d, double *__res
   double sums[2] = {0, 0};
   CHUNK_LOOP() {
     const int nv = min(32, nrows - row0);
+    // HOIST: both global loads are issued before any shared-memory work (memory-level parallelism)
+    double2 cz[4], ca[4], cd[4];
+    chunk_ld(z, row0, nv, lane, cz);
+    if (HOIST) chunk_ld(d, row0, nv, lane, cd);
     double zz[8], az[8];
-    rows_lap(z, row0, nv, nbr, sw, lane, zz, az, IRR ? irr : IrrView());
+    rows_lap_c(cz, z, row0, nv, nbr, sw, lane, zz, az, IRR ? irr : IrrView());
     // back to chunk layout: the dots and the store are element-wise
-    double2 ca[4], cd[4];
-    chunk_ld(d, row0, nv, lane, cd);
+    if (!HOIST) chunk_ld(d, row0, nv, lane, cd);
     rows_to_chunk(sw, lane, az, ca);
 #pragma unroll
     for (int j = 0; j < 4; j++) {
@@ -352,6 +359,7 @@ int poisson_solve(cup2d_sim *s, double tol_abs, double tol_rel, int max_restarts
   const int nrows = (int)s->nloc * 8;
   const int grid = red_grid(s, nrows);
   const int4 *nbr = reinterpret_cast<const int4 *>(s->d_nbr);
+  static const bool hoist = getenv("CUP2D_SPMV_HOIST") ? atoi(getenv("CUP2D_SPMV_HOIST")) != 0 : true;
   const bool has_irr = s->n_irr_rows > 0; // general rows present: kernels with the CSR override compiled in
   KrylovState *h = s->h_state;
   *h = KrylovState{};
@@ -388,11 +396,11 @@ int poisson_solve(cup2d_sim *s, double tol_abs, double tol_rel, int max_restarts
       {
         ProfScope prof(s, KC_SPMV_NU);
         if (has_irr)
-          k_spmv<0, true><<<grid, NT, 0, s->stream>>>(s->kz, s->krhat, s->knu, nbr, nrows, s->d_state,
+          k_spmv<0, true, false><<<grid, NT, 0, s->stream>>>(s->kz, s->krhat, s->knu, nbr, nrows, s->d_state,
                                                       s->d_partials, s->d_counter, s->comm, irr_view(s));
         else
-          k_spmv<0, false><<<grid, NT, 0, s->stream>>>(s->kz, s->krhat, s->knu, nbr, nrows, s->d_state,
-                                                       s->d_partials, s->d_counter, s->comm, irr_view(s));
+          (hoist ? k_spmv<0, false, true> : k_spmv<0, false, false>)<<<grid, NT, 0, s->stream>>>(
+              s->kz, s->krhat, s->knu, nbr, nrows, s->d_state, s->d_partials, s->d_counter, s->comm, irr_view(s));
       }
       {
         ProfScope prof(s, KC_XRUPDATE);
@@ -403,11 +411,11 @@ int poisson_solve(cup2d_sim *s, double tol_abs, double tol_rel, int max_restarts
       {
         ProfScope prof(s, KC_SPMV_T);
         if (has_irr)
-          k_spmv<1, true><<<grid, NT, 0, s->stream>>>(s->kz, s->kr, s->kt, nbr, nrows, s->d_state,
+          k_spmv<1, true, false><<<grid, NT, 0, s->stream>>>(s->kz, s->kr, s->kt, nbr, nrows, s->d_state,
                                                       s->d_partials, s->d_counter, s->comm, irr_view(s));
         else
-          k_spmv<1, false><<<grid, NT, 0, s->stream>>>(s->kz, s->kr, s->kt, nbr, nrows, s->d_state,
-                                                       s->d_partials, s->d_counter, s->comm, irr_view(s));
+          (hoist ? k_spmv<1, false, true> : k_spmv<1, false, false>)<<<grid, NT, 0, s->stream>>>(
+              s->kz, s->kr, s->kt, nbr, nrows, s->d_state, s->d_partials, s->d_counter, s->comm, irr_view(s));
       }
       {
         ProfScope prof(s, KC_FINAL);

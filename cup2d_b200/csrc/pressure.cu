@@ -50,11 +50,11 @@ int launch_umax(cup2d_sim *s, double *umax_out) {
 // (pressure_rhs main.cpp:6105-6139: ((u_E - u_W) + v_N) - v_S, left to right; VectorLab ghosts
 // main.cpp:3131-3154: normal component negated)
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void rows_div(const double *__restrict__ f, int row0, int nvalid,
+__device__ __forceinline__ void rows_div(const double2 (&cf)[8], const double *__restrict__ f, int nvalid,
                                          const int4 nb, int slot, int y, double *sw, int lane,
                                          double (&d)[8]) {
   double2 c[8];
-  rows_load2(f, row0, nvalid, sw, lane, c);
+  chunk2_to_rows(sw, nvalid, lane, cf, c);
   if (lane < nvalid) {
     const double2 *f2 = reinterpret_cast<const double2 *>(f);
     double vu[8], vd[8];
@@ -114,17 +114,23 @@ pressure_rhs_kernel(const double *__restrict__ vel, const double *__restrict__ u
     const int row = row0 + lane, slot = row >> 3, y = row & 7;
     const int4 nb = lane < nv ? nbr[slot] : make_int4(-1, -1, -1, -1);
     double out[8], t[8], pc[8];
-    rows_div(vel, row0, nv, nb, slot, y, sw, lane, out);
+    // every global load of the chunk is issued up front (memory-level parallelism), then the smem work
+    double2 cvel[8], cpold[4];
+    chunk2_ld(vel, row0, nv, lane, cvel);
+    chunk_ld(pold, row0, nv, lane, cpold);
+    rows_div(cvel, vel, nv, nb, slot, y, sw, lane, out);
 #pragma unroll
     for (int i = 0; i < 8; i++) out[i] *= fac;
     if (HAS_UDEF) {
       double du[8];
-      rows_div(udef, row0, nv, nb, slot, y, sw, lane, du);
+      double2 cud[8];
+      chunk2_ld(udef, row0, nv, lane, cud);
+      rows_div(cud, udef, nv, nb, slot, y, sw, lane, du);
       rows_load1(chi, row0, nv, sw, lane, t);
 #pragma unroll
       for (int i = 0; i < 8; i++) out[i] = out[i] - fac * t[i] * du[i];
     }
-    rows_lap(pold, row0, nv, nbr, sw, lane, pc, t);
+    rows_lap_c(cpold, pold, row0, nv, nbr, sw, lane, pc, t);
 #pragma unroll
     for (int i = 0; i < 8; i++) out[i] -= t[i];
     rows_store1(tmp, row0, nv, sw, lane, out);

@@ -95,6 +95,55 @@ __device__ __forceinline__ void rows_store1(double *__restrict__ f, int row0, in
 }
 
 // ---- vector field (u,v interleaved): lane l gets row row0+l as 8 double2 (padded scratch) -----------
+// chunk layout of a vector field: lane l holds pieces j*32+l, j = 0..7 (4 KB per warp, coalesced)
+__device__ __forceinline__ void chunk2_ld(const double *__restrict__ f, int row0, int nvalid, int lane,
+                                          double2 (&c)[8]) {
+  const double2 *src = reinterpret_cast<const double2 *>(f) + (size_t)row0 * 8;
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    const int i = j * 32 + lane;
+    c[j] = (i >> 3) < nvalid ? src[i] : make_double2(0.0, 0.0);
+  }
+}
+__device__ __forceinline__ void chunk2_st(double *__restrict__ f, int row0, int nvalid, int lane,
+                                          const double2 (&c)[8]) {
+  double2 *dst = reinterpret_cast<double2 *>(f) + (size_t)row0 * 8;
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    const int i = j * 32 + lane;
+    if ((i >> 3) < nvalid) dst[i] = c[j];
+  }
+}
+__device__ __forceinline__ void chunk2_to_rows(double *sw, int nvalid, int lane, const double2 (&t)[8],
+                                               double2 (&c)[8]) {
+  double2 *s2 = reinterpret_cast<double2 *>(sw);
+  __syncwarp();
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    const int i = j * 32 + lane;
+    s2[(i >> 3) * RS2 + (i & 7)] = t[j];
+  }
+  __syncwarp();
+  if (lane < nvalid) {
+#pragma unroll
+    for (int p = 0; p < 8; p++) c[p] = s2[lane * RS2 + p];
+  } else {
+#pragma unroll
+    for (int p = 0; p < 8; p++) c[p] = make_double2(0.0, 0.0);
+  }
+}
+__device__ __forceinline__ void rows2_to_chunk(double *sw, int lane, const double2 (&c)[8], double2 (&t)[8]) {
+  double2 *s2 = reinterpret_cast<double2 *>(sw);
+  __syncwarp();
+#pragma unroll
+  for (int p = 0; p < 8; p++) s2[lane * RS2 + p] = c[p];
+  __syncwarp();
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    const int i = j * 32 + lane;
+    t[j] = s2[(i >> 3) * RS2 + (i & 7)];
+  }
+}
 __device__ __forceinline__ void rows_load2(const double *__restrict__ f, int row0, int nvalid,
                                            double *sw, int lane, double2 (&c)[8]) {
   const double2 *src = reinterpret_cast<const double2 *>(f) + (size_t)row0 * 8;
@@ -164,10 +213,21 @@ struct IrrView {
 // Undivided 5-point Laplacian rows of a scalar field for the warp's 32 rows, ghost = the cell itself at
 // a domain wall (Neumann rows of main.cpp:7100-7107 / ScalarLab::Neumann2D main.cpp:3210-3245).
 // Returns the own row in c and the Laplacian in out.  Summation order S,W,E,N then -4C.
+// rows_lap_c: the caller already holds the chunk of z (so that other global loads can be in flight too)
+__device__ __forceinline__ void rows_lap_c(const double2 (&cz)[4], const double *__restrict__ z, int row0,
+                                           int nvalid, const int4 *__restrict__ nbr, double *sw, int lane,
+                                           double (&c)[8], double (&out)[8], const IrrView irr = IrrView());
 __device__ __forceinline__ void rows_lap(const double *__restrict__ z, int row0, int nvalid,
                                          const int4 *__restrict__ nbr, double *sw, int lane,
                                          double (&c)[8], double (&out)[8], const IrrView irr = IrrView()) {
-  rows_load1(z, row0, nvalid, sw, lane, c);
+  double2 cz[4];
+  chunk_ld(z, row0, nvalid, lane, cz);
+  rows_lap_c(cz, z, row0, nvalid, nbr, sw, lane, c, out, irr);
+}
+__device__ __forceinline__ void rows_lap_c(const double2 (&cz)[4], const double *__restrict__ z, int row0,
+                                           int nvalid, const int4 *__restrict__ nbr, double *sw, int lane,
+                                           double (&c)[8], double (&out)[8], const IrrView irr) {
+  chunk_to_rows(sw, lane, cz, c);
   const int row = row0 + lane, slot = row >> 3, y = row & 7;
   if (lane < nvalid) {
     const int4 nb = nbr[slot];

@@ -62,6 +62,7 @@ struct cup2d_sim {
   int *d_tiles = nullptr;              // [ntiles][TILE_SLOTS]
   int *d_tile_org = nullptr;           // [ntiles][2] tile origin in blocks
   int ntiles = 0;
+  unsigned *d_adv_lut = nullptr;       // repack table of the advect kernel (interior tiles)
   // fields (dim*64*nslots doubles each)
   double *f[CUP2D_NFIELDS] = {};
   // Krylov vectors (64*nslots)
