@@ -407,7 +407,7 @@ int launch_advect(cup2d_sim *s, const double *in, const double *old, double *out
   const double ofac = coef / (s->h * s->h);
   dim3 grid(s->ntiles), block(NT_ADV);
   ProfScope prof(s, KC_ADVECT);
-  static const int pf = getenv("CUP2D_ADV_PREFETCH") ? atoi(getenv("CUP2D_ADV_PREFETCH")) : 1;
+  static const int pf = getenv("CUP2D_ADV_PREFETCH") ? atoi(getenv("CUP2D_ADV_PREFETCH")) : 0; // measured: prefetching costs 7 % (profiles/r01h_ab_test.jsonl)
   const int prefetch_dist = pf ? s->num_sms * 4 : (1 << 30); // one resident wave ahead (4 CTAs per SM)
   fn<<<grid, block, ADV_SMEM, s->stream>>>(in, old, out, s->d_tiles, s->d_tile_org, s->d_adv_lut, s->nbx,
                                            s->nby, (int)s->nloc, prefetch_dist, afac, dfac, ofac);
