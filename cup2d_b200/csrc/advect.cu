@@ -356,6 +356,154 @@ advect_stage_kernel(const double *__restrict__ in, const double *__restrict__ ol
   }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Component-split variant: 256 threads per tile, warps 0-3 carry the u-lines, warps 4-7 the v-lines.
+// Same arithmetic; each thread runs ONE dependency chain with half the registers, so 8 CTAs x ... no:
+// 4 CTAs x 8 warps = 32 warps/SM instead of 16: the kernel is bound by dependent-issue latency of the
+// FP64 chains (stall_wait 30 %, FP64 pipe 57 % in profiles/r01f_advect_ncu.md), which more resident warps hide.
+// ---------------------------------------------------------------------------------------------------
+constexpr int NT_ADV2 = 256;
+
+// one component q along one line, sign/multiplier from the advecting plane U (same window indexing)
+template <int NEWTON, bool CM, class Emit>
+__device__ __forceinline__ void weno_line1(const double *__restrict__ q, const double *__restrict__ U,
+                                           const int es, Emit emit) {
+  LineState A;
+  line_init<CM>(A, q, es);
+  unsigned pos = 0;
+#pragma unroll
+  for (int k = 2; k <= 12; k++) pos |= is_pos(U[k * es]) ? (1u << k) : 0u;
+#pragma unroll
+  for (int w = 2; w <= 11; ++w) {
+    const bool vc = (unsigned)(w - 3) < 8u, vn = (unsigned)(w - 2) < 8u, vp = (unsigned)(w - 4) < 8u;
+    const unsigned pw = pos >> (w - 1);
+    const bool posp = pw & 1u;
+    const bool needP = (pw & ((vc ? 2u : 0u) | (vn ? 4u : 0u))) != 0u;
+    const bool needM = (~pw & ((vc ? 2u : 0u) | (vp ? 1u : 0u))) != 0u;
+    double a1, a2, a3;
+    line_betas(A, a1, a2, a3);
+    double rP = 0, rM = 0;
+    if (needP) rP = ratio_plus<CM, NEWTON>(A, a1, a2, a3);
+    if (needM) rM = ratio_minus<CM, NEWTON>(A, a1, a2, a3);
+    if (vp) {
+      const double dq = posp ? A.dm2 + (A.rP1 - A.rP2) : A.dm1 + (rM - A.rM1);
+      emit(w - 4, U[(w - 1) * es], q[(w - 1) * es], dq, A.dm1 - A.dm2);
+    }
+    if (w < 11) line_advance<CM>(A, q[(w + 3) * es], rP, rM);
+  }
+}
+
+template <int MODE, bool CM>
+__global__ void __launch_bounds__(NT_ADV2, 4)
+advect_stage_kernel2(const double *__restrict__ in, const double *__restrict__ old,
+                     double *__restrict__ out, const int *__restrict__ tiles,
+                     const int *__restrict__ tile_org, const unsigned *__restrict__ lut, int nbx, int nby,
+                     int nloc, int prefetch_dist, double afac, double dfac, double ofac) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  double2 *stg = reinterpret_cast<double2 *>(smem);
+  double *su = reinterpret_cast<double *>(smem + OFF_SU);
+  double *sv = reinterpret_cast<double *>(smem + OFF_SV);
+  double *Ru = reinterpret_cast<double *>(smem + OFF_RU);
+  double *Rv = reinterpret_cast<double *>(smem + OFF_RV);
+  uint64_t *bar = reinterpret_cast<uint64_t *>(smem + OFF_BAR);
+  int *s_slots = reinterpret_cast<int *>(smem + OFF_SLOTS);
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int comp = warp >> 2, sub = warp & 3; // component carried by this thread, segment index
+  const int tile = blockIdx.x;
+  if (tid < TILE_SLOTS) s_slots[tid] = tiles[tile * TILE_SLOTS + tid];
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  if (warp == 0) {
+    const int slot = s_slots[lane];
+    const uint32_t bytes = slot >= 0 ? (lane < 24 ? 1024u : 384u) : 0u;
+    uint32_t tot = bytes;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+    if (lane == 0) mbar_arrive_expect_tx(bar, tot);
+    __syncwarp();
+    if (slot >= 0) {
+      const unsigned char *src = reinterpret_cast<const unsigned char *>(in + (size_t)slot * 128);
+      if (lane >= 24 && lane < 28) src += 5 * 128;
+      unsigned char *dst = smem + (lane < 24 ? lane * 1024 : 24 * 1024 + (lane - 24) * 384);
+      tma_load_1d(dst, src, bytes, bar);
+    }
+  }
+  // y-pass ownership: column yx of block row `sub`, component `comp`
+  const int yx = lane, ys = sub;
+  const int yb = ys * 4 + (yx >> 3);
+  const int yslot = s_slots[yb];
+  const bool store = yslot >= 0 && yslot < nloc;
+  double oldv[8];
+  if (MODE == 2) {
+    const double *oldp = old + ((size_t)(store ? yslot : 0) * 64 + (yx & 7)) * 2 + comp;
+#pragma unroll
+    for (int c = 0; c < 8; c++) oldv[c] = store ? oldp[c * 16] : 0.0;
+  }
+  const int gx0 = tile_org[2 * tile] * CUP2D_BS, gy0 = tile_org[2 * tile + 1] * CUP2D_BS;
+  const int NX = nbx * CUP2D_BS, NY = nby * CUP2D_BS;
+  if (warp == 0) mbar_wait(bar, 0);
+  __syncthreads();
+  const bool edge = gx0 < GH || gy0 < GH || gx0 + TC + GH > NX || gy0 + TC + GH > NY;
+  if (!edge) {
+#pragma unroll
+    for (int k = 0; k < (ADV_LUT_N + NT_ADV2 - 1) / NT_ADV2; k++) {
+      const int i = k * NT_ADV2 + tid;
+      if (i < ADV_LUT_N) {
+        const unsigned e = __ldg(lut + i);
+        const double2 v = stg[e & 0xffffu];
+        su[e >> 16] = v.x;
+        sv[e >> 16] = v.y;
+      }
+    }
+  } else {
+    for (int idx = tid; idx < TW * TW; idx += NT_ADV2) {
+      const int ty = idx / TW, tx = idx - ty * TW;
+      const int lx = tx - GH, ly = ty - GH;
+      const bool xin = (unsigned)lx < (unsigned)TC, yin = (unsigned)ly < (unsigned)TC;
+      if (!xin && !yin) continue;
+      int gx = gx0 + lx, gy = gy0 + ly;
+      double sgu = 1.0, sgv = 1.0;
+      if (gx < 0) { gx = 0; sgu = -1.0; } else if (gx >= NX) { gx = NX - 1; sgu = -1.0; }
+      if (gy < 0) { gy = 0; sgv = -1.0; } else if (gy >= NY) { gy = NY - 1; sgv = -1.0; }
+      const double2 v = stg[adv_src_slot(gx - gx0, gy - gy0)];
+      su[ty * SP + tx] = sgu * v.x;
+      sv[ty * SP + tx] = sgv * v.y;
+    }
+  }
+  __syncthreads();
+  double *sq = comp == 0 ? su : sv; // the plane of this thread's component
+  double *R = comp == 0 ? Ru : Rv;
+  // x pass: lane = row, advecting plane su
+  {
+    const int off = (lane + GH) * SP + 8 * sub;
+    double *r = R + lane * RP + 8 * sub;
+    weno_line1<2, CM>(sq + off, su + off, 1, [&](int c, double U, double, double dq, double D2q) {
+      r[c] = fma(afac * U, dq, dfac * D2q);
+    });
+  }
+  __syncthreads();
+  // y pass: lane = column, advecting plane sv; final combine and store of this component
+  {
+    const int off = (8 * ys) * SP + (yx + GH);
+    const double *r = R + (8 * ys) * RP + yx;
+    double *outp = out + ((size_t)(store ? yslot : 0) * 64 + (yx & 7)) * 2 + comp;
+    weno_line1<2, CM>(sq + off, sv + off, SP, [&](int c, double V, double qc, double dq, double D2q) {
+      const double t = r[c * RP] + fma(afac * V, dq, dfac * D2q);
+      if (store) {
+        double o;
+        if (MODE == 0) o = t;
+        else if (MODE == 1) o = fma(ofac, t, qc);
+        else o = fma(ofac, t, oldv[c]);
+        outp[c * 16] = o;
+      }
+    });
+  }
+}
+
 typedef void (*adv_fn)(const double *, const double *, double *, const int *, const int *, const unsigned *, int,
                        int, int, int, double, double, double);
 template <int UNR, bool CM, bool ONE> static adv_fn pick_mode(int mode) {
@@ -396,7 +544,8 @@ int launch_advect(cup2d_sim *s, const double *in, const double *old, double *out
     CUP2D_CUDA(cudaMemcpy(s->d_adv_lut, lut.data(), lut.size() * sizeof(unsigned), cudaMemcpyHostToDevice));
   }
   const int mode = raw ? 0 : (old == in ? 1 : 2);
-  adv_fn fn = unr == 5 ? pick_flags<5>(mode, cm, one) : pick_flags<10>(mode, cm, one);
+  static const int split = getenv("CUP2D_ADV_SPLIT") ? atoi(getenv("CUP2D_ADV_SPLIT")) : 0;
+  adv_fn fn = split ? (mode == 0 ? advect_stage_kernel2<0, true> : mode == 1 ? advect_stage_kernel2<1, true> : advect_stage_kernel2<2, true>) : unr == 5 ? pick_flags<5>(mode, cm, one) : pick_flags<10>(mode, cm, one);
   static bool configured[3] = {false, false, false};
   if (!configured[mode]) {
     CUP2D_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, ADV_SMEM));
@@ -405,7 +554,7 @@ int launch_advect(cup2d_sim *s, const double *in, const double *old, double *out
   const double afac = -dt * s->h; // main.cpp:5447
   const double dfac = s->nu * dt; // main.cpp:5446
   const double ofac = coef / (s->h * s->h);
-  dim3 grid(s->ntiles), block(NT_ADV);
+  dim3 grid(s->ntiles), block(split ? NT_ADV2 : NT_ADV);
   ProfScope prof(s, KC_ADVECT);
   static const int pf = getenv("CUP2D_ADV_PREFETCH") ? atoi(getenv("CUP2D_ADV_PREFETCH")) : 0; // measured: prefetching costs 7 % (profiles/r01h_ab_test.jsonl)
   const int prefetch_dist = pf ? s->num_sms * 4 : (1 << 30); // one resident wave ahead (4 CTAs per SM)

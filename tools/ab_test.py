@@ -5,8 +5,7 @@ import subprocess
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-combos = [dict(CUP2D_ADV_PREFETCH="1", CUP2D_SPMV_HOIST="1"), dict(CUP2D_ADV_PREFETCH="0", CUP2D_SPMV_HOIST="1"),
-          dict(CUP2D_ADV_PREFETCH="1", CUP2D_SPMV_HOIST="0")]
+combos = [dict(CUP2D_ADV_SPLIT="0"), dict(CUP2D_ADV_SPLIT="1")]
 out = []
 for c in combos:
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--no-cpu-baseline", "--no-e2e", "--steps", "5"],
