@@ -331,9 +331,12 @@ def main():
     if adv:
         # the north-star kernel: HBM fraction and the FP64-pipe bound it actually sits under
         gcell = cells_loc / (adv["ms_per_launch"] * 1e-3) / 1e9
+        sm_mhz = (clocks or {}).get("sm_mhz") or 1920.0
+        fp64_floor_ms = cells_loc * 191.0 / 32.0 / (148 * 2 * sm_mhz * 1e6) * 1e3   # 191 FP64 instr/cell (ncu), 2 warp-instr/clk/SM
         extra["advect_stage"] = {"Gcell_per_s": gcell, "achieved_GBs": adv["achieved_GBs"], "frac_hbm": adv["frac_hbm"],
                                  "ms_per_launch": adv["ms_per_launch"], "alg_bytes_per_cell": 48.0,
-                                 "note": "FP64-pipe-bound (~230 DFMA-class instr/cell vs 64 lanes/clk/SM): see DESIGN.md"}
+                                 "fp64_floor_ms": fp64_floor_ms, "frac_fp64_floor": fp64_floor_ms / adv["ms_per_launch"],
+                                 "note": "bound by the FP64 pipe, not HBM: 191 FP64 instr/cell (ncu) at 64 lanes/clk/SM; see DESIGN.md 3.1"}
     it_ms = sum(k["ms_per_launch"] * k["launches_per_step"] for k in kernels
                 if k["kernel"] in ("k_pupdate", "k_spmv<0>", "k_xr_update", "k_spmv<1>", "k_final")) / max(K, 1)
     if it_ms > 0:

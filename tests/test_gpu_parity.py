@@ -316,3 +316,84 @@ def test_two_ranks_on_two_gpus_match_the_oracle():
                        stderr=subprocess.STDOUT, text=True, timeout=300)
     assert r.returncode == 0, r.stdout[-2000:]
     assert '"check": "parity_256"' in r.stdout
+
+
+def test_general_rows_override_reproduces_stencil_solve():
+    """cup2d_poisson_create_general: cut a few block faces out of the neighbour table and hand the affected
+    rows over as complete CSR rows instead (what the adapter does with coarse-fine rows).  The matrix is the
+    same, so K iterations must give the same iterate as the pure stencil path."""
+    import ctypes as C
+    from cup2d_b200 import lib as Lb
+    lib = cup2d_b200.load_library()
+    Lv = 3
+    nb1 = 1 << Lv
+    order = cup2d_b200.block_order(1, 1, Lv)
+    nblk = len(order)
+    gid = -np.ones((nb1, nb1), dtype=np.int64)
+    gid[order[:, 1], order[:, 0]] = np.arange(nblk)
+    nbr = np.empty((nblk, 4), dtype=np.int32)
+    for k, (i, j) in enumerate(order):
+        nbr[k] = [gid[j, i - 1] if i > 0 else -1, gid[j, i + 1] if i < nb1 - 1 else -1,
+                  gid[j - 1, i] if j > 0 else -1, gid[j + 1, i] if j < nb1 - 1 else -1]
+    full = nbr.copy()
+    rng = np.random.default_rng(3)
+    rows = {}
+
+    def stencil_row(k, lr):  # complete row of the 5-point Neumann matrix from the FULL table
+        x, y = lr % 8, lr // 8
+        cols = []
+        for d, (dx, dy) in enumerate([(-1, 0), (1, 0), (0, -1), (0, 1)]):
+            xx, yy = x + dx, y + dy
+            if 0 <= xx < 8 and 0 <= yy < 8:
+                cols.append(k * 64 + yy * 8 + xx)
+            elif full[k, d] >= 0:
+                cols.append(full[k, d] * 64 + (yy % 8) * 8 + (xx % 8))
+        return [(c, 1.0) for c in cols] + [(k * 64 + lr, -float(len(cols)))]
+
+    for k in rng.choice(nblk, 10, replace=False):
+        d = int(rng.integers(0, 4))
+        n = full[k, d]
+        if n < 0:
+            continue
+        od = d ^ 1
+        nbr[k, d] = -1
+        nbr[n, od] = -1
+        for kk, dd in ((k, d), (n, od)):
+            for t in range(8):
+                lr = {0: t * 8, 1: t * 8 + 7, 2: t, 3: 56 + t}[dd]
+                rows[kk * 64 + lr] = None
+    # any row whose block lost a face must be complete in the CSR (corner cells may touch two cut faces)
+    irr = sorted(rows)
+    rowptr, cols, vals = [0], [], []
+    for r in irr:
+        for c, v in sorted(stencil_row(r // 64, r % 64)):
+            cols.append(c)
+            vals.append(v)
+        rowptr.append(len(cols))
+    irr_a, rp_a = np.array(irr, dtype=np.int32), np.array(rowptr, dtype=np.int32)
+    col_a, val_a = np.array(cols, dtype=np.int32), np.array(vals, dtype=np.float64)
+    h = C.c_void_p()
+    I32 = C.POINTER(C.c_int32)
+    Lb.check(lib.cup2d_poisson_create_general(nblk, nbr.ctypes.data_as(I32), len(irr), irr_a.ctypes.data_as(I32),
+                                              rp_a.ctypes.data_as(I32), col_a.ctypes.data_as(I32),
+                                              val_a.ctypes.data_as(C.POINTER(C.c_double)), 0, C.byref(h)))
+    N = 8 << Lv
+    bglob = rng.uniform(-1, 1, (N, N))
+    bglob -= bglob.mean()
+    bb = cup2d_b200.to_blocks(bglob, order, nb1)
+    x0 = np.zeros_like(bb)
+    Lb.check(lib.cup2d_field_upload(h, 6, bb.ctypes.data))
+    Lb.check(lib.cup2d_field_upload(h, 4, x0.ctypes.data))
+    it, err = C.c_int(), C.c_double()
+    Lb.check(lib.cup2d_poisson_solve(h, 0.0, 0.0, 0, 12, C.byref(it), C.byref(err)))
+    xg = np.empty_like(bb)
+    Lb.check(lib.cup2d_field_download(h, 4, xg.ctypes.data))
+    lib.cup2d_destroy(h)
+    sim = cup2d_b200.Simulation(Lv)
+    sim.upload("tmp", bglob)
+    sim.upload("pres", np.zeros((N, N)))
+    it2, err2 = sim.poisson_solve(max_iter=12)
+    xs = cup2d_b200.to_blocks(sim.download("pres"), order, nb1)
+    sim.close()
+    assert it.value == it2 == 12 and len(irr) > 0
+    assert np.abs(xg - xs).max() < 1e-10 and abs(err.value - err2) < 1e-10
