@@ -397,3 +397,21 @@ def test_general_rows_override_reproduces_stencil_solve():
     sim.close()
     assert it.value == it2 == 12 and len(irr) > 0
     assert np.abs(xg - xs).max() < 1e-10 and abs(err.value - err2) < 1e-10
+
+
+def test_full_step_1024_vs_oracle():
+    """BASELINE config 2 size (1024^2, Taylor-Green, nu = 1e-3 => Re 1000): one full step, 10 BiCGSTAB
+    iterations, against the numpy oracle."""
+    L = 7
+    N = 8 << L
+    u, v, p, *_ = make_fields(N, 2024)
+    sim = cup2d_b200.Simulation(L, nu=1e-3, cfl=0.5)
+    sim.upload("vel", u, v)
+    sim.upload("pres", p)
+    dt, it, err = sim.step(max_iter=10)
+    ref = orc.step(u, v, p, 1e-3, 0.5, kiter=10)
+    assert abs(dt - ref["dt"]) < 1e-16 and it == 10
+    gu, gv = sim.download("vel")
+    assert np.abs(gu - ref["u"]).max() < 1e-9 and np.abs(gv - ref["v"]).max() < 1e-9
+    assert np.abs(sim.download("pres") - ref["p"]).max() < 1e-8
+    sim.close()
