@@ -2,7 +2,7 @@
 # Run on the GPU box (via gpurun): bench line + ncu launch list + ncu full captures of the top kernels.
 # Outputs land in gpurun_out/ (scratch); summaries worth judging are copied to profiles/ by hand.
 set -u
-TAG=${1:-r01f}
+TAG=${1:-r01i}
 OUT=gpurun_out
 mkdir -p $OUT
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $OUT/smi_$TAG.txt 2>&1
