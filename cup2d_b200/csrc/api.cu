@@ -441,7 +441,7 @@ void cup2d_destroy(cup2d_sim *s) {
   for (auto p : s->f) cudaFree(p);
   for (auto p : s->kx) cudaFree(p);
   cudaFree(s->kr); cudaFree(s->krhat); cudaFree(s->kp); cudaFree(s->knu); cudaFree(s->kt); cudaFree(s->kz);
-  cudaFree(s->d_nbr); cudaFree(s->d_tiles); cudaFree(s->d_tile_org); cudaFree(s->d_halo_src); cudaFree(s->d_adv_lut);
+  cudaFree(s->d_nbr); cudaFree(s->d_tiles); cudaFree(s->d_tile_org); cudaFree(s->d_halo_src); cudaFree(s->d_adv_lut); cudaFree(s->d_linf);
   cudaFree(s->d_state); cudaFree(s->d_partials); cudaFree(s->d_counter); cudaFree(s->d_scal);
   cudaFree(s->d_mailbox); cudaFree(s->d_peer_ptrs);
   cudaFree(s->d_irr_blk); cudaFree(s->d_irr_tab); cudaFree(s->d_irr_rowptr); cudaFree(s->d_irr_col); cudaFree(s->d_irr_val);
@@ -604,6 +604,14 @@ int cup2d_poisson_solve(cup2d_sim *s, double tol_abs, double tol_rel, int max_re
   CUP2D_CUDA(cudaMemcpyAsync(s->f[CUP2D_PRES], s->kx[s->h_state->opt], (size_t)s->nloc * 64 * sizeof(double),
                              cudaMemcpyDeviceToDevice, s->stream));
   return CUP2D_OK;
+}
+int cup2d_vorticity_tag(cup2d_sim *s, double *block_linf_out) {
+  CHECK_SIM(s);
+  CUP2D_REQUIRE(!s->poisson_only, "vorticity_tag: Poisson-only context has no velocity field geometry");
+  CUP2D_CUDA(cudaSetDevice(s->device));
+  int rc = need_peers(s);
+  if (rc) return rc;
+  return launch_vorticity_tag(s, block_linf_out);
 }
 int cup2d_pressure_correct(cup2d_sim *s, double dt) {
   CHECK_SIM(s);

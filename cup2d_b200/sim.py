@@ -141,6 +141,12 @@ class Simulation:
         _l.check(self.lib.cup2d_poisson_solve(self._h, tol_abs, tol_rel, max_restarts, max_iter, C.byref(it), C.byref(err)))
         return it.value, err.value
 
+    def vorticity_tag(self):
+        """tmp = vorticity(vel); returns max|tmp| per local block (reference infos[] order)."""
+        out = np.empty(self.nloc)
+        _l.check(self.lib.cup2d_vorticity_tag(self._h, out.ctypes.data_as(C.POINTER(C.c_double))))
+        return out
+
     def pressure_correct(self, dt):
         _l.check(self.lib.cup2d_pressure_correct(self._h, dt))
 

@@ -106,6 +106,9 @@ int cup2d_poisson_solve(cup2d_sim *s, double tol_abs, double tol_rel, int max_re
 /* pres = pres - mean(pres); pres += pold - mean(pres); tmpV = -0.5 dt h grad(pres) (undivided);
  * vel += tmpV/h^2.  main.cpp:7120-7187 */
 int cup2d_pressure_correct(cup2d_sim *s, double dt);
+/* Regridding input (main.cpp:3343-3366, 4659-4689): tmp = KernelVorticity(vel); block_linf_out[k] = max|tmp| over
+ * local block k (host array of cup2d_nblocks_local doubles, may be NULL) — what adapt() compares with Rtol/Ctol. */
+int cup2d_vorticity_tag(cup2d_sim *s, double *block_linf_out);
 /* One full time step of the hot path (no bodies): compute_dt (unless dt>0 is given), rk2, tmpV=0
  * (or kept if keep_udef), pressure_rhs, poisson_solve, pressure_correct.  Returns dt used. */
 int cup2d_step(cup2d_sim *s, double dt_in, int keep_udef, double tol_abs, double tol_rel,

@@ -237,6 +237,22 @@ def pressure_rhs1(tmp, pold):
     return tmp - laplacian_neumann(pold)
 
 
+def vorticity(u, v, h):
+    """KernelVorticity::operator() (main.cpp:3343-3366): tmp = (0.5/h) * ((u_S - u_N + v_E) - v_W); this is the
+    field adapt() tags blocks with (L-inf per block against Rtol / Ctol, main.cpp:4676-4689)."""
+    NY, NX = u.shape
+    up, vp = pad_vector(u, v, 1)
+    cy, cx = slice(1, 1 + NY), slice(1, 1 + NX)
+    i2h = 0.5 / h
+    return i2h * (((up[:-2, cx] - up[2:, cx]) + vp[cy, 2:]) - vp[cy, :-2])
+
+
+def block_linf(a):
+    """per-block max |a| on the 8x8 blocks, as an array [nby, nbx] (the quantity adapt() compares, main.cpp:4676-4680)"""
+    NY, NX = a.shape
+    return np.abs(a).reshape(NY // BS, BS, NX // BS, BS).max(axis=(1, 3))
+
+
 def grad_p(p, h, dt):
     """pressureCorrectionKernel::operator() (main.cpp:6021-6043)"""
     NY, NX = p.shape

@@ -19,6 +19,8 @@
 //        out: K(vel)_u K(vel)_v  rhs  rhs1  gradp_u gradp_v   (6 N^2 doubles)
 //             K = KernelAdvectDiffuse output tmpV (undivided), rhs = pressure_rhs(vel,udef,chi),
 //             rhs1 = rhs - lap(p) (pressure_rhs1 with pold = p), gradp = pressureCorrectionKernel(p)
+//   ref_harness vort  L in.bin out.bin
+//        in : as ops;  out: KernelVorticity(vel) written to tmp (N^2 doubles) = adapt()'s tagging field
 //   ref_harness steps L nu cfl nsteps kiter in.bin out.bin
 //        in : as above (udef ignored: no shapes => udef = 0, chi = 0 ; p = initial pres)
 //        out: per step: dt, then u v p  b x   (1 + 5 N^2 doubles), b/x = Poisson rhs / solution
@@ -39,7 +41,7 @@ extern int cup2d_ref_force_iters;
 extern int cup2d_ref_fixed_iters;
 
 namespace {
-enum Mode { ORDER, OPS, STEPS, TIME, AMR } g_mode;
+enum Mode { ORDER, OPS, STEPS, TIME, AMR, VORT } g_mode;
 int g_L, g_N, g_NY, g_bx = 1, g_by = 1, g_nsteps, g_reps, g_kiter;
 double g_nu, g_dt, g_cfl;
 std::string g_in, g_out;
@@ -210,6 +212,15 @@ void do_ops() {
   write_field(var.tmpV, 2);
   fclose(g_fout);
 }
+void do_vort() { // adapt()'s tagging input: KernelVorticity on vel -> tmp (main.cpp:3343-3366, 4659)
+  const size_t n2 = (size_t)g_N * g_NY;
+  read_input(6);
+  scatter(var.vel, 2, g_input.data(), g_input.data() + n2);
+  computeA<VectorLab>(KernelVorticity(), var.vel, 2);
+  g_fout = fopen(g_out.c_str(), "wb");
+  write_field(var.tmp, 1);
+  fclose(g_fout);
+}
 void do_time() {
   seed_taylor_green();
   const size_t n2 = (size_t)g_N * g_NY;
@@ -251,6 +262,7 @@ void cup2d_ref_hook(int op, void *buf, int count) {
   const int call = g_calls++;
   if (g_mode == ORDER) { do_order(); exit(0); }
   if (g_mode == OPS) { do_ops(); exit(0); }
+  if (g_mode == VORT) { do_vort(); exit(0); }
   if (g_mode == TIME) {
     // call 0: seed a Taylor-Green field and let the reference run step 0 (builds the sync plans and the
     // Poisson matrix); call 1: time the operators on the state after that step.
@@ -331,6 +343,7 @@ int main(int argc, char **argv) {
   g_cfl = 0.5;
   if (mode == "order" && argc == 4) { g_mode = ORDER; g_out = argv[3]; }
   else if (mode == "ops" && argc == 7) { g_mode = OPS; g_nu = atof(argv[3]); g_dt = atof(argv[4]); g_in = argv[5]; g_out = argv[6]; }
+  else if (mode == "vort" && argc == 5) { g_mode = VORT; g_in = argv[3]; g_out = argv[4]; }
   else if (mode == "steps" && argc == 9) {
     g_mode = STEPS; g_nu = atof(argv[3]); g_cfl = atof(argv[4]); g_nsteps = atoi(argv[5]);
     g_kiter = atoi(argv[6]); g_in = argv[7]; g_out = argv[8];

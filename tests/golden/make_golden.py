@@ -113,6 +113,17 @@ def gen_ops(tmp, kind, L, seed, nu, dt):
     print("ops", kind, L, float(np.abs(o).max()))
 
 
+def gen_vort(tmp, kind, L, seed):
+    N = 8 << L
+    ins = make_inputs(kind, L, seed)
+    fin, fout = os.path.join(tmp, "in.bin"), os.path.join(tmp, "out.bin")
+    np.concatenate([a.ravel() for a in ins]).tofile(fin)
+    run("vort", L, fin, fout)
+    np.savez_compressed(os.path.join(HERE, f"vort_L{L}_{kind}.npz"), L=L, u=ins[0], v=ins[1],
+                        vort=np.fromfile(fout).reshape(N, N))
+    print("vort", kind, L)
+
+
 def gen_steps(tmp, kind, L, seed, nu, cfl, nsteps, kiter):
     N = 8 << L
     ins = make_inputs(kind, L, seed)
@@ -135,6 +146,8 @@ if __name__ == "__main__":
     with tempfile.TemporaryDirectory() as tmp:
         gen_rect(tmp)
         gen_order(tmp)
+        gen_vort(tmp, "random", 2, 4242)
+        gen_vort(tmp, "tg", 3, 4243)
         gen_ops(tmp, "random", 2, 1234, 1e-3, 2.5e-3)
         gen_ops(tmp, "tg", 3, 4321, 1e-3, 1.2e-3)
         gen_steps(tmp, "tg", 2, 777, 1e-3, 0.5, 3, 12)

@@ -415,3 +415,18 @@ def test_full_step_1024_vs_oracle():
     assert np.abs(gu - ref["u"]).max() < 1e-9 and np.abs(gv - ref["v"]).max() < 1e-9
     assert np.abs(sim.download("pres") - ref["p"]).max() < 1e-8
     sim.close()
+
+
+@pytest.mark.parametrize("name", ["vort_L2_random", "vort_L3_tg"])
+def test_vorticity_tagging_vs_reference_golden(golden_dir, name):
+    """adapt()'s tagging field (KernelVorticity, main.cpp:3343-3366) and its per-block L-inf from device data."""
+    d = np.load(os.path.join(golden_dir, name + ".npz"))
+    L = int(d["L"])
+    sim = cup2d_b200.Simulation(L)
+    sim.upload("vel", d["u"], d["v"])
+    linf = sim.vorticity_tag()
+    assert rel(sim.download("tmp"), d["vort"]) < 1e-14
+    ref = orc.block_linf(d["vort"])
+    want = ref[sim.local_order[:, 1], sim.local_order[:, 0]]
+    assert np.abs(linf - want).max() < 1e-12 * np.abs(want).max()
+    sim.close()
