@@ -23,7 +23,6 @@
 // by (B1 B2 B3)^2: one division per flux instead of four.  Same real-number result; rounding differs
 // from the reference's CPU evaluation at the 1e-16 relative level (tests bound it at 1e-12).
 #include "sim.h"
-#include <cstdlib>
 #include <vector>
 
 namespace cup2d {
@@ -44,8 +43,8 @@ constexpr int OFF_BAR = OFF_SV + TW * SP * 8;
 constexpr int OFF_SLOTS = OFF_BAR + 16;
 constexpr int ADV_SMEM = OFF_SLOTS + TILE_SLOTS * 4; // 51.5 KB -> 4 CTAs/SM
 
-// WENO constants.  With CM (constant memory) they are DFMA constant-bank operands; otherwise the
-// compiler materialises each 64-bit literal with a pair of UMOVs (36 UMOV per cell in the r01c profile).
+// WENO constants live in constant memory so that they are DFMA constant-bank operands; as literals the
+// compiler materialises each with a pair of UMOVs (36 UMOV per cell in profiles/r01c).
 enum { K_G = 0, K_EPS, K_D1, K_D2, K_D3,            // 13/3, 4e-6, den weights .1 .6 .3
        K_PA1, K_PB1, K_PA2, K_PB2, K_PA3, K_PB3,    // plus-flux phi coefficients (gamma folded in)
        K_MA1, K_MB1, K_MA2, K_MB2, K_MA3, K_MB3, K_N };
@@ -53,13 +52,6 @@ __constant__ double cW[K_N];
 static const double hW[K_N] = {13.0 / 3.0, 4e-6, 0.1, 0.6, 0.3,
                                0.1 * 5.0 / 6.0, -0.1 / 3.0, 0.6 / 6.0, 0.6 / 3.0, 0.3 * 2.0 / 3.0, -0.3 / 6.0,
                                -0.3 * 2.0 / 3.0, 0.3 / 6.0, -0.6 / 3.0, -0.6 / 6.0, -0.1 * 5.0 / 6.0, 0.1 / 3.0};
-template <bool CM, int I> __device__ __forceinline__ double KW() {
-  if (CM) return cW[I];
-  constexpr double v[K_N] = {13.0 / 3.0, 4e-6, 0.1, 0.6, 0.3,
-                             0.1 * 5.0 / 6.0, -0.1 / 3.0, 0.6 / 6.0, 0.6 / 3.0, 0.3 * 2.0 / 3.0, -0.3 / 6.0,
-                             -0.3 * 2.0 / 3.0, 0.3 / 6.0, -0.6 / 3.0, -0.6 / 6.0, -0.1 * 5.0 / 6.0, 0.1 / 3.0};
-  return v[I];
-}
 
 constexpr int ADV_LUT_N = TW * TW - 4 * GH * GH; // 1408 cells of the cross-shaped footprint = 11 * 128
 static_assert(ADV_LUT_N % NT_ADV == 0, "table must divide evenly among the threads");
@@ -80,18 +72,18 @@ struct LineState {
   double rP1, rP2, rM1;     // ratioP(w-1), ratioP(w-2), ratioM(w-1)
 };
 
-template <bool CM> __device__ __forceinline__ double Gfun(double D2) {
-  return fma(KW<CM, K_G>() * D2, D2, KW<CM, K_EPS>());
+__device__ __forceinline__ double Gfun(double D2) {
+  return fma(cW[K_G] * D2, D2, cW[K_EPS]);
 }
-template <bool CM> __device__ __forceinline__ void line_init(LineState &s, const double *q, int es) {
+__device__ __forceinline__ void line_init(LineState &s, const double *q, int es) {
   double q0 = q[0], q1 = q[es], q2 = q[2 * es], q3 = q[3 * es], q4 = q[4 * es];
   s.dm2 = q1 - q0; // w = 2: D[0]
   s.dm1 = q2 - q1; // D[1]
   s.d0 = q3 - q2;  // D[2]
   s.dp1 = q4 - q3; // D[3]
-  s.Gm1 = Gfun<CM>(s.dm1 - s.dm2);
-  s.G0 = Gfun<CM>(s.d0 - s.dm1);
-  s.Gp1 = Gfun<CM>(s.dp1 - s.d0);
+  s.Gm1 = Gfun(s.dm1 - s.dm2);
+  s.G0 = Gfun(s.d0 - s.dm1);
+  s.Gp1 = Gfun(s.dp1 - s.d0);
   s.qlast = q4;
   s.rP1 = s.rP2 = s.rM1 = 0.0;
 }
@@ -107,37 +99,37 @@ __device__ __forceinline__ void line_betas(const LineState &s, double &s1, doubl
   s2 = q2 * q2;
   s3 = q3 * q3;
 }
-template <int NEWTON> __device__ __forceinline__ double rcp_pos(double x) {
+// 1/x for x > 0, normal: MUFU.RCP64H seed (~2^-20) + two Newton steps = full double accuracy.  (One step
+// leaves 1.3e-13 relative error for 3 % of the kernel time, profiles/r01h; not worth it.)
+__device__ __forceinline__ double rcp_pos(double x) {
   double r;
-  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x)); // MUFU.RCP64H seed
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
 #pragma unroll
-  for (int i = 0; i < NEWTON; i++) {
+  for (int i = 0; i < 2; i++) {
     const double e = fma(-x, r, 1.0);
     r = fma(r, e, r);
   }
   return r;
 }
 // upwind-from-the-left flux ratio at face w+1/2 (weno5_plus, main.cpp:162-181; gammas .1,.6,.3)
-template <bool CM, int NEWTON>
 __device__ __forceinline__ double ratio_plus(const LineState &s, double s1, double s2, double s3) {
-  const double den = fma(KW<CM, K_D1>(), s1, fma(KW<CM, K_D3>(), s3, KW<CM, K_D2>() * s2));
-  const double p1 = fma(KW<CM, K_PA1>(), s.dm1, KW<CM, K_PB1>() * s.dm2);
-  const double p2 = fma(KW<CM, K_PA2>(), s.dm1, KW<CM, K_PB2>() * s.d0);
-  const double p3 = fma(KW<CM, K_PA3>(), s.d0, KW<CM, K_PB3>() * s.dp1);
+  const double den = fma(cW[K_D1], s1, fma(cW[K_D3], s3, cW[K_D2] * s2));
+  const double p1 = fma(cW[K_PA1], s.dm1, cW[K_PB1] * s.dm2);
+  const double p2 = fma(cW[K_PA2], s.dm1, cW[K_PB2] * s.d0);
+  const double p3 = fma(cW[K_PA3], s.d0, cW[K_PB3] * s.dp1);
   const double num = fma(s1, p1, fma(s3, p3, s2 * p2));
-  return num * rcp_pos<NEWTON>(den);
+  return num * rcp_pos(den);
 }
 // upwind-from-the-right flux ratio at face w-1/2 (weno5_minus, main.cpp:182-201; gammas .3,.6,.1)
-template <bool CM, int NEWTON>
 __device__ __forceinline__ double ratio_minus(const LineState &s, double s1, double s2, double s3) {
-  const double den = fma(KW<CM, K_D3>(), s1, fma(KW<CM, K_D1>(), s3, KW<CM, K_D2>() * s2));
-  const double p1 = fma(KW<CM, K_MA1>(), s.dm1, KW<CM, K_MB1>() * s.dm2);
-  const double p2 = fma(KW<CM, K_MA2>(), s.dm1, KW<CM, K_MB2>() * s.d0);
-  const double p3 = fma(KW<CM, K_MA3>(), s.d0, KW<CM, K_MB3>() * s.dp1);
+  const double den = fma(cW[K_D3], s1, fma(cW[K_D1], s3, cW[K_D2] * s2));
+  const double p1 = fma(cW[K_MA1], s.dm1, cW[K_MB1] * s.dm2);
+  const double p2 = fma(cW[K_MA2], s.dm1, cW[K_MB2] * s.d0);
+  const double p3 = fma(cW[K_MA3], s.d0, cW[K_MB3] * s.dp1);
   const double num = fma(s1, p1, fma(s3, p3, s2 * p2));
-  return num * rcp_pos<NEWTON>(den);
+  return num * rcp_pos(den);
 }
-template <bool CM> __device__ __forceinline__ void line_advance(LineState &s, double qn, double rP, double rM) {
+__device__ __forceinline__ void line_advance(LineState &s, double qn, double rP, double rM) {
   s.rP2 = s.rP1;
   s.rP1 = rP;
   s.rM1 = rM;
@@ -148,26 +140,26 @@ template <bool CM> __device__ __forceinline__ void line_advance(LineState &s, do
   s.qlast = qn;
   s.Gm1 = s.G0;
   s.G0 = s.Gp1;
-  s.Gp1 = Gfun<CM>(s.dp1 - s.d0);
+  s.Gp1 = Gfun(s.dp1 - s.d0);
 }
 
 // Upwind WENO5 differences of both components along one line of 8 cells (window of 14 values per
 // component, element stride es).  qa = advecting component (sign + multiplier), qb = the other one.
 // emit(c, Ua, Ub, da, db, D2a, D2b) is called once per cell c = 0..7 with the cell values, the undivided
 // differences (reference `derivative`, main.cpp:202-208) and the second differences (diffusion term).
-template <int UNR, int NEWTON, bool CM, class Emit>
+template <class Emit>
 __device__ __forceinline__ void weno_line(const double *__restrict__ qa, const double *__restrict__ qb,
                                           const int es, Emit emit) {
   LineState A, B;
-  line_init<CM>(A, qa, es);
-  line_init<CM>(B, qb, es);
+  line_init(A, qa, es);
+  line_init(B, qb, es);
   // sign of the advecting velocity at window indices 2..12 (bit k <-> index k), one pass, no FP64 pipe
   unsigned pos = 0;
 #pragma unroll
   for (int k = 2; k <= 12; k++) pos |= is_pos(qa[k * es]) ? (1u << k) : 0u;
   double Ubm1 = qb[2 * es]; // qb at window index w-1 (cell value of the other component)
   double Uam1 = qa[2 * es];
-#pragma unroll UNR
+#pragma unroll
   for (int w = 2; w <= 11; ++w) {
     const bool vc = (unsigned)(w - 3) < 8u, vn = (unsigned)(w - 2) < 8u, vp = (unsigned)(w - 4) < 8u;
     const unsigned pw = pos >> (w - 1); // bit 0: cell w-1, bit 1: cell w, bit 2: cell w+1
@@ -180,12 +172,12 @@ __device__ __forceinline__ void weno_line(const double *__restrict__ qa, const d
     line_betas(B, b1, b2, b3);
     double rPa = 0, rPb = 0, rMa = 0, rMb = 0;
     if (needP) {
-      rPa = ratio_plus<CM, NEWTON>(A, a1, a2, a3);
-      rPb = ratio_plus<CM, NEWTON>(B, b1, b2, b3);
+      rPa = ratio_plus(A, a1, a2, a3);
+      rPb = ratio_plus(B, b1, b2, b3);
     }
     if (needM) {
-      rMa = ratio_minus<CM, NEWTON>(A, a1, a2, a3);
-      rMb = ratio_minus<CM, NEWTON>(B, b1, b2, b3);
+      rMa = ratio_minus(A, a1, a2, a3);
+      rMb = ratio_minus(B, b1, b2, b3);
     }
     if (vp) { // finalize cell c = w-4 (window index w-1)
       double da, db;
@@ -202,21 +194,21 @@ __device__ __forceinline__ void weno_line(const double *__restrict__ qa, const d
       Uam1 = qa[w * es];
       Ubm1 = qb[w * es];
       const double qna = qa[(w + 3) * es], qnb = qb[(w + 3) * es];
-      line_advance<CM>(A, qna, rPa, rMa);
-      line_advance<CM>(B, qnb, rPb, rMb);
+      line_advance(A, qna, rPa, rMa);
+      line_advance(B, qnb, rPb, rMb);
     }
   }
 }
 
 // MODE 0: out = tot (raw K, undivided)   1: old == in (stage 1)   2: old is a separate field (stage 2)
-// ONE: both passes run through ONE copy of the unrolled line code (a 2-trip loop with run-time strides)
-//      instead of two specialised copies: halves the instruction footprint (I-cache).
-template <int MODE, int UNR, int NEWTON, bool CM, bool ONE>
+// Both passes run through ONE copy of the fully unrolled line code (a 2-trip loop with run-time strides)
+// instead of two specialised copies: halves the instruction footprint (I-cache), profiles/r01g.
+template <int MODE>
 __global__ void __launch_bounds__(NT_ADV, 4)
 advect_stage_kernel(const double *__restrict__ in, const double *__restrict__ old,
                     double *__restrict__ out, const int *__restrict__ tiles,
                     const int *__restrict__ tile_org, const unsigned *__restrict__ lut, int nbx, int nby,
-                    int nloc, int prefetch_dist, double afac, double dfac, double ofac) {
+                    int nloc, double afac, double dfac, double ofac) {
   extern __shared__ __align__(128) unsigned char smem[];
   double2 *stg = reinterpret_cast<double2 *>(smem);
   double *su = reinterpret_cast<double *>(smem + OFF_SU);
@@ -250,16 +242,7 @@ advect_stage_kernel(const double *__restrict__ in, const double *__restrict__ ol
       unsigned char *dst = smem + (lane < 24 ? lane * 1024 : 24 * 1024 + (lane - 24) * 384);
       tma_load_1d(dst, src, bytes, bar);
     }
-    // warm L2 for the tile that the CTA scheduled one resident wave later will ask for
-    const int nt = tile + prefetch_dist;
-    if (nt < (int)gridDim.x) {
-      const int ns = tiles[nt * TILE_SLOTS + lane];
-      if (ns >= 0) {
-        const unsigned char *nsrc = reinterpret_cast<const unsigned char *>(in + (size_t)ns * 128);
-        if (lane >= 24 && lane < 28) nsrc += 5 * 128;
-        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(nsrc), "r"(lane < 24 ? 1024u : 384u) : "memory");
-      }
-    }
+    // (an L2 prefetch of the next wave's tile here costs 7 %: profiles/r01h_ab_test.jsonl)
   }
   // y-pass ownership (known now, so the `old` loads of stage 2 can be in flight during everything else)
   const int yx = lane, ys = warp;
@@ -337,200 +320,28 @@ advect_stage_kernel(const double *__restrict__ in, const double *__restrict__ ol
       outp[c * 8] = o;
     }
   };
-  if (ONE) {
 #pragma unroll 1
-    for (int pass = 0; pass < 2; pass++) {
-      const double *qa = pass == 0 ? su + (lane + GH) * SP + 8 * warp : sv + (8 * ys) * SP + (yx + GH);
-      const double *qb = pass == 0 ? sv + (lane + GH) * SP + 8 * warp : su + (8 * ys) * SP + (yx + GH);
-      const int es = pass == 0 ? 1 : SP;
-      weno_line<UNR, NEWTON, CM>(qa, qb, es, [&](int c, double Ua, double Ub, double da, double db, double D2a, double D2b) {
-        if (pass == 0) emit_x(c, Ua, Ub, da, db, D2a, D2b);
-        else emit_y(c, Ua, Ub, da, db, D2a, D2b);
-      });
-      __syncthreads();
-    }
-  } else {
-    weno_line<UNR, NEWTON, CM>(su + (lane + GH) * SP + 8 * warp, sv + (lane + GH) * SP + 8 * warp, 1, emit_x);
+  for (int pass = 0; pass < 2; pass++) {
+    const double *qa = pass == 0 ? su + (lane + GH) * SP + 8 * warp : sv + (8 * ys) * SP + (yx + GH);
+    const double *qb = pass == 0 ? sv + (lane + GH) * SP + 8 * warp : su + (8 * ys) * SP + (yx + GH);
+    const int es = pass == 0 ? 1 : SP;
+    weno_line(qa, qb, es, [&](int c, double Ua, double Ub, double da, double db, double D2a, double D2b) {
+      if (pass == 0) emit_x(c, Ua, Ub, da, db, D2a, D2b);
+      else emit_y(c, Ua, Ub, da, db, D2a, D2b);
+    });
     __syncthreads();
-    weno_line<UNR, NEWTON, CM>(sv + (8 * ys) * SP + (yx + GH), su + (8 * ys) * SP + (yx + GH), SP, emit_y);
-  }
-}
-
-// ---------------------------------------------------------------------------------------------------
-// Component-split variant: 256 threads per tile, warps 0-3 carry the u-lines, warps 4-7 the v-lines.
-// Same arithmetic; each thread runs ONE dependency chain with half the registers, so 8 CTAs x ... no:
-// 4 CTAs x 8 warps = 32 warps/SM instead of 16: the kernel is bound by dependent-issue latency of the
-// FP64 chains (stall_wait 30 %, FP64 pipe 57 % in profiles/r01f_advect_ncu.md), which more resident warps hide.
-// ---------------------------------------------------------------------------------------------------
-constexpr int NT_ADV2 = 256;
-
-// one component q along one line, sign/multiplier from the advecting plane U (same window indexing)
-template <int NEWTON, bool CM, class Emit>
-__device__ __forceinline__ void weno_line1(const double *__restrict__ q, const double *__restrict__ U,
-                                           const int es, Emit emit) {
-  LineState A;
-  line_init<CM>(A, q, es);
-  unsigned pos = 0;
-#pragma unroll
-  for (int k = 2; k <= 12; k++) pos |= is_pos(U[k * es]) ? (1u << k) : 0u;
-#pragma unroll
-  for (int w = 2; w <= 11; ++w) {
-    const bool vc = (unsigned)(w - 3) < 8u, vn = (unsigned)(w - 2) < 8u, vp = (unsigned)(w - 4) < 8u;
-    const unsigned pw = pos >> (w - 1);
-    const bool posp = pw & 1u;
-    const bool needP = (pw & ((vc ? 2u : 0u) | (vn ? 4u : 0u))) != 0u;
-    const bool needM = (~pw & ((vc ? 2u : 0u) | (vp ? 1u : 0u))) != 0u;
-    double a1, a2, a3;
-    line_betas(A, a1, a2, a3);
-    double rP = 0, rM = 0;
-    if (needP) rP = ratio_plus<CM, NEWTON>(A, a1, a2, a3);
-    if (needM) rM = ratio_minus<CM, NEWTON>(A, a1, a2, a3);
-    if (vp) {
-      const double dq = posp ? A.dm2 + (A.rP1 - A.rP2) : A.dm1 + (rM - A.rM1);
-      emit(w - 4, U[(w - 1) * es], q[(w - 1) * es], dq, A.dm1 - A.dm2);
-    }
-    if (w < 11) line_advance<CM>(A, q[(w + 3) * es], rP, rM);
-  }
-}
-
-template <int MODE, bool CM>
-__global__ void __launch_bounds__(NT_ADV2, 4)
-advect_stage_kernel2(const double *__restrict__ in, const double *__restrict__ old,
-                     double *__restrict__ out, const int *__restrict__ tiles,
-                     const int *__restrict__ tile_org, const unsigned *__restrict__ lut, int nbx, int nby,
-                     int nloc, int prefetch_dist, double afac, double dfac, double ofac) {
-  extern __shared__ __align__(128) unsigned char smem[];
-  double2 *stg = reinterpret_cast<double2 *>(smem);
-  double *su = reinterpret_cast<double *>(smem + OFF_SU);
-  double *sv = reinterpret_cast<double *>(smem + OFF_SV);
-  double *Ru = reinterpret_cast<double *>(smem + OFF_RU);
-  double *Rv = reinterpret_cast<double *>(smem + OFF_RV);
-  uint64_t *bar = reinterpret_cast<uint64_t *>(smem + OFF_BAR);
-  int *s_slots = reinterpret_cast<int *>(smem + OFF_SLOTS);
-
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int comp = warp >> 2, sub = warp & 3; // component carried by this thread, segment index
-  const int tile = blockIdx.x;
-  if (tid < TILE_SLOTS) s_slots[tid] = tiles[tile * TILE_SLOTS + tid];
-  if (tid == 0) {
-    mbar_init(bar, 1);
-    fence_mbar_init();
-  }
-  __syncthreads();
-  if (warp == 0) {
-    const int slot = s_slots[lane];
-    const uint32_t bytes = slot >= 0 ? (lane < 24 ? 1024u : 384u) : 0u;
-    uint32_t tot = bytes;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
-    if (lane == 0) mbar_arrive_expect_tx(bar, tot);
-    __syncwarp();
-    if (slot >= 0) {
-      const unsigned char *src = reinterpret_cast<const unsigned char *>(in + (size_t)slot * 128);
-      if (lane >= 24 && lane < 28) src += 5 * 128;
-      unsigned char *dst = smem + (lane < 24 ? lane * 1024 : 24 * 1024 + (lane - 24) * 384);
-      tma_load_1d(dst, src, bytes, bar);
-    }
-  }
-  // y-pass ownership: column yx of block row `sub`, component `comp`
-  const int yx = lane, ys = sub;
-  const int yb = ys * 4 + (yx >> 3);
-  const int yslot = s_slots[yb];
-  const bool store = yslot >= 0 && yslot < nloc;
-  double oldv[8];
-  if (MODE == 2) {
-    const double *oldp = old + ((size_t)(store ? yslot : 0) * 64 + (yx & 7)) * 2 + comp;
-#pragma unroll
-    for (int c = 0; c < 8; c++) oldv[c] = store ? oldp[c * 16] : 0.0;
-  }
-  const int gx0 = tile_org[2 * tile] * CUP2D_BS, gy0 = tile_org[2 * tile + 1] * CUP2D_BS;
-  const int NX = nbx * CUP2D_BS, NY = nby * CUP2D_BS;
-  if (warp == 0) mbar_wait(bar, 0);
-  __syncthreads();
-  const bool edge = gx0 < GH || gy0 < GH || gx0 + TC + GH > NX || gy0 + TC + GH > NY;
-  if (!edge) {
-#pragma unroll
-    for (int k = 0; k < (ADV_LUT_N + NT_ADV2 - 1) / NT_ADV2; k++) {
-      const int i = k * NT_ADV2 + tid;
-      if (i < ADV_LUT_N) {
-        const unsigned e = __ldg(lut + i);
-        const double2 v = stg[e & 0xffffu];
-        su[e >> 16] = v.x;
-        sv[e >> 16] = v.y;
-      }
-    }
-  } else {
-    for (int idx = tid; idx < TW * TW; idx += NT_ADV2) {
-      const int ty = idx / TW, tx = idx - ty * TW;
-      const int lx = tx - GH, ly = ty - GH;
-      const bool xin = (unsigned)lx < (unsigned)TC, yin = (unsigned)ly < (unsigned)TC;
-      if (!xin && !yin) continue;
-      int gx = gx0 + lx, gy = gy0 + ly;
-      double sgu = 1.0, sgv = 1.0;
-      if (gx < 0) { gx = 0; sgu = -1.0; } else if (gx >= NX) { gx = NX - 1; sgu = -1.0; }
-      if (gy < 0) { gy = 0; sgv = -1.0; } else if (gy >= NY) { gy = NY - 1; sgv = -1.0; }
-      const double2 v = stg[adv_src_slot(gx - gx0, gy - gy0)];
-      su[ty * SP + tx] = sgu * v.x;
-      sv[ty * SP + tx] = sgv * v.y;
-    }
-  }
-  __syncthreads();
-  double *sq = comp == 0 ? su : sv; // the plane of this thread's component
-  double *R = comp == 0 ? Ru : Rv;
-  // x pass: lane = row, advecting plane su
-  {
-    const int off = (lane + GH) * SP + 8 * sub;
-    double *r = R + lane * RP + 8 * sub;
-    weno_line1<2, CM>(sq + off, su + off, 1, [&](int c, double U, double, double dq, double D2q) {
-      r[c] = fma(afac * U, dq, dfac * D2q);
-    });
-  }
-  __syncthreads();
-  // y pass: lane = column, advecting plane sv; final combine and store of this component
-  {
-    const int off = (8 * ys) * SP + (yx + GH);
-    const double *r = R + (8 * ys) * RP + yx;
-    double *outp = out + ((size_t)(store ? yslot : 0) * 64 + (yx & 7)) * 2 + comp;
-    weno_line1<2, CM>(sq + off, sv + off, SP, [&](int c, double V, double qc, double dq, double D2q) {
-      const double t = r[c * RP] + fma(afac * V, dq, dfac * D2q);
-      if (store) {
-        double o;
-        if (MODE == 0) o = t;
-        else if (MODE == 1) o = fma(ofac, t, qc);
-        else o = fma(ofac, t, oldv[c]);
-        outp[c * 16] = o;
-      }
-    });
   }
 }
 
 typedef void (*adv_fn)(const double *, const double *, double *, const int *, const int *, const unsigned *, int,
-                       int, int, int, double, double, double);
-template <int UNR, bool CM, bool ONE> static adv_fn pick_mode(int mode) {
-  switch (mode) {
-  case 0: return advect_stage_kernel<0, UNR, 2, CM, ONE>;
-  case 1: return advect_stage_kernel<1, UNR, 2, CM, ONE>;
-  default: return advect_stage_kernel<2, UNR, 2, CM, ONE>;
-  }
-}
-template <int UNR> static adv_fn pick_flags(int mode, bool cm, bool one) {
-  if (cm) return one ? pick_mode<UNR, true, true>(mode) : pick_mode<UNR, true, false>(mode);
-  return one ? pick_mode<UNR, false, true>(mode) : pick_mode<UNR, false, false>(mode);
-}
+                       int, int, double, double, double);
 
 int launch_advect(cup2d_sim *s, const double *in, const double *old, double *out, double coef,
                   double dt, bool raw) {
-  // tuning knobs (profiles/ records the sweeps): loop unroll factor, constants from constant memory,
-  // one shared code copy for both passes; the defaults are the measured best
-  static int unr = -1, cm = 1, one = 1;
-  if (unr < 0) {
-    const char *e = getenv("CUP2D_ADV_UNROLL");
-    unr = e ? atoi(e) : 10;
-    e = getenv("CUP2D_ADV_CONSTMEM");
-    cm = e ? atoi(e) : 1;
-    e = getenv("CUP2D_ADV_ONECOPY");
-    one = e ? atoi(e) : 1;
+  static bool constants_up = false;
+  if (!constants_up) {
     CUP2D_CUDA(cudaMemcpyToSymbol(cW, hW, sizeof hW));
+    constants_up = true;
   }
   if (!s->d_adv_lut) { // repack table of interior tiles: (destination in the planes) << 16 | source slot
     std::vector<unsigned> lut;
@@ -544,8 +355,7 @@ int launch_advect(cup2d_sim *s, const double *in, const double *old, double *out
     CUP2D_CUDA(cudaMemcpy(s->d_adv_lut, lut.data(), lut.size() * sizeof(unsigned), cudaMemcpyHostToDevice));
   }
   const int mode = raw ? 0 : (old == in ? 1 : 2);
-  static const int split = getenv("CUP2D_ADV_SPLIT") ? atoi(getenv("CUP2D_ADV_SPLIT")) : 0;
-  adv_fn fn = split ? (mode == 0 ? advect_stage_kernel2<0, true> : mode == 1 ? advect_stage_kernel2<1, true> : advect_stage_kernel2<2, true>) : unr == 5 ? pick_flags<5>(mode, cm, one) : pick_flags<10>(mode, cm, one);
+  const adv_fn fn = mode == 0 ? advect_stage_kernel<0> : mode == 1 ? advect_stage_kernel<1> : advect_stage_kernel<2>;
   static bool configured[3] = {false, false, false};
   if (!configured[mode]) {
     CUP2D_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, ADV_SMEM));
@@ -554,12 +364,9 @@ int launch_advect(cup2d_sim *s, const double *in, const double *old, double *out
   const double afac = -dt * s->h; // main.cpp:5447
   const double dfac = s->nu * dt; // main.cpp:5446
   const double ofac = coef / (s->h * s->h);
-  dim3 grid(s->ntiles), block(split ? NT_ADV2 : NT_ADV);
   ProfScope prof(s, KC_ADVECT);
-  static const int pf = getenv("CUP2D_ADV_PREFETCH") ? atoi(getenv("CUP2D_ADV_PREFETCH")) : 0; // measured: prefetching costs 7 % (profiles/r01h_ab_test.jsonl)
-  const int prefetch_dist = pf ? s->num_sms * 4 : (1 << 30); // one resident wave ahead (4 CTAs per SM)
-  fn<<<grid, block, ADV_SMEM, s->stream>>>(in, old, out, s->d_tiles, s->d_tile_org, s->d_adv_lut, s->nbx,
-                                           s->nby, (int)s->nloc, prefetch_dist, afac, dfac, ofac);
+  fn<<<s->ntiles, NT_ADV, ADV_SMEM, s->stream>>>(in, old, out, s->d_tiles, s->d_tile_org, s->d_adv_lut, s->nbx,
+                                                 s->nby, (int)s->nloc, afac, dfac, ofac);
   s->launches++;
   CUP2D_CUDA(cudaGetLastError());
   return CUP2D_OK;

@@ -443,7 +443,7 @@ void cup2d_destroy(cup2d_sim *s) {
   cudaFree(s->kr); cudaFree(s->krhat); cudaFree(s->kp); cudaFree(s->knu); cudaFree(s->kt); cudaFree(s->kz);
   cudaFree(s->d_nbr); cudaFree(s->d_tiles); cudaFree(s->d_tile_org); cudaFree(s->d_halo_src); cudaFree(s->d_adv_lut); cudaFree(s->d_linf);
   cudaFree(s->d_state); cudaFree(s->d_partials); cudaFree(s->d_counter); cudaFree(s->d_scal);
-  cudaFree(s->d_mailbox); cudaFree(s->d_peer_ptrs);
+  cudaFree(s->d_mailbox);
   cudaFree(s->d_irr_blk); cudaFree(s->d_irr_tab); cudaFree(s->d_irr_rowptr); cudaFree(s->d_irr_col); cudaFree(s->d_irr_val);
   if (s->h_state) cudaFreeHost(s->h_state);
   if (s->h_scal) cudaFreeHost(s->h_scal);
@@ -457,7 +457,7 @@ int64_t cup2d_launch_count(const cup2d_sim *s) { return s ? s->launches : 0; }
 
 static const char *kclass_name[KC_COUNT] = {"advect_stage_kernel", "umax_kernel", "pressure_rhs_kernel",
     "pressure_correct_kernel", "k_init", "k_pupdate", "k_spmv<0>", "k_xr_update", "k_spmv<1>", "k_final",
-    "halo_pull_kernel", "memset(udef)"};
+    "halo_pull_kernel", "vorticity_tag_kernel"};
 int cup2d_profile_enable(cup2d_sim *s, int on) {
   if (!s) return CUP2D_EINVAL;
   for (auto &r : s->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }

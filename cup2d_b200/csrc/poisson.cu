@@ -207,7 +207,7 @@ k_pupdate(const double *__restrict__ r, double *__restrict__ rhat, double *__res
 // ---- K2 / K4: y = A z with one or two dots against `d` and y -------------------------------------
 //   MODE 0 (K2): nu = A z ; rhat.nu             -> alpha = rho/(rhat.nu + eps)   (cuda.cu:487-496)
 //   MODE 1 (K4): t  = A z ; t.r, t.t            -> omega = t.r/(t.t + eps)       (cuda.cu:506-518)
-template <int MODE, bool IRR, bool HOIST>
+template <int MODE, bool IRR>
 __global__ void __launch_bounds__(NT, 3)
 k_spmv(const double *__restrict__ z, const double *__restrict__ d, double *__restrict__ yout,
        const int4 *__restrict__ nbr, int nrows, KrylovState *st, double *partials,
@@ -217,7 +217,9 @@ k_spmv(const double *__restrict__ z, const double *__restrict__ d, double *__res
   double sums[2] = {0, 0};
   CHUNK_LOOP() {
     const int nv = min(32, nrows - row0);
-    // HOIST: both global loads are issued before any shared-memory work (memory-level parallelism)
+    // uniform grids: both global loads are issued before any shared-memory work (memory-level parallelism,
+    // -4 % per iteration in profiles/r01h); with general rows the extra live registers cost more than that
+    constexpr bool HOIST = !IRR;
     double2 cz[4], ca[4], cd[4];
     chunk_ld(z, row0, nv, lane, cz);
     if (HOIST) chunk_ld(d, row0, nv, lane, cd);
@@ -359,7 +361,6 @@ int poisson_solve(cup2d_sim *s, double tol_abs, double tol_rel, int max_restarts
   const int nrows = (int)s->nloc * 8;
   const int grid = red_grid(s, nrows);
   const int4 *nbr = reinterpret_cast<const int4 *>(s->d_nbr);
-  static const bool hoist = getenv("CUP2D_SPMV_HOIST") ? atoi(getenv("CUP2D_SPMV_HOIST")) != 0 : true;
   const bool has_irr = s->n_irr_rows > 0; // general rows present: kernels with the CSR override compiled in
   KrylovState *h = s->h_state;
   *h = KrylovState{};
@@ -396,10 +397,10 @@ int poisson_solve(cup2d_sim *s, double tol_abs, double tol_rel, int max_restarts
       {
         ProfScope prof(s, KC_SPMV_NU);
         if (has_irr)
-          k_spmv<0, true, false><<<grid, NT, 0, s->stream>>>(s->kz, s->krhat, s->knu, nbr, nrows, s->d_state,
+          k_spmv<0, true><<<grid, NT, 0, s->stream>>>(s->kz, s->krhat, s->knu, nbr, nrows, s->d_state,
                                                       s->d_partials, s->d_counter, s->comm, irr_view(s));
         else
-          (hoist ? k_spmv<0, false, true> : k_spmv<0, false, false>)<<<grid, NT, 0, s->stream>>>(
+          k_spmv<0, false><<<grid, NT, 0, s->stream>>>(
               s->kz, s->krhat, s->knu, nbr, nrows, s->d_state, s->d_partials, s->d_counter, s->comm, irr_view(s));
       }
       {
@@ -411,10 +412,10 @@ int poisson_solve(cup2d_sim *s, double tol_abs, double tol_rel, int max_restarts
       {
         ProfScope prof(s, KC_SPMV_T);
         if (has_irr)
-          k_spmv<1, true, false><<<grid, NT, 0, s->stream>>>(s->kz, s->kr, s->kt, nbr, nrows, s->d_state,
+          k_spmv<1, true><<<grid, NT, 0, s->stream>>>(s->kz, s->kr, s->kt, nbr, nrows, s->d_state,
                                                       s->d_partials, s->d_counter, s->comm, irr_view(s));
         else
-          (hoist ? k_spmv<1, false, true> : k_spmv<1, false, false>)<<<grid, NT, 0, s->stream>>>(
+          k_spmv<1, false><<<grid, NT, 0, s->stream>>>(
               s->kz, s->kr, s->kt, nbr, nrows, s->d_state, s->d_partials, s->d_counter, s->comm, irr_view(s));
       }
       {

@@ -172,8 +172,11 @@ int launch_vorticity_tag(cup2d_sim *s, double *linf_host) {
   if (!s->d_linf) CUP2D_CUDA(cudaMalloc(&s->d_linf, (size_t)s->nloc * sizeof(double)));
   const int nrows = (int)s->nloc * 8;
   const int grid = min((nrows + NT - 1) / NT, s->num_sms * 8);
-  vorticity_tag_kernel<<<grid, NT, 0, s->stream>>>(s->f[CUP2D_VEL], s->f[CUP2D_TMP], s->d_linf,
-                                                   reinterpret_cast<const int4 *>(s->d_nbr), nrows, 0.5 / s->h);
+  {
+    ProfScope prof(s, KC_VORT);
+    vorticity_tag_kernel<<<grid, NT, 0, s->stream>>>(s->f[CUP2D_VEL], s->f[CUP2D_TMP], s->d_linf,
+                                                     reinterpret_cast<const int4 *>(s->d_nbr), nrows, 0.5 / s->h);
+  }
   s->launches++;
   CUP2D_CUDA(cudaGetLastError());
   if (linf_host) {

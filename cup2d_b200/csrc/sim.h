@@ -83,7 +83,6 @@ struct cup2d_sim {
   unsigned long long *peer_mailbox[cup2d::MAX_RANKS] = {};
   unsigned long long epoch = 0;
   cup2d::Comm comm = {};               // by-value kernel argument of every reducing kernel
-  double **d_peer_ptrs = nullptr;      // device copy of peer_base
   // general (non-stencil) Poisson rows: CSR side table (cup2d_poisson_create_general)
   int *d_irr_blk = nullptr, *d_irr_tab = nullptr, *d_irr_rowptr = nullptr, *d_irr_col = nullptr;
   double *d_irr_val = nullptr;
@@ -97,7 +96,7 @@ struct cup2d_sim {
 
 namespace cup2d {
 enum KClass { KC_ADVECT = 0, KC_UMAX, KC_RHS, KC_CORRECT, KC_KINIT, KC_PUPDATE, KC_SPMV_NU, KC_XRUPDATE,
-              KC_SPMV_T, KC_FINAL, KC_HALO, KC_MEMSET, KC_COUNT };
+              KC_SPMV_T, KC_FINAL, KC_HALO, KC_VORT, KC_COUNT };
 // bracket one launch with events when profiling is on (no-op otherwise)
 struct ProfScope {
   cup2d_sim *s;
