@@ -441,7 +441,7 @@ void cup2d_destroy(cup2d_sim *s) {
   for (auto p : s->f) cudaFree(p);
   for (auto p : s->kx) cudaFree(p);
   cudaFree(s->kr); cudaFree(s->krhat); cudaFree(s->kp); cudaFree(s->knu); cudaFree(s->kt); cudaFree(s->kz);
-  cudaFree(s->d_nbr); cudaFree(s->d_tiles); cudaFree(s->d_tile_org); cudaFree(s->d_halo_src); cudaFree(s->d_adv_lut); cudaFree(s->d_linf);
+  cudaFree(s->d_nbr); cudaFree(s->d_tiles); cudaFree(s->d_tile_org); cudaFree(s->d_halo_src); cudaFree(s->d_adv_lut); cudaFree(s->d_linf); cudaFree(s->d_chi_mask); cudaFree(s->d_ij);
   cudaFree(s->d_state); cudaFree(s->d_partials); cudaFree(s->d_counter); cudaFree(s->d_scal);
   cudaFree(s->d_mailbox);
   cudaFree(s->d_irr_blk); cudaFree(s->d_irr_tab); cudaFree(s->d_irr_rowptr); cudaFree(s->d_irr_col); cudaFree(s->d_irr_val);
@@ -605,13 +605,23 @@ int cup2d_poisson_solve(cup2d_sim *s, double tol_abs, double tol_rel, int max_re
                              cudaMemcpyDeviceToDevice, s->stream));
   return CUP2D_OK;
 }
-int cup2d_vorticity_tag(cup2d_sim *s, double *block_linf_out) {
+int cup2d_adapt_tags(cup2d_sim *s, double rtol, int chi_cells, double *block_linf_out) {
   CHECK_SIM(s);
-  CUP2D_REQUIRE(!s->poisson_only, "vorticity_tag: Poisson-only context has no velocity field geometry");
+  CUP2D_REQUIRE(!s->poisson_only, "adapt_tags: a Poisson-only context has no velocity field");
+  CUP2D_REQUIRE(chi_cells >= 0 && chi_cells <= CUP2D_BS, "adapt_tags: chi_cells must be 0..8 (the reference uses 2 or 4)");
+  CUP2D_REQUIRE(chi_cells == 0 || s->nranks == 1,
+                "adapt_tags: the chi criterion needs diagonal neighbour blocks, which the multi-rank halo does not hold yet");
   CUP2D_CUDA(cudaSetDevice(s->device));
   int rc = need_peers(s);
   if (rc) return rc;
-  return launch_vorticity_tag(s, block_linf_out);
+  return launch_adapt_tags(s, rtol, chi_cells, block_linf_out);
+}
+int cup2d_vorticity_tag(cup2d_sim *s, double *block_linf_out) { return cup2d_adapt_tags(s, 0.0, 0, block_linf_out); }
+int cup2d_dump(cup2d_sim *s, double time, const char *path) {
+  CHECK_SIM(s);
+  CUP2D_REQUIRE(!s->poisson_only && path && *path, "dump: bad arguments");
+  CUP2D_CUDA(cudaSetDevice(s->device));
+  return dump_fields(s, time, path);
 }
 int cup2d_pressure_correct(cup2d_sim *s, double dt) {
   CHECK_SIM(s);

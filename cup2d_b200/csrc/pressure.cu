@@ -99,93 +99,6 @@ __device__ __forceinline__ void rows_div(const double2 (&cf)[8], const double *_
   }
 }
 
-// ------------------------------------------------------------------------------------------------
-// Regridding input: tmp = KernelVorticity(vel) (main.cpp:3343-3366) and its L-inf
-// per block, the quantity adapt() compares against Rtol/Ctol (main.cpp:4676-4689), so that tagging can
-// run from device-resident data: only nblocks doubles cross PCIe instead of the velocity field.
-//   omega = (0.5/h) * (((u_S - u_N) + v_E) - v_W), free-slip ghosts (tangential component copied).
-// ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(NT)
-vorticity_tag_kernel(const double *__restrict__ vel, double *__restrict__ tmp, double *__restrict__ linf,
-                     const int4 *__restrict__ nbr, int nrows, double i2h) {
-  __shared__ __align__(16) double s_scr[WPB * ROWS_SCRATCH];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  double *sw = s_scr + warp * ROWS_SCRATCH;
-  for (int row0 = (blockIdx.x * WPB + warp) * 32; row0 < nrows; row0 += gridDim.x * WPB * 32) {
-    const int nv = min(32, nrows - row0);
-    const int row = row0 + lane, slot = row >> 3, y = row & 7;
-    const bool act = lane < nv;
-    const int4 nb = act ? nbr[slot] : make_int4(-1, -1, -1, -1);
-    double2 cv[8], c[8];
-    chunk2_ld(vel, row0, nv, lane, cv);
-    chunk2_to_rows(sw, nv, lane, cv, c);
-    double w[8];
-    double m = 0.0;
-    if (act) {
-      const double2 *f2 = reinterpret_cast<const double2 *>(vel);
-      double un[8], us[8];
-      double2 t[8];
-      if (y < 7) { rows_peek2(sw, lane + 1, t);
-#pragma unroll
-        for (int i = 0; i < 8; i++) un[i] = t[i].x; }
-      else if (nb.w >= 0) { grow_load2(vel, nb.w, 0, t);
-#pragma unroll
-        for (int i = 0; i < 8; i++) un[i] = t[i].x; }
-      else {
-#pragma unroll
-        for (int i = 0; i < 8; i++) un[i] = c[i].x; }
-      if (y > 0) { rows_peek2(sw, lane - 1, t);
-#pragma unroll
-        for (int i = 0; i < 8; i++) us[i] = t[i].x; }
-      else if (nb.z >= 0) { grow_load2(vel, nb.z, 7, t);
-#pragma unroll
-        for (int i = 0; i < 8; i++) us[i] = t[i].x; }
-      else {
-#pragma unroll
-        for (int i = 0; i < 8; i++) us[i] = c[i].x; }
-      const double vW = nb.x >= 0 ? f2[(size_t)nb.x * 64 + y * 8 + 7].y : c[0].y;
-      const double vE = nb.y >= 0 ? f2[(size_t)nb.y * 64 + y * 8 + 0].y : c[7].y;
-#pragma unroll
-      for (int i = 0; i < 8; i++) {
-        const double e = i < 7 ? c[i + 1].y : vE, ww = i > 0 ? c[i - 1].y : vW;
-        w[i] = i2h * (((us[i] - un[i]) + e) - ww);
-        m = fmax(m, fabs(w[i]));
-      }
-    } else {
-#pragma unroll
-      for (int i = 0; i < 8; i++) w[i] = 0.0;
-    }
-    // block L-inf: the 8 lanes of a block
-    m = fmax(m, __shfl_xor_sync(0xffffffffu, m, 1));
-    m = fmax(m, __shfl_xor_sync(0xffffffffu, m, 2));
-    m = fmax(m, __shfl_xor_sync(0xffffffffu, m, 4));
-    if (act && y == 0) linf[slot] = m;
-    rows_store1(tmp, row0, nv, sw, lane, w);
-  }
-}
-
-int launch_vorticity_tag(cup2d_sim *s, double *linf_host) {
-  if (s->nranks > 1) {
-    int rc = halo_exchange_ptr(s, s->f[CUP2D_VEL], 2, CUP2D_VEL);
-    if (rc) return rc;
-  }
-  if (!s->d_linf) CUP2D_CUDA(cudaMalloc(&s->d_linf, (size_t)s->nloc * sizeof(double)));
-  const int nrows = (int)s->nloc * 8;
-  const int grid = min((nrows + NT - 1) / NT, s->num_sms * 8);
-  {
-    ProfScope prof(s, KC_VORT);
-    vorticity_tag_kernel<<<grid, NT, 0, s->stream>>>(s->f[CUP2D_VEL], s->f[CUP2D_TMP], s->d_linf,
-                                                     reinterpret_cast<const int4 *>(s->d_nbr), nrows, 0.5 / s->h);
-  }
-  s->launches++;
-  CUP2D_CUDA(cudaGetLastError());
-  if (linf_host) {
-    CUP2D_CUDA(cudaMemcpyAsync(linf_host, s->d_linf, (size_t)s->nloc * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
-    CUP2D_CUDA(cudaStreamSynchronize(s->stream));
-  }
-  return CUP2D_OK;
-}
-
 // tmp = fac*(div vel) - fac*chi*(div udef) - lap(pold);  pres = 0     (main.cpp:7011-7027)
 template <bool HAS_UDEF>
 __global__ void __launch_bounds__(NT)

@@ -62,7 +62,9 @@ struct cup2d_sim {
   int *d_tiles = nullptr;              // [ntiles][TILE_SLOTS]
   int *d_tile_org = nullptr;           // [ntiles][2] tile origin in blocks
   int ntiles = 0;
-  double *d_linf = nullptr;            // per-block L-inf of the tagging field (cup2d_vorticity_tag)
+  double *d_linf = nullptr;            // per-block L-inf of the tagging field (cup2d_adapt_tags)
+  unsigned long long *d_chi_mask = nullptr; // per-block bit mask of chi > 0 (cup2d_adapt_tags)
+  int *d_ij = nullptr;                 // (i,j) of the local blocks (cup2d_dump)
   unsigned *d_adv_lut = nullptr;       // repack table of the advect kernel (interior tiles)
   // fields (dim*64*nslots doubles each)
   double *f[CUP2D_NFIELDS] = {};
@@ -129,7 +131,8 @@ int launch_advect(cup2d_sim *s, const double *in, const double *old, double *out
 int launch_umax(cup2d_sim *s, double *umax_out);
 int launch_pressure_rhs(cup2d_sim *s, double dt, bool has_udef);
 int launch_pressure_correct(cup2d_sim *s, double dt);
-int launch_vorticity_tag(cup2d_sim *s, double *linf_host);
+int launch_adapt_tags(cup2d_sim *s, double rtol, int chi_cells, double *linf_host);
+int dump_fields(cup2d_sim *s, double time, const char *path);
 int poisson_solve(cup2d_sim *s, double tol_abs, double tol_rel, int max_restarts, int max_iter,
                   int *iters, double *err);
 int halo_exchange_ptr(cup2d_sim *s, double *base, int dim, int peer_index, bool done_barrier = true);

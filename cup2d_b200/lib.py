@@ -17,7 +17,7 @@ SYMBOLS = [
     "cup2d_pressure_rhs", "cup2d_poisson_solve", "cup2d_pressure_correct", "cup2d_step",
     "cup2d_peer_blob_size", "cup2d_peer_export", "cup2d_peer_attach", "cup2d_halo_exchange",
     "cup2d_launch_count", "cup2d_profile_enable", "cup2d_profile_read",
-    "cup2d_plan_create", "cup2d_plan_table", "cup2d_poisson_create", "cup2d_poisson_create_general", "cup2d_vorticity_tag",
+    "cup2d_plan_create", "cup2d_plan_table", "cup2d_poisson_create", "cup2d_poisson_create_general", "cup2d_vorticity_tag", "cup2d_adapt_tags", "cup2d_dump",
 ]
 
 
@@ -82,6 +82,8 @@ def load_library():
     lib.cup2d_poisson_create_general.argtypes = [L, C.POINTER(C.c_int32), L, C.POINTER(C.c_int32), C.POINTER(C.c_int32),
                                                  C.POINTER(C.c_int32), C.POINTER(D), C.c_int32, C.POINTER(P)]
     lib.cup2d_vorticity_tag.argtypes = [P, C.POINTER(D)]
+    lib.cup2d_adapt_tags.argtypes = [P, D, C.c_int, C.POINTER(D)]
+    lib.cup2d_dump.argtypes = [P, D, C.c_char_p]
     lib.cup2d_plan_create.argtypes = [C.POINTER(Config), C.POINTER(P)]
     lib.cup2d_plan_table.argtypes = [P, I, C.POINTER(C.c_int32)]
     lib.cup2d_plan_table.restype = L

@@ -5,6 +5,7 @@ with levelMax = level+1, i.e. a uniform grid), extent, nu, CFL.  Fields cross th
 numpy arrays in the reference block layout; `to_blocks/from_blocks` convert from/to global 2-D arrays.
 """
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -146,6 +147,16 @@ class Simulation:
         out = np.empty(self.nloc)
         _l.check(self.lib.cup2d_vorticity_tag(self._h, out.ctypes.data_as(C.POINTER(C.c_double))))
         return out
+
+    def adapt_tags(self, rtol, chi_cells):
+        """adapt()'s criterion (vorticity + body proximity); returns max|tmp| per local block."""
+        out = np.empty(self.nloc)
+        _l.check(self.lib.cup2d_adapt_tags(self._h, float(rtol), int(chi_cells), out.ctypes.data_as(C.POINTER(C.c_double))))
+        return out
+
+    def dump(self, time, path):
+        """the reference's dump(): <path>.xyz.raw, .attr.raw, .xdmf2"""
+        _l.check(self.lib.cup2d_dump(self._h, float(time), os.fsencode(path)))
 
     def pressure_correct(self, dt):
         _l.check(self.lib.cup2d_pressure_correct(self._h, dt))

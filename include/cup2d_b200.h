@@ -106,9 +106,18 @@ int cup2d_poisson_solve(cup2d_sim *s, double tol_abs, double tol_rel, int max_re
 /* pres = pres - mean(pres); pres += pold - mean(pres); tmpV = -0.5 dt h grad(pres) (undivided);
  * vel += tmpV/h^2.  main.cpp:7120-7187 */
 int cup2d_pressure_correct(cup2d_sim *s, double dt);
-/* Regridding input (main.cpp:3343-3366, 4659-4689): tmp = KernelVorticity(vel); block_linf_out[k] = max|tmp| over
- * local block k (host array of cup2d_nblocks_local doubles, may be NULL) — what adapt() compares with Rtol/Ctol. */
+/* Regridding criterion from device-resident fields = the first two lines of adapt() and its per-block loop
+ * (main.cpp:4659-4660, 4676-4680): tmp = KernelVorticity(vel) (main.cpp:3343-3366); if chi_cells > 0, GradChiOnTmp
+ * (main.cpp:4631-4656): blocks with chi > 0 within chi_cells cells (reference: 4 on the finest level, else 2) get
+ * their 4 centre cells set to 2*rtol; block_linf_out[k] = max|tmp| over local block k, `infos` order (host array of
+ * cup2d_nblocks_local doubles, may be NULL).  The caller compares with Rtol / Ctol exactly as main.cpp:4681-4682.
+ * chi_cells > 0 is single-rank for now.  cup2d_vorticity_tag(s, out) == cup2d_adapt_tags(s, 0, 0, out). */
+int cup2d_adapt_tags(cup2d_sim *s, double rtol, int chi_cells, double *block_linf_out);
 int cup2d_vorticity_tag(cup2d_sim *s, double *block_linf_out);
+/* dump() (main.cpp:3367-3467): writes <path>.xyz.raw, <path>.attr.raw (float32, cell quads and (u,v,0) in `infos`
+ * order; every rank writes its own byte range) and, on the last rank, <path>.xdmf2 — byte-identical to the
+ * reference's files (what post.py reads).  The narrowing to float32 happens on the device. */
+int cup2d_dump(cup2d_sim *s, double time, const char *path);
 /* One full time step of the hot path (no bodies): compute_dt (unless dt>0 is given), rk2, tmpV=0
  * (or kept if keep_udef), pressure_rhs, poisson_solve, pressure_correct.  Returns dt used. */
 int cup2d_step(cup2d_sim *s, double dt_in, int keep_udef, double tol_abs, double tol_rel,

@@ -253,6 +253,75 @@ def block_linf(a):
     return np.abs(a).reshape(NY // BS, BS, NX // BS, BS).max(axis=(1, 3))
 
 
+def adapt_tags(u, v, chi, h, rtol, offset):
+    """The field adapt() thresholds (main.cpp:4659-4660): KernelVorticity, then GradChiOnTmp (main.cpp:4631-4656):
+    a block whose surroundings — the block grown by `offset` cells on every side, corners included; offset = 4 on the
+    finest level, else 2 — hold any chi > 0 (after clamping to [0,1]) gets its four centre cells set to 2 Rtol.
+    Neumann ghosts outside the domain replicate wall-adjacent cells that are inside the grown box anyway."""
+    w = vorticity(u, v, h).copy()
+    NY, NX = chi.shape
+    pos = np.minimum(chi, 1.0)
+    pos = np.maximum(pos, 0.0) > 0.0
+    c = BS // 2
+    for j in range(NY // BS):
+        for i in range(NX // BS):
+            y0, y1 = max(0, BS * j - offset), min(NY, BS * (j + 1) + offset)
+            x0, x1 = max(0, BS * i - offset), min(NX, BS * (i + 1) + offset)
+            if pos[y0:y1, x0:x1].any():
+                w[BS * j + c - 1:BS * j + c + 1, BS * i + c - 1:BS * i + c + 1] = 2 * rtol
+    return w
+
+
+def dump_arrays(u, v, order, h0, level):
+    """dump() (main.cpp:3425-3453): per block in `infos` order, per cell row-major: the 4 corners of the cell quad
+    (u0,v0, u0,v1, u1,v1, u1,v0) and the attribute (u, v, 0), all narrowed to float32.  origin as main.cpp:695-696."""
+    order = np.asarray(order)
+    h = h0 / (1 << level)
+    ox = (order[:, 0] * BS) * h0 / (1 << level)
+    oy = (order[:, 1] * BS) * h0 / (1 << level)
+    k = np.arange(BS, dtype=np.float64)
+    u0 = ox[:, None, None] + (h * k)[None, None, :] + np.zeros((1, BS, 1))
+    v0 = oy[:, None, None] + (h * k)[None, :, None] + np.zeros((1, 1, BS))
+    u1, v1 = u0 + h, v0 + h
+    xyz = np.stack([u0, v0, u0, v1, u1, v1, u1, v0], axis=-1).astype(np.float32)
+    vel = to_blocks((u, v), order, 2).reshape(len(order), BS, BS, 2)
+    attr = np.concatenate([vel, np.zeros((len(order), BS, BS, 1))], axis=-1).astype(np.float32)
+    return xyz.reshape(-1), attr.reshape(-1)
+
+
+def dump_xdmf(time, ncell, xyz_base, attr_base):
+    """the .xdmf2 text dump() writes (main.cpp:3390-3423), byte for byte"""
+    return ("<Xdmf\n"
+            "    Version=\"2.0\">\n"
+            "  <Domain>\n"
+            "    <Grid>\n"
+            "      <Time Value=\"%.16e\"/>\n"
+            "      <Topology\n"
+            "          Dimensions=\"%d\"\n"
+            "          TopologyType=\"Quadrilateral\"/>\n"
+            "     <Geometry\n"
+            "         GeometryType=\"XY\">\n"
+            "       <DataItem\n"
+            "           Dimensions=\"%d 2\"\n"
+            "           Format=\"Binary\">\n"
+            "         %s\n"
+            "       </DataItem>\n"
+            "     </Geometry>\n"
+            "       <Attribute\n"
+            "           AttributeType=\"Vector\"\n"
+            "           Name=\"vort\"\n"
+            "           Center=\"Cell\">\n"
+            "         <DataItem\n"
+            "             Dimensions=\"3 %d\"\n"
+            "             Format=\"Binary\">\n"
+            "           %s\n"
+            "         </DataItem>\n"
+            "       </Attribute>\n"
+            "    </Grid>\n"
+            "  </Domain>\n"
+            "</Xdmf>\n") % (time, ncell, 4 * ncell, xyz_base, ncell, attr_base)
+
+
 def grad_p(p, h, dt):
     """pressureCorrectionKernel::operator() (main.cpp:6021-6043)"""
     NY, NX = p.shape

@@ -21,6 +21,12 @@
 //             rhs1 = rhs - lap(p) (pressure_rhs1 with pold = p), gradp = pressureCorrectionKernel(p)
 //   ref_harness vort  L in.bin out.bin
 //        in : as ops;  out: KernelVorticity(vel) written to tmp (N^2 doubles) = adapt()'s tagging field
+//   ref_harness tags  L rtol extra in.bin out.bin
+//        adapt()'s first two lines (main.cpp:4659-4660) with sim.Rtol = rtol and levelMax = L+1+extra
+//        (extra = 0: the grid is at the finest level -> GradChiOnTmp looks 4 cells around a block, else 2);
+//        out: tmp (N^2 doubles) = vorticity with the 4 centre cells of body-adjacent blocks set to 2 Rtol
+//   ref_harness dump  L time in.bin prefix
+//        the reference's own dump() (main.cpp:3367-3467) of vel -> prefix.xyz.raw, prefix.attr.raw, prefix.xdmf2
 //   ref_harness steps L nu cfl nsteps kiter in.bin out.bin
 //        in : as above (udef ignored: no shapes => udef = 0, chi = 0 ; p = initial pres)
 //        out: per step: dt, then u v p  b x   (1 + 5 N^2 doubles), b/x = Poisson rhs / solution
@@ -41,7 +47,9 @@ extern int cup2d_ref_force_iters;
 extern int cup2d_ref_fixed_iters;
 
 namespace {
-enum Mode { ORDER, OPS, STEPS, TIME, AMR, VORT } g_mode;
+enum Mode { ORDER, OPS, STEPS, TIME, AMR, VORT, TAGS, DUMP } g_mode;
+int g_extra = 0;
+double g_rtol = 0, g_time = 0;
 int g_L, g_N, g_NY, g_bx = 1, g_by = 1, g_nsteps, g_reps, g_kiter;
 double g_nu, g_dt, g_cfl;
 std::string g_in, g_out;
@@ -221,6 +229,26 @@ void do_vort() { // adapt()'s tagging input: KernelVorticity on vel -> tmp (main
   write_field(var.tmp, 1);
   fclose(g_fout);
 }
+void do_tags() { // main.cpp:4659-4660: what adapt() thresholds per block
+  const size_t n2 = (size_t)g_N * g_NY;
+  read_input(6);
+  scatter(var.vel, 2, g_input.data(), g_input.data() + n2);
+  scatter(var.chi, 1, g_input.data() + 3 * n2, nullptr);
+  sim.Rtol = g_rtol;
+  computeA<VectorLab>(KernelVorticity(), var.vel, 2);
+  computeA<ScalarLab>(GradChiOnTmp(), var.chi, 1);
+  g_fout = fopen(g_out.c_str(), "wb");
+  write_field(var.tmp, 1);
+  fclose(g_fout);
+}
+void do_dump() {
+  const size_t n2 = (size_t)g_N * g_NY;
+  read_input(6);
+  scatter(var.vel, 2, g_input.data(), g_input.data() + n2);
+  std::vector<char> path(g_out.begin(), g_out.end());
+  path.push_back(0);
+  dump(g_time, var.vel->infos.size(), var.vel->infos.data(), path.data());
+}
 void do_time() {
   seed_taylor_green();
   const size_t n2 = (size_t)g_N * g_NY;
@@ -263,6 +291,8 @@ void cup2d_ref_hook(int op, void *buf, int count) {
   if (g_mode == ORDER) { do_order(); exit(0); }
   if (g_mode == OPS) { do_ops(); exit(0); }
   if (g_mode == VORT) { do_vort(); exit(0); }
+  if (g_mode == TAGS) { do_tags(); exit(0); }
+  if (g_mode == DUMP) { do_dump(); exit(0); }
   if (g_mode == TIME) {
     // call 0: seed a Taylor-Green field and let the reference run step 0 (builds the sync plans and the
     // Poisson matrix); call 1: time the operators on the state after that step.
@@ -344,6 +374,8 @@ int main(int argc, char **argv) {
   if (mode == "order" && argc == 4) { g_mode = ORDER; g_out = argv[3]; }
   else if (mode == "ops" && argc == 7) { g_mode = OPS; g_nu = atof(argv[3]); g_dt = atof(argv[4]); g_in = argv[5]; g_out = argv[6]; }
   else if (mode == "vort" && argc == 5) { g_mode = VORT; g_in = argv[3]; g_out = argv[4]; }
+  else if (mode == "tags" && argc == 7) { g_mode = TAGS; g_rtol = atof(argv[3]); g_extra = atoi(argv[4]); g_in = argv[5]; g_out = argv[6]; }
+  else if (mode == "dump" && argc == 6) { g_mode = DUMP; g_time = atof(argv[3]); g_in = argv[4]; g_out = argv[5]; }
   else if (mode == "steps" && argc == 9) {
     g_mode = STEPS; g_nu = atof(argv[3]); g_cfl = atof(argv[4]); g_nsteps = atoi(argv[5]);
     g_kiter = atoi(argv[6]); g_in = argv[7]; g_out = argv[8];
@@ -366,7 +398,7 @@ int main(int argc, char **argv) {
   else { fprintf(stderr, "ref_harness: bad arguments\n"); return 2; }
   char a_ls[32], a_lm[32], a_nu[64], a_cfl[64];
   snprintf(a_ls, sizeof a_ls, "%d", g_L);
-  snprintf(a_lm, sizeof a_lm, "%d", g_L + 1);
+  snprintf(a_lm, sizeof a_lm, "%d", g_L + 1 + g_extra);
   snprintf(a_nu, sizeof a_nu, "%.17g", g_nu);
   snprintf(a_cfl, sizeof a_cfl, "%.17g", g_cfl);
   char a_bx[16], a_by[16];

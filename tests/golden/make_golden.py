@@ -124,6 +124,41 @@ def gen_vort(tmp, kind, L, seed):
     print("vort", kind, L)
 
 
+def body_chi(N, blobs):
+    """compactly supported chi with values below 0 and above 1 (GradChiOnTmp clamps before testing)"""
+    x = (np.arange(N) + 0.5) / N
+    X, Y = np.meshgrid(x, x)
+    chi = np.full((N, N), -0.25)
+    for (cx, cy, r) in blobs:
+        chi = np.maximum(chi, 1.5 * (1.0 - np.hypot(X - cx, Y - cy) / r))
+    return chi
+
+
+def gen_tags(tmp, name, L, seed, rtol, extra, blobs):
+    N = 8 << L
+    ins = make_inputs("tg", L, seed)
+    ins[3] = body_chi(N, blobs)
+    fin, fout = os.path.join(tmp, "in.bin"), os.path.join(tmp, "out.bin")
+    np.concatenate([a.ravel() for a in ins]).tofile(fin)
+    run("tags", L, repr(rtol), extra, fin, fout)
+    np.savez_compressed(os.path.join(HERE, f"tags_{name}.npz"), L=L, rtol=rtol, offset=4 if extra == 0 else 2,
+                        u=ins[0], v=ins[1], chi=ins[3], tags=np.fromfile(fout).reshape(N, N))
+    print("tags", name)
+
+
+def gen_dump(tmp, L, seed, time):
+    N = 8 << L
+    ins = make_inputs("random", L, seed)
+    fin, pref = os.path.join(tmp, "in.bin"), os.path.join(tmp, "vel.00000007")
+    np.concatenate([a.ravel() for a in ins]).tofile(fin)
+    run("dump", L, repr(time), fin, pref)
+    np.savez_compressed(os.path.join(HERE, f"dump_L{L}.npz"), L=L, time=time, u=ins[0], v=ins[1],
+                        xyz=np.fromfile(pref + ".xyz.raw", dtype=np.float32),
+                        attr=np.fromfile(pref + ".attr.raw", dtype=np.float32),
+                        xdmf=np.frombuffer(open(pref + ".xdmf2", "rb").read(), dtype=np.uint8))
+    print("dump", L)
+
+
 def gen_steps(tmp, kind, L, seed, nu, cfl, nsteps, kiter):
     N = 8 << L
     ins = make_inputs(kind, L, seed)
@@ -148,6 +183,9 @@ if __name__ == "__main__":
         gen_order(tmp)
         gen_vort(tmp, "random", 2, 4242)
         gen_vort(tmp, "tg", 3, 4243)
+        gen_tags(tmp, "L3_finest", 3, 4244, 5.0, 0, [(0.4, 0.55, 0.12), (0.02, 0.97, 0.05)])
+        gen_tags(tmp, "L3_coarser", 3, 4245, 3.0, 1, [(0.7, 0.3, 0.1), (0.99, 0.01, 0.04), (0.26, 0.76, 0.015)])
+        gen_dump(tmp, 2, 4246, 0.1875)
         gen_ops(tmp, "random", 2, 1234, 1e-3, 2.5e-3)
         gen_ops(tmp, "tg", 3, 4321, 1e-3, 1.2e-3)
         gen_steps(tmp, "tg", 2, 777, 1e-3, 0.5, 3, 12)

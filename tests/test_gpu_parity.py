@@ -430,3 +430,56 @@ def test_vorticity_tagging_vs_reference_golden(golden_dir, name):
     want = ref[sim.local_order[:, 1], sim.local_order[:, 0]]
     assert np.abs(linf - want).max() < 1e-12 * np.abs(want).max()
     sim.close()
+
+
+@pytest.mark.parametrize("name", ["L3_finest", "L3_coarser"])
+def test_adapt_tags_vs_reference_golden(golden_dir, name):
+    """adapt()'s whole block criterion (vorticity + body proximity, main.cpp:4631-4689) from device data"""
+    d = np.load(os.path.join(golden_dir, f"tags_{name}.npz"))
+    L, rtol = int(d["L"]), float(d["rtol"])
+    sim = cup2d_b200.Simulation(L)
+    sim.upload("vel", d["u"], d["v"])
+    sim.upload("chi", d["chi"])
+    linf = sim.adapt_tags(rtol, int(d["offset"]))
+    got = sim.download("tmp")
+    flagged = d["tags"] == 2 * rtol
+    assert np.array_equal(got == 2 * rtol, flagged)           # same blocks flagged, same cells overwritten
+    assert rel(got, d["tags"]) < 1e-14
+    want = orc.block_linf(d["tags"])[sim.local_order[:, 1], sim.local_order[:, 0]]
+    assert np.abs(linf - want).max() < 1e-12 * np.abs(want).max()
+    sim.close()
+
+
+def test_dump_files_byte_identical_to_reference(golden_dir, tmp_path):
+    """cup2d_dump writes the reference's .xyz.raw / .attr.raw / .xdmf2 byte for byte (main.cpp:3367-3467)"""
+    d = np.load(os.path.join(golden_dir, "dump_L2.npz"))
+    sim = cup2d_b200.Simulation(int(d["L"]))
+    sim.upload("vel", d["u"], d["v"])
+    pref = str(tmp_path / "vel.00000007")
+    sim.dump(float(d["time"]), pref)
+    assert open(pref + ".xyz.raw", "rb").read() == d["xyz"].tobytes()
+    assert open(pref + ".attr.raw", "rb").read() == d["attr"].tobytes()
+    assert open(pref + ".xdmf2", "rb").read() == d["xdmf"].tobytes()
+    sim.close()
+
+
+def test_dump_large_multi_chunk(tmp_path):
+    """more blocks than one staging chunk (16384): every cell lands at its offset"""
+    L = 8  # 65536 blocks, 2048^2 cells: 4 chunks, 185 MB of output
+    N = 8 << L
+    rng = np.random.default_rng(5)
+    u, v = rng.uniform(-1, 1, (N, N)), rng.uniform(-1, 1, (N, N))
+    sim = cup2d_b200.Simulation(L)
+    sim.upload("vel", u, v)
+    pref = str(tmp_path / "big")
+    sim.dump(0.5, pref)
+    attr = np.fromfile(pref + ".attr.raw", dtype=np.float32).reshape(-1, 8, 8, 3)
+    xyz = np.fromfile(pref + ".xyz.raw", dtype=np.float32).reshape(-1, 8, 8, 8)
+    order = sim.local_order
+    for k in (0, 16383, 16384, 40000, len(order) - 1):
+        i, j = order[k]
+        assert np.array_equal(attr[k, :, :, 0], u[8 * j:8 * j + 8, 8 * i:8 * i + 8].astype(np.float32))
+        assert np.array_equal(attr[k, :, :, 1], v[8 * j:8 * j + 8, 8 * i:8 * i + 8].astype(np.float32))
+        assert xyz[k, 0, 0, 0] == np.float32(8 * i / N) and xyz[k, 0, 0, 1] == np.float32(8 * j / N)
+    assert not attr[..., 2].any()
+    sim.close()
