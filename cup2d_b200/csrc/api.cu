@@ -441,7 +441,8 @@ void cup2d_destroy(cup2d_sim *s) {
   for (auto p : s->f) cudaFree(p);
   for (auto p : s->kx) cudaFree(p);
   cudaFree(s->kr); cudaFree(s->krhat); cudaFree(s->kp); cudaFree(s->knu); cudaFree(s->kt); cudaFree(s->kz);
-  cudaFree(s->d_nbr); cudaFree(s->d_tiles); cudaFree(s->d_tile_org); cudaFree(s->d_halo_src); cudaFree(s->d_adv_lut); cudaFree(s->d_linf); cudaFree(s->d_chi_mask); cudaFree(s->d_ij);
+  cudaFree(s->d_nbr); cudaFree(s->d_tiles); cudaFree(s->d_tile_org); cudaFree(s->d_halo_src); shapes_free(s);
+  cudaFree(s->d_adv_lut); cudaFree(s->d_linf); cudaFree(s->d_chi_mask); cudaFree(s->d_ij);
   cudaFree(s->d_state); cudaFree(s->d_partials); cudaFree(s->d_counter); cudaFree(s->d_scal);
   cudaFree(s->d_mailbox);
   cudaFree(s->d_irr_blk); cudaFree(s->d_irr_tab); cudaFree(s->d_irr_rowptr); cudaFree(s->d_irr_col); cudaFree(s->d_irr_val);
@@ -622,6 +623,42 @@ int cup2d_dump(cup2d_sim *s, double time, const char *path) {
   CUP2D_REQUIRE(!s->poisson_only && path && *path, "dump: bad arguments");
   CUP2D_CUDA(cudaSetDevice(s->device));
   return dump_fields(s, time, path);
+}
+#define CHECK_SHAPE(s, shape, must_exist)                                                         \
+  CUP2D_REQUIRE(!s->poisson_only, "shape call on a Poisson-only context");                        \
+  CUP2D_REQUIRE(shape >= 0 && shape < 64, "shape index out of range (0..63)");                    \
+  CUP2D_REQUIRE(!(must_exist) || shape < (int)s->shapes.size(), "shape has not been set (cup2d_shape_set)")
+int cup2d_shape_set(cup2d_sim *s, int shape, int nob, const int32_t *block_ids, const double *chi,
+                    const double *udef) {
+  CHECK_SIM(s);
+  CHECK_SHAPE(s, shape, false);
+  CUP2D_REQUIRE(nob >= 0 && (nob == 0 || (block_ids && chi && udef)), "cup2d_shape_set: bad arguments");
+  for (int k = 0; k < nob; k++)
+    CUP2D_REQUIRE(block_ids[k] >= 0 && block_ids[k] < s->nloc, "cup2d_shape_set: block id outside the local range");
+  CUP2D_CUDA(cudaSetDevice(s->device));
+  return shape_set(s, shape, nob, block_ids, chi, udef);
+}
+int cup2d_shape_integrals(cup2d_sim *s, int shape, double lambda, double dt, double cx, double cy, double *out7) {
+  CHECK_SIM(s);
+  CHECK_SHAPE(s, shape, true);
+  CUP2D_REQUIRE(out7, "cup2d_shape_integrals: null output");
+  CUP2D_CUDA(cudaSetDevice(s->device));
+  int rc = need_peers(s);
+  if (rc) return rc;
+  return shape_integrals(s, shape, lambda, dt, cx, cy, out7);
+}
+int cup2d_penalize(cup2d_sim *s, int shape, double lambda, double dt, double cx, double cy, double us, double vs,
+                   double omega) {
+  CHECK_SIM(s);
+  CHECK_SHAPE(s, shape, true);
+  CUP2D_CUDA(cudaSetDevice(s->device));
+  return shape_penalize(s, shape, lambda, dt, cx, cy, us, vs, omega);
+}
+int cup2d_udef_assemble(cup2d_sim *s) {
+  CHECK_SIM(s);
+  CUP2D_REQUIRE(!s->poisson_only, "udef_assemble on a Poisson-only context");
+  CUP2D_CUDA(cudaSetDevice(s->device));
+  return udef_assemble(s);
 }
 int cup2d_pressure_correct(cup2d_sim *s, double dt) {
   CHECK_SIM(s);

@@ -230,10 +230,9 @@ int dump_fields(cup2d_sim *s, double time, const char *path) {
             basename_of(attr_path).c_str());
     fclose(xmf);
   }
-  if (!s->d_ij) {
-    CUP2D_CUDA(cudaMalloc(&s->d_ij, (size_t)s->nloc * sizeof(int2)));
-    CUP2D_CUDA(cudaMemcpy(s->d_ij, s->ij.data() + 2 * s->gbegin, (size_t)s->nloc * sizeof(int2),
-                          cudaMemcpyHostToDevice));
+  {
+    const int rc = ensure_block_ij(s);
+    if (rc) return rc;
   }
   // staging: CHUNK blocks at a time, device + pinned host (44 B per cell)
   const int CHUNK = (int)std::min<int64_t>(s->nloc, 16384);

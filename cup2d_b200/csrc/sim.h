@@ -89,6 +89,9 @@ struct cup2d_sim {
   int *d_irr_blk = nullptr, *d_irr_tab = nullptr, *d_irr_rowptr = nullptr, *d_irr_col = nullptr;
   double *d_irr_val = nullptr;
   int64_t n_irr_rows = 0;
+  // bodies: per-shape obstacle blocks on the device (cup2d_shape_set)
+  struct Shape { int nob = 0, cap = 0; int *d_ids = nullptr; double *d_X = nullptr, *d_udef = nullptr; };
+  std::vector<Shape> shapes;
   int64_t launches = 0;
   // optional per-kernel-class CUDA-event instrumentation (cup2d_profile_*)
   bool prof_on = false;
@@ -133,6 +136,13 @@ int launch_pressure_rhs(cup2d_sim *s, double dt, bool has_udef);
 int launch_pressure_correct(cup2d_sim *s, double dt);
 int launch_adapt_tags(cup2d_sim *s, double rtol, int chi_cells, double *linf_host);
 int dump_fields(cup2d_sim *s, double time, const char *path);
+int ensure_block_ij(cup2d_sim *s);
+int shape_set(cup2d_sim *s, int shape, int nob, const int32_t *ids, const double *X, const double *udef);
+void shapes_free(cup2d_sim *s);
+int shape_integrals(cup2d_sim *s, int shape, double lambda, double dt, double cx, double cy, double *out);
+int shape_penalize(cup2d_sim *s, int shape, double lambda, double dt, double cx, double cy, double us, double vs,
+                   double omega);
+int udef_assemble(cup2d_sim *s);
 int poisson_solve(cup2d_sim *s, double tol_abs, double tol_rel, int max_restarts, int max_iter,
                   int *iters, double *err);
 int halo_exchange_ptr(cup2d_sim *s, double *base, int dim, int peer_index, bool done_barrier = true);

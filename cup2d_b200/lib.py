@@ -18,6 +18,7 @@ SYMBOLS = [
     "cup2d_peer_blob_size", "cup2d_peer_export", "cup2d_peer_attach", "cup2d_halo_exchange",
     "cup2d_launch_count", "cup2d_profile_enable", "cup2d_profile_read",
     "cup2d_plan_create", "cup2d_plan_table", "cup2d_poisson_create", "cup2d_poisson_create_general", "cup2d_vorticity_tag", "cup2d_adapt_tags", "cup2d_dump",
+    "cup2d_shape_set", "cup2d_shape_integrals", "cup2d_penalize", "cup2d_udef_assemble",
 ]
 
 
@@ -84,6 +85,10 @@ def load_library():
     lib.cup2d_vorticity_tag.argtypes = [P, C.POINTER(D)]
     lib.cup2d_adapt_tags.argtypes = [P, D, C.c_int, C.POINTER(D)]
     lib.cup2d_dump.argtypes = [P, D, C.c_char_p]
+    lib.cup2d_shape_set.argtypes = [P, C.c_int, C.c_int, C.POINTER(C.c_int32), C.POINTER(D), C.POINTER(D)]
+    lib.cup2d_shape_integrals.argtypes = [P, C.c_int, D, D, D, D, C.POINTER(D)]
+    lib.cup2d_penalize.argtypes = [P, C.c_int, D, D, D, D, D, D, D]
+    lib.cup2d_udef_assemble.argtypes = [P]
     lib.cup2d_plan_create.argtypes = [C.POINTER(Config), C.POINTER(P)]
     lib.cup2d_plan_table.argtypes = [P, I, C.POINTER(C.c_int32)]
     lib.cup2d_plan_table.restype = L

@@ -158,6 +158,27 @@ class Simulation:
         """the reference's dump(): <path>.xyz.raw, .attr.raw, .xdmf2"""
         _l.check(self.lib.cup2d_dump(self._h, float(time), os.fsencode(path)))
 
+    def shape_set(self, shape, ids, X, udef):
+        """upload one shape's obstacle blocks: ids[nob] local block ids, X[nob,8,8], udef[nob,8,8,2]"""
+        ids = np.ascontiguousarray(ids, dtype=np.int32)
+        X = np.ascontiguousarray(X, dtype=np.float64)
+        udef = np.ascontiguousarray(udef, dtype=np.float64)
+        assert X.size == 64 * len(ids) and udef.size == 128 * len(ids)
+        dp = C.POINTER(C.c_double)
+        _l.check(self.lib.cup2d_shape_set(self._h, shape, len(ids), ids.ctypes.data_as(C.POINTER(C.c_int32)),
+                                          X.ctypes.data_as(dp), udef.ctypes.data_as(dp)))
+
+    def shape_integrals(self, shape, lam, dt, cx, cy):
+        out = np.empty(7)
+        _l.check(self.lib.cup2d_shape_integrals(self._h, shape, lam, dt, cx, cy, out.ctypes.data_as(C.POINTER(C.c_double))))
+        return out
+
+    def penalize(self, shape, lam, dt, cx, cy, us, vs, omega):
+        _l.check(self.lib.cup2d_penalize(self._h, shape, lam, dt, cx, cy, us, vs, omega))
+
+    def udef_assemble(self):
+        _l.check(self.lib.cup2d_udef_assemble(self._h))
+
     def pressure_correct(self, dt):
         _l.check(self.lib.cup2d_pressure_correct(self._h, dt))
 

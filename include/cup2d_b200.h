@@ -118,6 +118,21 @@ int cup2d_vorticity_tag(cup2d_sim *s, double *block_linf_out);
  * order; every rank writes its own byte range) and, on the last rank, <path>.xdmf2 — byte-identical to the
  * reference's files (what post.py reads).  The narrowing to float32 happens on the device. */
 int cup2d_dump(cup2d_sim *s, double time, const char *path);
+/* ---- bodies: the penalisation phase on device-resident fields (main.cpp:6643-6681, 6944-7002) -------------------
+ * A shape = the reference's per-shape obstacleBlocks (main.cpp:3283-3286, 4245-4263): nob local block ids (`infos`
+ * order) with the shape's own chi[nob][8][8] and udef[nob][8][8][2].  Produced by the host body model every step. */
+int cup2d_shape_set(cup2d_sim *s, int shape, int nob, const int32_t *block_ids, const double *chi, const double *udef);
+/* main.cpp:6643-6688: out7 = {PM, PJ, PX, PY, UM, VM, AM}, summed over all ranks (every rank must call, also with
+ * nob = 0).  The 3x3 solve for (u, v, omega) (6689-6703) and the collision model (6704-6943) stay on the host. */
+int cup2d_shape_integrals(cup2d_sim *s, int shape, double lambda, double dt, double cx, double cy, double *out7);
+/* main.cpp:6944-6979: vel = alpha vel + (1-alpha)(us - omega*py + udef_x, vs + omega*px + udef_y) on the cells the
+ * shape owns (its chi > 0 and not below the chi field), alpha = 1/(1+lambda*dt) where its chi > 0.5.  Call per shape
+ * in the reference's order.  Bit-identical to the reference. */
+int cup2d_penalize(cup2d_sim *s, int shape, double lambda, double dt, double cx, double cy, double us, double vs,
+                   double omega);
+/* main.cpp:6980-7002: tmpV = 0, then += udef of every shape (index order) where its chi is not below the chi field:
+ * the u_def input of cup2d_pressure_rhs.  Bit-identical to the reference. */
+int cup2d_udef_assemble(cup2d_sim *s);
 /* One full time step of the hot path (no bodies): compute_dt (unless dt>0 is given), rk2, tmpV=0
  * (or kept if keep_udef), pressure_rhs, poisson_solve, pressure_correct.  Returns dt used. */
 int cup2d_step(cup2d_sim *s, double dt_in, int keep_udef, double tol_abs, double tol_rel,

@@ -322,6 +322,88 @@ def dump_xdmf(time, ncell, xyz_base, attr_base):
             "</Xdmf>\n") % (time, ncell, 4 * ncell, xyz_base, ncell, attr_base)
 
 
+# --------------------------------------------------------------------------------------------
+# Penalisation phase.  A shape is the reference's per-shape Obstacle list
+# (main.cpp:3283-3286, 4245-4263): ids[nob] = block positions in `infos` order, X[nob, 8, 8] = the shape's own chi,
+# udef[nob, 8, 8, 2] = its deformation velocity.
+# --------------------------------------------------------------------------------------------
+def _cell_centres(order, ids, h0, level):
+    """p = origin + h (i + 0.5) of the cells of blocks `ids` (main.cpp:695-696, 6667-6668) -> px[nob,1,8], py[nob,8,1]"""
+    order = np.asarray(order)
+    h = h0 / (1 << level)
+    ox = (order[ids, 0] * BS) * h0 / (1 << level)
+    oy = (order[ids, 1] * BS) * h0 / (1 << level)
+    k = np.arange(BS) + 0.5
+    return ox[:, None, None] + (h * k)[None, None, :], oy[:, None, None] + (h * k)[None, :, None]
+
+
+def shape_integrals(u, v, order, h0, level, ids, X, udef, lam, dt, cx, cy):
+    """main.cpp:6643-6681: {PM, PJ, PX, PY, UM, VM, AM}, summed block by block, cell by cell in the reference's
+    order (exactly reproducible with one OpenMP thread)."""
+    h = h0 / (1 << level)
+    hsq = h * h
+    lambdt = lam * dt
+    vel = to_blocks((u, v), np.asarray(order)[ids], 2).reshape(len(ids), BS, BS, 2)
+    px, py = _cell_centres(order, ids, h0, level)
+    px = px - cx + np.zeros((1, BS, 1))
+    py = py - cy + np.zeros((1, 1, BS))
+    Xl = np.where(X >= 0.5, lambdt, 0.0)
+    F = hsq * Xl / (1 + Xl)
+    du, dv = vel[..., 0] - udef[..., 0], vel[..., 1] - udef[..., 1]
+    terms = [F, F * (px * px + py * py), F * px, F * py, F * du, F * dv, F * (px * dv - py * du)]
+    sel = (X > 0).reshape(-1)
+    out = []
+    for t in terms:
+        acc = 0.0
+        for x in t.reshape(-1)[sel]:
+            acc += x
+        out.append(acc)
+    return np.array(out)
+
+
+def rigid_motion(Q):
+    """main.cpp:6690-6703: (u, v, omega) of the shape from the 3x3 system (the reference uses GSL's LU)"""
+    PM, PJ, PX, PY, UM, VM, AM = Q
+    A = np.array([[PM, 0, -PY], [0, PM, PX], [-PY, PX, PJ]])
+    return np.linalg.solve(A, np.array([UM, VM, AM]))
+
+
+def penalize(u, v, chi, order, h0, level, shapes, lam, dt):
+    """main.cpp:6944-6979.  shapes: dicts with ids, X, udef, cx, cy, u, v, omega; applied in order."""
+    order = np.asarray(order)
+    u, v = u.copy(), v.copy()
+    for sh in shapes:
+        ids, X, udef = sh["ids"], sh["X"], sh["udef"]
+        CHI = to_blocks(chi, order[ids], 1).reshape(len(ids), BS, BS)
+        V = to_blocks((u, v), order[ids], 2).reshape(len(ids), BS, BS, 2)
+        px, py = _cell_centres(order, ids, h0, level)
+        px, py = px - sh["cx"], py - sh["cy"]
+        alpha = np.where(X > 0.5, 1 / (1 + lam * dt), 1.0)
+        US = sh["u"] - sh["omega"] * py + udef[..., 0]
+        VS = sh["v"] + sh["omega"] * px + udef[..., 1]
+        on = ~(CHI > X) & ~(X <= 0)
+        nu_ = np.where(on, alpha * V[..., 0] + (1 - alpha) * US, V[..., 0])
+        nv_ = np.where(on, alpha * V[..., 1] + (1 - alpha) * VS, V[..., 1])
+        for k, (i, j) in enumerate(order[ids]):
+            u[j * BS:(j + 1) * BS, i * BS:(i + 1) * BS] = nu_[k]
+            v[j * BS:(j + 1) * BS, i * BS:(i + 1) * BS] = nv_[k]
+    return u, v
+
+
+def udef_assemble(chi, order, shapes):
+    """main.cpp:6980-7002: tmpV = 0, then += udef of every shape where its chi is not below the chi field"""
+    order = np.asarray(order)
+    udu, udv = np.zeros_like(chi), np.zeros_like(chi)
+    for sh in shapes:
+        ids, X, udef = sh["ids"], sh["X"], sh["udef"]
+        CHI = to_blocks(chi, order[ids], 1).reshape(len(ids), BS, BS)
+        on = ~(X < CHI)
+        for k, (i, j) in enumerate(order[ids]):
+            udu[j * BS:(j + 1) * BS, i * BS:(i + 1) * BS] += np.where(on[k], udef[k, :, :, 0], 0.0)
+            udv[j * BS:(j + 1) * BS, i * BS:(i + 1) * BS] += np.where(on[k], udef[k, :, :, 1], 0.0)
+    return udu, udv
+
+
 def grad_p(p, h, dt):
     """pressureCorrectionKernel::operator() (main.cpp:6021-6043)"""
     NY, NX = p.shape

@@ -27,6 +27,14 @@
 //        out: tmp (N^2 doubles) = vorticity with the 4 centre cells of body-adjacent blocks set to 2 Rtol
 //   ref_harness dump  L time in.bin prefix
 //        the reference's own dump() (main.cpp:3367-3467) of vel -> prefix.xyz.raw, prefix.attr.raw, prefix.xdmf2
+//   ref_harness penal L nsteps kiter out.bin
+//        two self-propelled fish on a uniform level-L grid (extent 1, no regridding); records the penalisation phase
+//        of every step (main.cpp:6643-6681, 6944-7002) as a stream of records [tag, n, n doubles]:
+//        tag 1 (per shape, at the 7-sum of main.cpp:6681): step, k, lambda, dt, Cx, Cy, Q[7], nob, ids[nob],
+//              chi[nob*64], udef[nob*128]      (the shape's Obstacle blocks, main.cpp:3283-3286)
+//        tag 2 (once per step, shape 0's hook): u, v before penalisation (2 N^2)
+//        tag 3 (at main.cpp:7138, i.e. after penalisation + solve, before the correction): per shape (u, v, omega),
+//              then u, v after penalisation, tmpV = summed udef (2 N^2), chi field (N^2)
 //   ref_harness steps L nu cfl nsteps kiter in.bin out.bin
 //        in : as above (udef ignored: no shapes => udef = 0, chi = 0 ; p = initial pres)
 //        out: per step: dt, then u v p  b x   (1 + 5 N^2 doubles), b/x = Poisson rhs / solution
@@ -47,7 +55,8 @@ extern int cup2d_ref_force_iters;
 extern int cup2d_ref_fixed_iters;
 
 namespace {
-enum Mode { ORDER, OPS, STEPS, TIME, AMR, VORT, TAGS, DUMP } g_mode;
+enum Mode { ORDER, OPS, STEPS, TIME, AMR, VORT, TAGS, DUMP, PENAL } g_mode;
+int g_sum7 = 0, g_sum2 = 0, g_step = 0;
 int g_extra = 0;
 double g_rtol = 0, g_time = 0;
 int g_L, g_N, g_NY, g_bx = 1, g_by = 1, g_nsteps, g_reps, g_kiter;
@@ -285,7 +294,66 @@ void do_time() {
 }
 } // namespace
 
+static void put(double tag, const std::vector<double> &v) {
+  const double hdr[2] = {tag, (double)v.size()};
+  fwrite(hdr, sizeof(double), 2, g_fout);
+  fwrite(v.data(), sizeof(double), v.size(), g_fout);
+}
+static void put_fields(double tag, std::initializer_list<std::pair<Grid *, int>> gs, std::vector<double> head = {}) {
+  const size_t n2 = (size_t)g_N * g_NY;
+  for (auto &g : gs) {
+    std::vector<double> a(n2), b(n2);
+    gather(g.first, g.second, a.data(), b.data());
+    head.insert(head.end(), a.begin(), a.end());
+    if (g.second == 2) head.insert(head.end(), b.begin(), b.end());
+  }
+  put(tag, head);
+}
+static void penal_hook(int op, void *buf, int count) {
+  const int S = (int)sim.shapes.size();
+  if (op == MPI_MAX && count == 1) { // dt of a new step (main.cpp:6592)
+    if (!g_fout) g_fout = fopen(g_out.c_str(), "wb");
+    if (g_step == g_nsteps) { fclose(g_fout); exit(0); }
+    g_sum7 = g_sum2 = 0;
+    g_step++;
+    return;
+  }
+  if (g_step == 0) return; // initialisation calls before the time loop
+  if (op == MPI_SUM && count == 7) {
+    const int c = g_sum7++;
+    if (c < S) return; // the S calls of ongrid() (main.cpp:4514) come first
+    const int k = c - S;
+    const auto &shape = sim.shapes[k];
+    if (k == 0) put_fields(2, {{var.vel, 2}});
+    const double *Q = (const double *)buf;
+    std::vector<double> r = {(double)(g_step - 1), (double)k, sim.lambda, sim.dt, shape->centerOfMass[0],
+                             shape->centerOfMass[1]};
+    r.insert(r.end(), Q, Q + 7);
+    std::vector<double> ids, chi, udef;
+    const auto &ob = shape->obstacleBlocks;
+    for (size_t i = 0; i < ob.size(); i++) {
+      if (!ob[i]) continue;
+      ids.push_back((double)i);
+      const double *c0 = (const double *)ob[i]->chi, *u0 = (const double *)ob[i]->udef;
+      chi.insert(chi.end(), c0, c0 + _BS_ * _BS_);
+      udef.insert(udef.end(), u0, u0 + 2 * _BS_ * _BS_);
+    }
+    r.push_back((double)ids.size());
+    r.insert(r.end(), ids.begin(), ids.end());
+    r.insert(r.end(), chi.begin(), chi.end());
+    r.insert(r.end(), udef.begin(), udef.end());
+    put(1, r);
+    return;
+  }
+  if (op == MPI_SUM && count == 2 && g_sum2++ == 0) { // main.cpp:7138
+    std::vector<double> head;
+    for (auto &sh : sim.shapes) { head.push_back(sh->u); head.push_back(sh->v); head.push_back(sh->omega); }
+    put_fields(3, {{var.vel, 2}, {var.tmpV, 2}, {var.chi, 1}}, head);
+  }
+}
+
 void cup2d_ref_hook(int op, void *buf, int count) {
+  if (g_mode == PENAL) { penal_hook(op, buf, count); return; }
   if (op != MPI_MAX || count != 1) return;
   const int call = g_calls++;
   if (g_mode == ORDER) { do_order(); exit(0); }
@@ -393,6 +461,20 @@ int main(int argc, char **argv) {
                           "-maxPoissonIterations", "1000", "-maxPoissonRestarts", "0", "-nu", "0.00004",
                           "-poissonTol", "1e-3", "-poissonTolRel", "1e-2", "-Rtol", "2", "-tdump", "0", "-tend", "10.0",
                           "-shapes", "angle=0 L=0.2 xpos=1.8 ypos=0.8\n angle=180 L=0.2 xpos=1.6 ypos=0.8"};
+    return ref_main(sizeof args / sizeof *args, (char **)args);
+  }
+  else if (mode == "penal" && argc == 6) {
+    g_mode = PENAL; g_nsteps = atoi(argv[3]); g_kiter = atoi(argv[4]); g_out = argv[5];
+    cup2d_ref_force_iters = g_kiter;
+    char a_l[16], a_lm[16];
+    snprintf(a_l, sizeof a_l, "%d", g_L);
+    snprintf(a_lm, sizeof a_lm, "%d", g_L + 1);
+    const char *args[] = {"ref_main", "-AdaptSteps", "1000000", "-bpdx", "1", "-bpdy", "1", "-CFL", "0.5", "-Ctol", "0",
+                          "-extent", "1", "-lambda", "1e7", "-levelMax", a_lm, "-levelStart", a_l,
+                          "-maxPoissonIterations", "1000", "-maxPoissonRestarts", "0", "-nu", "0.00004",
+                          "-poissonTol", "0", "-poissonTolRel", "0", "-Rtol", "1e300", "-tdump", "0", "-tend", "10.0",
+                          "-shapes", getenv("CUP2D_REF_SHAPES") ? getenv("CUP2D_REF_SHAPES")
+                                                                : "angle=0 L=0.4 xpos=0.55 ypos=0.4\n angle=180 L=0.4 xpos=0.45 ypos=0.6"};
     return ref_main(sizeof args / sizeof *args, (char **)args);
   }
   else { fprintf(stderr, "ref_harness: bad arguments\n"); return 2; }

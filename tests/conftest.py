@@ -18,3 +18,11 @@ def pytest_configure(config):
 @pytest.fixture(scope="session")
 def golden_dir():
     return GOLDEN
+
+
+@pytest.fixture(scope="session")
+def penal_golden():
+    """(L, steps) of tests/golden/penal_L4.npz: the reference's penalisation phase, recorded step by step"""
+    sys.path.insert(0, GOLDEN)
+    from make_golden import load_penal
+    return load_penal(os.path.join(GOLDEN, "penal_L4.npz"))

@@ -159,6 +159,76 @@ def gen_dump(tmp, L, seed, time):
     print("dump", L)
 
 
+def parse_penal(path, L):
+    """records of `ref_harness penal` (see oracle/ref_harness.cpp) -> list of per-step dicts"""
+    N = 8 << L
+    n2 = N * N
+    a = np.fromfile(path)
+    i, steps = 0, []
+    while i < len(a):
+        tag, n = int(a[i]), int(a[i + 1])
+        p = a[i + 2:i + 2 + n]
+        i += 2 + n
+        if tag == 2:
+            cur = {"u0": p[:n2].reshape(N, N), "v0": p[n2:].reshape(N, N), "shapes": []}
+            steps.append(cur)
+        elif tag == 1:
+            nob = int(p[13])
+            o = 14
+            ids = p[o:o + nob].astype(np.int32)
+            o += nob
+            X = p[o:o + nob * 64].reshape(nob, 8, 8)
+            o += nob * 64
+            cur["lam"], cur["dt"] = p[2], p[3]
+            cur["shapes"].append(dict(ids=ids, X=X, udef=p[o:o + nob * 128].reshape(nob, 8, 8, 2), cx=p[4], cy=p[5],
+                                      Q=p[6:13].copy()))
+        elif tag == 3:
+            S = len(cur["shapes"])
+            for k, sh in enumerate(cur["shapes"]):
+                sh["u"], sh["v"], sh["omega"] = p[3 * k:3 * k + 3]
+            cur["u1"], cur["v1"], cur["udu"], cur["udv"], cur["chi"] = p[3 * S:].reshape(5, N, N)
+    return steps
+
+
+def gen_penal(tmp, L, nsteps, keep):
+    """penalisation phase of the reference with two fish close enough for their blocks to overlap (and, at the
+    last step, to collide, which changes the rigid motion the host hands to the blend)"""
+    fout = os.path.join(tmp, "penal.bin")
+    env = dict(os.environ, OMP_NUM_THREADS="1",
+               CUP2D_REF_SHAPES="angle=0 L=0.8 xpos=0.52 ypos=0.44\n angle=175 L=0.8 xpos=0.47 ypos=0.56")
+    subprocess.run([HARNESS, "penal", str(L), str(nsteps), "5", fout], check=True, stderr=subprocess.DEVNULL,
+                   stdout=subprocess.DEVNULL, env=env)
+    steps = parse_penal(fout, L)
+    out = {"L": L, "nshapes": 2, "steps": np.array(keep)}
+    for s in keep:
+        st = steps[s]
+        for k in ("u0", "v0", "u1", "v1", "udu", "udv", "chi", "lam", "dt"):
+            out[f"s{s}_{k}"] = st[k]
+        for j, sh in enumerate(st["shapes"]):
+            for k in ("ids", "X", "udef", "Q"):
+                out[f"s{s}_sh{j}_{k}"] = sh[k]
+            out[f"s{s}_sh{j}_rigid"] = np.array([sh["cx"], sh["cy"], sh["u"], sh["v"], sh["omega"]])
+    np.savez_compressed(os.path.join(HERE, f"penal_L{L}.npz"), **out)
+    print("penal", L, keep)
+
+
+def load_penal(path):
+    """inverse of gen_penal's flattening: list of per-step dicts (used by the tests)"""
+    d = np.load(path)
+    steps = []
+    for s in d["steps"]:
+        st = {k: d[f"s{s}_{k}"] for k in ("u0", "v0", "u1", "v1", "udu", "udv", "chi")}
+        st["lam"], st["dt"] = float(d[f"s{s}_lam"]), float(d[f"s{s}_dt"])
+        st["shapes"] = []
+        for j in range(int(d["nshapes"])):
+            cx, cy, u, v, om = d[f"s{s}_sh{j}_rigid"]
+            st["shapes"].append(dict(ids=d[f"s{s}_sh{j}_ids"], X=d[f"s{s}_sh{j}_X"], udef=d[f"s{s}_sh{j}_udef"],
+                                     Q=d[f"s{s}_sh{j}_Q"], cx=float(cx), cy=float(cy), u=float(u), v=float(v),
+                                     omega=float(om)))
+        steps.append(st)
+    return int(d["L"]), steps
+
+
 def gen_steps(tmp, kind, L, seed, nu, cfl, nsteps, kiter):
     N = 8 << L
     ins = make_inputs(kind, L, seed)
@@ -186,6 +256,7 @@ if __name__ == "__main__":
         gen_tags(tmp, "L3_finest", 3, 4244, 5.0, 0, [(0.4, 0.55, 0.12), (0.02, 0.97, 0.05)])
         gen_tags(tmp, "L3_coarser", 3, 4245, 3.0, 1, [(0.7, 0.3, 0.1), (0.99, 0.01, 0.04), (0.26, 0.76, 0.015)])
         gen_dump(tmp, 2, 4246, 0.1875)
+        gen_penal(tmp, 4, 4, [2, 3])
         gen_ops(tmp, "random", 2, 1234, 1e-3, 2.5e-3)
         gen_ops(tmp, "tg", 3, 4321, 1e-3, 1.2e-3)
         gen_steps(tmp, "tg", 2, 777, 1e-3, 0.5, 3, 12)

@@ -483,3 +483,37 @@ def test_dump_large_multi_chunk(tmp_path):
         assert xyz[k, 0, 0, 0] == np.float32(8 * i / N) and xyz[k, 0, 0, 1] == np.float32(8 * j / N)
     assert not attr[..., 2].any()
     sim.close()
+
+
+def test_penalisation_phase_vs_reference_golden(penal_golden):
+    """shape integrals, penalisation blend and udef assembly on device data against the reference's own
+    penalisation phase (two interacting fish; main.cpp:6643-6681, 6944-7002).  Blend and assembly: bit for bit."""
+    L, steps = penal_golden
+    sim = cup2d_b200.Simulation(L)
+    for st in steps:
+        sim.upload("vel", st["u0"], st["v0"])
+        sim.upload("chi", st["chi"])
+        for k, sh in enumerate(st["shapes"]):
+            sim.shape_set(k, sh["ids"], sh["X"], sh["udef"])
+        for k, sh in enumerate(st["shapes"]):
+            Q = sim.shape_integrals(k, st["lam"], st["dt"], sh["cx"], sh["cy"])
+            assert np.abs(Q - sh["Q"]).max() <= 1e-12 * np.abs(sh["Q"]).max(), (Q, sh["Q"])
+        for k, sh in enumerate(st["shapes"]):
+            sim.penalize(k, st["lam"], st["dt"], sh["cx"], sh["cy"], sh["u"], sh["v"], sh["omega"])
+        u1, v1 = sim.download("vel")
+        assert np.array_equal(u1, st["u1"]) and np.array_equal(v1, st["v1"])
+        sim.udef_assemble()
+        udu, udv = sim.download("tmpV")
+        assert np.array_equal(udu, st["udu"]) and np.array_equal(udv, st["udv"])
+    sim.close()
+
+
+def test_shape_calls_reject_bad_arguments():
+    sim = cup2d_b200.Simulation(2)
+    with pytest.raises(cup2d_b200.lib.Cup2dError):
+        sim.shape_integrals(0, 1e7, 1e-3, 0.5, 0.5)  # shape never set
+    with pytest.raises(cup2d_b200.lib.Cup2dError):
+        sim.shape_set(0, [16], np.zeros((1, 8, 8)), np.zeros((1, 8, 8, 2)))  # block id outside the grid
+    sim.shape_set(0, [], np.zeros((0, 8, 8)), np.zeros((0, 8, 8, 2)))
+    assert not sim.shape_integrals(0, 1e7, 1e-3, 0.5, 0.5).any()
+    sim.close()
