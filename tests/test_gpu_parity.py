@@ -464,23 +464,25 @@ def test_dump_files_byte_identical_to_reference(golden_dir, tmp_path):
 
 
 def test_dump_large_multi_chunk(tmp_path):
-    """more blocks than one staging chunk (16384): every cell lands at its offset"""
-    L = 8  # 65536 blocks, 2048^2 cells: 4 chunks, 185 MB of output
-    N = 8 << L
+    """more blocks than one staging chunk (16384), rectangular domain: every cell lands at its offset"""
+    L = 7  # 2x1 boxes of 128^2 blocks = 32768 blocks = 2 chunks, 92 MB of output
+    NX, NY = 2 * (8 << L), 8 << L
     rng = np.random.default_rng(5)
-    u, v = rng.uniform(-1, 1, (N, N)), rng.uniform(-1, 1, (N, N))
-    sim = cup2d_b200.Simulation(L)
+    u, v = rng.uniform(-1, 1, (NY, NX)), rng.uniform(-1, 1, (NY, NX))
+    sim = cup2d_b200.Simulation(L, bpdx=2, bpdy=1)
     sim.upload("vel", u, v)
     pref = str(tmp_path / "big")
     sim.dump(0.5, pref)
     attr = np.fromfile(pref + ".attr.raw", dtype=np.float32).reshape(-1, 8, 8, 3)
     xyz = np.fromfile(pref + ".xyz.raw", dtype=np.float32).reshape(-1, 8, 8, 8)
     order = sim.local_order
-    for k in (0, 16383, 16384, 40000, len(order) - 1):
+    assert len(order) == 32768 and len(attr) == 32768
+    h = 1.0 / NX  # extent / max(bpdx, bpdy) / 8 / 2^L
+    for k in (0, 16383, 16384, 20000, len(order) - 1):
         i, j = order[k]
         assert np.array_equal(attr[k, :, :, 0], u[8 * j:8 * j + 8, 8 * i:8 * i + 8].astype(np.float32))
         assert np.array_equal(attr[k, :, :, 1], v[8 * j:8 * j + 8, 8 * i:8 * i + 8].astype(np.float32))
-        assert xyz[k, 0, 0, 0] == np.float32(8 * i / N) and xyz[k, 0, 0, 1] == np.float32(8 * j / N)
+        assert xyz[k, 0, 0, 0] == np.float32(8 * i * h) and xyz[k, 0, 0, 1] == np.float32(8 * j * h)
     assert not attr[..., 2].any()
     sim.close()
 
