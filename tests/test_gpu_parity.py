@@ -315,7 +315,8 @@ def test_two_ranks_on_two_gpus_match_the_oracle():
                         os.path.join(root, "tools", "multi_gpu_check.py")], stdout=subprocess.PIPE,
                        stderr=subprocess.STDOUT, text=True, timeout=300)
     assert r.returncode == 0, r.stdout[-2000:]
-    assert '"check": "parity_256"' in r.stdout
+    for check in ("parity_256", "tags_dump", "penalisation"):
+        assert f'"check": "{check}"' in r.stdout
 
 
 def test_general_rows_override_reproduces_stencil_solve():

@@ -54,6 +54,55 @@ for s in range(2):
 if rank == 0:
     print(json.dumps({"check": "parity_256", "ranks": world, "Linf_u_v_p_dt": worst, "nhalo": int(sim.lib.cup2d_nblocks_halo(sim._h))}), flush=True)
 assert worst < 1e-8, worst
+
+# ---- regridding criterion (vorticity part), dump files and the penalisation phase on N ranks ----
+gu, gv = gather_field(sim, "vel", 2)
+linf = sim.vorticity_tag()
+w = orc.vorticity(gu, gv, 1.0 / N)
+want = orc.block_linf(w)[sim.local_order[:, 1], sim.local_order[:, 0]]
+gw = gather_field(sim, "tmp", 1)
+tag_err = max(float(np.abs(linf - want).max() / np.abs(want).max()), float(np.abs(gw - w).max() / np.abs(w).max()))
+pref = "/tmp/cup2d_mgpu_dump"
+if rank == 0:
+    for ext in (".xyz.raw", ".attr.raw", ".xdmf2"):
+        if os.path.exists(pref + ext):
+            os.remove(pref + ext)
+dist.barrier()
+sim.dump(0.25, pref)
+dist.barrier()
+xyz, attr = orc.dump_arrays(gu, gv, sim.order, 1.0 / 8, L)
+dump_ok = (open(pref + ".xyz.raw", "rb").read() == xyz.tobytes() and open(pref + ".attr.raw", "rb").read() == attr.tobytes()
+           and open(pref + ".xdmf2").read() == orc.dump_xdmf(0.25, len(sim.order) * 64, "cup2d_mgpu_dump.xyz.raw", "cup2d_mgpu_dump.attr.raw"))
+if rank == 0:
+    print(json.dumps({"check": "tags_dump", "ranks": world, "tag_rel_err": tag_err, "dump_identical": bool(dump_ok)}), flush=True)
+assert tag_err < 1e-12 and dump_ok
+sim.close()
+
+sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+from make_golden import load_penal  # noqa: E402
+
+PL, steps = load_penal(os.path.join(ROOT, "tests", "golden", "penal_L4.npz"))
+sim = cup2d_b200.Simulation(PL, device=lrank, rank=rank, nranks=world)
+sim.attach_peers(dist)
+pen_err, pen_exact = 0.0, True
+for st in steps:
+    sim.upload("vel", st["u0"], st["v0"])
+    sim.upload("chi", st["chi"])
+    for k, sh in enumerate(st["shapes"]):
+        mine = (sh["ids"] >= sim.gbegin) & (sh["ids"] < sim.gend)
+        sim.shape_set(k, sh["ids"][mine] - sim.gbegin, sh["X"][mine], sh["udef"][mine])
+    for k, sh in enumerate(st["shapes"]):
+        Q = sim.shape_integrals(k, st["lam"], st["dt"], sh["cx"], sh["cy"])  # global sums on every rank
+        pen_err = max(pen_err, float(np.abs(Q - sh["Q"]).max() / np.abs(sh["Q"]).max()))
+    for k, sh in enumerate(st["shapes"]):
+        sim.penalize(k, st["lam"], st["dt"], sh["cx"], sh["cy"], sh["u"], sh["v"], sh["omega"])
+    sim.udef_assemble()
+    gu, gv = gather_field(sim, "vel", 2)
+    du, dv = gather_field(sim, "tmpV", 2)
+    pen_exact = pen_exact and all(np.array_equal(a, b) for a, b in ((gu, st["u1"]), (gv, st["v1"]), (du, st["udu"]), (dv, st["udv"])))
+if rank == 0:
+    print(json.dumps({"check": "penalisation", "ranks": world, "integrals_rel_err": pen_err, "blend_udef_bit_exact": bool(pen_exact)}), flush=True)
+assert pen_err < 1e-12 and pen_exact
 sim.close()
 dist.barrier()
 dist.destroy_process_group()
