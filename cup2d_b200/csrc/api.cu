@@ -442,7 +442,7 @@ void cup2d_destroy(cup2d_sim *s) {
   for (auto p : s->kx) cudaFree(p);
   cudaFree(s->kr); cudaFree(s->krhat); cudaFree(s->kp); cudaFree(s->knu); cudaFree(s->kt); cudaFree(s->kz);
   cudaFree(s->d_nbr); cudaFree(s->d_tiles); cudaFree(s->d_tile_org); cudaFree(s->d_halo_src); shapes_free(s);
-  cudaFree(s->d_adv_lut); cudaFree(s->d_linf); cudaFree(s->d_chi_mask); cudaFree(s->d_ij);
+  cudaFree(s->d_adv_lut); cudaFree(s->d_linf); cudaFree(s->d_ij);
   cudaFree(s->d_state); cudaFree(s->d_partials); cudaFree(s->d_counter); cudaFree(s->d_scal);
   cudaFree(s->d_mailbox);
   cudaFree(s->d_irr_blk); cudaFree(s->d_irr_tab); cudaFree(s->d_irr_rowptr); cudaFree(s->d_irr_col); cudaFree(s->d_irr_val);
@@ -610,8 +610,6 @@ int cup2d_adapt_tags(cup2d_sim *s, double rtol, int chi_cells, double *block_lin
   CHECK_SIM(s);
   CUP2D_REQUIRE(!s->poisson_only, "adapt_tags: a Poisson-only context has no velocity field");
   CUP2D_REQUIRE(chi_cells >= 0 && chi_cells <= CUP2D_BS, "adapt_tags: chi_cells must be 0..8 (the reference uses 2 or 4)");
-  CUP2D_REQUIRE(chi_cells == 0 || s->nranks == 1,
-                "adapt_tags: the chi criterion needs diagonal neighbour blocks, which the multi-rank halo does not hold yet");
   CUP2D_CUDA(cudaSetDevice(s->device));
   int rc = need_peers(s);
   if (rc) return rc;

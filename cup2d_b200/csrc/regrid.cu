@@ -19,7 +19,13 @@ namespace cup2d {
 constexpr int NT = 256;
 constexpr int WPB = NT / 32;
 
-// bit (8*y + x) of mask[slot] <-> chi(x, y) of that block is > 0 after the clamp of main.cpp:4644-4645
+// Body-proximity masks live in the first three 64-bit words of every block of the Krylov scratch vector kz (idle
+// outside the Poisson solve and already peer-mapped, so the ordinary block halo pull moves them between GPUs):
+//   word 0: bit (8*y + x) <-> chi(x, y) of this block is > 0 after the clamp of main.cpp:4644-4645
+//   word 1 / 2: word 0 of the block's S / N neighbour (0 at a wall) — so that a block finds its DIAGONAL neighbours'
+//   masks in its W / E neighbours' slots even when those are halo copies of another rank's blocks.
+constexpr int MASK_STRIDE = 64; // 64-bit words per block of a scalar vector
+
 __global__ void __launch_bounds__(NT)
 chi_mask_kernel(const double *__restrict__ chi, unsigned long long *__restrict__ mask, int nrows) {
   __shared__ __align__(16) double s_scr[WPB * ROWS_SCRATCH];
@@ -36,8 +42,17 @@ chi_mask_kernel(const double *__restrict__ chi, unsigned long long *__restrict__
     m |= __shfl_xor_sync(0xffffffffu, m, 1);
     m |= __shfl_xor_sync(0xffffffffu, m, 2);
     m |= __shfl_xor_sync(0xffffffffu, m, 4);
-    if (lane < nv && (lane & 7) == 0) mask[(row0 + lane) >> 3] = m;
+    if (lane < nv && (lane & 7) == 0) mask[(size_t)((row0 + lane) >> 3) * MASK_STRIDE] = m;
     __syncwarp();
+  }
+}
+
+__global__ void __launch_bounds__(NT)
+chi_mask_diag_kernel(unsigned long long *__restrict__ mask, const int4 *__restrict__ nbr, int nloc) {
+  for (int k = blockIdx.x * NT + threadIdx.x; k < nloc; k += gridDim.x * NT) {
+    const int4 nb = nbr[k];
+    mask[(size_t)k * MASK_STRIDE + 1] = nb.z >= 0 ? mask[(size_t)nb.z * MASK_STRIDE] : 0ull;
+    mask[(size_t)k * MASK_STRIDE + 2] = nb.w >= 0 ? mask[(size_t)nb.w * MASK_STRIDE] : 0ull;
   }
 }
 
@@ -52,7 +67,7 @@ __device__ __forceinline__ unsigned long long rows_hi(int o) { return rows_lo(o)
 template <bool CHI>
 __global__ void __launch_bounds__(NT)
 adapt_tag_kernel(const double *__restrict__ vel, double *__restrict__ tmp, double *__restrict__ linf,
-                 const int4 *__restrict__ nbr, const unsigned long long *__restrict__ mask, int nrows, int nloc,
+                 const int4 *__restrict__ nbr, const unsigned long long *__restrict__ mask, int nrows,
                  double i2h, double two_rtol, int o) {
   __shared__ __align__(16) double s_scr[WPB * ROWS_SCRATCH];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -98,24 +113,18 @@ adapt_tag_kernel(const double *__restrict__ vel, double *__restrict__ tmp, doubl
       for (int i = 0; i < 8; i++) w[i] = 0.0;
     }
     if (CHI) {
-      // lane y of a block looks at one of the 8 surrounding blocks (0..3 = W,E,S,N; 4..7 = SW,SE,NW,NE); a
-      // diagonal block is the S/N neighbour of the W/E neighbour.  Everyone adds the block's own mask.
+      // lane y of a block looks at one of the 8 surrounding blocks (0..3 = W,E,S,N; 4..7 = SW,SE,NW,NE); the mask of
+      // a diagonal block is word 1 (S) / 2 (N) of the W / E neighbour's slot.  Everyone adds the block's own mask.
       unsigned long long hit = 0;
       if (act) {
-        hit = mask[slot];
-        const int side = (y & 1) ? nb.y : nb.x;       // W for even, E for odd lanes
-        int src = -1;
-        if (y < 2) src = side;
-        else if (y < 4) src = y == 2 ? nb.z : nb.w;
-        else if (side >= 0 && side < nloc) {
-          const int4 nn = nbr[side];
-          src = y < 6 ? nn.z : nn.w;
-        }
+        hit = mask[(size_t)slot * MASK_STRIDE];
+        const int src = y == 2 ? nb.z : y == 3 ? nb.w : (y & 1) ? nb.y : nb.x;
         if (src >= 0) {
+          const int word = y < 4 ? 0 : (y < 6 ? 1 : 2);
           unsigned long long sel = ~0ull;
           if (y < 2 || y >= 4) sel &= (y & 1) ? cols_lo(o) : cols_hi(o); // E block: its first columns; W: its last
           if (y >= 2) sel &= (y == 2 || y == 4 || y == 5) ? rows_hi(o) : rows_lo(o); // S block: its top rows
-          hit |= mask[src] & sel;
+          hit |= mask[(size_t)src * MASK_STRIDE + word] & sel;
         }
       }
       unsigned any = hit != 0ull;
@@ -146,15 +155,18 @@ int launch_adapt_tags(cup2d_sim *s, double rtol, int chi_cells, double *linf_hos
   const int4 *nbr = reinterpret_cast<const int4 *>(s->d_nbr);
   ProfScope prof(s, KC_VORT);
   if (chi_cells > 0) {
-    if (!s->d_chi_mask) CUP2D_CUDA(cudaMalloc(&s->d_chi_mask, (size_t)s->nloc * sizeof(unsigned long long)));
-    chi_mask_kernel<<<grid, NT, 0, s->stream>>>(s->f[CUP2D_CHI], s->d_chi_mask, nrows);
-    adapt_tag_kernel<true><<<grid, NT, 0, s->stream>>>(s->f[CUP2D_VEL], s->f[CUP2D_TMP], s->d_linf, nbr,
-                                                       s->d_chi_mask, nrows, (int)s->nloc, 0.5 / s->h, 2.0 * rtol,
-                                                       chi_cells);
-    s->launches += 2;
+    unsigned long long *mask = reinterpret_cast<unsigned long long *>(s->kz);
+    int rc;
+    chi_mask_kernel<<<grid, NT, 0, s->stream>>>(s->f[CUP2D_CHI], mask, nrows);
+    if (s->nranks > 1 && (rc = halo_exchange_ptr(s, s->kz, 1, CUP2D_NFIELDS))) return rc;
+    chi_mask_diag_kernel<<<min((int)((s->nloc + NT - 1) / NT), s->num_sms * 8), NT, 0, s->stream>>>(mask, nbr, (int)s->nloc);
+    if (s->nranks > 1 && (rc = halo_exchange_ptr(s, s->kz, 1, CUP2D_NFIELDS))) return rc;
+    adapt_tag_kernel<true><<<grid, NT, 0, s->stream>>>(s->f[CUP2D_VEL], s->f[CUP2D_TMP], s->d_linf, nbr, mask, nrows,
+                                                       0.5 / s->h, 2.0 * rtol, chi_cells);
+    s->launches += 3;
   } else {
     adapt_tag_kernel<false><<<grid, NT, 0, s->stream>>>(s->f[CUP2D_VEL], s->f[CUP2D_TMP], s->d_linf, nbr, nullptr,
-                                                        nrows, (int)s->nloc, 0.5 / s->h, 0.0, 0);
+                                                        nrows, 0.5 / s->h, 0.0, 0);
     s->launches++;
   }
   CUP2D_CUDA(cudaGetLastError());

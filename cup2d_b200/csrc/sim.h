@@ -63,7 +63,6 @@ struct cup2d_sim {
   int *d_tile_org = nullptr;           // [ntiles][2] tile origin in blocks
   int ntiles = 0;
   double *d_linf = nullptr;            // per-block L-inf of the tagging field (cup2d_adapt_tags)
-  unsigned long long *d_chi_mask = nullptr; // per-block bit mask of chi > 0 (cup2d_adapt_tags)
   int *d_ij = nullptr;                 // (i,j) of the local blocks (cup2d_dump)
   unsigned *d_adv_lut = nullptr;       // repack table of the advect kernel (interior tiles)
   // fields (dim*64*nslots doubles each)

@@ -111,7 +111,7 @@ int cup2d_pressure_correct(cup2d_sim *s, double dt);
  * (main.cpp:4631-4656): blocks with chi > 0 within chi_cells cells (reference: 4 on the finest level, else 2) get
  * their 4 centre cells set to 2*rtol; block_linf_out[k] = max|tmp| over local block k, `infos` order (host array of
  * cup2d_nblocks_local doubles, may be NULL).  The caller compares with Rtol / Ctol exactly as main.cpp:4681-4682.
- * chi_cells > 0 is single-rank for now.  cup2d_vorticity_tag(s, out) == cup2d_adapt_tags(s, 0, 0, out). */
+ * Uses the Krylov scratch vector for the chi masks.  cup2d_vorticity_tag(s, out) == cup2d_adapt_tags(s, 0, 0, out). */
 int cup2d_adapt_tags(cup2d_sim *s, double rtol, int chi_cells, double *block_linf_out);
 int cup2d_vorticity_tag(cup2d_sim *s, double *block_linf_out);
 /* dump() (main.cpp:3367-3467): writes <path>.xyz.raw, <path>.attr.raw (float32, cell quads and (u,v,0) in `infos`

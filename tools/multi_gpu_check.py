@@ -78,6 +78,26 @@ if rank == 0:
 assert tag_err < 1e-12 and dump_ok
 sim.close()
 
+# ---- adapt()'s full criterion (vorticity + body proximity, diagonal neighbours across ranks) vs the reference golden
+chi_ok = True
+for name in ("L3_finest", "L3_coarser"):
+    d = np.load(os.path.join(ROOT, "tests", "golden", f"tags_{name}.npz"))
+    rtol_ = float(d["rtol"])
+    sim = cup2d_b200.Simulation(int(d["L"]), device=lrank, rank=rank, nranks=world)
+    sim.attach_peers(dist)
+    sim.upload("vel", d["u"], d["v"])
+    sim.upload("chi", d["chi"])
+    linf = sim.adapt_tags(rtol_, int(d["offset"]))
+    got = gather_field(sim, "tmp", 1)
+    want = orc.block_linf(d["tags"])[sim.local_order[:, 1], sim.local_order[:, 0]]
+    chi_ok = (chi_ok and np.array_equal(got == 2 * rtol_, d["tags"] == 2 * rtol_)
+              and np.abs(got - d["tags"]).max() < 1e-12 * np.abs(d["tags"]).max()
+              and np.abs(linf - want).max() < 1e-12 * np.abs(want).max())
+    sim.close()
+if rank == 0:
+    print(json.dumps({"check": "adapt_tags_chi", "ranks": world, "same_blocks_flagged": bool(chi_ok)}), flush=True)
+assert chi_ok
+
 sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
 from make_golden import load_penal  # noqa: E402
 
