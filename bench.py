@@ -39,10 +39,9 @@ ALG_BYTES = {
     "k_init": 56.0,                   # b, x0 read; x, r, rhat, p, nu written
     "k_pupdate": 40.0,                # r, p, nu read; p, z written
     "k_spmv<0>": 24.0,                # z, rhat read; nu written
-    "k_xr_update": 56.0,              # x, z, r, nu read; x, r, z written
+    "k_r_update": 32.0,               # r, nu read; r, z_r written (the x half-step is deferred to k_final)
     "k_spmv<1>": 24.0,                # z, r read; t written
-    "k_final": 56.0,                  # x, z, r, t, rhat read; x, r written
-    "memset(udef)": 16.0,
+    "k_final": 64.0,                  # x, z_p, z_r, r, t, rhat read; x, r written
 }
 
 
@@ -338,11 +337,13 @@ def main():
                                  "fp64_floor_ms": fp64_floor_ms, "frac_fp64_floor": fp64_floor_ms / adv["ms_per_launch"],
                                  "note": "bound by the FP64 pipe, not HBM: 191 FP64 instr/cell (ncu) at 64 lanes/clk/SM; see DESIGN.md 3.1"}
     it_ms = sum(k["ms_per_launch"] * k["launches_per_step"] for k in kernels
-                if k["kernel"] in ("k_pupdate", "k_spmv<0>", "k_xr_update", "k_spmv<1>", "k_final")) / max(K, 1)
+                if k["kernel"] in ("k_pupdate", "k_spmv<0>", "k_r_update", "k_spmv<1>", "k_final")) / max(K, 1)
     if it_ms > 0:
-        gbs = cells_loc * 200.0 / (it_ms * 1e-3) / 1e9
+        gbs = cells_loc * 184.0 / (it_ms * 1e-3) / 1e9
         extra["poisson_iteration"] = {"ms_per_iteration": it_ms, "Gcell_iter_per_s": cells_loc / (it_ms * 1e-3) / 1e9,
-                                      "alg_bytes_per_cell": 200.0, "achieved_GBs": gbs, "frac_hbm": gbs / peak}
+                                      "alg_bytes_per_cell": 184.0, "achieved_GBs": gbs, "frac_hbm": gbs / peak,
+                                      "note": "23 doubles/cell/iteration (SURVEY 8(d) budgets 25 = 200 B): the x half-step "
+                                              "is deferred into k_final"}
 
     if rank != 0:
         if dist is not None:

@@ -399,7 +399,7 @@ static int alloc_device_state(cup2d_sim *s) {
     CUP2D_CUDA(cudaMemset(s->f[f], 0, bytes));
   }
   const size_t vb = (size_t)s->nslots * 64 * sizeof(double);
-  double **kv[] = {&s->kx[0], &s->kx[1], &s->kx[2], &s->kr, &s->krhat, &s->kp, &s->knu, &s->kt, &s->kz};
+  double **kv[] = {&s->kx[0], &s->kx[1], &s->kx[2], &s->kr, &s->krhat, &s->kp, &s->knu, &s->kt, &s->kz, &s->kzr};
   for (auto p : kv) {
     CUP2D_CUDA(cudaMalloc(p, vb));
     CUP2D_CUDA(cudaMemset(*p, 0, vb));
@@ -440,7 +440,7 @@ void cup2d_destroy(cup2d_sim *s) {
   }
   for (auto p : s->f) cudaFree(p);
   for (auto p : s->kx) cudaFree(p);
-  cudaFree(s->kr); cudaFree(s->krhat); cudaFree(s->kp); cudaFree(s->knu); cudaFree(s->kt); cudaFree(s->kz);
+  cudaFree(s->kr); cudaFree(s->krhat); cudaFree(s->kp); cudaFree(s->knu); cudaFree(s->kt); cudaFree(s->kz); cudaFree(s->kzr);
   cudaFree(s->d_nbr); cudaFree(s->d_tiles); cudaFree(s->d_tile_org); cudaFree(s->d_halo_src); shapes_free(s);
   cudaFree(s->d_adv_lut); cudaFree(s->d_linf); cudaFree(s->d_ij);
   cudaFree(s->d_state); cudaFree(s->d_partials); cudaFree(s->d_counter); cudaFree(s->d_scal);
@@ -457,7 +457,7 @@ int64_t cup2d_nblocks_halo(const cup2d_sim *s) { return s ? s->nhalo : 0; }
 int64_t cup2d_launch_count(const cup2d_sim *s) { return s ? s->launches : 0; }
 
 static const char *kclass_name[KC_COUNT] = {"advect_stage_kernel", "umax_kernel", "pressure_rhs_kernel",
-    "pressure_correct_kernel", "k_init", "k_pupdate", "k_spmv<0>", "k_xr_update", "k_spmv<1>", "k_final",
+    "pressure_correct_kernel", "k_init", "k_pupdate", "k_spmv<0>", "k_r_update", "k_spmv<1>", "k_final",
     "halo_pull_kernel", "vorticity_tag_kernel"};
 int cup2d_profile_enable(cup2d_sim *s, int on) {
   if (!s) return CUP2D_EINVAL;

@@ -113,6 +113,7 @@ int cup2d_peer_export(cup2d_sim *s, void *blob) {
   for (int f = 0; f < CUP2D_NFIELDS; f++) CUP2D_CUDA(cudaIpcGetMemHandle(&b.field[f], s->f[f]));
   CUP2D_CUDA(cudaIpcGetMemHandle(&b.kz, s->kz));
   for (int k = 0; k < 3; k++) CUP2D_CUDA(cudaIpcGetMemHandle(&b.kx[k], s->kx[k]));
+  CUP2D_CUDA(cudaIpcGetMemHandle(&b.kzr, s->kzr));
   CUP2D_CUDA(cudaIpcGetMemHandle(&b.mailbox, s->d_mailbox));
   b.nloc = s->nloc;
   b.rank = s->rank;
@@ -141,6 +142,7 @@ int cup2d_peer_attach(cup2d_sim *s, const void *all_blobs) {
       for (int f = 0; f < CUP2D_NFIELDS; f++) s->peer_base[r][f] = s->f[f];
       s->peer_base[r][CUP2D_NFIELDS] = s->kz;
       for (int k = 0; k < 3; k++) s->peer_base[r][CUP2D_NFIELDS + 1 + k] = s->kx[k];
+      s->peer_base[r][CUP2D_NFIELDS + 4] = s->kzr;
       s->peer_mailbox[r] = s->d_mailbox;
       continue;
     }
@@ -149,6 +151,7 @@ int cup2d_peer_attach(cup2d_sim *s, const void *all_blobs) {
     CUP2D_CUDA(cudaIpcOpenMemHandle(&s->peer_base[r][CUP2D_NFIELDS], blobs[r].kz, cudaIpcMemLazyEnablePeerAccess));
     for (int k = 0; k < 3; k++)
       CUP2D_CUDA(cudaIpcOpenMemHandle(&s->peer_base[r][CUP2D_NFIELDS + 1 + k], blobs[r].kx[k], cudaIpcMemLazyEnablePeerAccess));
+    CUP2D_CUDA(cudaIpcOpenMemHandle(&s->peer_base[r][CUP2D_NFIELDS + 4], blobs[r].kzr, cudaIpcMemLazyEnablePeerAccess));
     void *mb = nullptr;
     CUP2D_CUDA(cudaIpcOpenMemHandle(&mb, blobs[r].mailbox, cudaIpcMemLazyEnablePeerAccess));
     s->peer_mailbox[r] = static_cast<unsigned long long *>(mb);

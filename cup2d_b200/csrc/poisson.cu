@@ -14,7 +14,9 @@
 //     (set_alpha/beta/omega/rho, cuda.cu:303-330) run in the last CTA of the producing kernel, the
 //     x_opt snapshot (cuda.cu:537) is a rotation among three x buffers, and convergence is a device
 //     flag that turns the remaining launches into no-ops.
-// Traffic per iteration: 25 doubles/cell = 200 B/cell.
+// Traffic per iteration: 23 doubles/cell = 184 B/cell (SURVEY.md §8(d) budgets 25 = 200 B): the half-step update
+// x' = x + alpha z of cuda.cu:498 is deferred into the final kernel, which applies x'' = (x + alpha z_p) + omega z_r
+// in the reference's order (bitwise the same iterate), so the middle kernel neither reads nor writes x or z_p.
 // Memory access: warp-cooperative coalesced rows through padded shared memory (rows.cuh).
 #include "rows.cuh"
 #include "sim.h"
@@ -252,50 +254,44 @@ k_spmv(const double *__restrict__ z, const double *__restrict__ d, double *__res
   });
 }
 
-// ---- K3: x' = x + alpha z ; r -= alpha nu ; z = M r     (cuda.cu:498-505) -------------------------
+// ---- K3: r -= alpha nu ; z_r = M r     (cuda.cu:499-505; the x half-step of cuda.cu:498 happens in K5) ----------
 __global__ void __launch_bounds__(NT)
-k_xr_update(double *x0, double *x1, double *x2, const double *zin, double *__restrict__ r,
-            const double *__restrict__ nu, double *zout, int nrows,
-            const KrylovState *__restrict__ st) {
+k_r_update(double *__restrict__ r, const double *__restrict__ nu, double *__restrict__ zr, int nrows,
+           const KrylovState *__restrict__ st) {
   __shared__ __align__(16) double s_scr[WPB * SCR1];
   if (st->done) return;
   const double alpha = st->alpha;
-  const int cur = st->cur, nxt = next_buf(st->cur, st->opt);
-  const double *xc = cur == 0 ? x0 : (cur == 1 ? x1 : x2);
-  double *xn = nxt == 0 ? x0 : (nxt == 1 ? x1 : x2);
   CHUNK_LOOP() {
     const int nv = min(32, nrows - row0);
     // element-wise part in chunk layout (coalesced, no shared memory)
-    double2 cx[4], cz[4], cr[4], cn[4];
-    chunk_ld(xc, row0, nv, lane, cx);
-    chunk_ld(zin, row0, nv, lane, cz);
+    double2 cr[4], cn[4];
     chunk_ld(r, row0, nv, lane, cr);
     chunk_ld(nu, row0, nv, lane, cn);
 #pragma unroll
     for (int j = 0; j < 4; j++) {
-      cx[j].x = fma(alpha, cz[j].x, cx[j].x);
-      cx[j].y = fma(alpha, cz[j].y, cx[j].y);
       cr[j].x = fma(-alpha, cn[j].x, cr[j].x);
       cr[j].y = fma(-alpha, cn[j].y, cr[j].y);
     }
-    chunk_st(xn, row0, nv, lane, cx);
     chunk_st(r, row0, nv, lane, cr);
     // block preconditioner in row layout
     double rr[8];
     chunk_to_rows(sw, lane, cr, rr);
     precond_row(rr, sw, lane);
-    rows_store1(zout, row0, nv, sw, lane, rr);
+    rows_store1(zr, row0, nv, sw, lane, rr);
   }
 }
 
-// ---- K5: x += omega z ; r -= omega t ; err, rhat.r, |r|^2, sum(x) ; end-of-iteration logic --------
+// ---- K5: x = (x + alpha z_p) + omega z_r ; r -= omega t ; err, rhat.r, |r|^2, sum(x) ; end-of-iteration logic ----
+// The new iterate goes to the x buffer that holds neither the current nor the best iterate (x_opt snapshot of
+// cuda.cu:537 without a copy).
 __global__ void __launch_bounds__(NT)
-k_final(double *x0, double *x1, double *x2, const double *__restrict__ z, double *__restrict__ r,
-        const double *__restrict__ t, const double *__restrict__ rhat, int nrows, KrylovState *st,
-        double *partials, unsigned int *counter, Comm comm) {
+k_final(double *x0, double *x1, double *x2, const double *__restrict__ zp, const double *__restrict__ zr,
+        double *__restrict__ r, const double *__restrict__ t, const double *__restrict__ rhat, int nrows,
+        KrylovState *st, double *partials, unsigned int *counter, Comm comm) {
   if (st->done) return;
-  const double omega = st->omega;
-  const int nxt = next_buf(st->cur, st->opt);
+  const double alpha = st->alpha, omega = st->omega;
+  const int cur = st->cur, nxt = next_buf(st->cur, st->opt);
+  const double *xc = cur == 0 ? x0 : (cur == 1 ? x1 : x2);
   double *xn = nxt == 0 ? x0 : (nxt == 1 ? x1 : x2);
   double sums[3] = {0, 0, 0}; // rhat.r, r.r, sum x
   double mx = 0;
@@ -303,16 +299,17 @@ k_final(double *x0, double *x1, double *x2, const double *__restrict__ z, double
   for (int row0 = (blockIdx.x * WPB + warp) * 32; row0 < nrows; row0 += gridDim.x * WPB * 32) {
     const int nv = min(32, nrows - row0);
     // purely element-wise: chunk layout only, no shared memory
-    double2 cx[4], cz[4], cr[4], ct[4], ch[4];
-    chunk_ld(xn, row0, nv, lane, cx);
-    chunk_ld(z, row0, nv, lane, cz);
+    double2 cx[4], cz[4], cy[4], cr[4], ct[4], ch[4];
+    chunk_ld(xc, row0, nv, lane, cx);
+    chunk_ld(zp, row0, nv, lane, cz);
+    chunk_ld(zr, row0, nv, lane, cy);
     chunk_ld(r, row0, nv, lane, cr);
     chunk_ld(t, row0, nv, lane, ct);
     chunk_ld(rhat, row0, nv, lane, ch);
 #pragma unroll
     for (int j = 0; j < 4; j++) {
-      cx[j].x = fma(omega, cz[j].x, cx[j].x); // cuda.cu:520
-      cx[j].y = fma(omega, cz[j].y, cx[j].y);
+      cx[j].x = fma(omega, cy[j].x, fma(alpha, cz[j].x, cx[j].x)); // cuda.cu:498 then 520
+      cx[j].y = fma(omega, cy[j].y, fma(alpha, cz[j].y, cx[j].y));
       cr[j].x = fma(-omega, ct[j].x, cr[j].x); // cuda.cu:524
       cr[j].y = fma(-omega, ct[j].y, cr[j].y);
       sums[0] = fma(ch[j].x, cr[j].x, sums[0]);
@@ -405,22 +402,21 @@ int poisson_solve(cup2d_sim *s, double tol_abs, double tol_rel, int max_restarts
       }
       {
         ProfScope prof(s, KC_XRUPDATE);
-        k_xr_update<<<grid, NT, 0, s->stream>>>(s->kx[0], s->kx[1], s->kx[2], s->kz, s->kr, s->knu,
-                                                s->kz, nrows, s->d_state);
+        k_r_update<<<grid, NT, 0, s->stream>>>(s->kr, s->knu, s->kzr, nrows, s->d_state);
       }
-      if (s->nranks > 1 && (rc = halo_exchange_ptr(s, s->kz, 1, CUP2D_NFIELDS, false))) return rc;
+      if (s->nranks > 1 && (rc = halo_exchange_ptr(s, s->kzr, 1, CUP2D_NFIELDS + 4, false))) return rc;
       {
         ProfScope prof(s, KC_SPMV_T);
         if (has_irr)
-          k_spmv<1, true><<<grid, NT, 0, s->stream>>>(s->kz, s->kr, s->kt, nbr, nrows, s->d_state,
+          k_spmv<1, true><<<grid, NT, 0, s->stream>>>(s->kzr, s->kr, s->kt, nbr, nrows, s->d_state,
                                                       s->d_partials, s->d_counter, s->comm, irr_view(s));
         else
           k_spmv<1, false><<<grid, NT, 0, s->stream>>>(
-              s->kz, s->kr, s->kt, nbr, nrows, s->d_state, s->d_partials, s->d_counter, s->comm, irr_view(s));
+              s->kzr, s->kr, s->kt, nbr, nrows, s->d_state, s->d_partials, s->d_counter, s->comm, irr_view(s));
       }
       {
         ProfScope prof(s, KC_FINAL);
-        k_final<<<grid, NT, 0, s->stream>>>(s->kx[0], s->kx[1], s->kx[2], s->kz, s->kr, s->kt,
+        k_final<<<grid, NT, 0, s->stream>>>(s->kx[0], s->kx[1], s->kx[2], s->kz, s->kzr, s->kr, s->kt,
                                             s->krhat, nrows, s->d_state, s->d_partials, s->d_counter,
                                             s->comm);
       }

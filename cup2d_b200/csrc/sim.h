@@ -35,7 +35,7 @@ struct KrylovState {
 
 struct PeerBlob { // what every rank publishes to the others (cup2d_peer_export)
   cudaIpcMemHandle_t field[CUP2D_NFIELDS];
-  cudaIpcMemHandle_t kz, kx[3];
+  cudaIpcMemHandle_t kz, kx[3], kzr;
   cudaIpcMemHandle_t mailbox;
   int64_t nloc;
   int32_t rank, device;
@@ -69,7 +69,7 @@ struct cup2d_sim {
   double *f[CUP2D_NFIELDS] = {};
   // Krylov vectors (64*nslots)
   double *kx[3] = {}, *kr = nullptr, *krhat = nullptr, *kp = nullptr, *knu = nullptr, *kt = nullptr,
-         *kz = nullptr;
+         *kz = nullptr, *kzr = nullptr; // kz = M p, kzr = M r
   cup2d::KrylovState *d_state = nullptr, *h_state = nullptr;
   // reductions
   double *d_partials = nullptr;
@@ -78,7 +78,7 @@ struct cup2d_sim {
   int num_sms = 0;
   // multi-GPU (peer memory over NVLink)
   bool peers_attached = false;
-  void *peer_base[cup2d::MAX_RANKS][CUP2D_NFIELDS + 4] = {};
+  void *peer_base[cup2d::MAX_RANKS][CUP2D_NFIELDS + 5] = {}; // fields, kz, kx[3], kzr
   int *d_halo_src = nullptr;           // [nhalo][2] = (owner rank, slot on owner)
   unsigned long long *d_mailbox = nullptr;       // this rank's flag/scalar mailbox (peer-writable)
   unsigned long long *peer_mailbox[cup2d::MAX_RANKS] = {};

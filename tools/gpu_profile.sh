@@ -15,7 +15,7 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-fil
 # full captures: the advect stage (both variants), and the five Krylov kernels
 ncu --set full --clock-control none --import-source on -k regex:advect_stage -s 2 -c 2 -o $OUT/advect_$TAG -f \
     python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-e2e > $OUT/ncu_adv_$TAG.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:'k_pupdate|k_spmv|k_xr_update|k_final' -s 10 -c 5 -o $OUT/krylov_$TAG -f \
+ncu --set full --clock-control none --import-source on -k regex:'k_pupdate|k_spmv|k_r_update|k_final' -s 10 -c 5 -o $OUT/krylov_$TAG -f \
     python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-e2e > $OUT/ncu_kry_$TAG.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:'pressure_rhs|pressure_correct|umax' -s 3 -c 3 -o $OUT/press_$TAG -f \
     python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-e2e > $OUT/ncu_prs_$TAG.log 2>&1
