@@ -28,24 +28,46 @@ namespace cup2d {
 constexpr int NT = 256;
 constexpr int WPB = NT / 32;
 constexpr double EPS21 = 1e-21;    // cuda.cu:409
+#ifndef PRECOND_CTAS
+#define PRECOND_CTAS 4 // resident CTAs/SM of the two preconditioner kernels (latency-bound: occupancy matters)
+#endif
 
-__constant__ double cQ[64];  // Q[i*8+k]
-__constant__ double cIL[64]; // -1/(lambda_m + lambda_k)
+// Fast diagonalisation constants.  S[j][k] = sin((j+1)(k+1) pi/9) (DST-I of length 8) has only four distinct
+// magnitudes, so one transform is an even/odd split + two 4x4 products with zeros: 38 FP64 operations instead of
+// 64, and four constants that live in uniform registers (the dense 64-entry table needed one LDC per FMA and spilled).
+//   Q = sqrt(2/9) S,  Q^2 = I;   z = -(Q(x)Q) diag(1/(l_m+l_k)) (Q(x)Q) v = (S(x)S) [cIL .* ((S(x)S) v)]
+__constant__ double cS[4];   // sin(pi/9), sin(2pi/9), sin(3pi/9), sin(4pi/9)
+__constant__ double cIL[64]; // -(2/9)^2 / (lambda_m + lambda_k)
 
 static bool g_consts_ready = false;
 static int init_consts() {
   if (g_consts_ready) return CUP2D_OK;
-  double Q[64], IL[64], lam[8];
+  double S[4], IL[64], lam[8];
   const double pi = 3.14159265358979323846;
+  for (int k = 0; k < 4; k++) S[k] = std::sin((k + 1) * pi / 9.0);
   for (int k = 0; k < 8; k++) lam[k] = 2.0 - 2.0 * std::cos((k + 1) * pi / 9.0);
-  for (int i = 0; i < 8; i++)
-    for (int k = 0; k < 8; k++) Q[i * 8 + k] = std::sqrt(2.0 / 9.0) * std::sin((i + 1) * (k + 1) * pi / 9.0);
   for (int m = 0; m < 8; m++)
-    for (int k = 0; k < 8; k++) IL[m * 8 + k] = -1.0 / (lam[m] + lam[k]);
-  CUP2D_CUDA(cudaMemcpyToSymbol(cQ, Q, sizeof Q));
+    for (int k = 0; k < 8; k++) IL[m * 8 + k] = -(4.0 / 81.0) / (lam[m] + lam[k]);
+  CUP2D_CUDA(cudaMemcpyToSymbol(cS, S, sizeof S));
   CUP2D_CUDA(cudaMemcpyToSymbol(cIL, IL, sizeof IL));
   g_consts_ready = true;
   return CUP2D_OK;
+}
+
+// X[k] = sum_j x[j] sin((j+1)(k+1) pi/9).  sin((9-j')k' pi/9) = (-1)^(k'+1) sin(j'k' pi/9): odd modes see the
+// symmetric part u of the input, even modes the antisymmetric part w.
+__host__ __device__ __forceinline__ void dst8(const double (&x)[8], double (&X)[8], double a, double b, double c,
+                                              double d) {
+  const double u1 = x[0] + x[7], u2 = x[1] + x[6], u3 = x[2] + x[5], u4 = x[3] + x[4];
+  const double w1 = x[0] - x[7], w2 = x[1] - x[6], w3 = x[2] - x[5], w4 = x[3] - x[4];
+  X[0] = fma(d, u4, fma(c, u3, fma(b, u2, a * u1)));
+  X[2] = c * ((u1 + u2) - u4);
+  X[4] = fma(b, u4, fma(-c, u3, fma(-a, u2, d * u1)));
+  X[6] = fma(-a, u4, fma(c, u3, fma(-d, u2, b * u1)));
+  X[1] = fma(a, w4, fma(c, w3, fma(d, w2, b * w1)));
+  X[3] = fma(-b, w4, fma(-c, w3, fma(a, w2, d * w1)));
+  X[5] = c * ((w1 - w2) + w4);
+  X[7] = fma(-d, w4, fma(c, w3, fma(-b, w2, a * w1)));
 }
 
 // z_blk = P_inv v_blk for the block whose row `y` this lane holds (8 lanes = one block).
@@ -53,48 +75,26 @@ static int init_consts() {
 __device__ __forceinline__ void precond_row(double (&v)[8], double *sw, int lane) {
   const int y = lane & 7, bl = lane >> 3;
   double *sb = sw + bl * 72;
-  double a[8];
-#pragma unroll
-  for (int k = 0; k < 8; k++) {
-    double s = cQ[k] * v[0];
-#pragma unroll
-    for (int i = 1; i < 8; i++) s = fma(cQ[i * 8 + k], v[i], s);
-    a[k] = s;
-  }
+  const double sa = cS[0], sb_ = cS[1], sc = cS[2], sd = cS[3];
+  double a[8], b[8];
+  dst8(v, a, sa, sb_, sc, sd); // along x: lane = row y, a[k] = x-mode k
   __syncwarp();
 #pragma unroll
   for (int k = 0; k < 8; k++) sb[y * 9 + k] = a[k];
   __syncwarp();
-  double b[8];
 #pragma unroll
-  for (int yy = 0; yy < 8; yy++) b[yy] = sb[yy * 9 + y]; // lane now owns x-mode kx = y
+  for (int yy = 0; yy < 8; yy++) b[yy] = sb[yy * 9 + y]; // lane now owns x-mode kx = y, b[yy] over rows
+  dst8(b, a, sa, sb_, sc, sd);                            // along y: a[m] = y-mode m
 #pragma unroll
-  for (int m = 0; m < 8; m++) {
-    double s = cQ[m] * b[0];
-#pragma unroll
-    for (int yy = 1; yy < 8; yy++) s = fma(cQ[yy * 8 + m], b[yy], s);
-    a[m] = s * cIL[m * 8 + y];
-  }
-#pragma unroll
-  for (int yy = 0; yy < 8; yy++) {
-    double s = cQ[yy * 8] * a[0];
-#pragma unroll
-    for (int m = 1; m < 8; m++) s = fma(cQ[yy * 8 + m], a[m], s);
-    b[yy] = s;
-  }
+  for (int m = 0; m < 8; m++) a[m] *= cIL[m * 8 + y];
+  dst8(a, b, sa, sb_, sc, sd); // back along y
   __syncwarp();
 #pragma unroll
   for (int yy = 0; yy < 8; yy++) sb[yy * 9 + y] = b[yy];
   __syncwarp();
 #pragma unroll
   for (int k = 0; k < 8; k++) a[k] = sb[y * 9 + k];
-#pragma unroll
-  for (int i = 0; i < 8; i++) {
-    double s = cQ[i * 8] * a[0];
-#pragma unroll
-    for (int k = 1; k < 8; k++) s = fma(cQ[i * 8 + k], a[k], s);
-    v[i] = s;
-  }
+  dst8(a, v, sa, sb_, sc, sd); // back along x
 }
 
 __device__ __forceinline__ int next_buf(int cur, int opt) { return cur != opt ? 3 - cur - opt : (cur + 1) % 3; }
@@ -170,7 +170,7 @@ k_init(const double *__restrict__ b, const double *__restrict__ x0, double *__re
 }
 
 // ---- K1: p = r + beta (p - omega nu) ; z = M p    (cuda.cu:478-486) -------------------------------
-__global__ void __launch_bounds__(NT)
+__global__ void __launch_bounds__(NT, PRECOND_CTAS)
 k_pupdate(const double *__restrict__ r, double *__restrict__ rhat, double *__restrict__ p,
           const double *__restrict__ nu, double *__restrict__ z, int nrows,
           const KrylovState *__restrict__ st) {
@@ -255,7 +255,7 @@ k_spmv(const double *__restrict__ z, const double *__restrict__ d, double *__res
 }
 
 // ---- K3: r -= alpha nu ; z_r = M r     (cuda.cu:499-505; the x half-step of cuda.cu:498 happens in K5) ----------
-__global__ void __launch_bounds__(NT)
+__global__ void __launch_bounds__(NT, PRECOND_CTAS)
 k_r_update(double *__restrict__ r, const double *__restrict__ nu, double *__restrict__ zr, int nrows,
            const KrylovState *__restrict__ st) {
   __shared__ __align__(16) double s_scr[WPB * SCR1];

@@ -43,10 +43,11 @@ def load_library():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
-        raise Cup2dError(f"{LIB_PATH} not built: run `python -c 'import __graft_entry__ as g; g.build()'` "
+    path = os.environ.get("CUP2D_B200_LIB", LIB_PATH)  # override: an alternative build of the same ABI
+    if not os.path.exists(path):
+        raise Cup2dError(f"{path} not built: run `python -c 'import __graft_entry__ as g; g.build()'` "
                          "(there is no CPU fallback)")
-    lib = C.CDLL(LIB_PATH)
+    lib = C.CDLL(path)
     P, D, I, L = C.c_void_p, C.c_double, C.c_int, C.c_int64
     lib.cup2d_create.argtypes = [C.POINTER(Config), C.POINTER(P)]
     lib.cup2d_destroy.argtypes = [P]

@@ -15,6 +15,14 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a real B200 (run with -m gpu on the GPU box)")
 
 
+def pytest_collection_modifyitems(config, items):
+    """Tests that execute the reference's own GPU binaries (oracle/_ref/ref_harness_gpu: cuBLAS + cuSPARSE) go last:
+    on a freshly provisioned box the first load of those libraries has been seen to take minutes."""
+    slow = [it for it in items if "reference_driver" in it.name or "reference_amr" in it.name]
+    if slow:
+        items[:] = [it for it in items if it not in slow] + slow
+
+
 @pytest.fixture(scope="session")
 def golden_dir():
     return GOLDEN

@@ -31,14 +31,14 @@ def read_records(path):
     return recs
 
 
-def compare(nsteps=12, level_max=8, names=("ref_harness_gpu", "ref_harness_b200")):
+def compare(nsteps=12, level_max=8, names=("ref_harness_gpu", "ref_harness_b200"), timeout=None):
     out = {}
     with tempfile.TemporaryDirectory() as tmp:
         recs = {}
         for n in names:
             f = os.path.join(tmp, n + ".bin")
             subprocess.run([os.path.join(ROOT, "oracle", "_ref", n), "amr", str(level_max), str(nsteps), "1000", f],
-                           check=True, stderr=subprocess.DEVNULL, env=dict(os.environ, OMP_NUM_THREADS="8"))
+                           check=True, stderr=subprocess.DEVNULL, env=dict(os.environ, OMP_NUM_THREADS="8"), timeout=timeout)
             recs[n] = read_records(f)
     a, b = recs[names[0]], recs[names[1]]
     rows = []
