@@ -29,7 +29,7 @@ constexpr int NT = 256;
 constexpr int WPB = NT / 32;
 constexpr double EPS21 = 1e-21;    // cuda.cu:409
 #ifndef PRECOND_CTAS
-#define PRECOND_CTAS 4 // resident CTAs/SM of the two preconditioner kernels (latency-bound: occupancy matters)
+#define PRECOND_CTAS 3 // resident CTAs/SM of the two preconditioner kernels (3: 73-78 regs; 4 (64 regs) measured 2 % slower)
 #endif
 
 // Fast diagonalisation constants.  S[j][k] = sin((j+1)(k+1) pi/9) (DST-I of length 8) has only four distinct
