@@ -118,10 +118,10 @@ def gpu_visible():
         return False
 
 
-def run_harness_time(binary, level, reps, kiter, threads):
+def run_harness_time(binary, level, reps, kiter, threads, timeout=None):
     env = dict(os.environ, OMP_NUM_THREADS=str(threads), OMP_PROC_BIND="close")
     out = subprocess.run([binary, "time", str(level), str(reps), str(kiter)], env=env, check=True,
-                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True).stdout
+                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, timeout=timeout).stdout
     return json.loads(out.strip().splitlines()[-1])
 
 
@@ -131,7 +131,17 @@ def cpu_composite(level, reps, kiter):
     cuda.cu (cuSPARSE/cuBLAS, its only solver) when a GPU is visible, else the CPU restatement of it."""
     threads = os.cpu_count() or 1
     use_gpu = os.path.exists(HARNESS_GPU) and gpu_visible()
-    t = run_harness_time(HARNESS_GPU if use_gpu else HARNESS, level, reps, kiter, threads)
+    note = None
+    t = None
+    if use_gpu:
+        # bounded: on a freshly provisioned box the first load of cuBLAS/cuSPARSE by the reference binary has been
+        # seen to take minutes; the bench line must not wait for that
+        try:
+            t = run_harness_time(HARNESS_GPU, level, reps, kiter, threads, timeout=120)
+        except (subprocess.TimeoutExpired, subprocess.CalledProcessError) as e:
+            note = f"reference GPU solver binary unavailable in time ({type(e).__name__}); Poisson iterations timed on the CPU restatement"
+    if t is None:
+        t = run_harness_time(HARNESS, level, reps, kiter, threads, timeout=600)
     step_s = 2 * t["t_stage"] + t["t_rhs"] + kiter * t["t_poisson_iter"] + t["t_correct"]
     val = t["cells"] * (2 + kiter) / step_s / 1e6
     N = t["N"]
@@ -145,6 +155,7 @@ def cpu_composite(level, reps, kiter):
         "stage_Mcells_s": t["cells"] / t["t_stage"] / 1e6,
         "poisson_iter_Mcells_s": t["cells"] / t["t_poisson_iter"] / 1e6 if t["t_poisson_iter"] > 0 else None,
         "poisson_solver": t.get("poisson_solver"),
+        **({"note": note} if note else {}),
     }
 
 
