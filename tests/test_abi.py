@@ -64,3 +64,23 @@ def test_block_order_rectangular_matches_reference_golden(golden_dir, bx, by, lv
     """non-regular space-filling curve (bounding square not filled, main.cpp:6358-6376)"""
     g = np.load(os.path.join(golden_dir, f"order_{bx}x{by}_L{lvl}.npy"))
     assert np.array_equal(cup2d_b200.block_order(bx, by, lvl), g)
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the driver's reference arm) on a tiny sample: one JSON line with the contract keys.
+    Uses oracle/_ref/ref_harness (CPU): skipped where the reference was not compiled."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if not os.path.exists(os.path.join(root, "oracle", "_ref", "ref_harness")):
+        pytest.skip("oracle/_ref/ref_harness not built")
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--cpu-level", "4",
+                          "--steps", "3", "--warmup", "1"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True,
+                         timeout=300, env=dict(os.environ, CUDA_VISIBLE_DEVICES=""), check=True).stdout
+    line = json.loads(out.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "Mcell-updates/s" and line["higher_is_better"] is True
+    assert line["value"] > 0 and line["cpu_baseline"]["kind"] == "reference" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"] == {"value": line["value"], "unit": line["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    for k in ("metric", "n_gpus", "steps", "warmup", "ms_per_step", "scaling", "dtype", "data", "config"):
+        assert k in line

@@ -125,7 +125,7 @@ def worker(rank, world, port, level, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,level", [(2, 3), (2, 4), (4, 3)])
+@pytest.mark.parametrize("world,level", [(2, 3), (2, 4), (4, 3), (3, 2), (8, 3)])  # 3: uneven SFC ranges; 8: the node size
 def test_halo_plan_two_and_four_ranks_gloo(world, level):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
