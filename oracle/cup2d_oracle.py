@@ -168,11 +168,11 @@ def derivative(U, um3, um2, um1, u, up1, up2, up3):
 # --------------------------------------------------------------------------------------------
 # Operators
 # --------------------------------------------------------------------------------------------
-def advect_diffuse(u, v, h, nu, dt):
-    """KernelAdvectDiffuse::operator() (main.cpp:5441-5503): undivided RHS written to tmpV."""
+def advect_diffuse_padded(up, vp, h, nu, dt):
+    """KernelAdvectDiffuse::operator() (main.cpp:5441-5503) on fields that already carry their 3 ghost layers
+    (shape (NY + 6, NX + 6)): the undivided RHS of the NY x NX interior."""
     g = 3
-    NY, NX = u.shape
-    up, vp = pad_vector(u, v, g)
+    NY, NX = up.shape[0] - 2 * g, up.shape[1] - 2 * g
     dfac = nu * dt
     afac = -dt * h
 
@@ -182,6 +182,7 @@ def advect_diffuse(u, v, h, nu, dt):
     def sy(a, k):  # a(ix, iy+k)
         return a[g + k:g + k + NY, g:g + NX]
 
+    u, v = sx(up, 0), sx(vp, 0)
     dudx = derivative(u, sx(up, -3), sx(up, -2), sx(up, -1), u, sx(up, 1), sx(up, 2), sx(up, 3))
     dudy = derivative(v, sy(up, -3), sy(up, -2), sy(up, -1), u, sy(up, 1), sy(up, 2), sy(up, 3))
     dvdx = derivative(u, sx(vp, -3), sx(vp, -2), sx(vp, -1), v, sx(vp, 1), sx(vp, 2), sx(vp, 3))
@@ -189,6 +190,12 @@ def advect_diffuse(u, v, h, nu, dt):
     tu = afac * (u * dudx + v * dudy) + dfac * (sx(up, 1) + sx(up, -1) + sy(up, 1) + sy(up, -1) - 4 * u)
     tv = afac * (u * dvdx + v * dvdy) + dfac * (sx(vp, 1) + sx(vp, -1) + sy(vp, 1) + sy(vp, -1) - 4 * v)
     return tu, tv
+
+
+def advect_diffuse(u, v, h, nu, dt):
+    """KernelAdvectDiffuse on a uniform grid: free-slip wall ghosts, then the kernel."""
+    up, vp = pad_vector(u, v, 3)
+    return advect_diffuse_padded(up, vp, h, nu, dt)
 
 
 def compute_dt(u, v, h, nu, cfl):

@@ -35,6 +35,15 @@
 //        tag 2 (once per step, shape 0's hook): u, v before penalisation (2 N^2)
 //        tag 3 (at main.cpp:7138, i.e. after penalisation + solve, before the correction): per shape (u, v, omega),
 //              then u, v after penalisation, tmpV = summed udef (2 N^2), chi field (N^2)
+//   ref_harness amrlab levelMax nsteps out.bin
+//        the run.sh case for nsteps steps (so that the mesh is genuinely multi-level), then seeded fields on that mesh
+//        and the reference's own ghost assembly + operators on them (round-2 groundwork);
+//        record stream [tag, n, n doubles]:  10: nu, dt, h0, bpdx, bpdy, levelMax   11: (level,i,j) per block
+//        12: vel blocks (128/block)  13: pres = pold blocks  14: chi blocks  15: udef blocks (128/block)
+//        20: VectorLab of vel, stencil {-3,-3,4,4,tensorial} (14*14*2/block)   21: VectorLab of vel {-1,-1,2,2} (10*10*2)
+//        22: ScalarLab of pres {-1,-1,2,2} (10*10)
+//        30: tmpV after KernelAdvectDiffuse + flux correction   31: tmp after pressure_rhs (+fc)
+//        32: tmp after pressure_rhs1 (+fc)   33: tmpV after pressureCorrectionKernel (+fc)
 //   ref_harness steps L nu cfl nsteps kiter in.bin out.bin
 //        in : as above (udef ignored: no shapes => udef = 0, chi = 0 ; p = initial pres)
 //        out: per step: dt, then u v p  b x   (1 + 5 N^2 doubles), b/x = Poisson rhs / solution
@@ -55,7 +64,7 @@ extern int cup2d_ref_force_iters;
 extern int cup2d_ref_fixed_iters;
 
 namespace {
-enum Mode { ORDER, OPS, STEPS, TIME, AMR, VORT, TAGS, DUMP, PENAL } g_mode;
+enum Mode { ORDER, OPS, STEPS, TIME, AMR, VORT, TAGS, DUMP, PENAL, AMRLAB } g_mode;
 int g_sum7 = 0, g_sum2 = 0, g_step = 0;
 int g_extra = 0;
 double g_rtol = 0, g_time = 0;
@@ -309,6 +318,84 @@ static void put_fields(double tag, std::initializer_list<std::pair<Grid *, int>>
   }
   put(tag, head);
 }
+// ---- amrlab: ghost assembly and operators of the reference on a real multi-level mesh -----------------------------
+template <class LabT, int DIM> struct DumpLab { // a "kernel" that only copies the assembled lab out
+  Stencil stencil;
+  std::vector<double> *out;
+  int nm;
+  DumpLab(Stencil st, std::vector<double> *o) : stencil(st), out(o), nm(_BS_ + st.ex - st.sx - 1) {}
+  void operator()(LabT *lab, const Info *info) const {
+    const size_t n = (size_t)nm * nm * DIM;
+    memcpy(out->data() + (size_t)info->id * n, lab->m, n * sizeof(double));
+  }
+};
+static double seeded(int level, int i, int j, int ix, int iy, int comp, double x, double y) {
+  // smooth part + a deterministic per-cell perturbation (so that an indexing error cannot hide behind smoothness)
+  unsigned long long k = (((((unsigned long long)level * 4099 + i) * 4099 + j) * 67 + ix) * 67 + iy) * 7 + comp;
+  k ^= k >> 33; k *= 0xff51afd7ed558ccdULL; k ^= k >> 33; k *= 0xc4ceb9fe1a85ec53ULL; k ^= k >> 33;
+  const double noise = (double)(k >> 11) / 9007199254740992.0 - 0.5;
+  const double s = comp == 0 ? sin(1.3 * x + 0.4) * cos(2.1 * y) : comp == 1 ? cos(0.9 * x) * sin(1.7 * y + 0.2)
+                 : comp == 2 ? cos(1.1 * x - 0.3) * cos(0.8 * y) : comp == 3 ? 0.5 + 0.5 * sin(2.0 * x) * sin(1.5 * y)
+                 : comp == 4 ? 0.3 * sin(3 * x + y) : 0.2 * cos(2 * y - x);
+  return s + 0.05 * noise;
+}
+static void seed_grid(Grid *g, int dim, int comp0) {
+  for (auto &info : g->infos)
+    for (int iy = 0; iy < _BS_; iy++)
+      for (int ix = 0; ix < _BS_; ix++)
+        for (int c = 0; c < dim; c++)
+          info.block[dim * (_BS_ * iy + ix) + c] =
+              seeded(info.level, info.index[0], info.index[1], ix, iy, comp0 + c, info.origin[0] + info.h * (ix + 0.5),
+                     info.origin[1] + info.h * (iy + 0.5));
+}
+static void put_blocks(double tag, Grid *g, int dim) {
+  std::vector<double> v;
+  for (auto &info : g->infos) v.insert(v.end(), info.block, info.block + dim * _BS_ * _BS_);
+  put(tag, v);
+}
+static void do_amrlab() {
+  g_fout = fopen(g_out.c_str(), "wb");
+  sim.dt = 1e-3; // fixed, so that the operator outputs do not depend on the flow the mesh was grown with
+  put(10, {sim.nu, sim.dt, sim.h0, (double)sim.bpdx, (double)sim.bpdy, (double)sim.levelMax});
+  std::vector<double> mesh;
+  for (auto &info : var.vel->infos) { mesh.push_back(info.level); mesh.push_back(info.index[0]); mesh.push_back(info.index[1]); }
+  put(11, mesh);
+  seed_grid(var.vel, 2, 0);
+  seed_grid(var.pres, 1, 2);
+  seed_grid(var.pold, 1, 2);
+  seed_grid(var.chi, 1, 3);
+  put_blocks(12, var.vel, 2);
+  put_blocks(13, var.pres, 1);
+  put_blocks(14, var.chi, 1);
+  const size_t nb = var.vel->infos.size();
+  {
+    std::vector<double> lab(nb * 14 * 14 * 2);
+    computeA<VectorLab>(DumpLab<VectorLab, 2>(Stencil{-3, -3, 4, 4, true}, &lab), var.vel, 2);
+    put(20, lab);
+  }
+  {
+    std::vector<double> lab(nb * 10 * 10 * 2);
+    computeA<VectorLab>(DumpLab<VectorLab, 2>(Stencil{-1, -1, 2, 2, false}, &lab), var.vel, 2);
+    put(21, lab);
+  }
+  {
+    std::vector<double> lab(nb * 10 * 10);
+    computeA<ScalarLab>(DumpLab<ScalarLab, 1>(Stencil{-1, -1, 2, 2, false}, &lab), var.pres, 1);
+    put(22, lab);
+  }
+  call_advect();
+  put_blocks(30, var.tmpV, 2);
+  seed_grid(var.tmpV, 2, 4); // u_def
+  put_blocks(15, var.tmpV, 2);
+  call_rhs();
+  put_blocks(31, var.tmp, 1);
+  call_rhs1();
+  put_blocks(32, var.tmp, 1);
+  call_gradp();
+  put_blocks(33, var.tmpV, 2);
+  fclose(g_fout);
+}
+
 static void penal_hook(int op, void *buf, int count) {
   const int S = (int)sim.shapes.size();
   if (op == MPI_MAX && count == 1) { // dt of a new step (main.cpp:6592)
@@ -354,6 +441,12 @@ static void penal_hook(int op, void *buf, int count) {
 
 void cup2d_ref_hook(int op, void *buf, int count) {
   if (g_mode == PENAL) { penal_hook(op, buf, count); return; }
+  if (g_mode == AMRLAB) {
+    if (op != MPI_MAX || count != 1) return;
+    if (g_calls++ < g_nsteps) return; // let the reference run nsteps steps first
+    do_amrlab();
+    exit(0);
+  }
   if (op != MPI_MAX || count != 1) return;
   const int call = g_calls++;
   if (g_mode == ORDER) { do_order(); exit(0); }
@@ -456,6 +549,18 @@ int main(int argc, char **argv) {
     char a_lmax[16];
     snprintf(a_lmax, sizeof a_lmax, "%d", g_L);
     // run.sh:1-22 verbatim except levelMax (argument) and tdump 0 (no output files)
+    const char *args[] = {"ref_main", "-AdaptSteps", "20", "-bpdx", "2", "-bpdy", "1", "-CFL", "0.5", "-Ctol", "1",
+                          "-extent", "4", "-lambda", "1e7", "-levelMax", a_lmax, "-levelStart", "5",
+                          "-maxPoissonIterations", "1000", "-maxPoissonRestarts", "0", "-nu", "0.00004",
+                          "-poissonTol", "1e-3", "-poissonTolRel", "1e-2", "-Rtol", "2", "-tdump", "0", "-tend", "10.0",
+                          "-shapes", "angle=0 L=0.2 xpos=1.8 ypos=0.8\n angle=180 L=0.2 xpos=1.6 ypos=0.8"};
+    return ref_main(sizeof args / sizeof *args, (char **)args);
+  }
+  else if (mode == "amrlab" && argc == 5) {
+    g_mode = AMRLAB; g_nsteps = atoi(argv[3]); g_out = argv[4];
+    cup2d_ref_force_iters = 5;
+    char a_lmax[16];
+    snprintf(a_lmax, sizeof a_lmax, "%d", g_L);
     const char *args[] = {"ref_main", "-AdaptSteps", "20", "-bpdx", "2", "-bpdy", "1", "-CFL", "0.5", "-Ctol", "1",
                           "-extent", "4", "-lambda", "1e7", "-levelMax", a_lmax, "-levelStart", "5",
                           "-maxPoissonIterations", "1000", "-maxPoissonRestarts", "0", "-nu", "0.00004",

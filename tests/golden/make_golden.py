@@ -229,6 +229,32 @@ def load_penal(path):
     return int(d["L"]), steps
 
 
+def gen_amrlab(tmp, level_max, nsteps):
+    """ghost assembly + the four operators of the reference on its own multi-level run.sh mesh:
+    mesh, seeded inputs, flux-corrected outputs for every block and the assembled labs of every second block"""
+    fout = os.path.join(tmp, "amrlab.bin")
+    subprocess.run([HARNESS, "amrlab", str(level_max), str(nsteps), fout], check=True, stderr=subprocess.DEVNULL,
+                   stdout=subprocess.DEVNULL, env=dict(os.environ, OMP_NUM_THREADS="1"))
+    a = np.fromfile(fout)
+    i, rec = 0, {}
+    while i < len(a):
+        tag, n = int(a[i]), int(a[i + 1])
+        rec[tag] = a[i + 2:i + 2 + n]
+        i += 2 + n
+    nu, dt, h0, bpdx, bpdy, lmax = rec[10]
+    blocks = rec[11].reshape(-1, 3).astype(np.int32)
+    nb = len(blocks)
+    sub = np.arange(0, nb, 2)
+    np.savez_compressed(
+        os.path.join(HERE, f"amrlab_lmax{level_max}.npz"), nu=nu, dt=dt, h0=h0, bpdx=int(bpdx), bpdy=int(bpdy),
+        blocks=blocks, vel=rec[12].reshape(nb, 8, 8, 2), pres=rec[13].reshape(nb, 8, 8, 1),
+        chi=rec[14].reshape(nb, 8, 8, 1), udef=rec[15].reshape(nb, 8, 8, 2), lab_blocks=sub,
+        lab_vel3=rec[20].reshape(nb, 14, 14, 2)[sub], lab_vel1=rec[21].reshape(nb, 10, 10, 2)[sub],
+        lab_pres1=rec[22].reshape(nb, 10, 10, 1)[sub], adv=rec[30].reshape(nb, 8, 8, 2),
+        rhs=rec[31].reshape(nb, 8, 8, 1), rhs1=rec[32].reshape(nb, 8, 8, 1), gradp=rec[33].reshape(nb, 8, 8, 2))
+    print("amrlab", nb, "blocks, levels", sorted(set(blocks[:, 0].tolist())))
+
+
 def gen_steps(tmp, kind, L, seed, nu, cfl, nsteps, kiter):
     N = 8 << L
     ins = make_inputs(kind, L, seed)
@@ -257,6 +283,7 @@ if __name__ == "__main__":
         gen_tags(tmp, "L3_coarser", 3, 4245, 3.0, 1, [(0.7, 0.3, 0.1), (0.99, 0.01, 0.04), (0.26, 0.76, 0.015)])
         gen_dump(tmp, 2, 4246, 0.1875)
         gen_penal(tmp, 4, 4, [2, 3])
+        gen_amrlab(tmp, 8, 3)
         gen_ops(tmp, "random", 2, 1234, 1e-3, 2.5e-3)
         gen_ops(tmp, "tg", 3, 4321, 1e-3, 1.2e-3)
         gen_steps(tmp, "tg", 2, 777, 1e-3, 0.5, 3, 12)
