@@ -1,0 +1,48 @@
+"""ctypes view of the host-side AMR ghost-stencil plan (cup2d_amr_plan_*, include/cup2d_b200.h).  No compute here:
+the tables are built by the C++ library; this only hands them out as numpy arrays."""
+import ctypes as C
+
+import numpy as np
+
+from . import lib as _l
+
+LAB_SHAPES = {0: (14, 14, 2), 1: (10, 10, 2), 2: (10, 10, 1)}
+
+
+class AmrPlan:
+    def __init__(self, level_ij, bpdx, bpdy):
+        self.lib = _l.load_library()
+        self.blocks = np.ascontiguousarray(level_ij, dtype=np.int32).reshape(-1, 3)
+        self._h = C.c_void_p()
+        _l.check(self.lib.cup2d_amr_plan_create(len(self.blocks), self.blocks.ctypes.data_as(C.POINTER(C.c_int32)),
+                                                bpdx, bpdy, C.byref(self._h)))
+
+    def stencil(self, which):
+        """CSR (rowptr, src_block, src_cellcomp, weight) of lab kind `which`; rows = (block, iy, ix, comp)"""
+        nnz = self.lib.cup2d_amr_plan_stencil(self._h, which, None, None, None, None)
+        if nnz < 0:
+            _l.check(int(nnz))
+        ny, nx, dim = LAB_SHAPES[which]
+        rowptr = np.empty(len(self.blocks) * ny * nx * dim + 1, dtype=np.int64)
+        sb, sc, w = np.empty(nnz, dtype=np.int32), np.empty(nnz, dtype=np.int32), np.empty(nnz)
+        self.lib.cup2d_amr_plan_stencil(self._h, which, rowptr.ctypes.data_as(C.POINTER(C.c_int64)),
+                                        sb.ctypes.data_as(C.POINTER(C.c_int32)), sc.ctypes.data_as(C.POINTER(C.c_int32)),
+                                        w.ctypes.data_as(C.POINTER(C.c_double)))
+        return rowptr, sb, sc, w
+
+    def faces(self):
+        n = self.lib.cup2d_amr_plan_faces(self._h, None)
+        out = np.empty((n, 5), dtype=np.int32)
+        self.lib.cup2d_amr_plan_faces(self._h, out.ctypes.data_as(C.POINTER(C.c_int32)))
+        return out
+
+    def close(self):
+        if self._h:
+            self.lib.cup2d_amr_plan_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

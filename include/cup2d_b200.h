@@ -182,6 +182,25 @@ int64_t cup2d_launch_count(const cup2d_sim *s);
 int cup2d_profile_enable(cup2d_sim *s, int on);
 int cup2d_profile_read(cup2d_sim *s, int max_entries, char *names, double *total_ms, int64_t *launches);
 
+/* ---- multi-level (block-AMR) meshes: ghost-stencil plan, host-only (no GPU needed) --------------------------------
+ * The reference assembles the ghost cells of a block next to coarser / finer blocks by interpolation and averaging
+ * (BlockLab::load / post_load, main.cpp:2247-2933).  Every such ghost is a fixed linear combination of owned cells, so
+ * the plan evaluates that assembly once per regrid on symbolic values and returns it as CSR tables for the tile loaders.
+ * level_ij[k] = (level, i, j) of block k in `infos` order; bpdx, bpdy = level-0 blocks per direction. */
+typedef struct cup2d_amr_plan cup2d_amr_plan;
+int cup2d_amr_plan_create(int64_t nblocks, const int32_t *level_ij, int32_t bpdx, int32_t bpdy, cup2d_amr_plan **out);
+void cup2d_amr_plan_destroy(cup2d_amr_plan *p);
+/* which: 0 = velocity lab of the advect stencil {-3,-3,4,4,tensorial} (14x14x2 per block), 1 = velocity lab of the
+ * +-1 stencil (10x10x2), 2 = scalar lab of the +-1 stencil (10x10).  Rows = (block, iy, ix, comp) in that order; row r
+ * is sum_e weight[e] * field[src_block[e]][src_cellcomp[e]] (cell*dim + comp of the source block).  A row without
+ * entries is a lab cell the reference never writes (corner ghosts of the non-tensorial stencils).  Returns nnz; any
+ * output pointer may be NULL (call once to size, once to fill; rowptr has nrows + 1 entries). */
+int64_t cup2d_amr_plan_stencil(cup2d_amr_plan *p, int which, int64_t *rowptr, int32_t *src_block, int32_t *src_cellcomp,
+                               double *weight);
+/* coarse-fine faces for the flux correction (prepare0, main.cpp:1683-1735): records of 5 int32 = (fine block, its face,
+ * coarse block, its face, which half of the coarse face); faces 0 = x-, 1 = x+, 2 = y-, 3 = y+.  Returns the count. */
+int64_t cup2d_amr_plan_faces(cup2d_amr_plan *p, int32_t *out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,107 @@
+"""CPU tests of the host-side AMR ghost-stencil plan (cup2d_b200/csrc/amr_plan.cpp through the C ABI): the CSR tables,
+applied to the seeded fields of the reference's own 7-level mesh, must reproduce the labs the unmodified reference
+assembled (tests/golden/amrlab_lmax8.npz) and, fed through the operators, its flux-corrected results."""
+import os
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+import cup2d_amr_oracle as amr
+from cup2d_b200.amr import AmrPlan, LAB_SHAPES
+
+
+@pytest.fixture(scope="module")
+def setup(golden_dir):
+    d = np.load(os.path.join(golden_dir, "amrlab_lmax8.npz"))
+    plan = AmrPlan(d["blocks"], int(d["bpdx"]), int(d["bpdy"]))
+    yield d, plan
+    plan.close()
+
+
+def apply(plan, which, field):
+    """lab[k, iy, ix, d] = table . field;  unwritten cells -> NaN"""
+    rowptr, sb, sc, w = plan.stencil(which)
+    ny, nx, dim = LAB_SHAPES[which]
+    nb = len(plan.blocks)
+    cols = sb.astype(np.int64) * (64 * dim) + sc
+    T = sp.csr_matrix((w, cols, rowptr), shape=(nb * ny * nx * dim, nb * 64 * dim))
+    lab = (T @ field.reshape(-1)).reshape(nb, ny, nx, dim)
+    empty = (np.diff(rowptr) == 0).reshape(nb, ny, nx, dim)
+    lab[empty] = np.nan
+    return lab
+
+
+@pytest.mark.parametrize("which,name,fieldname", [(2, "lab_pres1", "pres"), (1, "lab_vel1", "vel"), (0, "lab_vel3", "vel")])
+def test_ghost_stencil_tables_reproduce_reference_labs(setup, which, name, fieldname):
+    d, plan = setup
+    lab = apply(plan, which, d[fieldname])
+    got = lab[d["lab_blocks"]]
+    want = d[name]
+    written = ~np.isnan(got)
+    scale = np.abs(want).max()
+    assert np.abs(got[written] - want[written]).max() < 1e-13 * scale
+    g = 3 if which == 0 else 1
+    if which == 0:
+        assert written.all()
+    else:  # everything but the four corner ghosts of the cross-shaped stencils
+        assert written[:, g:-g, :, :].all() and written[:, :, g:-g, :].all()
+    # interior rows are the identity
+    assert np.array_equal(got[:, g:g + 8, g:g + 8, :], d[fieldname][d["lab_blocks"]])
+
+
+def test_tables_are_small_and_mostly_copies(setup):
+    d, plan = setup
+    rowptr, sb, sc, w = plan.stencil(0)
+    per_row = np.diff(rowptr)
+    assert per_row.max() <= 64              # the widest ghost (Taylor from 3x3 coarse cells that are 2x2 averages)
+    assert (per_row == 1).mean() > 0.6      # interior + same-level copies + wall ghosts
+
+
+def test_flux_correction_faces_match_oracle(setup):
+    d, plan = setup
+    mesh = amr.Mesh(d["blocks"], int(d["bpdx"]), int(d["bpdy"]))
+    faces = plan.faces()
+    want = []
+    for k, (level, I, J) in enumerate(mesh.blocks):
+        st = amr.face_states(mesh, k)
+        for f, (cx, cy) in enumerate(amr.FACE_CODES):
+            if st[f] == "coarse":
+                want.append((k, f, mesh.index[(level - 1, (I + cx) // 2, (J + cy) // 2)], f ^ 1, (J % 2) if cx else (I % 2)))
+    assert sorted(map(tuple, faces.tolist())) == sorted(want) and len(want) > 50
+
+
+def test_operators_on_table_labs_match_reference(setup):
+    """the advect kernel of the oracle fed with labs from the TABLES (not from the oracle's own assembly) + the oracle's
+    flux correction reproduces the reference's flux-corrected tmpV to rounding"""
+    import cup2d_oracle as orc
+    d, plan = setup
+    mesh = amr.Mesh(d["blocks"], int(d["bpdx"]), int(d["bpdy"]))
+    nu, dt, h0 = float(d["nu"]), float(d["dt"]), float(d["h0"])
+    lab = apply(plan, 0, d["vel"])
+    nb = len(mesh.blocks)
+    adv = np.empty((nb, 8, 8, 2))
+    faces = []
+    for k in range(nb):
+        m = lab[k]
+        h = h0 / (1 << mesh.blocks[k][0])
+        adv[k, :, :, 0], adv[k, :, :, 1] = orc.advect_diffuse_padded(m[:, :, 0], m[:, :, 1], h, nu, dt)
+        st = amr.face_states(mesh, k)
+        c = m[3:11, 3:11]
+        fl = [nu * dt * (c[:, 0] - m[3:11, 2]), nu * dt * (c[:, 7] - m[3:11, 11]), nu * dt * (c[0, :] - m[2, 3:11]),
+              nu * dt * (c[7, :] - m[11, 3:11])]
+        faces.append([fl[f] if st[f] in ("coarse", "fine") else None for f in range(4)])
+    amr.flux_correct(mesh, adv, faces, 2)
+    assert np.abs(adv - d["adv"]).max() < 1e-12 * np.abs(d["adv"]).max()
+
+
+def test_plan_rejects_bad_meshes():
+    from cup2d_b200 import Cup2dError
+    with pytest.raises(Cup2dError):
+        AmrPlan([[0, 0, 0], [0, 0, 0]], 1, 1)          # duplicate block
+    with pytest.raises(Cup2dError):
+        AmrPlan([[1, 2, 0]], 1, 1)                     # outside the domain
+    # level 0 next to level 2: more than one level apart
+    blocks = [[0, 0, 0]] + [[2, 4 + i, j] for i in range(4) for j in range(4)]
+    with pytest.raises(Cup2dError):
+        AmrPlan(blocks, 2, 1)
