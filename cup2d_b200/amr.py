@@ -30,6 +30,26 @@ class AmrPlan:
                                         w.ctypes.data_as(C.POINTER(C.c_double)))
         return rowptr, sb, sc, w
 
+    def irregular(self):
+        n = self.lib.cup2d_amr_plan_irregular(self._h, None)
+        out = np.empty(n, dtype=np.int32)
+        self.lib.cup2d_amr_plan_irregular(self._h, out.ctypes.data_as(C.POINTER(C.c_int32)))
+        return out
+
+    def ghosts(self, which):
+        """compact CSR over the ghost cells of the irregular blocks: (rowptr, dst, src_block, src_cellcomp, weight)"""
+        nrows = C.c_int64()
+        nnz = self.lib.cup2d_amr_plan_ghosts(self._h, which, C.byref(nrows), None, None, None, None, None)
+        if nnz < 0:
+            _l.check(int(nnz))
+        rowptr = np.empty(nrows.value + 1, dtype=np.int64)
+        dst, sb, sc, w = (np.empty(nrows.value, dtype=np.int32), np.empty(nnz, dtype=np.int32),
+                          np.empty(nnz, dtype=np.int32), np.empty(nnz))
+        ip = C.POINTER(C.c_int32)
+        self.lib.cup2d_amr_plan_ghosts(self._h, which, None, rowptr.ctypes.data_as(C.POINTER(C.c_int64)), dst.ctypes.data_as(ip),
+                                       sb.ctypes.data_as(ip), sc.ctypes.data_as(ip), w.ctypes.data_as(C.POINTER(C.c_double)))
+        return rowptr, dst, sb, sc, w
+
     def faces(self):
         n = self.lib.cup2d_amr_plan_faces(self._h, None)
         out = np.empty((n, 5), dtype=np.int32)

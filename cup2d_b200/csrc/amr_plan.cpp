@@ -20,6 +20,7 @@
 #include <cstring>
 #include <map>
 #include <string>
+#include <thread>
 #include <vector>
 
 namespace cup2d {
@@ -389,8 +390,17 @@ struct LabBuilder {
 };
 } // namespace
 
+struct GhostTable { // compact form: ghost rows of irregular blocks only
+  std::vector<int64_t> rowptr;
+  std::vector<int32_t> dst, src_block, src_cc; // dst = (position in the irregular list * ncell + lab cell) * dim + comp
+  std::vector<double> w;
+  bool built = false;
+};
+
 struct cup2d_amr_plan {
   Mesh mesh;
+  std::vector<int32_t> irregular; // blocks with a coarser or finer block among their 8 neighbours
+  GhostTable ghosts[3];
   // CSR per stencil kind: rows = (block, iy, ix, comp)
   std::vector<int64_t> rowptr[3];
   std::vector<int32_t> src_block[3], src_cc[3]; // source block, source cell*dim + comp
@@ -420,6 +430,54 @@ static void build(cup2d_amr_plan *p, int which) {
     }
   }
   p->built[which] = true;
+}
+
+// ghost rows (every lab cell outside the 8x8 interior) of the irregular blocks; blocks are independent
+static void build_ghosts(cup2d_amr_plan *p, int which) {
+  GhostTable &g = p->ghosts[which];
+  const int n = (int)p->irregular.size();
+  struct Part { std::vector<int64_t> len; std::vector<int32_t> dst, sb, sc; std::vector<double> w; };
+  std::vector<Part> parts(n);
+  auto work = [&](int t, int nt) { // blocks are independent: interleaved static partition over plain threads
+    LabBuilder lb(p->mesh, which);
+    for (int q = t; q < n; q += nt) {
+      lb.load(p->irregular[q]);
+      Part &pt = parts[q];
+      for (int iy = lb.sy; iy < BS + lb.ey - 1; iy++)
+        for (int ix = lb.sx; ix < BS + lb.ex - 1; ix++) {
+          if (ix >= 0 && ix < BS && iy >= 0 && iy < BS) continue;
+          for (int d = 0; d < lb.dim; d++) {
+            const LC &row = lb.M(ix, iy, d);
+            if (!row.set) continue;
+            int64_t cnt = 0;
+            for (auto &t2 : row.t) {
+              if (t2.second == 0.0) continue;
+              pt.sb.push_back((int32_t)(t2.first / (64 * lb.dim)));
+              pt.sc.push_back((int32_t)(t2.first % (64 * lb.dim)));
+              pt.w.push_back(t2.second);
+              cnt++;
+            }
+            pt.len.push_back(cnt);
+            pt.dst.push_back((int32_t)((((int64_t)q * lb.nmy + (iy - lb.sy)) * lb.nmx + (ix - lb.sx)) * lb.dim + d));
+          }
+        }
+    }
+  };
+  int nt = (int)std::thread::hardware_concurrency();
+  nt = std::max(1, std::min({nt, 32, n / 64 + 1}));
+  std::vector<std::thread> pool;
+  for (int t = 1; t < nt; t++) pool.emplace_back(work, t, nt);
+  work(0, nt);
+  for (auto &th : pool) th.join();
+  g.rowptr.assign(1, 0);
+  for (auto &pt : parts) {
+    for (auto c : pt.len) g.rowptr.push_back(g.rowptr.back() + c);
+    g.dst.insert(g.dst.end(), pt.dst.begin(), pt.dst.end());
+    g.src_block.insert(g.src_block.end(), pt.sb.begin(), pt.sb.end());
+    g.src_cc.insert(g.src_cc.end(), pt.sc.begin(), pt.sc.end());
+    g.w.insert(g.w.end(), pt.w.begin(), pt.w.end());
+  }
+  g.built = true;
 }
 
 extern "C" {
@@ -459,11 +517,42 @@ int cup2d_amr_plan_create(int64_t nblocks, const int32_t *level_ij, int32_t bpdx
       p->faces.insert(p->faces.end(), rec, rec + 5);
     }
   }
+  for (int64_t k = 0; k < nblocks; k++) {
+    const int l = level_ij[3 * k], i = level_ij[3 * k + 1], j = level_ij[3 * k + 2];
+    bool irr = false;
+    for (int c = 0; c < 9 && !irr; c++) {
+      const int ni = i + c % 3 - 1, nj = j + c / 3 - 1;
+      if (c == 4 || ni < 0 || nj < 0 || ni >= (bpdx << l) || nj >= (bpdy << l)) continue;
+      irr = p->mesh.state(l, ni, nj) < 0;
+    }
+    if (irr) p->irregular.push_back((int32_t)k);
+  }
   *out = p;
   return CUP2D_OK;
 }
 
 void cup2d_amr_plan_destroy(cup2d_amr_plan *p) { delete p; }
+
+int64_t cup2d_amr_plan_irregular(cup2d_amr_plan *p, int32_t *out) {
+  if (!p) return CUP2D_EINVAL;
+  if (out) memcpy(out, p->irregular.data(), p->irregular.size() * sizeof(int32_t));
+  return (int64_t)p->irregular.size();
+}
+
+int64_t cup2d_amr_plan_ghosts(cup2d_amr_plan *p, int which, int64_t *nrows, int64_t *rowptr, int32_t *dst, int32_t *src_block,
+                              int32_t *src_cellcomp, double *weight) {
+  if (!p || which < 0 || which > 2) return CUP2D_EINVAL;
+  GhostTable &g = p->ghosts[which];
+  if (!g.built) build_ghosts(p, which);
+  const int64_t nnz = (int64_t)g.w.size();
+  if (nrows) *nrows = (int64_t)g.dst.size();
+  if (rowptr) memcpy(rowptr, g.rowptr.data(), g.rowptr.size() * sizeof(int64_t));
+  if (dst) memcpy(dst, g.dst.data(), g.dst.size() * sizeof(int32_t));
+  if (src_block) memcpy(src_block, g.src_block.data(), nnz * sizeof(int32_t));
+  if (src_cellcomp) memcpy(src_cellcomp, g.src_cc.data(), nnz * sizeof(int32_t));
+  if (weight) memcpy(weight, g.w.data(), nnz * sizeof(double));
+  return nnz;
+}
 
 int64_t cup2d_amr_plan_stencil(cup2d_amr_plan *p, int which, int64_t *rowptr, int32_t *src_block, int32_t *src_cellcomp,
                                double *weight) {

@@ -197,6 +197,14 @@ void cup2d_amr_plan_destroy(cup2d_amr_plan *p);
  * output pointer may be NULL (call once to size, once to fill; rowptr has nrows + 1 entries). */
 int64_t cup2d_amr_plan_stencil(cup2d_amr_plan *p, int which, int64_t *rowptr, int32_t *src_block, int32_t *src_cellcomp,
                                double *weight);
+/* Compact form for the device.  irregular = blocks that have a coarser or finer block among their 8 neighbours (all
+ * other blocks get their ghosts from same-level copies and wall reflections alone).  ghosts: CSR over the ghost cells
+ * (everything outside the 8x8 interior) of the irregular blocks only; dst[r] = ((position of the block in the irregular
+ * list * ncell_lab + lab cell) * dim + comp) with the lab shapes of cup2d_amr_plan_stencil.  Returns nnz, *nrows rows.
+ * Blocks are independent: built on several host threads. */
+int64_t cup2d_amr_plan_irregular(cup2d_amr_plan *p, int32_t *blocks_out);
+int64_t cup2d_amr_plan_ghosts(cup2d_amr_plan *p, int which, int64_t *nrows, int64_t *rowptr, int32_t *dst,
+                              int32_t *src_block, int32_t *src_cellcomp, double *weight);
 /* coarse-fine faces for the flux correction (prepare0, main.cpp:1683-1735): records of 5 int32 = (fine block, its face,
  * coarse block, its face, which half of the coarse face); faces 0 = x-, 1 = x+, 2 = y-, 3 = y+.  Returns the count. */
 int64_t cup2d_amr_plan_faces(cup2d_amr_plan *p, int32_t *out);

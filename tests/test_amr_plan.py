@@ -105,3 +105,54 @@ def test_plan_rejects_bad_meshes():
     blocks = [[0, 0, 0]] + [[2, 4 + i, j] for i in range(4) for j in range(4)]
     with pytest.raises(Cup2dError):
         AmrPlan(blocks, 2, 1)
+
+
+def balanced_disc_mesh(l0, lmax, bpdx=1, bpdy=1):
+    """synthetic 2:1-balanced mesh: level l0 everywhere, refined level by level toward a circle"""
+    blocks = {(l0, i, j) for i in range(bpdx << l0) for j in range(bpdy << l0)}
+    for L in range(l0, lmax):
+        n = 1 << L
+        want = {b for b in blocks if b[0] == L and abs(np.hypot((b[1] + 0.5) / n - 0.5 * bpdx, (b[2] + 0.5) / n - 0.5 * bpdy) - 0.3) < 1.5 / n}
+        # ripple: a block may only be refined if all its neighbours are at its level or finer
+        changed = True
+        while changed:
+            changed = False
+            for (l, i, j) in list(want):
+                for di in (-1, 0, 1):
+                    for dj in (-1, 0, 1):
+                        a, b = i + di, j + dj
+                        if 0 <= a < (bpdx << l) and 0 <= b < (bpdy << l) and (l, a, b) not in blocks:
+                            par = (l - 1, a >> 1, b >> 1)
+                            if par in blocks:        # coarser neighbour: it has to be refined first -> skip this one
+                                want.discard((l, i, j))
+                                changed = True
+        for (l, i, j) in want:
+            blocks.discard((l, i, j))
+            blocks.update({(l + 1, 2 * i + a, 2 * j + b) for a in (0, 1) for b in (0, 1)})
+    return np.array(sorted(blocks), dtype=np.int32)
+
+
+def test_compact_ghost_tables_equal_full_rows_and_scale():
+    """the compact tables (ghost rows of irregular blocks, built on several host threads) are exactly the corresponding
+    rows of the full tables, on a synthetic mesh of a few thousand blocks"""
+    import time
+    blocks = balanced_disc_mesh(4, 8)
+    assert len(blocks) > 1500 and len(set(blocks[:, 0].tolist())) >= 4
+    plan = AmrPlan(blocks, 1, 1)
+    irr = plan.irregular()
+    assert 0 < len(irr) < len(blocks)
+    for which in (0, 2):
+        ny, nx, dim = LAB_SHAPES[which]
+        t0 = time.time()
+        rp, dst, sb, sc, w = plan.ghosts(which)
+        t_compact = time.time() - t0
+        frp, fsb, fsc, fw = plan.stencil(which)
+        ncell = ny * nx * dim
+        q, rem = np.divmod(dst, ncell)
+        full_rows = irr[q].astype(np.int64) * ncell + rem
+        assert np.array_equal(np.diff(rp), frp[full_rows + 1] - frp[full_rows])
+        take = np.concatenate([np.arange(frp[r], frp[r + 1]) for r in full_rows[:4000]])
+        n = len(take)
+        assert np.array_equal(sb[:n], fsb[take]) and np.array_equal(sc[:n], fsc[take]) and np.array_equal(w[:n], fw[take])
+        assert t_compact < 20.0
+    plan.close()
