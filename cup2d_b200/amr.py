@@ -50,6 +50,16 @@ class AmrPlan:
                                        sb.ctypes.data_as(ip), sc.ctypes.data_as(ip), w.ctypes.data_as(C.POINTER(C.c_double)))
         return rowptr, dst, sb, sc, w
 
+    def stats(self, which):
+        a, b = C.c_int32(), C.c_int32()
+        _l.check(self.lib.cup2d_amr_plan_stats(self._h, which, C.byref(a), C.byref(b)))
+        return {"patterns": a.value, "fallbacks": b.value}
+
+    def neighbours(self):
+        out = np.empty((len(self.blocks), 8), dtype=np.int32)
+        _l.check(self.lib.cup2d_amr_plan_neighbours(self._h, out.ctypes.data_as(C.POINTER(C.c_int32))))
+        return out
+
     def faces(self):
         n = self.lib.cup2d_amr_plan_faces(self._h, None)
         out = np.empty((n, 5), dtype=np.int32)

@@ -394,6 +394,7 @@ struct GhostTable { // compact form: ghost rows of irregular blocks only
   std::vector<int64_t> rowptr;
   std::vector<int32_t> dst, src_block, src_cc; // dst = (position in the irregular list * ncell + lab cell) * dim + comp
   std::vector<double> w;
+  int npatterns = 0, fallbacks = 0;
   bool built = false;
 };
 
@@ -432,50 +433,179 @@ static void build(cup2d_amr_plan *p, int which) {
   p->built[which] = true;
 }
 
-// ghost rows (every lab cell outside the 8x8 interior) of the irregular blocks; blocks are independent
+// ---- compact ghost tables -----------------------------------------------------------------------------------------
+// The ghost stencil of a block depends on its surroundings only through a small local configuration: the state of its
+// 8 neighbour positions (same level / wall / coarser / finer, and which of the blocks involved exist), the parity of
+// its index (which quadrant of its parent it is) and which domain walls it touches.  Blocks with the same configuration
+// share one PATTERN — the ghost rows with sources named relative to the block (level offset, block offset) — which is
+// evaluated symbolically once (about 2 ms) and then instantiated per block by looking the relative blocks up (microseconds).
+struct Pattern {
+  std::vector<int64_t> len;
+  std::vector<int32_t> cell, ref, sc; // cell = lab cell * dim + comp; ref indexes `refs`
+  std::vector<double> w;
+  std::vector<std::array<int, 3>> refs; // (level offset, di, dj) relative to (I,J), (I>>1,J>>1) or (2I,2J)
+};
+
+static std::vector<int> config_key(const Mesh &m, int k) {
+  const int l = m.lij[3 * k], I = m.lij[3 * k + 1], J = m.lij[3 * k + 2];
+  const int NX = m.bpdx << l, NY = m.bpdy << l;
+  std::vector<int> key = {I & 1, J & 1, I == 0, I == NX - 1, J == 0, J == NY - 1, l == 0};
+  for (int c = 0; c < 9; c++) {
+    if (c == 4) continue;
+    const int cx = c % 3 - 1, cy = c / 3 - 1, ni = I + cx, nj = J + cy;
+    if (ni < 0 || nj < 0 || ni >= NX || nj >= NY) { key.push_back(9); continue; }
+    const int st = m.state(l, ni, nj);
+    if (st >= 0) key.push_back(0);
+    else if (st == -2) key.push_back(m.find(l - 1, ni >> 1, nj >> 1) >= 0 ? 1 : 2);
+    else { // finer: which of the (up to two) children that touch this block exist one level down
+      int mask = 0;
+      const int ac0 = abs(cx), ac1 = abs(cy);
+      for (int B = 0; B < 2; B++) {
+        const int aux = ac0 == 1 ? (B % 2) : (B / 2);
+        if (m.find(l + 1, 2 * I + std::max(cx, 0) + cx + (B % 2) * std::max(0, 1 - ac0),
+                   2 * J + std::max(cy, 0) + cy + aux * std::max(0, 1 - ac1)) >= 0)
+          mask |= 1 << B;
+      }
+      // faces look at B = 0..3 but only two distinct children exist in 2-D; corners at one child
+      for (int B = 2; B < 4; B++) {
+        const int aux = ac0 == 1 ? (B % 2) : (B / 2);
+        if (m.find(l + 1, 2 * I + std::max(cx, 0) + cx + (B % 2) * std::max(0, 1 - ac0),
+                   2 * J + std::max(cy, 0) + cy + aux * std::max(0, 1 - ac1)) >= 0)
+          mask |= 1 << B;
+      }
+      key.push_back(16 + mask);
+    }
+  }
+  return key;
+}
+
+static Pattern make_pattern(LabBuilder &lb, const Mesh &m, int k) {
+  Pattern pt;
+  const int l = m.lij[3 * k], I = m.lij[3 * k + 1], J = m.lij[3 * k + 2];
+  std::map<int, int> refidx;
+  lb.load(k);
+  for (int iy = lb.sy; iy < BS + lb.ey - 1; iy++)
+    for (int ix = lb.sx; ix < BS + lb.ex - 1; ix++) {
+      if (ix >= 0 && ix < BS && iy >= 0 && iy < BS) continue;
+      for (int d = 0; d < lb.dim; d++) {
+        const LC &row = lb.M(ix, iy, d);
+        if (!row.set) continue;
+        int64_t cnt = 0;
+        for (auto &t : row.t) {
+          if (t.second == 0.0) continue;
+          const int blk = (int)(t.first / (64 * lb.dim));
+          auto it = refidx.find(blk);
+          if (it == refidx.end()) {
+            const int bl = m.lij[3 * blk], bi = m.lij[3 * blk + 1], bj = m.lij[3 * blk + 2];
+            const int dl = bl - l;
+            const int base_i = dl == 0 ? I : (dl < 0 ? I >> 1 : 2 * I), base_j = dl == 0 ? J : (dl < 0 ? J >> 1 : 2 * J);
+            it = refidx.emplace(blk, (int)pt.refs.size()).first;
+            pt.refs.push_back({dl, bi - base_i, bj - base_j});
+          }
+          pt.ref.push_back(it->second);
+          pt.sc.push_back((int32_t)(t.first % (64 * lb.dim)));
+          pt.w.push_back(t.second);
+          cnt++;
+        }
+        pt.len.push_back(cnt);
+        pt.cell.push_back((int32_t)((((iy - lb.sy)) * lb.nmx + (ix - lb.sx)) * lb.dim + d));
+      }
+    }
+  return pt;
+}
+
 static void build_ghosts(cup2d_amr_plan *p, int which) {
   GhostTable &g = p->ghosts[which];
+  const Mesh &m = p->mesh;
   const int n = (int)p->irregular.size();
-  struct Part { std::vector<int64_t> len; std::vector<int32_t> dst, sb, sc; std::vector<double> w; };
-  std::vector<Part> parts(n);
-  auto work = [&](int t, int nt) { // blocks are independent: interleaved static partition over plain threads
-    LabBuilder lb(p->mesh, which);
+  LabBuilder lb0(m, which);
+  const int ncell = lb0.nmx * lb0.nmy * lb0.dim;
+  // 1. dictionary of local configurations (serial: a few dozen patterns even on large meshes)
+  std::map<std::vector<int>, int> dict;
+  std::vector<Pattern> patterns;
+  std::vector<int> pat_of(n);
+  for (int q = 0; q < n; q++) {
+    auto key = config_key(m, p->irregular[q]);
+    auto it = dict.find(key);
+    if (it == dict.end()) {
+      it = dict.emplace(key, (int)patterns.size()).first;
+      patterns.push_back(make_pattern(lb0, m, p->irregular[q]));
+    }
+    pat_of[q] = it->second;
+  }
+  g.npatterns = (int)patterns.size();
+  // 2. instantiate per block (independent: interleaved static partition over plain threads)
+  std::vector<std::vector<int32_t>> ids(n);
+  std::vector<char> okv(n, 1);
+  auto resolve = [&](int t, int nt) {
     for (int q = t; q < n; q += nt) {
-      lb.load(p->irregular[q]);
-      Part &pt = parts[q];
-      for (int iy = lb.sy; iy < BS + lb.ey - 1; iy++)
-        for (int ix = lb.sx; ix < BS + lb.ex - 1; ix++) {
-          if (ix >= 0 && ix < BS && iy >= 0 && iy < BS) continue;
-          for (int d = 0; d < lb.dim; d++) {
-            const LC &row = lb.M(ix, iy, d);
-            if (!row.set) continue;
-            int64_t cnt = 0;
-            for (auto &t2 : row.t) {
-              if (t2.second == 0.0) continue;
-              pt.sb.push_back((int32_t)(t2.first / (64 * lb.dim)));
-              pt.sc.push_back((int32_t)(t2.first % (64 * lb.dim)));
-              pt.w.push_back(t2.second);
-              cnt++;
-            }
-            pt.len.push_back(cnt);
-            pt.dst.push_back((int32_t)((((int64_t)q * lb.nmy + (iy - lb.sy)) * lb.nmx + (ix - lb.sx)) * lb.dim + d));
-          }
-        }
+      const int k = p->irregular[q];
+      const int l = m.lij[3 * k], I = m.lij[3 * k + 1], J = m.lij[3 * k + 2];
+      const Pattern &pt = patterns[pat_of[q]];
+      ids[q].resize(pt.refs.size());
+      for (size_t r = 0; r < pt.refs.size(); r++) {
+        const int dl = pt.refs[r][0];
+        const int bi = (dl == 0 ? I : (dl < 0 ? I >> 1 : 2 * I)) + pt.refs[r][1], bj = (dl == 0 ? J : (dl < 0 ? J >> 1 : 2 * J)) + pt.refs[r][2];
+        const int id = m.find(l + dl, bi, bj);
+        if (id < 0) okv[q] = 0;
+        ids[q][r] = id;
+      }
     }
   };
   int nt = (int)std::thread::hardware_concurrency();
-  nt = std::max(1, std::min({nt, 32, n / 64 + 1}));
-  std::vector<std::thread> pool;
-  for (int t = 1; t < nt; t++) pool.emplace_back(work, t, nt);
-  work(0, nt);
-  for (auto &th : pool) th.join();
-  g.rowptr.assign(1, 0);
-  for (auto &pt : parts) {
-    for (auto c : pt.len) g.rowptr.push_back(g.rowptr.back() + c);
-    g.dst.insert(g.dst.end(), pt.dst.begin(), pt.dst.end());
-    g.src_block.insert(g.src_block.end(), pt.sb.begin(), pt.sb.end());
-    g.src_cc.insert(g.src_cc.end(), pt.sc.begin(), pt.sc.end());
-    g.w.insert(g.w.end(), pt.w.begin(), pt.w.end());
+  nt = std::max(1, std::min({nt, 32, n / 256 + 1}));
+  {
+    std::vector<std::thread> pool;
+    for (int t = 1; t < nt; t++) pool.emplace_back(resolve, t, nt);
+    resolve(0, nt);
+    for (auto &th : pool) th.join();
+  }
+  // 3. assemble.  A block whose relative blocks could not all be found is evaluated directly (never seen; kept as a net).
+  std::map<int, Pattern> own;
+  g.fallbacks = 0;
+  for (int q = 0; q < n; q++)
+    if (!okv[q]) {
+      Pattern &o = own[q] = make_pattern(lb0, m, p->irregular[q]);
+      const int k = p->irregular[q];
+      const int l = m.lij[3 * k], I = m.lij[3 * k + 1], J = m.lij[3 * k + 2];
+      ids[q].resize(o.refs.size());
+      for (size_t r = 0; r < o.refs.size(); r++) {
+        const int dl = o.refs[r][0];
+        ids[q][r] = m.find(l + dl, (dl == 0 ? I : (dl < 0 ? I >> 1 : 2 * I)) + o.refs[r][1], (dl == 0 ? J : (dl < 0 ? J >> 1 : 2 * J)) + o.refs[r][2]);
+      }
+      g.fallbacks++;
+    }
+  auto pat = [&](int q) -> const Pattern & { return okv[q] ? patterns[pat_of[q]] : own.at(q); };
+  std::vector<int64_t> row0(n + 1, 0), nnz0(n + 1, 0);
+  for (int q = 0; q < n; q++) {
+    row0[q + 1] = row0[q] + (int64_t)pat(q).len.size();
+    nnz0[q + 1] = nnz0[q] + (int64_t)pat(q).w.size();
+  }
+  g.rowptr.resize(row0[n] + 1);
+  g.dst.resize(row0[n]);
+  g.src_block.resize(nnz0[n]);
+  g.src_cc.resize(nnz0[n]);
+  g.w.resize(nnz0[n]);
+  g.rowptr[0] = 0;
+  auto fill = [&](int t, int nthr) {
+    for (int q = t; q < n; q += nthr) {
+      const Pattern &pt = pat(q);
+      int64_t at = nnz0[q];
+      for (size_t r = 0; r < pt.len.size(); r++) {
+        at += pt.len[r];
+        g.rowptr[row0[q] + r + 1] = at;
+        g.dst[row0[q] + r] = (int32_t)((int64_t)q * ncell + pt.cell[r]);
+      }
+      for (size_t e = 0; e < pt.w.size(); e++) g.src_block[nnz0[q] + e] = ids[q][pt.ref[e]];
+      memcpy(g.src_cc.data() + nnz0[q], pt.sc.data(), pt.sc.size() * sizeof(int32_t));
+      memcpy(g.w.data() + nnz0[q], pt.w.data(), pt.w.size() * sizeof(double));
+    }
+  };
+  {
+    std::vector<std::thread> pool;
+    for (int t = 1; t < nt; t++) pool.emplace_back(fill, t, nt);
+    fill(0, nt);
+    for (auto &th : pool) th.join();
   }
   g.built = true;
 }
@@ -564,6 +694,37 @@ int64_t cup2d_amr_plan_stencil(cup2d_amr_plan *p, int which, int64_t *rowptr, in
   if (src_cellcomp) memcpy(src_cellcomp, p->src_cc[which].data(), nnz * sizeof(int32_t));
   if (weight) memcpy(weight, p->w[which].data(), nnz * sizeof(double));
   return nnz;
+}
+
+/* bookkeeping of the last cup2d_amr_plan_ghosts(which): distinct local configurations, directly evaluated blocks */
+int cup2d_amr_plan_stats(cup2d_amr_plan *p, int which, int32_t *npatterns, int32_t *fallbacks) {
+  if (!p || which < 0 || which > 2 || !p->ghosts[which].built) return CUP2D_EINVAL;
+  if (npatterns) *npatterns = p->ghosts[which].npatterns;
+  if (fallbacks) *fallbacks = p->ghosts[which].fallbacks;
+  return CUP2D_OK;
+}
+
+/* the 8 neighbour positions of every block, order (-1,-1),(0,-1),(1,-1),(-1,0),(1,0),(-1,1),(0,1),(1,1):
+ * >= 0 same-level block, -1 domain wall, -2 covered by a coarser block, -3 refined further */
+int cup2d_amr_plan_neighbours(cup2d_amr_plan *p, int32_t *out) {
+  if (!p || !out) return CUP2D_EINVAL;
+  const Mesh &m = p->mesh;
+  const int64_t n = (int64_t)m.lij.size() / 3;
+  for (int64_t k = 0; k < n; k++) {
+    const int l = m.lij[3 * k], I = m.lij[3 * k + 1], J = m.lij[3 * k + 2];
+    int q = 0;
+    for (int c = 0; c < 9; c++) {
+      if (c == 4) continue;
+      const int ni = I + c % 3 - 1, nj = J + c / 3 - 1;
+      int v = -1;
+      if (ni >= 0 && nj >= 0 && ni < (m.bpdx << l) && nj < (m.bpdy << l)) {
+        const int st = m.state(l, ni, nj);
+        v = st >= 0 ? st : (st == -2 ? -2 : -3);
+      }
+      out[8 * k + q++] = v;
+    }
+  }
+  return CUP2D_OK;
 }
 
 int64_t cup2d_amr_plan_faces(cup2d_amr_plan *p, int32_t *out) {

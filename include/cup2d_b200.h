@@ -205,6 +205,12 @@ int64_t cup2d_amr_plan_stencil(cup2d_amr_plan *p, int which, int64_t *rowptr, in
 int64_t cup2d_amr_plan_irregular(cup2d_amr_plan *p, int32_t *blocks_out);
 int64_t cup2d_amr_plan_ghosts(cup2d_amr_plan *p, int which, int64_t *nrows, int64_t *rowptr, int32_t *dst,
                               int32_t *src_block, int32_t *src_cellcomp, double *weight);
+/* ghost tables are instantiated from a dictionary of local configurations (blocks with the same neighbourhood share one
+ * symbolically evaluated pattern); after cup2d_amr_plan_ghosts(which): how many patterns, how many blocks bypassed it */
+int cup2d_amr_plan_stats(cup2d_amr_plan *p, int which, int32_t *npatterns, int32_t *fallbacks);
+/* out[k][8]: the 8 neighbour positions of block k in the order (-1,-1),(0,-1),(1,-1),(-1,0),(1,0),(-1,1),(0,1),(1,1):
+ * >= 0 same-level block, -1 domain wall, -2 covered by a coarser block, -3 refined further (the regular-ghost fast path) */
+int cup2d_amr_plan_neighbours(cup2d_amr_plan *p, int32_t *out);
 /* coarse-fine faces for the flux correction (prepare0, main.cpp:1683-1735): records of 5 int32 = (fine block, its face,
  * coarse block, its face, which half of the coarse face); faces 0 = x-, 1 = x+, 2 = y-, 3 = y+.  Returns the count. */
 int64_t cup2d_amr_plan_faces(cup2d_amr_plan *p, int32_t *out);

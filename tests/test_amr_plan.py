@@ -156,3 +156,26 @@ def test_compact_ghost_tables_equal_full_rows_and_scale():
         assert np.array_equal(sb[:n], fsb[take]) and np.array_equal(sc[:n], fsc[take]) and np.array_equal(w[:n], fw[take])
         assert t_compact < 20.0
     plan.close()
+
+
+def test_pattern_dictionary_and_neighbour_table(setup):
+    d, plan = setup
+    plan.ghosts(0)
+    st = plan.stats(0)
+    assert st["fallbacks"] == 0 and 10 < st["patterns"] < len(plan.irregular())
+    mesh = amr.Mesh(d["blocks"], int(d["bpdx"]), int(d["bpdy"]))
+    nb = plan.neighbours()
+    codes = [(-1, -1), (0, -1), (1, -1), (-1, 0), (1, 0), (-1, 1), (0, 1), (1, 1)]
+    irregular = []
+    for k, (l, I, J) in enumerate(mesh.blocks):
+        NX, NY = mesh.bpdx << l, mesh.bpdy << l
+        for q, (cx, cy) in enumerate(codes):
+            if not (0 <= I + cx < NX and 0 <= J + cy < NY):
+                want = -1
+            else:
+                s = mesh.state(l, I + cx, J + cy)
+                want = s if s >= 0 else (-2 if s == -2 else -3)
+            assert nb[k, q] == want
+        if (nb[k] < -1).any():
+            irregular.append(k)
+    assert irregular == plan.irregular().tolist()
