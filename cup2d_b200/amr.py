@@ -76,3 +76,40 @@ class AmrPlan:
             self.close()
         except Exception:
             pass
+
+
+class AmrSimulation:
+    """ctypes view of cup2d_amr (csrc/amr_ops.cu): the first device path for multi-level meshes.  NOT YET VALIDATED ON
+    HARDWARE — see include/cup2d_b200.h."""
+
+    def __init__(self, level_ij, bpdx, bpdy, h0, nu, device=0):
+        self.lib = _l.load_library()
+        self.blocks = np.ascontiguousarray(level_ij, dtype=np.int32).reshape(-1, 3)
+        self._h = C.c_void_p()
+        _l.check(self.lib.cup2d_amr_create(len(self.blocks), self.blocks.ctypes.data_as(C.POINTER(C.c_int32)), bpdx, bpdy,
+                                           float(h0), float(nu), device, C.byref(self._h)))
+
+    def upload(self, name, blocks):
+        a = np.ascontiguousarray(blocks, dtype=np.float64)
+        _l.check(self.lib.cup2d_amr_field_upload(self._h, _l.FIELDS[name], a.ctypes.data_as(C.c_void_p)))
+
+    def download(self, name):
+        f = _l.FIELDS[name]
+        dim = 2 if name in ("vel", "vold", "tmpV") else 1
+        out = np.empty((len(self.blocks), 8, 8, dim))
+        _l.check(self.lib.cup2d_amr_field_download(self._h, f, out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def advect_diffuse_rhs(self, dt):
+        _l.check(self.lib.cup2d_amr_advect_diffuse_rhs(self._h, float(dt)))
+
+    def pressure_rhs(self, dt, with_laplacian=True):
+        _l.check(self.lib.cup2d_amr_pressure_rhs(self._h, float(dt), int(with_laplacian)))
+
+    def pressure_gradient(self, dt):
+        _l.check(self.lib.cup2d_amr_pressure_gradient(self._h, float(dt)))
+
+    def close(self):
+        if self._h:
+            self.lib.cup2d_amr_destroy(self._h)
+            self._h = C.c_void_p()

@@ -1,0 +1,430 @@
+// Stencil operators on multi-level (block-AMR) meshes — FIRST, CORRECTNESS-ORIENTED DEVICE PATH.
+//
+// STATUS: compiled and wired to the C ABI (cup2d_amr_*), NOT YET RUN ON HARDWARE: written after the round's GPU budget was
+// spent.  Its GPU tests (tests/test_gpu_amr.py) are skipped unless CUP2D_TEST_UNVALIDATED=1; nothing in bench.py or the
+// validated paths calls into this file.  See DESIGN.md 7.1 for the plan this is step 0 of.
+//
+// Shape (deliberately the simplest thing that can be compared with the reference, not the fast design):
+//   1. lab = T . field : the ghost-stencil tables of the host plan (csrc/amr_plan.cpp) applied as a CSR gather into a
+//      lab buffer in global memory (one lab per block: 14x14x2 for the advect stencil, 10x10x{2,1} for the +-1 stencils);
+//   2. one thread per cell evaluates the operator from its block's lab, in the reference's own expression order
+//      (KernelAdvectDiffuse main.cpp:5441-5503 with weno5_plus/minus main.cpp:162-208 in division form; pressure_rhs
+//      main.cpp:6105-6139; pressure_rhs1 main.cpp:6209-6230; pressureCorrectionKernel main.cpp:6021-6043);
+//   3. flux correction per coarse face (fillcases, main.cpp:1763-1849): the coarse block's own face flux plus the
+//      pairwise sums of the two fine blocks' face fluxes, all recomputed from the labs, added to the coarse cells next to
+//      the face — x faces first, then y faces, and for vector fields the second pass over the upper part of the face
+//      that the reference's fillcase1 performs (property 3).  The pressure-gradient update is not
+//      corrected (property 4).
+#include "sim.h"
+#include <algorithm>
+#include <map>
+#include <vector>
+
+struct cup2d_amr_plan;
+struct cup2d_amr;
+extern "C" {
+void cup2d_amr_destroy(cup2d_amr *a);
+int cup2d_amr_plan_create(int64_t nblocks, const int32_t *level_ij, int32_t bpdx, int32_t bpdy, cup2d_amr_plan **out);
+void cup2d_amr_plan_destroy(cup2d_amr_plan *p);
+int64_t cup2d_amr_plan_stencil(cup2d_amr_plan *p, int which, int64_t *rowptr, int32_t *src_block, int32_t *src_cellcomp,
+                               double *weight);
+int64_t cup2d_amr_plan_faces(cup2d_amr_plan *p, int32_t *out);
+}
+
+namespace cup2d {
+
+struct Csr {
+  int64_t *rowptr = nullptr;
+  int *src_block = nullptr, *src_cc = nullptr;
+  double *w = nullptr;
+  int64_t nrows = 0;
+};
+struct CoarseFace { // one coarse-fine face seen from the coarse side
+  int coarse, face, fine[2]; // fine[half] = the fine block abutting that half of the face (-1: absent)
+};
+
+} // namespace cup2d
+
+struct cup2d_amr {
+  int64_t nb = 0;
+  int device = 0;
+  double h0 = 0, nu = 0;
+  cup2d_amr_plan *plan = nullptr;
+  cudaStream_t stream = nullptr;
+  double *f[CUP2D_NFIELDS] = {};
+  double *d_h = nullptr;            // cell size per block
+  cup2d::Csr csr[3];
+  double *lab[3] = {};              // lab buffers (kinds 0, 1, 2); a second kind-1 buffer for u_def
+  double *lab_udef = nullptr;
+  cup2d::CoarseFace *d_cf[2] = {};  // [0] x faces, [1] y faces
+  int ncf[2] = {0, 0};
+};
+
+namespace cup2d {
+
+constexpr int LABN[3] = {14, 10, 10}, LABD[3] = {2, 2, 1}, LABG[3] = {3, 1, 1};
+
+__global__ void amr_gather_kernel(Csr t, const double *__restrict__ field, double *__restrict__ lab, int dim) {
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < t.nrows; r += (int64_t)gridDim.x * blockDim.x) {
+    double acc = 0.0;
+    for (int64_t e = t.rowptr[r]; e < t.rowptr[r + 1]; e++)
+      acc += t.w[e] * field[(int64_t)t.src_block[e] * 64 * dim + t.src_cc[e]];
+    lab[r] = acc;
+  }
+}
+
+// ---- WENO5 in the reference's own form (main.cpp:162-208) -----------------------------------------------------------
+__device__ __forceinline__ void betas(double um2, double um1, double u, double up1, double up2, double &b1, double &b2,
+                                      double &b3) {
+  const double a1 = (um2 + u) - 2 * um1, c1 = (um2 + 3 * u) - 4 * um1;
+  const double a2 = (um1 + up1) - 2 * u, c2 = um1 - up1;
+  const double a3 = (u + up2) - 2 * up1, c3 = (3 * u + up2) - 4 * up1;
+  b1 = 13.0 / 12.0 * (a1 * a1) + 0.25 * (c1 * c1);
+  b2 = 13.0 / 12.0 * (a2 * a2) + 0.25 * (c2 * c2);
+  b3 = 13.0 / 12.0 * (a3 * a3) + 0.25 * (c3 * c3);
+}
+__device__ __forceinline__ double weno_plus(double um2, double um1, double u, double up1, double up2) {
+  const double e = 1e-6;
+  double b1, b2, b3;
+  betas(um2, um1, u, up1, up2, b1, b2, b3);
+  const double w1 = 0.1 / ((b1 + e) * (b1 + e)), w2 = 0.6 / ((b2 + e) * (b2 + e)), w3 = 0.3 / ((b3 + e) * (b3 + e));
+  const double aux = 1.0 / ((w1 + w3) + w2);
+  const double f1 = (11.0 / 6.0) * u + ((1.0 / 3.0) * um2 - (7.0 / 6.0) * um1);
+  const double f2 = (5.0 / 6.0) * u + ((-1.0 / 6.0) * um1 + (1.0 / 3.0) * up1);
+  const double f3 = (1.0 / 3.0) * u + ((+5.0 / 6.0) * up1 - (1.0 / 6.0) * up2);
+  return ((w1 * aux) * f1 + (w3 * aux) * f3) + (w2 * aux) * f2;
+}
+__device__ __forceinline__ double weno_minus(double um2, double um1, double u, double up1, double up2) {
+  const double e = 1e-6;
+  double b1, b2, b3;
+  betas(um2, um1, u, up1, up2, b1, b2, b3);
+  const double w1 = 0.3 / ((b1 + e) * (b1 + e)), w2 = 0.6 / ((b2 + e) * (b2 + e)), w3 = 0.1 / ((b3 + e) * (b3 + e));
+  const double aux = 1.0 / ((w1 + w3) + w2);
+  const double f1 = (1.0 / 3.0) * u + ((-1.0 / 6.0) * um2 + (5.0 / 6.0) * um1);
+  const double f2 = (5.0 / 6.0) * u + ((1.0 / 3.0) * um1 - (1.0 / 6.0) * up1);
+  const double f3 = (11.0 / 6.0) * u + ((-7.0 / 6.0) * up1 + (1.0 / 3.0) * up2);
+  return ((w1 * aux) * f1 + (w3 * aux) * f3) + (w2 * aux) * f2;
+}
+__device__ __forceinline__ double derivative(double U, double um3, double um2, double um1, double u, double up1, double up2,
+                                             double up3) {
+  if (U > 0) return weno_plus(um2, um1, u, up1, up2) - weno_plus(um3, um2, um1, u, up1);
+  return weno_minus(um1, u, up1, up2, up3) - weno_minus(um2, um1, u, up1, up2);
+}
+
+// lab accessors: L0 = 14x14x2 (ghost 3), L1 = 10x10x2 (ghost 1), L2 = 10x10 (ghost 1); (ix, iy) block-relative
+__device__ __forceinline__ double L0(const double *lab, int64_t k, int ix, int iy, int c) {
+  return lab[((k * 14 + (iy + 3)) * 14 + (ix + 3)) * 2 + c];
+}
+__device__ __forceinline__ double L1(const double *lab, int64_t k, int ix, int iy, int c) {
+  return lab[((k * 10 + (iy + 1)) * 10 + (ix + 1)) * 2 + c];
+}
+__device__ __forceinline__ double L2(const double *lab, int64_t k, int ix, int iy) {
+  return lab[(k * 10 + (iy + 1)) * 10 + (ix + 1)];
+}
+
+__global__ void amr_advect_kernel(const double *__restrict__ lab, double *__restrict__ out, const double *__restrict__ hb,
+                                  int64_t ncells, double nu, double dt) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < ncells; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t k = i >> 6;
+    const int ix = (int)(i & 7), iy = (int)((i >> 3) & 7);
+    const double h = hb[k], dfac = nu * dt, afac = -dt * h;
+    auto U = [&](int dx, int dy) { return L0(lab, k, ix + dx, iy + dy, 0); };
+    auto V = [&](int dx, int dy) { return L0(lab, k, ix + dx, iy + dy, 1); };
+    const double u = U(0, 0), v = V(0, 0);
+    const double dudx = derivative(u, U(-3, 0), U(-2, 0), U(-1, 0), u, U(1, 0), U(2, 0), U(3, 0));
+    const double dudy = derivative(v, U(0, -3), U(0, -2), U(0, -1), u, U(0, 1), U(0, 2), U(0, 3));
+    const double dvdx = derivative(u, V(-3, 0), V(-2, 0), V(-1, 0), v, V(1, 0), V(2, 0), V(3, 0));
+    const double dvdy = derivative(v, V(0, -3), V(0, -2), V(0, -1), v, V(0, 1), V(0, 2), V(0, 3));
+    out[2 * i] = afac * (u * dudx + v * dudy) + dfac * ((((U(1, 0) + U(-1, 0)) + U(0, 1)) + U(0, -1)) - 4 * u);
+    out[2 * i + 1] = afac * (u * dvdx + v * dvdy) + dfac * ((((V(1, 0) + V(-1, 0)) + V(0, 1)) + V(0, -1)) - 4 * v);
+  }
+}
+
+__global__ void amr_div_kernel(const double *__restrict__ labv, const double *__restrict__ labu,
+                               const double *__restrict__ chi, double *__restrict__ tmp, const double *__restrict__ hb,
+                               int64_t ncells, double dt) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < ncells; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t k = i >> 6;
+    const int ix = (int)(i & 7), iy = (int)((i >> 3) & 7);
+    const double fac = 0.5 * hb[k] / dt;
+    const double dv = ((L1(labv, k, ix + 1, iy, 0) - L1(labv, k, ix - 1, iy, 0)) + L1(labv, k, ix, iy + 1, 1)) - L1(labv, k, ix, iy - 1, 1);
+    const double du = ((L1(labu, k, ix + 1, iy, 0) - L1(labu, k, ix - 1, iy, 0)) + L1(labu, k, ix, iy + 1, 1)) - L1(labu, k, ix, iy - 1, 1);
+    tmp[i] = fac * dv - fac * chi[i] * du;
+  }
+}
+
+__global__ void amr_lap_kernel(const double *__restrict__ labp, double *__restrict__ tmp, int64_t ncells) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < ncells; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t k = i >> 6;
+    const int ix = (int)(i & 7), iy = (int)((i >> 3) & 7);
+    tmp[i] -= (((L2(labp, k, ix - 1, iy) + L2(labp, k, ix + 1, iy)) + L2(labp, k, ix, iy - 1)) + L2(labp, k, ix, iy + 1)) -
+              4 * L2(labp, k, ix, iy);
+  }
+}
+
+__global__ void amr_gradp_kernel(const double *__restrict__ labp, double *__restrict__ tmpv, const double *__restrict__ hb,
+                                 int64_t ncells, double dt) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < ncells; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t k = i >> 6;
+    const int ix = (int)(i & 7), iy = (int)((i >> 3) & 7);
+    const double pfac = -0.5 * dt * hb[k];
+    tmpv[2 * i] = pfac * (L2(labp, k, ix + 1, iy) - L2(labp, k, ix - 1, iy));
+    tmpv[2 * i + 1] = pfac * (L2(labp, k, ix, iy + 1) - L2(labp, k, ix, iy - 1));
+  }
+}
+
+// ---- face fluxes (what the kernels store in BlockCase::d[face]) -----------------------------------------------------
+// position t along the face (0..7), face 0 = x-, 1 = x+, 2 = y-, 3 = y+; inner cell and the ghost behind the face
+__device__ __forceinline__ void face_cells(int face, int t, int &ix, int &iy, int &gx, int &gy) {
+  if (face < 2) {
+    ix = face == 0 ? 0 : 7, iy = t, gx = face == 0 ? -1 : 8, gy = t;
+  } else {
+    ix = t, iy = face == 2 ? 0 : 7, gx = t, gy = face == 2 ? -1 : 8;
+  }
+}
+// MODE 0: advect (dim 2, main.cpp:5515-5569)   1: pressure_rhs (dim 1, 6152-6205)   2: pressure_rhs1 (dim 1, 6243-6283)
+template <int MODE>
+__device__ __forceinline__ double face_flux(const double *labA, const double *labB, const double *chi, const double *hb,
+                                            int64_t k, int face, int t, int comp, double nu, double dt) {
+  int ix, iy, gx, gy;
+  face_cells(face, t, ix, iy, gx, gy);
+  if (MODE == 0) return (nu * dt) * (L0(labA, k, ix, iy, comp) - L0(labA, k, gx, gy, comp));
+  if (MODE == 2) return L2(labA, k, gx, gy) - L2(labA, k, ix, iy);
+  const double fac = 0.5 * hb[k] / dt;
+  const int c = face < 2 ? 0 : 1;
+  const double sv = L1(labA, k, gx, gy, c) + L1(labA, k, ix, iy, c), su = L1(labB, k, gx, gy, c) + L1(labB, k, ix, iy, c);
+  const double x = chi[k * 64 + iy * 8 + ix];
+  return (face & 1) == 0 ? fac * sv - (fac * x) * su : -fac * sv + (fac * x) * su;
+}
+
+// one thread per (coarse face, position t, comp): coarse cell += [own flux + (fine a + fine b)], twice where the reference does
+template <int MODE>
+__global__ void amr_fluxcorr_kernel(const CoarseFace *__restrict__ cf, int ncf, const double *labA, const double *labB,
+                                    const double *chi, const double *hb, double *__restrict__ result, double nu,
+                                    double dt) {
+  constexpr int DIM = MODE == 0 ? 2 : 1;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= ncf * 8 * DIM) return;
+  const int comp = i % DIM, t = (i / DIM) % 8;
+  const CoarseFace f = cf[i / (8 * DIM)];
+  double acc = face_flux<MODE>(labA, labB, chi, hb, f.coarse, f.face, t, comp, nu, dt);
+  const int fb = f.fine[t >> 2];
+  if (fb >= 0) { // the fine block abutting this half: its face is the opposite one; positions 2(t%4), 2(t%4)+1
+    const int ff = f.face ^ 1, t2 = 2 * (t & 3);
+    acc += face_flux<MODE>(labA, labB, chi, hb, fb, ff, t2, comp, nu, dt) + face_flux<MODE>(labA, labB, chi, hb, fb, ff, t2 + 1, comp, nu, dt);
+  }
+  int ix, iy, gx, gy;
+  face_cells(f.face, t, ix, iy, gx, gy);
+  double *dst = result + ((int64_t)f.coarse * 64 + iy * 8 + ix) * DIM + comp;
+  double v = *dst + acc;
+  // fillcase1 runs once per fine block and clears only entries [0, 8] of the 16 of a vector face in its first pass
+  if (DIM == 2 && f.fine[0] >= 0 && f.fine[1] >= 0 && 2 * t + comp >= 9) v += acc;
+  *dst = v;
+}
+
+static int grid_for(int64_t n) { return (int)std::min<int64_t>((n + 255) / 256, 148 * 16); }
+
+static int upload_csr(cup2d_amr *a, int which) {
+  const int64_t nnz = cup2d_amr_plan_stencil(a->plan, which, nullptr, nullptr, nullptr, nullptr);
+  if (nnz < 0) return CUP2D_EINVAL;
+  const int64_t nrows = a->nb * LABN[which] * LABN[which] * LABD[which];
+  std::vector<int64_t> rp(nrows + 1);
+  std::vector<int32_t> sb(nnz), sc(nnz);
+  std::vector<double> w(nnz);
+  cup2d_amr_plan_stencil(a->plan, which, rp.data(), sb.data(), sc.data(), w.data());
+  Csr &c = a->csr[which];
+  c.nrows = nrows;
+  CUP2D_CUDA(cudaMalloc(&c.rowptr, (nrows + 1) * sizeof(int64_t)));
+  CUP2D_CUDA(cudaMalloc(&c.src_block, std::max<int64_t>(nnz, 1) * sizeof(int)));
+  CUP2D_CUDA(cudaMalloc(&c.src_cc, std::max<int64_t>(nnz, 1) * sizeof(int)));
+  CUP2D_CUDA(cudaMalloc(&c.w, std::max<int64_t>(nnz, 1) * sizeof(double)));
+  CUP2D_CUDA(cudaMemcpy(c.rowptr, rp.data(), (nrows + 1) * sizeof(int64_t), cudaMemcpyHostToDevice));
+  CUP2D_CUDA(cudaMemcpy(c.src_block, sb.data(), nnz * sizeof(int), cudaMemcpyHostToDevice));
+  CUP2D_CUDA(cudaMemcpy(c.src_cc, sc.data(), nnz * sizeof(int), cudaMemcpyHostToDevice));
+  CUP2D_CUDA(cudaMemcpy(c.w, w.data(), nnz * sizeof(double), cudaMemcpyHostToDevice));
+  CUP2D_CUDA(cudaMalloc(&a->lab[which], nrows * sizeof(double)));
+  return CUP2D_OK;
+}
+
+static int gather(cup2d_amr *a, int which, const double *field, double *lab) {
+  amr_gather_kernel<<<grid_for(a->csr[which].nrows), 256, 0, a->stream>>>(a->csr[which], field, lab, LABD[which]);
+  CUP2D_CUDA(cudaGetLastError());
+  return CUP2D_OK;
+}
+
+template <int MODE>
+static int fluxcorr(cup2d_amr *a, const double *labA, const double *labB, double *result, double dt) {
+  constexpr int DIM = MODE == 0 ? 2 : 1;
+  for (int dir = 0; dir < 2; dir++) { // x faces, then y faces (fillcases order)
+    const int n = a->ncf[dir] * 8 * DIM;
+    if (n == 0) continue;
+    amr_fluxcorr_kernel<MODE><<<(n + 127) / 128, 128, 0, a->stream>>>(a->d_cf[dir], a->ncf[dir], labA, labB, a->f[CUP2D_CHI],
+                                                                      a->d_h, result, a->nu, dt);
+  }
+  CUP2D_CUDA(cudaGetLastError());
+  return CUP2D_OK;
+}
+
+} // namespace cup2d
+
+using namespace cup2d;
+
+#define CHECK_AMR(a)                                                                              \
+  if (!(a)) {                                                                                     \
+    cup2d::set_error("null cup2d_amr handle");                                                    \
+    return CUP2D_EINVAL;                                                                          \
+  }
+
+extern "C" {
+
+int cup2d_amr_create(int64_t nblocks, const int32_t *level_ij, int32_t bpdx, int32_t bpdy, double h0, double nu,
+                     int32_t device, cup2d_amr **out) {
+  if (!out || !level_ij || nblocks <= 0 || !(h0 > 0)) {
+    set_error("cup2d_amr_create: bad arguments");
+    return CUP2D_EINVAL;
+  }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    set_error("cup2d_amr_create: no CUDA device visible; this library has no CPU fallback");
+    return CUP2D_ENOGPU;
+  }
+  if (device < 0 || device >= ndev) {
+    set_error("cup2d_amr_create: bad device ordinal");
+    return CUP2D_EINVAL;
+  }
+  cup2d_amr_plan *plan = nullptr;
+  int rc = cup2d_amr_plan_create(nblocks, level_ij, bpdx, bpdy, &plan);
+  if (rc) return rc;
+  cup2d_amr *a = new cup2d_amr;
+  a->plan = plan;
+  a->nb = nblocks;
+  a->device = device;
+  a->h0 = h0;
+  a->nu = nu;
+  auto fail = [&](int code) {
+    cup2d_amr_destroy(a);
+    return code;
+  };
+  if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreate(&a->stream) != cudaSuccess) {
+    set_error("cup2d_amr_create: cannot initialise the device");
+    return fail(CUP2D_ECUDA);
+  }
+  for (int f = 0; f < CUP2D_NFIELDS; f++) {
+    const size_t bytes = (size_t)nblocks * 64 * dim_of(f) * sizeof(double);
+    if (cudaMalloc(&a->f[f], bytes) != cudaSuccess || cudaMemset(a->f[f], 0, bytes) != cudaSuccess) {
+      set_error("cup2d_amr_create: out of device memory");
+      return fail(CUP2D_ECUDA);
+    }
+  }
+  std::vector<double> h(nblocks);
+  for (int64_t k = 0; k < nblocks; k++) h[k] = h0 / (double)(1 << level_ij[3 * k]);
+  if (cudaMalloc(&a->d_h, nblocks * sizeof(double)) != cudaSuccess ||
+      cudaMemcpy(a->d_h, h.data(), nblocks * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess)
+    return fail(CUP2D_ECUDA);
+  for (int which = 0; which < 3; which++)
+    if ((rc = upload_csr(a, which))) return fail(rc);
+  if (cudaMalloc(&a->lab_udef, a->csr[1].nrows * sizeof(double)) != cudaSuccess) return fail(CUP2D_ECUDA);
+  // coarse faces: group the plan's (fine block, face, coarse block, face, half) records by (coarse block, face)
+  const int64_t nf = cup2d_amr_plan_faces(plan, nullptr);
+  std::vector<int32_t> rec(5 * std::max<int64_t>(nf, 1));
+  cup2d_amr_plan_faces(plan, rec.data());
+  std::map<std::pair<int, int>, CoarseFace> byface;
+  for (int64_t r = 0; r < nf; r++) {
+    const int fine = rec[5 * r], kc = rec[5 * r + 2], fc = rec[5 * r + 3], half = rec[5 * r + 4];
+    auto it = byface.find({kc, fc});
+    if (it == byface.end()) it = byface.emplace(std::make_pair(kc, fc), CoarseFace{kc, fc, {-1, -1}}).first;
+    it->second.fine[half] = fine;
+  }
+  std::vector<CoarseFace> lists[2];
+  for (auto &e : byface) lists[e.second.face < 2 ? 0 : 1].push_back(e.second);
+  for (int d = 0; d < 2; d++) {
+    a->ncf[d] = (int)lists[d].size();
+    if (lists[d].empty()) continue;
+    if (cudaMalloc(&a->d_cf[d], lists[d].size() * sizeof(CoarseFace)) != cudaSuccess ||
+        cudaMemcpy(a->d_cf[d], lists[d].data(), lists[d].size() * sizeof(CoarseFace), cudaMemcpyHostToDevice) != cudaSuccess)
+      return fail(CUP2D_ECUDA);
+  }
+  *out = a;
+  return CUP2D_OK;
+}
+
+void cup2d_amr_destroy(cup2d_amr *a) {
+  if (!a) return;
+  cudaSetDevice(a->device);
+  for (auto p : a->f) cudaFree(p);
+  for (auto &c : a->csr) {
+    cudaFree(c.rowptr); cudaFree(c.src_block); cudaFree(c.src_cc); cudaFree(c.w);
+  }
+  for (auto p : a->lab) cudaFree(p);
+  cudaFree(a->lab_udef); cudaFree(a->d_h); cudaFree(a->d_cf[0]); cudaFree(a->d_cf[1]);
+  if (a->stream) cudaStreamDestroy(a->stream);
+  if (a->plan) cup2d_amr_plan_destroy(a->plan);
+  delete a;
+}
+
+int cup2d_amr_field_upload(cup2d_amr *a, int field, const double *host) {
+  CHECK_AMR(a);
+  if (field < 0 || field >= CUP2D_NFIELDS || !host) return CUP2D_EINVAL;
+  CUP2D_CUDA(cudaSetDevice(a->device));
+  CUP2D_CUDA(cudaMemcpyAsync(a->f[field], host, (size_t)a->nb * 64 * dim_of(field) * sizeof(double), cudaMemcpyHostToDevice, a->stream));
+  CUP2D_CUDA(cudaStreamSynchronize(a->stream));
+  return CUP2D_OK;
+}
+
+int cup2d_amr_field_download(cup2d_amr *a, int field, double *host) {
+  CHECK_AMR(a);
+  if (field < 0 || field >= CUP2D_NFIELDS || !host) return CUP2D_EINVAL;
+  CUP2D_CUDA(cudaSetDevice(a->device));
+  CUP2D_CUDA(cudaMemcpyAsync(host, a->f[field], (size_t)a->nb * 64 * dim_of(field) * sizeof(double), cudaMemcpyDeviceToHost, a->stream));
+  CUP2D_CUDA(cudaStreamSynchronize(a->stream));
+  return CUP2D_OK;
+}
+
+/* tmpV = KernelAdvectDiffuse(vel), flux-corrected (main.cpp:6611-6617) */
+int cup2d_amr_advect_diffuse_rhs(cup2d_amr *a, double dt) {
+  CHECK_AMR(a);
+  CUP2D_CUDA(cudaSetDevice(a->device));
+  int rc = gather(a, 0, a->f[CUP2D_VEL], a->lab[0]);
+  if (rc) return rc;
+  amr_advect_kernel<<<grid_for(a->nb * 64), 256, 0, a->stream>>>(a->lab[0], a->f[CUP2D_TMPV], a->d_h, a->nb * 64, a->nu, dt);
+  CUP2D_CUDA(cudaGetLastError());
+  return fluxcorr<0>(a, a->lab[0], nullptr, a->f[CUP2D_TMPV], dt);
+}
+
+/* tmp = pressure_rhs(vel, u_def = tmpV, chi), flux-corrected (main.cpp:7007-7013); with_laplacian: then
+ * tmp -= lap(pold), flux-corrected (main.cpp:7022-7027) */
+int cup2d_amr_pressure_rhs(cup2d_amr *a, double dt, int with_laplacian) {
+  CHECK_AMR(a);
+  CUP2D_CUDA(cudaSetDevice(a->device));
+  int rc = gather(a, 1, a->f[CUP2D_VEL], a->lab[1]);
+  if (rc || (rc = gather(a, 1, a->f[CUP2D_TMPV], a->lab_udef))) return rc;
+  amr_div_kernel<<<grid_for(a->nb * 64), 256, 0, a->stream>>>(a->lab[1], a->lab_udef, a->f[CUP2D_CHI], a->f[CUP2D_TMP], a->d_h,
+                                                             a->nb * 64, dt);
+  CUP2D_CUDA(cudaGetLastError());
+  if ((rc = fluxcorr<1>(a, a->lab[1], a->lab_udef, a->f[CUP2D_TMP], dt))) return rc;
+  if (!with_laplacian) return CUP2D_OK;
+  if ((rc = gather(a, 2, a->f[CUP2D_POLD], a->lab[2]))) return rc;
+  amr_lap_kernel<<<grid_for(a->nb * 64), 256, 0, a->stream>>>(a->lab[2], a->f[CUP2D_TMP], a->nb * 64);
+  CUP2D_CUDA(cudaGetLastError());
+  return fluxcorr<2>(a, a->lab[2], nullptr, a->f[CUP2D_TMP], dt);
+}
+
+/* tmpV = pressureCorrectionKernel(pres) (main.cpp:7174-7179; not flux-corrected in the reference either) */
+int cup2d_amr_pressure_gradient(cup2d_amr *a, double dt) {
+  CHECK_AMR(a);
+  CUP2D_CUDA(cudaSetDevice(a->device));
+  int rc = gather(a, 2, a->f[CUP2D_PRES], a->lab[2]);
+  if (rc) return rc;
+  amr_gradp_kernel<<<grid_for(a->nb * 64), 256, 0, a->stream>>>(a->lab[2], a->f[CUP2D_TMPV], a->d_h, a->nb * 64, dt);
+  CUP2D_CUDA(cudaGetLastError());
+  return CUP2D_OK;
+}
+
+int cup2d_amr_sync(cup2d_amr *a) {
+  CHECK_AMR(a);
+  CUP2D_CUDA(cudaSetDevice(a->device));
+  CUP2D_CUDA(cudaStreamSynchronize(a->stream));
+  return CUP2D_OK;
+}
+
+} // extern "C"

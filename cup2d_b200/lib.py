@@ -21,6 +21,8 @@ SYMBOLS = [
     "cup2d_shape_set", "cup2d_shape_integrals", "cup2d_penalize", "cup2d_udef_assemble",
     "cup2d_amr_plan_create", "cup2d_amr_plan_destroy", "cup2d_amr_plan_stencil", "cup2d_amr_plan_faces",
     "cup2d_amr_plan_irregular", "cup2d_amr_plan_ghosts", "cup2d_amr_plan_stats", "cup2d_amr_plan_neighbours",
+    "cup2d_amr_create", "cup2d_amr_destroy", "cup2d_amr_field_upload", "cup2d_amr_field_download", "cup2d_amr_sync",
+    "cup2d_amr_advect_diffuse_rhs", "cup2d_amr_pressure_rhs", "cup2d_amr_pressure_gradient",
 ]
 
 
@@ -98,6 +100,15 @@ def load_library():
     lib.cup2d_amr_plan_stencil.argtypes = [P, I, C.POINTER(L), C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(D)]
     lib.cup2d_amr_plan_stencil.restype = L
     lib.cup2d_amr_plan_faces.argtypes = [P, C.POINTER(C.c_int32)]
+    lib.cup2d_amr_create.argtypes = [L, C.POINTER(C.c_int32), C.c_int32, C.c_int32, D, D, C.c_int32, C.POINTER(P)]
+    lib.cup2d_amr_destroy.argtypes = [P]
+    lib.cup2d_amr_destroy.restype = None
+    lib.cup2d_amr_field_upload.argtypes = [P, I, P]
+    lib.cup2d_amr_field_download.argtypes = [P, I, P]
+    lib.cup2d_amr_sync.argtypes = [P]
+    lib.cup2d_amr_advect_diffuse_rhs.argtypes = [P, D]
+    lib.cup2d_amr_pressure_rhs.argtypes = [P, D, I]
+    lib.cup2d_amr_pressure_gradient.argtypes = [P, D]
     lib.cup2d_amr_plan_stats.argtypes = [P, I, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
     lib.cup2d_amr_plan_neighbours.argtypes = [P, C.POINTER(C.c_int32)]
     lib.cup2d_amr_plan_irregular.argtypes = [P, C.POINTER(C.c_int32)]

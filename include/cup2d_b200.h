@@ -215,6 +215,24 @@ int cup2d_amr_plan_neighbours(cup2d_amr_plan *p, int32_t *out);
  * coarse block, its face, which half of the coarse face); faces 0 = x-, 1 = x+, 2 = y-, 3 = y+.  Returns the count. */
 int64_t cup2d_amr_plan_faces(cup2d_amr_plan *p, int32_t *out);
 
+/* ---- multi-level meshes on the device: first, correctness-oriented path (csrc/amr_ops.cu) --------------------------
+ * NOT YET VALIDATED ON HARDWARE (written after round 1's GPU budget was spent; tests/test_gpu_amr.py runs only with
+ * CUP2D_TEST_UNVALIDATED=1).  One GPU.  Fields as in cup2d_sim (same ids and block layout, blocks in `infos` order). */
+typedef struct cup2d_amr cup2d_amr;
+int cup2d_amr_create(int64_t nblocks, const int32_t *level_ij, int32_t bpdx, int32_t bpdy, double h0, double nu,
+                     int32_t device, cup2d_amr **out);
+void cup2d_amr_destroy(cup2d_amr *a);
+int cup2d_amr_field_upload(cup2d_amr *a, int field, const double *host);
+int cup2d_amr_field_download(cup2d_amr *a, int field, double *host);
+int cup2d_amr_sync(cup2d_amr *a);
+/* tmpV = KernelAdvectDiffuse(vel), flux-corrected (main.cpp:6611-6617) */
+int cup2d_amr_advect_diffuse_rhs(cup2d_amr *a, double dt);
+/* tmp = pressure_rhs(vel, u_def = tmpV, chi), flux-corrected (main.cpp:7007-7013); with_laplacian != 0: then
+ * tmp -= lap(pold), flux-corrected (main.cpp:7022-7027) */
+int cup2d_amr_pressure_rhs(cup2d_amr *a, double dt, int with_laplacian);
+/* tmpV = pressureCorrectionKernel(pres) (main.cpp:7174-7179; not flux-corrected in the reference either) */
+int cup2d_amr_pressure_gradient(cup2d_amr *a, double dt);
+
 #ifdef __cplusplus
 }
 #endif

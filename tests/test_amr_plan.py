@@ -179,3 +179,50 @@ def test_pattern_dictionary_and_neighbour_table(setup):
         if (nb[k] < -1).any():
             irregular.append(k)
     assert irregular == plan.irregular().tolist()
+
+
+def test_coarse_face_formulation_of_the_flux_correction(setup):
+    """csrc/amr_ops.cu applies fillcases per COARSE face: own flux + (fine a + fine b) per position, added once, and once
+    more for flat entries >= 9 of a vector face when both fine blocks exist.  Same algorithm in numpy, from the plan's
+    face list and table-made labs, against the reference's flux-corrected advect result (bit for bit when the labs are
+    the oracle's; 1e-12 with table labs)."""
+    import cup2d_oracle as orc
+    d, plan = setup
+    mesh = amr.Mesh(d["blocks"], int(d["bpdx"]), int(d["bpdy"]))
+    nu, dt, h0 = float(d["nu"]), float(d["dt"]), float(d["h0"])
+    nb = len(mesh.blocks)
+    lab = amr.Lab(mesh, d["vel"], (-3, -3, 4, 4, True), "vector")
+    labs = np.stack([lab.load(k).copy() for k in range(nb)])
+    adv = np.empty((nb, 8, 8, 2))
+    for k in range(nb):
+        adv[k, :, :, 0], adv[k, :, :, 1] = orc.advect_diffuse_padded(labs[k, :, :, 0], labs[k, :, :, 1],
+                                                                     h0 / (1 << mesh.blocks[k][0]), nu, dt)
+
+    def cells(face, t):
+        return ((0 if face == 0 else 7, t, -1 if face == 0 else 8, t) if face < 2
+                else (t, 0 if face == 2 else 7, t, -1 if face == 2 else 8))
+
+    def flux(k, face, t, comp):
+        ix, iy, gx, gy = cells(face, t)
+        return (nu * dt) * (labs[k, iy + 3, ix + 3, comp] - labs[k, gy + 3, gx + 3, comp])
+
+    byface = {}
+    for fine, ff, kc, fc, half in plan.faces().tolist():
+        byface.setdefault((kc, fc), [-1, -1])[half] = fine
+    for xfaces in (True, False):
+        for (kc, fc), fine in sorted(byface.items()):
+            if (fc < 2) != xfaces:
+                continue
+            for t in range(8):
+                for comp in range(2):
+                    acc = flux(kc, fc, t, comp)
+                    fb = fine[t >> 2]
+                    if fb >= 0:
+                        t2 = 2 * (t & 3)
+                        acc += flux(fb, fc ^ 1, t2, comp) + flux(fb, fc ^ 1, t2 + 1, comp)
+                    ix, iy, _, _ = cells(fc, t)
+                    v = adv[kc, iy, ix, comp] + acc
+                    if fine[0] >= 0 and fine[1] >= 0 and 2 * t + comp >= 9:
+                        v += acc
+                    adv[kc, iy, ix, comp] = v
+    assert np.array_equal(adv, d["adv"])
