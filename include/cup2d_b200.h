@@ -217,7 +217,7 @@ int64_t cup2d_amr_plan_faces(cup2d_amr_plan *p, int32_t *out);
 
 /* ---- multi-level meshes on the device: first, correctness-oriented path (csrc/amr_ops.cu) --------------------------
  * NOT YET VALIDATED ON HARDWARE (written after round 1's GPU budget was spent; tests/test_gpu_amr.py runs only with
- * CUP2D_TEST_UNVALIDATED=1).  One GPU.  Fields as in cup2d_sim (same ids and block layout, blocks in `infos` order). */
+ * CUP2D_TEST_UNVALIDATED=1).  One GPU.  Same field ids and block layout as the uniform-grid context, blocks in `infos` order. */
 typedef struct cup2d_amr cup2d_amr;
 int cup2d_amr_create(int64_t nblocks, const int32_t *level_ij, int32_t bpdx, int32_t bpdy, double h0, double nu,
                      int32_t device, cup2d_amr **out);
