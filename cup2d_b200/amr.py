@@ -60,6 +60,20 @@ class AmrPlan:
         _l.check(self.lib.cup2d_amr_plan_neighbours(self._h, out.ctypes.data_as(C.POINTER(C.c_int32))))
         return out
 
+    def poisson(self):
+        """(nbr[n,4], irr_rows, irr_rowptr, irr_col, irr_val): the arguments of cup2d_poisson_create_general"""
+        nnz = C.c_int64()
+        ip = C.POINTER(C.c_int32)
+        nrows = self.lib.cup2d_amr_plan_poisson(self._h, None, C.byref(nnz), None, None, None, None)
+        if nrows < 0:
+            _l.check(int(nrows))
+        nbr = np.empty((len(self.blocks), 4), dtype=np.int32)
+        rows, rowptr = np.empty(nrows, dtype=np.int32), np.empty(nrows + 1, dtype=np.int32)
+        col, val = np.empty(nnz.value, dtype=np.int32), np.empty(nnz.value)
+        self.lib.cup2d_amr_plan_poisson(self._h, nbr.ctypes.data_as(ip), C.byref(nnz), rows.ctypes.data_as(ip),
+                                        rowptr.ctypes.data_as(ip), col.ctypes.data_as(ip), val.ctypes.data_as(C.POINTER(C.c_double)))
+        return nbr, rows, rowptr, col, val
+
     def faces(self):
         n = self.lib.cup2d_amr_plan_faces(self._h, None)
         out = np.empty((n, 5), dtype=np.int32)

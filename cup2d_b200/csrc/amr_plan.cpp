@@ -696,6 +696,129 @@ int64_t cup2d_amr_plan_stencil(cup2d_amr_plan *p, int which, int64_t *rowptr, in
   return nnz;
 }
 
+/* ---- Poisson matrix of a multi-level mesh -----------------------------------------------------------------------------
+ * The rows the reference's assembly loop pushes (main.cpp:7051-7113) for the cells whose 5-point stencil crosses a
+ * coarse-fine face (makeFlux / interpolate / D1 / D2, main.cpp:5915-5997: weights 2/3, -1/5, 8/15 and the Taylor
+ * corrections +-1/8, +-1/2, +-3/8 / 1/32, -1/16), complete, in CSR — every other row is the same-level stencil and is
+ * described by the face-neighbour table.  Exactly what cup2d_poisson_create_general consumes.  Entries are accumulated
+ * in the reference's order (it sums into a std::map per row), so the values are bitwise the reference's.
+ * nbr_out[4k..] = W,E,S,N same-level neighbour of block k or -1 (wall, coarser, finer).  Returns the number of general
+ * rows; irr_rows may be NULL to size (then *nnz_out is set and nothing else is written). */
+int64_t cup2d_amr_plan_poisson(cup2d_amr_plan *p, int32_t *nbr_out, int64_t *nnz_out, int32_t *irr_rows,
+                               int32_t *irr_rowptr, int32_t *irr_col, double *irr_val) {
+  if (!p) return CUP2D_EINVAL;
+  const Mesh &m = p->mesh;
+  const int64_t n = (int64_t)m.lij.size() / 3;
+  static const int fc[4][2] = {{-1, 0}, {1, 0}, {0, -1}, {0, 1}};
+  int64_t nrows = 0, nnz = 0;
+  if (irr_rowptr) irr_rowptr[0] = 0;
+  for (int64_t k = 0; k < n; k++) {
+    const int l = m.lij[3 * k], I = m.lij[3 * k + 1], J = m.lij[3 * k + 2];
+    const int NX = m.bpdx << l, NY = m.bpdy << l;
+    int st[4];
+    for (int j = 0; j < 4; j++) {
+      const int ni = I + fc[j][0], nj = J + fc[j][1];
+      st[j] = (ni < 0 || nj < 0 || ni >= NX || nj >= NY) ? -9 : m.state(l, ni, nj); // -9: domain wall
+      if (nbr_out) nbr_out[4 * k + j] = st[j] >= 0 ? st[j] : -1;
+    }
+    auto idx = [](int64_t blk, int x, int y) { return blk * 64 + y * BS + x; };
+    for (int iy = 0; iy < BS; iy++)
+      for (int ix = 0; ix < BS; ix++) {
+        const bool valid[4] = {ix > 0, ix < BS - 1, iy > 0, iy < BS - 1};
+        bool general = false;
+        for (int j = 0; j < 4; j++) general = general || (!valid[j] && (st[j] == -1 || st[j] == -2));
+        if (!general) continue;
+        std::map<int64_t, double> row;
+        const int64_t self = idx(k, ix, iy);
+        const int inb[4][2] = {{ix - 1, iy}, {ix + 1, iy}, {ix, iy - 1}, {ix, iy + 1}};
+        for (int j = 0; j < 4; j++) {
+          if (valid[j]) {
+            row[idx(k, inb[j][0], inb[j][1])] += 1;
+            row[self] += -1;
+            continue;
+          }
+          if (st[j] == -9) continue; // Neumann wall: the neighbour is simply absent
+          const bool xface = j < 2;
+          // tangential coordinate helpers of the face (main.cpp:5793-5812 / 5852-5866)
+          auto isBD = [&](int t) { return t == BS - 1 || t == H - 1; };
+          auto isFD = [&](int t) { return t == 0 || t == H; };
+          auto interpolate = [&](int64_t cblk, int cx, int cy, int64_t close, int64_t far, double signInt, double signTaylor) {
+            row[close] += signInt * 2. / 3.;
+            row[far] += -signInt * 1. / 5.;
+            const double tf = signInt * 8. / 15.;
+            row[idx(cblk, cx, cy)] += tf;
+            const int t = xface ? cy : cx;
+            auto nei = [&](int d) { return xface ? idx(cblk, cx, cy + d) : idx(cblk, cx + d, cy); };
+            struct E { int64_t c; double w; };
+            E d1[3], d2[3];
+            if (isBD(t)) {
+              d1[0] = {nei(-2), 1. / 8.}, d1[1] = {nei(-1), -1. / 2.}, d1[2] = {nei(0), 3. / 8.};
+              d2[0] = {nei(-2), 1. / 32.}, d2[1] = {nei(-1), -1. / 16.}, d2[2] = {nei(0), 1. / 32.};
+            } else if (isFD(t)) {
+              d1[0] = {nei(2), -1. / 8.}, d1[1] = {nei(1), 1. / 2.}, d1[2] = {nei(0), -3. / 8.};
+              d2[0] = {nei(2), 1. / 32.}, d2[1] = {nei(1), -1. / 16.}, d2[2] = {nei(0), 1. / 32.};
+            } else {
+              d1[0] = {nei(-1), -1. / 8.}, d1[1] = {nei(1), 1. / 8.}, d1[2] = {nei(0), 0.};
+              d2[0] = {nei(-1), 1. / 32.}, d2[1] = {nei(1), 1. / 32.}, d2[2] = {nei(0), -1. / 16.};
+            }
+            for (auto &e : d1) row[e.c] += signTaylor * tf * e.w;
+            for (auto &e : d2) row[e.c] += tf * e.w;
+          };
+          if (st[j] >= 0) { // same level: the facing cell of the neighbour block
+            const int fx = xface ? (j == 0 ? BS - 1 : 0) : ix, fy = xface ? iy : (j == 2 ? BS - 1 : 0);
+            row[idx(st[j], fx, fy)] += 1.;
+            row[self] += -1.;
+          } else if (st[j] == -2) { // coarser: this (fine) cell against the coarse cell behind the face
+            const int ni = I + fc[j][0], nj = J + fc[j][1];
+            const int64_t cb = m.find(l - 1, ni >> 1, nj >> 1);
+            if (cb < 0) {
+              cup2d::set_error("cup2d_amr_plan_poisson: neighbouring blocks differ by more than one level");
+              return CUP2D_EINVAL;
+            }
+            const int bx = I % 2 == 0 ? ix / 2 : ix / 2 + H, by = J % 2 == 0 ? iy / 2 : iy / 2 + H;
+            const int cx = xface ? (j == 0 ? BS - 1 : 0) : bx, cy = xface ? by : (j == 2 ? BS - 1 : 0);
+            const int64_t inward = xface ? idx(k, j == 0 ? ix + 1 : ix - 1, iy) : idx(k, ix, j == 2 ? iy + 1 : iy - 1);
+            const double signTaylor = ((xface ? iy : ix) % 2 == 0) ? -1. : 1.;
+            interpolate(cb, cx, cy, self, inward, 1., signTaylor);
+            row[self] += -1.;
+          } else { // finer: this (coarse) cell against the two fine cells behind the face
+            const int t = xface ? iy : ix;
+            const int hi = t >= H ? 1 : 0;
+            const int ci = xface ? 2 * (I + fc[j][0]) + (j == 0 ? 1 : 0) : 2 * I + hi;
+            const int cj = xface ? 2 * J + hi : 2 * (J + fc[j][1]) + (j == 2 ? 1 : 0);
+            const int64_t fb = m.find(l + 1, ci, cj);
+            if (fb < 0) {
+              cup2d::set_error("cup2d_amr_plan_poisson: neighbouring blocks differ by more than one level");
+              return CUP2D_EINVAL;
+            }
+            const int tf0 = (t % H) * 2; // first of the two fine cells along the face
+            for (int q = 0; q < 2; q++) {
+              auto fine = [&](int off) { // off = 0: the fine cell at the face, 1: the one behind it
+                const int a = (j == 0 || j == 2) ? BS - 1 - off : off;
+                return xface ? idx(fb, a, tf0 + q) : idx(fb, tf0 + q, a);
+              };
+              row[fine(0)] += 1.;
+              interpolate(k, ix, iy, fine(0), fine(1), -1., q == 0 ? -1. : 1.);
+            }
+          }
+        }
+        if (irr_rows) {
+          irr_rows[nrows] = (int32_t)self;
+          for (auto &e : row) {
+            irr_col[nnz] = (int32_t)e.first;
+            irr_val[nnz] = e.second;
+            nnz++;
+          }
+          irr_rowptr[nrows + 1] = (int32_t)nnz;
+        } else
+          nnz += (int64_t)row.size();
+        nrows++;
+      }
+  }
+  if (nnz_out) *nnz_out = nnz;
+  return nrows;
+}
+
 /* bookkeeping of the last cup2d_amr_plan_ghosts(which): distinct local configurations, directly evaluated blocks */
 int cup2d_amr_plan_stats(cup2d_amr_plan *p, int which, int32_t *npatterns, int32_t *fallbacks) {
   if (!p || which < 0 || which > 2 || !p->ghosts[which].built) return CUP2D_EINVAL;

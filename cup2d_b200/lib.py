@@ -20,7 +20,7 @@ SYMBOLS = [
     "cup2d_plan_create", "cup2d_plan_table", "cup2d_poisson_create", "cup2d_poisson_create_general", "cup2d_vorticity_tag", "cup2d_adapt_tags", "cup2d_dump",
     "cup2d_shape_set", "cup2d_shape_integrals", "cup2d_penalize", "cup2d_udef_assemble",
     "cup2d_amr_plan_create", "cup2d_amr_plan_destroy", "cup2d_amr_plan_stencil", "cup2d_amr_plan_faces",
-    "cup2d_amr_plan_irregular", "cup2d_amr_plan_ghosts", "cup2d_amr_plan_stats", "cup2d_amr_plan_neighbours",
+    "cup2d_amr_plan_irregular", "cup2d_amr_plan_ghosts", "cup2d_amr_plan_stats", "cup2d_amr_plan_neighbours", "cup2d_amr_plan_poisson",
     "cup2d_amr_create", "cup2d_amr_destroy", "cup2d_amr_field_upload", "cup2d_amr_field_download", "cup2d_amr_sync",
     "cup2d_amr_advect_diffuse_rhs", "cup2d_amr_pressure_rhs", "cup2d_amr_pressure_gradient",
 ]
@@ -109,6 +109,9 @@ def load_library():
     lib.cup2d_amr_advect_diffuse_rhs.argtypes = [P, D]
     lib.cup2d_amr_pressure_rhs.argtypes = [P, D, I]
     lib.cup2d_amr_pressure_gradient.argtypes = [P, D]
+    lib.cup2d_amr_plan_poisson.argtypes = [P, C.POINTER(C.c_int32), C.POINTER(L), C.POINTER(C.c_int32), C.POINTER(C.c_int32),
+                                           C.POINTER(C.c_int32), C.POINTER(D)]
+    lib.cup2d_amr_plan_poisson.restype = L
     lib.cup2d_amr_plan_stats.argtypes = [P, I, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
     lib.cup2d_amr_plan_neighbours.argtypes = [P, C.POINTER(C.c_int32)]
     lib.cup2d_amr_plan_irregular.argtypes = [P, C.POINTER(C.c_int32)]

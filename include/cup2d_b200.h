@@ -211,6 +211,13 @@ int cup2d_amr_plan_stats(cup2d_amr_plan *p, int which, int32_t *npatterns, int32
 /* out[k][8]: the 8 neighbour positions of block k in the order (-1,-1),(0,-1),(1,-1),(-1,0),(1,0),(-1,1),(0,1),(1,1):
  * >= 0 same-level block, -1 domain wall, -2 covered by a coarser block, -3 refined further (the regular-ghost fast path) */
 int cup2d_amr_plan_neighbours(cup2d_amr_plan *p, int32_t *out);
+/* Poisson matrix of the mesh in the form cup2d_poisson_create_general takes: nbr_out[4k..] = W,E,S,N same-level neighbour
+ * of block k or -1 (wall, coarser, finer), and the rows whose stencil crosses a coarse-fine face, complete, in CSR —
+ * the rows the reference's assembly loop pushes (main.cpp:7051-7113 with makeFlux / interpolate / D1 / D2,
+ * main.cpp:5915-5997), values bitwise identical (same accumulation order).  Returns the number of such rows and *nnz_out;
+ * call with irr_rows = NULL to size. */
+int64_t cup2d_amr_plan_poisson(cup2d_amr_plan *p, int32_t *nbr_out, int64_t *nnz_out, int32_t *irr_rows,
+                               int32_t *irr_rowptr, int32_t *irr_col, double *irr_val);
 /* coarse-fine faces for the flux correction (prepare0, main.cpp:1683-1735): records of 5 int32 = (fine block, its face,
  * coarse block, its face, which half of the coarse face); faces 0 = x-, 1 = x+, 2 = y-, 3 = y+.  Returns the count. */
 int64_t cup2d_amr_plan_faces(cup2d_amr_plan *p, int32_t *out);

@@ -238,6 +238,17 @@ void LocalSpMatDnVec::make(const std::vector<long long> &Nrows_xcumsum) { // cud
     loc_cooColA_int_[i] = (int)(loc_cooColA_long_[i] + shift);
   }
   solver_->build_rowptr();
+  // fixtures: the matrix exactly as the reference's assembly loop pushed it (main.cpp:7051-7113), latest regrid wins
+  if (const char *path = getenv("CUP2D_REF_DUMP_COO")) {
+    FILE *f = fopen(path, "wb");
+    const long long n = loc_nnz_, m = m_;
+    fwrite(&m, sizeof m, 1, f);
+    fwrite(&n, sizeof n, 1, f);
+    fwrite(loc_cooRowA_int_.data(), sizeof(int), n, f);
+    fwrite(loc_cooColA_int_.data(), sizeof(int), n, f);
+    fwrite(loc_cooValA_.data(), sizeof(double), n, f);
+    fclose(f);
+  }
 }
 void LocalSpMatDnVec::solveWithUpdate(const double max_error, const double max_rel_error,
                                       const int max_restarts) {

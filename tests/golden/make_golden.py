@@ -233,8 +233,14 @@ def gen_amrlab(tmp, level_max, nsteps):
     """ghost assembly + the four operators of the reference on its own multi-level run.sh mesh:
     mesh, seeded inputs, flux-corrected outputs for every block and the assembled labs of every second block"""
     fout = os.path.join(tmp, "amrlab.bin")
+    fcoo = os.path.join(tmp, "coo.bin")
     subprocess.run([HARNESS, "amrlab", str(level_max), str(nsteps), fout], check=True, stderr=subprocess.DEVNULL,
-                   stdout=subprocess.DEVNULL, env=dict(os.environ, OMP_NUM_THREADS="1"))
+                   stdout=subprocess.DEVNULL, env=dict(os.environ, OMP_NUM_THREADS="1", CUP2D_REF_DUMP_COO=fcoo))
+    raw = open(fcoo, "rb").read()   # the Poisson matrix of the same mesh, as the reference's assembly pushed it
+    m_rows, nnz = np.frombuffer(raw, dtype=np.int64, count=2)
+    coo_row = np.frombuffer(raw, dtype=np.int32, count=nnz, offset=16)
+    coo_col = np.frombuffer(raw, dtype=np.int32, count=nnz, offset=16 + 4 * nnz)
+    coo_val = np.frombuffer(raw, dtype=np.float64, count=nnz, offset=16 + 8 * nnz)
     a = np.fromfile(fout)
     i, rec = 0, {}
     while i < len(a):
@@ -251,7 +257,9 @@ def gen_amrlab(tmp, level_max, nsteps):
         chi=rec[14].reshape(nb, 8, 8, 1), udef=rec[15].reshape(nb, 8, 8, 2), lab_blocks=sub,
         lab_vel3=rec[20].reshape(nb, 14, 14, 2)[sub], lab_vel1=rec[21].reshape(nb, 10, 10, 2)[sub],
         lab_pres1=rec[22].reshape(nb, 10, 10, 1)[sub], adv=rec[30].reshape(nb, 8, 8, 2),
-        rhs=rec[31].reshape(nb, 8, 8, 1), rhs1=rec[32].reshape(nb, 8, 8, 1), gradp=rec[33].reshape(nb, 8, 8, 2))
+        rhs=rec[31].reshape(nb, 8, 8, 1), rhs1=rec[32].reshape(nb, 8, 8, 1), gradp=rec[33].reshape(nb, 8, 8, 2),
+        coo_row=coo_row, coo_col=coo_col, coo_val=coo_val)
+    assert m_rows == 64 * nb, "the dumped matrix belongs to another mesh"
     print("amrlab", nb, "blocks, levels", sorted(set(blocks[:, 0].tolist())))
 
 

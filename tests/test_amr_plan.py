@@ -226,3 +226,40 @@ def test_coarse_face_formulation_of_the_flux_correction(setup):
                         v += acc
                     adv[kc, iy, ix, comp] = v
     assert np.array_equal(adv, d["adv"])
+
+
+def test_poisson_rows_equal_the_reference_assembly(setup):
+    """stencil rows (from the face-neighbour table) + general rows (CSR) == the COO the reference's own assembly loop
+    pushed for this mesh (main.cpp:7051-7113), value for value"""
+    d, plan = setup
+    nbr, rows, rowptr, col, val = plan.poisson()
+    n = 64 * len(plan.blocks)
+    ref = sp.coo_matrix((d["coo_val"], (d["coo_row"], d["coo_col"])), shape=(n, n)).tocsr()
+    ref.sum_duplicates()
+    ref.sort_indices()
+    general = set(rows.tolist())
+    assert 1000 < len(general) < n // 2
+    # general rows: bitwise
+    for q, r in enumerate(rows):
+        a, b = ref.indptr[r], ref.indptr[r + 1]
+        nz = ref.data[a:b] != 0
+        mine_nz = val[rowptr[q]:rowptr[q + 1]] != 0
+        assert np.array_equal(ref.indices[a:b][nz], col[rowptr[q]:rowptr[q + 1]][mine_nz])
+        assert np.array_equal(ref.data[a:b][nz], val[rowptr[q]:rowptr[q + 1]][mine_nz])
+    # all other rows: the 5-point stencil through the neighbour table
+    for k in range(len(plan.blocks)):
+        for iy in range(8):
+            for ix in range(8):
+                r = 64 * k + 8 * iy + ix
+                if r in general:
+                    continue
+                cols = []
+                for (x, y, face) in ((ix - 1, iy, 0), (ix + 1, iy, 1), (ix, iy - 1, 2), (ix, iy + 1, 3)):
+                    if 0 <= x < 8 and 0 <= y < 8:
+                        cols.append(64 * k + 8 * y + x)
+                    elif nbr[k, face] >= 0:
+                        cols.append(64 * int(nbr[k, face]) + 8 * (y % 8) + (x % 8))
+                want = dict.fromkeys(cols, 1.0)
+                want[r] = -float(len(cols))
+                a, b = ref.indptr[r], ref.indptr[r + 1]
+                assert dict(zip(ref.indices[a:b].tolist(), ref.data[a:b].tolist())) == want
