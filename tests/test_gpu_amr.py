@@ -51,3 +51,41 @@ def test_amr_pressure_gradient(case):
     sim.upload("pres", d["pres"])
     sim.pressure_gradient(float(d["dt"]))
     assert rel(sim.download("tmpV"), d["gradp"]) < 1e-12
+
+
+def test_native_amr_poisson_matrix_on_the_device_solver(golden_dir):
+    """host-built multi-level Poisson rows (cup2d_amr_plan_poisson, bitwise the reference's) -> the validated general-rows
+    solver (cup2d_poisson_create_general): 20 BiCGSTAB iterations against the oracle's BiCGSTAB on the reference's COO"""
+    import ctypes as C
+    import scipy.sparse as sp
+    import cup2d_oracle as orc
+    from cup2d_b200 import lib as Lb
+    from cup2d_b200.amr import AmrPlan
+    d = np.load(os.path.join(golden_dir, "amrlab_lmax8.npz"))
+    plan = AmrPlan(d["blocks"], int(d["bpdx"]), int(d["bpdy"]))
+    nbr, rows, rowptr, col, val = plan.poisson()
+    nb = len(plan.blocks)
+    lib = Lb.load_library()
+    h = C.c_void_p()
+    I32 = C.POINTER(C.c_int32)
+    Lb.check(lib.cup2d_poisson_create_general(nb, nbr.ctypes.data_as(I32), len(rows), rows.ctypes.data_as(I32),
+                                              rowptr.ctypes.data_as(I32), col.ctypes.data_as(I32),
+                                              val.ctypes.data_as(C.POINTER(C.c_double)), 0, C.byref(h)))
+    b = np.ascontiguousarray(d["rhs1"].reshape(-1))
+    x0 = np.zeros_like(b)
+    Lb.check(lib.cup2d_field_upload(h, 6, b.ctypes.data))
+    Lb.check(lib.cup2d_field_upload(h, 4, x0.ctypes.data))
+    it, err = C.c_int(), C.c_double()
+    K = 20
+    Lb.check(lib.cup2d_poisson_solve(h, 0.0, 0.0, 0, K, C.byref(it), C.byref(err)))
+    x = np.empty_like(b)
+    Lb.check(lib.cup2d_field_download(h, 4, x.ctypes.data))
+    lib.cup2d_destroy(h)
+    plan.close()
+    n = 64 * nb
+    A = sp.coo_matrix((d["coo_val"], (d["coo_row"], d["coo_col"])), shape=(n, n)).tocsr()
+    P = orc.build_P_inv()
+    xr, itr, errr = orc.bicgstab(b, x0, max_iter=K, A=lambda v: A @ v, M=lambda v: (v.reshape(nb, 64) @ P.T).reshape(-1))
+    assert it.value == itr == K
+    assert np.abs(x - xr).max() < 1e-9 * np.abs(xr).max()
+    assert abs(err.value - errr) < 1e-9 * errr
