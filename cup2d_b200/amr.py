@@ -123,6 +123,31 @@ class AmrSimulation:
     def pressure_gradient(self, dt):
         _l.check(self.lib.cup2d_amr_pressure_gradient(self._h, float(dt)))
 
+    def compute_dt(self, cfl):
+        u, dt = C.c_double(), C.c_double()
+        _l.check(self.lib.cup2d_amr_compute_dt(self._h, float(cfl), C.byref(u), C.byref(dt)))
+        return u.value, dt.value
+
+    def advect_diffuse_rk2(self, dt):
+        _l.check(self.lib.cup2d_amr_advect_diffuse_rk2(self._h, float(dt)))
+
+    def poisson_rhs(self, dt):
+        _l.check(self.lib.cup2d_amr_poisson_rhs(self._h, float(dt)))
+
+    def poisson_solve(self, tol_abs=0.0, tol_rel=0.0, max_restarts=0, max_iter=1000):
+        it, err = C.c_int(), C.c_double()
+        _l.check(self.lib.cup2d_amr_poisson_solve(self._h, tol_abs, tol_rel, max_restarts, max_iter, C.byref(it), C.byref(err)))
+        return it.value, err.value
+
+    def pressure_correct(self, dt):
+        _l.check(self.lib.cup2d_amr_pressure_correct(self._h, float(dt)))
+
+    def step(self, cfl=0.5, dt=0.0, tol_abs=0.0, tol_rel=0.0, max_restarts=0, max_iter=1000):
+        dto, it, err = C.c_double(), C.c_int(), C.c_double()
+        _l.check(self.lib.cup2d_amr_step(self._h, cfl, dt, tol_abs, tol_rel, max_restarts, max_iter, C.byref(dto), C.byref(it),
+                                         C.byref(err)))
+        return dto.value, it.value, err.value
+
     def close(self):
         if self._h:
             self.lib.cup2d_amr_destroy(self._h)

@@ -29,6 +29,11 @@ void cup2d_amr_plan_destroy(cup2d_amr_plan *p);
 int64_t cup2d_amr_plan_stencil(cup2d_amr_plan *p, int which, int64_t *rowptr, int32_t *src_block, int32_t *src_cellcomp,
                                double *weight);
 int64_t cup2d_amr_plan_faces(cup2d_amr_plan *p, int32_t *out);
+int64_t cup2d_amr_plan_poisson(cup2d_amr_plan *p, int32_t *nbr_out, int64_t *nnz_out, int32_t *irr_rows, int32_t *irr_rowptr,
+                               int32_t *irr_col, double *irr_val);
+int cup2d_amr_advect_diffuse_rhs(cup2d_amr *a, double dt);
+int cup2d_amr_pressure_rhs(cup2d_amr *a, double dt, int with_laplacian);
+int cup2d_amr_pressure_gradient(cup2d_amr *a, double dt);
 }
 
 namespace cup2d {
@@ -58,6 +63,10 @@ struct cup2d_amr {
   double *lab_udef = nullptr;
   cup2d::CoarseFace *d_cf[2] = {};  // [0] x faces, [1] y faces
   int ncf[2] = {0, 0};
+  double *d_part = nullptr;         // 2 doubles per block (partial maxima / sums)
+  std::vector<double> h_part;
+  double hmin = 0;
+  cup2d_sim *poisson = nullptr;     // general-rows Poisson context over the same blocks (cup2d_amr_poisson_solve)
 };
 
 namespace cup2d {
@@ -170,6 +179,46 @@ __global__ void amr_gradp_kernel(const double *__restrict__ labp, double *__rest
     const double pfac = -0.5 * dt * hb[k];
     tmpv[2 * i] = pfac * (L2(labp, k, ix + 1, iy) - L2(labp, k, ix - 1, iy));
     tmpv[2 * i + 1] = pfac * (L2(labp, k, ix, iy + 1) - L2(labp, k, ix, iy - 1));
+  }
+}
+
+// ---- the glue of a time step on a multi-level mesh (per-block cell size) --------------------------------------------
+__global__ void amr_block_absmax_kernel(const double *__restrict__ vel, double *__restrict__ out, int64_t nb) {
+  for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < nb; k += (int64_t)gridDim.x * blockDim.x) {
+    double m = 0.0;
+    for (int j = 0; j < 128; j++) m = fmax(m, fabs(vel[k * 128 + j]));
+    out[k] = m;
+  }
+}
+// V = Vold + c * tmpV / h^2   (main.cpp:6618-6626, 6634-6642, 7180-7187 with Vold = V)
+__global__ void amr_axpy_h2_kernel(double *__restrict__ v, const double *__restrict__ vold, const double *__restrict__ tmpv,
+                                   const double *__restrict__ hb, int64_t n, double c) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const double h = hb[i >> 7], ih2 = c / (h * h);
+    v[i] = vold[i] + tmpv[i] * ih2;
+  }
+}
+// per block: sum(P * h^2) and 64 h^2 (main.cpp:7126-7135, 7150-7158); the host adds the blocks up in order
+__global__ void amr_block_wsum_kernel(const double *__restrict__ p, const double *__restrict__ hb, double *__restrict__ out,
+                                      int64_t nb) {
+  for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < nb; k += (int64_t)gridDim.x * blockDim.x) {
+    const double vv = hb[k] * hb[k];
+    double a = 0.0, w = 0.0;
+    for (int j = 0; j < 64; j++) {
+      a += p[k * 64 + j] * vv;
+      w += vv;
+    }
+    out[2 * k] = a;
+    out[2 * k + 1] = w;
+  }
+}
+// p[i] = (src ? src[i] : p[i]) + (add ? add[i] : 0) - shift
+__global__ void amr_shift_kernel(double *__restrict__ p, const double *__restrict__ src, const double *__restrict__ add,
+                                 int64_t n, double shift) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    double v = src ? src[i] : p[i];
+    if (add) v += add[i] - shift; else v += -shift;
+    p[i] = v;
   }
 }
 
@@ -318,6 +367,9 @@ int cup2d_amr_create(int64_t nblocks, const int32_t *level_ij, int32_t bpdx, int
   }
   std::vector<double> h(nblocks);
   for (int64_t k = 0; k < nblocks; k++) h[k] = h0 / (double)(1 << level_ij[3 * k]);
+  a->hmin = *std::min_element(h.begin(), h.end());
+  a->h_part.resize(2 * nblocks);
+  if (cudaMalloc(&a->d_part, 2 * nblocks * sizeof(double)) != cudaSuccess) return fail(CUP2D_ECUDA);
   if (cudaMalloc(&a->d_h, nblocks * sizeof(double)) != cudaSuccess ||
       cudaMemcpy(a->d_h, h.data(), nblocks * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess)
     return fail(CUP2D_ECUDA);
@@ -356,7 +408,10 @@ void cup2d_amr_destroy(cup2d_amr *a) {
     cudaFree(c.rowptr); cudaFree(c.src_block); cudaFree(c.src_cc); cudaFree(c.w);
   }
   for (auto p : a->lab) cudaFree(p);
-  cudaFree(a->lab_udef); cudaFree(a->d_h); cudaFree(a->d_cf[0]); cudaFree(a->d_cf[1]);
+  cudaFree(a->lab_udef); cudaFree(a->d_h); cudaFree(a->d_cf[0]); cudaFree(a->d_cf[1]); cudaFree(a->d_part);
+#ifndef CUP2D_AMR_EMU
+  if (a->poisson) cup2d_destroy(a->poisson);
+#endif
   if (a->stream) cudaStreamDestroy(a->stream);
   if (a->plan) cup2d_amr_plan_destroy(a->plan);
   delete a;
@@ -419,6 +474,138 @@ int cup2d_amr_pressure_gradient(cup2d_amr *a, double dt) {
   CUP2D_CUDA(cudaGetLastError());
   return CUP2D_OK;
 }
+
+static int block_partials(cup2d_amr *a, int n_per_block) {
+  CUP2D_CUDA(cudaMemcpyAsync(a->h_part.data(), a->d_part, (size_t)a->nb * n_per_block * sizeof(double), cudaMemcpyDeviceToHost,
+                             a->stream));
+  CUP2D_CUDA(cudaStreamSynchronize(a->stream));
+  return CUP2D_OK;
+}
+
+/* main.cpp:6579-6595 with h = the smallest cell size of the mesh */
+int cup2d_amr_compute_dt(cup2d_amr *a, double cfl, double *umax_out, double *dt_out) {
+  CHECK_AMR(a);
+  CUP2D_CUDA(cudaSetDevice(a->device));
+  amr_block_absmax_kernel<<<grid_for(a->nb), 256, 0, a->stream>>>(a->f[CUP2D_VEL], a->d_part, a->nb);
+  CUP2D_CUDA(cudaGetLastError());
+  int rc = block_partials(a, 1);
+  if (rc) return rc;
+  double umax = 0;
+  for (int64_t k = 0; k < a->nb; k++) umax = std::max(umax, a->h_part[k]);
+  const double h = a->hmin;
+  const double dt_diff = 0.25 * h * h / (a->nu + 0.25 * h * umax), dt_adv = h / (umax + 1e-8);
+  if (umax_out) *umax_out = umax;
+  if (dt_out) *dt_out = std::min(dt_diff, cfl * dt_adv);
+  return CUP2D_OK;
+}
+
+/* main.cpp:6607-6642: vold = vel; vel = vold + 0.5 K(vel)/h^2; vel = vold + K(vel)/h^2 (K flux-corrected) */
+int cup2d_amr_advect_diffuse_rk2(cup2d_amr *a, double dt) {
+  CHECK_AMR(a);
+  CUP2D_CUDA(cudaSetDevice(a->device));
+  const int64_t n = a->nb * 128;
+  CUP2D_CUDA(cudaMemcpyAsync(a->f[CUP2D_VOLD], a->f[CUP2D_VEL], n * sizeof(double), cudaMemcpyDeviceToDevice, a->stream));
+  for (int stage = 0; stage < 2; stage++) {
+    int rc = cup2d_amr_advect_diffuse_rhs(a, dt);
+    if (rc) return rc;
+    amr_axpy_h2_kernel<<<grid_for(n), 256, 0, a->stream>>>(a->f[CUP2D_VEL], a->f[CUP2D_VOLD], a->f[CUP2D_TMPV], a->d_h, n,
+                                                          stage == 0 ? 0.5 : 1.0);
+    CUP2D_CUDA(cudaGetLastError());
+  }
+  return CUP2D_OK;
+}
+
+/* main.cpp:7007-7027 as one call: tmp = pressure_rhs(vel, u_def = tmpV, chi); pold = pres; pres = 0; tmp -= lap(pold) */
+int cup2d_amr_poisson_rhs(cup2d_amr *a, double dt) {
+  CHECK_AMR(a);
+  CUP2D_CUDA(cudaSetDevice(a->device));
+  int rc = cup2d_amr_pressure_rhs(a, dt, 0);
+  if (rc) return rc;
+  const size_t bytes = (size_t)a->nb * 64 * sizeof(double);
+  CUP2D_CUDA(cudaMemcpyAsync(a->f[CUP2D_POLD], a->f[CUP2D_PRES], bytes, cudaMemcpyDeviceToDevice, a->stream));
+  CUP2D_CUDA(cudaMemsetAsync(a->f[CUP2D_PRES], 0, bytes, a->stream));
+  if ((rc = gather(a, 2, a->f[CUP2D_POLD], a->lab[2]))) return rc;
+  amr_lap_kernel<<<grid_for(a->nb * 64), 256, 0, a->stream>>>(a->lab[2], a->f[CUP2D_TMP], a->nb * 64);
+  CUP2D_CUDA(cudaGetLastError());
+  return fluxcorr<2>(a, a->lab[2], nullptr, a->f[CUP2D_TMP], dt);
+}
+
+static int weighted_mean(cup2d_amr *a, const double *p, double *mean) {
+  amr_block_wsum_kernel<<<grid_for(a->nb), 256, 0, a->stream>>>(p, a->d_h, a->d_part, a->nb);
+  CUP2D_CUDA(cudaGetLastError());
+  int rc = block_partials(a, 2);
+  if (rc) return rc;
+  double s = 0, w = 0;
+  for (int64_t k = 0; k < a->nb; k++) s += a->h_part[2 * k], w += a->h_part[2 * k + 1];
+  *mean = s / w;
+  return CUP2D_OK;
+}
+
+/* main.cpp:7120-7187 with the solution x of the Poisson solve in `pres`: pres = x - mean_h2(x); pres += pold - mean_h2(pres);
+ * tmpV = pressureCorrectionKernel(pres); vel += tmpV / h^2 */
+int cup2d_amr_pressure_correct(cup2d_amr *a, double dt) {
+  CHECK_AMR(a);
+  CUP2D_CUDA(cudaSetDevice(a->device));
+  const int64_t n = a->nb * 64;
+  double avg = 0;
+  int rc = weighted_mean(a, a->f[CUP2D_PRES], &avg);
+  if (rc) return rc;
+  amr_shift_kernel<<<grid_for(n), 256, 0, a->stream>>>(a->f[CUP2D_PRES], nullptr, nullptr, n, avg);
+  if ((rc = weighted_mean(a, a->f[CUP2D_PRES], &avg))) return rc;
+  amr_shift_kernel<<<grid_for(n), 256, 0, a->stream>>>(a->f[CUP2D_PRES], nullptr, a->f[CUP2D_POLD], n, avg);
+  CUP2D_CUDA(cudaGetLastError());
+  if ((rc = cup2d_amr_pressure_gradient(a, dt))) return rc;
+  amr_axpy_h2_kernel<<<grid_for(2 * n), 256, 0, a->stream>>>(a->f[CUP2D_VEL], a->f[CUP2D_VEL], a->f[CUP2D_TMPV], a->d_h, 2 * n, 1.0);
+  CUP2D_CUDA(cudaGetLastError());
+  return CUP2D_OK;
+}
+
+#ifndef CUP2D_AMR_EMU
+/* the Poisson solve of the step: b = tmp, x0 = pres -> pres, on the general-rows solver (csrc/poisson.cu) with the
+ * rows of cup2d_amr_plan_poisson; same stopping parameters as cup2d_poisson_solve */
+int cup2d_amr_poisson_solve(cup2d_amr *a, double tol_abs, double tol_rel, int max_restarts, int max_iter, int *iters,
+                            double *err) {
+  CHECK_AMR(a);
+  CUP2D_CUDA(cudaSetDevice(a->device));
+  int rc;
+  if (!a->poisson) {
+    int64_t nnz = 0;
+    const int64_t nr = cup2d_amr_plan_poisson(a->plan, nullptr, &nnz, nullptr, nullptr, nullptr, nullptr);
+    if (nr < 0) return (int)nr;
+    std::vector<int32_t> nbr(4 * a->nb), rows(std::max<int64_t>(nr, 1)), rowptr(nr + 1), col(std::max<int64_t>(nnz, 1));
+    std::vector<double> val(std::max<int64_t>(nnz, 1));
+    cup2d_amr_plan_poisson(a->plan, nbr.data(), &nnz, rows.data(), rowptr.data(), col.data(), val.data());
+    if ((rc = cup2d_poisson_create_general(a->nb, nbr.data(), nr, rows.data(), rowptr.data(), col.data(), val.data(), a->device,
+                                           &a->poisson)))
+      return rc;
+  }
+  const size_t bytes = (size_t)a->nb * 64 * sizeof(double);
+  CUP2D_CUDA(cudaStreamSynchronize(a->stream));
+  cudaStream_t ps = (cudaStream_t)cup2d_stream(a->poisson);
+  CUP2D_CUDA(cudaMemcpyAsync(cup2d_field_device_ptr(a->poisson, CUP2D_TMP), a->f[CUP2D_TMP], bytes, cudaMemcpyDeviceToDevice, ps));
+  CUP2D_CUDA(cudaMemcpyAsync(cup2d_field_device_ptr(a->poisson, CUP2D_PRES), a->f[CUP2D_PRES], bytes, cudaMemcpyDeviceToDevice, ps));
+  if ((rc = cup2d_poisson_solve(a->poisson, tol_abs, tol_rel, max_restarts, max_iter, iters, err))) return rc;
+  CUP2D_CUDA(cudaMemcpyAsync(a->f[CUP2D_PRES], cup2d_field_device_ptr(a->poisson, CUP2D_PRES), bytes, cudaMemcpyDeviceToDevice, ps));
+  CUP2D_CUDA(cudaStreamSynchronize(ps));
+  return CUP2D_OK;
+}
+
+/* one time step without bodies (main.cpp:6576-7187 minus the OUT-of-scope parts) on a multi-level mesh */
+int cup2d_amr_step(cup2d_amr *a, double cfl, double dt_in, double tol_abs, double tol_rel, int max_restarts, int max_iter,
+                   double *dt_out, int *iters, double *err) {
+  CHECK_AMR(a);
+  double dt = dt_in, umax = 0;
+  int rc;
+  if (!(dt > 0) && (rc = cup2d_amr_compute_dt(a, cfl, &umax, &dt))) return rc;
+  if ((rc = cup2d_amr_advect_diffuse_rk2(a, dt))) return rc;
+  CUP2D_CUDA(cudaMemsetAsync(a->f[CUP2D_TMPV], 0, (size_t)a->nb * 128 * sizeof(double), a->stream)); // no bodies: u_def = 0
+  if ((rc = cup2d_amr_poisson_rhs(a, dt))) return rc;
+  if ((rc = cup2d_amr_poisson_solve(a, tol_abs, tol_rel, max_restarts, max_iter, iters, err))) return rc;
+  if ((rc = cup2d_amr_pressure_correct(a, dt))) return rc;
+  if (dt_out) *dt_out = dt;
+  return CUP2D_OK;
+}
+#endif
 
 int cup2d_amr_sync(cup2d_amr *a) {
   CHECK_AMR(a);

@@ -239,6 +239,21 @@ int cup2d_amr_advect_diffuse_rhs(cup2d_amr *a, double dt);
 int cup2d_amr_pressure_rhs(cup2d_amr *a, double dt, int with_laplacian);
 /* tmpV = pressureCorrectionKernel(pres) (main.cpp:7174-7179; not flux-corrected in the reference either) */
 int cup2d_amr_pressure_gradient(cup2d_amr *a, double dt);
+/* the pieces of one time step without bodies (main.cpp:6576-7187), cell size per block:
+ *   compute_dt        6579-6595 with h = the smallest cell of the mesh
+ *   advect_diffuse_rk2 6607-6642
+ *   poisson_rhs       7007-7027: tmp = pressure_rhs(vel, u_def = tmpV, chi); pold = pres; pres = 0; tmp -= lap(pold)
+ *   poisson_solve     b = tmp, x0 = pres -> pres, on the general-rows solver with the rows of cup2d_amr_plan_poisson
+ *   pressure_correct  7120-7187: pres = x - mean_h2(x); pres += pold - mean_h2(pres); vel += grad-term / h^2
+ *   step              all of the above with u_def = 0 */
+int cup2d_amr_compute_dt(cup2d_amr *a, double cfl, double *umax_out, double *dt_out);
+int cup2d_amr_advect_diffuse_rk2(cup2d_amr *a, double dt);
+int cup2d_amr_poisson_rhs(cup2d_amr *a, double dt);
+int cup2d_amr_poisson_solve(cup2d_amr *a, double tol_abs, double tol_rel, int max_restarts, int max_iter, int *iters,
+                            double *err);
+int cup2d_amr_pressure_correct(cup2d_amr *a, double dt);
+int cup2d_amr_step(cup2d_amr *a, double cfl, double dt_in, double tol_abs, double tol_rel, int max_restarts, int max_iter,
+                   double *dt_out, int *iters, double *err);
 
 #ifdef __cplusplus
 }

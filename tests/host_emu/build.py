@@ -27,11 +27,11 @@ def build():
     src = src.replace('#include "sim.h"', '#include "cuda_host_shim.h"')
     launch = re.compile(r"(\w+(?:<[^<>;]*>)?)<<<(.*?),\s*(\d+|\w+),\s*0,\s*a->stream>>>\((.*?)\);", re.S)
     src, n = launch.subn(lambda m: f"emu_launch({m.group(2)}, {m.group(3)}, [&] {{ {m.group(1)}({m.group(4)}); }});", src)
-    assert n >= 6 and "<<<" not in src, f"launch rewrite incomplete ({n})"
+    assert n >= 10 and "<<<" not in src, f"launch rewrite incomplete ({n})"
     emu = os.path.join(OUT, "amr_ops_emu.cpp")
     open(emu, "w").write(src + GLUE)
     lib = os.path.join(OUT, "libamr_emu.so")
-    subprocess.run(["/usr/bin/g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-pthread", "-I", HERE, "-o", lib, emu,
+    subprocess.run(["/usr/bin/g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-pthread", "-DCUP2D_AMR_EMU", "-I", HERE, "-o", lib, emu,
                     os.path.join(CSRC, "amr_plan.cpp")], check=True)
     return lib
 

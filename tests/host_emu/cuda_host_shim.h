@@ -5,6 +5,8 @@
 // the product library, and not a CPU fallback of it.
 #pragma once
 #include "../../include/cup2d_b200.h"
+#include <algorithm>
+#include <cmath>
 #include <cstdlib>
 #include <cstring>
 #include <functional>
@@ -28,6 +30,7 @@ inline cudaError_t cudaFree(void *p) { free(p); return 0; }
 inline cudaError_t cudaMemcpy(void *d, const void *s, size_t n, cudaMemcpyKind) { memcpy(d, s, n); return 0; }
 inline cudaError_t cudaMemcpyAsync(void *d, const void *s, size_t n, cudaMemcpyKind, cudaStream_t) { memcpy(d, s, n); return 0; }
 inline cudaError_t cudaMemset(void *d, int v, size_t n) { memset(d, v, n); return 0; }
+inline cudaError_t cudaMemsetAsync(void *d, int v, size_t n, cudaStream_t) { memset(d, v, n); return 0; }
 inline cudaError_t cudaSetDevice(int) { return 0; }
 inline cudaError_t cudaGetDeviceCount(int *n) { *n = 1; return 0; }
 inline cudaError_t cudaStreamCreate(cudaStream_t *s) { *s = nullptr; return 0; }
@@ -45,6 +48,10 @@ inline void emu_launch(int grid, int block, const std::function<void()> &body) {
       body();
     }
 }
+
+using std::fabs;
+using std::fmax;
+struct cup2d_sim;
 
 // what csrc/amr_ops.cu takes from sim.h
 namespace cup2d {

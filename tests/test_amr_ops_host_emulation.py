@@ -75,3 +75,45 @@ def test_emulated_amr_pressure_gradient(emu):
     up("pres", d["pres"])
     assert lib.cup2d_amr_pressure_gradient(h, float(d["dt"])) == 0
     assert rel(down("tmpV", 2), d["gradp"]) < 1e-12
+
+
+def test_emulated_time_step_glue(emu, golden_dir):
+    """dt control, RK2, the Poisson right-hand side and the correction (mean removal with h^2 weights, gradient, velocity
+    update) of csrc/amr_ops.cu against the same pieces composed from the pinned oracle operators"""
+    import cup2d_amr_oracle as amr
+    d, lib, h, up, down = emu
+    D = C.c_double
+    lib.cup2d_amr_compute_dt.argtypes = [C.c_void_p, D, C.POINTER(D), C.POINTER(D)]
+    lib.cup2d_amr_advect_diffuse_rk2.argtypes = [C.c_void_p, D]
+    lib.cup2d_amr_poisson_rhs.argtypes = [C.c_void_p, D]
+    lib.cup2d_amr_pressure_correct.argtypes = [C.c_void_p, D]
+    mesh = amr.Mesh(d["blocks"], int(d["bpdx"]), int(d["bpdy"]))
+    h0, nu = float(d["h0"]), float(d["nu"])
+    up("vel", d["vel"])
+    umax, dt = D(), D()
+    assert lib.cup2d_amr_compute_dt(h, 0.5, C.byref(umax), C.byref(dt)) == 0
+    want_dt = amr.amr_compute_dt(mesh, h0, d["vel"], nu, 0.5)
+    assert umax.value == np.abs(d["vel"]).max() and abs(dt.value - want_dt) <= 1e-15 * want_dt
+    dt = float(d["dt"])
+    # RK2
+    assert lib.cup2d_amr_advect_diffuse_rk2(h, dt) == 0
+    v2 = amr.amr_rk2(mesh, h0, d["vel"], nu, dt)
+    got = down("vel", 2)
+    assert rel(got, v2) < 1e-12 and np.array_equal(down("vold", 2), d["vel"])
+    # Poisson right-hand side (with a body term: u_def = tmpV, chi)
+    up("vel", d["vel"])
+    up("tmpV", d["udef"])
+    up("chi", d["chi"])
+    up("pres", d["pres"])
+    assert lib.cup2d_amr_poisson_rhs(h, dt) == 0
+    tmp, pold, pres0 = amr.amr_poisson_rhs(mesh, h0, d["vel"], d["udef"], d["chi"], d["pres"], dt)
+    assert rel(down("tmp", 1), tmp) < 1e-12 and np.array_equal(down("pold", 1), pold) and not down("pres", 1).any()
+    assert np.array_equal(tmp, d["rhs1"])        # and that composition is the reference's own sequence
+    # correction, with a stand-in for the Poisson solution
+    x = d["pres"][::-1].copy() * 0.7
+    up("pres", x)
+    up("pold", d["pres"])
+    up("vel", d["vel"])
+    assert lib.cup2d_amr_pressure_correct(h, dt) == 0
+    vel, pres = amr.amr_pressure_correct(mesh, h0, d["vel"], x, d["pres"], dt)
+    assert rel(down("pres", 1), pres) < 1e-12 and rel(down("vel", 2), vel) < 1e-12

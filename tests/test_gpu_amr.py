@@ -89,3 +89,30 @@ def test_native_amr_poisson_matrix_on_the_device_solver(golden_dir):
     assert it.value == itr == K
     assert np.abs(x - xr).max() < 1e-9 * np.abs(xr).max()
     assert abs(err.value - errr) < 1e-9 * errr
+
+
+def test_amr_full_step_against_composed_oracle(case):
+    """one whole time step without bodies on the 7-level mesh (dt, RK2, rhs, 15 BiCGSTAB iterations on the native Poisson
+    rows, correction) against the same step composed from the pinned oracle pieces"""
+    import scipy.sparse as sp
+    import cup2d_amr_oracle as amr
+    import cup2d_oracle as orc
+    d, sim = case
+    mesh = amr.Mesh(d["blocks"], int(d["bpdx"]), int(d["bpdy"]))
+    h0, nu, nb = float(d["h0"]), float(d["nu"]), len(d["blocks"])
+    sim.upload("vel", d["vel"])
+    sim.upload("pres", d["pres"])
+    sim.upload("chi", np.zeros_like(d["chi"]))
+    dt, it, err = sim.step(cfl=0.5, max_iter=15)
+    want_dt = amr.amr_compute_dt(mesh, h0, d["vel"], nu, 0.5)
+    assert abs(dt - want_dt) < 1e-15 * want_dt and it == 15
+    v = amr.amr_rk2(mesh, h0, d["vel"], nu, want_dt)
+    zero2, zero1 = np.zeros_like(d["vel"]), np.zeros_like(d["chi"])
+    b, pold, p0 = amr.amr_poisson_rhs(mesh, h0, v, zero2, zero1, d["pres"], want_dt)
+    n = 64 * nb
+    A = sp.coo_matrix((d["coo_val"], (d["coo_row"], d["coo_col"])), shape=(n, n)).tocsr()
+    P = orc.build_P_inv()
+    x, _, _ = orc.bicgstab(b.reshape(-1), p0.reshape(-1), max_iter=15, A=lambda q: A @ q,
+                           M=lambda q: (q.reshape(nb, 64) @ P.T).reshape(-1))
+    vel, pres = amr.amr_pressure_correct(mesh, h0, v, x.reshape(nb, 8, 8, 1), pold, want_dt)
+    assert rel(sim.download("vel"), vel) < 1e-9 and rel(sim.download("pres"), pres) < 1e-9
