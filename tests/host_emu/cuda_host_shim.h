@@ -40,6 +40,7 @@ inline cudaError_t cudaGetLastError() { return 0; }
 inline const char *cudaGetErrorString(cudaError_t) { return "emulated"; }
 
 // kernel<<<grid, block, smem, stream>>>(args)  ->  emu_launch(grid, block, [&] { kernel(args); })   (rewritten by build.py)
+// Serial form: one emulated thread after the other — enough for kernels without shared memory, barriers or shuffles.
 inline void emu_launch(int grid, int block, const std::function<void()> &body) {
   gridDim.x = grid, blockDim.x = block;
   for (int b = 0; b < grid; b++)
@@ -48,6 +49,65 @@ inline void emu_launch(int grid, int block, const std::function<void()> &body) {
       body();
     }
 }
+
+// Cooperative form: the threads of a block are OS threads that really run concurrently and meet at __syncthreads() /
+// __syncwarp() / warp shuffles; blocks run one after the other, so `__shared__` can simply be `static` storage.
+// A thread that returns from the kernel drops out of the barriers (as an exited CUDA thread does).
+#include <barrier>
+#include <memory>
+#include <thread>
+#include <vector>
+struct EmuBlock {
+  std::barrier<> block_bar;
+  std::vector<std::unique_ptr<std::barrier<>>> warp_bar;
+  std::vector<unsigned long long> slot; // shuffle exchange, 32 per warp
+  explicit EmuBlock(int n) : block_bar(n), slot((size_t)((n + 31) / 32) * 32) {
+    for (int w = 0; w < (n + 31) / 32; w++) warp_bar.emplace_back(new std::barrier<>(std::min(32, n - 32 * w)));
+  }
+};
+inline thread_local EmuBlock *emu_block = nullptr;
+inline void __syncthreads() { emu_block->block_bar.arrive_and_wait(); }
+inline void __syncwarp(unsigned = 0xffffffffu) { emu_block->warp_bar[threadIdx.x >> 5]->arrive_and_wait(); }
+template <class T> T emu_shfl(T v, int src_lane) {
+  static_assert(sizeof(T) <= 8, "shuffle of at most 64 bits");
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  unsigned long long bits = 0;
+  memcpy(&bits, &v, sizeof(T));
+  emu_block->slot[w * 32 + l] = bits;
+  __syncwarp();
+  bits = emu_block->slot[w * 32 + (src_lane & 31)];
+  __syncwarp();
+  T r;
+  memcpy(&r, &bits, sizeof(T));
+  return r;
+}
+template <class T> T __shfl_xor_sync(unsigned, T v, int mask) { return emu_shfl(v, (threadIdx.x & 31) ^ mask); }
+template <class T> T __shfl_sync(unsigned, T v, int lane) { return emu_shfl(v, lane); }
+template <class T> T __shfl_down_sync(unsigned, T v, int d) { return emu_shfl(v, std::min(31, (int)(threadIdx.x & 31) + d)); }
+inline void emu_launch_coop(int grid, int block, const std::function<void()> &body) {
+  for (int b = 0; b < grid; b++) {
+    EmuBlock blk(block);
+    std::vector<std::thread> pool;
+    for (int t = 0; t < block; t++)
+      pool.emplace_back([&, t] {
+        gridDim.x = grid, blockDim.x = block, blockIdx.x = b, threadIdx.x = t;
+        emu_block = &blk;
+        body();
+        blk.block_bar.arrive_and_drop();
+        blk.warp_bar[t >> 5]->arrive_and_drop();
+      });
+    for (auto &th : pool) th.join();
+  }
+}
+#define __shared__ static
+#define __align__(n) alignas(n)
+#define __restrict__
+struct double2 { double x, y; };
+struct int2 { int x, y; };
+struct int4 { int x, y, z, w; };
+inline double2 make_double2(double x, double y) { return {x, y}; }
+inline int2 make_int2(int x, int y) { return {x, y}; }
+inline int4 make_int4(int x, int y, int z, int w) { return {x, y, z, w}; }
 
 using std::fabs;
 using std::fmax;
