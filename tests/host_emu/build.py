@@ -31,7 +31,7 @@ def build():
     emu = os.path.join(OUT, "amr_ops_emu.cpp")
     open(emu, "w").write(src + GLUE)
     lib = os.path.join(OUT, "libamr_emu.so")
-    subprocess.run(["/usr/bin/g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-pthread", "-DCUP2D_AMR_EMU", "-I", HERE, "-o", lib, emu,
+    subprocess.run(["/usr/bin/g++", "-O2", "-std=c++20", "-fPIC", "-shared", "-pthread", "-DCUP2D_AMR_EMU", "-I", HERE, "-o", lib, emu,
                     os.path.join(CSRC, "amr_plan.cpp")], check=True)
     return lib
 

@@ -101,7 +101,6 @@ inline void emu_launch_coop(int grid, int block, const std::function<void()> &bo
 }
 #define __shared__ static
 #define __align__(n) alignas(n)
-#define __restrict__
 struct double2 { double x, y; };
 struct int2 { int x, y; };
 struct int4 { int x, y, z, w; };
