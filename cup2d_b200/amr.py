@@ -117,6 +117,9 @@ class AmrSimulation:
     def advect_diffuse_rhs(self, dt):
         _l.check(self.lib.cup2d_amr_advect_diffuse_rhs(self._h, float(dt)))
 
+    def advect_diffuse_rhs_fast(self, dt):
+        _l.check(self.lib.cup2d_amr_advect_diffuse_rhs_fast(self._h, float(dt)))
+
     def pressure_rhs(self, dt, with_laplacian=True):
         _l.check(self.lib.cup2d_amr_pressure_rhs(self._h, float(dt), int(with_laplacian)))
 

@@ -20,54 +20,7 @@
 #include <map>
 #include <vector>
 
-struct cup2d_amr_plan;
-struct cup2d_amr;
-extern "C" {
-void cup2d_amr_destroy(cup2d_amr *a);
-int cup2d_amr_plan_create(int64_t nblocks, const int32_t *level_ij, int32_t bpdx, int32_t bpdy, cup2d_amr_plan **out);
-void cup2d_amr_plan_destroy(cup2d_amr_plan *p);
-int64_t cup2d_amr_plan_stencil(cup2d_amr_plan *p, int which, int64_t *rowptr, int32_t *src_block, int32_t *src_cellcomp,
-                               double *weight);
-int64_t cup2d_amr_plan_faces(cup2d_amr_plan *p, int32_t *out);
-int64_t cup2d_amr_plan_poisson(cup2d_amr_plan *p, int32_t *nbr_out, int64_t *nnz_out, int32_t *irr_rows, int32_t *irr_rowptr,
-                               int32_t *irr_col, double *irr_val);
-int cup2d_amr_advect_diffuse_rhs(cup2d_amr *a, double dt);
-int cup2d_amr_pressure_rhs(cup2d_amr *a, double dt, int with_laplacian);
-int cup2d_amr_pressure_gradient(cup2d_amr *a, double dt);
-}
-
-namespace cup2d {
-
-struct Csr {
-  int64_t *rowptr = nullptr;
-  int *src_block = nullptr, *src_cc = nullptr;
-  double *w = nullptr;
-  int64_t nrows = 0;
-};
-struct CoarseFace { // one coarse-fine face seen from the coarse side
-  int coarse, face, fine[2]; // fine[half] = the fine block abutting that half of the face (-1: absent)
-};
-
-} // namespace cup2d
-
-struct cup2d_amr {
-  int64_t nb = 0;
-  int device = 0;
-  double h0 = 0, nu = 0;
-  cup2d_amr_plan *plan = nullptr;
-  cudaStream_t stream = nullptr;
-  double *f[CUP2D_NFIELDS] = {};
-  double *d_h = nullptr;            // cell size per block
-  cup2d::Csr csr[3];
-  double *lab[3] = {};              // lab buffers (kinds 0, 1, 2); a second kind-1 buffer for u_def
-  double *lab_udef = nullptr;
-  cup2d::CoarseFace *d_cf[2] = {};  // [0] x faces, [1] y faces
-  int ncf[2] = {0, 0};
-  double *d_part = nullptr;         // 2 doubles per block (partial maxima / sums)
-  std::vector<double> h_part;
-  double hmin = 0;
-  cup2d_sim *poisson = nullptr;     // general-rows Poisson context over the same blocks (cup2d_amr_poisson_solve)
-};
+#include "amr.h"
 
 namespace cup2d {
 

@@ -24,7 +24,7 @@ SYMBOLS = [
     "cup2d_amr_create", "cup2d_amr_destroy", "cup2d_amr_field_upload", "cup2d_amr_field_download", "cup2d_amr_sync",
     "cup2d_amr_advect_diffuse_rhs", "cup2d_amr_pressure_rhs", "cup2d_amr_pressure_gradient",
     "cup2d_amr_compute_dt", "cup2d_amr_advect_diffuse_rk2", "cup2d_amr_poisson_rhs", "cup2d_amr_poisson_solve",
-    "cup2d_amr_pressure_correct", "cup2d_amr_step",
+    "cup2d_amr_pressure_correct", "cup2d_amr_step", "cup2d_amr_advect_diffuse_rhs_fast",
 ]
 
 
@@ -114,6 +114,7 @@ def load_library():
     lib.cup2d_amr_plan_poisson.argtypes = [P, C.POINTER(C.c_int32), C.POINTER(L), C.POINTER(C.c_int32), C.POINTER(C.c_int32),
                                            C.POINTER(C.c_int32), C.POINTER(D)]
     lib.cup2d_amr_plan_poisson.restype = L
+    lib.cup2d_amr_advect_diffuse_rhs_fast.argtypes = [P, D]
     lib.cup2d_amr_compute_dt.argtypes = [P, D, C.POINTER(D), C.POINTER(D)]
     lib.cup2d_amr_advect_diffuse_rk2.argtypes = [P, D]
     lib.cup2d_amr_poisson_rhs.argtypes = [P, D]

@@ -1,14 +1,17 @@
-"""TEST INFRASTRUCTURE: builds tests/host_emu/_build/libamr_emu.so = csrc/amr_ops.cu (kernel launches rewritten into
-serial loops, CUDA runtime calls mapped to malloc/memcpy by cuda_host_shim.h) + csrc/amr_plan.cpp, with g++.
-The product library is NOT involved and nothing here ships."""
+"""TEST INFRASTRUCTURE: builds tests/host_emu/_build/libamr_emu.so = csrc/amr_ops.cu + csrc/amr_fast.cu (kernel launches
+rewritten into emulated launches, CUDA runtime calls mapped to malloc/memcpy by cuda_host_shim.h, the one PTX instruction of
+weno.cuh replaced by a single-precision reciprocal seed) + csrc/amr_plan.cpp, with g++.  The product library is NOT involved
+and nothing here ships."""
 import os
 import re
+import shutil
 import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "cup2d_b200", "csrc")
 OUT = os.path.join(HERE, "_build")
+COOP = {"amr_advect_fast_kernel"}   # kernels that use shared memory / warp barriers: threads must really run together
 
 GLUE = r'''
 #include <string>
@@ -20,19 +23,41 @@ int dim_of(int f) { return (f == CUP2D_VEL || f == CUP2D_VOLD || f == CUP2D_TMPV
 extern "C" const char *cup2d_last_error(void) { return cup2d::g_err.c_str(); }
 '''
 
+LAUNCH = re.compile(r"(\w+)((?:<[^<>;]*>)?)<<<(.*?),\s*(\w+),\s*(\w+),\s*a->stream>>>\((.*?)\);", re.S)
+
+
+def rewrite(src):
+    def sub(m):
+        name, targs, grid, block, _smem, args = m.groups()
+        fn = "emu_launch_coop" if name in COOP else "emu_launch"
+        return f"{fn}({grid}, {block}, [&] {{ {name}{targs}({args}); }});"
+    src, n = LAUNCH.subn(sub, src)
+    assert "<<<" not in src, "launch rewrite incomplete"
+    src = src.replace("extern __shared__ __align__(16) double af_smem[];", "static double af_smem[AF_SMEM / 8];")
+    return src, n
+
 
 def build():
     os.makedirs(OUT, exist_ok=True)
-    src = open(os.path.join(CSRC, "amr_ops.cu")).read()
-    src = src.replace('#include "sim.h"', '#include "cuda_host_shim.h"')
-    launch = re.compile(r"(\w+(?:<[^<>;]*>)?)<<<(.*?),\s*(\d+|\w+),\s*0,\s*a->stream>>>\((.*?)\);", re.S)
-    src, n = launch.subn(lambda m: f"emu_launch({m.group(2)}, {m.group(3)}, [&] {{ {m.group(1)}({m.group(4)}); }});", src)
-    assert n >= 10 and "<<<" not in src, f"launch rewrite incomplete ({n})"
-    emu = os.path.join(OUT, "amr_ops_emu.cpp")
-    open(emu, "w").write(src + GLUE)
+    open(os.path.join(OUT, "sim.h"), "w").write('#pragma once\n#include "cuda_host_shim.h"\n')
+    open(os.path.join(OUT, "common.cuh"), "w").write('#pragma once\n#include "cuda_host_shim.h"\n')
+    shutil.copy(os.path.join(CSRC, "amr.h"), OUT)
+    weno = open(os.path.join(CSRC, "weno.cuh")).read()
+    weno, k = re.subn(r'asm\("rcp\.approx\.ftz\.f64 %0, %1;" : "=d"\(r\) : "d"\(x\)\);', "r = (double)(1.0f / (float)x);", weno)
+    assert k == 1, "reciprocal seed not found in weno.cuh"
+    open(os.path.join(OUT, "weno.cuh"), "w").write(weno)
+    total = 0
+    srcs = []
+    for name in ("amr_ops.cu", "amr_fast.cu"):
+        src, n = rewrite(open(os.path.join(CSRC, name)).read())
+        total += n
+        dst = os.path.join(OUT, name.replace(".cu", "_emu.cpp"))
+        open(dst, "w").write(src + (GLUE if name == "amr_ops.cu" else ""))
+        srcs.append(dst)
+    assert total >= 12, f"only {total} launches rewritten"
     lib = os.path.join(OUT, "libamr_emu.so")
-    subprocess.run(["/usr/bin/g++", "-O2", "-std=c++20", "-fPIC", "-shared", "-pthread", "-DCUP2D_AMR_EMU", "-I", HERE, "-o", lib, emu,
-                    os.path.join(CSRC, "amr_plan.cpp")], check=True)
+    subprocess.run(["/usr/bin/g++", "-O2", "-std=c++20", "-fPIC", "-shared", "-pthread", "-DCUP2D_AMR_EMU", "-I", OUT, "-I", HERE,
+                    "-o", lib, *srcs, os.path.join(CSRC, "amr_plan.cpp")], check=True)
     return lib
 
 

@@ -17,6 +17,7 @@
 #define __host__
 #define __forceinline__ inline
 #define __launch_bounds__(...)
+#define __constant__
 
 typedef int cudaError_t;
 typedef void *cudaStream_t;
@@ -109,7 +110,14 @@ inline int2 make_int2(int x, int y) { return {x, y}; }
 inline int4 make_int4(int x, int y, int z, int w) { return {x, y, z, w}; }
 
 using std::fabs;
+using std::fma;
 using std::fmax;
+enum { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
+template <class F> cudaError_t cudaFuncSetAttribute(F, int, int) { return 0; }
+template <class T, class U> cudaError_t cudaMemcpyToSymbol(T &sym, const U &src, size_t n) { memcpy(&sym, &src, n); return 0; }
+namespace cup2d {
+inline bool is_pos(double x) { return !(x <= 0); } // U > 0, NaN counted as positive (common.cuh)
+}
 struct cup2d_sim;
 
 // what csrc/amr_ops.cu takes from sim.h

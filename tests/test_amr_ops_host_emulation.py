@@ -117,3 +117,17 @@ def test_emulated_time_step_glue(emu, golden_dir):
     assert lib.cup2d_amr_pressure_correct(h, dt) == 0
     vel, pres = amr.amr_pressure_correct(mesh, h0, d["vel"], x, d["pres"], dt)
     assert rel(down("pres", 1), pres) < 1e-12 and rel(down("vel", 2), vel) < 1e-12
+
+
+def test_emulated_fast_advect_kernel(emu):
+    """csrc/amr_fast.cu (per-block lab loader on the WENO line core of the uniform-grid kernel, compact ghost tables,
+    stored face fluxes): emulated with real concurrent threads per block (shared memory, warp barriers) — same result as
+    the reference's flux-corrected KernelAdvectDiffuse, and as the table-gather baseline"""
+    d, lib, h, up, down = emu
+    lib.cup2d_amr_advect_diffuse_rhs_fast.argtypes = [C.c_void_p, C.c_double]
+    up("vel", d["vel"])
+    assert lib.cup2d_amr_advect_diffuse_rhs_fast(h, float(d["dt"])) == 0
+    fast = down("tmpV", 2)
+    assert rel(fast, d["adv"]) < 1e-12
+    assert lib.cup2d_amr_advect_diffuse_rhs(h, float(d["dt"])) == 0
+    assert rel(fast, down("tmpV", 2)) < 1e-12

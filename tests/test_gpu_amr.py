@@ -33,6 +33,13 @@ def test_amr_advect_diffuse_with_flux_correction(case):
     assert rel(sim.download("tmpV"), d["adv"]) < 1e-12
 
 
+def test_amr_fast_advect_kernel(case):
+    d, sim = case
+    sim.upload("vel", d["vel"])
+    sim.advect_diffuse_rhs_fast(float(d["dt"]))
+    assert rel(sim.download("tmpV"), d["adv"]) < 1e-12
+
+
 def test_amr_pressure_rhs_and_laplacian(case):
     d, sim = case
     sim.upload("vel", d["vel"])
