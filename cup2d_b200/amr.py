@@ -120,6 +120,12 @@ class AmrSimulation:
     def advect_diffuse_rhs_fast(self, dt):
         _l.check(self.lib.cup2d_amr_advect_diffuse_rhs_fast(self._h, float(dt)))
 
+    def pressure_rhs_fast(self, dt, with_laplacian=True):
+        _l.check(self.lib.cup2d_amr_pressure_rhs_fast(self._h, float(dt), int(with_laplacian)))
+
+    def pressure_gradient_fast(self, dt):
+        _l.check(self.lib.cup2d_amr_pressure_gradient_fast(self._h, float(dt)))
+
     def pressure_rhs(self, dt, with_laplacian=True):
         _l.check(self.lib.cup2d_amr_pressure_rhs(self._h, float(dt), int(with_laplacian)))
 

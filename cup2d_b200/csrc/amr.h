@@ -27,6 +27,12 @@ struct Csr {
   double *w = nullptr;
   int64_t nrows = 0;
 };
+struct GhostDev { // compact ghost CSR of one stencil kind on the device
+  int64_t *grow = nullptr;    // [nirr+1] first row of every irregular block
+  int64_t *rowptr = nullptr;
+  int *dst = nullptr, *sb = nullptr, *sc = nullptr;
+  double *w = nullptr;
+};
 struct CoarseFace { // one coarse-fine face seen from the coarse side
   int coarse, face, fine[2]; // fine[half] = the fine block abutting that half of the face (-1: absent)
 };
@@ -50,14 +56,11 @@ struct cup2d_amr {
   std::vector<double> h_part;
   double hmin = 0;
   cup2d_sim *poisson = nullptr;     // general-rows Poisson context over the same blocks (cup2d_amr_poisson_solve)
-  // fast advect path (csrc/amr_fast.cu)
+  // fast paths (csrc/amr_fast.cu)
   int *d_nbr4 = nullptr;            // [nb][4] W,E,S,N: same-level block, -1 wall, -2 coarser/finer
   int *d_irr_of = nullptr;          // [nb] position in the irregular list or -1
   int64_t nirr = 0;
-  int64_t *d_grow = nullptr;        // [nirr+1] first ghost row of every irregular block in the compact table
-  int64_t *d_growptr = nullptr;     // compact ghost CSR (cup2d_amr_plan_ghosts, advect stencil)
-  int *d_gdst = nullptr, *d_gsb = nullptr, *d_gsc = nullptr;
-  double *d_gw = nullptr;
+  cup2d::GhostDev gt[3];            // compact ghost tables per stencil kind (cup2d_amr_plan_ghosts)
   double *d_faceflux = nullptr;     // [nirr][4 faces][8][2] face fluxes of the irregular blocks
 };
 

@@ -41,10 +41,8 @@ constexpr int AF_SMEM = AF_WARPS * AF_BPW * AF_BLK * 8; // 72 192 B per CTA -> 3
 
 __global__ void __launch_bounds__(AF_NT)
 amr_advect_fast_kernel(const double *__restrict__ vel, double *__restrict__ out, const int4 *__restrict__ nbr4,
-                       const int *__restrict__ irr_of, const int64_t *__restrict__ grow, const int64_t *__restrict__ growptr,
-                       const int *__restrict__ gdst, const int *__restrict__ gsb, const int *__restrict__ gsc,
-                       const double *__restrict__ gw, const double *__restrict__ hb, double *__restrict__ faceflux,
-                       int nb, double nu, double dt) {
+                       const int *__restrict__ irr_of, const GhostDev gt, const double *__restrict__ hb,
+                       double *__restrict__ faceflux, int nb, double nu, double dt) {
   extern __shared__ __align__(16) double af_smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int q = lane >> 3, r = lane & 7;
@@ -94,10 +92,10 @@ amr_advect_fast_kernel(const double *__restrict__ vel, double *__restrict__ out,
     const int qi = irr_of[k];
     if (qi < 0) continue;
     double *su = base + qq * AF_BLK;
-    for (int64_t row = grow[qi] + lane; row < grow[qi + 1]; row += 32) {
+    for (int64_t row = gt.grow[qi] + lane; row < gt.grow[qi + 1]; row += 32) {
       double acc = 0.0;
-      for (int64_t e = growptr[row]; e < growptr[row + 1]; e++) acc += gw[e] * vel[(size_t)gsb[e] * 128 + gsc[e]];
-      const int cc = gdst[row] % (14 * 14 * 2); // (lab row * 14 + lab column) * 2 + component
+      for (int64_t e = gt.rowptr[row]; e < gt.rowptr[row + 1]; e++) acc += gt.w[e] * vel[(size_t)gt.sb[e] * 128 + gt.sc[e]];
+      const int cc = gt.dst[row] % (14 * 14 * 2); // (lab row * 14 + lab column) * 2 + component
       const int comp = cc & 1, lx = (cc >> 1) % 14, ly = (cc >> 1) / 14;
       su[comp * AF_PLANE + ly * AF_PS + lx] = acc;
     }
@@ -144,14 +142,137 @@ amr_advect_fast_kernel(const double *__restrict__ vel, double *__restrict__ out,
   });
 }
 
+// ---- the +-1 stencils (pressure_rhs, pressure_rhs1, pressureCorrectionKernel): 10x10 labs, one warp = four blocks ----
+constexpr int A1_WARPS = 2, A1_NT = 64, A1_PS = 11, A1_PLANE = 10 * A1_PS;
+
+// the whole warp loads the +-1 lab of block k into DIM planes: interior, one ghost layer per face from the neighbour
+// table (vector fields: normal component negated at walls, main.cpp:3144-3154; scalars: copied, main.cpp:3239-3244), then
+// the ghost rows of the compact table if the block has a coarser / finer neighbour.  Ends with a __syncwarp.
+template <int DIM>
+__device__ __forceinline__ void load_lab1(double *pl, const double *__restrict__ field, int k, const int4 nbk, int qi,
+                                          const GhostDev &gt, int lane) {
+  for (int i = lane; i < 64; i += 32)
+    for (int d = 0; d < DIM; d++) pl[d * A1_PLANE + ((i >> 3) + 1) * A1_PS + (i & 7) + 1] = field[((size_t)k * 64 + i) * DIM + d];
+  {
+    const int f = lane >> 3, t = lane & 7;
+    const int nbf = f == 0 ? nbk.x : f == 1 ? nbk.y : f == 2 ? nbk.z : nbk.w;
+    if (nbf >= -1) {
+      int ix, iy, sx, sy;
+      if (f < 2) ix = f == 0 ? -1 : 8, iy = t, sx = nbf >= 0 ? (f == 0 ? 7 : 0) : (f == 0 ? 0 : 7), sy = t;
+      else ix = t, iy = f == 2 ? -1 : 8, sx = t, sy = nbf >= 0 ? (f == 2 ? 7 : 0) : (f == 2 ? 0 : 7);
+      for (int d = 0; d < DIM; d++) {
+        double v = field[((size_t)(nbf >= 0 ? nbf : k) * 64 + sy * 8 + sx) * DIM + d];
+        if (DIM == 2 && nbf < 0 && d == (f < 2 ? 0 : 1)) v = -v;
+        pl[d * A1_PLANE + (iy + 1) * A1_PS + ix + 1] = v;
+      }
+    }
+  }
+  __syncwarp();
+  if (qi >= 0)
+    for (int64_t row = gt.grow[qi] + lane; row < gt.grow[qi + 1]; row += 32) {
+      double acc = 0.0;
+      for (int64_t e = gt.rowptr[row]; e < gt.rowptr[row + 1]; e++) acc += gt.w[e] * field[(size_t)gt.sb[e] * 64 * DIM + gt.sc[e]];
+      const int cc = gt.dst[row] % (10 * 10 * DIM);
+      const int d = cc % DIM, lx = (cc / DIM) % 10, ly = (cc / DIM) / 10;
+      pl[d * A1_PLANE + ly * A1_PS + lx] = acc;
+    }
+  __syncwarp();
+}
+__device__ __forceinline__ void face_pos(int f, int t, int &pi, int &pg) { // inner cell and ghost behind face f at position t
+  int ix, iy, gx, gy;
+  if (f < 2) ix = f == 0 ? 0 : 7, iy = t, gx = f == 0 ? -1 : 8, gy = t;
+  else ix = t, iy = f == 2 ? 0 : 7, gx = t, gy = f == 2 ? -1 : 8;
+  pi = (iy + 1) * A1_PS + ix + 1, pg = (gy + 1) * A1_PS + gx + 1;
+}
+
+// tmp = pressure_rhs(vel, u_def, chi) (main.cpp:6105-6139) + the face fluxes of main.cpp:6152-6205
+__global__ void __launch_bounds__(A1_NT)
+amr_div_fast_kernel(const double *__restrict__ vel, const double *__restrict__ udef, const double *__restrict__ chi,
+                    double *__restrict__ tmp, const int4 *__restrict__ nbr4, const int *__restrict__ irr_of, const GhostDev gt,
+                    const double *__restrict__ hb, double *__restrict__ faceflux, int nb, double dt) {
+  __shared__ double s_lab[A1_WARPS * 4 * 4 * A1_PLANE];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, q = lane >> 3, r = lane & 7;
+  const int b0 = (blockIdx.x * A1_WARPS + warp) * 4;
+  if (b0 >= nb) return;
+  double *base = s_lab + warp * 4 * 4 * A1_PLANE;
+  for (int qq = 0; qq < 4 && b0 + qq < nb; qq++) {
+    const int k = b0 + qq;
+    load_lab1<2>(base + qq * 4 * A1_PLANE, vel, k, nbr4[k], irr_of[k], gt, lane);
+    load_lab1<2>(base + qq * 4 * A1_PLANE + 2 * A1_PLANE, udef, k, nbr4[k], irr_of[k], gt, lane);
+  }
+  for (int qq = 0; qq < 4 && b0 + qq < nb; qq++) { // face fluxes: lane = (face q, position r)
+    const int k = b0 + qq, qi = irr_of[k];
+    if (qi < 0) continue;
+    const double *vu = base + qq * 4 * A1_PLANE, *uu = vu + 2 * A1_PLANE;
+    const double fac = 0.5 * hb[k] / dt;
+    int pi, pg;
+    face_pos(q, r, pi, pg);
+    const int c = q < 2 ? 0 : 1;
+    const double sv = vu[c * A1_PLANE + pg] + vu[c * A1_PLANE + pi], su = uu[c * A1_PLANE + pg] + uu[c * A1_PLANE + pi];
+    const int ix = q < 2 ? (q == 0 ? 0 : 7) : r, iy = q < 2 ? r : (q == 2 ? 0 : 7);
+    const double x = chi[(size_t)k * 64 + iy * 8 + ix];
+    faceflux[((size_t)qi * 4 + q) * 8 + r] = (q & 1) == 0 ? fac * sv - (fac * x) * su : -fac * sv + (fac * x) * su;
+  }
+  const int k = b0 + q;
+  if (k >= nb) return;
+  const double *vu = base + q * 4 * A1_PLANE, *vv = vu + A1_PLANE, *uu = vv + A1_PLANE, *uv = uu + A1_PLANE;
+  const double fac = 0.5 * hb[k] / dt;
+  const int row = (r + 1) * A1_PS + 1;
+  for (int i = 0; i < 8; i++) {
+    const int p = row + i;
+    const double dv = ((vu[p + 1] - vu[p - 1]) + vv[p + A1_PS]) - vv[p - A1_PS];
+    const double du = ((uu[p + 1] - uu[p - 1]) + uv[p + A1_PS]) - uv[p - A1_PS];
+    const size_t cell = (size_t)k * 64 + r * 8 + i;
+    tmp[cell] = fac * dv - fac * chi[cell] * du;
+  }
+}
+
+// MODE 0: tmp -= lap(p) (main.cpp:6209-6230) + face fluxes (6243-6283);  MODE 1: tmpV = pressureCorrectionKernel(p) (6021-6043)
+template <int MODE>
+__global__ void __launch_bounds__(A1_NT)
+amr_scalar_fast_kernel(const double *__restrict__ p, double *__restrict__ out, const int4 *__restrict__ nbr4,
+                       const int *__restrict__ irr_of, const GhostDev gt, const double *__restrict__ hb,
+                       double *__restrict__ faceflux, int nb, double dt) {
+  __shared__ double s_lab[A1_WARPS * 4 * A1_PLANE];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, q = lane >> 3, r = lane & 7;
+  const int b0 = (blockIdx.x * A1_WARPS + warp) * 4;
+  if (b0 >= nb) return;
+  double *base = s_lab + warp * 4 * A1_PLANE;
+  for (int qq = 0; qq < 4 && b0 + qq < nb; qq++) load_lab1<1>(base + qq * A1_PLANE, p, b0 + qq, nbr4[b0 + qq], irr_of[b0 + qq], gt, lane);
+  if (MODE == 0)
+    for (int qq = 0; qq < 4 && b0 + qq < nb; qq++) {
+      const int qi = irr_of[b0 + qq];
+      if (qi < 0) continue;
+      int pi, pg;
+      face_pos(q, r, pi, pg);
+      const double *m = base + qq * A1_PLANE;
+      faceflux[((size_t)qi * 4 + q) * 8 + r] = m[pg] - m[pi];
+    }
+  const int k = b0 + q;
+  if (k >= nb) return;
+  const double *m = base + q * A1_PLANE;
+  const int row = (r + 1) * A1_PS + 1;
+  const double pfac = -0.5 * dt * hb[k];
+  for (int i = 0; i < 8; i++) {
+    const int c = row + i;
+    const size_t cell = (size_t)k * 64 + r * 8 + i;
+    if (MODE == 0) out[cell] -= (((m[c - 1] + m[c + 1]) + m[c - A1_PS]) + m[c + A1_PS]) - 4 * m[c];
+    else {
+      out[2 * cell] = pfac * (m[c + 1] - m[c - 1]);
+      out[2 * cell + 1] = pfac * (m[c + A1_PS] - m[c - A1_PS]);
+    }
+  }
+}
+
 // fillcases per coarse face from the stored face fluxes (see amr_fluxcorr_kernel in amr_ops.cu for the formulation)
+template <int DIM>
 __global__ void amr_fluxcorr_faces_kernel(const CoarseFace *__restrict__ cf, int ncf, const double *__restrict__ faceflux,
                                           const int *__restrict__ irr_of, double *__restrict__ result) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= ncf * 16) return;
-  const int comp = i & 1, t = (i >> 1) & 7;
-  const CoarseFace f = cf[i >> 4];
-  auto flux = [&](int blk, int face, int pos) { return faceflux[(((size_t)irr_of[blk] * 4 + face) * 8 + pos) * 2 + comp]; };
+  if (i >= ncf * 8 * DIM) return;
+  const int comp = i % DIM, t = (i / DIM) % 8;
+  const CoarseFace f = cf[i / (8 * DIM)];
+  auto flux = [&](int blk, int face, int pos) { return faceflux[(((size_t)irr_of[blk] * 4 + face) * 8 + pos) * DIM + comp]; };
   double acc = flux(f.coarse, f.face, t);
   const int fb = f.fine[t >> 2];
   if (fb >= 0) {
@@ -159,14 +280,25 @@ __global__ void amr_fluxcorr_faces_kernel(const CoarseFace *__restrict__ cf, int
     acc += flux(fb, f.face ^ 1, t2) + flux(fb, f.face ^ 1, t2 + 1);
   }
   const int ix = f.face < 2 ? (f.face == 0 ? 0 : 7) : t, iy = f.face < 2 ? t : (f.face == 2 ? 0 : 7);
-  double *dst = result + ((size_t)f.coarse * 64 + iy * 8 + ix) * 2 + comp;
+  double *dst = result + ((size_t)f.coarse * 64 + iy * 8 + ix) * DIM + comp;
   double v = *dst + acc;
-  if (f.fine[0] >= 0 && f.fine[1] >= 0 && 2 * t + comp >= 9) v += acc; // second pass of fillcase1 (property 3)
+  if (DIM == 2 && f.fine[0] >= 0 && f.fine[1] >= 0 && 2 * t + comp >= 9) v += acc; // second pass of fillcase1 (property 3)
   *dst = v;
 }
 
+template <int DIM> static int fluxcorr_faces(cup2d_amr *a, double *result) {
+  for (int dir = 0; dir < 2; dir++) { // x faces, then y faces (fillcases order)
+    const int n = a->ncf[dir] * 8 * DIM;
+    if (n == 0) continue;
+    amr_fluxcorr_faces_kernel<DIM><<<(n + 127) / 128, 128, 0, a->stream>>>(a->d_cf[dir], a->ncf[dir], a->d_faceflux, a->d_irr_of,
+                                                                         result);
+  }
+  CUP2D_CUDA(cudaGetLastError());
+  return CUP2D_OK;
+}
+
 static int fast_setup(cup2d_amr *a) {
-  if (a->d_nbr4) return CUP2D_OK;
+  if (a->d_faceflux) return CUP2D_OK;
   const int64_t nb = a->nb;
   std::vector<int32_t> n8(8 * nb), n4(4 * nb), irr_of(nb, -1);
   if (cup2d_amr_plan_neighbours(a->plan, n8.data())) return CUP2D_EINVAL;
@@ -178,15 +310,6 @@ static int fast_setup(cup2d_amr *a) {
   std::vector<int32_t> irr(std::max<int64_t>(nirr, 1));
   cup2d_amr_plan_irregular(a->plan, irr.data());
   for (int64_t qi = 0; qi < nirr; qi++) irr_of[irr[qi]] = (int32_t)qi;
-  int64_t nrows = 0;
-  const int64_t nnz = cup2d_amr_plan_ghosts(a->plan, 0, &nrows, nullptr, nullptr, nullptr, nullptr, nullptr);
-  if (nnz < 0) return CUP2D_EINVAL;
-  std::vector<int64_t> rp(nrows + 1), grow(nirr + 1, nrows);
-  std::vector<int32_t> dst(std::max<int64_t>(nrows, 1)), sb(std::max<int64_t>(nnz, 1)), sc(std::max<int64_t>(nnz, 1));
-  std::vector<double> w(std::max<int64_t>(nnz, 1));
-  cup2d_amr_plan_ghosts(a->plan, 0, &nrows, rp.data(), dst.data(), sb.data(), sc.data(), w.data());
-  for (int64_t row = nrows - 1; row >= 0; row--) grow[dst[row] / (14 * 14 * 2)] = row; // rows are grouped by block, in order
-  for (int64_t qi = nirr - 1; qi >= 0; qi--) grow[qi] = std::min(grow[qi], grow[qi + 1]); // blocks without rows
   a->nirr = nirr;
   auto up = [](auto **d, const auto &h) -> cudaError_t {
     using T = typename std::remove_reference<decltype(h[0])>::type;
@@ -194,14 +317,27 @@ static int fast_setup(cup2d_amr *a) {
     if (e != cudaSuccess) return e;
     return cudaMemcpy(*d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice);
   };
+  const int ncell[3] = {14 * 14 * 2, 10 * 10 * 2, 10 * 10};
+  for (int which = 0; which < 3; which++) {
+    int64_t nrows = 0;
+    const int64_t nnz = cup2d_amr_plan_ghosts(a->plan, which, &nrows, nullptr, nullptr, nullptr, nullptr, nullptr);
+    if (nnz < 0) return CUP2D_EINVAL;
+    std::vector<int64_t> rp(nrows + 1), grow(nirr + 1, nrows);
+    std::vector<int32_t> dst(std::max<int64_t>(nrows, 1)), sb(std::max<int64_t>(nnz, 1)), sc(std::max<int64_t>(nnz, 1));
+    std::vector<double> w(std::max<int64_t>(nnz, 1));
+    cup2d_amr_plan_ghosts(a->plan, which, &nrows, rp.data(), dst.data(), sb.data(), sc.data(), w.data());
+    for (int64_t row = nrows - 1; row >= 0; row--) grow[dst[row] / ncell[which]] = row; // rows are grouped by block, in order
+    for (int64_t qi = nirr - 1; qi >= 0; qi--) grow[qi] = std::min(grow[qi], grow[qi + 1]); // blocks without rows
+    GhostDev &g = a->gt[which];
+    CUP2D_CUDA(up(&g.grow, grow));
+    CUP2D_CUDA(up(&g.rowptr, rp));
+    CUP2D_CUDA(up(&g.dst, dst));
+    CUP2D_CUDA(up(&g.sb, sb));
+    CUP2D_CUDA(up(&g.sc, sc));
+    CUP2D_CUDA(up(&g.w, w));
+  }
   CUP2D_CUDA(up(&a->d_nbr4, n4));
   CUP2D_CUDA(up(&a->d_irr_of, irr_of));
-  CUP2D_CUDA(up(&a->d_grow, grow));
-  CUP2D_CUDA(up(&a->d_growptr, rp));
-  CUP2D_CUDA(up(&a->d_gdst, dst));
-  CUP2D_CUDA(up(&a->d_gsb, sb));
-  CUP2D_CUDA(up(&a->d_gsc, sc));
-  CUP2D_CUDA(up(&a->d_gw, w));
   CUP2D_CUDA(cudaMalloc(&a->d_faceflux, std::max<int64_t>(nirr, 1) * 64 * sizeof(double)));
   CUP2D_CUDA(cudaMemcpyToSymbol(cW, hW, sizeof hW));
   CUP2D_CUDA(cudaFuncSetAttribute(amr_advect_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AF_SMEM));
@@ -226,15 +362,44 @@ int cup2d_amr_advect_diffuse_rhs_fast(cup2d_amr *a, double dt) {
   const int per_cta = AF_WARPS * AF_BPW;
   const int grid = (int)((a->nb + per_cta - 1) / per_cta);
   amr_advect_fast_kernel<<<grid, AF_NT, AF_SMEM, a->stream>>>(
-      a->f[CUP2D_VEL], a->f[CUP2D_TMPV], reinterpret_cast<const int4 *>(a->d_nbr4), a->d_irr_of, a->d_grow, a->d_growptr,
-      a->d_gdst, a->d_gsb, a->d_gsc, a->d_gw, a->d_h, a->d_faceflux, (int)a->nb, a->nu, dt);
+      a->f[CUP2D_VEL], a->f[CUP2D_TMPV], reinterpret_cast<const int4 *>(a->d_nbr4), a->d_irr_of, a->gt[0], a->d_h,
+      a->d_faceflux, (int)a->nb, a->nu, dt);
   CUP2D_CUDA(cudaGetLastError());
-  for (int dir = 0; dir < 2; dir++) { // x faces, then y faces (fillcases order)
-    const int n = a->ncf[dir] * 16;
-    if (n == 0) continue;
-    amr_fluxcorr_faces_kernel<<<(n + 127) / 128, 128, 0, a->stream>>>(a->d_cf[dir], a->ncf[dir], a->d_faceflux, a->d_irr_of,
-                                                                    a->f[CUP2D_TMPV]);
+  return fluxcorr_faces<2>(a, a->f[CUP2D_TMPV]);
+}
+
+/* same results as cup2d_amr_pressure_rhs / cup2d_amr_pressure_gradient through per-block +-1 labs in shared memory */
+int cup2d_amr_pressure_rhs_fast(cup2d_amr *a, double dt, int with_laplacian) {
+  if (!a) {
+    set_error("null cup2d_amr handle");
+    return CUP2D_EINVAL;
   }
+  CUP2D_CUDA(cudaSetDevice(a->device));
+  int rc = fast_setup(a);
+  if (rc) return rc;
+  const int grid = (int)((a->nb + A1_WARPS * 4 - 1) / (A1_WARPS * 4));
+  const int4 *nbr4 = reinterpret_cast<const int4 *>(a->d_nbr4);
+  amr_div_fast_kernel<<<grid, A1_NT, 0, a->stream>>>(a->f[CUP2D_VEL], a->f[CUP2D_TMPV], a->f[CUP2D_CHI], a->f[CUP2D_TMP], nbr4,
+                                                     a->d_irr_of, a->gt[1], a->d_h, a->d_faceflux, (int)a->nb, dt);
+  CUP2D_CUDA(cudaGetLastError());
+  if ((rc = fluxcorr_faces<1>(a, a->f[CUP2D_TMP])) || !with_laplacian) return rc;
+  amr_scalar_fast_kernel<0><<<grid, A1_NT, 0, a->stream>>>(a->f[CUP2D_POLD], a->f[CUP2D_TMP], nbr4, a->d_irr_of, a->gt[2], a->d_h,
+                                                           a->d_faceflux, (int)a->nb, dt);
+  CUP2D_CUDA(cudaGetLastError());
+  return fluxcorr_faces<1>(a, a->f[CUP2D_TMP]);
+}
+
+int cup2d_amr_pressure_gradient_fast(cup2d_amr *a, double dt) {
+  if (!a) {
+    set_error("null cup2d_amr handle");
+    return CUP2D_EINVAL;
+  }
+  CUP2D_CUDA(cudaSetDevice(a->device));
+  int rc = fast_setup(a);
+  if (rc) return rc;
+  const int grid = (int)((a->nb + A1_WARPS * 4 - 1) / (A1_WARPS * 4));
+  amr_scalar_fast_kernel<1><<<grid, A1_NT, 0, a->stream>>>(a->f[CUP2D_PRES], a->f[CUP2D_TMPV], reinterpret_cast<const int4 *>(a->d_nbr4),
+                                                           a->d_irr_of, a->gt[2], a->d_h, a->d_faceflux, (int)a->nb, dt);
   CUP2D_CUDA(cudaGetLastError());
   return CUP2D_OK;
 }

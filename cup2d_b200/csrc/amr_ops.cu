@@ -362,6 +362,10 @@ void cup2d_amr_destroy(cup2d_amr *a) {
   }
   for (auto p : a->lab) cudaFree(p);
   cudaFree(a->lab_udef); cudaFree(a->d_h); cudaFree(a->d_cf[0]); cudaFree(a->d_cf[1]); cudaFree(a->d_part);
+  cudaFree(a->d_nbr4); cudaFree(a->d_irr_of); cudaFree(a->d_faceflux);
+  for (auto &g : a->gt) {
+    cudaFree(g.grow); cudaFree(g.rowptr); cudaFree(g.dst); cudaFree(g.sb); cudaFree(g.sc); cudaFree(g.w);
+  }
 #ifndef CUP2D_AMR_EMU
   if (a->poisson) cup2d_destroy(a->poisson);
 #endif

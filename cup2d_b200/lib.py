@@ -25,6 +25,7 @@ SYMBOLS = [
     "cup2d_amr_advect_diffuse_rhs", "cup2d_amr_pressure_rhs", "cup2d_amr_pressure_gradient",
     "cup2d_amr_compute_dt", "cup2d_amr_advect_diffuse_rk2", "cup2d_amr_poisson_rhs", "cup2d_amr_poisson_solve",
     "cup2d_amr_pressure_correct", "cup2d_amr_step", "cup2d_amr_advect_diffuse_rhs_fast",
+    "cup2d_amr_pressure_rhs_fast", "cup2d_amr_pressure_gradient_fast",
 ]
 
 
@@ -115,6 +116,8 @@ def load_library():
                                            C.POINTER(C.c_int32), C.POINTER(D)]
     lib.cup2d_amr_plan_poisson.restype = L
     lib.cup2d_amr_advect_diffuse_rhs_fast.argtypes = [P, D]
+    lib.cup2d_amr_pressure_rhs_fast.argtypes = [P, D, I]
+    lib.cup2d_amr_pressure_gradient_fast.argtypes = [P, D]
     lib.cup2d_amr_compute_dt.argtypes = [P, D, C.POINTER(D), C.POINTER(D)]
     lib.cup2d_amr_advect_diffuse_rk2.argtypes = [P, D]
     lib.cup2d_amr_poisson_rhs.argtypes = [P, D]

@@ -236,6 +236,8 @@ int cup2d_amr_sync(cup2d_amr *a);
 int cup2d_amr_advect_diffuse_rhs(cup2d_amr *a, double dt);
 /* same result through the per-block lab loader on the WENO line core of the uniform-grid kernel (csrc/amr_fast.cu) */
 int cup2d_amr_advect_diffuse_rhs_fast(cup2d_amr *a, double dt);
+int cup2d_amr_pressure_rhs_fast(cup2d_amr *a, double dt, int with_laplacian);
+int cup2d_amr_pressure_gradient_fast(cup2d_amr *a, double dt);
 /* tmp = pressure_rhs(vel, u_def = tmpV, chi), flux-corrected (main.cpp:7007-7013); with_laplacian != 0: then
  * tmp -= lap(pold), flux-corrected (main.cpp:7022-7027) */
 int cup2d_amr_pressure_rhs(cup2d_amr *a, double dt, int with_laplacian);

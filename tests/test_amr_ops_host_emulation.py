@@ -131,3 +131,22 @@ def test_emulated_fast_advect_kernel(emu):
     assert rel(fast, d["adv"]) < 1e-12
     assert lib.cup2d_amr_advect_diffuse_rhs(h, float(d["dt"])) == 0
     assert rel(fast, down("tmpV", 2)) < 1e-12
+
+
+def test_emulated_fast_pressure_kernels(emu):
+    """the +-1 stencils of csrc/amr_fast.cu (per-block labs in shared memory, stored face fluxes)"""
+    d, lib, h, up, down = emu
+    lib.cup2d_amr_pressure_rhs_fast.argtypes = [C.c_void_p, C.c_double, C.c_int]
+    lib.cup2d_amr_pressure_gradient_fast.argtypes = [C.c_void_p, C.c_double]
+    dt = float(d["dt"])
+    up("vel", d["vel"])
+    up("tmpV", d["udef"])
+    up("chi", d["chi"])
+    up("pold", d["pres"])
+    assert lib.cup2d_amr_pressure_rhs_fast(h, dt, 0) == 0
+    assert rel(down("tmp", 1), d["rhs"]) < 1e-12
+    assert lib.cup2d_amr_pressure_rhs_fast(h, dt, 1) == 0
+    assert rel(down("tmp", 1), d["rhs1"]) < 1e-12
+    up("pres", d["pres"])
+    assert lib.cup2d_amr_pressure_gradient_fast(h, dt) == 0
+    assert rel(down("tmpV", 2), d["gradp"]) < 1e-12

@@ -40,6 +40,21 @@ def test_amr_fast_advect_kernel(case):
     assert rel(sim.download("tmpV"), d["adv"]) < 1e-12
 
 
+def test_amr_fast_pressure_kernels(case):
+    d, sim = case
+    sim.upload("vel", d["vel"])
+    sim.upload("tmpV", d["udef"])
+    sim.upload("chi", d["chi"])
+    sim.upload("pold", d["pres"])
+    sim.pressure_rhs_fast(float(d["dt"]), with_laplacian=False)
+    assert rel(sim.download("tmp"), d["rhs"]) < 1e-12
+    sim.pressure_rhs_fast(float(d["dt"]), with_laplacian=True)
+    assert rel(sim.download("tmp"), d["rhs1"]) < 1e-12
+    sim.upload("pres", d["pres"])
+    sim.pressure_gradient_fast(float(d["dt"]))
+    assert rel(sim.download("tmpV"), d["gradp"]) < 1e-12
+
+
 def test_amr_pressure_rhs_and_laplacian(case):
     d, sim = case
     sim.upload("vel", d["vel"])
