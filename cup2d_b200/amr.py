@@ -117,6 +117,9 @@ class AmrSimulation:
     def advect_diffuse_rhs(self, dt):
         _l.check(self.lib.cup2d_amr_advect_diffuse_rhs(self._h, float(dt)))
 
+    def set_fast(self, on=True):
+        _l.check(self.lib.cup2d_amr_set_fast(self._h, int(on)))
+
     def advect_diffuse_rhs_fast(self, dt):
         _l.check(self.lib.cup2d_amr_advect_diffuse_rhs_fast(self._h, float(dt)))
 

@@ -17,6 +17,10 @@ int64_t cup2d_amr_plan_poisson(cup2d_amr_plan *p, int32_t *nbr_out, int64_t *nnz
 int cup2d_amr_advect_diffuse_rhs(cup2d_amr *a, double dt);
 int cup2d_amr_pressure_rhs(cup2d_amr *a, double dt, int with_laplacian);
 int cup2d_amr_pressure_gradient(cup2d_amr *a, double dt);
+int cup2d_amr_advect_diffuse_rhs_fast(cup2d_amr *a, double dt);
+int cup2d_amr_pressure_rhs_fast(cup2d_amr *a, double dt, int with_laplacian);
+int cup2d_amr_pressure_gradient_fast(cup2d_amr *a, double dt);
+int cup2d_amr_laplacian_fast(cup2d_amr *a, double dt);
 }
 
 namespace cup2d {
@@ -57,6 +61,7 @@ struct cup2d_amr {
   double hmin = 0;
   cup2d_sim *poisson = nullptr;     // general-rows Poisson context over the same blocks (cup2d_amr_poisson_solve)
   // fast paths (csrc/amr_fast.cu)
+  bool fast = false;                // cup2d_amr_set_fast: the operator entry points dispatch to the fast kernels
   int *d_nbr4 = nullptr;            // [nb][4] W,E,S,N: same-level block, -1 wall, -2 coarser/finer
   int *d_irr_of = nullptr;          // [nb] position in the irregular list or -1
   int64_t nirr = 0;

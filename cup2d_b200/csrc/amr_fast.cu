@@ -383,10 +383,30 @@ int cup2d_amr_pressure_rhs_fast(cup2d_amr *a, double dt, int with_laplacian) {
                                                      a->d_irr_of, a->gt[1], a->d_h, a->d_faceflux, (int)a->nb, dt);
   CUP2D_CUDA(cudaGetLastError());
   if ((rc = fluxcorr_faces<1>(a, a->f[CUP2D_TMP])) || !with_laplacian) return rc;
-  amr_scalar_fast_kernel<0><<<grid, A1_NT, 0, a->stream>>>(a->f[CUP2D_POLD], a->f[CUP2D_TMP], nbr4, a->d_irr_of, a->gt[2], a->d_h,
-                                                           a->d_faceflux, (int)a->nb, dt);
+  return cup2d_amr_laplacian_fast(a, dt);
+}
+
+/* tmp -= lap(pold), flux-corrected (main.cpp:7022-7027) */
+int cup2d_amr_laplacian_fast(cup2d_amr *a, double dt) {
+  if (!a) {
+    set_error("null cup2d_amr handle");
+    return CUP2D_EINVAL;
+  }
+  CUP2D_CUDA(cudaSetDevice(a->device));
+  int rc = fast_setup(a);
+  if (rc) return rc;
+  const int grid = (int)((a->nb + A1_WARPS * 4 - 1) / (A1_WARPS * 4));
+  amr_scalar_fast_kernel<0><<<grid, A1_NT, 0, a->stream>>>(a->f[CUP2D_POLD], a->f[CUP2D_TMP], reinterpret_cast<const int4 *>(a->d_nbr4),
+                                                           a->d_irr_of, a->gt[2], a->d_h, a->d_faceflux, (int)a->nb, dt);
   CUP2D_CUDA(cudaGetLastError());
   return fluxcorr_faces<1>(a, a->f[CUP2D_TMP]);
+}
+
+/* route the operator entry points (and with them cup2d_amr_step) through the fast kernels of this file */
+int cup2d_amr_set_fast(cup2d_amr *a, int on) {
+  if (!a) return CUP2D_EINVAL;
+  a->fast = on != 0;
+  return CUP2D_OK;
 }
 
 int cup2d_amr_pressure_gradient_fast(cup2d_amr *a, double dt) {

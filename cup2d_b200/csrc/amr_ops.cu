@@ -395,6 +395,7 @@ int cup2d_amr_field_download(cup2d_amr *a, int field, double *host) {
 /* tmpV = KernelAdvectDiffuse(vel), flux-corrected (main.cpp:6611-6617) */
 int cup2d_amr_advect_diffuse_rhs(cup2d_amr *a, double dt) {
   CHECK_AMR(a);
+  if (a->fast) return cup2d_amr_advect_diffuse_rhs_fast(a, dt);
   CUP2D_CUDA(cudaSetDevice(a->device));
   int rc = gather(a, 0, a->f[CUP2D_VEL], a->lab[0]);
   if (rc) return rc;
@@ -407,6 +408,7 @@ int cup2d_amr_advect_diffuse_rhs(cup2d_amr *a, double dt) {
  * tmp -= lap(pold), flux-corrected (main.cpp:7022-7027) */
 int cup2d_amr_pressure_rhs(cup2d_amr *a, double dt, int with_laplacian) {
   CHECK_AMR(a);
+  if (a->fast) return cup2d_amr_pressure_rhs_fast(a, dt, with_laplacian);
   CUP2D_CUDA(cudaSetDevice(a->device));
   int rc = gather(a, 1, a->f[CUP2D_VEL], a->lab[1]);
   if (rc || (rc = gather(a, 1, a->f[CUP2D_TMPV], a->lab_udef))) return rc;
@@ -424,6 +426,7 @@ int cup2d_amr_pressure_rhs(cup2d_amr *a, double dt, int with_laplacian) {
 /* tmpV = pressureCorrectionKernel(pres) (main.cpp:7174-7179; not flux-corrected in the reference either) */
 int cup2d_amr_pressure_gradient(cup2d_amr *a, double dt) {
   CHECK_AMR(a);
+  if (a->fast) return cup2d_amr_pressure_gradient_fast(a, dt);
   CUP2D_CUDA(cudaSetDevice(a->device));
   int rc = gather(a, 2, a->f[CUP2D_PRES], a->lab[2]);
   if (rc) return rc;
@@ -481,6 +484,7 @@ int cup2d_amr_poisson_rhs(cup2d_amr *a, double dt) {
   const size_t bytes = (size_t)a->nb * 64 * sizeof(double);
   CUP2D_CUDA(cudaMemcpyAsync(a->f[CUP2D_POLD], a->f[CUP2D_PRES], bytes, cudaMemcpyDeviceToDevice, a->stream));
   CUP2D_CUDA(cudaMemsetAsync(a->f[CUP2D_PRES], 0, bytes, a->stream));
+  if (a->fast) return cup2d_amr_laplacian_fast(a, dt);
   if ((rc = gather(a, 2, a->f[CUP2D_POLD], a->lab[2]))) return rc;
   amr_lap_kernel<<<grid_for(a->nb * 64), 256, 0, a->stream>>>(a->lab[2], a->f[CUP2D_TMP], a->nb * 64);
   CUP2D_CUDA(cudaGetLastError());

@@ -25,7 +25,7 @@ SYMBOLS = [
     "cup2d_amr_advect_diffuse_rhs", "cup2d_amr_pressure_rhs", "cup2d_amr_pressure_gradient",
     "cup2d_amr_compute_dt", "cup2d_amr_advect_diffuse_rk2", "cup2d_amr_poisson_rhs", "cup2d_amr_poisson_solve",
     "cup2d_amr_pressure_correct", "cup2d_amr_step", "cup2d_amr_advect_diffuse_rhs_fast",
-    "cup2d_amr_pressure_rhs_fast", "cup2d_amr_pressure_gradient_fast",
+    "cup2d_amr_pressure_rhs_fast", "cup2d_amr_pressure_gradient_fast", "cup2d_amr_laplacian_fast", "cup2d_amr_set_fast",
 ]
 
 
@@ -118,6 +118,8 @@ def load_library():
     lib.cup2d_amr_advect_diffuse_rhs_fast.argtypes = [P, D]
     lib.cup2d_amr_pressure_rhs_fast.argtypes = [P, D, I]
     lib.cup2d_amr_pressure_gradient_fast.argtypes = [P, D]
+    lib.cup2d_amr_laplacian_fast.argtypes = [P, D]
+    lib.cup2d_amr_set_fast.argtypes = [P, I]
     lib.cup2d_amr_compute_dt.argtypes = [P, D, C.POINTER(D), C.POINTER(D)]
     lib.cup2d_amr_advect_diffuse_rk2.argtypes = [P, D]
     lib.cup2d_amr_poisson_rhs.argtypes = [P, D]

@@ -238,6 +238,9 @@ int cup2d_amr_advect_diffuse_rhs(cup2d_amr *a, double dt);
 int cup2d_amr_advect_diffuse_rhs_fast(cup2d_amr *a, double dt);
 int cup2d_amr_pressure_rhs_fast(cup2d_amr *a, double dt, int with_laplacian);
 int cup2d_amr_pressure_gradient_fast(cup2d_amr *a, double dt);
+int cup2d_amr_laplacian_fast(cup2d_amr *a, double dt);
+/* on != 0: the operator entry points above, and with them cup2d_amr_step, run on the fast kernels */
+int cup2d_amr_set_fast(cup2d_amr *a, int on);
 /* tmp = pressure_rhs(vel, u_def = tmpV, chi), flux-corrected (main.cpp:7007-7013); with_laplacian != 0: then
  * tmp -= lap(pold), flux-corrected (main.cpp:7022-7027) */
 int cup2d_amr_pressure_rhs(cup2d_amr *a, double dt, int with_laplacian);

@@ -77,7 +77,8 @@ def test_emulated_amr_pressure_gradient(emu):
     assert rel(down("tmpV", 2), d["gradp"]) < 1e-12
 
 
-def test_emulated_time_step_glue(emu, golden_dir):
+@pytest.mark.parametrize("fast", [0, 1])
+def test_emulated_time_step_glue(emu, golden_dir, fast):
     """dt control, RK2, the Poisson right-hand side and the correction (mean removal with h^2 weights, gradient, velocity
     update) of csrc/amr_ops.cu against the same pieces composed from the pinned oracle operators"""
     import cup2d_amr_oracle as amr
@@ -87,6 +88,8 @@ def test_emulated_time_step_glue(emu, golden_dir):
     lib.cup2d_amr_advect_diffuse_rk2.argtypes = [C.c_void_p, D]
     lib.cup2d_amr_poisson_rhs.argtypes = [C.c_void_p, D]
     lib.cup2d_amr_pressure_correct.argtypes = [C.c_void_p, D]
+    lib.cup2d_amr_set_fast.argtypes = [C.c_void_p, C.c_int]
+    assert lib.cup2d_amr_set_fast(h, fast) == 0
     mesh = amr.Mesh(d["blocks"], int(d["bpdx"]), int(d["bpdy"]))
     h0, nu = float(d["h0"]), float(d["nu"])
     up("vel", d["vel"])
@@ -117,6 +120,7 @@ def test_emulated_time_step_glue(emu, golden_dir):
     assert lib.cup2d_amr_pressure_correct(h, dt) == 0
     vel, pres = amr.amr_pressure_correct(mesh, h0, d["vel"], x, d["pres"], dt)
     assert rel(down("pres", 1), pres) < 1e-12 and rel(down("vel", 2), vel) < 1e-12
+    assert lib.cup2d_amr_set_fast(h, 0) == 0
 
 
 def test_emulated_fast_advect_kernel(emu):

@@ -113,7 +113,8 @@ def test_native_amr_poisson_matrix_on_the_device_solver(golden_dir):
     assert abs(err.value - errr) < 1e-9 * errr
 
 
-def test_amr_full_step_against_composed_oracle(case):
+@pytest.mark.parametrize("fast", [False, True])
+def test_amr_full_step_against_composed_oracle(case, fast):
     """one whole time step without bodies on the 7-level mesh (dt, RK2, rhs, 15 BiCGSTAB iterations on the native Poisson
     rows, correction) against the same step composed from the pinned oracle pieces"""
     import scipy.sparse as sp
@@ -125,7 +126,9 @@ def test_amr_full_step_against_composed_oracle(case):
     sim.upload("vel", d["vel"])
     sim.upload("pres", d["pres"])
     sim.upload("chi", np.zeros_like(d["chi"]))
+    sim.set_fast(fast)
     dt, it, err = sim.step(cfl=0.5, max_iter=15)
+    sim.set_fast(False)
     want_dt = amr.amr_compute_dt(mesh, h0, d["vel"], nu, 0.5)
     assert abs(dt - want_dt) < 1e-15 * want_dt and it == 15
     v = amr.amr_rk2(mesh, h0, d["vel"], nu, want_dt)
