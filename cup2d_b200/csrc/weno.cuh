@@ -52,17 +52,34 @@ __device__ __forceinline__ void line_betas(const LineState &s, double &s1, doubl
   s2 = q2 * q2;
   s3 = q3 * q3;
 }
+// Two arithmetic variants prepared for measurement, OFF by default (the validated kernels are built without them):
+//   CUP2D_WENO_CUBIC_RCP   one cubic step r0 (1 + e + e^2) instead of two Newton steps: 3 FP64 operations instead of 4 per
+//                          reciprocal, error (seed error)^3 ~ 2^-63
+//   CUP2D_WENO_LAZY_BETAS  no smoothness indicators at a window position where neither flux family is needed (the first
+//                          position when the flow there is not positive, the last when it is)
+#ifndef CUP2D_WENO_CUBIC_RCP
+#define CUP2D_WENO_CUBIC_RCP 0
+#endif
+#ifndef CUP2D_WENO_LAZY_BETAS
+#define CUP2D_WENO_LAZY_BETAS 0
+#endif
+
 // 1/x for x > 0, normal: MUFU.RCP64H seed (~2^-20) + two Newton steps = full double accuracy.  (One step
 // leaves 1.3e-13 relative error for 3 % of the kernel time, profiles/r01h; not worth it.)
 __device__ __forceinline__ double rcp_pos(double x) {
   double r;
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+#if CUP2D_WENO_CUBIC_RCP
+  const double e = fma(-x, r, 1.0);
+  return fma(r, fma(e, e, e), r);
+#else
 #pragma unroll
   for (int i = 0; i < 2; i++) {
     const double e = fma(-x, r, 1.0);
     r = fma(r, e, r);
   }
   return r;
+#endif
 }
 // upwind-from-the-left flux ratio at face w+1/2 (weno5_plus, main.cpp:162-181; gammas .1,.6,.3)
 __device__ __forceinline__ double ratio_plus(const LineState &s, double s1, double s2, double s3) {
@@ -120,9 +137,11 @@ __device__ __forceinline__ void weno_line(const double *__restrict__ qa, const d
     // flux families needed at this window position (masks are compile-time after unrolling)
     const bool needP = (pw & ((vc ? 2u : 0u) | (vn ? 4u : 0u))) != 0u;
     const bool needM = (~pw & ((vc ? 2u : 0u) | (vp ? 1u : 0u))) != 0u;
-    double a1, a2, a3, b1, b2, b3;
-    line_betas(A, a1, a2, a3);
-    line_betas(B, b1, b2, b3);
+    double a1 = 0, a2 = 0, a3 = 0, b1 = 0, b2 = 0, b3 = 0;
+    if (!CUP2D_WENO_LAZY_BETAS || needP || needM) {
+      line_betas(A, a1, a2, a3);
+      line_betas(B, b1, b2, b3);
+    }
     double rPa = 0, rPb = 0, rMa = 0, rMb = 0;
     if (needP) {
       rPa = ratio_plus(A, a1, a2, a3);

@@ -37,7 +37,8 @@ def rewrite(src):
     return src, n
 
 
-def build():
+def build(defines=(), tag=""):
+    """defines: extra -D flags (e.g. the arithmetic variants of weno.cuh); tag names the resulting library"""
     os.makedirs(OUT, exist_ok=True)
     open(os.path.join(OUT, "sim.h"), "w").write('#pragma once\n#include "cuda_host_shim.h"\n')
     open(os.path.join(OUT, "common.cuh"), "w").write('#pragma once\n#include "cuda_host_shim.h"\n')
@@ -55,8 +56,8 @@ def build():
         open(dst, "w").write(src + (GLUE if name == "amr_ops.cu" else ""))
         srcs.append(dst)
     assert total >= 16, f"only {total} launches rewritten"
-    lib = os.path.join(OUT, "libamr_emu.so")
-    subprocess.run(["/usr/bin/g++", "-O2", "-std=c++20", "-fPIC", "-shared", "-pthread", "-DCUP2D_AMR_EMU", "-I", OUT, "-I", HERE,
+    lib = os.path.join(OUT, f"libamr_emu{tag}.so")
+    subprocess.run(["/usr/bin/g++", "-O2", "-std=c++20", "-fPIC", "-shared", "-pthread", "-DCUP2D_AMR_EMU", *[f"-D{d}" for d in defines], "-I", OUT, "-I", HERE,
                     "-o", lib, *srcs, os.path.join(CSRC, "amr_plan.cpp")], check=True)
     return lib
 
