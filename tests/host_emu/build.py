@@ -62,5 +62,69 @@ def build(defines=(), tag=""):
     return lib
 
 
+# ---- the WHOLE product library under emulation -------------------------------------------------------------------------
+FULL = os.path.join(HERE, "_build_full")
+ASM_REWRITES = [  # (regex over the source text, replacement): the PTX of common.cuh / halo.cu / weno.cuh in host terms
+    (r'asm volatile\("mbarrier\.init.*?\);', "(void)bar; (void)count;"),
+    (r'asm volatile\("fence\.mbarrier_init.*?\);', ";"),
+    (r'asm volatile\("mbarrier\.arrive\.expect_tx.*?: "memory"\);', "(void)bar; (void)bytes;"),
+    (r'asm volatile\("\{\\n".*?: "memory"\);', "(void)bar; (void)parity; /* copies are synchronous here */"),
+    (r'asm volatile\("cp\.async\.bulk\.shared.*?: "memory"\);', "memcpy(smem_dst, gmem_src, bytes); (void)bar;"),
+    (r'asm\("rcp\.approx\.ftz\.f64 %0, %1;" : "=d"\(r\) : "d"\(x\)\);', "r = (double)(1.0f / (float)x);"),
+    (r'asm volatile\("st\.release\.sys.*?: "memory"\);', "__threadfence(); *(volatile unsigned long long *)p = v;"),
+    (r'asm volatile\("st\.relaxed\.sys.*?: "memory"\);', "*(volatile unsigned long long *)p = v;"),
+    (r'asm volatile\("ld\.acquire\.sys.*?: "memory"\);', "v = *(volatile const unsigned long long *)p; __threadfence();"),
+    (r'asm volatile\("ld\.relaxed\.sys\.global\.u64.*?: "memory"\);', "v = *(volatile const unsigned long long *)p;"),
+    (r'asm volatile\("ld\.relaxed\.sys\.global\.v2\.f64.*?: "memory"\);', "v = from[i];"),
+]
+LAUNCH_ANY = re.compile(r"(\b\w+)((?:<[^<>;]*>)?)<<<(.*?)>>>\((.*?)\);", re.S)
+
+
+def split_top(s):
+    """split a launch configuration at top-level commas"""
+    out, depth, cur = [], 0, ""
+    for ch in s:
+        if ch in "([":
+            depth += 1
+        elif ch in ")]":
+            depth -= 1
+        if ch == "," and depth == 0:
+            out.append(cur.strip())
+            cur = ""
+        else:
+            cur += ch
+    out.append(cur.strip())
+    return out
+
+
+def build_full():
+    """libcup2d_emu.so: every .cu / .cpp of cup2d_b200/csrc compiled with g++, one OS thread per CUDA thread"""
+    os.makedirs(FULL, exist_ok=True)
+    srcs = []
+    for name in sorted(os.listdir(CSRC)):
+        if not name.endswith((".cu", ".cuh", ".h", ".cpp")):
+            continue
+        text = open(os.path.join(CSRC, name)).read()
+        for pat, rep in ASM_REWRITES:
+            text = re.sub(pat, rep, text, flags=re.S)
+        assert "asm" not in re.sub(r"//.*", "", text).replace("__asm", ""), f"PTX left in {name}"
+
+        def sub(m):
+            cfg = split_top(m.group(3))
+            return f"emu_launch_coop({cfg[0]}, {cfg[1]}, [&] {{ {m.group(1)}{m.group(2)}({m.group(4)}); }});"
+        text = LAUNCH_ANY.sub(sub, text)
+        assert "<<<" not in text, f"launch left in {name}"
+        text = text.replace("extern __shared__ __align__(128) unsigned char smem[];", "static __attribute__((aligned(128))) unsigned char smem[ADV_SMEM];")
+        text = text.replace("extern __shared__ __align__(16) double af_smem[];", "static double af_smem[AF_SMEM / 8];")
+        out = name.replace(".cu", "_emu.cpp") if name.endswith(".cu") else name
+        open(os.path.join(FULL, out), "w").write(text)
+        if out.endswith(".cpp"):
+            srcs.append(os.path.join(FULL, out))
+    lib = os.path.join(FULL, "libcup2d_emu.so")
+    subprocess.run(["/usr/bin/g++", "-O2", "-std=c++20", "-fPIC", "-shared", "-pthread", "-w", "-I", FULL, "-I", HERE,
+                    "-o", lib, *srcs], check=True)
+    return lib
+
+
 if __name__ == "__main__":
     print(build())

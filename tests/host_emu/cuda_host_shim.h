@@ -101,7 +101,7 @@ inline void emu_launch_coop(int grid, int block, const std::function<void()> &bo
   }
 }
 #define __shared__ static
-#define __align__(n) alignas(n)
+#define __align__(n) __attribute__((aligned(n)))
 struct double2 { double x, y; };
 struct int2 { int x, y; };
 struct int4 { int x, y, z, w; };
@@ -115,11 +115,14 @@ using std::fmax;
 enum { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
 template <class F> cudaError_t cudaFuncSetAttribute(F, int, int) { return 0; }
 template <class T, class U> cudaError_t cudaMemcpyToSymbol(T &sym, const U &src, size_t n) { memcpy(&sym, &src, n); return 0; }
+#ifndef CUP2D_FULL_EMU
 namespace cup2d {
 inline bool is_pos(double x) { return !(x <= 0); } // U > 0, NaN counted as positive (common.cuh)
 }
+#endif
 struct cup2d_sim;
 
+#ifndef CUP2D_FULL_EMU
 // what csrc/amr_ops.cu takes from sim.h
 namespace cup2d {
 void set_error(const std::string &msg);
@@ -132,3 +135,4 @@ int dim_of(int field);
       return CUP2D_ECUDA;                                                                         \
     }                                                                                             \
   } while (0)
+#endif

@@ -1,0 +1,8 @@
+#!/bin/bash
+# All GPU parity tests (including the opt-in multi-level ones) on the CPU, against the g++ build of the product sources
+# (tests/host_emu/; see tests/test_full_emulation.py for what this does and does not check).  About 5 minutes.
+set -e
+cd "$(dirname "$0")/.."
+LIB=$(python -c "import sys; sys.path.insert(0, 'tests/host_emu'); import build; print(build.build_full())")
+CUP2D_TEST_UNVALIDATED=1 CUP2D_B200_LIB=$LIB python -m pytest tests/test_gpu_parity.py tests/test_gpu_amr.py -m gpu -q \
+  -k "not 1024 and not large_grid and not reference_driver and not reference_amr and not two_ranks and not multi_chunk" "$@"
