@@ -114,8 +114,15 @@ def build_full():
             return f"emu_launch_coop({cfg[0]}, {cfg[1]}, [&] {{ {m.group(1)}{m.group(2)}({m.group(4)}); }});"
         text = LAUNCH_ANY.sub(sub, text)
         assert "<<<" not in text, f"launch left in {name}"
-        text = text.replace("extern __shared__ __align__(128) unsigned char smem[];", "static __attribute__((aligned(128))) unsigned char smem[ADV_SMEM];")
-        text = text.replace("extern __shared__ __align__(16) double af_smem[];", "static double af_smem[AF_SMEM / 8];")
+        # shared memory becomes block-local storage of the emulated block (ranks emulated in one process run kernels concurrently)
+        text = text.replace("extern __shared__ __align__(128) unsigned char smem[];",
+                            "unsigned char *smem = (unsigned char *)emu_shared(__COUNTER__, ADV_SMEM);")
+        text = text.replace("extern __shared__ __align__(16) double af_smem[];", "double *af_smem = (double *)emu_shared(__COUNTER__, AF_SMEM);")
+        text = re.sub(r"__shared__\s+(?:__align__\(\d+\)\s+)?(\w+)\s+(\w+)\[([^\]]+)\];",
+                      lambda m: f"{m.group(1)} *{m.group(2)} = ({m.group(1)} *)emu_shared(__COUNTER__, sizeof({m.group(1)}) * ({m.group(3)}));", text)
+        text = re.sub(r"__shared__\s+(\w+)\s+(\w+);",
+                      lambda m: f"{m.group(1)} &{m.group(2)} = *({m.group(1)} *)emu_shared(__COUNTER__, sizeof({m.group(1)}));", text)
+        assert "__shared__" not in re.sub(r"//.*", "", text), f"__shared__ left in {name}"
         out = name.replace(".cu", "_emu.cpp") if name.endswith(".cu") else name
         open(os.path.join(FULL, out), "w").write(text)
         if out.endswith(".cpp"):

@@ -58,7 +58,12 @@ inline void emu_launch(int grid, int block, const std::function<void()> &body) {
 #include <memory>
 #include <thread>
 #include <vector>
+#include <map>
+#include <mutex>
 struct EmuBlock {
+  std::mutex shm_lock;
+  std::map<int, void *> shm; // block-local "shared memory": one buffer per __shared__ declaration site (build.py rewrites them)
+  ~EmuBlock() { for (auto &e : shm) free(e.second); }
   std::barrier<> block_bar;
   std::vector<std::unique_ptr<std::barrier<>>> warp_bar;
   std::vector<unsigned long long> slot; // shuffle exchange, 32 per warp
@@ -85,6 +90,14 @@ template <class T> T emu_shfl(T v, int src_lane) {
 template <class T> T __shfl_xor_sync(unsigned, T v, int mask) { return emu_shfl(v, (threadIdx.x & 31) ^ mask); }
 template <class T> T __shfl_sync(unsigned, T v, int lane) { return emu_shfl(v, lane); }
 template <class T> T __shfl_down_sync(unsigned, T v, int d) { return emu_shfl(v, std::min(31, (int)(threadIdx.x & 31) + d)); }
+// storage of the __shared__ variable declared at site `id`, common to the threads of the current block only (several
+// emulated ranks may run kernels at the same time in one process)
+inline void *emu_shared(int id, size_t bytes) {
+  std::lock_guard<std::mutex> g(emu_block->shm_lock);
+  void *&p = emu_block->shm[id];
+  if (!p) p = aligned_alloc(128, (bytes + 127) / 128 * 128);
+  return p;
+}
 inline void emu_launch_coop(int grid, int block, const std::function<void()> &body) {
   for (int b = 0; b < grid; b++) {
     EmuBlock blk(block);

@@ -39,3 +39,60 @@ def test_gpu_parity_subset_on_the_emulated_library(emulated_library):
     assert " passed" in tail and "failed" not in tail
     n = int(tail.split(" passed")[0].split()[-1])
     assert n >= 12, tail
+
+
+def test_two_ranks_emulated_in_one_process(emulated_library):
+    """the multi-GPU path (peer-memory halo pulls with ready flags, in-kernel all-reduce of the Krylov dots, SFC-range
+    partition) with the two ranks running as threads of one process: their 'device' buffers are mapped into each other through
+    the emulated IPC handles and their kernels really run concurrently.  2 steps x 10 Poisson iterations vs the oracle."""
+    code = r'''
+import sys, threading, numpy as np
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+import cup2d_b200, cup2d_oracle as orc
+W, L = 2, 3
+N = 8 << L
+x = (np.arange(N) + 0.5) / N
+X, Y = np.meshgrid(x, x)
+rng = np.random.default_rng(5)
+u = np.sin(2 * np.pi * X) * np.cos(2 * np.pi * Y) + 0.05 * rng.uniform(-1, 1, (N, N))
+v = -np.cos(2 * np.pi * X) * np.sin(2 * np.pi * Y) + 0.05 * rng.uniform(-1, 1, (N, N))
+p = np.cos(2 * np.pi * X) * np.cos(2 * np.pi * Y)
+bar, slots, res, errs = threading.Barrier(W), [None] * W, [None] * W, []
+class Dist:                       # in-process stand-in for torch.distributed (only carries the opaque blobs)
+    def __init__(self, rank): self.rank = rank
+    def all_gather_object(self, out, obj):
+        slots[self.rank] = obj; bar.wait()
+        out[:] = slots; bar.wait()
+    def barrier(self): bar.wait()
+def run(rank):
+    try:
+        sim = cup2d_b200.Simulation(L, nu=1e-3, cfl=0.5, rank=rank, nranks=W)
+        sim.attach_peers(Dist(rank))
+        sim.upload("vel", u, v); sim.upload("pres", p)
+        outs = []
+        for s in range(2):
+            dt, it, err = sim.step(max_iter=10)
+            outs.append((dt, sim.download_blocks("vel"), sim.download_blocks("pres")))
+            bar.wait()
+        res[rank] = (sim.order, sim.nbx, sim.nby, outs)
+        bar.wait(); sim.close()
+    except Exception as e:
+        errs.append(repr(e)); bar.abort()
+ths = [threading.Thread(target=run, args=(r,)) for r in range(W)]
+[t.start() for t in ths]; [t.join() for t in ths]
+assert not errs, errs
+order, nbx, nby, _ = res[0]
+ru, rv, rp, worst = u, v, p, 0.0
+for s in range(2):
+    ref = orc.step(ru, rv, rp, 1e-3, 0.5, kiter=10)
+    vel = np.concatenate([res[r][3][s][1] for r in range(W)]); pr = np.concatenate([res[r][3][s][2] for r in range(W)])
+    gu, gv = cup2d_b200.from_blocks(vel, order, nbx, nby, 2); gp = cup2d_b200.from_blocks(pr, order, nbx, nby, 1)
+    worst = max(worst, abs(res[0][3][s][0] - ref["dt"]) / ref["dt"], np.abs(gu - ref["u"]).max(), np.abs(gv - ref["v"]).max(),
+                np.abs(gp - ref["p"]).max())
+    ru, rv, rp = ref["u"], ref["v"], ref["p"]
+print("WORST", worst)
+assert worst < 1e-12
+''' % (ROOT, os.path.join(ROOT, "oracle"))
+    r = subprocess.run([sys.executable, "-c", code], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900,
+                       env=dict(os.environ, CUP2D_B200_LIB=emulated_library))
+    assert r.returncode == 0 and "WORST" in r.stdout, r.stdout[-1500:]
