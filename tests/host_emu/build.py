@@ -23,6 +23,20 @@ int dim_of(int f) { return (f == CUP2D_VEL || f == CUP2D_VOLD || f == CUP2D_TMPV
 extern "C" const char *cup2d_last_error(void) { return cup2d::g_err.c_str(); }
 '''
 
+def _fresh(out, inputs):
+    """True if `out` exists and is newer than every input file (the builds below are skipped then)"""
+    if not os.path.exists(out):
+        return False
+    t = os.path.getmtime(out)
+    return all(os.path.getmtime(i) <= t for i in inputs)
+
+
+def _inputs():
+    files = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".h", ".cpp"))]
+    files += [os.path.join(HERE, f) for f in os.listdir(HERE) if f.endswith((".h", ".py", ".cpp"))]
+    return files + [os.path.join(ROOT, "include", "cup2d_b200.h")]
+
+
 LAUNCH = re.compile(r"(\w+)((?:<[^<>;]*>)?)<<<(.*?),\s*(\w+),\s*(\w+),\s*a->stream>>>\((.*?)\);", re.S)
 
 
@@ -40,6 +54,8 @@ def rewrite(src):
 def build(defines=(), tag=""):
     """defines: extra -D flags (e.g. the arithmetic variants of weno.cuh); tag names the resulting library"""
     os.makedirs(OUT, exist_ok=True)
+    if _fresh(os.path.join(OUT, f"libamr_emu{tag}.so"), _inputs()):
+        return os.path.join(OUT, f"libamr_emu{tag}.so")
     open(os.path.join(OUT, "sim.h"), "w").write('#pragma once\n#include "cuda_host_shim.h"\n')
     open(os.path.join(OUT, "common.cuh"), "w").write('#pragma once\n#include "cuda_host_shim.h"\n')
     shutil.copy(os.path.join(CSRC, "amr.h"), OUT)
@@ -100,6 +116,8 @@ def split_top(s):
 def build_full():
     """libcup2d_emu.so: every .cu / .cpp of cup2d_b200/csrc compiled with g++, one OS thread per CUDA thread"""
     os.makedirs(FULL, exist_ok=True)
+    if _fresh(os.path.join(FULL, "libcup2d_emu.so"), _inputs()):
+        return os.path.join(FULL, "libcup2d_emu.so")
     srcs = []
     for name in sorted(os.listdir(CSRC)):
         if not name.endswith((".cu", ".cuh", ".h", ".cpp")):
@@ -131,6 +149,18 @@ def build_full():
     subprocess.run(["/usr/bin/g++", "-O2", "-std=c++20", "-fPIC", "-shared", "-pthread", "-w", "-I", FULL, "-I", HERE,
                     "-o", lib, *srcs], check=True)
     return lib
+
+
+def build_tsan():
+    """the emulated product sources + tsan_driver.cpp with -fsanitize=thread -> an executable that hunts for data races"""
+    build_full()
+    srcs = [os.path.join(FULL, f) for f in sorted(os.listdir(FULL)) if f.endswith(".cpp")]
+    exe = os.path.join(FULL, "tsan_driver")
+    if _fresh(exe, _inputs()):
+        return exe
+    subprocess.run(["/usr/bin/g++", "-O1", "-g", "-std=c++20", "-pthread", "-fsanitize=thread", "-w", "-I", FULL, "-I", HERE, "-o", exe,
+                    os.path.join(HERE, "tsan_driver.cpp"), *srcs], check=True)
+    return exe
 
 
 if __name__ == "__main__":

@@ -96,3 +96,22 @@ assert worst < 1e-12
     r = subprocess.run([sys.executable, "-c", code], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900,
                        env=dict(os.environ, CUP2D_B200_LIB=emulated_library))
     assert r.returncode == 0 and "WORST" in r.stdout, r.stdout[-1500:]
+
+
+def test_no_data_races_under_thread_sanitizer():
+    """race hunt: the emulated product sources rebuilt with -fsanitize=thread run a uniform-grid time step (advect with its
+    staged loads, pressure kernels, the Krylov kernels with their grid reductions, the chi-mask tags) and the multi-level step
+    on baseline and fast kernels.  Every CUDA thread being an OS thread, an access pair not ordered by a barrier, shuffle or
+    atomic is a ThreadSanitizer report (checked by hand: removing the __syncwarp between the two passes of the multi-level
+    advect kernel produces reports at its partial-result planes).  None is expected."""
+    sys.path.insert(0, os.path.join(HERE, "host_emu"))
+    import build
+    try:
+        exe = build.build_tsan()
+    except subprocess.CalledProcessError:
+        pytest.skip("ThreadSanitizer runtime not available to g++ on this box")
+    r = subprocess.run([exe], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=1800,
+                       env=dict(os.environ, TSAN_OPTIONS="halt_on_error=0 report_signal_unsafe=0"))
+    assert r.returncode == 0, r.stdout[-3000:]
+    assert "ThreadSanitizer" not in r.stdout, r.stdout[-3000:]
+    assert r.stdout.count("multi-level step") == 2 and "uniform step" in r.stdout
