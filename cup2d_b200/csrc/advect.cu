@@ -28,6 +28,10 @@
 
 namespace cup2d {
 
+#ifndef CUP2D_ADV_WARP_ROWS
+#define CUP2D_ADV_WARP_ROWS 0
+#endif
+
 constexpr int TC = 32;          // tile cells per side
 constexpr int GH = 3;           // ghost width (stencil -3..+3, main.cpp:5442)
 constexpr int TW = TC + 2 * GH; // 38
@@ -150,8 +154,18 @@ advect_stage_kernel(const double *__restrict__ in, const double *__restrict__ ol
   double2 *outp = reinterpret_cast<double2 *>(out) + (size_t)(store ? yslot : 0) * 64 + (yx & 7);
   // x pass: lanes = rows, thread = 8 consecutive cells of one row (advecting component u)
   // y pass: lanes = columns, thread = 8 consecutive cells of one column = one block (advecting v)
+  // x-pass ownership.  Default: lane = row, warp = 8-cell segment (every warp touches all 32 rows, so the y pass, whose warp
+  // ys needs rows 8ys..8ys+7 complete, waits at a CTA barrier).  CUP2D_ADV_WARP_ROWS (prepared for measurement, off in the
+  // validated build): warp = the 8 rows of ITS OWN block row, lane = (segment, row): the y pass of a warp then only reads what
+  // the same warp wrote and the CTA barrier between the passes becomes a __syncwarp (stall_barrier was 20 % in
+  // profiles/r01i_advect_ncu.md).  Bank-conflict-free either way (row stride 39 / 33 doubles).
+#if CUP2D_ADV_WARP_ROWS
+  const int xrow = 8 * warp + (lane & 7), xseg = lane >> 3;
+#else
+  const int xrow = lane, xseg = warp;
+#endif
   auto emit_x = [&](int c, double U, double, double du, double dv, double D2u, double D2v) {
-    double *ru = Ru + lane * RP + 8 * warp, *rv = Rv + lane * RP + 8 * warp;
+    double *ru = Ru + xrow * RP + 8 * xseg, *rv = Rv + xrow * RP + 8 * xseg;
     const double aU = afac * U;
     ru[c] = fma(aU, du, dfac * D2u); // afac*u*dudx + dfac*(u_E + u_W - 2u)
     rv[c] = fma(aU, dv, dfac * D2v);
@@ -178,14 +192,18 @@ advect_stage_kernel(const double *__restrict__ in, const double *__restrict__ ol
   };
 #pragma unroll 1
   for (int pass = 0; pass < 2; pass++) {
-    const double *qa = pass == 0 ? su + (lane + GH) * SP + 8 * warp : sv + (8 * ys) * SP + (yx + GH);
-    const double *qb = pass == 0 ? sv + (lane + GH) * SP + 8 * warp : su + (8 * ys) * SP + (yx + GH);
+    const double *qa = pass == 0 ? su + (xrow + GH) * SP + 8 * xseg : sv + (8 * ys) * SP + (yx + GH);
+    const double *qb = pass == 0 ? sv + (xrow + GH) * SP + 8 * xseg : su + (8 * ys) * SP + (yx + GH);
     const int es = pass == 0 ? 1 : SP;
     weno_line(qa, qb, es, [&](int c, double Ua, double Ub, double da, double db, double D2a, double D2b) {
       if (pass == 0) emit_x(c, Ua, Ub, da, db, D2a, D2b);
       else emit_y(c, Ua, Ub, da, db, D2a, D2b);
     });
+#if CUP2D_ADV_WARP_ROWS
+    __syncwarp();
+#else
     __syncthreads();
+#endif
   }
 }
 

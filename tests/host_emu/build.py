@@ -113,11 +113,12 @@ def split_top(s):
     return out
 
 
-def build_full():
-    """libcup2d_emu.so: every .cu / .cpp of cup2d_b200/csrc compiled with g++, one OS thread per CUDA thread"""
+def build_full(defines=(), tag=""):
+    """libcup2d_emu<tag>.so: every .cu / .cpp of cup2d_b200/csrc compiled with g++, one OS thread per CUDA thread;
+    defines: extra -D flags (the measurement variants of advect.cu / weno.cuh)"""
     os.makedirs(FULL, exist_ok=True)
-    if _fresh(os.path.join(FULL, "libcup2d_emu.so"), _inputs()):
-        return os.path.join(FULL, "libcup2d_emu.so")
+    if _fresh(os.path.join(FULL, f"libcup2d_emu{tag}.so"), _inputs()):
+        return os.path.join(FULL, f"libcup2d_emu{tag}.so")
     srcs = []
     for name in sorted(os.listdir(CSRC)):
         if not name.endswith((".cu", ".cuh", ".h", ".cpp")):
@@ -145,20 +146,21 @@ def build_full():
         open(os.path.join(FULL, out), "w").write(text)
         if out.endswith(".cpp"):
             srcs.append(os.path.join(FULL, out))
-    lib = os.path.join(FULL, "libcup2d_emu.so")
-    subprocess.run(["/usr/bin/g++", "-O2", "-std=c++20", "-fPIC", "-shared", "-pthread", "-w", "-I", FULL, "-I", HERE,
+    lib = os.path.join(FULL, f"libcup2d_emu{tag}.so")
+    subprocess.run(["/usr/bin/g++", "-O2", "-std=c++20", "-fPIC", "-shared", "-pthread", "-w", *[f"-D{d}" for d in defines], "-I", FULL, "-I", HERE,
                     "-o", lib, *srcs], check=True)
     return lib
 
 
-def build_tsan():
+def build_tsan(defines=(), tag=""):
     """the emulated product sources + tsan_driver.cpp with -fsanitize=thread -> an executable that hunts for data races"""
     build_full()
     srcs = [os.path.join(FULL, f) for f in sorted(os.listdir(FULL)) if f.endswith(".cpp")]
-    exe = os.path.join(FULL, "tsan_driver")
+    exe = os.path.join(FULL, f"tsan_driver{tag}")
     if _fresh(exe, _inputs()):
         return exe
-    subprocess.run(["/usr/bin/g++", "-O1", "-g", "-std=c++20", "-pthread", "-fsanitize=thread", "-w", "-I", FULL, "-I", HERE, "-o", exe,
+    subprocess.run(["/usr/bin/g++", "-O1", "-g", "-std=c++20", "-pthread", "-fsanitize=thread", "-w", *[f"-D{d}" for d in defines],
+                    "-I", FULL, "-I", HERE, "-o", exe,
                     os.path.join(HERE, "tsan_driver.cpp"), *srcs], check=True)
     return exe
 

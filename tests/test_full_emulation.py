@@ -115,3 +115,18 @@ def test_no_data_races_under_thread_sanitizer():
     assert r.returncode == 0, r.stdout[-3000:]
     assert "ThreadSanitizer" not in r.stdout, r.stdout[-3000:]
     assert r.stdout.count("multi-level step") == 2 and "uniform step" in r.stdout
+
+
+def test_measurement_variants_keep_parity():
+    """the default-off variants prepared for round-2 measurements (advect.cu: CUP2D_ADV_WARP_ROWS — warp-local rows, the CTA
+    barrier between the passes becomes a __syncwarp; weno.cuh: cubic reciprocal step, lazy smoothness indicators) built
+    together into an emulated library: the operator / time-step parity tests still pass.  (Their race check:
+    build.build_tsan(defines, tag) + the resulting executable; clean when this was written.)"""
+    sys.path.insert(0, os.path.join(HERE, "host_emu"))
+    import build
+    lib = build.build_full(("CUP2D_ADV_WARP_ROWS=1", "CUP2D_WENO_CUBIC_RCP=1", "CUP2D_WENO_LAZY_BETAS=1"), "_variants")
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(HERE, "test_gpu_parity.py"), "-m", "gpu", "-q", "-x", "-k",
+                        "operators_vs_reference_golden or steps_L2_random_k8 or rectangular_domain", "-p", "no:cacheprovider"],
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=dict(os.environ, CUP2D_B200_LIB=lib),
+                       timeout=900, cwd=ROOT)
+    assert r.returncode == 0 and " passed" in r.stdout, r.stdout[-1500:]
