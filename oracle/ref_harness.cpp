@@ -54,7 +54,11 @@
 //        prints one JSON line with per-operator CPU times (seconds, median of reps)
 #define CUP2D_REF_HOOK_TU 1
 #define main ref_main
+#ifdef CUP2D_PATCHED_MAIN
+#include "main_patched.cpp" // oracle/_ref/: main.cpp with its hot path spliced onto cup2d_b200 (oracle/Makefile, ref_patched)
+#else
 #include "main.cpp" // resolved with -I/root/reference
+#endif
 #undef main
 #include <chrono>
 
@@ -118,8 +122,12 @@ void write_field(Grid *g, int dim) {
 }
 void write_vec(const std::vector<double> &x) {
   // solver vectors are block-major in `infos` order (main.cpp:5753-5771): back to global order
-  std::vector<double> a((size_t)g_N * g_NY);
+  std::vector<double> a((size_t)g_N * g_NY, 0.0);
   auto &infos = var.tmp->infos;
+  if (x.size() < infos.size() * _BS_ * _BS_) { // the patched loop never fills the host solver's vectors: zeros
+    fwrite(a.data(), sizeof(double), a.size(), g_fout);
+    return;
+  }
   for (size_t i = 0; i < infos.size(); i++) {
     const int bi = infos[i].index[0], bj = infos[i].index[1];
     for (int iy = 0; iy < _BS_; iy++)

@@ -130,3 +130,30 @@ def test_measurement_variants_keep_parity():
                        stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=dict(os.environ, CUP2D_B200_LIB=lib),
                        timeout=900, cwd=ROOT)
     assert r.returncode == 0 and " passed" in r.stdout, r.stdout[-1500:]
+
+
+@pytest.mark.parametrize("name", ["steps_L2_random_k8", "steps_L3_tg_k15"])
+def test_reference_time_loop_on_the_emulated_library(emulated_library, golden_dir, name, tmp_path):
+    """the drop-in boundary for the operators, end to end: the reference's OWN time loop (unmodified main.cpp with lines
+    6607-6642 and 7007-7187 replaced at build time by dropin/patched_loop_*.inc + dropin/b200_loop_glue.h), linked against the
+    emulated library, against the steps the unmodified reference produced (tests/golden/steps_*.npz)"""
+    import numpy as np
+    if not os.path.exists("/root/reference/main.cpp"):
+        pytest.skip("needs the reference sources to build the patched driver (build container only)")
+    emu_dir = os.path.dirname(emulated_library)
+    subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), "ref_patched", f"LIBDIR={emu_dir}", "LIBNAME=cup2d_emu",
+                    "PATCHED=ref_harness_patched_emu", f"RPATH={emu_dir}"], check=True, stdout=subprocess.DEVNULL)
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    L, K, ns = int(g["L"]), int(g["kiter"]), len(g["dt"])
+    N = 8 << L
+    z = np.zeros((N, N))
+    fin, fout = tmp_path / "in.bin", tmp_path / "out.bin"
+    np.concatenate([a.ravel() for a in (g["u0"], g["v0"], g["p0"], z, z, z)]).tofile(fin)
+    subprocess.run([os.path.join(ROOT, "oracle", "_ref", "ref_harness_patched_emu"), "steps", str(L), repr(float(g["nu"])),
+                    repr(float(g["cfl"])), str(ns), str(K), str(fin), str(fout)], check=True, stderr=subprocess.DEVNULL,
+                   env=dict(os.environ, OMP_NUM_THREADS="1", CUP2D_B200_MAX_ITER=str(K)), timeout=900)
+    raw = np.fromfile(fout).reshape(ns, 1 + 5 * N * N)
+    f = raw[:, 1:].reshape(ns, 5, N, N)
+    assert np.abs(raw[:, 0] - g["dt"]).max() < 1e-15
+    assert np.abs(f[:, 0] - g["u"]).max() < 1e-12 and np.abs(f[:, 1] - g["v"]).max() < 1e-12
+    assert np.abs(f[:, 2] - g["p"]).max() < 1e-10

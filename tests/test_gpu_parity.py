@@ -261,6 +261,35 @@ def test_reference_driver_with_adapter_matches_reference_gpu_solver(tmp_path):
     assert np.abs(f0[:, :3] - f1[:, :3]).max() < 1e-8
 
 
+@pytest.mark.parametrize("name", ["steps_L2_random_k8", "steps_L3_tg_k15"])
+def test_reference_driver_patched_loop_matches_golden(golden_dir, name, tmp_path):
+    """The drop-in boundary for the operators: the reference's OWN time loop (unmodified main.cpp with lines 6607-6642 and
+    7007-7187 replaced at build time by dropin/patched_loop_*.inc, oracle/_ref/ref_harness_patched) running its hot path on
+    libcup2d_b200.so, against the steps the unmodified reference produced."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "oracle", "_ref", "ref_harness_patched")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/ref_harness_patched not built (make -C oracle all in the build container)")
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    L, K, ns = int(g["L"]), int(g["kiter"]), len(g["dt"])
+    N = 8 << L
+    z = np.zeros((N, N))
+    fin, fout = tmp_path / "in.bin", tmp_path / "out.bin"
+    np.concatenate([a.ravel() for a in (g["u0"], g["v0"], g["p0"], z, z, z)]).tofile(fin)
+    try:
+        subprocess.run([exe, "steps", str(L), repr(float(g["nu"])), repr(float(g["cfl"])), str(ns), str(K), str(fin), str(fout)],
+                       check=True, stderr=subprocess.DEVNULL, timeout=300,
+                       env=dict(os.environ, OMP_NUM_THREADS="8", CUP2D_B200_MAX_ITER=str(K)))
+    except subprocess.TimeoutExpired:
+        pytest.skip("the patched reference driver did not finish in 300 s on this box")
+    raw = np.fromfile(fout).reshape(ns, 1 + 5 * N * N)
+    f = raw[:, 1:].reshape(ns, 5, N, N)
+    assert np.abs(raw[:, 0] - g["dt"]).max() < 1e-15
+    assert np.abs(f[:, 0] - g["u"]).max() < 1e-12 and np.abs(f[:, 1] - g["v"]).max() < 1e-12
+    assert np.abs(f[:, 2] - g["p"]).max() < 1e-10
+
+
 def test_rectangular_domain_vs_reference_golden(golden_dir):
     """2x1 base blocks, level 2 (64x32 cells): operators and two full steps against the reference."""
     d = np.load(os.path.join(golden_dir, "rect_2x1_L2.npz"))
