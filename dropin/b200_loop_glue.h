@@ -68,6 +68,20 @@ template <class GridT> void download(int field, GridT *grid, int dim) {
   check(cup2d_field_download(ctx, field, stage.data()), "cup2d_field_download");
   for (size_t i = 0; i < infos.size(); i++) memcpy(infos[i].block, stage.data() + i * n, n * sizeof(double));
 }
+// hand one shape's obstacle blocks (main.cpp:3283-3286: per block its own chi and u_def) to the device
+template <class ShapeT> void shape_set(int k, const ShapeT &shape) {
+  std::vector<int32_t> ids;
+  std::vector<double> X, U;
+  const auto &ob = shape->obstacleBlocks;
+  for (size_t i = 0; i < ob.size(); i++) {
+    if (!ob[i]) continue;
+    ids.push_back((int32_t)i);
+    const double *c = (const double *)ob[i]->chi, *u = (const double *)ob[i]->udef;
+    X.insert(X.end(), c, c + CUP2D_BS * CUP2D_BS);
+    U.insert(U.end(), u, u + 2 * CUP2D_BS * CUP2D_BS);
+  }
+  check(cup2d_shape_set(ctx, k, (int)ids.size(), ids.data(), X.data(), U.data()), "cup2d_shape_set");
+}
 inline int max_iter() { // cuda.cu:438 hard-codes 1000; the test harness may lower it
   const char *e = getenv("CUP2D_B200_MAX_ITER");
   return e ? atoi(e) : 1000;

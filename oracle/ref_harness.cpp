@@ -44,6 +44,10 @@
 //        22: ScalarLab of pres {-1,-1,2,2} (10*10)
 //        30: tmpV after KernelAdvectDiffuse + flux correction   31: tmp after pressure_rhs (+fc)
 //        32: tmp after pressure_rhs1 (+fc)   33: tmpV after pressureCorrectionKernel (+fc)
+//   ref_harness fsteps L nsteps kiter out.bin
+//        two fish on a uniform level-L grid (the configuration of `penal`), recorded at the dt reduction of every step
+//        (so it also works for the patched drivers): per step dt, then u v p (1 + 3 N^2 doubles), then per shape
+//        centerOfMass[2], u, v, omega
 //   ref_harness steps L nu cfl nsteps kiter in.bin out.bin
 //        in : as above (udef ignored: no shapes => udef = 0, chi = 0 ; p = initial pres)
 //        out: per step: dt, then u v p  b x   (1 + 5 N^2 doubles), b/x = Poisson rhs / solution
@@ -54,7 +58,9 @@
 //        prints one JSON line with per-operator CPU times (seconds, median of reps)
 #define CUP2D_REF_HOOK_TU 1
 #define main ref_main
-#ifdef CUP2D_PATCHED_MAIN
+#if defined(CUP2D_PATCHED_MAIN) && CUP2D_PATCHED_MAIN == 2
+#include "main_resident.cpp" // oracle/_ref/: the device-resident form with bodies (oracle/Makefile, ref_resident)
+#elif defined(CUP2D_PATCHED_MAIN)
 #include "main_patched.cpp" // oracle/_ref/: main.cpp with its hot path spliced onto cup2d_b200 (oracle/Makefile, ref_patched)
 #else
 #include "main.cpp" // resolved with -I/root/reference
@@ -68,7 +74,7 @@ extern int cup2d_ref_force_iters;
 extern int cup2d_ref_fixed_iters;
 
 namespace {
-enum Mode { ORDER, OPS, STEPS, TIME, AMR, VORT, TAGS, DUMP, PENAL, AMRLAB } g_mode;
+enum Mode { ORDER, OPS, STEPS, TIME, AMR, VORT, TAGS, DUMP, PENAL, AMRLAB, FSTEPS } g_mode;
 int g_sum7 = 0, g_sum2 = 0, g_step = 0;
 int g_extra = 0;
 double g_rtol = 0, g_time = 0;
@@ -449,6 +455,20 @@ static void penal_hook(int op, void *buf, int count) {
 
 void cup2d_ref_hook(int op, void *buf, int count) {
   if (g_mode == PENAL) { penal_hook(op, buf, count); return; }
+  if (g_mode == FSTEPS) {
+    if (op != MPI_MAX || count != 1) return;
+    const int call = g_calls++;
+    if (call == 0) { g_fout = fopen(g_out.c_str(), "wb"); return; }
+    fwrite(&sim.dt, sizeof(double), 1, g_fout);
+    write_field(var.vel, 2);
+    write_field(var.pres, 1);
+    for (auto &sh : sim.shapes) {
+      const double r[5] = {sh->centerOfMass[0], sh->centerOfMass[1], sh->u, sh->v, sh->omega};
+      fwrite(r, sizeof(double), 5, g_fout);
+    }
+    if (call == g_nsteps) { fclose(g_fout); exit(0); }
+    return;
+  }
   if (g_mode == AMRLAB) {
     if (op != MPI_MAX || count != 1) return;
     if (g_calls++ < g_nsteps) return; // let the reference run nsteps steps first
@@ -576,8 +596,8 @@ int main(int argc, char **argv) {
                           "-shapes", "angle=0 L=0.2 xpos=1.8 ypos=0.8\n angle=180 L=0.2 xpos=1.6 ypos=0.8"};
     return ref_main(sizeof args / sizeof *args, (char **)args);
   }
-  else if (mode == "penal" && argc == 6) {
-    g_mode = PENAL; g_nsteps = atoi(argv[3]); g_kiter = atoi(argv[4]); g_out = argv[5];
+  else if ((mode == "penal" || mode == "fsteps") && argc == 6) {
+    g_mode = mode == "penal" ? PENAL : FSTEPS; g_nsteps = atoi(argv[3]); g_kiter = atoi(argv[4]); g_out = argv[5];
     cup2d_ref_force_iters = g_kiter;
     char a_l[16], a_lm[16];
     snprintf(a_l, sizeof a_l, "%d", g_L);

@@ -159,3 +159,31 @@ def test_reference_time_loop_on_the_emulated_library(emulated_library, golden_di
     assert np.abs(raw[:, 0] - g["dt"]).max() < 1e-15
     assert np.abs(f[:, 0] - g["u"]).max() < 1e-12 and np.abs(f[:, 1] - g["v"]).max() < 1e-12
     assert np.abs(f[:, 2] - g["p"]).max() < 1e-10
+
+
+def test_reference_loop_with_bodies_device_resident_on_the_emulated_library(emulated_library, tmp_path):
+    """the device-resident form of the drop-in, WITH bodies: the reference's own loop with RK2, the penalisation sums, the
+    blend, the u_def assembly and the pressure section on the library (dropin/resident_*.inc over main.cpp:6607-6642, 6648-6679,
+    6945-6979, 6981-7187) while ongrid(), the 3x3 rigid-motion solve, the collision model and the forces stay on the host —
+    two interacting fish, 4 steps (the last one with a collision), against the unmodified reference run the same way"""
+    import numpy as np
+    if not os.path.exists("/root/reference/main.cpp"):
+        pytest.skip("needs the reference sources to build the patched driver (build container only)")
+    emu_dir = os.path.dirname(emulated_library)
+    subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), "ref", "ref_resident", f"LIBDIR={emu_dir}", "LIBNAME=cup2d_emu",
+                    "RESIDENT=ref_harness_resident_emu", f"RPATH={emu_dir}"], check=True, stdout=subprocess.DEVNULL)
+    env = dict(os.environ, OMP_NUM_THREADS="1", CUP2D_B200_MAX_ITER="8",
+               CUP2D_REF_SHAPES="angle=0 L=0.8 xpos=0.52 ypos=0.44\n angle=175 L=0.8 xpos=0.47 ypos=0.56")
+    outs = []
+    for exe in ("ref_harness", "ref_harness_resident_emu"):
+        out = tmp_path / (exe + ".bin")
+        subprocess.run([os.path.join(ROOT, "oracle", "_ref", exe), "fsteps", "4", "4", "8", str(out)], check=True,
+                       stderr=subprocess.DEVNULL, stdout=subprocess.DEVNULL, env=env, timeout=900)
+        outs.append(np.fromfile(out))
+    N = 128
+    a, b = (o.reshape(-1, 1 + 3 * N * N + 10) for o in outs)
+    assert a.shape == b.shape and len(a) == 4
+    assert np.abs(a[:, 0] - b[:, 0]).max() < 1e-15                      # dt
+    assert np.abs(a[:, 1:-10] - b[:, 1:-10]).max() < 1e-12              # u, v, p
+    assert np.abs(a[:, -10:] - b[:, -10:]).max() < 1e-12                # centre of mass, u, v, omega of both fish
+    assert np.abs(a[-1, 1:1 + N * N]).max() > 0.1                       # the fish really drive the flow

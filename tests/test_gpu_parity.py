@@ -290,6 +290,34 @@ def test_reference_driver_patched_loop_matches_golden(golden_dir, name, tmp_path
     assert np.abs(f[:, 2] - g["p"]).max() < 1e-10
 
 
+def test_reference_driver_resident_loop_with_bodies(tmp_path):
+    """The device-resident drop-in with bodies (oracle/_ref/ref_harness_resident: dropin/resident_*.inc spliced over
+    main.cpp:6607-6642, 6648-6679, 6945-6979, 6981-7187) against the unmodified reference loop with its CPU solver
+    (oracle/_ref/ref_harness): two interacting fish, 4 steps, 8 Poisson iterations each."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exes = [os.path.join(root, "oracle", "_ref", n) for n in ("ref_harness", "ref_harness_resident")]
+    if not all(os.path.exists(e) for e in exes):
+        pytest.skip("oracle/_ref binaries not built (make -C oracle all in the build container)")
+    env = dict(os.environ, OMP_NUM_THREADS="8", CUP2D_B200_MAX_ITER="8",
+               CUP2D_REF_SHAPES="angle=0 L=0.8 xpos=0.52 ypos=0.44\n angle=175 L=0.8 xpos=0.47 ypos=0.56")
+    outs = []
+    for exe in exes:
+        out = tmp_path / (os.path.basename(exe) + ".bin")
+        try:
+            subprocess.run([exe, "fsteps", "4", "4", "8", str(out)], check=True, stderr=subprocess.DEVNULL, stdout=subprocess.DEVNULL,
+                           env=env, timeout=300)
+        except subprocess.TimeoutExpired:
+            pytest.skip("a reference driver did not finish in 300 s on this box")
+        outs.append(np.fromfile(out))
+    N = 128
+    a, b = (o.reshape(-1, 1 + 3 * N * N + 10) for o in outs)
+    assert a.shape == b.shape and len(a) == 4
+    assert np.abs(a[:, 0] - b[:, 0]).max() < 1e-14
+    assert np.abs(a[:, 1:-10] - b[:, 1:-10]).max() < 1e-9    # OpenMP summation order on the reference side
+    assert np.abs(a[:, -10:] - b[:, -10:]).max() < 1e-9
+
+
 def test_rectangular_domain_vs_reference_golden(golden_dir):
     """2x1 base blocks, level 2 (64x32 cells): operators and two full steps against the reference."""
     d = np.load(os.path.join(golden_dir, "rect_2x1_L2.npz"))
