@@ -82,6 +82,38 @@ template <class ShapeT> void shape_set(int k, const ShapeT &shape) {
   }
   check(cup2d_shape_set(ctx, k, (int)ids.size(), ids.data(), X.data(), U.data()), "cup2d_shape_set");
 }
+// ---- multi-level meshes: the same glue on the cup2d_amr context, re-created whenever adapt() changed the mesh ----------
+inline cup2d_amr *amr = nullptr;
+inline std::vector<int32_t> amr_mesh;
+template <class Sim, class GridT> void ensure_amr(const Sim &sim, GridT *grid) {
+  const auto &infos = grid->infos;
+  std::vector<int32_t> mesh(3 * infos.size());
+  for (size_t i = 0; i < infos.size(); i++) {
+    mesh[3 * i] = infos[i].level;
+    mesh[3 * i + 1] = infos[i].index[0];
+    mesh[3 * i + 2] = infos[i].index[1];
+  }
+  if (amr && mesh == amr_mesh) return;
+  if (amr) cup2d_amr_destroy(amr);
+  amr = nullptr;
+  check(cup2d_amr_create((int64_t)infos.size(), mesh.data(), sim.bpdx, sim.bpdy, sim.h0, sim.nu, 0, &amr), "cup2d_amr_create");
+  if (const char *e = getenv("CUP2D_B200_AMR_FAST")) check(cup2d_amr_set_fast(amr, atoi(e)), "cup2d_amr_set_fast");
+  amr_mesh.swap(mesh);
+}
+template <class GridT> void amr_upload(int field, GridT *grid, int dim) {
+  const auto &infos = grid->infos;
+  const size_t n = (size_t)dim * CUP2D_BS * CUP2D_BS;
+  stage.resize(infos.size() * n);
+  for (size_t i = 0; i < infos.size(); i++) memcpy(stage.data() + i * n, infos[i].block, n * sizeof(double));
+  check(cup2d_amr_field_upload(amr, field, stage.data()), "cup2d_amr_field_upload");
+}
+template <class GridT> void amr_download(int field, GridT *grid, int dim) {
+  auto &infos = grid->infos;
+  const size_t n = (size_t)dim * CUP2D_BS * CUP2D_BS;
+  stage.resize(infos.size() * n);
+  check(cup2d_amr_field_download(amr, field, stage.data()), "cup2d_amr_field_download");
+  for (size_t i = 0; i < infos.size(); i++) memcpy(infos[i].block, stage.data() + i * n, n * sizeof(double));
+}
 inline int max_iter() { // cuda.cu:438 hard-codes 1000; the test harness may lower it
   const char *e = getenv("CUP2D_B200_MAX_ITER");
   return e ? atoi(e) : 1000;

@@ -48,6 +48,9 @@
 //        two fish on a uniform level-L grid (the configuration of `penal`), recorded at the dt reduction of every step
 //        (so it also works for the patched drivers): per step dt, then u v p (1 + 3 N^2 doubles), then per shape
 //        centerOfMass[2], u, v, omega
+//   ref_harness asteps levelMax nsteps kiter out.bin
+//        the run.sh case (2 fish, regridding) recorded at the dt reduction of every step, so that it also works for the
+//        patched multi-level driver: per step double dt, double nblocks, then (level,i,j) as doubles, vel blocks, pres blocks
 //   ref_harness steps L nu cfl nsteps kiter in.bin out.bin
 //        in : as above (udef ignored: no shapes => udef = 0, chi = 0 ; p = initial pres)
 //        out: per step: dt, then u v p  b x   (1 + 5 N^2 doubles), b/x = Poisson rhs / solution
@@ -58,7 +61,9 @@
 //        prints one JSON line with per-operator CPU times (seconds, median of reps)
 #define CUP2D_REF_HOOK_TU 1
 #define main ref_main
-#if defined(CUP2D_PATCHED_MAIN) && CUP2D_PATCHED_MAIN == 2
+#if defined(CUP2D_PATCHED_MAIN) && CUP2D_PATCHED_MAIN == 3
+#include "main_amrloop.cpp" // oracle/_ref/: the multi-level form (oracle/Makefile, ref_amrloop)
+#elif defined(CUP2D_PATCHED_MAIN) && CUP2D_PATCHED_MAIN == 2
 #include "main_resident.cpp" // oracle/_ref/: the device-resident form with bodies (oracle/Makefile, ref_resident)
 #elif defined(CUP2D_PATCHED_MAIN)
 #include "main_patched.cpp" // oracle/_ref/: main.cpp with its hot path spliced onto cup2d_b200 (oracle/Makefile, ref_patched)
@@ -74,7 +79,7 @@ extern int cup2d_ref_force_iters;
 extern int cup2d_ref_fixed_iters;
 
 namespace {
-enum Mode { ORDER, OPS, STEPS, TIME, AMR, VORT, TAGS, DUMP, PENAL, AMRLAB, FSTEPS } g_mode;
+enum Mode { ORDER, OPS, STEPS, TIME, AMR, VORT, TAGS, DUMP, PENAL, AMRLAB, FSTEPS, ASTEPS } g_mode;
 int g_sum7 = 0, g_sum2 = 0, g_step = 0;
 int g_extra = 0;
 double g_rtol = 0, g_time = 0;
@@ -455,6 +460,20 @@ static void penal_hook(int op, void *buf, int count) {
 
 void cup2d_ref_hook(int op, void *buf, int count) {
   if (g_mode == PENAL) { penal_hook(op, buf, count); return; }
+  if (g_mode == ASTEPS) {
+    if (op != MPI_MAX || count != 1) return;
+    const int call = g_calls++;
+    if (call == 0) { g_fout = fopen(g_out.c_str(), "wb"); return; }
+    const double hdr[2] = {sim.dt, (double)var.vel->infos.size()};
+    fwrite(hdr, sizeof(double), 2, g_fout);
+    std::vector<double> mesh;
+    for (auto &info : var.vel->infos) { mesh.push_back(info.level); mesh.push_back(info.index[0]); mesh.push_back(info.index[1]); }
+    fwrite(mesh.data(), sizeof(double), mesh.size(), g_fout);
+    for (auto &info : var.vel->infos) fwrite(info.block, sizeof(double), 2 * _BS_ * _BS_, g_fout);
+    for (auto &info : var.pres->infos) fwrite(info.block, sizeof(double), _BS_ * _BS_, g_fout);
+    if (call == g_nsteps) { fclose(g_fout); exit(0); }
+    return;
+  }
   if (g_mode == FSTEPS) {
     if (op != MPI_MAX || count != 1) return;
     const int call = g_calls++;
@@ -584,9 +603,9 @@ int main(int argc, char **argv) {
                           "-shapes", "angle=0 L=0.2 xpos=1.8 ypos=0.8\n angle=180 L=0.2 xpos=1.6 ypos=0.8"};
     return ref_main(sizeof args / sizeof *args, (char **)args);
   }
-  else if (mode == "amrlab" && argc == 5) {
-    g_mode = AMRLAB; g_nsteps = atoi(argv[3]); g_out = argv[4];
-    cup2d_ref_force_iters = 5;
+  else if ((mode == "amrlab" && argc == 5) || (mode == "asteps" && argc == 6)) {
+    if (mode == "amrlab") { g_mode = AMRLAB; g_nsteps = atoi(argv[3]); g_out = argv[4]; cup2d_ref_force_iters = 5; }
+    else { g_mode = ASTEPS; g_nsteps = atoi(argv[3]); g_kiter = atoi(argv[4]); g_out = argv[5]; cup2d_ref_force_iters = g_kiter; }
     char a_lmax[16];
     snprintf(a_lmax, sizeof a_lmax, "%d", g_L);
     const char *args[] = {"ref_main", "-AdaptSteps", "20", "-bpdx", "2", "-bpdy", "1", "-CFL", "0.5", "-Ctol", "1",

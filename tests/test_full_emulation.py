@@ -187,3 +187,44 @@ def test_reference_loop_with_bodies_device_resident_on_the_emulated_library(emul
     assert np.abs(a[:, 1:-10] - b[:, 1:-10]).max() < 1e-12              # u, v, p
     assert np.abs(a[:, -10:] - b[:, -10:]).max() < 1e-12                # centre of mass, u, v, omega of both fish
     assert np.abs(a[-1, 1:1 + N * N]).max() > 0.1                       # the fish really drive the flow
+
+
+def _parse_asteps(path):
+    import numpy as np
+    a, i, out = np.fromfile(path), 0, []
+    while i < len(a):
+        dt, nb = a[i], int(a[i + 1])
+        i += 2
+        mesh = a[i:i + 3 * nb].reshape(nb, 3).astype(int)
+        i += 3 * nb
+        vel, pres = a[i:i + 128 * nb], a[i + 128 * nb:i + 192 * nb]
+        i += 192 * nb
+        out.append((dt, mesh, vel, pres))
+    return out
+
+
+def test_reference_amr_case_on_the_multi_level_path_emulated(emulated_library, tmp_path):
+    """config C1 end to end: the reference's own run.sh case (two fish, 7 refinement levels, 278 blocks, its own adapt() /
+    ongrid() / penalisation on the host) with RK2 and the whole pressure section on the multi-level path of the library
+    (dropin/amr_loop_*.inc on cup2d_amr: fast kernels, Poisson rows from the library's own plan), linked against the emulated
+    library, against the unmodified reference: same mesh and fields to rounding at every step.  (By hand: 13 steps across a
+    regrid 278 -> 281 blocks stay within 3e-15 / 1.3e-14 relative in velocity / pressure.)"""
+    import numpy as np
+    if not os.path.exists("/root/reference/main.cpp"):
+        pytest.skip("needs the reference sources to build the patched driver (build container only)")
+    emu_dir = os.path.dirname(emulated_library)
+    subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), "ref", "ref_amrloop", f"LIBDIR={emu_dir}", "LIBNAME=cup2d_emu",
+                    "AMRLOOP=ref_harness_amrloop_emu", f"RPATH={emu_dir}"], check=True, stdout=subprocess.DEVNULL)
+    env = dict(os.environ, OMP_NUM_THREADS="1", CUP2D_B200_MAX_ITER="5", CUP2D_B200_AMR_FAST="1")
+    runs = []
+    for exe in ("ref_harness", "ref_harness_amrloop_emu"):
+        out = tmp_path / (exe + ".bin")
+        subprocess.run([os.path.join(ROOT, "oracle", "_ref", exe), "asteps", "8", "3", "5", str(out)], check=True,
+                       stderr=subprocess.DEVNULL, stdout=subprocess.DEVNULL, env=env, timeout=1500)
+        runs.append(_parse_asteps(out))
+    assert len(runs[0]) == len(runs[1]) == 3
+    for (dt0, m0, v0, p0), (dt1, m1, v1, p1) in zip(*runs):
+        assert m0.shape == m1.shape and (m0 == m1).all() and len(set(m0[:, 0].tolist())) >= 5
+        assert abs(dt0 - dt1) < 1e-15
+        assert np.abs(v0 - v1).max() < 1e-12 * np.abs(v0).max()
+        assert np.abs(p0 - p1).max() < 1e-11 * max(np.abs(p0).max(), 1e-300)

@@ -141,3 +141,29 @@ def test_amr_full_step_against_composed_oracle(case, fast):
                            M=lambda q: (q.reshape(nb, 64) @ P.T).reshape(-1))
     vel, pres = amr.amr_pressure_correct(mesh, h0, v, x.reshape(nb, 8, 8, 1), pold, want_dt)
     assert rel(sim.download("vel"), vel) < 1e-9 and rel(sim.download("pres"), pres) < 1e-9
+
+
+def test_reference_amr_case_on_the_multi_level_device_path(tmp_path):
+    """config C1 on the device: the reference's own run.sh case with RK2 and the pressure section on cup2d_amr (fast kernels)
+    — oracle/_ref/ref_harness_amrloop — against the unmodified reference loop (oracle/_ref/ref_harness), 6 steps"""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exes = [os.path.join(root, "oracle", "_ref", n) for n in ("ref_harness", "ref_harness_amrloop")]
+    if not all(os.path.exists(e) for e in exes):
+        pytest.skip("oracle/_ref binaries not built")
+    env = dict(os.environ, OMP_NUM_THREADS="1", CUP2D_B200_MAX_ITER="8", CUP2D_B200_AMR_FAST="1")
+    runs = []
+    for exe in exes:
+        out = tmp_path / (os.path.basename(exe) + ".bin")
+        subprocess.run([exe, "asteps", "8", "6", "8", str(out)], check=True, stderr=subprocess.DEVNULL, stdout=subprocess.DEVNULL,
+                       env=env, timeout=600)
+        a, i, steps = np.fromfile(out), 0, []
+        while i < len(a):
+            dt, nb = a[i], int(a[i + 1])
+            steps.append((dt, a[i + 2:i + 2 + 3 * nb].copy(), a[i + 2 + 3 * nb:i + 2 + 131 * nb].copy(), a[i + 2 + 131 * nb:i + 2 + 195 * nb].copy()))
+            i += 2 + 195 * nb
+        runs.append(steps)
+    assert len(runs[0]) == len(runs[1]) == 6
+    for (dt0, m0, v0, p0), (dt1, m1, v1, p1) in zip(*runs):
+        assert np.array_equal(m0, m1) and abs(dt0 - dt1) < 1e-14
+        assert np.abs(v0 - v1).max() < 1e-10 * np.abs(v0).max() and np.abs(p0 - p1).max() < 1e-9 * np.abs(p0).max()
