@@ -85,7 +85,7 @@ ASM_REWRITES = [  # (regex over the source text, replacement): the PTX of common
     (r'asm volatile\("fence\.mbarrier_init.*?\);', ";"),
     (r'asm volatile\("mbarrier\.arrive\.expect_tx.*?: "memory"\);', "(void)bar; (void)bytes;"),
     (r'asm volatile\("\{\\n".*?: "memory"\);', "(void)bar; (void)parity; /* copies are synchronous here */"),
-    (r'asm volatile\("cp\.async\.bulk\.shared.*?: "memory"\);', "memcpy(smem_dst, gmem_src, bytes); (void)bar;"),
+    (r'asm volatile\("cp\.async\.bulk\.shared.*?: "memory"\);', "emu_bulk_copy(smem_dst, gmem_src, bytes); (void)bar;"),
     (r'asm\("rcp\.approx\.ftz\.f64 %0, %1;" : "=d"\(r\) : "d"\(x\)\);', "r = (double)(1.0f / (float)x);"),
     (r'asm volatile\("st\.release\.sys.*?: "memory"\);', "__threadfence(); *(volatile unsigned long long *)p = v;"),
     (r'asm volatile\("st\.relaxed\.sys.*?: "memory"\);', "*(volatile unsigned long long *)p = v;"),
@@ -152,14 +152,18 @@ def build_full(defines=(), tag=""):
     return lib
 
 
-def build_tsan(defines=(), tag=""):
-    """the emulated product sources + tsan_driver.cpp with -fsanitize=thread -> an executable that hunts for data races"""
+def build_tsan(defines=(), tag="", sanitize="thread"):
+    """the emulated product sources + tsan_driver.cpp with -fsanitize=thread -> an executable that hunts for data races;
+    sanitize="address,alignment,bounds" -> the same driver hunting for out-of-bounds accesses of device buffers and shared
+    arrays (each its own exact-size allocation) and for vector loads/stores that are not aligned to their size"""
     build_full()
     srcs = [os.path.join(FULL, f) for f in sorted(os.listdir(FULL)) if f.endswith(".cpp")]
-    exe = os.path.join(FULL, f"tsan_driver{tag}")
+    exe = os.path.join(FULL, f"{'tsan' if sanitize == 'thread' else 'asan'}_driver{tag}")
     if _fresh(exe, _inputs()):
         return exe
-    subprocess.run(["/usr/bin/g++", "-O1", "-g", "-std=c++20", "-pthread", "-fsanitize=thread", "-w", *[f"-D{d}" for d in defines],
+    subprocess.run(["/usr/bin/g++", "-O1", "-g", "-std=c++20", "-pthread", f"-fsanitize={sanitize}",
+                    *([] if sanitize == "thread" else ["-fno-sanitize-recover=all"]), "-w",
+                    *[f"-D{d}" for d in defines],
                     "-I", FULL, "-I", HERE, "-o", exe,
                     os.path.join(HERE, "tsan_driver.cpp"), *srcs], check=True)
     return exe

@@ -7,7 +7,9 @@
 #include "../../include/cup2d_b200.h"
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
+#include <cstdint>
 #include <cstring>
 #include <functional>
 #include <string>
@@ -26,8 +28,24 @@ enum cudaMemcpyKind { cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpy
 struct EmuIdx { int x = 0; };
 inline thread_local EmuIdx blockIdx, threadIdx, blockDim, gridDim;
 
-template <class T> cudaError_t cudaMalloc(T **p, size_t n) { *p = (T *)malloc(n ? n : 1); return *p ? 0 : 2; }
+// device allocations: 256-byte aligned like cudaMalloc, exact size (so that AddressSanitizer sees overruns), and filled with
+// 0xFF bytes (NaN doubles, -1 indices): cudaMalloc does not zero memory, a fresh malloc often does
+template <class T> cudaError_t cudaMalloc(T **p, size_t n) {
+  void *q = nullptr;
+  if (posix_memalign(&q, 256, n ? n : 1)) return 2;
+  memset(q, 0xFF, n ? n : 1);
+  *p = (T *)q;
+  return 0;
+}
 inline cudaError_t cudaFree(void *p) { free(p); return 0; }
+// cp.async.bulk: both addresses and the size must be multiples of 16 bytes
+inline void emu_bulk_copy(void *dst, const void *src, size_t bytes) {
+  if (((uintptr_t)dst | (uintptr_t)src | bytes) & 15) {
+    fprintf(stderr, "emulation: misaligned bulk copy %p <- %p, %zu bytes\n", dst, src, bytes);
+    abort();
+  }
+  memcpy(dst, src, bytes);
+}
 inline cudaError_t cudaMemcpy(void *d, const void *s, size_t n, cudaMemcpyKind) { memcpy(d, s, n); return 0; }
 inline cudaError_t cudaMemcpyAsync(void *d, const void *s, size_t n, cudaMemcpyKind, cudaStream_t) { memcpy(d, s, n); return 0; }
 inline cudaError_t cudaMemset(void *d, int v, size_t n) { memset(d, v, n); return 0; }
@@ -95,7 +113,10 @@ template <class T> T __shfl_down_sync(unsigned, T v, int d) { return emu_shfl(v,
 inline void *emu_shared(int id, size_t bytes) {
   std::lock_guard<std::mutex> g(emu_block->shm_lock);
   void *&p = emu_block->shm[id];
-  if (!p) p = aligned_alloc(128, (bytes + 127) / 128 * 128);
+  if (!p) { // exact size + garbage, like the real thing
+    if (posix_memalign(&p, 128, bytes ? bytes : 1)) abort();
+    memset(p, 0xFF, bytes ? bytes : 1);
+  }
   return p;
 }
 inline void emu_launch_coop(int grid, int block, const std::function<void()> &body) {
@@ -115,9 +136,10 @@ inline void emu_launch_coop(int grid, int block, const std::function<void()> &bo
 }
 #define __shared__ static
 #define __align__(n) __attribute__((aligned(n)))
-struct double2 { double x, y; };
-struct int2 { int x, y; };
-struct int4 { int x, y, z, w; };
+// vector types carry the alignment the hardware demands of their loads and stores (-fsanitize=alignment reports a violation)
+struct alignas(16) double2 { double x, y; };
+struct alignas(8) int2 { int x, y; };
+struct alignas(16) int4 { int x, y, z, w; };
 inline double2 make_double2(double x, double y) { return {x, y}; }
 inline int2 make_int2(int x, int y) { return {x, y}; }
 inline int4 make_int4(int x, int y, int z, int w) { return {x, y, z, w}; }

@@ -41,5 +41,5 @@ inline size_t __cvta_generic_to_shared(const void *p) { return (size_t)p; }
 using std::max;
 using std::min;
 inline int min(int a, long b) { return (int)std::min<long>(a, b); }
-struct float4 { float x, y, z, w; };
+struct alignas(16) float4 { float x, y, z, w; };
 inline float4 make_float4(float x, float y, float z, float w) { return {x, y, z, w}; }

@@ -5,6 +5,7 @@
 #include "../../include/cup2d_b200.h"
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <vector>
 
 #define CHECK(x)                                                                                  \
@@ -16,7 +17,36 @@
     }                                                                                             \
   } while (0)
 
-int main() {
+// tsan_driver <mesh.bin> <bpdx> <bpdy> <h0>: multi-level steps on a mesh given as int32 (level, i, j) triples
+static int run_mesh(const char *path, int bpdx, int bpdy, double h0) {
+  FILE *f = fopen(path, "rb");
+  if (!f) return 2;
+  std::vector<int32_t> b;
+  int32_t t[3];
+  while (fread(t, sizeof(int32_t), 3, f) == 3) b.insert(b.end(), t, t + 3);
+  fclose(f);
+  const int64_t n = (int64_t)b.size() / 3;
+  cup2d_amr *a = nullptr;
+  CHECK(cup2d_amr_create(n, b.data(), bpdx, bpdy, h0, 1e-3, 0, &a));
+  std::vector<double> vel(n * 128), pres(n * 64);
+  for (size_t i = 0; i < vel.size(); i++) vel[i] = std::sin(0.29 * i) * 0.7;
+  for (size_t i = 0; i < pres.size(); i++) pres[i] = std::cos(0.13 * i);
+  for (int fast = 0; fast < 2; fast++) {
+    CHECK(cup2d_amr_set_fast(a, fast));
+    CHECK(cup2d_amr_field_upload(a, CUP2D_VEL, vel.data()));
+    CHECK(cup2d_amr_field_upload(a, CUP2D_PRES, pres.data()));
+    double dt, err;
+    int it;
+    CHECK(cup2d_amr_step(a, 0.5, 0.0, 0.0, 0.0, 0, 3, &dt, &it, &err));
+    if (!std::isfinite(dt) || !std::isfinite(err)) return 3;
+    printf("mesh step (fast=%d): %lld blocks dt %.3e iters %d err %.3e\n", fast, (long long)n, dt, it, err);
+  }
+  cup2d_amr_destroy(a);
+  return 0;
+}
+
+int main(int argc, char **argv) {
+  if (argc == 5) return run_mesh(argv[1], atoi(argv[2]), atoi(argv[3]), atof(argv[4]));
   { // uniform grid, level 2: 16 blocks
     const int L = 2, nb1 = 1 << L, n = nb1 * nb1;
     std::vector<int32_t> ij(2 * n);
