@@ -212,11 +212,12 @@ typedef void (*adv_fn)(const double *, const double *, double *, const int *, co
 
 int launch_advect(cup2d_sim *s, const double *in, const double *old, double *out, double coef,
                   double dt, bool raw) {
-  static bool constants_up = false;
-  if (!constants_up) {
+  static PerDeviceOnce constants;
+  int rc = constants.run(s->device, []() -> int {
     CUP2D_CUDA(cudaMemcpyToSymbol(cW, hW, sizeof hW));
-    constants_up = true;
-  }
+    return (int)CUP2D_OK;
+  });
+  if (rc) return rc;
   if (!s->d_adv_lut) { // repack table of interior tiles: (destination in the planes) << 16 | source slot
     std::vector<unsigned> lut;
     for (int ty = 0; ty < TW; ty++)
@@ -230,11 +231,12 @@ int launch_advect(cup2d_sim *s, const double *in, const double *old, double *out
   }
   const int mode = raw ? 0 : (old == in ? 1 : 2);
   const adv_fn fn = mode == 0 ? advect_stage_kernel<0> : mode == 1 ? advect_stage_kernel<1> : advect_stage_kernel<2>;
-  static bool configured[3] = {false, false, false};
-  if (!configured[mode]) {
+  static PerDeviceOnce configured[3];
+  rc = configured[mode].run(s->device, [fn]() -> int {
     CUP2D_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, ADV_SMEM));
-    configured[mode] = true;
-  }
+    return (int)CUP2D_OK;
+  });
+  if (rc) return rc;
   const double afac = -dt * s->h; // main.cpp:5447
   const double dfac = s->nu * dt; // main.cpp:5446
   const double ofac = coef / (s->h * s->h);

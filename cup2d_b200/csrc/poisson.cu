@@ -39,9 +39,7 @@ constexpr double EPS21 = 1e-21;    // cuda.cu:409
 __constant__ double cS[4];   // sin(pi/9), sin(2pi/9), sin(3pi/9), sin(4pi/9)
 __constant__ double cIL[64]; // -(2/9)^2 / (lambda_m + lambda_k)
 
-static bool g_consts_ready = false;
-static int init_consts() {
-  if (g_consts_ready) return CUP2D_OK;
+static int upload_consts() {
   double S[4], IL[64], lam[8];
   const double pi = 3.14159265358979323846;
   for (int k = 0; k < 4; k++) S[k] = std::sin((k + 1) * pi / 9.0);
@@ -50,9 +48,9 @@ static int init_consts() {
     for (int k = 0; k < 8; k++) IL[m * 8 + k] = -(4.0 / 81.0) / (lam[m] + lam[k]);
   CUP2D_CUDA(cudaMemcpyToSymbol(cS, S, sizeof S));
   CUP2D_CUDA(cudaMemcpyToSymbol(cIL, IL, sizeof IL));
-  g_consts_ready = true;
   return CUP2D_OK;
 }
+static PerDeviceOnce g_consts;
 
 // X[k] = sum_j x[j] sin((j+1)(k+1) pi/9).  sin((9-j')k' pi/9) = (-1)^(k'+1) sin(j'k' pi/9): odd modes see the
 // symmetric part u of the input, even modes the antisymmetric part w.
@@ -353,7 +351,7 @@ static inline int red_grid(const cup2d_sim *s, int nrows) {
 
 int poisson_solve(cup2d_sim *s, double tol_abs, double tol_rel, int max_restarts, int max_iter,
                   int *iters, double *err) {
-  int rc = init_consts();
+  int rc = g_consts.run(s->device, upload_consts);
   if (rc) return rc;
   const int nrows = (int)s->nloc * 8;
   const int grid = red_grid(s, nrows);

@@ -3,6 +3,7 @@
 #include "../../include/cup2d_b200.h"
 #include "common.cuh"
 #include "rows.cuh"
+#include <mutex>
 #include <vector>
 
 namespace cup2d {
@@ -39,6 +40,21 @@ struct PeerBlob { // what every rank publishes to the others (cup2d_peer_export)
   cudaIpcMemHandle_t mailbox;
   int64_t nloc;
   int32_t rank, device;
+};
+
+// Constant memory and function attributes are per-DEVICE state: a call site that sets them up once keeps one of these and
+// runs its setup once per device ordinal (one process may drive several devices).
+struct PerDeviceOnce {
+  std::mutex m;
+  unsigned long long seen = 0;
+  template <class F> int run(int device, F &&setup) {
+    std::lock_guard<std::mutex> g(m);
+    const unsigned long long bit = 1ull << (device & 63);
+    if (seen & bit) return CUP2D_OK;
+    const int rc = setup();
+    if (rc == CUP2D_OK) seen |= bit;
+    return rc;
+  }
 };
 
 } // namespace cup2d
