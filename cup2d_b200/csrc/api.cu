@@ -380,11 +380,19 @@ int cup2d_poisson_create_general(int64_t nblocks, const int32_t *nbr, int64_t n_
     if (e != cudaSuccess) return e;
     return cudaMemcpy(*d, h, bytes, cudaMemcpyHostToDevice);
   };
-  CUP2D_CUDA(up((void **)&s->d_irr_blk, blk.data(), blk.size() * sizeof(int)));
-  CUP2D_CUDA(up((void **)&s->d_irr_tab, tab.data(), tab.size() * sizeof(int)));
-  CUP2D_CUDA(up((void **)&s->d_irr_rowptr, irr_rowptr, (size_t)(n_irr + 1) * sizeof(int)));
-  CUP2D_CUDA(up((void **)&s->d_irr_col, irr_col, (size_t)nnz * sizeof(int)));
-  CUP2D_CUDA(up((void **)&s->d_irr_val, irr_val, (size_t)nnz * sizeof(double)));
+  auto upload_rows = [&]() -> int {
+    CUP2D_CUDA(up((void **)&s->d_irr_blk, blk.data(), blk.size() * sizeof(int)));
+    CUP2D_CUDA(up((void **)&s->d_irr_tab, tab.data(), tab.size() * sizeof(int)));
+    CUP2D_CUDA(up((void **)&s->d_irr_rowptr, irr_rowptr, (size_t)(n_irr + 1) * sizeof(int)));
+    CUP2D_CUDA(up((void **)&s->d_irr_col, irr_col, (size_t)nnz * sizeof(int)));
+    CUP2D_CUDA(up((void **)&s->d_irr_val, irr_val, (size_t)nnz * sizeof(double)));
+    return CUP2D_OK;
+  };
+  if ((rc = upload_rows())) { // no half-built context escapes: the caller gets an error and a null handle
+    cup2d_destroy(s);
+    *out = nullptr;
+    return rc;
+  }
   s->n_irr_rows = n_irr;
   return CUP2D_OK;
 }
