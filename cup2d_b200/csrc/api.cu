@@ -446,6 +446,14 @@ void cup2d_destroy(cup2d_sim *s) {
       if (s->peer_mailbox[r]) cudaIpcCloseMemHandle(s->peer_mailbox[r]);
     }
   }
+  for (auto &ps : s->pipe) {
+    cudaFree(ps.vel); cudaFree(ps.pres);
+    if (ps.in_done) cudaEventDestroy(ps.in_done);
+    if (ps.step_done) cudaEventDestroy(ps.step_done);
+    if (ps.out_done) cudaEventDestroy(ps.out_done);
+  }
+  if (s->pipe_in) cudaStreamDestroy(s->pipe_in);
+  if (s->pipe_out) cudaStreamDestroy(s->pipe_out);
   for (auto p : s->f) cudaFree(p);
   for (auto p : s->kx) cudaFree(p);
   cudaFree(s->kr); cudaFree(s->krhat); cudaFree(s->kp); cudaFree(s->knu); cudaFree(s->kt); cudaFree(s->kz); cudaFree(s->kzr);
@@ -693,6 +701,78 @@ int cup2d_step(cup2d_sim *s, double dt_in, int keep_udef, double tol_abs, double
   if ((rc = poisson_solve(s, tol_abs, tol_rel, max_restarts, max_iter, iters_out, err_out))) return rc;
   if ((rc = launch_pressure_correct(s, dt))) return rc;
   if (dt_out) *dt_out = dt;
+  return CUP2D_OK;
+}
+
+/* ---- host-buffer pipeline: upload(n+1) || step(n) || download(n-1) on three streams (include/cup2d_b200.h) ---- */
+static int pipe_slot(cup2d_sim *s, int slot) {
+  CHECK_SIM(s);
+  CUP2D_REQUIRE(slot >= 0 && slot < CUP2D_PIPE_SLOTS, "cup2d_pipe: slot out of range");
+  CUP2D_REQUIRE(s->nranks == 1 && !s->poisson_only, "cup2d_pipe: single-rank contexts with a grid only (peer mappings are tied to the field buffers)");
+  CUP2D_CUDA(cudaSetDevice(s->device));
+  if (!s->pipe_in) {
+    CUP2D_CUDA(cudaStreamCreateWithFlags(&s->pipe_in, cudaStreamNonBlocking));
+    CUP2D_CUDA(cudaStreamCreateWithFlags(&s->pipe_out, cudaStreamNonBlocking));
+  }
+  cup2d_sim::PipeSet &ps = s->pipe[slot];
+  if (!ps.vel) {
+    CUP2D_CUDA(cudaMalloc(&ps.vel, (size_t)s->nslots * 128 * sizeof(double)));
+    CUP2D_CUDA(cudaMalloc(&ps.pres, (size_t)s->nslots * 64 * sizeof(double)));
+    CUP2D_CUDA(cudaEventCreateWithFlags(&ps.in_done, cudaEventDisableTiming));
+    CUP2D_CUDA(cudaEventCreateWithFlags(&ps.step_done, cudaEventDisableTiming));
+    CUP2D_CUDA(cudaEventCreateWithFlags(&ps.out_done, cudaEventDisableTiming));
+  }
+  return CUP2D_OK;
+}
+int cup2d_pipe_upload(cup2d_sim *s, int slot, const double *vel_host, const double *pres_host) {
+  int rc = pipe_slot(s, slot);
+  if (rc) return rc;
+  CUP2D_REQUIRE(vel_host && pres_host, "cup2d_pipe_upload: null host pointer");
+  cup2d_sim::PipeSet &ps = s->pipe[slot];
+  // the set may still be written by a step or read by a download enqueued earlier (a never-recorded event does not block)
+  CUP2D_CUDA(cudaStreamWaitEvent(s->pipe_in, ps.step_done, 0));
+  CUP2D_CUDA(cudaStreamWaitEvent(s->pipe_in, ps.out_done, 0));
+  CUP2D_CUDA(cudaMemcpyAsync(ps.vel, vel_host, (size_t)s->nloc * 128 * sizeof(double), cudaMemcpyHostToDevice, s->pipe_in));
+  CUP2D_CUDA(cudaMemcpyAsync(ps.pres, pres_host, (size_t)s->nloc * 64 * sizeof(double), cudaMemcpyHostToDevice, s->pipe_in));
+  CUP2D_CUDA(cudaEventRecord(ps.in_done, s->pipe_in));
+  return CUP2D_OK;
+}
+int cup2d_pipe_step(cup2d_sim *s, int slot, double dt_in, double tol_abs, double tol_rel, int max_restarts, int max_iter,
+                    double *dt_out, int *iters_out, double *err_out) {
+  int rc = pipe_slot(s, slot);
+  if (rc) return rc;
+  cup2d_sim::PipeSet &ps = s->pipe[slot];
+  CUP2D_CUDA(cudaStreamWaitEvent(s->stream, ps.in_done, 0));
+  CUP2D_CUDA(cudaStreamWaitEvent(s->stream, ps.out_done, 0)); // a download of this set's previous contents
+  // The context trades its vel / pres buffers for the set's for the duration of the step and trades back afterwards: the
+  // step swaps buffers internally (vold <-> vel, pold <-> pres), so what comes back to the set are the buffers that hold
+  // the RESULT, whichever they are, and the context keeps the same number of buffers it had.  Work enqueued on s->stream by
+  // later steps never touches a buffer a set owns, so a download can run beside the next step.
+  std::swap(s->f[CUP2D_VEL], ps.vel);
+  std::swap(s->f[CUP2D_PRES], ps.pres);
+  rc = cup2d_step(s, dt_in, 0, tol_abs, tol_rel, max_restarts, max_iter, dt_out, iters_out, err_out);
+  std::swap(s->f[CUP2D_VEL], ps.vel);
+  std::swap(s->f[CUP2D_PRES], ps.pres);
+  if (rc) return rc;
+  CUP2D_CUDA(cudaEventRecord(ps.step_done, s->stream));
+  return CUP2D_OK;
+}
+int cup2d_pipe_download(cup2d_sim *s, int slot, double *vel_host, double *pres_host) {
+  int rc = pipe_slot(s, slot);
+  if (rc) return rc;
+  CUP2D_REQUIRE(vel_host && pres_host, "cup2d_pipe_download: null host pointer");
+  cup2d_sim::PipeSet &ps = s->pipe[slot];
+  CUP2D_CUDA(cudaStreamWaitEvent(s->pipe_out, ps.in_done, 0));
+  CUP2D_CUDA(cudaStreamWaitEvent(s->pipe_out, ps.step_done, 0));
+  CUP2D_CUDA(cudaMemcpyAsync(vel_host, ps.vel, (size_t)s->nloc * 128 * sizeof(double), cudaMemcpyDeviceToHost, s->pipe_out));
+  CUP2D_CUDA(cudaMemcpyAsync(pres_host, ps.pres, (size_t)s->nloc * 64 * sizeof(double), cudaMemcpyDeviceToHost, s->pipe_out));
+  CUP2D_CUDA(cudaEventRecord(ps.out_done, s->pipe_out));
+  return CUP2D_OK;
+}
+int cup2d_pipe_wait(cup2d_sim *s, int slot) {
+  int rc = pipe_slot(s, slot);
+  if (rc) return rc;
+  CUP2D_CUDA(cudaEventSynchronize(s->pipe[slot].out_done));
   return CUP2D_OK;
 }
 

@@ -107,6 +107,10 @@ struct cup2d_sim {
   // bodies: per-shape obstacle blocks on the device (cup2d_shape_set)
   struct Shape { int nob = 0, cap = 0; int *d_ids = nullptr; double *d_X = nullptr, *d_udef = nullptr; };
   std::vector<Shape> shapes;
+  // host-buffer pipeline (cup2d_pipe_*): staging sets, copy streams, ordering events
+  struct PipeSet { double *vel = nullptr, *pres = nullptr; cudaEvent_t in_done = nullptr, step_done = nullptr, out_done = nullptr; };
+  PipeSet pipe[CUP2D_PIPE_SLOTS];
+  cudaStream_t pipe_in = nullptr, pipe_out = nullptr;
   int64_t launches = 0;
   // optional per-kernel-class CUDA-event instrumentation (cup2d_profile_*)
   bool prof_on = false;

@@ -188,6 +188,45 @@ class Simulation:
                                      C.byref(dto), C.byref(it), C.byref(err)))
         return dto.value, it.value, err.value
 
+    # ---- host-buffer pipeline (cup2d_pipe_*): independent steps with inputs and results in host memory ----
+    PIPE_SLOTS = 4
+
+    def pipe_upload(self, slot, vel_ptr, pres_ptr):
+        _l.check(self.lib.cup2d_pipe_upload(self._h, slot, vel_ptr, pres_ptr))
+
+    def pipe_step(self, slot, dt=0.0, tol_abs=0.0, tol_rel=0.0, max_restarts=100, max_iter=1000):
+        dto, it, err = C.c_double(), C.c_int(), C.c_double()
+        _l.check(self.lib.cup2d_pipe_step(self._h, slot, dt, tol_abs, tol_rel, max_restarts, max_iter,
+                                          C.byref(dto), C.byref(it), C.byref(err)))
+        return dto.value, it.value, err.value
+
+    def pipe_download(self, slot, vel_ptr, pres_ptr):
+        _l.check(self.lib.cup2d_pipe_download(self._h, slot, vel_ptr, pres_ptr))
+
+    def pipe_wait(self, slot):
+        _l.check(self.lib.cup2d_pipe_wait(self._h, slot))
+
+    def pipelined_steps(self, jobs, **step_args):
+        """Run independent steps whose inputs and results are host buffers, overlapping upload(n+1), step(n) and
+        download(n-1).  `jobs` yields (vel_in_ptr, pres_in_ptr, vel_out_ptr, pres_out_ptr) addresses of page-locked host
+        buffers; returns the per-step (dt, iterations, error).  An output buffer may be reused after PIPE_SLOTS - 1
+        further jobs; all of them are complete when this returns."""
+        jobs = iter(jobs)
+        out, n, nxt = [], 0, next(jobs, None)
+        if nxt is not None:
+            self.pipe_upload(0, nxt[0], nxt[1])
+        while nxt is not None:
+            cur, slot = nxt, n % self.PIPE_SLOTS
+            nxt = next(jobs, None)
+            if nxt is not None:  # the next step's inputs travel while this step computes
+                self.pipe_upload((n + 1) % self.PIPE_SLOTS, nxt[0], nxt[1])
+            out.append(self.pipe_step(slot, **step_args))
+            self.pipe_download(slot, cur[2], cur[3])
+            n += 1
+        for slot in range(min(n, self.PIPE_SLOTS)):
+            self.pipe_wait(slot)
+        return out
+
     def sync(self):
         _l.check(self.lib.cup2d_sync(self._h))
 

@@ -138,6 +138,25 @@ int cup2d_udef_assemble(cup2d_sim *s);
 int cup2d_step(cup2d_sim *s, double dt_in, int keep_udef, double tol_abs, double tol_rel,
                int max_restarts, int max_iter, double *dt_out, int *iters_out, double *err_out);
 
+/* ---- host-buffer pipeline (single rank): independent steps whose inputs and results live in HOST memory ----
+ * What the reference does around every solve is upload, compute, download, one after the other (cuda.cu:298-301,
+ * 546-547).  Here the three legs of successive, independent steps overlap: a context owns CUP2D_PIPE_SLOTS staging sets
+ * (vel + pres) and two copy streams, so that   upload(n+1) || step(n) || download(n-1)   run concurrently (PCIe is full
+ * duplex; the copies take < 1 % of the HBM bandwidth the step uses).  Per slot the order is
+ * upload -> step -> download [-> wait]; the calls only enqueue (cup2d_pipe_step blocks like cup2d_step does), the library
+ * orders them with events, including reuse of a slot.  Host buffers must be page-locked for the copies to be asynchronous.
+ * Results are bit-identical to cup2d_field_upload + cup2d_step + cup2d_field_download. */
+#define CUP2D_PIPE_SLOTS 4
+/* enqueue host -> staging set `slot` (vel: 128 doubles per block, pres: 64, block layout as cup2d_field_upload) */
+int cup2d_pipe_upload(cup2d_sim *s, int slot, const double *vel_host, const double *pres_host);
+/* cup2d_step on the contents of staging set `slot` (arguments as cup2d_step); the set then holds the step's vel and pres */
+int cup2d_pipe_step(cup2d_sim *s, int slot, double dt_in, double tol_abs, double tol_rel, int max_restarts, int max_iter,
+                    double *dt_out, int *iters_out, double *err_out);
+/* enqueue staging set `slot` -> host */
+int cup2d_pipe_download(cup2d_sim *s, int slot, double *vel_host, double *pres_host);
+/* block until the last download of `slot` has landed in host memory */
+int cup2d_pipe_wait(cup2d_sim *s, int slot);
+
 /* ---- multi-GPU (one process per GPU; peers on the same NVSwitch node) ---- */
 /* Size in bytes of the opaque per-rank handle blob exchanged by the launcher (torch.distributed). */
 int cup2d_peer_blob_size(void);

@@ -586,3 +586,38 @@ def test_shape_calls_reject_bad_arguments():
     sim.shape_set(0, [], np.zeros((0, 8, 8)), np.zeros((0, 8, 8, 2)))
     assert not sim.shape_integrals(0, 1e7, 1e-3, 0.5, 0.5).any()
     sim.close()
+
+
+def test_host_pipeline_matches_blocking_calls():
+    """cup2d_pipe_*: independent steps with host inputs and results, upload(n+1) || step(n) || download(n-1) on three
+    streams with buffer trading — bit-identical to cup2d_field_upload + cup2d_step + cup2d_field_download, for more jobs
+    than staging sets (slot reuse), with the context's own fields left alone in between."""
+    import torch
+    L, jobs = 3, 6
+    sim = cup2d_b200.Simulation(L, nu=1e-3, cfl=0.4)
+    n = sim.nloc
+    rng = np.random.default_rng(5)
+    pin = (lambda a: a.pin_memory()) if torch.cuda.is_available() else (lambda a: a)
+    vin = [pin(torch.from_numpy(rng.uniform(-1, 1, n * 128))) for _ in range(jobs)]
+    pin_ = [pin(torch.from_numpy(rng.uniform(-1, 1, n * 64))) for _ in range(jobs)]
+    vout = [pin(torch.empty(n * 128, dtype=torch.float64)) for _ in range(jobs)]
+    pout = [pin(torch.empty(n * 64, dtype=torch.float64)) for _ in range(jobs)]
+    # blocking reference, job by job
+    want = []
+    for j in range(jobs):
+        sim.upload_blocks("vel", vin[j].numpy())
+        sim.upload_blocks("pres", pin_[j].numpy())
+        info = sim.step(max_iter=3, max_restarts=0)
+        want.append((sim.download_blocks("vel").copy(), sim.download_blocks("pres").copy(), info))
+    # the context's own fields must survive a pipelined batch untouched
+    sim.upload_blocks("vel", vin[0].numpy())
+    sim.upload_blocks("pres", pin_[0].numpy())
+    got = sim.pipelined_steps(((vin[j].data_ptr(), pin_[j].data_ptr(), vout[j].data_ptr(), pout[j].data_ptr()) for j in range(jobs)),
+                              max_iter=3, max_restarts=0)
+    for j in range(jobs):
+        assert np.array_equal(vout[j].numpy(), want[j][0]) and np.array_equal(pout[j].numpy(), want[j][1]), j
+        assert got[j] == want[j][2]
+    assert np.array_equal(sim.download_blocks("vel"), vin[0].numpy()) and np.array_equal(sim.download_blocks("pres"), pin_[0].numpy())
+    # slot misuse is refused, not silently accepted
+    with pytest.raises(Exception):
+        sim.pipe_upload(sim.PIPE_SLOTS, vin[0].data_ptr(), pin_[0].data_ptr())
