@@ -621,3 +621,29 @@ def test_host_pipeline_matches_blocking_calls():
     # slot misuse is refused, not silently accepted
     with pytest.raises(Exception):
         sim.pipe_upload(sim.PIPE_SLOTS, vin[0].data_ptr(), pin_[0].data_ptr())
+
+
+@pytest.mark.parametrize("case", ["all_zero", "constant_pressure", "uniform_flow", "tiny_values"])
+def test_degenerate_inputs_vs_oracle(case):
+    """inputs on which the Krylov recurrences divide by (almost) nothing — zero right-hand side, zero residual after the
+    first half-step — and the dt rule has umax = 0: the eps = 1e-21 guards of the reference (cuda.cu:315-326) and its
+    1e-8 in the CFL rule (main.cpp:6594) must give the same finite results, no NaN"""
+    L = 2
+    N = 8 << L
+    z = np.zeros((N, N))
+    rng = np.random.default_rng(9)
+    u, v, p = {"all_zero": (z, z, z), "constant_pressure": (z, z, z + 3.0), "uniform_flow": (z + 0.7, z, z),
+               "tiny_values": (1e-150 * rng.uniform(-1, 1, (N, N)), 1e-150 * rng.uniform(-1, 1, (N, N)), z)}[case]
+    sim = cup2d_b200.Simulation(L, nu=1e-3, cfl=0.5)
+    sim.upload("vel", u, v)
+    sim.upload("pres", p)
+    dt, it, err = sim.step(max_iter=6, max_restarts=0)
+    ref = orc.step(u, v, p, 1e-3, 0.5, kiter=6)
+    gu, gv = sim.download("vel")
+    gp = sim.download("pres")
+    assert np.isfinite(gu).all() and np.isfinite(gv).all() and np.isfinite(gp).all() and np.isfinite(err)
+    assert abs(dt - ref["dt"]) <= 1e-16 * ref["dt"]
+    scale = max(np.abs(ref["u"]).max(), np.abs(ref["v"]).max(), 1e-300)
+    assert np.abs(gu - ref["u"]).max() <= 1e-9 * scale and np.abs(gv - ref["v"]).max() <= 1e-9 * scale
+    assert np.abs(gp - ref["p"]).max() <= 1e-8 * max(np.abs(ref["p"]).max(), 1e-300)
+    sim.close()
