@@ -160,6 +160,25 @@ class AmrSimulation:
                                          C.byref(err)))
         return dto.value, it.value, err.value
 
+    # ---- bodies (cup2d_amr_shape_*): the calls of Simulation.shape_* on the multi-level context ----
+    def shape_set(self, shape, ids, X, udef):
+        ids = np.ascontiguousarray(ids, dtype=np.int32)
+        X = np.ascontiguousarray(X, dtype=np.float64)
+        udef = np.ascontiguousarray(udef, dtype=np.float64)
+        assert X.size == 64 * len(ids) and udef.size == 128 * len(ids)
+        _l.check(self.lib.cup2d_amr_shape_set(self._h, shape, len(ids), ids.ctypes.data, X.ctypes.data, udef.ctypes.data))
+
+    def shape_integrals(self, shape, lam, dt, cx, cy):
+        out = np.empty(7)
+        _l.check(self.lib.cup2d_amr_shape_integrals(self._h, shape, lam, dt, cx, cy, out.ctypes.data_as(C.POINTER(C.c_double))))
+        return out
+
+    def penalize(self, shape, lam, dt, cx, cy, us, vs, omega):
+        _l.check(self.lib.cup2d_amr_penalize(self._h, shape, lam, dt, cx, cy, us, vs, omega))
+
+    def udef_assemble(self):
+        _l.check(self.lib.cup2d_amr_udef_assemble(self._h))
+
     def close(self):
         if self._h:
             self.lib.cup2d_amr_destroy(self._h)

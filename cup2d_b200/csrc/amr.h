@@ -67,5 +67,21 @@ struct cup2d_amr {
   int64_t nirr = 0;
   cup2d::GhostDev gt[3];            // compact ghost tables per stencil kind (cup2d_amr_plan_ghosts)
   double *d_faceflux = nullptr;     // [nirr][4 faces][8][2] face fluxes of the irregular blocks
+  // bodies (csrc/amr_penalize.cu): per-shape obstacle blocks, as cup2d_sim::Shape
+  struct Shape { int nob = 0, cap = 0; int *d_ids = nullptr; double *d_X = nullptr, *d_udef = nullptr; };
+  std::vector<Shape> shapes;
+  std::vector<int32_t> h_ij;        // [nb][2] block index (i, j) at the block's own level (filled by cup2d_amr_create)
+  int *d_ij = nullptr;              // the same on the device (first use)
+  double *d_shape_part = nullptr;   // [cap][7] per-obstacle-block partial sums
+  int shape_part_cap = 0;
+  std::vector<double> h_shape_part;
+  void free_shapes() {
+    for (auto &sh : shapes) {
+      cudaFree(sh.d_ids); cudaFree(sh.d_X); cudaFree(sh.d_udef);
+    }
+    shapes.clear();
+    cudaFree(d_ij); cudaFree(d_shape_part);
+    d_ij = nullptr, d_shape_part = nullptr, shape_part_cap = 0;
+  }
 };
 

@@ -320,6 +320,8 @@ int cup2d_amr_create(int64_t nblocks, const int32_t *level_ij, int32_t bpdx, int
   }
   std::vector<double> h(nblocks);
   for (int64_t k = 0; k < nblocks; k++) h[k] = h0 / (double)(1 << level_ij[3 * k]);
+  a->h_ij.resize(2 * nblocks);
+  for (int64_t k = 0; k < nblocks; k++) a->h_ij[2 * k] = level_ij[3 * k + 1], a->h_ij[2 * k + 1] = level_ij[3 * k + 2];
   a->hmin = *std::min_element(h.begin(), h.end());
   a->h_part.resize(2 * nblocks);
   if (cudaMalloc(&a->d_part, 2 * nblocks * sizeof(double)) != cudaSuccess) return fail(CUP2D_ECUDA);
@@ -363,6 +365,7 @@ void cup2d_amr_destroy(cup2d_amr *a) {
   for (auto p : a->lab) cudaFree(p);
   cudaFree(a->lab_udef); cudaFree(a->d_h); cudaFree(a->d_cf[0]); cudaFree(a->d_cf[1]); cudaFree(a->d_part);
   cudaFree(a->d_nbr4); cudaFree(a->d_irr_of); cudaFree(a->d_faceflux);
+  a->free_shapes();
   for (auto &g : a->gt) {
     cudaFree(g.grow); cudaFree(g.rowptr); cudaFree(g.dst); cudaFree(g.sb); cudaFree(g.sc); cudaFree(g.w);
   }

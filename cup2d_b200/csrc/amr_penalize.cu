@@ -1,0 +1,213 @@
+// Penalisation phase on a multi-level mesh (SURVEY §8(f) rank 3 on the meshes of rank 2; main.cpp:6643-6681, 6944-7002):
+// the calls of penalize.cu on the cup2d_amr context.  Same contract — a shape is the reference's per-shape list of obstacle
+// blocks with their own chi and u_def (main.cpp:3283-3286), uploaded every step; the velocity never leaves the device —
+// with the cell size and the block position taken per block (Info::h, Info::origin: main.cpp:695-696).
+//   cup2d_amr_shape_integrals : {PM,PJ,PX,PY,UM,VM,AM} of main.cpp:6648-6679: one CTA per obstacle block reduces its 64 cells,
+//                               the host adds the per-block results in block order (deterministic; the reference's OpenMP
+//                               reduction has no fixed order: agreement to rounding, not bitwise)
+//   cup2d_amr_penalize        : the blend of main.cpp:6944-6979, explicit round-to-nearest operations: bit-identical
+//   cup2d_amr_udef_assemble   : tmpV = sum of u_def where the shape's chi is not below the field's (6980-7002): bit-identical
+// STATUS: like the rest of the multi-level device path, written after the round's GPU budget was spent — compiled for
+// sm_100a, run under the host emulation only.
+#include "sim.h"
+#include "amr.h"
+#include <algorithm>
+
+#define CUP2D_REQUIRE(cond, msg)                                                                  \
+  do {                                                                                            \
+    if (!(cond)) {                                                                                \
+      cup2d::set_error(msg);                                                                      \
+      return CUP2D_EINVAL;                                                                        \
+    }                                                                                             \
+  } while (0)
+
+namespace cup2d {
+
+struct AmrShapeView {
+  const int *ids;
+  const double *X, *udef;
+  int nob;
+};
+
+// cell centre relative to the shape's centre of mass: p = origin + h (i + 0.5) - C, origin = (8 i) h  (main.cpp:695, 6667-6670)
+__device__ __forceinline__ void amr_rel_pos(const int2 b, double h, int ix, int iy, double cx, double cy, double &px,
+                                            double &py) {
+  px = __dsub_rn(__dadd_rn(__dmul_rn((double)(b.x * CUP2D_BS), h), __dmul_rn(h, (double)ix + 0.5)), cx);
+  py = __dsub_rn(__dadd_rn(__dmul_rn((double)(b.y * CUP2D_BS), h), __dmul_rn(h, (double)iy + 0.5)), cy);
+}
+
+// one CTA (64 threads) per obstacle block: part[k][0..6] = the block's share of {PM, PJ, PX, PY, UM, VM, AM}
+__global__ void __launch_bounds__(64)
+amr_shape_sums_kernel(AmrShapeView sh, const double *__restrict__ vel, const int2 *__restrict__ ij,
+                      const double *__restrict__ hb, double lambdt, double cx, double cy, double *__restrict__ part) {
+  __shared__ double s_w1[7];
+  const int k = blockIdx.x, cell = threadIdx.x, ix = cell & 7, iy = cell >> 3;
+  double sums[7] = {0, 0, 0, 0, 0, 0, 0};
+  const double x = sh.X[(size_t)k * 64 + cell];
+  if (x > 0) {
+    const int id = sh.ids[k];
+    const double h = hb[id];
+    const double xl = x >= 0.5 ? lambdt : 0.0;
+    const double F = (h * h) * xl / (1 + xl);
+    double px, py;
+    amr_rel_pos(ij[id], h, ix, iy, cx, cy, px, py);
+    const double2 v = reinterpret_cast<const double2 *>(vel)[(size_t)id * 64 + cell];
+    const double2 ud = reinterpret_cast<const double2 *>(sh.udef)[(size_t)k * 64 + cell];
+    const double du = v.x - ud.x, dv = v.y - ud.y;
+    sums[0] = F;
+    sums[1] = F * (px * px + py * py);
+    sums[2] = F * px;
+    sums[3] = F * py;
+    sums[4] = F * du;
+    sums[5] = F * dv;
+    sums[6] = F * (px * dv - py * du);
+  }
+  warp_sum<7>(sums);
+  if (threadIdx.x == 32)
+    for (int q = 0; q < 7; q++) s_w1[q] = sums[q];
+  __syncthreads();
+  if (threadIdx.x == 0)
+    for (int q = 0; q < 7; q++) part[(size_t)k * 7 + q] = sums[q] + s_w1[q];
+}
+
+__global__ void __launch_bounds__(256)
+amr_penalize_kernel(AmrShapeView sh, double *__restrict__ vel, const double *__restrict__ chi, const int2 *__restrict__ ij,
+                    const double *__restrict__ hb, double inv1lam, double cx, double cy, double us, double vs, double omega) {
+  const int cell = threadIdx.x & 63, ix = cell & 7, iy = cell >> 3;
+  for (int k = blockIdx.x * 4 + (threadIdx.x >> 6); k < sh.nob; k += gridDim.x * 4) {
+    const double x = sh.X[(size_t)k * 64 + cell];
+    const int id = sh.ids[k];
+    if (chi[(size_t)id * 64 + cell] > x || x <= 0) continue;
+    double px, py;
+    amr_rel_pos(ij[id], hb[id], ix, iy, cx, cy, px, py);
+    const double alpha = x > 0.5 ? inv1lam : 1.0, beta = __dsub_rn(1.0, alpha);
+    const double2 ud = reinterpret_cast<const double2 *>(sh.udef)[(size_t)k * 64 + cell];
+    const double US = __dadd_rn(__dsub_rn(us, __dmul_rn(omega, py)), ud.x);
+    const double VS = __dadd_rn(__dadd_rn(vs, __dmul_rn(omega, px)), ud.y);
+    double2 *vp = reinterpret_cast<double2 *>(vel) + (size_t)id * 64 + cell;
+    double2 v = *vp;
+    v.x = __dadd_rn(__dmul_rn(alpha, v.x), __dmul_rn(beta, US));
+    v.y = __dadd_rn(__dmul_rn(alpha, v.y), __dmul_rn(beta, VS));
+    *vp = v;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+amr_udef_add_kernel(AmrShapeView sh, double *__restrict__ tmpv, const double *__restrict__ chi) {
+  const int cell = threadIdx.x & 63;
+  for (int k = blockIdx.x * 4 + (threadIdx.x >> 6); k < sh.nob; k += gridDim.x * 4) {
+    const int id = sh.ids[k];
+    if (sh.X[(size_t)k * 64 + cell] < chi[(size_t)id * 64 + cell]) continue;
+    const double2 ud = reinterpret_cast<const double2 *>(sh.udef)[(size_t)k * 64 + cell];
+    double2 *tp = reinterpret_cast<double2 *>(tmpv) + (size_t)id * 64 + cell;
+    double2 t = *tp;
+    t.x += ud.x;
+    t.y += ud.y;
+    *tp = t;
+  }
+}
+
+static AmrShapeView view_of(const cup2d_amr::Shape &sh) { return AmrShapeView{sh.d_ids, sh.d_X, sh.d_udef, sh.nob}; }
+static int ob_grid(int nob) { return std::max(1, std::min((nob + 3) / 4, 148 * 8)); }
+
+static int ensure_ij(cup2d_amr *a) {
+  if (a->d_ij) return CUP2D_OK;
+  CUP2D_CUDA(cudaMalloc(&a->d_ij, (size_t)a->nb * 2 * sizeof(int)));
+  CUP2D_CUDA(cudaMemcpy(a->d_ij, a->h_ij.data(), (size_t)a->nb * 2 * sizeof(int), cudaMemcpyHostToDevice));
+  return CUP2D_OK;
+}
+
+} // namespace cup2d
+
+using namespace cup2d;
+
+#define CHECK_AMR_SHAPE(a, shape, must_exist)                                                     \
+  CUP2D_REQUIRE((a) != nullptr, "null cup2d_amr handle");                                         \
+  CUP2D_REQUIRE(shape >= 0 && shape < 64, "shape index out of range (0..63)");                    \
+  CUP2D_REQUIRE(!(must_exist) || shape < (int)(a)->shapes.size(), "shape has not been set (cup2d_amr_shape_set)")
+
+extern "C" {
+
+int cup2d_amr_shape_set(cup2d_amr *a, int shape, int nob, const int32_t *block_ids, const double *chi, const double *udef) {
+  CHECK_AMR_SHAPE(a, shape, false);
+  CUP2D_REQUIRE(nob >= 0 && (nob == 0 || (block_ids && chi && udef)), "cup2d_amr_shape_set: bad arguments");
+  for (int k = 0; k < nob; k++)
+    CUP2D_REQUIRE(block_ids[k] >= 0 && block_ids[k] < a->nb, "cup2d_amr_shape_set: block id outside the mesh");
+  CUP2D_CUDA(cudaSetDevice(a->device));
+  if ((int)a->shapes.size() <= shape) a->shapes.resize(shape + 1);
+  cup2d_amr::Shape &sh = a->shapes[shape];
+  if (nob > sh.cap) {
+    cudaFree(sh.d_ids); cudaFree(sh.d_X); cudaFree(sh.d_udef);
+    sh.d_ids = nullptr; sh.d_X = sh.d_udef = nullptr;
+    sh.cap = 0;
+    const int cap = nob + nob / 4 + 16;
+    CUP2D_CUDA(cudaMalloc(&sh.d_ids, (size_t)cap * sizeof(int)));
+    CUP2D_CUDA(cudaMalloc(&sh.d_X, (size_t)cap * 64 * sizeof(double)));
+    CUP2D_CUDA(cudaMalloc(&sh.d_udef, (size_t)cap * 128 * sizeof(double)));
+    sh.cap = cap;
+  }
+  sh.nob = nob;
+  if (nob > 0) {
+    CUP2D_CUDA(cudaMemcpyAsync(sh.d_ids, block_ids, (size_t)nob * sizeof(int), cudaMemcpyHostToDevice, a->stream));
+    CUP2D_CUDA(cudaMemcpyAsync(sh.d_X, chi, (size_t)nob * 64 * sizeof(double), cudaMemcpyHostToDevice, a->stream));
+    CUP2D_CUDA(cudaMemcpyAsync(sh.d_udef, udef, (size_t)nob * 128 * sizeof(double), cudaMemcpyHostToDevice, a->stream));
+    CUP2D_CUDA(cudaStreamSynchronize(a->stream)); // the caller's arrays may be pageable and short-lived
+  }
+  return CUP2D_OK;
+}
+
+int cup2d_amr_shape_integrals(cup2d_amr *a, int shape, double lambda, double dt, double cx, double cy, double *out7) {
+  CHECK_AMR_SHAPE(a, shape, true);
+  CUP2D_REQUIRE(out7, "cup2d_amr_shape_integrals: null output");
+  CUP2D_CUDA(cudaSetDevice(a->device));
+  int rc = ensure_ij(a);
+  if (rc) return rc;
+  for (int q = 0; q < 7; q++) out7[q] = 0.0;
+  const AmrShapeView v = view_of(a->shapes[shape]);
+  if (v.nob == 0) return CUP2D_OK;
+  if (v.nob > a->shape_part_cap) {
+    cudaFree(a->d_shape_part);
+    a->d_shape_part = nullptr, a->shape_part_cap = 0;
+    CUP2D_CUDA(cudaMalloc(&a->d_shape_part, (size_t)(v.nob + 64) * 7 * sizeof(double)));
+    a->shape_part_cap = v.nob + 64;
+  }
+  amr_shape_sums_kernel<<<v.nob, 64, 0, a->stream>>>(v, a->f[CUP2D_VEL], reinterpret_cast<const int2 *>(a->d_ij), a->d_h,
+                                                     lambda * dt, cx, cy, a->d_shape_part);
+  CUP2D_CUDA(cudaGetLastError());
+  a->h_shape_part.resize((size_t)v.nob * 7);
+  CUP2D_CUDA(cudaMemcpyAsync(a->h_shape_part.data(), a->d_shape_part, (size_t)v.nob * 7 * sizeof(double), cudaMemcpyDeviceToHost,
+                             a->stream));
+  CUP2D_CUDA(cudaStreamSynchronize(a->stream));
+  for (int k = 0; k < v.nob; k++)
+    for (int q = 0; q < 7; q++) out7[q] += a->h_shape_part[(size_t)k * 7 + q];
+  return CUP2D_OK;
+}
+
+int cup2d_amr_penalize(cup2d_amr *a, int shape, double lambda, double dt, double cx, double cy, double us, double vs,
+                       double omega) {
+  CHECK_AMR_SHAPE(a, shape, true);
+  CUP2D_CUDA(cudaSetDevice(a->device));
+  int rc = ensure_ij(a);
+  if (rc) return rc;
+  const AmrShapeView v = view_of(a->shapes[shape]);
+  if (v.nob == 0) return CUP2D_OK;
+  amr_penalize_kernel<<<ob_grid(v.nob), 256, 0, a->stream>>>(v, a->f[CUP2D_VEL], a->f[CUP2D_CHI],
+                                                             reinterpret_cast<const int2 *>(a->d_ij), a->d_h,
+                                                             1 / (1 + lambda * dt), cx, cy, us, vs, omega);
+  CUP2D_CUDA(cudaGetLastError());
+  return CUP2D_OK;
+}
+
+int cup2d_amr_udef_assemble(cup2d_amr *a) {
+  CUP2D_REQUIRE(a != nullptr, "null cup2d_amr handle");
+  CUP2D_CUDA(cudaSetDevice(a->device));
+  CUP2D_CUDA(cudaMemsetAsync(a->f[CUP2D_TMPV], 0, (size_t)a->nb * 128 * sizeof(double), a->stream));
+  for (const auto &sh : a->shapes) {
+    if (sh.nob == 0) continue;
+    amr_udef_add_kernel<<<ob_grid(sh.nob), 256, 0, a->stream>>>(view_of(sh), a->f[CUP2D_TMPV], a->f[CUP2D_CHI]);
+  }
+  CUP2D_CUDA(cudaGetLastError());
+  return CUP2D_OK;
+}
+
+} // extern "C"

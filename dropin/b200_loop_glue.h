@@ -114,6 +114,19 @@ template <class GridT> void amr_download(int field, GridT *grid, int dim) {
   check(cup2d_amr_field_download(amr, field, stage.data()), "cup2d_amr_field_download");
   for (size_t i = 0; i < infos.size(); i++) memcpy(infos[i].block, stage.data() + i * n, n * sizeof(double));
 }
+template <class ShapeT> void amr_shape_set(int k, const ShapeT &shape) {
+  std::vector<int32_t> ids;
+  std::vector<double> X, U;
+  const auto &ob = shape->obstacleBlocks;
+  for (size_t i = 0; i < ob.size(); i++) {
+    if (!ob[i]) continue;
+    ids.push_back((int32_t)i);
+    const double *c = (const double *)ob[i]->chi, *u = (const double *)ob[i]->udef;
+    X.insert(X.end(), c, c + CUP2D_BS * CUP2D_BS);
+    U.insert(U.end(), u, u + 2 * CUP2D_BS * CUP2D_BS);
+  }
+  check(cup2d_amr_shape_set(amr, k, (int)ids.size(), ids.data(), X.data(), U.data()), "cup2d_amr_shape_set");
+}
 inline int max_iter() { // cuda.cu:438 hard-codes 1000; the test harness may lower it
   const char *e = getenv("CUP2D_B200_MAX_ITER");
   return e ? atoi(e) : 1000;

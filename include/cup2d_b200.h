@@ -281,6 +281,16 @@ int cup2d_amr_pressure_correct(cup2d_amr *a, double dt);
 int cup2d_amr_step(cup2d_amr *a, double cfl, double dt_in, double tol_abs, double tol_rel, int max_restarts, int max_iter,
                    double *dt_out, int *iters, double *err);
 
+/* Bodies on a multi-level mesh: the cup2d_shape_* calls (above) on the cup2d_amr context, with the cell size and the block
+ * position taken per block (Info::h, Info::origin, main.cpp:695-696).  block_ids index the context's blocks; a shape's
+ * arrays are copied before the call returns.  Sums to rounding (per-block partial sums added in block order), blend and
+ * assembly bit-identical to the reference.  Same status as the rest of the multi-level device path. */
+int cup2d_amr_shape_set(cup2d_amr *a, int shape, int nob, const int32_t *block_ids, const double *chi, const double *udef);
+int cup2d_amr_shape_integrals(cup2d_amr *a, int shape, double lambda, double dt, double cx, double cy, double *out7);
+int cup2d_amr_penalize(cup2d_amr *a, int shape, double lambda, double dt, double cx, double cy, double us, double vs,
+                       double omega);
+int cup2d_amr_udef_assemble(cup2d_amr *a);
+
 #ifdef __cplusplus
 }
 #endif

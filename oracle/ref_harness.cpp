@@ -61,7 +61,9 @@
 //        prints one JSON line with per-operator CPU times (seconds, median of reps)
 #define CUP2D_REF_HOOK_TU 1
 #define main ref_main
-#if defined(CUP2D_PATCHED_MAIN) && CUP2D_PATCHED_MAIN == 3
+#if defined(CUP2D_PATCHED_MAIN) && CUP2D_PATCHED_MAIN == 4
+#include "main_amrresident.cpp" // oracle/_ref/: multi-level and device-resident with bodies (oracle/Makefile, ref_amrresident)
+#elif defined(CUP2D_PATCHED_MAIN) && CUP2D_PATCHED_MAIN == 3
 #include "main_amrloop.cpp" // oracle/_ref/: the multi-level form (oracle/Makefile, ref_amrloop)
 #elif defined(CUP2D_PATCHED_MAIN) && CUP2D_PATCHED_MAIN == 2
 #include "main_resident.cpp" // oracle/_ref/: the device-resident form with bodies (oracle/Makefile, ref_resident)

@@ -19,7 +19,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 
 SUBSET = ("(operators_vs_reference_golden or vorticity_tagging or adapt_tags or dump_files or penalisation_phase or shape_calls "
-          "or steps_L2_random_k8 or rectangular_domain or host_pipeline or degenerate or amr_fast or amr_advect_diffuse or amr_pressure_gradient) "
+          "or steps_L2_random_k8 or rectangular_domain or host_pipeline or degenerate or amr_bodies or amr_fast or amr_advect_diffuse or amr_pressure_gradient) "
           "and not reference_driver")
 
 
@@ -230,26 +230,30 @@ def _parse_asteps(path):
     return out
 
 
-def test_reference_amr_case_on_the_multi_level_path_emulated(emulated_library, tmp_path):
+@pytest.mark.parametrize("form,steps", [("amrloop", 2), ("amrresident", 3)])
+def test_reference_amr_case_on_the_multi_level_path_emulated(emulated_library, tmp_path, form, steps):
     """config C1 end to end: the reference's own run.sh case (two fish, 7 refinement levels, 278 blocks, its own adapt() /
-    ongrid() / penalisation on the host) with RK2 and the whole pressure section on the multi-level path of the library
-    (dropin/amr_loop_*.inc on cup2d_amr: fast kernels, Poisson rows from the library's own plan), linked against the emulated
-    library, against the unmodified reference: same mesh and fields to rounding at every step.  (By hand: 13 steps across a
-    regrid 278 -> 281 blocks stay within 3e-15 / 1.3e-14 relative in velocity / pressure.)"""
+    ongrid() on the host) on the multi-level path of the library (fast kernels, Poisson rows from the library's own plan),
+    linked against the emulated library, against the unmodified reference: same mesh and fields to rounding at every step.
+      amrloop      RK2 and the whole pressure section on cup2d_amr, penalisation on the host (dropin/amr_loop_*.inc)
+      amrresident  additionally the penalisation sums, the blend and the u_def assembly on the device
+                   (cup2d_amr_shape_*, dropin/amr_resident_*.inc): the velocity crosses PCIe once each way per step
+    (By hand, both forms: 13 steps across a regrid 278 -> 281 blocks stay within 3e-15 / 1.3e-14 relative in velocity /
+    pressure.)"""
     import numpy as np
     if not os.path.exists("/root/reference/main.cpp"):
         pytest.skip("needs the reference sources to build the patched driver (build container only)")
     emu_dir = os.path.dirname(emulated_library)
-    subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), "ref", "ref_amrloop", f"LIBDIR={emu_dir}", "LIBNAME=cup2d_emu",
-                    "AMRLOOP=ref_harness_amrloop_emu", f"RPATH={emu_dir}"], check=True, stdout=subprocess.DEVNULL)
+    subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), "ref", f"ref_{form}", f"LIBDIR={emu_dir}", "LIBNAME=cup2d_emu",
+                    f"{form.upper()}=ref_harness_{form}_emu", f"RPATH={emu_dir}"], check=True, stdout=subprocess.DEVNULL)
     env = dict(os.environ, OMP_NUM_THREADS="1", CUP2D_B200_MAX_ITER="5", CUP2D_B200_AMR_FAST="1")
     runs = []
-    for exe in ("ref_harness", "ref_harness_amrloop_emu"):
+    for exe in ("ref_harness", f"ref_harness_{form}_emu"):
         out = tmp_path / (exe + ".bin")
-        subprocess.run([os.path.join(ROOT, "oracle", "_ref", exe), "asteps", "8", "3", "5", str(out)], check=True,
+        subprocess.run([os.path.join(ROOT, "oracle", "_ref", exe), "asteps", "8", str(steps), "5", str(out)], check=True,
                        stderr=subprocess.DEVNULL, stdout=subprocess.DEVNULL, env=env, timeout=1500)
         runs.append(_parse_asteps(out))
-    assert len(runs[0]) == len(runs[1]) == 3
+    assert len(runs[0]) == len(runs[1]) == steps
     for (dt0, m0, v0, p0), (dt1, m1, v1, p1) in zip(*runs):
         assert m0.shape == m1.shape and (m0 == m1).all() and len(set(m0[:, 0].tolist())) >= 5
         assert abs(dt0 - dt1) < 1e-15

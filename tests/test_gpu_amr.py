@@ -143,12 +143,80 @@ def test_amr_full_step_against_composed_oracle(case, fast):
     assert rel(sim.download("vel"), vel) < 1e-9 and rel(sim.download("pres"), pres) < 1e-9
 
 
-def test_reference_amr_case_on_the_multi_level_device_path(tmp_path):
+def test_amr_bodies_sums_blend_and_udef_assembly(case):
+    """cup2d_amr_shape_*: two synthetic shapes whose obstacle blocks span several refinement levels (the field chi is the
+    golden's own).  Against a block-wise numpy restatement of main.cpp:6648-6679, 6944-6979, 6980-7002 with the per-block
+    cell size and origin (main.cpp:695-696): sums to rounding, blend and assembly bit for bit."""
+    d, sim = case
+    blocks = np.asarray(d["blocks"])
+    nb, h0 = len(blocks), float(d["h0"])
+    rng = np.random.default_rng(11)
+    h = h0 / (1 << blocks[:, 0]).astype(np.float64)
+    levels = sorted(set(blocks[:, 0].tolist()))
+    vel = np.asarray(d["vel"]).reshape(nb, 8, 8, 2)
+    chi = np.asarray(d["chi"]).reshape(nb, 8, 8)
+    lam, dt = 1e7, float(d["dt"])
+    shapes = []
+    for k in range(2):  # obstacle blocks: some of every level, in increasing block order like obstacleBlocks
+        ids = np.sort(np.concatenate([rng.choice(np.flatnonzero(blocks[:, 0] == lv), size=min(3, (blocks[:, 0] == lv).sum()), replace=False)
+                                      for lv in levels])).astype(np.int32)
+        X = rng.uniform(-0.3, 1.0, (len(ids), 8, 8))
+        X[rng.uniform(size=X.shape) < 0.2] = 0.5     # the >= 0.5 / > 0.5 boundary of the two rules
+        X[0] = chi[ids[0]]                            # ties with the chi field
+        shapes.append(dict(ids=ids, X=X, udef=rng.uniform(-1, 1, (len(ids), 8, 8, 2)), cx=0.9 + 0.3 * k, cy=0.5,
+                           u=0.1 * (k + 1), v=-0.2, omega=0.7 - k))
+    sim.upload("vel", vel)
+    sim.upload("chi", chi)
+    ix = np.arange(8, dtype=np.float64)
+
+    def centres(ids, cx, cy):
+        hb = h[ids][:, None, None]
+        px = (blocks[ids, 1] * 8).astype(np.float64)[:, None, None] * hb + hb * (ix[None, None, :] + 0.5) - cx
+        py = (blocks[ids, 2] * 8).astype(np.float64)[:, None, None] * hb + hb * (ix[None, :, None] + 0.5) - cy
+        return px + 0 * py, py + 0 * px
+    want_v = vel.copy()
+    for k, sh in enumerate(shapes):
+        sim.shape_set(k, sh["ids"], sh["X"], sh["udef"])
+        ids, X, ud = sh["ids"], sh["X"], sh["udef"]
+        px, py = centres(ids, sh["cx"], sh["cy"])
+        Xl = np.where(X >= 0.5, lam * dt, 0.0)
+        F = np.where(X > 0, (h[ids] * h[ids])[:, None, None] * Xl / (1 + Xl), 0.0)
+        du, dv = want_v[ids][..., 0] - ud[..., 0], want_v[ids][..., 1] - ud[..., 1]
+        want = np.array([t.sum() for t in (F, F * (px * px + py * py), F * px, F * py, F * du, F * dv, F * (px * dv - py * du))])
+        got = sim.shape_integrals(k, lam, dt, sh["cx"], sh["cy"])
+        assert np.abs(got - want).max() <= 1e-12 * np.abs(want).max(), (k, got, want)
+    for k, sh in enumerate(shapes):  # the blend, shape after shape on the same field (a later shape sees the earlier one's result)
+        sim.penalize(k, lam, dt, sh["cx"], sh["cy"], sh["u"], sh["v"], sh["omega"])
+        ids, X, ud = sh["ids"], sh["X"], sh["udef"]
+        px, py = centres(ids, sh["cx"], sh["cy"])
+        alpha = np.where(X > 0.5, 1 / (1 + lam * dt), 1.0)
+        US, VS = sh["u"] - sh["omega"] * py + ud[..., 0], sh["v"] + sh["omega"] * px + ud[..., 1]
+        on = ~(chi[ids] > X) & ~(X <= 0)
+        V = want_v[ids]
+        V[..., 0] = np.where(on, alpha * V[..., 0] + (1 - alpha) * US, V[..., 0])
+        V[..., 1] = np.where(on, alpha * V[..., 1] + (1 - alpha) * VS, V[..., 1])
+        want_v[ids] = V
+    assert np.array_equal(sim.download("vel").reshape(nb, 8, 8, 2), want_v)
+    sim.udef_assemble()
+    want_t = np.zeros((nb, 8, 8, 2))
+    for sh in shapes:
+        on = ~(sh["X"] < chi[sh["ids"]])
+        np.add.at(want_t, sh["ids"], np.where(on[..., None], sh["udef"], 0.0))
+    assert np.array_equal(sim.download("tmpV").reshape(nb, 8, 8, 2), want_t)
+    with pytest.raises(Exception):
+        sim.shape_set(0, [nb], np.zeros((1, 8, 8)), np.zeros((1, 8, 8, 2)))   # block id outside the mesh
+    with pytest.raises(Exception):
+        sim.shape_integrals(5, lam, dt, 0.0, 0.0)                                # shape never set
+
+
+@pytest.mark.parametrize("form", ["amrloop", "amrresident"])
+def test_reference_amr_case_on_the_multi_level_device_path(tmp_path, form):
     """config C1 on the device: the reference's own run.sh case with RK2 and the pressure section on cup2d_amr (fast kernels)
-    — oracle/_ref/ref_harness_amrloop — against the unmodified reference loop (oracle/_ref/ref_harness), 6 steps"""
+    — oracle/_ref/ref_harness_amrloop; with the penalisation sums, blend and u_def assembly there too: ..._amrresident —
+    against the unmodified reference loop (oracle/_ref/ref_harness), 6 steps"""
     import subprocess
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    exes = [os.path.join(root, "oracle", "_ref", n) for n in ("ref_harness", "ref_harness_amrloop")]
+    exes = [os.path.join(root, "oracle", "_ref", n) for n in ("ref_harness", f"ref_harness_{form}")]
     if not all(os.path.exists(e) for e in exes):
         pytest.skip("oracle/_ref binaries not built")
     env = dict(os.environ, OMP_NUM_THREADS="1", CUP2D_B200_MAX_ITER="8", CUP2D_B200_AMR_FAST="1")
