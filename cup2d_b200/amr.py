@@ -6,7 +6,7 @@ import numpy as np
 
 from . import lib as _l
 
-LAB_SHAPES = {0: (14, 14, 2), 1: (10, 10, 2), 2: (10, 10, 1)}
+LAB_SHAPES = {0: (14, 14, 2), 1: (10, 10, 2), 2: (10, 10, 1), 3: (16, 16, 1)}  # kind 3: chi lab of GradChiOnTmp
 
 
 class AmrPlan:
@@ -159,6 +159,12 @@ class AmrSimulation:
         _l.check(self.lib.cup2d_amr_step(self._h, cfl, dt, tol_abs, tol_rel, max_restarts, max_iter, C.byref(dto), C.byref(it),
                                          C.byref(err)))
         return dto.value, it.value, err.value
+
+    def adapt_tags(self, rtol, level_max):
+        """per-block L-inf of adapt()'s tagging field (vorticity + the chi rule); the field itself is left in tmp"""
+        out = np.empty(len(self.blocks))
+        _l.check(self.lib.cup2d_amr_adapt_tags(self._h, float(rtol), int(level_max), out.ctypes.data_as(C.POINTER(C.c_double))))
+        return out
 
     # ---- bodies (cup2d_amr_shape_*): the calls of Simulation.shape_* on the multi-level context ----
     def shape_set(self, shape, ids, X, udef):

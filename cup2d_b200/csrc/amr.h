@@ -51,8 +51,8 @@ struct cup2d_amr {
   cudaStream_t stream = nullptr;
   double *f[CUP2D_NFIELDS] = {};
   double *d_h = nullptr;            // cell size per block
-  cup2d::Csr csr[3];
-  double *lab[3] = {};              // lab buffers (kinds 0, 1, 2); a second kind-1 buffer for u_def
+  cup2d::Csr csr[4];                // kinds 0-2 at creation, 3 (chi lab of the tagging rule) on first use
+  double *lab[4] = {};              // lab buffers per kind; a second kind-1 buffer for u_def
   double *lab_udef = nullptr;
   cup2d::CoarseFace *d_cf[2] = {};  // [0] x faces, [1] y faces
   int ncf[2] = {0, 0};

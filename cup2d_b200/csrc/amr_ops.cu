@@ -24,7 +24,7 @@
 
 namespace cup2d {
 
-constexpr int LABN[3] = {14, 10, 10}, LABD[3] = {2, 2, 1}, LABG[3] = {3, 1, 1};
+constexpr int LABN[4] = {14, 10, 10, 16}, LABD[4] = {2, 2, 1, 1}, LABG[4] = {3, 1, 1, 4}; // kind 3: chi lab of GradChiOnTmp
 
 __global__ void amr_gather_kernel(Csr t, const double *__restrict__ field, double *__restrict__ lab, int dim) {
   for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < t.nrows; r += (int64_t)gridDim.x * blockDim.x) {
@@ -141,6 +141,37 @@ __global__ void amr_block_absmax_kernel(const double *__restrict__ vel, double *
     double m = 0.0;
     for (int j = 0; j < 128; j++) m = fmax(m, fabs(vel[k * 128 + j]));
     out[k] = m;
+  }
+}
+// adapt()'s tagging field (main.cpp:4676-4678).  KernelVorticity (3343-3366): tmp = (0.5/h) ((u_S - u_N) + v_E - v_W)
+__global__ void amr_vorticity_kernel(const double *__restrict__ labv, double *__restrict__ tmp, const double *__restrict__ hb,
+                                     int64_t ncells) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < ncells; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t k = i >> 6;
+    const int ix = (int)(i & 7), iy = (int)((i >> 3) & 7);
+    const double i2h = 0.5 / hb[k];
+    tmp[i] = i2h * (((L1(labv, k, ix, iy - 1, 0) - L1(labv, k, ix, iy + 1, 0)) + L1(labv, k, ix + 1, iy, 1)) - L1(labv, k, ix - 1, iy, 1));
+  }
+}
+// GradChiOnTmp (4631-4656): a block whose chi lab is positive anywhere within `offset` cells of it (4 on the finest level,
+// 2 elsewhere; the clamp to [0,1] of 4645-4646 does not change the sign) gets 2 Rtol in its four centre cells; then the
+// per-block L-inf that adapt() thresholds (4693-4697).  One thread per block.
+__global__ void amr_tag_block_kernel(const double *__restrict__ labchi, double *__restrict__ tmp, const double *__restrict__ hb,
+                                     double h_finest, double rtol, double *__restrict__ linf, int64_t nb) {
+  for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < nb; k += (int64_t)gridDim.x * blockDim.x) {
+    const int offset = hb[k] == h_finest ? 4 : 2;
+    bool fire = false;
+    for (int y = -offset; y < CUP2D_BS + offset && !fire; y++)
+      for (int x = -offset; x < CUP2D_BS + offset; x++)
+        if (labchi[(k * 16 + (y + 4)) * 16 + (x + 4)] > 0.0) {
+          fire = true;
+          break;
+        }
+    double *t = tmp + k * 64;
+    if (fire) t[4 * 8 + 3] = t[3 * 8 + 3] = t[4 * 8 + 4] = t[3 * 8 + 4] = 2 * rtol;
+    double m = 0.0;
+    for (int j = 0; j < 64; j++) m = fmax(m, fabs(t[j]));
+    linf[k] = m;
   }
 }
 // V = Vold + c * tmpV / h^2   (main.cpp:6618-6626, 6634-6642, 7180-7187 with Vold = V)
@@ -442,6 +473,28 @@ static int block_partials(cup2d_amr *a, int n_per_block) {
   CUP2D_CUDA(cudaMemcpyAsync(a->h_part.data(), a->d_part, (size_t)a->nb * n_per_block * sizeof(double), cudaMemcpyDeviceToHost,
                              a->stream));
   CUP2D_CUDA(cudaStreamSynchronize(a->stream));
+  return CUP2D_OK;
+}
+
+/* adapt()'s per-block L-inf (main.cpp:4676-4697) on a multi-level mesh: vorticity of vel through the +-1 lab, the chi rule
+ * of GradChiOnTmp through the {-4,-4,5,5,tensorial} chi lab (ghost tables built on first use); leaves the tagging field in
+ * tmp like the reference does.  level_max = sim.levelMax (the finest level is level_max - 1). */
+int cup2d_amr_adapt_tags(cup2d_amr *a, double rtol, int level_max, double *block_linf_out) {
+  CHECK_AMR(a);
+  if (!block_linf_out || level_max < 1 || level_max > 30) {
+    set_error("cup2d_amr_adapt_tags: bad arguments");
+    return CUP2D_EINVAL;
+  }
+  CUP2D_CUDA(cudaSetDevice(a->device));
+  int rc;
+  if (!a->csr[3].rowptr && (rc = upload_csr(a, 3))) return rc;
+  if ((rc = gather(a, 1, a->f[CUP2D_VEL], a->lab[1])) || (rc = gather(a, 3, a->f[CUP2D_CHI], a->lab[3]))) return rc;
+  amr_vorticity_kernel<<<grid_for(a->nb * 64), 256, 0, a->stream>>>(a->lab[1], a->f[CUP2D_TMP], a->d_h, a->nb * 64);
+  amr_tag_block_kernel<<<grid_for(a->nb), 256, 0, a->stream>>>(a->lab[3], a->f[CUP2D_TMP], a->d_h,
+                                                               a->h0 / (double)(1 << (level_max - 1)), rtol, a->d_part, a->nb);
+  CUP2D_CUDA(cudaGetLastError());
+  if ((rc = block_partials(a, 1))) return rc;
+  memcpy(block_linf_out, a->h_part.data(), (size_t)a->nb * sizeof(double));
   return CUP2D_OK;
 }
 

@@ -117,7 +117,8 @@ struct LabBuilder {
   LabBuilder(const Mesh &ms, int which) : mesh(ms) {
     if (which == 0) { dim = 2; sx = sy = -3; ex = ey = 4; tens = true; vector_bc = true; }
     else if (which == 1) { dim = 2; sx = sy = -1; ex = ey = 2; tens = false; vector_bc = true; }
-    else { dim = 1; sx = sy = -1; ex = ey = 2; tens = false; vector_bc = false; }
+    else if (which == 2) { dim = 1; sx = sy = -1; ex = ey = 2; tens = false; vector_bc = false; }
+    else { dim = 1; sx = sy = -4; ex = ey = 5; tens = true; vector_bc = false; } // GradChiOnTmp's chi lab (main.cpp:4633)
     nmx = BS + ex - sx - 1, nmy = BS + ey - sy - 1;
     ox = cdiv(sx - 1, 2) - 1, oy = cdiv(sy - 1, 2) - 1;
     ncx = H + cdiv(ex, 2) + 1 - ox, ncy = H + cdiv(ey, 2) + 1 - oy;
@@ -401,14 +402,14 @@ struct GhostTable { // compact form: ghost rows of irregular blocks only
 struct cup2d_amr_plan {
   Mesh mesh;
   std::vector<int32_t> irregular; // blocks with a coarser or finer block among their 8 neighbours
-  GhostTable ghosts[3];
+  GhostTable ghosts[4];
   // CSR per stencil kind: rows = (block, iy, ix, comp)
-  std::vector<int64_t> rowptr[3];
-  std::vector<int32_t> src_block[3], src_cc[3]; // source block, source cell*dim + comp
-  std::vector<double> w[3];
+  std::vector<int64_t> rowptr[4];
+  std::vector<int32_t> src_block[4], src_cc[4]; // source block, source cell*dim + comp
+  std::vector<double> w[4];
   // coarse-fine faces: (fine block, fine face, coarse block, coarse face, half)
   std::vector<int32_t> faces;
-  bool built[3] = {false, false, false};
+  bool built[4] = {false, false, false, false};
 };
 
 static void build(cup2d_amr_plan *p, int which) {
@@ -671,7 +672,7 @@ int64_t cup2d_amr_plan_irregular(cup2d_amr_plan *p, int32_t *out) {
 
 int64_t cup2d_amr_plan_ghosts(cup2d_amr_plan *p, int which, int64_t *nrows, int64_t *rowptr, int32_t *dst, int32_t *src_block,
                               int32_t *src_cellcomp, double *weight) {
-  if (!p || which < 0 || which > 2) return CUP2D_EINVAL;
+  if (!p || which < 0 || which > 3) return CUP2D_EINVAL;
   GhostTable &g = p->ghosts[which];
   if (!g.built) build_ghosts(p, which);
   const int64_t nnz = (int64_t)g.w.size();
@@ -686,7 +687,7 @@ int64_t cup2d_amr_plan_ghosts(cup2d_amr_plan *p, int which, int64_t *nrows, int6
 
 int64_t cup2d_amr_plan_stencil(cup2d_amr_plan *p, int which, int64_t *rowptr, int32_t *src_block, int32_t *src_cellcomp,
                                double *weight) {
-  if (!p || which < 0 || which > 2) return CUP2D_EINVAL;
+  if (!p || which < 0 || which > 3) return CUP2D_EINVAL;
   if (!p->built[which]) build(p, which);
   const int64_t nnz = (int64_t)p->w[which].size();
   if (rowptr) memcpy(rowptr, p->rowptr[which].data(), p->rowptr[which].size() * sizeof(int64_t));
@@ -821,7 +822,7 @@ int64_t cup2d_amr_plan_poisson(cup2d_amr_plan *p, int32_t *nbr_out, int64_t *nnz
 
 /* bookkeeping of the last cup2d_amr_plan_ghosts(which): distinct local configurations, directly evaluated blocks */
 int cup2d_amr_plan_stats(cup2d_amr_plan *p, int which, int32_t *npatterns, int32_t *fallbacks) {
-  if (!p || which < 0 || which > 2 || !p->ghosts[which].built) return CUP2D_EINVAL;
+  if (!p || which < 0 || which > 3 || !p->ghosts[which].built) return CUP2D_EINVAL;
   if (npatterns) *npatterns = p->ghosts[which].npatterns;
   if (fallbacks) *fallbacks = p->ghosts[which].fallbacks;
   return CUP2D_OK;

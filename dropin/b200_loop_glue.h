@@ -127,6 +127,10 @@ template <class ShapeT> void amr_shape_set(int k, const ShapeT &shape) {
   }
   check(cup2d_amr_shape_set(amr, k, (int)ids.size(), ids.data(), X.data(), U.data()), "cup2d_amr_shape_set");
 }
+inline bool device_tags() { // adapt()'s tagging field from the device (default) or from the reference's own host sweeps
+  const char *e = getenv("CUP2D_B200_AMR_TAGS");
+  return !e || atoi(e) != 0;
+}
 inline int max_iter() { // cuda.cu:438 hard-codes 1000; the test harness may lower it
   const char *e = getenv("CUP2D_B200_MAX_ITER");
   return e ? atoi(e) : 1000;

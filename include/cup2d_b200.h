@@ -281,6 +281,13 @@ int cup2d_amr_pressure_correct(cup2d_amr *a, double dt);
 int cup2d_amr_step(cup2d_amr *a, double cfl, double dt_in, double tol_abs, double tol_rel, int max_restarts, int max_iter,
                    double *dt_out, int *iters, double *err);
 
+/* adapt()'s tagging on a multi-level mesh (main.cpp:4676-4697; cf. cup2d_adapt_tags): block_linf_out[k] = L-inf over block
+ * k of the field adapt() thresholds against Rtol / Ctol — the vorticity of vel (KernelVorticity, 3343-3366), with 2*rtol in
+ * the four centre cells of every block whose chi lab (stencil {-4,-4,5,5,tensorial}, ghosts across level jumps included) is
+ * positive within 4 cells (finest level, level_max - 1) or 2 cells (other levels) of it (GradChiOnTmp, 4631-4656).  The
+ * field itself is left in tmp.  States, 2:1 balancing and the mesh surgery stay on the host. */
+int cup2d_amr_adapt_tags(cup2d_amr *a, double rtol, int level_max, double *block_linf_out);
+
 /* Bodies on a multi-level mesh: the cup2d_shape_* calls (above) on the cup2d_amr context, with the cell size and the block
  * position taken per block (Info::h, Info::origin, main.cpp:695-696).  block_ids index the context's blocks; a shape's
  * arrays are copied before the call returns.  Sums to rounding (per-block partial sums added in block order), blend and

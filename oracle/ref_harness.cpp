@@ -42,6 +42,11 @@
 //        12: vel blocks (128/block)  13: pres = pold blocks  14: chi blocks  15: udef blocks (128/block)
 //        20: VectorLab of vel, stencil {-3,-3,4,4,tensorial} (14*14*2/block)   21: VectorLab of vel {-1,-1,2,2} (10*10*2)
 //        22: ScalarLab of pres {-1,-1,2,2} (10*10)
+//   ref_harness atags levelMax nsteps out.bin
+//        the run.sh case for nsteps steps, then what adapt() looks at (main.cpp:4676-4678) on the fields as they are:
+//        10: Rtol, Ctol, levelMax, h0, bpdx, bpdy   11: mesh   12: vel blocks   14: chi blocks
+//        23: ScalarLab of chi, stencil {-4,-4,5,5,tensorial} (16*16/block: GradChiOnTmp's lab)
+//        40: tmp after KernelVorticity   41: tmp after GradChiOnTmp (what the per-block L-inf is taken of)
 //        30: tmpV after KernelAdvectDiffuse + flux correction   31: tmp after pressure_rhs (+fc)
 //        32: tmp after pressure_rhs1 (+fc)   33: tmpV after pressureCorrectionKernel (+fc)
 //   ref_harness fsteps L nsteps kiter out.bin
@@ -81,7 +86,7 @@ extern int cup2d_ref_force_iters;
 extern int cup2d_ref_fixed_iters;
 
 namespace {
-enum Mode { ORDER, OPS, STEPS, TIME, AMR, VORT, TAGS, DUMP, PENAL, AMRLAB, FSTEPS, ASTEPS } g_mode;
+enum Mode { ORDER, OPS, STEPS, TIME, AMR, VORT, TAGS, DUMP, PENAL, AMRLAB, FSTEPS, ASTEPS, ATAGS } g_mode;
 int g_sum7 = 0, g_sum2 = 0, g_step = 0;
 int g_extra = 0;
 double g_rtol = 0, g_time = 0;
@@ -417,6 +422,28 @@ static void do_amrlab() {
   fclose(g_fout);
 }
 
+// ---- atags: what adapt() looks at on a real multi-level mesh with real bodies (main.cpp:4676-4678) ---------------------
+static void do_atags() {
+  g_fout = fopen(g_out.c_str(), "wb");
+  put(10, {sim.Rtol, sim.Ctol, (double)sim.levelMax, sim.h0, (double)sim.bpdx, (double)sim.bpdy});
+  std::vector<double> mesh;
+  for (auto &info : var.vel->infos) { mesh.push_back(info.level); mesh.push_back(info.index[0]); mesh.push_back(info.index[1]); }
+  put(11, mesh);
+  put_blocks(12, var.vel, 2);
+  put_blocks(14, var.chi, 1);
+  const size_t nb = var.vel->infos.size();
+  {
+    std::vector<double> lab(nb * 16 * 16);
+    computeA<ScalarLab>(DumpLab<ScalarLab, 1>(Stencil{-4, -4, 5, 5, true}, &lab), var.chi, 1);
+    put(23, lab);
+  }
+  computeA<VectorLab>(KernelVorticity(), var.vel, 2);
+  put_blocks(40, var.tmp, 1);
+  computeA<ScalarLab>(GradChiOnTmp(), var.chi, 1);
+  put_blocks(41, var.tmp, 1);
+  fclose(g_fout);
+}
+
 static void penal_hook(int op, void *buf, int count) {
   const int S = (int)sim.shapes.size();
   if (op == MPI_MAX && count == 1) { // dt of a new step (main.cpp:6592)
@@ -490,10 +517,11 @@ void cup2d_ref_hook(int op, void *buf, int count) {
     if (call == g_nsteps) { fclose(g_fout); exit(0); }
     return;
   }
-  if (g_mode == AMRLAB) {
+  if (g_mode == AMRLAB || g_mode == ATAGS) {
     if (op != MPI_MAX || count != 1) return;
     if (g_calls++ < g_nsteps) return; // let the reference run nsteps steps first
-    do_amrlab();
+    if (g_mode == AMRLAB) do_amrlab();
+    else do_atags();
     exit(0);
   }
   if (op != MPI_MAX || count != 1) return;
@@ -605,8 +633,8 @@ int main(int argc, char **argv) {
                           "-shapes", "angle=0 L=0.2 xpos=1.8 ypos=0.8\n angle=180 L=0.2 xpos=1.6 ypos=0.8"};
     return ref_main(sizeof args / sizeof *args, (char **)args);
   }
-  else if ((mode == "amrlab" && argc == 5) || (mode == "asteps" && argc == 6)) {
-    if (mode == "amrlab") { g_mode = AMRLAB; g_nsteps = atoi(argv[3]); g_out = argv[4]; cup2d_ref_force_iters = 5; }
+  else if (((mode == "amrlab" || mode == "atags") && argc == 5) || (mode == "asteps" && argc == 6)) {
+    if (mode != "asteps") { g_mode = mode == "amrlab" ? AMRLAB : ATAGS; g_nsteps = atoi(argv[3]); g_out = argv[4]; cup2d_ref_force_iters = 5; }
     else { g_mode = ASTEPS; g_nsteps = atoi(argv[3]); g_kiter = atoi(argv[4]); g_out = argv[5]; cup2d_ref_force_iters = g_kiter; }
     char a_lmax[16];
     snprintf(a_lmax, sizeof a_lmax, "%d", g_L);

@@ -263,6 +263,30 @@ def gen_amrlab(tmp, level_max, nsteps):
     print("amrlab", nb, "blocks, levels", sorted(set(blocks[:, 0].tolist())))
 
 
+def gen_amrtags(tmp, level_max, nsteps):
+    """what adapt() looks at (main.cpp:4676-4678) on the reference's own multi-level run.sh mesh with its two fish, after
+    nsteps steps: mesh, vel, chi, the chi lab of GradChiOnTmp ({-4,-4,5,5,tensorial}), the tagging field before and after
+    the chi rule"""
+    fout = os.path.join(tmp, "atags.bin")
+    subprocess.run([HARNESS, "atags", str(level_max), str(nsteps), fout], check=True, stderr=subprocess.DEVNULL,
+                   stdout=subprocess.DEVNULL, env=dict(os.environ, OMP_NUM_THREADS="1"))
+    a = np.fromfile(fout)
+    i, rec = 0, {}
+    while i < len(a):
+        tag, n = int(a[i]), int(a[i + 1])
+        rec[tag] = a[i + 2:i + 2 + n]
+        i += 2 + n
+    rtol, ctol, lmax, h0, bpdx, bpdy = rec[10]
+    blocks = rec[11].reshape(-1, 3).astype(np.int32)
+    nb = len(blocks)
+    np.savez_compressed(
+        os.path.join(HERE, f"amrtags_lmax{level_max}.npz"), rtol=rtol, ctol=ctol, level_max=int(lmax), h0=h0, bpdx=int(bpdx),
+        bpdy=int(bpdy), blocks=blocks, vel=rec[12].reshape(nb, 8, 8, 2), chi=rec[14].reshape(nb, 8, 8, 1),
+        lab_chi4=rec[23].reshape(nb, 16, 16), vort=rec[40].reshape(nb, 8, 8), tagfield=rec[41].reshape(nb, 8, 8))
+    fired = (rec[40] != rec[41]).reshape(nb, 64).any(axis=1)
+    print("amrtags", nb, "blocks; chi rule fired on", int(fired.sum()))
+
+
 def gen_steps(tmp, kind, L, seed, nu, cfl, nsteps, kiter):
     N = 8 << L
     ins = make_inputs(kind, L, seed)
@@ -292,6 +316,7 @@ if __name__ == "__main__":
         gen_dump(tmp, 2, 4246, 0.1875)
         gen_penal(tmp, 4, 4, [2, 3])
         gen_amrlab(tmp, 8, 3)
+        gen_amrtags(tmp, 8, 5)
         gen_ops(tmp, "random", 2, 1234, 1e-3, 2.5e-3)
         gen_ops(tmp, "tg", 3, 4321, 1e-3, 1.2e-3)
         gen_steps(tmp, "tg", 2, 777, 1e-3, 0.5, 3, 12)

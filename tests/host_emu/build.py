@@ -113,6 +113,56 @@ def split_top(s):
     return out
 
 
+SYNC_PAT = re.compile(r"__sync|__shfl|atomic|__shared__|mbar_|tma_load|__threadfence|volatile|asm\b|emu_bulk_copy")
+
+
+def _functions(text, qualifier):
+    """(name, body) of every function defined with `qualifier` in `text` (brace matching; declarations are skipped)"""
+    out = []
+    for m in re.finditer(re.escape(qualifier), text):
+        i, depth = m.end(), 0
+        while i < len(text) and not (text[i] in "{;" and depth == 0):
+            depth += text[i] == "("
+            depth -= text[i] == ")"
+            i += 1
+        if i >= len(text) or text[i] == ";":
+            continue
+        header = re.sub(r"__launch_bounds__\([^)]*\)", "", text[m.end():i])
+        nm = re.search(r"(\w+)\s*\(", header)
+        if not nm:
+            continue
+        j, depth = i, 0
+        while j < len(text):
+            depth += text[j] == "{"
+            depth -= text[j] == "}"
+            j += 1
+            if depth == 0:
+                break
+        out.append((nm.group(1), text[i:j]))
+    return out
+
+
+def serial_safe_kernels(texts):
+    """kernels whose threads never interact (no shared memory, barrier, shuffle, atomic, fence, volatile or PTX — directly or
+    through a device function): they can be emulated one thread after the other, which is far cheaper than one OS thread
+    per CUDA thread.  Everything else keeps real concurrent threads."""
+    text = "\n".join(re.sub(r"//.*", "", t) for t in texts)
+    dev = dict(_functions(text, "__device__"))
+    syncing = {n for n, b in dev.items() if SYNC_PAT.search(b)}
+    changed = True
+    while changed:
+        changed = False
+        for n, b in dev.items():
+            if n not in syncing and any(re.search(r"\b%s\s*[(<]" % re.escape(s), b) for s in syncing):
+                syncing.add(n)
+                changed = True
+    safe = set()
+    for n, b in _functions(text, "__global__"):
+        if not SYNC_PAT.search(b) and not any(re.search(r"\b%s\s*[(<]" % re.escape(s), b) for s in syncing):
+            safe.add(n)
+    return safe
+
+
 def build_full(defines=(), tag=""):
     """libcup2d_emu<tag>.so: every .cu / .cpp of cup2d_b200/csrc compiled with g++, one OS thread per CUDA thread;
     defines: extra -D flags (the measurement variants of advect.cu / weno.cuh)"""
@@ -120,9 +170,10 @@ def build_full(defines=(), tag=""):
     if _fresh(os.path.join(FULL, f"libcup2d_emu{tag}.so"), _inputs()):
         return os.path.join(FULL, f"libcup2d_emu{tag}.so")
     srcs = []
-    for name in sorted(os.listdir(CSRC)):
-        if not name.endswith((".cu", ".cuh", ".h", ".cpp")):
-            continue
+    names = [n for n in sorted(os.listdir(CSRC)) if n.endswith((".cu", ".cuh", ".h", ".cpp"))]
+    safe = serial_safe_kernels([open(os.path.join(CSRC, n)).read() for n in names])
+    assert "amr_gather_kernel" in safe and "k_spmv" not in safe and "advect_stage_kernel" not in safe and "amr_advect_fast_kernel" not in safe, safe
+    for name in names:
         text = open(os.path.join(CSRC, name)).read()
         for pat, rep in ASM_REWRITES:
             text = re.sub(pat, rep, text, flags=re.S)
@@ -130,7 +181,8 @@ def build_full(defines=(), tag=""):
 
         def sub(m):
             cfg = split_top(m.group(3))
-            return f"emu_launch_coop({cfg[0]}, {cfg[1]}, [&] {{ {m.group(1)}{m.group(2)}({m.group(4)}); }});"
+            fn = "emu_launch_auto" if m.group(1) in safe else "emu_launch_coop"   # auto: serial unless EMU_ALL_COOP (sanitizer builds)
+            return f"{fn}({cfg[0]}, {cfg[1]}, [&] {{ {m.group(1)}{m.group(2)}({m.group(4)}); }});"
         text = LAUNCH_ANY.sub(sub, text)
         assert "<<<" not in text, f"launch left in {name}"
         # shared memory becomes block-local storage of the emulated block (ranks emulated in one process run kernels concurrently)
@@ -162,7 +214,7 @@ def build_tsan(defines=(), tag="", sanitize="thread"):
     if _fresh(exe, _inputs()):
         return exe
     subprocess.run(["/usr/bin/g++", "-O1", "-g", "-std=c++20", "-pthread", f"-fsanitize={sanitize}",
-                    *([] if sanitize == "thread" else ["-fno-sanitize-recover=all"]), "-w",
+                    *([] if sanitize == "thread" else ["-fno-sanitize-recover=all"]), "-w", "-DEMU_ALL_COOP",
                     *[f"-D{d}" for d in defines],
                     "-I", FULL, "-I", HERE, "-o", exe,
                     os.path.join(HERE, "tsan_driver.cpp"), *srcs], check=True)

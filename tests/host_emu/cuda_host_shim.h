@@ -134,6 +134,15 @@ inline void emu_launch_coop(int grid, int block, const std::function<void()> &bo
     for (auto &th : pool) th.join();
   }
 }
+// kernels whose threads never interact (build.py: serial_safe_kernels) run one thread after the other, except in the
+// sanitizer builds, where every CUDA thread stays an OS thread so that ThreadSanitizer sees all of them
+inline void emu_launch_auto(int grid, int block, const std::function<void()> &body) {
+#ifdef EMU_ALL_COOP
+  emu_launch_coop(grid, block, body);
+#else
+  emu_launch(grid, block, body);
+#endif
+}
 #define __shared__ static
 #define __align__(n) __attribute__((aligned(n)))
 // vector types carry the alignment the hardware demands of their loads and stores (-fsanitize=alignment reports a violation)

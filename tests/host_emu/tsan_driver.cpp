@@ -62,7 +62,7 @@ int main(int argc, char **argv) {
     CHECK(cup2d_field_upload(s, CUP2D_PRES, pres.data()));
     double dt, err;
     int it;
-    CHECK(cup2d_step(s, 0.0, 0, 0.0, 0.0, 0, 6, &dt, &it, &err));
+    CHECK(cup2d_step(s, 0.0, 0, 0.0, 0.0, 0, 3, &dt, &it, &err));
     std::vector<double> linf(n);
     CHECK(cup2d_adapt_tags(s, 1.0, 4, linf.data()));
     printf("uniform step: dt %.3e iters %d err %.3e\n", dt, it, err);
@@ -89,7 +89,7 @@ int main(int argc, char **argv) {
       CHECK(cup2d_amr_field_upload(a, CUP2D_PRES, pres.data()));
       double dt, err;
       int it;
-      CHECK(cup2d_amr_step(a, 0.5, 0.0, 0.0, 0.0, 0, 5, &dt, &it, &err));
+      CHECK(cup2d_amr_step(a, 0.5, 0.0, 0.0, 0.0, 0, 2, &dt, &it, &err));
       printf("multi-level step (fast=%d): %lld blocks dt %.3e iters %d err %.3e\n", fast, (long long)n, dt, it, err);
     }
     cup2d_amr_destroy(a);

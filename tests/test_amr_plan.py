@@ -263,3 +263,18 @@ def test_poisson_rows_equal_the_reference_assembly(setup):
                 want[r] = -float(len(cols))
                 a, b = ref.indptr[r], ref.indptr[r + 1]
                 assert dict(zip(ref.indices[a:b].tolist(), ref.data[a:b].tolist())) == want
+
+
+def test_chi_lab_tables_of_the_tagging_rule(golden_dir):
+    """stencil kind 3 = GradChiOnTmp's {-4,-4,5,5,tensorial} chi lab (main.cpp:4633): the tables applied to the reference's
+    chi field give its lab to rounding and with the same sign pattern (the rule only asks where the lab is positive)"""
+    from cup2d_b200.amr import AmrPlan
+    d = np.load(os.path.join(golden_dir, "amrtags_lmax8.npz"))
+    nb = len(d["blocks"])
+    plan = AmrPlan(np.ascontiguousarray(d["blocks"], dtype=np.int32), int(d["bpdx"]), int(d["bpdy"]))
+    rp, sb, sc, w = plan.stencil(3)
+    assert len(rp) == nb * 256 + 1 and (rp[1:] > rp[:-1]).all()       # tensorial: every lab cell has sources
+    vals = w * d["chi"].reshape(nb, 64)[sb, sc]
+    lab = np.add.reduceat(vals, rp[:-1]).reshape(nb, 16, 16)
+    assert np.abs(lab - d["lab_chi4"]).max() < 1e-14
+    assert np.array_equal(lab > 0, d["lab_chi4"] > 0)

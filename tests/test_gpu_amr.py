@@ -143,6 +143,28 @@ def test_amr_full_step_against_composed_oracle(case, fast):
     assert rel(sim.download("vel"), vel) < 1e-9 and rel(sim.download("pres"), pres) < 1e-9
 
 
+def test_amr_adapt_tags_vs_reference_golden(golden_dir):
+    """cup2d_amr_adapt_tags on the reference's run.sh mesh with its two fish (tests/golden/amrtags_lmax8.npz): the tagging
+    field to rounding, the chi rule on exactly the reference's 80 blocks, the same refine / compress sets"""
+    from cup2d_b200.amr import AmrSimulation
+    d = np.load(os.path.join(golden_dir, "amrtags_lmax8.npz"))
+    nb, rtol, ctol = len(d["blocks"]), float(d["rtol"]), float(d["ctol"])
+    sim = AmrSimulation(d["blocks"], int(d["bpdx"]), int(d["bpdy"]), float(d["h0"]), 4e-5)
+    sim.upload("vel", d["vel"])
+    sim.upload("chi", d["chi"])
+    for _ in range(2):   # the second call reuses the tables built by the first
+        linf = sim.adapt_tags(rtol, int(d["level_max"]))
+    field = sim.download("tmp").reshape(nb, 8, 8)
+    want = d["tagfield"]
+    assert np.abs(field - want).max() < 1e-12 * np.abs(want).max()
+    fired = (d["vort"] != want).reshape(nb, -1).any(axis=1)
+    assert np.array_equal(field.reshape(nb, 64)[fired][:, [27, 28, 35, 36]], np.full((fired.sum(), 4), 2 * rtol))
+    wl = np.abs(want).reshape(nb, -1).max(axis=1)
+    assert np.abs(linf - wl).max() < 1e-12 * wl.max()
+    assert np.array_equal(linf > rtol, wl > rtol) and np.array_equal(linf < ctol, wl < ctol)
+    sim.close()
+
+
 def test_amr_bodies_sums_blend_and_udef_assembly(case):
     """cup2d_amr_shape_*: two synthetic shapes whose obstacle blocks span several refinement levels (the field chi is the
     golden's own).  Against a block-wise numpy restatement of main.cpp:6648-6679, 6944-6979, 6980-7002 with the per-block

@@ -593,7 +593,7 @@ def test_host_pipeline_matches_blocking_calls():
     streams with buffer trading — bit-identical to cup2d_field_upload + cup2d_step + cup2d_field_download, for more jobs
     than staging sets (slot reuse), with the context's own fields left alone in between."""
     import torch
-    L, jobs = 3, 6
+    L, jobs = 2, 6
     sim = cup2d_b200.Simulation(L, nu=1e-3, cfl=0.4)
     n = sim.nloc
     rng = np.random.default_rng(5)
@@ -607,13 +607,13 @@ def test_host_pipeline_matches_blocking_calls():
     for j in range(jobs):
         sim.upload_blocks("vel", vin[j].numpy())
         sim.upload_blocks("pres", pin_[j].numpy())
-        info = sim.step(max_iter=3, max_restarts=0)
+        info = sim.step(max_iter=2, max_restarts=0)
         want.append((sim.download_blocks("vel").copy(), sim.download_blocks("pres").copy(), info))
     # the context's own fields must survive a pipelined batch untouched
     sim.upload_blocks("vel", vin[0].numpy())
     sim.upload_blocks("pres", pin_[0].numpy())
     got = sim.pipelined_steps(((vin[j].data_ptr(), pin_[j].data_ptr(), vout[j].data_ptr(), pout[j].data_ptr()) for j in range(jobs)),
-                              max_iter=3, max_restarts=0)
+                              max_iter=2, max_restarts=0)
     for j in range(jobs):
         assert np.array_equal(vout[j].numpy(), want[j][0]) and np.array_equal(pout[j].numpy(), want[j][1]), j
         assert got[j] == want[j][2]
