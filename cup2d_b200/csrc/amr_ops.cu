@@ -279,7 +279,13 @@ static int upload_csr(cup2d_amr *a, int which) {
   return CUP2D_OK;
 }
 
-static int gather(cup2d_amr *a, int which, const double *field, double *lab) {
+// The full tables (every lab cell of every block) serve the baseline kernels only; they are built the first time one of
+// those runs, so that a context driven through the fast kernels (compact tables: ghost rows of irregular blocks) never pays
+// for them — they grow with the mesh, the compact ones with its level interfaces.
+static int gather(cup2d_amr *a, int which, const double *field, double *&lab) {
+  int rc;
+  if (!a->csr[which].rowptr && (rc = upload_csr(a, which))) return rc;
+  if (!lab) CUP2D_CUDA(cudaMalloc(&lab, a->csr[which].nrows * sizeof(double)));
   amr_gather_kernel<<<grid_for(a->csr[which].nrows), 256, 0, a->stream>>>(a->csr[which], field, lab, LABD[which]);
   CUP2D_CUDA(cudaGetLastError());
   return CUP2D_OK;
@@ -359,9 +365,6 @@ int cup2d_amr_create(int64_t nblocks, const int32_t *level_ij, int32_t bpdx, int
   if (cudaMalloc(&a->d_h, nblocks * sizeof(double)) != cudaSuccess ||
       cudaMemcpy(a->d_h, h.data(), nblocks * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess)
     return fail(CUP2D_ECUDA);
-  for (int which = 0; which < 3; which++)
-    if ((rc = upload_csr(a, which))) return fail(rc);
-  if (cudaMalloc(&a->lab_udef, a->csr[1].nrows * sizeof(double)) != cudaSuccess) return fail(CUP2D_ECUDA);
   // coarse faces: group the plan's (fine block, face, coarse block, face, half) records by (coarse block, face)
   const int64_t nf = cup2d_amr_plan_faces(plan, nullptr);
   std::vector<int32_t> rec(5 * std::max<int64_t>(nf, 1));
@@ -487,7 +490,6 @@ int cup2d_amr_adapt_tags(cup2d_amr *a, double rtol, int level_max, double *block
   }
   CUP2D_CUDA(cudaSetDevice(a->device));
   int rc;
-  if (!a->csr[3].rowptr && (rc = upload_csr(a, 3))) return rc;
   if ((rc = gather(a, 1, a->f[CUP2D_VEL], a->lab[1])) || (rc = gather(a, 3, a->f[CUP2D_CHI], a->lab[3]))) return rc;
   amr_vorticity_kernel<<<grid_for(a->nb * 64), 256, 0, a->stream>>>(a->lab[1], a->f[CUP2D_TMP], a->d_h, a->nb * 64);
   amr_tag_block_kernel<<<grid_for(a->nb), 256, 0, a->stream>>>(a->lab[3], a->f[CUP2D_TMP], a->d_h,

@@ -278,3 +278,25 @@ def test_chi_lab_tables_of_the_tagging_rule(golden_dir):
     lab = np.add.reduceat(vals, rp[:-1]).reshape(nb, 16, 16)
     assert np.abs(lab - d["lab_chi4"]).max() < 1e-14
     assert np.array_equal(lab > 0, d["lab_chi4"] > 0)
+
+
+def test_plan_of_the_c5_bench_mesh_scales():
+    """config C5 (3-level AMR, 16384^2 effective): the synthetic mesh of tools/bench_amr.py at full size — 501 376 blocks,
+    32 M cells — is accepted (2:1 balanced), and what a device context needs from the plan (compact ghost tables of the three
+    stencils, Poisson rows) is built in seconds and grows with the level interfaces (5 400 irregular blocks), not with the mesh"""
+    import sys
+    import time
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    import bench_amr
+    from cup2d_b200.amr import AmrPlan
+    blocks = bench_amr.three_level_mesh(9)
+    assert len(blocks) == 501376 and sorted(set(blocks[:, 0].tolist())) == [9, 10, 11]
+    assert (blocks[:, 1] >= 0).all() and (blocks[:, 1] < (1 << blocks[:, 0])).all()
+    t0 = time.time()
+    plan = AmrPlan(blocks, 1, 1)
+    irr = plan.irregular()
+    nnz = [len(plan.ghosts(k)[-1]) for k in range(3)]
+    nbr, rows, rowptr, col, val = plan.poisson()
+    dt = time.time() - t0
+    assert len(irr) == 5400 and nnz[0] < 1000 * len(irr) and len(rows) < 64 * len(irr)
+    assert dt < 60, dt

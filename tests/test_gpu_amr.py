@@ -143,6 +143,43 @@ def test_amr_full_step_against_composed_oracle(case, fast):
     assert rel(sim.download("vel"), vel) < 1e-9 and rel(sim.download("pres"), pres) < 1e-9
 
 
+@pytest.mark.parametrize("base", [pytest.param(3, id="base3"), pytest.param(4, id="base4")])
+def test_synthetic_three_level_mesh_vs_oracle(base):
+    """a second family of meshes (tools/bench_amr.py:three_level_mesh — the generator of the C5 bench mesh — here small): two
+    nested refined discs, so every orientation of a level interface and its corners occur, walls included; operators on
+    baseline and fast kernels against the reference restatement (oracle/cup2d_amr_oracle.py, bit-exact on the reference's own
+    meshes)"""
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(root, "tools"))
+    import bench_amr
+    import cup2d_amr_oracle as ao
+    from cup2d_b200.amr import AmrSimulation
+    blocks = bench_amr.three_level_mesh(base, r1=0.3, r2=0.15, centre=(0.45, 0.55))
+    assert sorted(set(blocks[:, 0].tolist())) == [base, base + 1, base + 2]
+    h0, nu, dt = 1 / 8, 1e-3, 1e-3
+    rng = np.random.default_rng(3)
+    vel, pres = bench_amr.seeded_fields(blocks, h0)
+    vel, pres = vel + 0.05 * rng.uniform(-1, 1, vel.shape), pres + 0.05 * rng.uniform(-1, 1, pres.shape)
+    chi, udef = rng.uniform(0, 1, pres.shape), rng.uniform(-1, 1, vel.shape)
+    out = ao.amr_operators(ao.Mesh(blocks, 1, 1), h0, vel, pres, chi, udef, nu, dt)
+    sim = AmrSimulation(blocks, 1, 1, h0, nu)
+    for fast in (False, True):
+        sim.set_fast(fast)
+        sim.upload("vel", vel)
+        sim.advect_diffuse_rhs(dt)
+        assert rel(sim.download("tmpV"), out["adv"]) < 1e-12
+        sim.upload("tmpV", udef)
+        sim.upload("chi", chi)
+        sim.upload("pold", pres)
+        sim.pressure_rhs(dt, True)
+        assert rel(sim.download("tmp"), out["rhs1"]) < 1e-12
+        sim.upload("pres", pres)
+        sim.pressure_gradient(dt)
+        assert rel(sim.download("tmpV"), out["gradp"]) < 1e-12
+    sim.close()
+
+
 def test_amr_adapt_tags_vs_reference_golden(golden_dir):
     """cup2d_amr_adapt_tags on the reference's run.sh mesh with its two fish (tests/golden/amrtags_lmax8.npz): the tagging
     field to rounding, the chi rule on exactly the reference's 80 blocks, the same refine / compress sets"""

@@ -67,6 +67,9 @@ for fast in 0 1; do
     timeout 300 python tools/bench_amr.py 9 10 10 $fast > $OUT/bench_amr_fast${fast}_$TAG.json 2> $OUT/bench_amr_fast${fast}_$TAG.err
     tail -c 600 $OUT/bench_amr_fast${fast}_$TAG.json; tail -c 300 $OUT/bench_amr_fast${fast}_$TAG.err
 done
+# config C5: synthetic 3-level mesh, 16384^2 effective (501 376 blocks, 32 M cells), fast kernels
+timeout 400 python tools/bench_amr.py synthetic 9 10 10 1 > $OUT/bench_amr_c5_$TAG.json 2> $OUT/bench_amr_c5_$TAG.err
+tail -c 600 $OUT/bench_amr_c5_$TAG.json; tail -c 300 $OUT/bench_amr_c5_$TAG.err
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $OUT/launches_amr_$TAG.csv \
     python tools/bench_amr.py 9 2 10 1 > $OUT/ncu_list_amr_$TAG.log 2>&1
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:'amr_.*fast|amr_fluxcorr' -s 20 -c 8 -o $OUT/amr_fast_$TAG -f \
