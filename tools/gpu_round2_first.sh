@@ -75,3 +75,28 @@ timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --c
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:'amr_.*fast|amr_fluxcorr' -s 20 -c 8 -o $OUT/amr_fast_$TAG -f \
     python tools/bench_amr.py 9 1 4 1 > $OUT/ncu_amr_$TAG.log 2>&1
 ls -la $OUT | tail -30
+
+echo "== 6. config C1 (the reference's run.sh case, levelMax 8, 40 steps, 20 Krylov iterations each): wall time of the whole program"
+# ref_harness_gpu = the unmodified reference with its own cuda.cu solver; the other two run its hot path on cup2d_amr
+for exe in ref_harness_gpu ref_harness_amrloop ref_harness_amrresident; do
+    [ -x oracle/_ref/$exe ] || { echo "$exe not built"; continue; }
+    s=$(date +%s%N)
+    OMP_NUM_THREADS=$(nproc) CUP2D_B200_AMR_FAST=1 CUP2D_B200_MAX_ITER=20 timeout 600 oracle/_ref/$exe asteps 8 40 20 /tmp/c1_$exe.bin > /dev/null 2>&1
+    echo "$exe rc=$? wall $(( ($(date +%s%N) - s) / 1000000 )) ms" | tee -a $OUT/c1_walltime_$TAG.txt
+done
+python - <<PY | tee -a $OUT/c1_walltime_$TAG.txt
+import numpy as np, os
+def last(path):
+    a, i, rec = np.fromfile(path), 0, None
+    while i < len(a):
+        nb = int(a[i + 1]); rec = (nb, a[i + 2 + 3 * nb:i + 2 + 131 * nb]); i += 2 + 195 * nb
+    return rec
+try:
+    ref = last("/tmp/c1_ref_harness_gpu.bin")
+    for exe in ("ref_harness_amrloop", "ref_harness_amrresident"):
+        got = last(f"/tmp/c1_{exe}.bin")
+        print(exe, "blocks", got[0], "vs", ref[0], "vel rel diff after 40 steps",
+              float(np.abs(got[1] - ref[1]).max() / np.abs(ref[1]).max()) if got[0] == ref[0] else "mesh differs")
+except Exception as e:
+    print("C1 comparison unavailable:", e)
+PY
