@@ -28,6 +28,9 @@ namespace cup2d {
 constexpr int NT = 256;
 constexpr int WPB = NT / 32;
 constexpr double EPS21 = 1e-21;    // cuda.cu:409
+#ifndef SPMV_CTAS
+#define SPMV_CTAS 3 // resident CTAs/SM of the SpMV kernels (80 registers); 4 is a measurement variant (make variant EXTRA=-DSPMV_CTAS=4)
+#endif
 #ifndef PRECOND_CTAS
 #define PRECOND_CTAS 3 // resident CTAs/SM of the two preconditioner kernels (3: 73-78 regs; 4 (64 regs) measured 2 % slower)
 #endif
@@ -208,7 +211,7 @@ k_pupdate(const double *__restrict__ r, double *__restrict__ rhat, double *__res
 //   MODE 0 (K2): nu = A z ; rhat.nu             -> alpha = rho/(rhat.nu + eps)   (cuda.cu:487-496)
 //   MODE 1 (K4): t  = A z ; t.r, t.t            -> omega = t.r/(t.t + eps)       (cuda.cu:506-518)
 template <int MODE, bool IRR>
-__global__ void __launch_bounds__(NT, 3)
+__global__ void __launch_bounds__(NT, SPMV_CTAS)
 k_spmv(const double *__restrict__ z, const double *__restrict__ d, double *__restrict__ yout,
        const int4 *__restrict__ nbr, int nrows, KrylovState *st, double *partials,
        unsigned int *counter, Comm comm, IrrView irr) {

@@ -40,7 +40,7 @@ echo "== 4. advect variants (same bench, kernel table only)"
 ab() { # name, defines
     make -s -C cup2d_b200/csrc variant EXTRA="$2" > $OUT/variant_$1_$TAG.log 2>&1 || { echo "variant $1 failed to build"; return; }
     cp cup2d_b200/libcup2d_b200_variant.so cup2d_b200/libcup2d_b200_$1.so
-    CUP2D_B200_LIB=$PWD/cup2d_b200/libcup2d_b200_$1.so timeout 200 python -m pytest tests/test_gpu_parity.py -m gpu -q -x -k "advect or rk2 or time_steps or full_step or operators" \
+    CUP2D_B200_LIB=$PWD/cup2d_b200/libcup2d_b200_$1.so timeout 200 python -m pytest tests/test_gpu_parity.py -m gpu -q -x -k "advect or rk2 or time_steps or full_step or operators or poisson" \
         > $OUT/variant_$1_pytest_$TAG.log 2>&1
     echo "variant $1 parity rc=$? $(tail -1 $OUT/variant_$1_pytest_$TAG.log)"
     CUP2D_B200_LIB=$PWD/cup2d_b200/libcup2d_b200_$1.so timeout 150 python bench.py --no-e2e --no-cpu-baseline --steps 10 \
@@ -51,13 +51,16 @@ ab warprows "-DCUP2D_ADV_WARP_ROWS=1"
 ab cubic "-DCUP2D_WENO_CUBIC_RCP=1"
 ab lazy "-DCUP2D_WENO_LAZY_BETAS=1"
 ab all3 "-DCUP2D_ADV_WARP_ROWS=1 -DCUP2D_WENO_CUBIC_RCP=1 -DCUP2D_WENO_LAZY_BETAS=1"
+ab spmv4 "-DSPMV_CTAS=4"        # SpMV at 4 CTAs/SM (64 registers, ~90 B of spills) instead of 3
 python - <<PY
 import json, glob
 for f in sorted(glob.glob("$OUT/bench_variant_*_$TAG.json")):
     try:
         d = json.loads(open(f).read().strip().splitlines()[-1])
         adv = [k for k in d["kernels"] if k["kernel"].startswith("advect")][0]
-        print(f, "advect ms", round(adv["ms_per_launch"], 4), "step ms", round(d["ms_per_step"], 3), d["clocks"]["sm_mhz"])
+        spmv = [k["ms_per_launch"] for k in d["kernels"] if k["kernel"].startswith("k_spmv")]
+        print(f, "advect ms", round(adv["ms_per_launch"], 4), "spmv ms", [round(x, 4) for x in spmv], "step ms", round(d["ms_per_step"], 3),
+              d["clocks"]["sm_mhz"])
     except Exception as e:
         print(f, "unreadable:", e)
 PY
