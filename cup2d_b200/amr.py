@@ -189,3 +189,58 @@ class AmrSimulation:
         if self._h:
             self.lib.cup2d_amr_destroy(self._h)
             self._h = C.c_void_p()
+
+
+class DistributedPoisson:
+    """The Poisson matrix of a (multi-level) mesh — neighbour table + general rows, e.g. AmrPlan.poisson() — distributed over
+    ranks by contiguous block ranges (cup2d_poisson_create_general_ranks): this rank's share.  One process (or, in the
+    emulation tests, one thread) per rank; attach_peers(dist) like Simulation."""
+
+    def __init__(self, nbr, rows, rowptr, col, val, rank_begin, rank, device=0):
+        self.lib = _l.load_library()
+        rank_begin = np.ascontiguousarray(rank_begin, dtype=np.int64)
+        self.rank, self.nranks = int(rank), len(rank_begin) - 1
+        b0, b1 = int(rank_begin[rank]), int(rank_begin[rank + 1])
+        self.b0, self.nloc = b0, b1 - b0
+        nbr = np.ascontiguousarray(np.asarray(nbr, dtype=np.int32).reshape(-1, 4)[b0:b1])
+        rows, rowptr = np.asarray(rows, dtype=np.int64), np.asarray(rowptr, dtype=np.int64)
+        k0, k1 = np.searchsorted(rows, 64 * b0), np.searchsorted(rows, 64 * b1)
+        my_rows = np.ascontiguousarray(rows[k0:k1] - 64 * b0, dtype=np.int32)
+        my_ptr = np.ascontiguousarray(rowptr[k0:k1 + 1] - rowptr[k0], dtype=np.int32)
+        my_col = np.ascontiguousarray(np.asarray(col)[rowptr[k0]:rowptr[k1]], dtype=np.int32)
+        my_val = np.ascontiguousarray(np.asarray(val)[rowptr[k0]:rowptr[k1]], dtype=np.float64)
+        I32 = C.POINTER(C.c_int32)
+        self._h = C.c_void_p()
+        _l.check(self.lib.cup2d_poisson_create_general_ranks(
+            int(rank_begin[-1]), self.rank, self.nranks, rank_begin.ctypes.data_as(C.POINTER(C.c_int64)), nbr.ctypes.data_as(I32),
+            len(my_rows), my_rows.ctypes.data_as(I32), my_ptr.ctypes.data_as(I32), my_col.ctypes.data_as(I32),
+            my_val.ctypes.data_as(C.POINTER(C.c_double)), device, C.byref(self._h)))
+
+    def attach_peers(self, dist=None):
+        n = self.lib.cup2d_peer_blob_size()
+        blob = (C.c_ubyte * n)()
+        _l.check(self.lib.cup2d_peer_export(self._h, blob))
+        gathered = [bytes(blob)]
+        if self.nranks > 1:
+            gathered = [None] * self.nranks
+            dist.all_gather_object(gathered, bytes(blob))
+        allb = b"".join(gathered)
+        _l.check(self.lib.cup2d_peer_attach(self._h, (C.c_ubyte * len(allb)).from_buffer_copy(allb)))
+        if dist is not None and self.nranks > 1:
+            dist.barrier()
+
+    def solve(self, b_blocks, x0_blocks, tol_abs=0.0, tol_rel=0.0, max_restarts=0, max_iter=1000):
+        """b, x0: this rank's blocks (nloc, 64) -> (x of this rank's blocks, iterations, error)"""
+        b = np.ascontiguousarray(b_blocks, dtype=np.float64).reshape(self.nloc * 64)
+        x = np.ascontiguousarray(x0_blocks, dtype=np.float64).reshape(self.nloc * 64).copy()
+        _l.check(self.lib.cup2d_field_upload(self._h, _l.FIELDS["tmp"], b.ctypes.data))
+        _l.check(self.lib.cup2d_field_upload(self._h, _l.FIELDS["pres"], x.ctypes.data))
+        it, err = C.c_int(), C.c_double()
+        _l.check(self.lib.cup2d_poisson_solve(self._h, tol_abs, tol_rel, max_restarts, max_iter, C.byref(it), C.byref(err)))
+        _l.check(self.lib.cup2d_field_download(self._h, _l.FIELDS["pres"], x.ctypes.data))
+        return x.reshape(self.nloc, 64), it.value, err.value
+
+    def close(self):
+        if self._h:
+            self.lib.cup2d_destroy(self._h)
+            self._h = C.c_void_p()

@@ -344,6 +344,40 @@ int cup2d_poisson_create(int64_t nblocks, const int32_t *nbr, int32_t device, cu
   return CUP2D_OK;
 }
 
+// general rows of a Poisson-only context: irr_rows (sorted, unique) index LOCAL rows 64*block + cell, irr_col index the
+// context's vector slots (local blocks, then halo slots)
+static int install_general_rows(cup2d_sim *s, int64_t n_irr, const int32_t *irr_rows, const int32_t *irr_rowptr,
+                                const int32_t *irr_col, const double *irr_val) {
+  std::vector<int> blk(s->nloc, -1), tab;
+  int nirrblk = 0;
+  for (int64_t k = 0; k < n_irr; k++) {
+    const int r = irr_rows[k];
+    CUP2D_REQUIRE(r >= 0 && r < s->nloc * 64 && (k == 0 || irr_rows[k - 1] < r),
+                  "cup2d_poisson_create_general: irr_rows must be sorted, unique, in range");
+    const int b = r / 64;
+    if (blk[b] < 0) {
+      blk[b] = nirrblk++;
+      tab.resize((size_t)nirrblk * 64, -1);
+    }
+    tab[(size_t)blk[b] * 64 + r % 64] = (int)k;
+  }
+  const int nnz = irr_rowptr[n_irr];
+  for (int j = 0; j < nnz; j++)
+    CUP2D_REQUIRE(irr_col[j] >= 0 && irr_col[j] < s->nslots * 64, "cup2d_poisson_create_general: column out of range");
+  auto up = [](void **d, const void *h, size_t bytes) -> cudaError_t {
+    cudaError_t e = cudaMalloc(d, bytes ? bytes : 8);
+    if (e != cudaSuccess) return e;
+    return cudaMemcpy(*d, h, bytes, cudaMemcpyHostToDevice);
+  };
+  CUP2D_CUDA(up((void **)&s->d_irr_blk, blk.data(), blk.size() * sizeof(int)));
+  CUP2D_CUDA(up((void **)&s->d_irr_tab, tab.data(), tab.size() * sizeof(int)));
+  CUP2D_CUDA(up((void **)&s->d_irr_rowptr, irr_rowptr, (size_t)(n_irr + 1) * sizeof(int)));
+  CUP2D_CUDA(up((void **)&s->d_irr_col, irr_col, (size_t)nnz * sizeof(int)));
+  CUP2D_CUDA(up((void **)&s->d_irr_val, irr_val, (size_t)nnz * sizeof(double)));
+  s->n_irr_rows = n_irr;
+  return CUP2D_OK;
+}
+
 // Poisson-only context whose matrix is "same-level stencil from nbr[] + general CSR rows that override
 // it".  irr_rows (sorted, unique) are row indices 64*block + 8*iy + ix; their complete rows are given
 // in CSR (rowptr has n_irr+1 entries).  nbr faces that are covered by general rows must be -1.
@@ -360,40 +394,99 @@ int cup2d_poisson_create_general(int64_t nblocks, const int32_t *nbr, int64_t n_
     return CUP2D_EINVAL;
   };
   if (!irr_rows || !irr_rowptr || !irr_col || !irr_val) return bail("cup2d_poisson_create_general: null table");
-  std::vector<int> blk(nblocks, -1), tab;
-  int nirrblk = 0;
-  for (int64_t k = 0; k < n_irr; k++) {
-    const int r = irr_rows[k];
-    if (r < 0 || r >= nblocks * 64 || (k > 0 && irr_rows[k - 1] >= r)) return bail("cup2d_poisson_create_general: irr_rows must be sorted, unique, in range");
-    const int b = r / 64;
-    if (blk[b] < 0) {
-      blk[b] = nirrblk++;
-      tab.resize((size_t)nirrblk * 64, -1);
-    }
-    tab[(size_t)blk[b] * 64 + r % 64] = (int)k;
-  }
-  const int nnz = irr_rowptr[n_irr];
-  for (int j = 0; j < nnz; j++)
-    if (irr_col[j] < 0 || irr_col[j] >= nblocks * 64) return bail("cup2d_poisson_create_general: column out of range");
-  auto up = [](void **d, const void *h, size_t bytes) -> cudaError_t {
-    cudaError_t e = cudaMalloc(d, bytes ? bytes : 8);
-    if (e != cudaSuccess) return e;
-    return cudaMemcpy(*d, h, bytes, cudaMemcpyHostToDevice);
-  };
-  auto upload_rows = [&]() -> int {
-    CUP2D_CUDA(up((void **)&s->d_irr_blk, blk.data(), blk.size() * sizeof(int)));
-    CUP2D_CUDA(up((void **)&s->d_irr_tab, tab.data(), tab.size() * sizeof(int)));
-    CUP2D_CUDA(up((void **)&s->d_irr_rowptr, irr_rowptr, (size_t)(n_irr + 1) * sizeof(int)));
-    CUP2D_CUDA(up((void **)&s->d_irr_col, irr_col, (size_t)nnz * sizeof(int)));
-    CUP2D_CUDA(up((void **)&s->d_irr_val, irr_val, (size_t)nnz * sizeof(double)));
-    return CUP2D_OK;
-  };
-  if ((rc = upload_rows())) { // no half-built context escapes: the caller gets an error and a null handle
+  if ((rc = install_general_rows(s, n_irr, irr_rows, irr_rowptr, irr_col, irr_val))) { // no half-built context escapes
     cup2d_destroy(s);
     *out = nullptr;
     return rc;
   }
-  s->n_irr_rows = n_irr;
+  return CUP2D_OK;
+}
+
+// The same on several ranks (one process per GPU): rank r owns the contiguous range rank_begin[r] .. rank_begin[r+1] of the
+// global block list.  nbr = W,E,S,N of the LOCAL blocks as GLOBAL block ids (-1: wall or covered by general rows);
+// irr_rows = LOCAL row indices 64*(block - rank_begin[rank]) + cell; irr_col = GLOBAL column indices 64*block + cell.
+// Every remote block these tables name becomes a halo slot of this rank (refreshed by whole-block peer pulls like the
+// face neighbours of the uniform path), the tables are renumbered to slots, and the Krylov kernels run unchanged.
+// cup2d_peer_export / cup2d_peer_attach must follow before the first solve.
+int cup2d_poisson_create_general_ranks(int64_t nblocks_global, int32_t rank, int32_t nranks, const int64_t *rank_begin,
+                                       const int32_t *nbr, int64_t n_irr, const int32_t *irr_rows,
+                                       const int32_t *irr_rowptr, const int32_t *irr_col, const double *irr_val,
+                                       int32_t device, cup2d_sim **out) {
+  CUP2D_REQUIRE(out && nbr && rank_begin && nblocks_global > 0, "cup2d_poisson_create_general_ranks: bad arguments");
+  CUP2D_REQUIRE(nranks >= 1 && nranks <= MAX_RANKS && rank >= 0 && rank < nranks, "cup2d_poisson_create_general_ranks: bad rank/nranks (1..8 ranks)");
+  CUP2D_REQUIRE(nblocks_global * 64 < (1LL << 31), "cup2d_poisson_create_general_ranks: more than 2^31 rows");
+  CUP2D_REQUIRE(n_irr == 0 || (irr_rows && irr_rowptr && irr_col && irr_val), "cup2d_poisson_create_general_ranks: null table");
+  bool ok = rank_begin[0] == 0 && rank_begin[nranks] == nblocks_global;
+  for (int r = 0; ok && r < nranks; r++) ok = rank_begin[r + 1] > rank_begin[r];
+  CUP2D_REQUIRE(ok, "cup2d_poisson_create_general_ranks: rank_begin must be increasing and span [0, nblocks_global]");
+  const int64_t gb = rank_begin[rank], ge = rank_begin[rank + 1], nloc = ge - gb;
+  const int64_t nnz = n_irr > 0 ? irr_rowptr[n_irr] : 0;
+  std::vector<int32_t> halo;
+  for (int64_t k = 0; k < 4 * nloc; k++) {
+    CUP2D_REQUIRE(nbr[k] >= -1 && nbr[k] < nblocks_global, "cup2d_poisson_create_general_ranks: neighbour id out of range");
+    if (nbr[k] >= 0 && (nbr[k] < gb || nbr[k] >= ge)) halo.push_back(nbr[k]);
+  }
+  for (int64_t j = 0; j < nnz; j++) {
+    CUP2D_REQUIRE(irr_col[j] >= 0 && irr_col[j] < nblocks_global * 64, "cup2d_poisson_create_general_ranks: column out of range");
+    const int32_t g = irr_col[j] / 64;
+    if (g < gb || g >= ge) halo.push_back(g);
+  }
+  std::sort(halo.begin(), halo.end());
+  halo.erase(std::unique(halo.begin(), halo.end()), halo.end());
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    set_error("cup2d_poisson_create_general_ranks: no CUDA device visible; this library has no CPU fallback");
+    return CUP2D_ENOGPU;
+  }
+  CUP2D_REQUIRE(device >= 0 && device < ndev, "cup2d_poisson_create_general_ranks: bad device ordinal");
+  CUP2D_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CUP2D_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) {
+    set_error(std::string("cup2d_poisson_create_general_ranks: device '") + prop.name + "' is not sm_100");
+    return CUP2D_ENOGPU;
+  }
+  cup2d_sim *s = new cup2d_sim;
+  s->nglobal = nblocks_global;
+  s->rank = rank;
+  s->nranks = nranks;
+  s->device = device;
+  s->h = 1.0;
+  s->poisson_only = true;
+  s->rank_begin.assign(rank_begin, rank_begin + nranks + 1);
+  s->gbegin = gb;
+  s->nloc = nloc;
+  s->halo_gid = halo;
+  s->nhalo = (int64_t)halo.size();
+  s->nslots = nloc + s->nhalo;
+  s->halo_owner.resize(halo.size());
+  s->h_halo_src.assign(2 * halo.size(), 0);
+  for (size_t k = 0; k < halo.size(); k++) {
+    int r = 0;
+    while (!(halo[k] >= rank_begin[r] && halo[k] < rank_begin[r + 1])) r++;
+    s->halo_owner[k] = r;
+    s->h_halo_src[2 * k] = r;
+    s->h_halo_src[2 * k + 1] = (int)(halo[k] - rank_begin[r]);
+  }
+  auto slot_of = [&](int32_t g) -> int {
+    if (g < 0) return -1;
+    if (g >= gb && g < ge) return (int)(g - gb);
+    return (int)(nloc + (std::lower_bound(halo.begin(), halo.end(), g) - halo.begin()));
+  };
+  s->h_nbr.resize(4 * nloc);
+  for (int64_t k = 0; k < 4 * nloc; k++) s->h_nbr[k] = slot_of(nbr[k]);
+  s->num_sms = prop.multiProcessorCount;
+  int rc = alloc_device_state(s);
+  if (!rc && n_irr > 0) {
+    std::vector<int32_t> col(nnz);
+    for (int64_t j = 0; j < nnz; j++) col[j] = slot_of(irr_col[j] / 64) * 64 + irr_col[j] % 64;
+    rc = install_general_rows(s, n_irr, irr_rows, irr_rowptr, col.data(), irr_val);
+  }
+  if (rc) {
+    cup2d_destroy(s);
+    return rc;
+  }
+  *out = s;
   return CUP2D_OK;
 }
 

@@ -18,7 +18,7 @@ SYMBOLS = [
     "cup2d_pipe_upload", "cup2d_pipe_step", "cup2d_pipe_download", "cup2d_pipe_wait",
     "cup2d_peer_blob_size", "cup2d_peer_export", "cup2d_peer_attach", "cup2d_halo_exchange",
     "cup2d_launch_count", "cup2d_profile_enable", "cup2d_profile_read",
-    "cup2d_plan_create", "cup2d_plan_table", "cup2d_poisson_create", "cup2d_poisson_create_general", "cup2d_vorticity_tag", "cup2d_adapt_tags", "cup2d_dump",
+    "cup2d_plan_create", "cup2d_plan_table", "cup2d_poisson_create", "cup2d_poisson_create_general", "cup2d_poisson_create_general_ranks", "cup2d_vorticity_tag", "cup2d_adapt_tags", "cup2d_dump",
     "cup2d_shape_set", "cup2d_shape_integrals", "cup2d_penalize", "cup2d_udef_assemble",
     "cup2d_amr_plan_create", "cup2d_amr_plan_destroy", "cup2d_amr_plan_stencil", "cup2d_amr_plan_faces",
     "cup2d_amr_plan_irregular", "cup2d_amr_plan_ghosts", "cup2d_amr_plan_stats", "cup2d_amr_plan_neighbours", "cup2d_amr_plan_poisson",
@@ -94,6 +94,8 @@ def load_library():
     lib.cup2d_peer_attach.argtypes = [P, P]
     lib.cup2d_halo_exchange.argtypes = [P, I]
     lib.cup2d_poisson_create.argtypes = [L, C.POINTER(C.c_int32), C.c_int32, C.POINTER(P)]
+    lib.cup2d_poisson_create_general_ranks.argtypes = [L, I, I, C.POINTER(C.c_int64), C.POINTER(C.c_int32), L, C.POINTER(C.c_int32),
+                                                       C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(D), I, C.POINTER(P)]
     lib.cup2d_poisson_create_general.argtypes = [L, C.POINTER(C.c_int32), L, C.POINTER(C.c_int32), C.POINTER(C.c_int32),
                                                  C.POINTER(C.c_int32), C.POINTER(D), C.c_int32, C.POINTER(P)]
     lib.cup2d_vorticity_tag.argtypes = [P, C.POINTER(D)]

@@ -180,6 +180,16 @@ int cup2d_poisson_create(int64_t nblocks, const int32_t *nbr, int32_t device, cu
 int cup2d_poisson_create_general(int64_t nblocks, const int32_t *nbr, int64_t n_irr, const int32_t *irr_rows,
                                  const int32_t *irr_rowptr, const int32_t *irr_col, const double *irr_val,
                                  int32_t device, cup2d_sim **out);
+/* The same matrix distributed over several ranks the way the reference distributes it (contiguous ranges of the block list,
+ * main.cpp:6494-6504; rows of rank r offset by 64*rank_begin[r], 7040-7050; remote columns = the halo of cuda.cu:611-689):
+ * nbr[4*nloc] = W,E,S,N of this rank's blocks as GLOBAL block ids, irr_rows = LOCAL rows 64*(block - rank_begin[rank]) + cell,
+ * irr_col = GLOBAL columns 64*block + cell.  Remote blocks named by either table become halo slots refreshed by whole-block
+ * peer pulls inside the solve; cup2d_peer_export / cup2d_peer_attach before the first cup2d_poisson_solve.  Fields are
+ * uploaded / downloaded per rank (nloc blocks). */
+int cup2d_poisson_create_general_ranks(int64_t nblocks_global, int32_t rank, int32_t nranks, const int64_t *rank_begin,
+                                       const int32_t *nbr, int64_t n_irr, const int32_t *irr_rows,
+                                       const int32_t *irr_rowptr, const int32_t *irr_col, const double *irr_val,
+                                       int32_t device, cup2d_sim **out);
 
 /* ---- host-side topology plan (no GPU needed; used by the CPU tests of the multi-rank logic) ---- */
 /* Same config as cup2d_create, but builds only the host tables: SFC-range partition, halo plan

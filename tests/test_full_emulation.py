@@ -99,6 +99,51 @@ assert worst < 1e-12
     assert r.returncode == 0 and "WORST" in r.stdout, r.stdout[-1500:]
 
 
+def test_amr_poisson_matrix_distributed_over_three_ranks_emulated(emulated_library):
+    """cup2d_poisson_create_general_ranks: the Poisson matrix of the reference's 7-level run.sh mesh (neighbour table +
+    coarse-fine rows from the library's plan) distributed over three ranks by block ranges, the ranks running as threads of one
+    process: remote blocks named by either table become halo slots refreshed by peer pulls, the Krylov kernels are the
+    uniform path's.  8 iterations against the same solve on one rank."""
+    code = r'''
+import sys, threading, numpy as np
+sys.path.insert(0, %r)
+from cup2d_b200.amr import AmrPlan, DistributedPoisson
+d = np.load(%r)
+blocks = np.ascontiguousarray(d["blocks"], dtype=np.int32)
+nb = len(blocks)
+nbr, rows, rowptr, col, val = AmrPlan(blocks, int(d["bpdx"]), int(d["bpdy"])).poisson()
+rng = np.random.default_rng(7)
+b, x0 = rng.uniform(-1, 1, (nb, 64)), rng.uniform(-0.1, 0.1, (nb, 64))
+one = DistributedPoisson(nbr, rows, rowptr, col, val, [0, nb], 0); one.attach_peers()
+xs, its, errs_ = one.solve(b, x0, max_iter=8); one.close()
+W, rb = 3, [0, 90, 190, nb]
+bar, slots, res, errs = threading.Barrier(W), [None] * W, [None] * W, []
+class Dist:
+    def __init__(self, rank): self.rank = rank
+    def all_gather_object(self, out, obj):
+        slots[self.rank] = obj; bar.wait(); out[:] = slots; bar.wait()
+    def barrier(self): bar.wait()
+def run(rank):
+    try:
+        p = DistributedPoisson(nbr, rows, rowptr, col, val, rb, rank)
+        p.attach_peers(Dist(rank))
+        res[rank] = p.solve(b[rb[rank]:rb[rank + 1]], x0[rb[rank]:rb[rank + 1]], max_iter=8)
+        bar.wait(); p.close()
+    except Exception as e:
+        errs.append(repr(e)); bar.abort()
+ths = [threading.Thread(target=run, args=(r,)) for r in range(W)]
+[t.start() for t in ths]; [t.join() for t in ths]
+assert not errs, errs
+x = np.concatenate([r[0] for r in res])
+worst = np.abs(x - xs).max() / np.abs(xs).max()
+print("WORST", worst, [r[1] for r in res], its)
+assert worst < 1e-10 and all(r[1] == 8 for r in res) and its == 8 and abs(res[0][2] - errs_) < 1e-10
+''' % (ROOT, os.path.join(ROOT, "tests", "golden", "amrlab_lmax8.npz"))
+    r = subprocess.run([sys.executable, "-c", code], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900,
+                       env=dict(os.environ, CUP2D_B200_LIB=emulated_library))
+    assert r.returncode == 0 and "WORST" in r.stdout, r.stdout[-1500:]
+
+
 def test_no_data_races_under_thread_sanitizer():
     """race hunt: the emulated product sources rebuilt with -fsanitize=thread run a uniform-grid time step (advect with its
     staged loads, pressure kernels, the Krylov kernels with their grid reductions, the chi-mask tags) and the multi-level step

@@ -124,5 +124,32 @@ if rank == 0:
     print(json.dumps({"check": "penalisation", "ranks": world, "integrals_rel_err": pen_err, "blend_udef_bit_exact": bool(pen_exact)}), flush=True)
 assert pen_err < 1e-12 and pen_exact
 sim.close()
+
+# ---- the Poisson matrix of the reference's 7-level run.sh mesh (neighbour table + coarse-fine rows from the plan),
+#      distributed over the ranks by block ranges, vs the same solve on one GPU (rank 0) ----
+from cup2d_b200.amr import AmrPlan, DistributedPoisson
+g = np.load(os.path.join(ROOT, "tests", "golden", "amrlab_lmax8.npz"))
+blocks = np.ascontiguousarray(g["blocks"], dtype=np.int32)
+nb = len(blocks)
+plan = AmrPlan(blocks, int(g["bpdx"]), int(g["bpdy"]))
+nbr, rows, rowptr, col, val = plan.poisson()
+rb = [round(r * nb / world) for r in range(world + 1)]
+rng = np.random.default_rng(7)
+b, x0 = rng.uniform(-1, 1, (nb, 64)), rng.uniform(-0.1, 0.1, (nb, 64))
+dp = DistributedPoisson(nbr, rows, rowptr, col, val, rb, rank, device=lrank)
+dp.attach_peers(dist)
+xr, it, err = dp.solve(b[rb[rank]:rb[rank + 1]], x0[rb[rank]:rb[rank + 1]], max_iter=12)
+parts = [None] * world
+dist.all_gather_object(parts, xr)
+dist.barrier()
+dp.close()
+if rank == 0:
+    one = DistributedPoisson(nbr, rows, rowptr, col, val, [0, nb], 0, device=lrank)
+    one.attach_peers()
+    xs, its, errs = one.solve(b, x0, max_iter=12)
+    one.close()
+    amr_err = float(np.abs(np.concatenate(parts) - xs).max() / np.abs(xs).max())
+    print(json.dumps({"check": "amr_poisson_ranks", "ranks": world, "iters": it, "rel_err_vs_one_gpu": amr_err, "err": err, "err_one_gpu": errs}), flush=True)
+    assert it == its == 12 and amr_err < 1e-9
 dist.barrier()
 dist.destroy_process_group()
