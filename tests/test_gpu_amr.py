@@ -1,8 +1,11 @@
-"""GPU tests of the first multi-level device path (csrc/amr_ops.cu) against the reference's own flux-corrected operator
-outputs on its 7-level run.sh mesh (tests/golden/amrlab_lmax8.npz).
+"""GPU tests of the multi-level device path (csrc/amr_ops.cu baseline kernels, csrc/amr_fast.cu, csrc/amr_penalize.cu, the
+tagging of cup2d_amr_adapt_tags) against the reference's own outputs on its 7-level run.sh mesh (tests/golden/amrlab_lmax8.npz,
+amrtags_lmax8.npz), against the reference restatement on a second mesh family, and in situ (the reference's run.sh case
+with its hot path spliced onto this path).
 
 This path was written after round 1's GPU budget was spent and has NOT been run on hardware yet: the tests are skipped
-unless CUP2D_TEST_UNVALIDATED=1, so that the suite reports only what has actually been validated."""
+unless CUP2D_TEST_UNVALIDATED=1, so that the suite reports only what has actually been validated.  All of them pass on
+the CPU against the emulated build of the same sources (tools/run_emulated_gpu_tests.sh, tests/test_full_emulation.py)."""
 import os
 
 import numpy as np
@@ -10,7 +13,7 @@ import pytest
 
 pytestmark = [pytest.mark.gpu,
               pytest.mark.skipif(os.environ.get("CUP2D_TEST_UNVALIDATED") != "1",
-                                 reason="csrc/amr_ops.cu has not been run on hardware yet (set CUP2D_TEST_UNVALIDATED=1)")]
+                                 reason="the multi-level device path has not been run on hardware yet (set CUP2D_TEST_UNVALIDATED=1)")]
 
 
 @pytest.fixture(scope="module")
