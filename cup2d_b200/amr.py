@@ -160,6 +160,24 @@ class AmrSimulation:
                                          C.byref(err)))
         return dto.value, it.value, err.value
 
+    def set_ranks(self, rank, rank_begin, dist=None):
+        """several GPUs, first form: this context (whole mesh, operators replicated) solves its Poisson problem together with
+        the other ranks, each owning the block range rank_begin[r]..rank_begin[r+1]; `dist` carries the peer blobs"""
+        rb = np.ascontiguousarray(rank_begin, dtype=np.int64)
+        nranks = len(rb) - 1
+        _l.check(self.lib.cup2d_amr_set_ranks(self._h, int(rank), nranks, rb.ctypes.data_as(C.POINTER(C.c_int64))))
+        n = self.lib.cup2d_peer_blob_size()
+        blob = (C.c_ubyte * n)()
+        _l.check(self.lib.cup2d_amr_peer_export(self._h, blob))
+        gathered = [bytes(blob)]
+        if nranks > 1:
+            gathered = [None] * nranks
+            dist.all_gather_object(gathered, bytes(blob))
+        allb = b"".join(gathered)
+        _l.check(self.lib.cup2d_amr_peer_attach(self._h, (C.c_ubyte * len(allb)).from_buffer_copy(allb)))
+        if dist is not None and nranks > 1:
+            dist.barrier()
+
     def adapt_tags(self, rtol, level_max):
         """per-block L-inf of adapt()'s tagging field (vorticity + the chi rule); the field itself is left in tmp"""
         out = np.empty(len(self.blocks))

@@ -60,6 +60,9 @@ struct cup2d_amr {
   std::vector<double> h_part;
   double hmin = 0;
   cup2d_sim *poisson = nullptr;     // general-rows Poisson context over the same blocks (cup2d_amr_poisson_solve)
+  // several GPUs (cup2d_amr_set_ranks): operators replicated on every rank, the Poisson solve distributed by block ranges
+  int rank = 0, nranks = 1;
+  std::vector<int64_t> rank_begin;
   // fast paths (csrc/amr_fast.cu)
   bool fast = false;                // cup2d_amr_set_fast: the operator entry points dispatch to the fast kernels
   int *d_nbr4 = nullptr;            // [nb][4] W,E,S,N: same-level block, -1 wall, -2 coarser/finer

@@ -580,6 +580,82 @@ int cup2d_amr_pressure_correct(cup2d_amr *a, double dt) {
 }
 
 #ifndef CUP2D_AMR_EMU
+/* Several GPUs, first form: every rank holds the whole mesh and computes the stencil operators redundantly (bitwise the same
+ * everywhere), the Poisson solve — the part that dominates a step — is distributed over the ranks by block ranges
+ * (cup2d_poisson_create_general_ranks) and its result all-gathered over NVLink.  rank_begin[nranks+1] partitions the block
+ * list.  Then cup2d_amr_peer_export / cup2d_amr_peer_attach like the cup2d_peer_* pair. */
+int cup2d_amr_set_ranks(cup2d_amr *a, int32_t rank, int32_t nranks, const int64_t *rank_begin) {
+  CHECK_AMR(a);
+  if (a->poisson || !rank_begin || nranks < 1 || rank < 0 || rank >= nranks || rank_begin[0] != 0 || rank_begin[nranks] != a->nb) {
+    set_error("cup2d_amr_set_ranks: bad arguments (or called after the first solve)");
+    return CUP2D_EINVAL;
+  }
+  CUP2D_CUDA(cudaSetDevice(a->device));
+  int64_t nnz = 0;
+  const int64_t nr = cup2d_amr_plan_poisson(a->plan, nullptr, &nnz, nullptr, nullptr, nullptr, nullptr);
+  if (nr < 0) return (int)nr;
+  std::vector<int32_t> nbr(4 * a->nb), rows(std::max<int64_t>(nr, 1)), rowptr(nr + 1), col(std::max<int64_t>(nnz, 1));
+  std::vector<double> val(std::max<int64_t>(nnz, 1));
+  cup2d_amr_plan_poisson(a->plan, nbr.data(), &nnz, rows.data(), rowptr.data(), col.data(), val.data());
+  const int64_t b0 = rank_begin[rank], b1 = rank_begin[rank + 1];
+  const int64_t k0 = std::lower_bound(rows.begin(), rows.begin() + nr, (int32_t)(64 * b0)) - rows.begin();
+  const int64_t k1 = std::lower_bound(rows.begin(), rows.begin() + nr, (int32_t)(64 * b1)) - rows.begin();
+  std::vector<int32_t> my_rows(rows.begin() + k0, rows.begin() + k1), my_ptr(rowptr.begin() + k0, rowptr.begin() + k1 + 1);
+  for (auto &r : my_rows) r -= (int32_t)(64 * b0);
+  const int32_t e0 = my_ptr[0];
+  for (auto &e : my_ptr) e -= e0;
+  int rc = cup2d_poisson_create_general_ranks(a->nb, rank, nranks, rank_begin, nbr.data() + 4 * b0, k1 - k0, my_rows.data(),
+                                              my_ptr.data(), col.data() + e0, val.data() + e0, a->device, &a->poisson);
+  if (rc) return rc;
+  a->rank = rank;
+  a->nranks = nranks;
+  a->rank_begin.assign(rank_begin, rank_begin + nranks + 1);
+  return CUP2D_OK;
+}
+int cup2d_amr_peer_export(cup2d_amr *a, void *blob) {
+  CHECK_AMR(a);
+  if (!a->poisson) {
+    set_error("cup2d_amr_peer_export: call cup2d_amr_set_ranks first");
+    return CUP2D_ESTATE;
+  }
+  return cup2d_peer_export(a->poisson, blob);
+}
+int cup2d_amr_peer_attach(cup2d_amr *a, const void *all_blobs) {
+  CHECK_AMR(a);
+  if (!a->poisson) {
+    set_error("cup2d_amr_peer_attach: call cup2d_amr_set_ranks first");
+    return CUP2D_ESTATE;
+  }
+  return cup2d_peer_attach(a->poisson, all_blobs);
+}
+
+static int poisson_solve_distributed(cup2d_amr *a, double tol_abs, double tol_rel, int max_restarts, int max_iter, int *iters,
+                                     double *err) {
+  const int64_t b0 = a->rank_begin[a->rank], nloc = a->rank_begin[a->rank + 1] - b0;
+  const size_t bytes = (size_t)nloc * 64 * sizeof(double);
+  CUP2D_CUDA(cudaStreamSynchronize(a->stream));
+  cudaStream_t ps = (cudaStream_t)cup2d_stream(a->poisson);
+  // this rank's rows of the right-hand side and of the initial guess (every rank computed the whole of both)
+  CUP2D_CUDA(cudaMemcpyAsync(cup2d_field_device_ptr(a->poisson, CUP2D_TMP), a->f[CUP2D_TMP] + b0 * 64, bytes, cudaMemcpyDeviceToDevice, ps));
+  CUP2D_CUDA(cudaMemcpyAsync(cup2d_field_device_ptr(a->poisson, CUP2D_PRES), a->f[CUP2D_PRES] + b0 * 64, bytes, cudaMemcpyDeviceToDevice, ps));
+  int rc = cup2d_poisson_solve(a->poisson, tol_abs, tol_rel, max_restarts, max_iter, iters, err);
+  // all-gather of the solution: a halo refresh is a barrier (every rank's pressure is final when it returns), then every
+  // rank copies the others' rows straight out of their arrays over NVLink; a second barrier before anyone overwrites them
+  if (rc || (rc = cup2d_halo_exchange(a->poisson, CUP2D_PRES))) return rc;
+  for (int r = 0; r < a->nranks; r++) {
+    const double *src = static_cast<const double *>(cup2d_peer_field_ptr(a->poisson, r, CUP2D_PRES));
+    if (!src) {
+      set_error("cup2d_amr_poisson_solve: peers not attached");
+      return CUP2D_ESTATE;
+    }
+    CUP2D_CUDA(cudaMemcpyAsync(a->f[CUP2D_PRES] + a->rank_begin[r] * 64, src, (size_t)(a->rank_begin[r + 1] - a->rank_begin[r]) * 64 * sizeof(double),
+                               cudaMemcpyDeviceToDevice, ps));
+  }
+  if ((rc = cup2d_halo_exchange(a->poisson, CUP2D_PRES))) return rc;
+  CUP2D_CUDA(cudaStreamSynchronize(ps));
+  return CUP2D_OK;
+}
+
 /* the Poisson solve of the step: b = tmp, x0 = pres -> pres, on the general-rows solver (csrc/poisson.cu) with the
  * rows of cup2d_amr_plan_poisson; same stopping parameters as cup2d_poisson_solve */
 int cup2d_amr_poisson_solve(cup2d_amr *a, double tol_abs, double tol_rel, int max_restarts, int max_iter, int *iters,
@@ -598,6 +674,7 @@ int cup2d_amr_poisson_solve(cup2d_amr *a, double tol_abs, double tol_rel, int ma
                                            &a->poisson)))
       return rc;
   }
+  if (a->nranks > 1) return poisson_solve_distributed(a, tol_abs, tol_rel, max_restarts, max_iter, iters, err);
   const size_t bytes = (size_t)a->nb * 64 * sizeof(double);
   CUP2D_CUDA(cudaStreamSynchronize(a->stream));
   cudaStream_t ps = (cudaStream_t)cup2d_stream(a->poisson);

@@ -163,6 +163,12 @@ int cup2d_peer_attach(cup2d_sim *s, const void *all_blobs) {
   return CUP2D_OK;
 }
 
+/* device address of `field` on rank `rank` as mapped into this process (this rank: its own array); null before attach */
+void *cup2d_peer_field_ptr(cup2d_sim *s, int rank, int field) {
+  if (!s || rank < 0 || rank >= s->nranks || field < 0 || field >= CUP2D_NFIELDS || !s->peers_attached) return nullptr;
+  return s->nranks == 1 ? (void *)s->f[field] : s->peer_base[rank][field];
+}
+
 int cup2d_halo_exchange(cup2d_sim *s, int field) {
   if (!s || field < 0 || field >= CUP2D_NFIELDS) {
     set_error("cup2d_halo_exchange: bad argument");

@@ -166,6 +166,8 @@ int cup2d_peer_export(cup2d_sim *s, void *blob);
 int cup2d_peer_attach(cup2d_sim *s, const void *all_blobs);
 /* Explicit halo refresh of one field (normally implicit inside the operators). */
 int cup2d_halo_exchange(cup2d_sim *s, int field);
+/* Device address of `field` on rank `rank` as mapped into this process by cup2d_peer_attach (NULL before). */
+void *cup2d_peer_field_ptr(cup2d_sim *s, int rank, int field);
 
 /* ---- Poisson-only context (the LocalSpMatDnVec boundary, cuda.h:26-79) ---- */
 /* nbr[4*k..4*k+3] = block indices of the W,E,S,N neighbours of block k on the same level, -1 = wall
@@ -290,6 +292,14 @@ int cup2d_amr_poisson_solve(cup2d_amr *a, double tol_abs, double tol_rel, int ma
 int cup2d_amr_pressure_correct(cup2d_amr *a, double dt);
 int cup2d_amr_step(cup2d_amr *a, double cfl, double dt_in, double tol_abs, double tol_rel, int max_restarts, int max_iter,
                    double *dt_out, int *iters, double *err);
+
+/* Several GPUs (first form): every rank creates the context over the WHOLE mesh and computes the stencil operators
+ * redundantly — bitwise the same on every rank — while the Poisson solve is distributed over the ranks by the block ranges
+ * rank_begin[nranks+1] (cup2d_poisson_create_general_ranks) and its solution all-gathered over NVLink.  Call once, before the
+ * first solve, then exchange the peer blobs exactly like cup2d_peer_export / cup2d_peer_attach. */
+int cup2d_amr_set_ranks(cup2d_amr *a, int32_t rank, int32_t nranks, const int64_t *rank_begin);
+int cup2d_amr_peer_export(cup2d_amr *a, void *blob);
+int cup2d_amr_peer_attach(cup2d_amr *a, const void *all_blobs);
 
 /* adapt()'s tagging on a multi-level mesh (main.cpp:4676-4697; cf. cup2d_adapt_tags): block_linf_out[k] = L-inf over block
  * k of the field adapt() thresholds against Rtol / Ctol — the vorticity of vel (KernelVorticity, 3343-3366), with 2*rtol in

@@ -144,6 +144,61 @@ assert worst < 1e-10 and all(r[1] == 8 for r in res) and its == 8 and abs(res[0]
     assert r.returncode == 0 and "WORST" in r.stdout, r.stdout[-1500:]
 
 
+def test_multi_level_steps_on_two_ranks_emulated(emulated_library):
+    """several GPUs on a multi-level mesh, first form (cup2d_amr_set_ranks): every rank holds the whole mesh and computes the
+    stencil operators redundantly, the Poisson solve is distributed by block ranges and all-gathered through the peers' arrays.
+    Two ranks as threads of one process, 2 steps x 6 iterations on a three-level mesh: both ranks bitwise identical, and equal
+    to the one-rank run to rounding."""
+    code = r'''
+import sys, threading, numpy as np
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+import bench_amr
+from cup2d_b200.amr import AmrSimulation
+blocks = bench_amr.three_level_mesh(3, r1=0.3, r2=0.15, centre=(0.45, 0.55))
+nb, h0, nu = len(blocks), 1 / 8, 1e-3
+rng = np.random.default_rng(3)
+vel, pres = bench_amr.seeded_fields(blocks, h0)
+vel, pres = vel + 0.05 * rng.uniform(-1, 1, vel.shape), pres + 0.05 * rng.uniform(-1, 1, pres.shape)
+def steps(sim):
+    out = []
+    sim.set_fast(True); sim.upload("vel", vel); sim.upload("pres", pres)
+    for s in range(2):
+        info = sim.step(cfl=0.5, max_iter=6)
+        out.append((info, sim.download("vel"), sim.download("pres")))
+    return out
+one = AmrSimulation(blocks, 1, 1, h0, nu); ref = steps(one); one.close()
+W = 2
+rb = [0, nb // 2 + 7, nb]
+bar, slots, res, errs = threading.Barrier(W), [None] * W, [None] * W, []
+class Dist:
+    def __init__(self, rank): self.rank = rank
+    def all_gather_object(self, out, obj):
+        slots[self.rank] = obj; bar.wait(); out[:] = slots; bar.wait()
+    def barrier(self): bar.wait()
+def run(rank):
+    try:
+        sim = AmrSimulation(blocks, 1, 1, h0, nu)
+        sim.set_ranks(rank, rb, Dist(rank))
+        res[rank] = steps(sim)
+        bar.wait(); sim.close()
+    except Exception as e:
+        errs.append(repr(e)); bar.abort()
+ths = [threading.Thread(target=run, args=(r,)) for r in range(W)]
+[t.start() for t in ths]; [t.join() for t in ths]
+assert not errs, errs
+worst = 0.0
+for s in range(2):
+    assert np.array_equal(res[0][s][1], res[1][s][1]) and np.array_equal(res[0][s][2], res[1][s][2]) and res[0][s][0] == res[1][s][0]
+    worst = max(worst, np.abs(res[0][s][1] - ref[s][1]).max() / np.abs(ref[s][1]).max(),
+                np.abs(res[0][s][2] - ref[s][2]).max() / np.abs(ref[s][2]).max(), abs(res[0][s][0][0] - ref[s][0][0]))
+print("WORST", worst)
+assert worst < 1e-11
+''' % (ROOT, os.path.join(ROOT, "tools"))
+    r = subprocess.run([sys.executable, "-c", code], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900,
+                       env=dict(os.environ, CUP2D_B200_LIB=emulated_library))
+    assert r.returncode == 0 and "WORST" in r.stdout, r.stdout[-1500:]
+
+
 def test_no_data_races_under_thread_sanitizer():
     """race hunt: the emulated product sources rebuilt with -fsanitize=thread run a uniform-grid time step (advect with its
     staged loads, pressure kernels, the Krylov kernels with their grid reductions, the chi-mask tags) and the multi-level step

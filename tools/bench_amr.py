@@ -2,7 +2,8 @@
 reference grows for its run.sh case (config C5 of SURVEY 8(d) at the chosen levelMax).
 
   python tools/bench_amr.py [levelMax=9] [steps=10] [poisson_iters=10] [fast=1]
-  python tools/bench_amr.py synthetic [base_level=9] [steps=10] [poisson_iters=10] [fast=1]     (config C5: 3 levels)
+  python tools/bench_amr.py synthetic [base_level=9] [steps=10] [poisson_iters=10] [fast=1]     (config C5: 3 levels;
+      under torchrun on N GPUs: operators replicated, Poisson solve distributed)
 
 The mesh comes from oracle/_ref/ref_harness amrlab (which travels to the GPU box prebuilt), the fields are its seeded ones,
 bodies are left out (u_def = 0, chi = 0).  Prints one JSON line: blocks, cells, levels, ms per step with CUDA events on the
@@ -101,14 +102,29 @@ def main():
         blocks = three_level_mesh(base)
         h0 = 1.0 / 8
         vel, pres = seeded_fields(blocks, h0)
+        world, rank, lrank = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
         t0 = time.time()
-        sim = AmrSimulation(blocks, 1, 1, h0, 1e-4)
+        sim = AmrSimulation(blocks, 1, 1, h0, 1e-4, device=lrank)
+        if world > 1:   # under torchrun: operators replicated, Poisson solve distributed over the ranks (cup2d_amr_set_ranks)
+            import torch
+            import torch.distributed as dist
+            torch.cuda.set_device(lrank)
+            dist.init_process_group("nccl", device_id=torch.device("cuda", lrank))
+            sim.set_ranks(rank, [round(r * len(blocks) / world) for r in range(world + 1)], dist)
         sim.set_fast(bool(fast))
         sim.upload("vel", vel)
         sim.upload("pres", pres)
         sim.step(cfl=0.5, max_iter=1)          # first step builds the compact tables and the Poisson rows
         t_create = time.time() - t0
-        run(sim, len(blocks), blocks, steps, K, f"synthetic 3-level mesh, base level {base} ({8 << (base + 2)}^2 effective)", t_create, fast)
+        label = f"synthetic 3-level mesh, base level {base} ({8 << (base + 2)}^2 effective), {world} GPU(s)"
+        if rank == 0:
+            run(sim, len(blocks), blocks, steps, K, label, t_create, fast)
+        else:           # same calls, no report (every step synchronises the ranks inside the solve)
+            for _ in range(3 + steps):
+                sim.step(cfl=0.5, max_iter=K)
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
         sim.close()
         return
     lmax = int(sys.argv[1]) if len(sys.argv) > 1 else 9

@@ -151,5 +151,44 @@ if rank == 0:
     amr_err = float(np.abs(np.concatenate(parts) - xs).max() / np.abs(xs).max())
     print(json.dumps({"check": "amr_poisson_ranks", "ranks": world, "iters": it, "rel_err_vs_one_gpu": amr_err, "err": err, "err_one_gpu": errs}), flush=True)
     assert it == its == 12 and amr_err < 1e-9
+
+# ---- multi-level time steps on several GPUs (cup2d_amr_set_ranks: operators replicated, Poisson solve distributed) vs the
+#      same steps on one GPU ----
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+import bench_amr
+from cup2d_b200.amr import AmrSimulation
+mblocks = bench_amr.three_level_mesh(4, r1=0.3, r2=0.15, centre=(0.45, 0.55))
+mnb, mh0 = len(mblocks), 1 / 8
+mvel, mpres = bench_amr.seeded_fields(mblocks, mh0)
+
+
+def amr_steps(sim):
+    out = []
+    sim.set_fast(True)
+    sim.upload("vel", mvel)
+    sim.upload("pres", mpres)
+    for _ in range(2):
+        info = sim.step(cfl=0.5, max_iter=10)
+        out.append((info, sim.download("vel"), sim.download("pres")))
+    return out
+
+
+asim = AmrSimulation(mblocks, 1, 1, mh0, 1e-3, device=lrank)
+asim.set_ranks(rank, [round(r * mnb / world) for r in range(world + 1)], dist)
+got = amr_steps(asim)
+dist.barrier()
+asim.close()
+allgot = [None] * world
+dist.all_gather_object(allgot, [(g[0], float(np.abs(g[1]).sum()), float(np.abs(g[2]).sum())) for g in got])
+if rank == 0:
+    one = AmrSimulation(mblocks, 1, 1, mh0, 1e-3, device=lrank)
+    ref = amr_steps(one)
+    one.close()
+    amr_step_err = max(max(float(np.abs(g[1] - r[1]).max() / np.abs(r[1]).max()), float(np.abs(g[2] - r[2]).max() / np.abs(r[2]).max()))
+                       for g, r in zip(got, ref))
+    same = all(a == allgot[0] for a in allgot)
+    print(json.dumps({"check": "amr_step_ranks", "ranks": world, "blocks": mnb, "rel_err_vs_one_gpu": amr_step_err,
+                      "ranks_identical": bool(same)}), flush=True)
+    assert amr_step_err < 1e-9 and same
 dist.barrier()
 dist.destroy_process_group()
