@@ -99,6 +99,8 @@ assert worst < 1e-12
     assert r.returncode == 0 and "WORST" in r.stdout, r.stdout[-1500:]
 
 
+@pytest.mark.skipif(os.environ.get("CUP2D_TEST_SLOW") != "1",
+                    reason="35 s; test_multi_level_steps_on_three_ranks_emulated runs the same constructor inside whole time steps")
 def test_amr_poisson_matrix_distributed_over_three_ranks_emulated(emulated_library):
     """cup2d_poisson_create_general_ranks: the Poisson matrix of the reference's 7-level run.sh mesh (neighbour table +
     coarse-fine rows from the library's plan) distributed over three ranks by block ranges, the ranks running as threads of one
@@ -144,11 +146,11 @@ assert worst < 1e-10 and all(r[1] == 8 for r in res) and its == 8 and abs(res[0]
     assert r.returncode == 0 and "WORST" in r.stdout, r.stdout[-1500:]
 
 
-def test_multi_level_steps_on_two_ranks_emulated(emulated_library):
+def test_multi_level_steps_on_three_ranks_emulated(emulated_library):
     """several GPUs on a multi-level mesh, first form (cup2d_amr_set_ranks): every rank holds the whole mesh and computes the
     stencil operators redundantly, the Poisson solve is distributed by block ranges and all-gathered through the peers' arrays.
-    Two ranks as threads of one process, 2 steps x 6 iterations on a three-level mesh: both ranks bitwise identical, and equal
-    to the one-rank run to rounding."""
+    Three ranks (uneven block ranges) as threads of one process, 2 steps x 5 iterations on a three-level mesh: all ranks
+    bitwise identical, and equal to the one-rank run to rounding."""
     code = r'''
 import sys, threading, numpy as np
 sys.path.insert(0, %r); sys.path.insert(0, %r)
@@ -163,12 +165,12 @@ def steps(sim):
     out = []
     sim.set_fast(True); sim.upload("vel", vel); sim.upload("pres", pres)
     for s in range(2):
-        info = sim.step(cfl=0.5, max_iter=6)
+        info = sim.step(cfl=0.5, max_iter=5)
         out.append((info, sim.download("vel"), sim.download("pres")))
     return out
 one = AmrSimulation(blocks, 1, 1, h0, nu); ref = steps(one); one.close()
-W = 2
-rb = [0, nb // 2 + 7, nb]
+W = 3
+rb = [0, nb // 3 + 7, 2 * nb // 3 - 5, nb]
 bar, slots, res, errs = threading.Barrier(W), [None] * W, [None] * W, []
 class Dist:
     def __init__(self, rank): self.rank = rank
@@ -188,7 +190,7 @@ ths = [threading.Thread(target=run, args=(r,)) for r in range(W)]
 assert not errs, errs
 worst = 0.0
 for s in range(2):
-    assert np.array_equal(res[0][s][1], res[1][s][1]) and np.array_equal(res[0][s][2], res[1][s][2]) and res[0][s][0] == res[1][s][0]
+    assert all(np.array_equal(res[0][s][1], res[r][s][1]) and np.array_equal(res[0][s][2], res[r][s][2]) and res[0][s][0] == res[r][s][0] for r in range(W))
     worst = max(worst, np.abs(res[0][s][1] - ref[s][1]).max() / np.abs(ref[s][1]).max(),
                 np.abs(res[0][s][2] - ref[s][2]).max() / np.abs(ref[s][2]).max(), abs(res[0][s][0][0] - ref[s][0][0]))
 print("WORST", worst)
