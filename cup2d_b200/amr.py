@@ -1,6 +1,7 @@
 """ctypes view of the host-side AMR ghost-stencil plan (cup2d_amr_plan_*, include/cup2d_b200.h).  No compute here:
 the tables are built by the C++ library; this only hands them out as numpy arrays."""
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -177,6 +178,10 @@ class AmrSimulation:
         _l.check(self.lib.cup2d_amr_peer_attach(self._h, (C.c_ubyte * len(allb)).from_buffer_copy(allb)))
         if dist is not None and nranks > 1:
             dist.barrier()
+
+    def dump(self, time, path):
+        """path.xdmf2 / .xyz.raw / .attr.raw of the velocity, the reference's dump() files"""
+        _l.check(self.lib.cup2d_amr_dump(self._h, float(time), os.fsencode(path)))
 
     def adapt_tags(self, rtol, level_max):
         """per-block L-inf of adapt()'s tagging field (vorticity + the chi rule); the field itself is left in tmp"""

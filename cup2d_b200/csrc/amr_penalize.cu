@@ -12,6 +12,9 @@
 #include "sim.h"
 #include "amr.h"
 #include <algorithm>
+#include <fcntl.h>
+#include <string>
+#include <unistd.h>
 
 #define CUP2D_REQUIRE(cond, msg)                                                                  \
   do {                                                                                            \
@@ -104,6 +107,27 @@ amr_udef_add_kernel(AmrShapeView sh, double *__restrict__ tmpv, const double *__
     t.x += ud.x;
     t.y += ud.y;
     *tp = t;
+  }
+}
+
+// dump() on a multi-level mesh (main.cpp:3425-3453): as dump_pack_kernel (regrid.cu) with the block's own cell size
+__global__ void __launch_bounds__(256)
+amr_dump_pack_kernel(const double *__restrict__ vel, const int2 *__restrict__ ij, const double *__restrict__ hb, int b0, int nb,
+                     float4 *__restrict__ xyz, float *__restrict__ attr) {
+  const size_t ncell = (size_t)nb * 64;
+  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < ncell; i += (size_t)gridDim.x * 256) {
+    const int k = (int)(i >> 6), x = (int)(i & 7), y = (int)((i >> 3) & 7);
+    const int2 b = ij[b0 + k];
+    const double h = hb[b0 + k];
+    const double u0 = __dadd_rn(__dmul_rn((double)(b.x * CUP2D_BS), h), __dmul_rn(h, (double)x));
+    const double v0 = __dadd_rn(__dmul_rn((double)(b.y * CUP2D_BS), h), __dmul_rn(h, (double)y));
+    const float fu0 = (float)u0, fv0 = (float)v0, fu1 = (float)__dadd_rn(u0, h), fv1 = (float)__dadd_rn(v0, h);
+    xyz[2 * i] = make_float4(fu0, fv0, fu0, fv1);
+    xyz[2 * i + 1] = make_float4(fu1, fv1, fu1, fv0);
+    const double2 q = reinterpret_cast<const double2 *>(vel)[(size_t)(b0 + k) * 64 + (i & 63)];
+    attr[3 * i] = (float)q.x;
+    attr[3 * i + 1] = (float)q.y;
+    attr[3 * i + 2] = 0.0f;
   }
 }
 
@@ -208,6 +232,52 @@ int cup2d_amr_udef_assemble(cup2d_amr *a) {
   }
   CUP2D_CUDA(cudaGetLastError());
   return CUP2D_OK;
+}
+
+/* dump() of the velocity on a multi-level mesh (main.cpp:3367-3467): path.xdmf2 / .xyz.raw / .attr.raw, the reference's
+ * three files byte for byte (float32 cell quads + (u, v, 0) in block order) */
+int cup2d_amr_dump(cup2d_amr *a, double time, const char *path) {
+  CUP2D_REQUIRE(a != nullptr && path && *path, "cup2d_amr_dump: bad arguments");
+  CUP2D_CUDA(cudaSetDevice(a->device));
+  int rc = ensure_ij(a);
+  if (rc) return rc;
+  const std::string base(path);
+  const std::string xyz_path = base + ".xyz.raw", attr_path = base + ".attr.raw", xdmf_path = base + ".xdmf2";
+  if ((rc = dump_write_xdmf(xdmf_path, xyz_path, attr_path, time, (long)a->nb * 64))) return rc;
+  const int CHUNK = (int)std::min<int64_t>(a->nb, 16384);
+  const size_t nx = (size_t)CHUNK * 64 * 8, na = (size_t)CHUNK * 64 * 3;
+  float *d_buf = nullptr, *h_buf = nullptr;
+  CUP2D_CUDA(cudaMalloc(&d_buf, (nx + na) * sizeof(float)));
+  if (cudaMallocHost(&h_buf, (nx + na) * sizeof(float)) != cudaSuccess) {
+    cudaFree(d_buf);
+    set_error("cup2d_amr_dump: cannot allocate the pinned staging buffer");
+    return CUP2D_ECUDA;
+  }
+  const int fx = open(xyz_path.c_str(), O_CREAT | O_WRONLY | O_TRUNC, 0644), fa = open(attr_path.c_str(), O_CREAT | O_WRONLY | O_TRUNC, 0644);
+  rc = (fx < 0 || fa < 0) ? CUP2D_EINVAL : CUP2D_OK;
+  for (int64_t b0 = 0; rc == CUP2D_OK && b0 < a->nb; b0 += CHUNK) {
+    const int nb = (int)std::min<int64_t>(CHUNK, a->nb - b0);
+    const size_t ncell = (size_t)nb * 64;
+    amr_dump_pack_kernel<<<(int)std::min<size_t>((ncell + 255) / 256, 148 * 8), 256, 0, a->stream>>>(
+        a->f[CUP2D_VEL], reinterpret_cast<const int2 *>(a->d_ij), a->d_h, (int)b0, nb, reinterpret_cast<float4 *>(d_buf), d_buf + nx);
+    cudaMemcpyAsync(h_buf, d_buf, ncell * 8 * sizeof(float), cudaMemcpyDeviceToHost, a->stream);
+    cudaMemcpyAsync(h_buf + nx, d_buf + nx, ncell * 3 * sizeof(float), cudaMemcpyDeviceToHost, a->stream);
+    if (cudaStreamSynchronize(a->stream) != cudaSuccess) {
+      rc = CUP2D_ECUDA;
+      break;
+    }
+    const off_t cell0 = (off_t)b0 * 64;
+    if (dump_write_all(fx, h_buf, ncell * 8 * sizeof(float), cell0 * 8 * (off_t)sizeof(float)) ||
+        dump_write_all(fa, h_buf + nx, ncell * 3 * sizeof(float), cell0 * 3 * (off_t)sizeof(float)))
+      rc = CUP2D_EINVAL;
+  }
+  if (fx >= 0) close(fx);
+  if (fa >= 0) close(fa);
+  cudaFreeHost(h_buf);
+  cudaFree(d_buf);
+  if (rc == CUP2D_EINVAL) set_error("cup2d_amr_dump: cannot write " + xyz_path + " / " + attr_path);
+  if (rc == CUP2D_ECUDA) set_error(std::string("cup2d_amr_dump: ") + cudaGetErrorString(cudaGetLastError()));
+  return rc;
 }
 
 } // extern "C"

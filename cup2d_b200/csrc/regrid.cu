@@ -202,7 +202,7 @@ dump_pack_kernel(const double *__restrict__ vel, const int2 *__restrict__ ij, do
   }
 }
 
-static int write_all(int fd, const void *buf, size_t n, off_t off) {
+int dump_write_all(int fd, const void *buf, size_t n, off_t off) {
   const char *p = static_cast<const char *>(buf);
   while (n > 0) {
     const ssize_t w = pwrite(fd, p, n, off);
@@ -214,33 +214,39 @@ static int write_all(int fd, const void *buf, size_t n, off_t off) {
   return 0;
 }
 
-int dump_fields(cup2d_sim *s, double time, const char *path) {
-  const std::string base(path);
-  const std::string xyz_path = base + ".xyz.raw", attr_path = base + ".attr.raw", xdmf_path = base + ".xdmf2";
+// the .xdmf2 descriptor of dump() (main.cpp:3380-3423), byte for byte
+int dump_write_xdmf(const std::string &xdmf_path, const std::string &xyz_path, const std::string &attr_path, double time,
+                    long ncell_total) {
   auto basename_of = [](const std::string &p) { // main.cpp:3380-3385: after the last '/' that is not the final char
     size_t cut = 0;
     for (size_t j = 0; j + 1 < p.size(); j++)
       if (p[j] == '/') cut = j + 1;
     return p.substr(cut);
   };
+  FILE *xmf = fopen(xdmf_path.c_str(), "w");
+  if (!xmf) {
+    set_error("dump: cannot open " + xdmf_path);
+    return CUP2D_EINVAL;
+  }
+  fprintf(xmf,
+          "<Xdmf\n    Version=\"2.0\">\n  <Domain>\n    <Grid>\n      <Time Value=\"%.16e\"/>\n      <Topology\n"
+          "          Dimensions=\"%ld\"\n          TopologyType=\"Quadrilateral\"/>\n     <Geometry\n"
+          "         GeometryType=\"XY\">\n       <DataItem\n           Dimensions=\"%ld 2\"\n"
+          "           Format=\"Binary\">\n         %s\n       </DataItem>\n     </Geometry>\n       <Attribute\n"
+          "           AttributeType=\"Vector\"\n           Name=\"vort\"\n           Center=\"Cell\">\n"
+          "         <DataItem\n             Dimensions=\"3 %ld\"\n             Format=\"Binary\">\n           %s\n"
+          "         </DataItem>\n       </Attribute>\n    </Grid>\n  </Domain>\n</Xdmf>\n",
+          time, ncell_total, 4 * ncell_total, basename_of(xyz_path).c_str(), ncell_total, basename_of(attr_path).c_str());
+  fclose(xmf);
+  return CUP2D_OK;
+}
+
+int dump_fields(cup2d_sim *s, double time, const char *path) {
+  const std::string base(path);
+  const std::string xyz_path = base + ".xyz.raw", attr_path = base + ".attr.raw", xdmf_path = base + ".xdmf2";
   if (s->rank == s->nranks - 1) { // main.cpp:3390: the last rank writes the descriptor
-    const long ncell_total = (long)s->nglobal * 64;
-    FILE *xmf = fopen(xdmf_path.c_str(), "w");
-    if (!xmf) {
-      set_error("dump: cannot open " + xdmf_path);
-      return CUP2D_EINVAL;
-    }
-    fprintf(xmf,
-            "<Xdmf\n    Version=\"2.0\">\n  <Domain>\n    <Grid>\n      <Time Value=\"%.16e\"/>\n      <Topology\n"
-            "          Dimensions=\"%ld\"\n          TopologyType=\"Quadrilateral\"/>\n     <Geometry\n"
-            "         GeometryType=\"XY\">\n       <DataItem\n           Dimensions=\"%ld 2\"\n"
-            "           Format=\"Binary\">\n         %s\n       </DataItem>\n     </Geometry>\n       <Attribute\n"
-            "           AttributeType=\"Vector\"\n           Name=\"vort\"\n           Center=\"Cell\">\n"
-            "         <DataItem\n             Dimensions=\"3 %ld\"\n             Format=\"Binary\">\n           %s\n"
-            "         </DataItem>\n       </Attribute>\n    </Grid>\n  </Domain>\n</Xdmf>\n",
-            time, ncell_total, 4 * ncell_total, basename_of(xyz_path).c_str(), ncell_total,
-            basename_of(attr_path).c_str());
-    fclose(xmf);
+    const int rc = dump_write_xdmf(xdmf_path, xyz_path, attr_path, time, (long)s->nglobal * 64);
+    if (rc) return rc;
   }
   {
     const int rc = ensure_block_ij(s);
@@ -270,8 +276,8 @@ int dump_fields(cup2d_sim *s, double time, const char *path) {
     cudaMemcpyAsync(h_buf + (size_t)CHUNK * 64 * 8, da, ncell * 3 * sizeof(float), cudaMemcpyDeviceToHost, s->stream);
     if (cudaStreamSynchronize(s->stream) != cudaSuccess) { rc = CUP2D_ECUDA; break; }
     const off_t cell0 = (off_t)(s->gbegin + b0) * 64; // MPI_Exscan offset (main.cpp:3387) + position in the range
-    if (write_all(fx, h_buf, ncell * 8 * sizeof(float), cell0 * 8 * (off_t)sizeof(float)) ||
-        write_all(fa, h_buf + (size_t)CHUNK * 64 * 8, ncell * 3 * sizeof(float), cell0 * 3 * (off_t)sizeof(float)))
+    if (dump_write_all(fx, h_buf, ncell * 8 * sizeof(float), cell0 * 8 * (off_t)sizeof(float)) ||
+        dump_write_all(fa, h_buf + (size_t)CHUNK * 64 * 8, ncell * 3 * sizeof(float), cell0 * 3 * (off_t)sizeof(float)))
       rc = CUP2D_EINVAL;
   }
   if (fx >= 0) close(fx);

@@ -4,6 +4,8 @@
 #include "common.cuh"
 #include "rows.cuh"
 #include <mutex>
+#include <string>
+#include <sys/types.h>
 #include <vector>
 
 namespace cup2d {
@@ -166,4 +168,7 @@ int poisson_solve(cup2d_sim *s, double tol_abs, double tol_rel, int max_restarts
                   int *iters, double *err);
 int halo_exchange_ptr(cup2d_sim *s, double *base, int dim, int peer_index, bool done_barrier = true);
 void swap_fields(cup2d_sim *s, int a, int b); // pointer swap, mirrored on the peer mappings
+int dump_write_xdmf(const std::string &xdmf_path, const std::string &xyz_path, const std::string &attr_path, double time,
+                    long ncell_total);
+int dump_write_all(int fd, const void *buf, size_t n, off_t off);
 } // namespace cup2d

@@ -308,6 +308,10 @@ int cup2d_amr_peer_attach(cup2d_amr *a, const void *all_blobs);
  * field itself is left in tmp.  States, 2:1 balancing and the mesh surgery stay on the host. */
 int cup2d_amr_adapt_tags(cup2d_amr *a, double rtol, int level_max, double *block_linf_out);
 
+/* dump() on a multi-level mesh (main.cpp:3367-3467; cf. cup2d_dump): path.xdmf2, path.xyz.raw, path.attr.raw — the
+ * reference's three files, byte for byte, from the device-resident velocity. */
+int cup2d_amr_dump(cup2d_amr *a, double time, const char *path);
+
 /* Bodies on a multi-level mesh: the cup2d_shape_* calls (above) on the cup2d_amr context, with the cell size and the block
  * position taken per block (Info::h, Info::origin, main.cpp:695-696).  block_ids index the context's blocks; a shape's
  * arrays are copied before the call returns.  Sums to rounding (per-block partial sums added in block order), blend and

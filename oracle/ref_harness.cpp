@@ -42,6 +42,9 @@
 //        12: vel blocks (128/block)  13: pres = pold blocks  14: chi blocks  15: udef blocks (128/block)
 //        20: VectorLab of vel, stencil {-3,-3,4,4,tensorial} (14*14*2/block)   21: VectorLab of vel {-1,-1,2,2} (10*10*2)
 //        22: ScalarLab of pres {-1,-1,2,2} (10*10)
+//   ref_harness adump levelMax nsteps prefix
+//        the run.sh case for nsteps steps, then the reference's dump() (main.cpp:3367-3467) of its velocity on that mesh:
+//        prefix.xdmf2 / .xyz.raw / .attr.raw, and prefix.bin = 10: time, h0, bpdx, bpdy  11: mesh  12: vel blocks
 //   ref_harness atags levelMax nsteps out.bin
 //        the run.sh case for nsteps steps, then what adapt() looks at (main.cpp:4676-4678) on the fields as they are:
 //        10: Rtol, Ctol, levelMax, h0, bpdx, bpdy   11: mesh   12: vel blocks   14: chi blocks
@@ -86,7 +89,7 @@ extern int cup2d_ref_force_iters;
 extern int cup2d_ref_fixed_iters;
 
 namespace {
-enum Mode { ORDER, OPS, STEPS, TIME, AMR, VORT, TAGS, DUMP, PENAL, AMRLAB, FSTEPS, ASTEPS, ATAGS } g_mode;
+enum Mode { ORDER, OPS, STEPS, TIME, AMR, VORT, TAGS, DUMP, PENAL, AMRLAB, FSTEPS, ASTEPS, ATAGS, ADUMP } g_mode;
 int g_sum7 = 0, g_sum2 = 0, g_step = 0;
 int g_extra = 0;
 double g_rtol = 0, g_time = 0;
@@ -444,6 +447,20 @@ static void do_atags() {
   fclose(g_fout);
 }
 
+// ---- adump: the reference's dump() on a real multi-level mesh (main.cpp:3367-3467) -------------------------------------
+static void do_adump() {
+  g_fout = fopen((g_out + ".bin").c_str(), "wb");
+  put(10, {0.1875, sim.h0, (double)sim.bpdx, (double)sim.bpdy});
+  std::vector<double> mesh;
+  for (auto &info : var.vel->infos) { mesh.push_back(info.level); mesh.push_back(info.index[0]); mesh.push_back(info.index[1]); }
+  put(11, mesh);
+  put_blocks(12, var.vel, 2);
+  fclose(g_fout);
+  std::vector<char> path(g_out.begin(), g_out.end());
+  path.push_back(0);
+  dump(0.1875, var.vel->infos.size(), var.vel->infos.data(), path.data());
+}
+
 static void penal_hook(int op, void *buf, int count) {
   const int S = (int)sim.shapes.size();
   if (op == MPI_MAX && count == 1) { // dt of a new step (main.cpp:6592)
@@ -517,11 +534,12 @@ void cup2d_ref_hook(int op, void *buf, int count) {
     if (call == g_nsteps) { fclose(g_fout); exit(0); }
     return;
   }
-  if (g_mode == AMRLAB || g_mode == ATAGS) {
+  if (g_mode == AMRLAB || g_mode == ATAGS || g_mode == ADUMP) {
     if (op != MPI_MAX || count != 1) return;
     if (g_calls++ < g_nsteps) return; // let the reference run nsteps steps first
     if (g_mode == AMRLAB) do_amrlab();
-    else do_atags();
+    else if (g_mode == ATAGS) do_atags();
+    else do_adump();
     exit(0);
   }
   if (op != MPI_MAX || count != 1) return;
@@ -633,8 +651,8 @@ int main(int argc, char **argv) {
                           "-shapes", "angle=0 L=0.2 xpos=1.8 ypos=0.8\n angle=180 L=0.2 xpos=1.6 ypos=0.8"};
     return ref_main(sizeof args / sizeof *args, (char **)args);
   }
-  else if (((mode == "amrlab" || mode == "atags") && argc == 5) || (mode == "asteps" && argc == 6)) {
-    if (mode != "asteps") { g_mode = mode == "amrlab" ? AMRLAB : ATAGS; g_nsteps = atoi(argv[3]); g_out = argv[4]; cup2d_ref_force_iters = 5; }
+  else if (((mode == "amrlab" || mode == "atags" || mode == "adump") && argc == 5) || (mode == "asteps" && argc == 6)) {
+    if (mode != "asteps") { g_mode = mode == "amrlab" ? AMRLAB : mode == "atags" ? ATAGS : ADUMP; g_nsteps = atoi(argv[3]); g_out = argv[4]; cup2d_ref_force_iters = 5; }
     else { g_mode = ASTEPS; g_nsteps = atoi(argv[3]); g_kiter = atoi(argv[4]); g_out = argv[5]; cup2d_ref_force_iters = g_kiter; }
     char a_lmax[16];
     snprintf(a_lmax, sizeof a_lmax, "%d", g_L);

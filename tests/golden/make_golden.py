@@ -287,6 +287,26 @@ def gen_amrtags(tmp, level_max, nsteps):
     print("amrtags", nb, "blocks; chi rule fired on", int(fired.sum()))
 
 
+def gen_amrdump(tmp, level_max, nsteps):
+    """the reference's dump() of its velocity on its own multi-level run.sh mesh after nsteps steps: mesh, vel, the three files"""
+    pref = os.path.join(tmp, "vel.00000003")
+    subprocess.run([HARNESS, "adump", str(level_max), str(nsteps), pref], check=True, stderr=subprocess.DEVNULL,
+                   stdout=subprocess.DEVNULL, env=dict(os.environ, OMP_NUM_THREADS="1"))
+    a = np.fromfile(pref + ".bin")
+    i, rec = 0, {}
+    while i < len(a):
+        tag, n = int(a[i]), int(a[i + 1])
+        rec[tag] = a[i + 2:i + 2 + n]
+        i += 2 + n
+    time, h0, bpdx, bpdy = rec[10]
+    blocks = rec[11].reshape(-1, 3).astype(np.int32)
+    np.savez_compressed(os.path.join(HERE, f"amrdump_lmax{level_max}.npz"), time=time, h0=h0, bpdx=int(bpdx), bpdy=int(bpdy),
+                        blocks=blocks, vel=rec[12].reshape(len(blocks), 8, 8, 2),
+                        xyz=np.fromfile(pref + ".xyz.raw", dtype=np.float32), attr=np.fromfile(pref + ".attr.raw", dtype=np.float32),
+                        xdmf=np.frombuffer(open(pref + ".xdmf2", "rb").read(), dtype=np.uint8))
+    print("amrdump", len(blocks), "blocks")
+
+
 def gen_steps(tmp, kind, L, seed, nu, cfl, nsteps, kiter):
     N = 8 << L
     ins = make_inputs(kind, L, seed)
@@ -317,6 +337,7 @@ if __name__ == "__main__":
         gen_penal(tmp, 4, 4, [2, 3])
         gen_amrlab(tmp, 8, 3)
         gen_amrtags(tmp, 8, 5)
+        gen_amrdump(tmp, 8, 4)
         gen_ops(tmp, "random", 2, 1234, 1e-3, 2.5e-3)
         gen_ops(tmp, "tg", 3, 4321, 1e-3, 1.2e-3)
         gen_steps(tmp, "tg", 2, 777, 1e-3, 0.5, 3, 12)

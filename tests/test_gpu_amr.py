@@ -205,6 +205,21 @@ def test_amr_adapt_tags_vs_reference_golden(golden_dir):
     sim.close()
 
 
+def test_amr_dump_files_byte_identical_to_reference(golden_dir, tmp_path):
+    """cup2d_amr_dump on the reference's run.sh mesh (7 levels) with its own velocity field: the three files dump() wrote
+    there (tests/golden/amrdump_lmax8.npz), byte for byte"""
+    from cup2d_b200.amr import AmrSimulation
+    d = np.load(os.path.join(golden_dir, "amrdump_lmax8.npz"))
+    sim = AmrSimulation(d["blocks"], int(d["bpdx"]), int(d["bpdy"]), float(d["h0"]), 4e-5)
+    sim.upload("vel", d["vel"])
+    pref = str(tmp_path / "vel.00000003")
+    sim.dump(float(d["time"]), pref)
+    sim.close()
+    assert np.array_equal(np.fromfile(pref + ".xyz.raw", dtype=np.float32), d["xyz"])
+    assert np.array_equal(np.fromfile(pref + ".attr.raw", dtype=np.float32), d["attr"])
+    assert open(pref + ".xdmf2", "rb").read() == d["xdmf"].tobytes()
+
+
 def test_amr_bodies_sums_blend_and_udef_assembly(case):
     """cup2d_amr_shape_*: two synthetic shapes whose obstacle blocks span several refinement levels (the field chi is the
     golden's own).  Against a block-wise numpy restatement of main.cpp:6648-6679, 6944-6979, 6980-7002 with the per-block

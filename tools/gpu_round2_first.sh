@@ -20,7 +20,7 @@ echo "== 2. multi-level device path, first contact"
 tail -25 $OUT/pytest_amr_$TAG.log
 for tool in memcheck racecheck; do
     CUP2D_TEST_UNVALIDATED=1 timeout 400 compute-sanitizer --tool $tool --error-exitcode 9 --print-limit 20 \
-        python -m pytest tests/test_gpu_amr.py -m gpu -q -x -k "advect or fast or full_step or bodies or adapt_tags" > $OUT/sanitizer_${tool}_amr_$TAG.log 2>&1
+        python -m pytest tests/test_gpu_amr.py -m gpu -q -x -k "advect or fast or full_step or bodies or adapt_tags or amr_dump" > $OUT/sanitizer_${tool}_amr_$TAG.log 2>&1
     echo "sanitizer $tool rc=$?"; grep -E "ERROR SUMMARY|RACECHECK SUMMARY|passed|failed" $OUT/sanitizer_${tool}_amr_$TAG.log | tail -3
 done
 
