@@ -7,6 +7,8 @@
 //                               reduction has no fixed order: agreement to rounding, not bitwise)
 //   cup2d_amr_penalize        : the blend of main.cpp:6944-6979, explicit round-to-nearest operations: bit-identical
 //   cup2d_amr_udef_assemble   : tmpV = sum of u_def where the shape's chi is not below the field's (6980-7002): bit-identical
+// Also here, because it needs the same per-block (i, j, h) tables: cup2d_amr_dump, dump()'s three files from a multi-level mesh
+// (main.cpp:3367-3467), byte for byte.
 // STATUS: like the rest of the multi-level device path, written after the round's GPU budget was spent — compiled for
 // sm_100a, run under the host emulation only.
 #include "sim.h"
