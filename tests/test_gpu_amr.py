@@ -312,3 +312,21 @@ def test_reference_amr_case_on_the_multi_level_device_path(tmp_path, form):
     for (dt0, m0, v0, p0), (dt1, m1, v1, p1) in zip(*runs):
         assert np.array_equal(m0, m1) and abs(dt0 - dt1) < 1e-14
         assert np.abs(v0 - v1).max() < 1e-10 * np.abs(v0).max() and np.abs(p0 - p1).max() < 1e-9 * np.abs(p0).max()
+
+
+def test_two_ranks_on_two_gpus_multi_level():
+    """N>1 on real GPUs (skipped on a single-GPU box): the distributed general-rows Poisson solve and multi-level steps with
+    replicated operators (cup2d_poisson_create_general_ranks, cup2d_amr_set_ranks) against the same work on one GPU"""
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29578", os.path.join(root, "tools", "multi_gpu_check.py")],
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=400,
+                       env=dict(os.environ, CUP2D_TEST_UNVALIDATED="1"))
+    assert r.returncode == 0, r.stdout[-2000:]
+    for check in ("amr_poisson_ranks", "amr_step_ranks"):
+        assert f'"check": "{check}"' in r.stdout

@@ -381,7 +381,7 @@ def test_two_ranks_on_two_gpus_match_the_oracle():
                         os.path.join(root, "tools", "multi_gpu_check.py")], stdout=subprocess.PIPE,
                        stderr=subprocess.STDOUT, text=True, timeout=300)
     assert r.returncode == 0, r.stdout[-2000:]
-    for check in ("parity_256", "tags_dump", "adapt_tags_chi", "penalisation", "amr_poisson_ranks", "amr_step_ranks"):
+    for check in ("parity_256", "tags_dump", "adapt_tags_chi", "penalisation"):
         assert f'"check": "{check}"' in r.stdout
 
 
