@@ -588,6 +588,9 @@ def test_shape_calls_reject_bad_arguments():
     sim.close()
 
 
+@pytest.mark.skipif(os.environ.get("CUP2D_TEST_UNVALIDATED") != "1",
+                    reason="cup2d_pipe_* was written after the GPU budget was spent: opt-in until it has run on hardware "
+                           "(bench.py verifies it bit for bit against the blocking calls before using its figure)")
 def test_host_pipeline_matches_blocking_calls():
     """cup2d_pipe_*: independent steps with host inputs and results, upload(n+1) || step(n) || download(n-1) on three
     streams with buffer trading — bit-identical to cup2d_field_upload + cup2d_step + cup2d_field_download, for more jobs
