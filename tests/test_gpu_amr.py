@@ -205,6 +205,41 @@ def test_amr_adapt_tags_vs_reference_golden(golden_dir):
     sim.close()
 
 
+@pytest.mark.parametrize("fast", [False, True])
+def test_multi_level_path_on_a_uniform_mesh_equals_the_uniform_path(fast):
+    """the two device paths against each other: a one-level mesh through cup2d_amr (tables, per-block cell size, general-rows
+    Poisson context) and through cup2d_sim (the path measured and validated on hardware), two full steps — same dt, same
+    iteration count, fields to rounding"""
+    import cup2d_b200
+    from cup2d_b200.amr import AmrSimulation
+    L = 3
+    N = 8 << L
+    order = cup2d_b200.block_order(1, 1, L)
+    nb = len(order)
+    blocks = np.concatenate([np.full((nb, 1), L), order], axis=1).astype(np.int32)
+    rng = np.random.default_rng(2)
+    x = (np.arange(N) + 0.5) / N
+    X, Y = np.meshgrid(x, x)
+    u = np.sin(2 * np.pi * X) * np.cos(2 * np.pi * Y) + 0.05 * rng.uniform(-1, 1, (N, N))
+    v = -np.cos(2 * np.pi * X) * np.sin(2 * np.pi * Y) + 0.05 * rng.uniform(-1, 1, (N, N))
+    p = np.cos(2 * np.pi * X) * np.cos(2 * np.pi * Y)
+    sim = cup2d_b200.Simulation(L, nu=1e-3, cfl=0.5)
+    sim.upload("vel", u, v)
+    sim.upload("pres", p)
+    a = AmrSimulation(blocks, 1, 1, 1 / 8, 1e-3)
+    a.set_fast(fast)
+    a.upload("vel", sim.download_blocks("vel").reshape(nb, 8, 8, 2))
+    a.upload("pres", sim.download_blocks("pres").reshape(nb, 8, 8, 1))
+    for _ in range(2):
+        dt1, it1, err1 = sim.step(max_iter=8, max_restarts=0)
+        dt2, it2, err2 = a.step(cfl=0.5, max_iter=8)
+        assert abs(dt1 - dt2) <= 1e-15 * dt1 and it1 == it2 == 8 and abs(err1 - err2) <= 1e-10 * err1
+        assert np.abs(sim.download_blocks("vel").reshape(nb, 8, 8, 2) - a.download("vel")).max() < 1e-12
+        assert np.abs(sim.download_blocks("pres").reshape(nb, 8, 8, 1) - a.download("pres")).max() < 1e-11
+    a.close()
+    sim.close()
+
+
 def test_amr_dump_files_byte_identical_to_reference(golden_dir, tmp_path):
     """cup2d_amr_dump on the reference's run.sh mesh (7 levels) with its own velocity field: the three files dump() wrote
     there (tests/golden/amrdump_lmax8.npz), byte for byte"""
