@@ -626,7 +626,10 @@ def test_host_pipeline_matches_blocking_calls():
         sim.pipe_upload(sim.PIPE_SLOTS, vin[0].data_ptr(), pin_[0].data_ptr())
 
 
-@pytest.mark.parametrize("case", ["all_zero", "constant_pressure", "uniform_flow", "tiny_values"])
+@pytest.mark.parametrize("case", ["all_zero", "constant_pressure", "uniform_flow",
+                                  pytest.param("tiny_values", marks=pytest.mark.skipif(
+                                      os.environ.get("CUP2D_TEST_UNVALIDATED") != "1",
+                                      reason="underflow corner added after the last GPU run: opt-in until seen on hardware"))])
 def test_degenerate_inputs_vs_oracle(case):
     """inputs on which the Krylov recurrences divide by (almost) nothing — zero right-hand side, zero residual after the
     first half-step — and the dt rule has umax = 0: the eps = 1e-21 guards of the reference (cuda.cu:315-326) and its
