@@ -16,7 +16,7 @@ tail -5 $OUT/pytest_gpu_$TAG.log
 
 echo "== 2. multi-level device path, first contact"
 (time CUP2D_TEST_UNVALIDATED=1 timeout 900 python -m pytest tests/test_gpu_amr.py tests/test_gpu_parity.py -m gpu -q --durations=0 -p no:cacheprovider \
-    -k "test_gpu_amr or host_pipeline") \
+    -k "test_gpu_amr or host_pipeline or tiny_values") \
     > $OUT/pytest_amr_$TAG.log 2>&1
 tail -25 $OUT/pytest_amr_$TAG.log
 for tool in memcheck racecheck; do
