@@ -104,6 +104,32 @@ class AmrSimulation:
         _l.check(self.lib.cup2d_amr_create(len(self.blocks), self.blocks.ctypes.data_as(C.POINTER(C.c_int32)), bpdx, bpdy,
                                            float(h0), float(nu), device, C.byref(self._h)))
 
+    @classmethod
+    def distributed(cls, level_ij, bpdx, bpdy, h0, nu, rank, rank_begin, dist=None, device=0):
+        """several GPUs, second form (cup2d_amr_create_ranks): this rank's share of a distributed mesh.  Every rank passes the
+        whole block list; upload / download then move the blocks rank_begin[rank] .. rank_begin[rank+1]."""
+        self = cls.__new__(cls)
+        self.lib = _l.load_library()
+        allb = np.ascontiguousarray(level_ij, dtype=np.int32).reshape(-1, 3)
+        rb = np.ascontiguousarray(rank_begin, dtype=np.int64)
+        nranks = len(rb) - 1
+        self.blocks = allb[int(rb[rank]):int(rb[rank + 1])]
+        self._h = C.c_void_p()
+        _l.check(self.lib.cup2d_amr_create_ranks(len(allb), allb.ctypes.data_as(C.POINTER(C.c_int32)), bpdx, bpdy, float(h0), float(nu),
+                                                 int(rank), nranks, rb.ctypes.data_as(C.POINTER(C.c_int64)), device, C.byref(self._h)))
+        n = self.lib.cup2d_peer_blob_size()
+        blob = (C.c_ubyte * n)()
+        _l.check(self.lib.cup2d_amr_peer_export(self._h, blob))
+        gathered = [bytes(blob)]
+        if nranks > 1:
+            gathered = [None] * nranks
+            dist.all_gather_object(gathered, bytes(blob))
+        allblob = b"".join(gathered)
+        _l.check(self.lib.cup2d_amr_peer_attach(self._h, (C.c_ubyte * len(allblob)).from_buffer_copy(allblob)))
+        if dist is not None and nranks > 1:
+            dist.barrier()
+        return self
+
     def upload(self, name, blocks):
         a = np.ascontiguousarray(blocks, dtype=np.float64)
         _l.check(self.lib.cup2d_amr_field_upload(self._h, _l.FIELDS[name], a.ctypes.data_as(C.c_void_p)))

@@ -37,11 +37,23 @@ struct GhostDev { // compact ghost CSR of one stencil kind on the device
   int *dst = nullptr, *sb = nullptr, *sc = nullptr;
   double *w = nullptr;
 };
+struct FluxBuf { // where the face fluxes of the irregular blocks live: per irregular block (position in the irregular list)
+  double *p;     // in a buffer of its own, or — distributed contexts — per block inside a field array, so that the
+  int stride;    // whole-block halo pulls of the fields carry them across a rank boundary
+  int by_block;
+};
 struct CoarseFace { // one coarse-fine face seen from the coarse side
   int coarse, face, fine[2]; // fine[half] = the fine block abutting that half of the face (-1: absent)
 };
 
 } // namespace cup2d
+
+struct cup2d_amr;
+// distributed contexts (cup2d_amr_create_ranks): refresh the halo slots of `field` from the owners (whole-block peer pulls,
+// csrc/halo.cu) before a kernel reads neighbours; a no-op otherwise
+extern "C" int amr_dist_refresh(cup2d_amr *a, int field);
+// fast-kernel tables of a distributed context for its block range [b0, b1): slot_of[global block] = local slot or -1
+int amr_fast_setup_dist(cup2d_amr *a, const std::vector<int32_t> &slot_of, int64_t b0, int64_t b1);
 
 struct cup2d_amr {
   int64_t nb = 0;
@@ -63,13 +75,14 @@ struct cup2d_amr {
   // several GPUs (cup2d_amr_set_ranks): operators replicated on every rank, the Poisson solve distributed by block ranges
   int rank = 0, nranks = 1;
   std::vector<int64_t> rank_begin;
+  bool dist = false;                // cup2d_amr_create_ranks: this context holds only its own block range (+ halo slots)
   // fast paths (csrc/amr_fast.cu)
   bool fast = false;                // cup2d_amr_set_fast: the operator entry points dispatch to the fast kernels
   int *d_nbr4 = nullptr;            // [nb][4] W,E,S,N: same-level block, -1 wall, -2 coarser/finer
   int *d_irr_of = nullptr;          // [nb] position in the irregular list or -1
   int64_t nirr = 0;
   cup2d::GhostDev gt[3];            // compact ghost tables per stencil kind (cup2d_amr_plan_ghosts)
-  double *d_faceflux = nullptr;     // [nirr][4 faces][8][2] face fluxes of the irregular blocks
+  double *d_faceflux = nullptr;     // [nirr][4 faces][8][2] face fluxes of the irregular blocks (single-rank contexts)
   // bodies (csrc/amr_penalize.cu): per-shape obstacle blocks, as cup2d_sim::Shape
   struct Shape { int nob = 0, cap = 0; int *d_ids = nullptr; double *d_X = nullptr, *d_udef = nullptr; };
   std::vector<Shape> shapes;

@@ -17,6 +17,7 @@
 // correction kernel below, which is the coarse-face formulation of fillcases (see amr_ops.cu) reading those buffers.
 #include "sim.h"
 #include "weno.cuh"
+#include <map>
 #include <algorithm>
 #include <vector>
 #include "amr.h"
@@ -42,7 +43,7 @@ constexpr int AF_SMEM = AF_WARPS * AF_BPW * AF_BLK * 8; // 72 192 B per CTA -> 3
 __global__ void __launch_bounds__(AF_NT)
 amr_advect_fast_kernel(const double *__restrict__ vel, double *__restrict__ out, const int4 *__restrict__ nbr4,
                        const int *__restrict__ irr_of, const GhostDev gt, const double *__restrict__ hb,
-                       double *__restrict__ faceflux, int nb, double nu, double dt) {
+                       const FluxBuf faceflux, int nb, double nu, double dt) {
   extern __shared__ __align__(16) double af_smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int q = lane >> 3, r = lane & 7;
@@ -118,7 +119,7 @@ amr_advect_fast_kernel(const double *__restrict__ vel, double *__restrict__ out,
     if (f < 2) ix = f == 0 ? 0 : 7, iy = t, gx = f == 0 ? -1 : 8, gy = t;
     else ix = t, iy = f == 2 ? 0 : 7, gx = t, gy = f == 2 ? -1 : 8;
     const int pi = (iy + 3) * AF_PS + ix + 3, pg = (gy + 3) * AF_PS + gx + 3;
-    double *ff = faceflux + ((size_t)qi * 32 + f * 8 + t) * 2;
+    double *ff = faceflux.p + (size_t)(faceflux.by_block ? kk : qi) * faceflux.stride + (f * 8 + t) * 2;
     ff[0] = dfac * (pu[pi] - pu[pg]);
     ff[1] = dfac * (pv[pi] - pv[pg]);
   }
@@ -189,7 +190,7 @@ __device__ __forceinline__ void face_pos(int f, int t, int &pi, int &pg) { // in
 __global__ void __launch_bounds__(A1_NT)
 amr_div_fast_kernel(const double *__restrict__ vel, const double *__restrict__ udef, const double *__restrict__ chi,
                     double *__restrict__ tmp, const int4 *__restrict__ nbr4, const int *__restrict__ irr_of, const GhostDev gt,
-                    const double *__restrict__ hb, double *__restrict__ faceflux, int nb, double dt) {
+                    const double *__restrict__ hb, const FluxBuf faceflux, int nb, double dt) {
   __shared__ double s_lab[A1_WARPS * 4 * 4 * A1_PLANE];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, q = lane >> 3, r = lane & 7;
   const int b0 = (blockIdx.x * A1_WARPS + warp) * 4;
@@ -211,7 +212,8 @@ amr_div_fast_kernel(const double *__restrict__ vel, const double *__restrict__ u
     const double sv = vu[c * A1_PLANE + pg] + vu[c * A1_PLANE + pi], su = uu[c * A1_PLANE + pg] + uu[c * A1_PLANE + pi];
     const int ix = q < 2 ? (q == 0 ? 0 : 7) : r, iy = q < 2 ? r : (q == 2 ? 0 : 7);
     const double x = chi[(size_t)k * 64 + iy * 8 + ix];
-    faceflux[((size_t)qi * 4 + q) * 8 + r] = (q & 1) == 0 ? fac * sv - (fac * x) * su : -fac * sv + (fac * x) * su;
+    faceflux.p[(size_t)(faceflux.by_block ? k : qi) * faceflux.stride + q * 8 + r] =
+        (q & 1) == 0 ? fac * sv - (fac * x) * su : -fac * sv + (fac * x) * su;
   }
   const int k = b0 + q;
   if (k >= nb) return;
@@ -232,7 +234,7 @@ template <int MODE>
 __global__ void __launch_bounds__(A1_NT)
 amr_scalar_fast_kernel(const double *__restrict__ p, double *__restrict__ out, const int4 *__restrict__ nbr4,
                        const int *__restrict__ irr_of, const GhostDev gt, const double *__restrict__ hb,
-                       double *__restrict__ faceflux, int nb, double dt) {
+                       const FluxBuf faceflux, int nb, double dt) {
   __shared__ double s_lab[A1_WARPS * 4 * A1_PLANE];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, q = lane >> 3, r = lane & 7;
   const int b0 = (blockIdx.x * A1_WARPS + warp) * 4;
@@ -246,7 +248,7 @@ amr_scalar_fast_kernel(const double *__restrict__ p, double *__restrict__ out, c
       int pi, pg;
       face_pos(q, r, pi, pg);
       const double *m = base + qq * A1_PLANE;
-      faceflux[((size_t)qi * 4 + q) * 8 + r] = m[pg] - m[pi];
+      faceflux.p[(size_t)(faceflux.by_block ? b0 + qq : qi) * faceflux.stride + q * 8 + r] = m[pg] - m[pi];
     }
   const int k = b0 + q;
   if (k >= nb) return;
@@ -266,13 +268,15 @@ amr_scalar_fast_kernel(const double *__restrict__ p, double *__restrict__ out, c
 
 // fillcases per coarse face from the stored face fluxes (see amr_fluxcorr_kernel in amr_ops.cu for the formulation)
 template <int DIM>
-__global__ void amr_fluxcorr_faces_kernel(const CoarseFace *__restrict__ cf, int ncf, const double *__restrict__ faceflux,
+__global__ void amr_fluxcorr_faces_kernel(const CoarseFace *__restrict__ cf, int ncf, const FluxBuf faceflux,
                                           const int *__restrict__ irr_of, double *__restrict__ result) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= ncf * 8 * DIM) return;
   const int comp = i % DIM, t = (i / DIM) % 8;
   const CoarseFace f = cf[i / (8 * DIM)];
-  auto flux = [&](int blk, int face, int pos) { return faceflux[(((size_t)irr_of[blk] * 4 + face) * 8 + pos) * DIM + comp]; };
+  auto flux = [&](int blk, int face, int pos) {
+    return faceflux.p[(size_t)(faceflux.by_block ? blk : irr_of[blk]) * faceflux.stride + (face * 8 + pos) * DIM + comp];
+  };
   double acc = flux(f.coarse, f.face, t);
   const int fb = f.fine[t >> 2];
   if (fb >= 0) {
@@ -286,19 +290,35 @@ __global__ void amr_fluxcorr_faces_kernel(const CoarseFace *__restrict__ cf, int
   *dst = v;
 }
 
+// single-rank contexts: a buffer per irregular block; distributed contexts: inside a field array that is free at that point
+// (advect: tmp, 64 doubles per block; pressure kernels: vold, 128 per block), refreshed across ranks before fillcases
+template <int DIM> static FluxBuf flux_buf(cup2d_amr *a) {
+  if (!a->dist) return FluxBuf{a->d_faceflux, 32 * DIM, 0};
+  return DIM == 2 ? FluxBuf{a->f[CUP2D_TMP], 64, 1} : FluxBuf{a->f[CUP2D_VOLD], 128, 1};
+}
 template <int DIM> static int fluxcorr_faces(cup2d_amr *a, double *result) {
+  { // the fine side of a coarse face may live on another rank
+    const int rc = amr_dist_refresh(a, DIM == 2 ? CUP2D_TMP : CUP2D_VOLD);
+    if (rc) return rc;
+  }
   for (int dir = 0; dir < 2; dir++) { // x faces, then y faces (fillcases order)
     const int n = a->ncf[dir] * 8 * DIM;
     if (n == 0) continue;
-    amr_fluxcorr_faces_kernel<DIM><<<(n + 127) / 128, 128, 0, a->stream>>>(a->d_cf[dir], a->ncf[dir], a->d_faceflux, a->d_irr_of,
+    amr_fluxcorr_faces_kernel<DIM><<<(n + 127) / 128, 128, 0, a->stream>>>(a->d_cf[dir], a->ncf[dir], flux_buf<DIM>(a), a->d_irr_of,
                                                                          result);
   }
   CUP2D_CUDA(cudaGetLastError());
   return CUP2D_OK;
 }
 
+static int fast_constants() {
+  CUP2D_CUDA(cudaMemcpyToSymbol(cW, hW, sizeof hW));
+  CUP2D_CUDA(cudaFuncSetAttribute(amr_advect_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AF_SMEM));
+  return CUP2D_OK;
+}
+
 static int fast_setup(cup2d_amr *a) {
-  if (a->d_faceflux) return CUP2D_OK;
+  if (a->d_faceflux || a->dist) return CUP2D_OK; // distributed contexts get their tables from amr_fast_setup_dist
   const int64_t nb = a->nb;
   std::vector<int32_t> n8(8 * nb), n4(4 * nb), irr_of(nb, -1);
   if (cup2d_amr_plan_neighbours(a->plan, n8.data())) return CUP2D_EINVAL;
@@ -339,12 +359,106 @@ static int fast_setup(cup2d_amr *a) {
   CUP2D_CUDA(up(&a->d_nbr4, n4));
   CUP2D_CUDA(up(&a->d_irr_of, irr_of));
   CUP2D_CUDA(cudaMalloc(&a->d_faceflux, std::max<int64_t>(nirr, 1) * 64 * sizeof(double)));
-  CUP2D_CUDA(cudaMemcpyToSymbol(cW, hW, sizeof hW));
-  CUP2D_CUDA(cudaFuncSetAttribute(amr_advect_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AF_SMEM));
-  return CUP2D_OK;
+  return fast_constants();
 }
 
 } // namespace cup2d
+
+// Tables of a DISTRIBUTED context: the plan knows the whole mesh; this rank keeps what concerns its blocks [b0, b1) and
+// names every block by its local slot (own blocks first, then the halo slots of the field arrays): slot_of[global block] or -1.
+int amr_fast_setup_dist(cup2d_amr *a, const std::vector<int32_t> &slot_of, int64_t b0, int64_t b1) {
+  using namespace cup2d;
+  const int64_t nglob = (int64_t)slot_of.size(), nloc = b1 - b0;
+  auto up = [](auto **d, const auto &h) -> cudaError_t {
+    using T = typename std::remove_reference<decltype(h[0])>::type;
+    cudaError_t e = cudaMalloc(d, std::max<size_t>(h.size(), 1) * sizeof(T));
+    if (e != cudaSuccess) return e;
+    return cudaMemcpy(*d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice);
+  };
+  auto slot = [&](int32_t g) -> int32_t {
+    if (g < 0) return g;
+    return slot_of[g]; // -1 would mean a block the halo set missed: caught below
+  };
+  std::vector<int32_t> n8(8 * nglob), n4(4 * nloc);
+  if (cup2d_amr_plan_neighbours(a->plan, n8.data())) return CUP2D_EINVAL;
+  for (int64_t k = 0; k < nloc; k++) {
+    const int pick[4] = {3, 4, 1, 6}; // W, E, S, N
+    for (int j = 0; j < 4; j++) {
+      const int32_t g = n8[8 * (b0 + k) + pick[j]];
+      n4[4 * k + j] = g < -1 ? -2 : slot(g);
+      if (g >= 0 && n4[4 * k + j] < 0) return CUP2D_EINVAL;
+    }
+  }
+  const int64_t nirr_g = cup2d_amr_plan_irregular(a->plan, nullptr);
+  std::vector<int32_t> irr(std::max<int64_t>(nirr_g, 1)), irr_of(nloc, -1), local_of_irr(std::max<int64_t>(nirr_g, 1), -1);
+  cup2d_amr_plan_irregular(a->plan, irr.data());
+  int64_t nirr = 0;
+  for (int64_t qi = 0; qi < nirr_g; qi++)
+    if (irr[qi] >= b0 && irr[qi] < b1) {
+      local_of_irr[qi] = (int32_t)nirr;
+      irr_of[irr[qi] - b0] = (int32_t)nirr++;
+    }
+  a->nirr = nirr;
+  const int ncell[3] = {14 * 14 * 2, 10 * 10 * 2, 10 * 10};
+  for (int which = 0; which < 3; which++) {
+    int64_t nrows_g = 0;
+    const int64_t nnz_g = cup2d_amr_plan_ghosts(a->plan, which, &nrows_g, nullptr, nullptr, nullptr, nullptr, nullptr);
+    if (nnz_g < 0) return CUP2D_EINVAL;
+    std::vector<int64_t> rp_g(nrows_g + 1);
+    std::vector<int32_t> dst_g(std::max<int64_t>(nrows_g, 1)), sb_g(std::max<int64_t>(nnz_g, 1)), sc_g(std::max<int64_t>(nnz_g, 1));
+    std::vector<double> w_g(std::max<int64_t>(nnz_g, 1));
+    cup2d_amr_plan_ghosts(a->plan, which, &nrows_g, rp_g.data(), dst_g.data(), sb_g.data(), sc_g.data(), w_g.data());
+    std::vector<int64_t> rp(1, 0);
+    std::vector<int32_t> dst, sb, sc;
+    std::vector<double> w;
+    for (int64_t row = 0; row < nrows_g; row++) {
+      const int32_t ql = local_of_irr[dst_g[row] / ncell[which]];
+      if (ql < 0) continue;
+      dst.push_back(ql * ncell[which] + dst_g[row] % ncell[which]);
+      for (int64_t e = rp_g[row]; e < rp_g[row + 1]; e++) {
+        const int32_t sl = slot(sb_g[e]);
+        if (sl < 0) return CUP2D_EINVAL;
+        sb.push_back(sl);
+        sc.push_back(sc_g[e]);
+        w.push_back(w_g[e]);
+      }
+      rp.push_back((int64_t)w.size());
+    }
+    const int64_t nrows = (int64_t)dst.size();
+    std::vector<int64_t> grow(nirr + 1, nrows);
+    for (int64_t row = nrows - 1; row >= 0; row--) grow[dst[row] / ncell[which]] = row;
+    for (int64_t qi = nirr - 1; qi >= 0; qi--) grow[qi] = std::min(grow[qi], grow[qi + 1]);
+    GhostDev &g = a->gt[which];
+    CUP2D_CUDA(up(&g.grow, grow));
+    CUP2D_CUDA(up(&g.rowptr, rp));
+    CUP2D_CUDA(up(&g.dst, dst));
+    CUP2D_CUDA(up(&g.sb, sb));
+    CUP2D_CUDA(up(&g.sc, sc));
+    CUP2D_CUDA(up(&g.w, w));
+  }
+  CUP2D_CUDA(up(&a->d_nbr4, n4));
+  CUP2D_CUDA(up(&a->d_irr_of, irr_of));
+  // coarse faces whose COARSE block is ours (the fine side may be a halo slot)
+  const int64_t nf = cup2d_amr_plan_faces(a->plan, nullptr);
+  std::vector<int32_t> rec(5 * std::max<int64_t>(nf, 1));
+  cup2d_amr_plan_faces(a->plan, rec.data());
+  std::map<std::pair<int, int>, CoarseFace> byface;
+  for (int64_t r = 0; r < nf; r++) {
+    const int fine = rec[5 * r], kc = rec[5 * r + 2], fc = rec[5 * r + 3], half = rec[5 * r + 4];
+    if (kc < b0 || kc >= b1) continue;
+    auto it = byface.find({kc, fc});
+    if (it == byface.end()) it = byface.emplace(std::make_pair(kc, fc), CoarseFace{(int)(kc - b0), fc, {-1, -1}}).first;
+    it->second.fine[half] = slot(fine);
+    if (it->second.fine[half] < 0) return CUP2D_EINVAL;
+  }
+  std::vector<CoarseFace> lists[2];
+  for (auto &e : byface) lists[e.second.face < 2 ? 0 : 1].push_back(e.second);
+  for (int d = 0; d < 2; d++) {
+    a->ncf[d] = (int)lists[d].size();
+    if (!lists[d].empty()) CUP2D_CUDA(up(&a->d_cf[d], lists[d]));
+  }
+  return fast_constants();
+}
 
 using namespace cup2d;
 
@@ -359,11 +473,12 @@ int cup2d_amr_advect_diffuse_rhs_fast(cup2d_amr *a, double dt) {
   CUP2D_CUDA(cudaSetDevice(a->device));
   int rc = fast_setup(a);
   if (rc) return rc;
+  if ((rc = amr_dist_refresh(a, CUP2D_VEL))) return rc;
   const int per_cta = AF_WARPS * AF_BPW;
   const int grid = (int)((a->nb + per_cta - 1) / per_cta);
   amr_advect_fast_kernel<<<grid, AF_NT, AF_SMEM, a->stream>>>(
       a->f[CUP2D_VEL], a->f[CUP2D_TMPV], reinterpret_cast<const int4 *>(a->d_nbr4), a->d_irr_of, a->gt[0], a->d_h,
-      a->d_faceflux, (int)a->nb, a->nu, dt);
+      flux_buf<2>(a), (int)a->nb, a->nu, dt);
   CUP2D_CUDA(cudaGetLastError());
   return fluxcorr_faces<2>(a, a->f[CUP2D_TMPV]);
 }
@@ -377,10 +492,11 @@ int cup2d_amr_pressure_rhs_fast(cup2d_amr *a, double dt, int with_laplacian) {
   CUP2D_CUDA(cudaSetDevice(a->device));
   int rc = fast_setup(a);
   if (rc) return rc;
+  if ((rc = amr_dist_refresh(a, CUP2D_VEL)) || (rc = amr_dist_refresh(a, CUP2D_TMPV))) return rc;
   const int grid = (int)((a->nb + A1_WARPS * 4 - 1) / (A1_WARPS * 4));
   const int4 *nbr4 = reinterpret_cast<const int4 *>(a->d_nbr4);
   amr_div_fast_kernel<<<grid, A1_NT, 0, a->stream>>>(a->f[CUP2D_VEL], a->f[CUP2D_TMPV], a->f[CUP2D_CHI], a->f[CUP2D_TMP], nbr4,
-                                                     a->d_irr_of, a->gt[1], a->d_h, a->d_faceflux, (int)a->nb, dt);
+                                                     a->d_irr_of, a->gt[1], a->d_h, flux_buf<1>(a), (int)a->nb, dt);
   CUP2D_CUDA(cudaGetLastError());
   if ((rc = fluxcorr_faces<1>(a, a->f[CUP2D_TMP])) || !with_laplacian) return rc;
   return cup2d_amr_laplacian_fast(a, dt);
@@ -395,9 +511,10 @@ int cup2d_amr_laplacian_fast(cup2d_amr *a, double dt) {
   CUP2D_CUDA(cudaSetDevice(a->device));
   int rc = fast_setup(a);
   if (rc) return rc;
+  if ((rc = amr_dist_refresh(a, CUP2D_POLD))) return rc;
   const int grid = (int)((a->nb + A1_WARPS * 4 - 1) / (A1_WARPS * 4));
   amr_scalar_fast_kernel<0><<<grid, A1_NT, 0, a->stream>>>(a->f[CUP2D_POLD], a->f[CUP2D_TMP], reinterpret_cast<const int4 *>(a->d_nbr4),
-                                                           a->d_irr_of, a->gt[2], a->d_h, a->d_faceflux, (int)a->nb, dt);
+                                                           a->d_irr_of, a->gt[2], a->d_h, flux_buf<1>(a), (int)a->nb, dt);
   CUP2D_CUDA(cudaGetLastError());
   return fluxcorr_faces<1>(a, a->f[CUP2D_TMP]);
 }
@@ -405,6 +522,10 @@ int cup2d_amr_laplacian_fast(cup2d_amr *a, double dt) {
 /* route the operator entry points (and with them cup2d_amr_step) through the fast kernels of this file */
 int cup2d_amr_set_fast(cup2d_amr *a, int on) {
   if (!a) return CUP2D_EINVAL;
+  if (a->dist && !on) {
+    set_error("cup2d_amr_set_fast: a distributed context has the fast kernels only");
+    return CUP2D_ESTATE;
+  }
   a->fast = on != 0;
   return CUP2D_OK;
 }
@@ -417,9 +538,10 @@ int cup2d_amr_pressure_gradient_fast(cup2d_amr *a, double dt) {
   CUP2D_CUDA(cudaSetDevice(a->device));
   int rc = fast_setup(a);
   if (rc) return rc;
+  if ((rc = amr_dist_refresh(a, CUP2D_PRES))) return rc;
   const int grid = (int)((a->nb + A1_WARPS * 4 - 1) / (A1_WARPS * 4));
   amr_scalar_fast_kernel<1><<<grid, A1_NT, 0, a->stream>>>(a->f[CUP2D_PRES], a->f[CUP2D_TMPV], reinterpret_cast<const int4 *>(a->d_nbr4),
-                                                           a->d_irr_of, a->gt[2], a->d_h, a->d_faceflux, (int)a->nb, dt);
+                                                           a->d_irr_of, a->gt[2], a->d_h, flux_buf<1>(a), (int)a->nb, dt);
   CUP2D_CUDA(cudaGetLastError());
   return CUP2D_OK;
 }

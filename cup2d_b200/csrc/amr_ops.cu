@@ -284,6 +284,10 @@ static int upload_csr(cup2d_amr *a, int which) {
 // for them — they grow with the mesh, the compact ones with its level interfaces.
 static int gather(cup2d_amr *a, int which, const double *field, double *&lab) {
   int rc;
+  if (a->dist) {
+    set_error("this operator runs on the table-gather baseline kernels, which a distributed context does not have");
+    return CUP2D_ESTATE;
+  }
   if (!a->csr[which].rowptr && (rc = upload_csr(a, which))) return rc;
   if (!lab) CUP2D_CUDA(cudaMalloc(&lab, a->csr[which].nrows * sizeof(double)));
   amr_gather_kernel<<<grid_for(a->csr[which].nrows), 256, 0, a->stream>>>(a->csr[which], field, lab, LABD[which]);
@@ -392,7 +396,8 @@ int cup2d_amr_create(int64_t nblocks, const int32_t *level_ij, int32_t bpdx, int
 void cup2d_amr_destroy(cup2d_amr *a) {
   if (!a) return;
   cudaSetDevice(a->device);
-  for (auto p : a->f) cudaFree(p);
+  if (!a->dist)
+    for (auto p : a->f) cudaFree(p); // a distributed context borrows the field arrays (and the stream) of its Poisson context
   for (auto &c : a->csr) {
     cudaFree(c.rowptr); cudaFree(c.src_block); cudaFree(c.src_cc); cudaFree(c.w);
   }
@@ -406,7 +411,7 @@ void cup2d_amr_destroy(cup2d_amr *a) {
 #ifndef CUP2D_AMR_EMU
   if (a->poisson) cup2d_destroy(a->poisson);
 #endif
-  if (a->stream) cudaStreamDestroy(a->stream);
+  if (a->stream && !a->dist) cudaStreamDestroy(a->stream);
   if (a->plan) cup2d_amr_plan_destroy(a->plan);
   delete a;
 }
@@ -500,6 +505,31 @@ int cup2d_amr_adapt_tags(cup2d_amr *a, double rtol, int level_max, double *block
   return CUP2D_OK;
 }
 
+#ifndef CUP2D_AMR_EMU
+// distributed contexts: two sums and one maximum over all ranks, by the one-warp peer all-reduce of the Krylov kernels
+__global__ void amr_allreduce_kernel(double *v, Comm comm) {
+  double tot[2] = {v[0], v[1]}, mx = v[2];
+  peer_allreduce<2>(comm, tot, mx, threadIdx.x & 31);
+  if (threadIdx.x == 0) v[0] = tot[0], v[1] = tot[1], v[2] = mx;
+}
+static int dist_allreduce(cup2d_amr *a, double &s0, double &s1, double &mx) {
+  if (!a->dist || a->nranks == 1) return CUP2D_OK;
+  cup2d_sim *ps = a->poisson;
+  ps->h_scal[0] = s0, ps->h_scal[1] = s1, ps->h_scal[2] = mx;
+  CUP2D_CUDA(cudaMemcpyAsync(ps->d_scal, ps->h_scal, 3 * sizeof(double), cudaMemcpyHostToDevice, a->stream));
+  amr_allreduce_kernel<<<1, 32, 0, a->stream>>>(ps->d_scal, ps->comm);
+  CUP2D_CUDA(cudaGetLastError());
+  CUP2D_CUDA(cudaMemcpyAsync(ps->h_scal, ps->d_scal, 3 * sizeof(double), cudaMemcpyDeviceToHost, a->stream));
+  CUP2D_CUDA(cudaStreamSynchronize(a->stream));
+  s0 = ps->h_scal[0], s1 = ps->h_scal[1], mx = ps->h_scal[2];
+  return CUP2D_OK;
+}
+int amr_dist_refresh(cup2d_amr *a, int field) { return a->dist ? cup2d_halo_exchange(a->poisson, field) : CUP2D_OK; }
+#else
+static int dist_allreduce(cup2d_amr *, double &, double &, double &) { return CUP2D_OK; }
+int amr_dist_refresh(cup2d_amr *, int) { return CUP2D_OK; }
+#endif
+
 /* main.cpp:6579-6595 with h = the smallest cell size of the mesh */
 int cup2d_amr_compute_dt(cup2d_amr *a, double cfl, double *umax_out, double *dt_out) {
   CHECK_AMR(a);
@@ -508,8 +538,9 @@ int cup2d_amr_compute_dt(cup2d_amr *a, double cfl, double *umax_out, double *dt_
   CUP2D_CUDA(cudaGetLastError());
   int rc = block_partials(a, 1);
   if (rc) return rc;
-  double umax = 0;
+  double umax = 0, z0 = 0, z1 = 0;
   for (int64_t k = 0; k < a->nb; k++) umax = std::max(umax, a->h_part[k]);
+  if ((rc = dist_allreduce(a, z0, z1, umax))) return rc;
   const double h = a->hmin;
   const double dt_diff = 0.25 * h * h / (a->nu + 0.25 * h * umax), dt_adv = h / (umax + 1e-8);
   if (umax_out) *umax_out = umax;
@@ -554,8 +585,9 @@ static int weighted_mean(cup2d_amr *a, const double *p, double *mean) {
   CUP2D_CUDA(cudaGetLastError());
   int rc = block_partials(a, 2);
   if (rc) return rc;
-  double s = 0, w = 0;
+  double s = 0, w = 0, m0 = 0;
   for (int64_t k = 0; k < a->nb; k++) s += a->h_part[2 * k], w += a->h_part[2 * k + 1];
+  if ((rc = dist_allreduce(a, s, w, m0))) return rc;
   *mean = s / w;
   return CUP2D_OK;
 }
@@ -580,6 +612,112 @@ int cup2d_amr_pressure_correct(cup2d_amr *a, double dt) {
 }
 
 #ifndef CUP2D_AMR_EMU
+/* Several GPUs, second form: the mesh is DISTRIBUTED — rank r holds the blocks rank_begin[r] .. rank_begin[r+1] of the list
+ * (all ranks pass the same whole list) plus halo slots for every remote block its tables name, and computes only its own
+ * blocks.  The field arrays are those of the distributed Poisson context (cup2d_poisson_create_general_ranks), so a halo
+ * refresh is the whole-block peer pull of the uniform path (csrc/halo.cu) and the solve runs in place; the face fluxes of
+ * fillcases travel the same way, stored per block in a field that is free at that point; dt and the pressure means are
+ * all-reduced by the in-kernel peer all-reduce.  Fast kernels only.  Then cup2d_amr_peer_export / _attach; field upload and
+ * download move this rank's blocks. */
+int cup2d_amr_create_ranks(int64_t nblocks, const int32_t *level_ij, int32_t bpdx, int32_t bpdy, double h0, double nu, int32_t rank,
+                           int32_t nranks, const int64_t *rank_begin, int32_t device, cup2d_amr **out) {
+  if (!out || !level_ij || !rank_begin || nblocks <= 0 || !(h0 > 0) || nranks < 1 || rank < 0 || rank >= nranks ||
+      rank_begin[0] != 0 || rank_begin[nranks] != nblocks) {
+    set_error("cup2d_amr_create_ranks: bad arguments");
+    return CUP2D_EINVAL;
+  }
+  cup2d_amr_plan *plan = nullptr;
+  int rc = cup2d_amr_plan_create(nblocks, level_ij, bpdx, bpdy, &plan);
+  if (rc) return rc;
+  cup2d_amr *a = new cup2d_amr;
+  a->plan = plan;
+  a->device = device;
+  a->h0 = h0;
+  a->nu = nu;
+  a->dist = a->fast = true;
+  a->rank = rank;
+  a->nranks = nranks;
+  a->rank_begin.assign(rank_begin, rank_begin + nranks + 1);
+  auto fail = [&](int code) {
+    cup2d_amr_destroy(a);
+    return code;
+  };
+  const int64_t b0 = rank_begin[rank], b1 = rank_begin[rank + 1], nloc = b1 - b0;
+  a->nb = nloc;
+  // every remote block the stencil tables of this rank name: face neighbours, sources of its ghost rows, fine sides of its
+  // coarse faces (the Poisson rows add theirs inside the constructor below)
+  std::vector<int32_t> extra, n8(8 * nblocks);
+  if (cup2d_amr_plan_neighbours(plan, n8.data())) return fail(CUP2D_EINVAL);
+  for (int64_t k = b0; k < b1; k++)
+    for (int j = 0; j < 8; j++)
+      if (n8[8 * k + j] >= 0) extra.push_back(n8[8 * k + j]);
+  const int64_t nirr_g = cup2d_amr_plan_irregular(plan, nullptr);
+  std::vector<int32_t> irr(std::max<int64_t>(nirr_g, 1));
+  cup2d_amr_plan_irregular(plan, irr.data());
+  const int ncell[3] = {14 * 14 * 2, 10 * 10 * 2, 10 * 10};
+  for (int which = 0; which < 3; which++) {
+    int64_t nrows = 0;
+    const int64_t nnz = cup2d_amr_plan_ghosts(plan, which, &nrows, nullptr, nullptr, nullptr, nullptr, nullptr);
+    if (nnz < 0) return fail(CUP2D_EINVAL);
+    std::vector<int64_t> rp(nrows + 1);
+    std::vector<int32_t> dst(std::max<int64_t>(nrows, 1)), sb(std::max<int64_t>(nnz, 1)), sc(std::max<int64_t>(nnz, 1));
+    std::vector<double> w(std::max<int64_t>(nnz, 1));
+    cup2d_amr_plan_ghosts(plan, which, &nrows, rp.data(), dst.data(), sb.data(), sc.data(), w.data());
+    for (int64_t row = 0; row < nrows; row++) {
+      const int32_t blk = irr[dst[row] / ncell[which]];
+      if (blk < b0 || blk >= b1) continue;
+      for (int64_t e = rp[row]; e < rp[row + 1]; e++) extra.push_back(sb[e]);
+    }
+  }
+  {
+    const int64_t nf = cup2d_amr_plan_faces(plan, nullptr);
+    std::vector<int32_t> rec(5 * std::max<int64_t>(nf, 1));
+    cup2d_amr_plan_faces(plan, rec.data());
+    for (int64_t r = 0; r < nf; r++)
+      if (rec[5 * r + 2] >= b0 && rec[5 * r + 2] < b1) extra.push_back(rec[5 * r]);
+  }
+  // this rank's rows of the Poisson matrix (as cup2d_amr_set_ranks)
+  int64_t nnz = 0;
+  const int64_t nr = cup2d_amr_plan_poisson(plan, nullptr, &nnz, nullptr, nullptr, nullptr, nullptr);
+  if (nr < 0) return fail((int)nr);
+  std::vector<int32_t> nbr(4 * nblocks), rows(std::max<int64_t>(nr, 1)), rowptr(nr + 1), col(std::max<int64_t>(nnz, 1));
+  std::vector<double> val(std::max<int64_t>(nnz, 1));
+  cup2d_amr_plan_poisson(plan, nbr.data(), &nnz, rows.data(), rowptr.data(), col.data(), val.data());
+  const int64_t k0 = std::lower_bound(rows.begin(), rows.begin() + nr, (int32_t)(64 * b0)) - rows.begin();
+  const int64_t k1 = std::lower_bound(rows.begin(), rows.begin() + nr, (int32_t)(64 * b1)) - rows.begin();
+  std::vector<int32_t> my_rows(rows.begin() + k0, rows.begin() + k1), my_ptr(rowptr.begin() + k0, rowptr.begin() + k1 + 1);
+  for (auto &r : my_rows) r -= (int32_t)(64 * b0);
+  const int32_t e0 = my_ptr[0];
+  for (auto &e : my_ptr) e -= e0;
+  if ((rc = poisson_create_general_ranks_ex(nblocks, rank, nranks, rank_begin, nbr.data() + 4 * b0, k1 - k0, my_rows.data(),
+                                            my_ptr.data(), col.data() + e0, val.data() + e0, (int64_t)extra.size(), extra.data(),
+                                            device, &a->poisson)))
+    return fail(rc);
+  cup2d_sim *ps = a->poisson;
+  a->stream = ps->stream;
+  for (int f = 0; f < CUP2D_NFIELDS; f++) a->f[f] = ps->f[f];
+  std::vector<int32_t> slot_of(nblocks, -1);
+  for (int64_t k = 0; k < nloc; k++) slot_of[b0 + k] = (int32_t)k;
+  for (int64_t k = 0; k < ps->nhalo; k++) slot_of[ps->halo_gid[k]] = (int32_t)(nloc + k);
+  // cell size: own blocks and halo slots; the time step uses the smallest cell of the WHOLE mesh
+  std::vector<double> h(ps->nslots, h0);
+  a->hmin = h0;
+  for (int64_t g = 0; g < nblocks; g++) {
+    const double hg = h0 / (double)(1 << level_ij[3 * g]);
+    a->hmin = std::min(a->hmin, hg);
+    if (slot_of[g] >= 0) h[slot_of[g]] = hg;
+  }
+  a->h_ij.resize(2 * nloc);
+  for (int64_t k = 0; k < nloc; k++) a->h_ij[2 * k] = level_ij[3 * (b0 + k) + 1], a->h_ij[2 * k + 1] = level_ij[3 * (b0 + k) + 2];
+  a->h_part.resize(2 * nloc);
+  if (cudaMalloc(&a->d_part, 2 * nloc * sizeof(double)) != cudaSuccess || cudaMalloc(&a->d_h, h.size() * sizeof(double)) != cudaSuccess ||
+      cudaMemcpy(a->d_h, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess)
+    return fail(CUP2D_ECUDA);
+  if ((rc = amr_fast_setup_dist(a, slot_of, b0, b1))) return fail(rc);
+  *out = a;
+  return CUP2D_OK;
+}
+
 /* Several GPUs, first form: every rank holds the whole mesh and computes the stencil operators redundantly (bitwise the same
  * everywhere), the Poisson solve — the part that dominates a step — is distributed over the ranks by block ranges
  * (cup2d_poisson_create_general_ranks) and its result all-gathered over NVLink.  rank_begin[nranks+1] partitions the block
@@ -673,6 +811,10 @@ int cup2d_amr_poisson_solve(cup2d_amr *a, double tol_abs, double tol_rel, int ma
     if ((rc = cup2d_poisson_create_general(a->nb, nbr.data(), nr, rows.data(), rowptr.data(), col.data(), val.data(), a->device,
                                            &a->poisson)))
       return rc;
+  }
+  if (a->dist) { // the fields ARE the Poisson context's: b = tmp and x0 = pres are in place, so is the result
+    CUP2D_CUDA(cudaSetDevice(a->device));
+    return cup2d_poisson_solve(a->poisson, tol_abs, tol_rel, max_restarts, max_iter, iters, err);
   }
   if (a->nranks > 1) return poisson_solve_distributed(a, tol_abs, tol_rel, max_restarts, max_iter, iters, err);
   const size_t bytes = (size_t)a->nb * 64 * sizeof(double);

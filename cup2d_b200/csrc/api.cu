@@ -412,6 +412,16 @@ int cup2d_poisson_create_general_ranks(int64_t nblocks_global, int32_t rank, int
                                        const int32_t *nbr, int64_t n_irr, const int32_t *irr_rows,
                                        const int32_t *irr_rowptr, const int32_t *irr_col, const double *irr_val,
                                        int32_t device, cup2d_sim **out) {
+  return poisson_create_general_ranks_ex(nblocks_global, rank, nranks, rank_begin, nbr, n_irr, irr_rows, irr_rowptr, irr_col,
+                                         irr_val, 0, nullptr, device, out);
+}
+} // extern "C"
+// + n_extra further remote blocks that must be halo slots of this rank (the stencil tables of a distributed multi-level
+// context name blocks the Poisson rows do not)
+int cup2d::poisson_create_general_ranks_ex(int64_t nblocks_global, int32_t rank, int32_t nranks, const int64_t *rank_begin,
+                                           const int32_t *nbr, int64_t n_irr, const int32_t *irr_rows,
+                                           const int32_t *irr_rowptr, const int32_t *irr_col, const double *irr_val,
+                                           int64_t n_extra, const int32_t *extra_blocks, int32_t device, cup2d_sim **out) {
   CUP2D_REQUIRE(out && nbr && rank_begin && nblocks_global > 0, "cup2d_poisson_create_general_ranks: bad arguments");
   CUP2D_REQUIRE(nranks >= 1 && nranks <= MAX_RANKS && rank >= 0 && rank < nranks, "cup2d_poisson_create_general_ranks: bad rank/nranks (1..8 ranks)");
   CUP2D_REQUIRE(nblocks_global * 64 < (1LL << 31), "cup2d_poisson_create_general_ranks: more than 2^31 rows");
@@ -430,6 +440,10 @@ int cup2d_poisson_create_general_ranks(int64_t nblocks_global, int32_t rank, int
     CUP2D_REQUIRE(irr_col[j] >= 0 && irr_col[j] < nblocks_global * 64, "cup2d_poisson_create_general_ranks: column out of range");
     const int32_t g = irr_col[j] / 64;
     if (g < gb || g >= ge) halo.push_back(g);
+  }
+  for (int64_t k = 0; k < n_extra; k++) {
+    CUP2D_REQUIRE(extra_blocks[k] >= 0 && extra_blocks[k] < nblocks_global, "cup2d_poisson_create_general_ranks: extra block out of range");
+    if (extra_blocks[k] < gb || extra_blocks[k] >= ge) halo.push_back(extra_blocks[k]);
   }
   std::sort(halo.begin(), halo.end());
   halo.erase(std::unique(halo.begin(), halo.end()), halo.end());
@@ -489,6 +503,7 @@ int cup2d_poisson_create_general_ranks(int64_t nblocks_global, int32_t rank, int
   *out = s;
   return CUP2D_OK;
 }
+extern "C" {
 
 static int alloc_device_state(cup2d_sim *s) {
   int rc = upload_tables(s);

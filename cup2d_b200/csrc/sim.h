@@ -168,6 +168,10 @@ int poisson_solve(cup2d_sim *s, double tol_abs, double tol_rel, int max_restarts
                   int *iters, double *err);
 int halo_exchange_ptr(cup2d_sim *s, double *base, int dim, int peer_index, bool done_barrier = true);
 void swap_fields(cup2d_sim *s, int a, int b); // pointer swap, mirrored on the peer mappings
+int poisson_create_general_ranks_ex(int64_t nblocks_global, int32_t rank, int32_t nranks, const int64_t *rank_begin,
+                                    const int32_t *nbr, int64_t n_irr, const int32_t *irr_rows, const int32_t *irr_rowptr,
+                                    const int32_t *irr_col, const double *irr_val, int64_t n_extra,
+                                    const int32_t *extra_blocks, int32_t device, cup2d_sim **out);
 int dump_write_xdmf(const std::string &xdmf_path, const std::string &xyz_path, const std::string &attr_path, double time,
                     long ncell_total);
 int dump_write_all(int fd, const void *buf, size_t n, off_t off);

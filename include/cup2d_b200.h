@@ -298,6 +298,14 @@ int cup2d_amr_step(cup2d_amr *a, double cfl, double dt_in, double tol_abs, doubl
  * rank_begin[nranks+1] (cup2d_poisson_create_general_ranks) and its solution all-gathered over NVLink.  Call once, before the
  * first solve, then exchange the peer blobs exactly like cup2d_peer_export / cup2d_peer_attach. */
 int cup2d_amr_set_ranks(cup2d_amr *a, int32_t rank, int32_t nranks, const int64_t *rank_begin);
+/* Several GPUs (second form): the mesh itself is distributed.  Every rank passes the same whole block list; rank r then holds
+ * only the blocks rank_begin[r] .. rank_begin[r+1] (the reference's partition, main.cpp:6494-6504) plus halo slots for every
+ * remote block its tables name, and computes only its own blocks.  Its field arrays are those of the distributed Poisson
+ * context, so halo refreshes are the whole-block peer pulls of the uniform path, the solve runs in place, the face fluxes of
+ * fillcases cross a rank boundary inside a field array, and dt / the pressure means are all-reduced in a kernel.  Fast kernels
+ * only; cup2d_amr_field_upload / _download move this rank's blocks.  Follow with cup2d_amr_peer_export / _attach. */
+int cup2d_amr_create_ranks(int64_t nblocks, const int32_t *level_ij, int32_t bpdx, int32_t bpdy, double h0, double nu,
+                           int32_t rank, int32_t nranks, const int64_t *rank_begin, int32_t device, cup2d_amr **out);
 int cup2d_amr_peer_export(cup2d_amr *a, void *blob);
 int cup2d_amr_peer_attach(cup2d_amr *a, const void *all_blobs);
 
