@@ -146,6 +146,7 @@ assert worst < 1e-10 and all(r[1] == 8 for r in res) and its == 8 and abs(res[0]
     assert r.returncode == 0 and "WORST" in r.stdout, r.stdout[-1500:]
 
 
+@pytest.mark.skipif(os.environ.get("CUP2D_TEST_SLOW") != "1", reason="first (replicated-operators) form; the distributed form below is the default test")
 def test_multi_level_steps_on_three_ranks_emulated(emulated_library):
     """several GPUs on a multi-level mesh, first form (cup2d_amr_set_ranks): every rank holds the whole mesh and computes the
     stencil operators redundantly, the Poisson solve is distributed by block ranges and all-gathered through the peers' arrays.
@@ -196,6 +197,86 @@ for s in range(2):
 print("WORST", worst)
 assert worst < 1e-11
 ''' % (ROOT, os.path.join(ROOT, "tools"))
+    r = subprocess.run([sys.executable, "-c", code], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900,
+                       env=dict(os.environ, CUP2D_B200_LIB=emulated_library))
+    assert r.returncode == 0 and "WORST" in r.stdout, r.stdout[-1500:]
+
+
+def test_distributed_multi_level_mesh_on_three_ranks_emulated(emulated_library):
+    """several GPUs on a multi-level mesh, second form (cup2d_amr_create_ranks): the mesh itself is distributed by block ranges;
+    every rank holds its blocks plus halo slots for the remote blocks its tables name (face neighbours, ghost-row sources, fine
+    sides of its coarse faces, Poisson columns), refreshed by whole-block peer pulls; face fluxes cross rank boundaries inside a
+    field array; dt and the pressure means are all-reduced in a kernel.  Three ranks (uneven ranges) as threads of one process:
+    (1) the flux-corrected operators on the reference's 7-level run.sh mesh against the reference's own outputs; (2) two full
+    steps on a three-level mesh against the one-rank run."""
+    code = r'''
+import sys, threading, numpy as np
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+import bench_amr
+from cup2d_b200.amr import AmrSimulation
+W = 3
+bar, slots, errs = threading.Barrier(W), [None] * W, []
+class Dist:
+    def __init__(self, rank): self.rank = rank
+    def all_gather_object(self, out, obj):
+        slots[self.rank] = obj; bar.wait(); out[:] = slots; bar.wait()
+    def barrier(self): bar.wait()
+def on_ranks(fn):
+    res = [None] * W
+    def run(rank):
+        try:
+            res[rank] = fn(rank); bar.wait()
+        except Exception as e:
+            errs.append(repr(e)); bar.abort()
+    ths = [threading.Thread(target=run, args=(r,)) for r in range(W)]
+    [t.start() for t in ths]; [t.join() for t in ths]
+    assert not errs, errs
+    return res
+# (1) operators on the reference's mesh
+d = np.load(%r)
+blocks = np.ascontiguousarray(d["blocks"], dtype=np.int32); nb = len(blocks); rb = [0, 81, 199, nb]
+def ops(rank):
+    sl, dt = slice(rb[rank], rb[rank + 1]), float(d["dt"])
+    sim = AmrSimulation.distributed(blocks, int(d["bpdx"]), int(d["bpdy"]), float(d["h0"]), float(d["nu"]), rank, rb, Dist(rank))
+    sim.upload("vel", d["vel"][sl]); sim.advect_diffuse_rhs(dt); adv = sim.download("tmpV")
+    sim.upload("tmpV", d["udef"][sl]); sim.upload("chi", d["chi"][sl]); sim.upload("pold", d["pres"][sl])
+    sim.pressure_rhs(dt, True); rhs1 = sim.download("tmp")
+    sim.upload("pres", d["pres"][sl]); sim.pressure_gradient(dt); gp = sim.download("tmpV")
+    bar.wait(); sim.close()
+    return adv, rhs1, gp
+res = on_ranks(ops)
+worst = 0.0
+for i, name in enumerate(("adv", "rhs1", "gradp")):
+    got = np.concatenate([res[r][i] for r in range(W)])
+    worst = max(worst, np.abs(got - d[name]).max() / np.abs(d[name]).max())
+# (2) full steps
+mb = bench_amr.three_level_mesh(3, r1=0.3, r2=0.15, centre=(0.45, 0.55)); mn = len(mb); h0 = 1 / 8
+rng = np.random.default_rng(3)
+vel, pres = bench_amr.seeded_fields(mb, h0)
+vel, pres = vel + 0.05 * rng.uniform(-1, 1, vel.shape), pres + 0.05 * rng.uniform(-1, 1, pres.shape)
+def steps(sim, sl):
+    out = []
+    sim.upload("vel", vel[sl]); sim.upload("pres", pres[sl])
+    for s in range(2):
+        info = sim.step(cfl=0.5, max_iter=5)
+        out.append((info, sim.download("vel"), sim.download("pres")))
+    return out
+one = AmrSimulation(mb, 1, 1, h0, 1e-3); one.set_fast(True); ref = steps(one, slice(0, mn)); one.close()
+mrb = [0, mn // 3 + 7, 2 * mn // 3 - 5, mn]
+def dsteps(rank):
+    sim = AmrSimulation.distributed(mb, 1, 1, h0, 1e-3, rank, mrb, Dist(rank))
+    out = steps(sim, slice(mrb[rank], mrb[rank + 1]))
+    bar.wait(); sim.close()
+    return out
+res = on_ranks(dsteps)
+for s in range(2):
+    v = np.concatenate([res[r][s][1] for r in range(W)]); p = np.concatenate([res[r][s][2] for r in range(W)])
+    worst = max(worst, np.abs(v - ref[s][1]).max() / np.abs(ref[s][1]).max(), np.abs(p - ref[s][2]).max() / np.abs(ref[s][2]).max(),
+                abs(res[0][s][0][0] - ref[s][0][0]) / ref[s][0][0])
+    assert all(res[r][s][0] == res[0][s][0] for r in range(W)) and res[0][s][0][1] == ref[s][0][1] == 5
+print("WORST", worst)
+assert worst < 1e-11
+''' % (ROOT, os.path.join(ROOT, "tools"), os.path.join(ROOT, "tests", "golden", "amrlab_lmax8.npz"))
     r = subprocess.run([sys.executable, "-c", code], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900,
                        env=dict(os.environ, CUP2D_B200_LIB=emulated_library))
     assert r.returncode == 0 and "WORST" in r.stdout, r.stdout[-1500:]

@@ -351,7 +351,8 @@ def test_reference_amr_case_on_the_multi_level_device_path(tmp_path, form):
 
 def test_two_ranks_on_two_gpus_multi_level():
     """N>1 on real GPUs (skipped on a single-GPU box): the distributed general-rows Poisson solve and multi-level steps with
-    replicated operators (cup2d_poisson_create_general_ranks, cup2d_amr_set_ranks) against the same work on one GPU"""
+    replicated operators and with the mesh distributed (cup2d_poisson_create_general_ranks, cup2d_amr_set_ranks,
+    cup2d_amr_create_ranks) against the same work on one GPU"""
     import subprocess
     import sys
     import torch
@@ -363,5 +364,5 @@ def test_two_ranks_on_two_gpus_multi_level():
                        stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=400,
                        env=dict(os.environ, CUP2D_TEST_UNVALIDATED="1"))
     assert r.returncode == 0, r.stdout[-2000:]
-    for check in ("amr_poisson_ranks", "amr_step_ranks"):
+    for check in ("amr_poisson_ranks", "amr_step_ranks", "amr_distributed_ranks"):
         assert f'"check": "{check}"' in r.stdout

@@ -3,7 +3,7 @@ reference grows for its run.sh case (config C5 of SURVEY 8(d) at the chosen leve
 
   python tools/bench_amr.py [levelMax=9] [steps=10] [poisson_iters=10] [fast=1]
   python tools/bench_amr.py synthetic [base_level=9] [steps=10] [poisson_iters=10] [fast=1]     (config C5: 3 levels;
-      under torchrun on N GPUs: operators replicated, Poisson solve distributed)
+      under torchrun on N GPUs: the mesh distributed by block ranges, cup2d_amr_create_ranks)
 
 The mesh comes from oracle/_ref/ref_harness amrlab (which travels to the GPU box prebuilt), the fields are its seeded ones,
 bodies are left out (u_def = 0, chi = 0).  Prints one JSON line: blocks, cells, levels, ms per step with CUDA events on the
@@ -104,14 +104,17 @@ def main():
         vel, pres = seeded_fields(blocks, h0)
         world, rank, lrank = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
         t0 = time.time()
-        sim = AmrSimulation(blocks, 1, 1, h0, 1e-4, device=lrank)
-        if world > 1:   # under torchrun: operators replicated, Poisson solve distributed over the ranks (cup2d_amr_set_ranks)
+        if world > 1:   # under torchrun: the mesh distributed over the GPUs by block ranges (cup2d_amr_create_ranks)
             import torch
             import torch.distributed as dist
             torch.cuda.set_device(lrank)
             dist.init_process_group("nccl", device_id=torch.device("cuda", lrank))
-            sim.set_ranks(rank, [round(r * len(blocks) / world) for r in range(world + 1)], dist)
-        sim.set_fast(bool(fast))
+            rb = [round(r * len(blocks) / world) for r in range(world + 1)]
+            sim = AmrSimulation.distributed(blocks, 1, 1, h0, 1e-4, rank, rb, dist, device=lrank)
+            vel, pres = vel[rb[rank]:rb[rank + 1]], pres[rb[rank]:rb[rank + 1]]
+        else:
+            sim = AmrSimulation(blocks, 1, 1, h0, 1e-4, device=lrank)
+            sim.set_fast(bool(fast))
         sim.upload("vel", vel)
         sim.upload("pres", pres)
         sim.step(cfl=0.5, max_iter=1)          # first step builds the compact tables and the Poisson rows

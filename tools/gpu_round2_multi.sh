@@ -1,7 +1,7 @@
 #!/bin/bash
 # Multi-GPU call of round 2:   gpurun --gpus N --timeout 900 -- 'bash tools/gpu_round2_multi.sh N r02m'
 # 1. N-rank parity checks (uniform path incl. the kzr halo of the deferred x-update, tags/dump, bodies, the distributed
-#    general-rows Poisson solve, multi-level steps with replicated operators);  2. the contract bench line at N GPUs;
+#    general-rows Poisson solve, multi-level steps with replicated operators and with the mesh distributed);  2. the contract bench line at N GPUs;
 # 3. config C5 (synthetic 3-level mesh, 32 M cells) at N GPUs.
 set -u
 N=${1:-2}
@@ -23,6 +23,6 @@ try:
 except Exception as e:
     print("bench line unreadable:", e)
 PY
-echo "== 3. config C5 at $N GPUs (operators replicated, Poisson solve distributed)"
+echo "== 3. config C5 at $N GPUs (mesh distributed by block ranges, cup2d_amr_create_ranks)"
 timeout 400 $TR --master-port 29573 tools/bench_amr.py synthetic 9 10 10 1 > $OUT/bench_amr_c5_${N}gpu_$TAG.json 2> $OUT/bench_amr_c5_${N}gpu_$TAG.err
 echo "rc=$?"; tail -c 600 $OUT/bench_amr_c5_${N}gpu_$TAG.json; tail -c 300 $OUT/bench_amr_c5_${N}gpu_$TAG.err

@@ -194,5 +194,28 @@ if rank == 0:
     print(json.dumps({"check": "amr_step_ranks", "ranks": world, "blocks": mnb, "rel_err_vs_one_gpu": amr_step_err,
                       "ranks_identical": bool(same)}), flush=True)
     assert amr_step_err < 1e-9 and same
+
+# ---- the same steps with the mesh itself DISTRIBUTED over the GPUs (cup2d_amr_create_ranks) ----
+mrb = [round(r * mnb / world) for r in range(world + 1)]
+dsim = AmrSimulation.distributed(mblocks, 1, 1, mh0, 1e-3, rank, mrb, dist, device=lrank)
+sl = slice(mrb[rank], mrb[rank + 1])
+dsim.upload("vel", mvel[sl])
+dsim.upload("pres", mpres[sl])
+dgot = []
+for _ in range(2):
+    info = dsim.step(cfl=0.5, max_iter=10)
+    dgot.append((info, dsim.download("vel"), dsim.download("pres")))
+dist.barrier()
+dsim.close()
+parts = [None] * world
+dist.all_gather_object(parts, dgot)
+if rank == 0:
+    derr = 0.0
+    for s_ in range(2):
+        v = np.concatenate([parts[r][s_][1] for r in range(world)])
+        p_ = np.concatenate([parts[r][s_][2] for r in range(world)])
+        derr = max(derr, float(np.abs(v - ref[s_][1]).max() / np.abs(ref[s_][1]).max()), float(np.abs(p_ - ref[s_][2]).max() / np.abs(ref[s_][2]).max()))
+    print(json.dumps({"check": "amr_distributed_ranks", "ranks": world, "blocks": mnb, "rel_err_vs_one_gpu": derr}), flush=True)
+    assert derr < 1e-9
 dist.barrier()
 dist.destroy_process_group()
