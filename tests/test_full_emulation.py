@@ -233,7 +233,7 @@ def on_ranks(fn):
     assert not errs, errs
     return res
 # (1) operators on the reference's mesh
-d = np.load(%r)
+d = dict(np.load(%r))   # read everything now: the lazy NpzFile is not safe to read from several threads
 blocks = np.ascontiguousarray(d["blocks"], dtype=np.int32); nb = len(blocks); rb = [0, 81, 199, nb]
 def ops(rank):
     sl, dt = slice(rb[rank], rb[rank + 1]), float(d["dt"])
@@ -277,7 +277,8 @@ for s in range(2):
 print("WORST", worst)
 assert worst < 1e-11
 ''' % (ROOT, os.path.join(ROOT, "tools"), os.path.join(ROOT, "tests", "golden", "amrlab_lmax8.npz"))
-    r = subprocess.run([sys.executable, "-c", code], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900,
+    r = subprocess.run([sys.executable, "-c", code], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300,  # a rank that dies leaves the others spinning on its flags
+                      
                        env=dict(os.environ, CUP2D_B200_LIB=emulated_library))
     assert r.returncode == 0 and "WORST" in r.stdout, r.stdout[-1500:]
 
