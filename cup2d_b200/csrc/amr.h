@@ -52,6 +52,8 @@ struct cup2d_amr;
 // distributed contexts (cup2d_amr_create_ranks): refresh the halo slots of `field` from the owners (whole-block peer pulls,
 // csrc/halo.cu) before a kernel reads neighbours; a no-op otherwise
 extern "C" int amr_dist_refresh(cup2d_amr *a, int field);
+// distributed contexts: v[0..n) summed over all ranks (identical result everywhere); a no-op otherwise
+extern "C" int amr_dist_sum(cup2d_amr *a, double *v, int n);
 // fast-kernel tables of a distributed context for its block range [b0, b1): slot_of[global block] = local slot or -1
 int amr_fast_setup_dist(cup2d_amr *a, const std::vector<int32_t> &slot_of, int64_t b0, int64_t b1);
 
@@ -76,6 +78,7 @@ struct cup2d_amr {
   int rank = 0, nranks = 1;
   std::vector<int64_t> rank_begin;
   bool dist = false;                // cup2d_amr_create_ranks: this context holds only its own block range (+ halo slots)
+  int64_t gbegin = 0, nglobal = 0;  // distributed contexts: first own block in the global list, size of that list
   // fast paths (csrc/amr_fast.cu)
   bool fast = false;                // cup2d_amr_set_fast: the operator entry points dispatch to the fast kernels
   int *d_nbr4 = nullptr;            // [nb][4] W,E,S,N: same-level block, -1 wall, -2 coarser/finer

@@ -525,9 +525,20 @@ static int dist_allreduce(cup2d_amr *a, double &s0, double &s1, double &mx) {
   return CUP2D_OK;
 }
 int amr_dist_refresh(cup2d_amr *a, int field) { return a->dist ? cup2d_halo_exchange(a->poisson, field) : CUP2D_OK; }
+int amr_dist_sum(cup2d_amr *a, double *v, int n) {
+  for (int k = 0; k < n; k += 2) {
+    double s0 = v[k], s1 = k + 1 < n ? v[k + 1] : 0.0, mx = 0.0;
+    const int rc = dist_allreduce(a, s0, s1, mx);
+    if (rc) return rc;
+    v[k] = s0;
+    if (k + 1 < n) v[k + 1] = s1;
+  }
+  return CUP2D_OK;
+}
 #else
 static int dist_allreduce(cup2d_amr *, double &, double &, double &) { return CUP2D_OK; }
 int amr_dist_refresh(cup2d_amr *, int) { return CUP2D_OK; }
+int amr_dist_sum(cup2d_amr *, double *, int) { return CUP2D_OK; }
 #endif
 
 /* main.cpp:6579-6595 with h = the smallest cell size of the mesh */
@@ -644,6 +655,8 @@ int cup2d_amr_create_ranks(int64_t nblocks, const int32_t *level_ij, int32_t bpd
   };
   const int64_t b0 = rank_begin[rank], b1 = rank_begin[rank + 1], nloc = b1 - b0;
   a->nb = nloc;
+  a->gbegin = b0;
+  a->nglobal = nblocks;
   // every remote block the stencil tables of this rank name: face neighbours, sources of its ghost rows, fine sides of its
   // coarse faces (the Poisson rows add theirs inside the constructor below)
   std::vector<int32_t> extra, n8(8 * nblocks);

@@ -190,7 +190,7 @@ int cup2d_amr_shape_integrals(cup2d_amr *a, int shape, double lambda, double dt,
   if (rc) return rc;
   for (int q = 0; q < 7; q++) out7[q] = 0.0;
   const AmrShapeView v = view_of(a->shapes[shape]);
-  if (v.nob == 0) return CUP2D_OK;
+  if (v.nob == 0) return amr_dist_sum(a, out7, 7); // a rank that holds no block of this shape still takes part in the sum
   if (v.nob > a->shape_part_cap) {
     cudaFree(a->d_shape_part);
     a->d_shape_part = nullptr, a->shape_part_cap = 0;
@@ -206,7 +206,7 @@ int cup2d_amr_shape_integrals(cup2d_amr *a, int shape, double lambda, double dt,
   CUP2D_CUDA(cudaStreamSynchronize(a->stream));
   for (int k = 0; k < v.nob; k++)
     for (int q = 0; q < 7; q++) out7[q] += a->h_shape_part[(size_t)k * 7 + q];
-  return CUP2D_OK;
+  return amr_dist_sum(a, out7, 7);
 }
 
 int cup2d_amr_penalize(cup2d_amr *a, int shape, double lambda, double dt, double cx, double cy, double us, double vs,
@@ -245,7 +245,10 @@ int cup2d_amr_dump(cup2d_amr *a, double time, const char *path) {
   if (rc) return rc;
   const std::string base(path);
   const std::string xyz_path = base + ".xyz.raw", attr_path = base + ".attr.raw", xdmf_path = base + ".xdmf2";
-  if ((rc = dump_write_xdmf(xdmf_path, xyz_path, attr_path, time, (long)a->nb * 64))) return rc;
+  const bool dist = a->dist && a->nranks > 1;   // every rank writes its own byte range, the last one the descriptor (main.cpp:3387-3390)
+  if ((!dist || a->rank == a->nranks - 1) &&
+      (rc = dump_write_xdmf(xdmf_path, xyz_path, attr_path, time, (long)(dist ? a->nglobal : a->nb) * 64)))
+    return rc;
   const int CHUNK = (int)std::min<int64_t>(a->nb, 16384);
   const size_t nx = (size_t)CHUNK * 64 * 8, na = (size_t)CHUNK * 64 * 3;
   float *d_buf = nullptr, *h_buf = nullptr;
@@ -255,7 +258,8 @@ int cup2d_amr_dump(cup2d_amr *a, double time, const char *path) {
     set_error("cup2d_amr_dump: cannot allocate the pinned staging buffer");
     return CUP2D_ECUDA;
   }
-  const int fx = open(xyz_path.c_str(), O_CREAT | O_WRONLY | O_TRUNC, 0644), fa = open(attr_path.c_str(), O_CREAT | O_WRONLY | O_TRUNC, 0644);
+  const int oflags = O_CREAT | O_WRONLY | (dist ? 0 : O_TRUNC);
+  const int fx = open(xyz_path.c_str(), oflags, 0644), fa = open(attr_path.c_str(), oflags, 0644);
   rc = (fx < 0 || fa < 0) ? CUP2D_EINVAL : CUP2D_OK;
   for (int64_t b0 = 0; rc == CUP2D_OK && b0 < a->nb; b0 += CHUNK) {
     const int nb = (int)std::min<int64_t>(CHUNK, a->nb - b0);
@@ -268,7 +272,7 @@ int cup2d_amr_dump(cup2d_amr *a, double time, const char *path) {
       rc = CUP2D_ECUDA;
       break;
     }
-    const off_t cell0 = (off_t)b0 * 64;
+    const off_t cell0 = (off_t)((dist ? a->gbegin : 0) + b0) * 64;
     if (dump_write_all(fx, h_buf, ncell * 8 * sizeof(float), cell0 * 8 * (off_t)sizeof(float)) ||
         dump_write_all(fa, h_buf + nx, ncell * 3 * sizeof(float), cell0 * 3 * (off_t)sizeof(float)))
       rc = CUP2D_EINVAL;

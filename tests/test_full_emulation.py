@@ -207,8 +207,8 @@ def test_distributed_multi_level_mesh_on_three_ranks_emulated(emulated_library):
     every rank holds its blocks plus halo slots for the remote blocks its tables name (face neighbours, ghost-row sources, fine
     sides of its coarse faces, Poisson columns), refreshed by whole-block peer pulls; face fluxes cross rank boundaries inside a
     field array; dt and the pressure means are all-reduced in a kernel.  Three ranks (uneven ranges) as threads of one process:
-    (1) the flux-corrected operators on the reference's 7-level run.sh mesh against the reference's own outputs; (2) two full
-    steps on a three-level mesh against the one-rank run."""
+    (1) on the reference's 7-level run.sh mesh the body sums / blend / u_def assembly against the one-rank context and the
+    flux-corrected operators against the reference's own outputs; (2) two full steps on a three-level mesh against the one-rank run."""
     code = r'''
 import sys, threading, numpy as np
 sys.path.insert(0, %r); sys.path.insert(0, %r)
@@ -235,9 +235,23 @@ def on_ranks(fn):
 # (1) operators on the reference's mesh
 d = dict(np.load(%r))   # read everything now: the lazy NpzFile is not safe to read from several threads
 blocks = np.ascontiguousarray(d["blocks"], dtype=np.int32); nb = len(blocks); rb = [0, 81, 199, nb]
+rng = np.random.default_rng(11)
+ids = np.sort(rng.choice(nb, 40, replace=False)).astype(np.int32)      # a body whose obstacle blocks lie on all three ranks
+X, ud = rng.uniform(-0.3, 1.0, (len(ids), 8, 8)), rng.uniform(-1, 1, (len(ids), 8, 8, 2))
+body = (1e7, float(d["dt"]), 0.9, 0.5)
+one = AmrSimulation(blocks, int(d["bpdx"]), int(d["bpdy"]), float(d["h0"]), float(d["nu"]))
+one.upload("vel", d["vel"]); one.upload("chi", d["chi"]); one.shape_set(0, ids, X, ud)
+want_q = one.shape_integrals(0, *body)
+one.penalize(0, *body, 0.1, -0.2, 0.7); want_v = one.download("vel"); one.udef_assemble(); want_t = one.download("tmpV")
+one.close()
 def ops(rank):
     sl, dt = slice(rb[rank], rb[rank + 1]), float(d["dt"])
     sim = AmrSimulation.distributed(blocks, int(d["bpdx"]), int(d["bpdy"]), float(d["h0"]), float(d["nu"]), rank, rb, Dist(rank))
+    mine = (ids >= rb[rank]) & (ids < rb[rank + 1])
+    sim.upload("vel", d["vel"][sl]); sim.upload("chi", d["chi"][sl]); sim.shape_set(0, ids[mine] - rb[rank], X[mine], ud[mine])
+    q = sim.shape_integrals(0, *body)                                   # all-reduced: the same seven sums on every rank
+    sim.penalize(0, *body, 0.1, -0.2, 0.7); pv = sim.download("vel"); sim.udef_assemble(); pt = sim.download("tmpV")
+    assert np.abs(q - want_q).max() <= 1e-12 * np.abs(want_q).max() and np.array_equal(pv, want_v[sl]) and np.array_equal(pt, want_t[sl])
     sim.upload("vel", d["vel"][sl]); sim.advect_diffuse_rhs(dt); adv = sim.download("tmpV")
     sim.upload("tmpV", d["udef"][sl]); sim.upload("chi", d["chi"][sl]); sim.upload("pold", d["pres"][sl])
     sim.pressure_rhs(dt, True); rhs1 = sim.download("tmp")
