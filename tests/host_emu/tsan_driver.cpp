@@ -92,6 +92,21 @@ int main(int argc, char **argv) {
       CHECK(cup2d_amr_step(a, 0.5, 0.0, 0.0, 0.0, 0, 2, &dt, &it, &err));
       printf("multi-level step (fast=%d): %lld blocks dt %.3e iters %d err %.3e\n", fast, (long long)n, dt, it, err);
     }
+    { // bodies, tagging and dump on the same mesh: one shape over blocks of both levels
+      std::vector<int32_t> ids = {0, 5, 6, 9, (int32_t)n - 1};
+      std::vector<double> X(ids.size() * 64), U(ids.size() * 128), q(7), linf(n);
+      for (size_t i = 0; i < X.size(); i++) X[i] = 0.5 + 0.6 * std::sin(0.7 * i);
+      for (size_t i = 0; i < U.size(); i++) U[i] = 0.3 * std::cos(0.31 * i);
+      CHECK(cup2d_amr_field_upload(a, CUP2D_CHI, pres.data()));
+      CHECK(cup2d_amr_shape_set(a, 0, (int)ids.size(), ids.data(), X.data(), U.data()));
+      CHECK(cup2d_amr_shape_integrals(a, 0, 1e7, 1e-3, 0.4, 0.3, q.data()));
+      CHECK(cup2d_amr_penalize(a, 0, 1e7, 1e-3, 0.4, 0.3, 0.1, -0.2, 0.5));
+      CHECK(cup2d_amr_udef_assemble(a));
+      CHECK(cup2d_amr_adapt_tags(a, 2.0, 4, linf.data()));
+      CHECK(cup2d_amr_dump(a, 0.5, "/tmp/cup2d_sanitizer_dump"));
+      if (!std::isfinite(q[0] + q[6] + linf[0])) return 4;
+      printf("multi-level bodies / tags / dump: PM %.3e AM %.3e linf[0] %.3e\n", q[0], q[6], linf[0]);
+    }
     cup2d_amr_destroy(a);
   }
   return 0;

@@ -313,7 +313,7 @@ def test_no_data_races_under_thread_sanitizer():
                        env=dict(os.environ, TSAN_OPTIONS="halt_on_error=0 report_signal_unsafe=0"))
     assert r.returncode == 0, r.stdout[-3000:]
     assert "ThreadSanitizer" not in r.stdout, r.stdout[-3000:]
-    assert r.stdout.count("multi-level step") == 2 and "uniform step" in r.stdout
+    assert r.stdout.count("multi-level step") == 2 and "uniform step" in r.stdout and "bodies / tags / dump" in r.stdout
 
 
 def test_no_out_of_bounds_or_misaligned_access_under_address_sanitizer(golden_dir, tmp_path):
@@ -334,6 +334,7 @@ def test_no_out_of_bounds_or_misaligned_access_under_address_sanitizer(golden_di
     r = subprocess.run([exe], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=1800, env=env)
     assert r.returncode == 0 and "runtime error" not in r.stdout and "AddressSanitizer" not in r.stdout, r.stdout[-3000:]
     assert r.stdout.count("multi-level step") == 2 and "uniform step" in r.stdout and "nan" not in r.stdout.lower()
+    assert "bodies / tags / dump" in r.stdout
     if os.environ.get("CUP2D_TEST_SLOW") == "1":
         d = np.load(os.path.join(golden_dir, "amrlab_lmax8.npz"))
         mesh = tmp_path / "mesh.bin"
