@@ -84,3 +84,24 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert line["e2e"] == {"value": line["value"], "unit": line["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     for k in ("metric", "n_gpus", "steps", "warmup", "ms_per_step", "scaling", "dtype", "data", "config"):
         assert k in line
+
+
+def test_multi_rank_constructors_reject_bad_partitions_before_touching_a_device():
+    """argument errors of the rank-aware constructors are reported as CUP2D_EINVAL with a message, GPU or not"""
+    import ctypes as C
+    from cup2d_b200 import lib as L
+    lib = L.load_library()
+    I32, I64 = C.POINTER(C.c_int32), C.POINTER(C.c_int64)
+    nbr = np.full(8, -1, dtype=np.int32)
+    h = C.c_void_p()
+    for rank, nranks, rb in ((2, 2, [0, 1, 2]), (0, 2, [0, 0, 2]), (0, 2, [1, 1, 2]), (0, 9, list(range(10)))):
+        rb_a = np.array(rb, dtype=np.int64)
+        rc = lib.cup2d_poisson_create_general_ranks(int(rb[-1]), rank, nranks, rb_a.ctypes.data_as(I64), nbr.ctypes.data_as(I32), 0, None, None,
+                                                    None, None, 0, C.byref(h))
+        assert rc == -1 and lib.cup2d_last_error(), (rank, nranks, rb)      # CUP2D_EINVAL
+    blocks = np.array([[0, 0, 0]], dtype=np.int32)
+    a = C.c_void_p()
+    for rank, nranks, rb in ((1, 1, [0, 1]), (0, 1, [0, 2]), (0, 2, [0, 1, 1])):
+        rb_a = np.array(rb, dtype=np.int64)
+        rc = lib.cup2d_amr_create_ranks(1, blocks.ctypes.data_as(I32), 1, 1, 0.125, 1e-3, rank, nranks, rb_a.ctypes.data_as(I64), 0, C.byref(a))
+        assert rc != 0 and not a.value, (rank, nranks, rb)
