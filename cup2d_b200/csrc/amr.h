@@ -79,6 +79,7 @@ struct cup2d_amr {
   std::vector<int64_t> rank_begin;
   bool dist = false;                // cup2d_amr_create_ranks: this context holds only its own block range (+ halo slots)
   int64_t gbegin = 0, nglobal = 0;  // distributed contexts: first own block in the global list, size of that list
+  std::vector<int32_t> slot_of;     // distributed contexts: global block -> local slot (own blocks, then halo slots) or -1
   // fast paths (csrc/amr_fast.cu)
   bool fast = false;                // cup2d_amr_set_fast: the operator entry points dispatch to the fast kernels
   int *d_nbr4 = nullptr;            // [nb][4] W,E,S,N: same-level block, -1 wall, -2 coarser/finer

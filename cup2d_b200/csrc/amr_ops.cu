@@ -258,13 +258,35 @@ __global__ void amr_fluxcorr_kernel(const CoarseFace *__restrict__ cf, int ncf, 
 static int grid_for(int64_t n) { return (int)std::min<int64_t>((n + 255) / 256, 148 * 16); }
 
 static int upload_csr(cup2d_amr *a, int which) {
-  const int64_t nnz = cup2d_amr_plan_stencil(a->plan, which, nullptr, nullptr, nullptr, nullptr);
+  int64_t nnz = cup2d_amr_plan_stencil(a->plan, which, nullptr, nullptr, nullptr, nullptr);
   if (nnz < 0) return CUP2D_EINVAL;
-  const int64_t nrows = a->nb * LABN[which] * LABN[which] * LABD[which];
-  std::vector<int64_t> rp(nrows + 1);
+  const int64_t per_block = LABN[which] * LABN[which] * LABD[which];
+  const int64_t nrows = a->nb * per_block;
+  std::vector<int64_t> rp((a->dist ? a->nglobal : a->nb) * per_block + 1);
   std::vector<int32_t> sb(nnz), sc(nnz);
   std::vector<double> w(nnz);
   cup2d_amr_plan_stencil(a->plan, which, rp.data(), sb.data(), sc.data(), w.data());
+  if (a->dist) { // the rows of this rank's blocks (contiguous: rows are in block order), sources renumbered to local slots
+    const int64_t r0 = a->gbegin * per_block, e0 = rp[r0], e1 = rp[r0 + nrows];
+    for (int64_t e = e0; e < e1; e++) {
+      sb[e] = a->slot_of[sb[e]];
+      if (sb[e] < 0) {
+        set_error("distributed context: a lab source lies outside the halo set");
+        return CUP2D_EINVAL;
+      }
+    }
+    std::vector<int64_t> rpl(nrows + 1);
+    for (int64_t r = 0; r <= nrows; r++) rpl[r] = rp[r0 + r] - e0;
+    rp.swap(rpl);
+    auto keep = [&](auto &v) {
+      v.erase(v.begin() + e1, v.end());
+      v.erase(v.begin(), v.begin() + e0);
+    };
+    keep(sb);
+    keep(sc);
+    keep(w);
+    nnz = e1 - e0;
+  }
   Csr &c = a->csr[which];
   c.nrows = nrows;
   CUP2D_CUDA(cudaMalloc(&c.rowptr, (nrows + 1) * sizeof(int64_t)));
@@ -284,7 +306,7 @@ static int upload_csr(cup2d_amr *a, int which) {
 // for them — they grow with the mesh, the compact ones with its level interfaces.
 static int gather(cup2d_amr *a, int which, const double *field, double *&lab) {
   int rc;
-  if (a->dist) {
+  if (a->dist && which != 1 && which != 3) { // (1 and 3: the labs of the tagging field, whose sources are in the halo set)
     set_error("this operator runs on the table-gather baseline kernels, which a distributed context does not have");
     return CUP2D_ESTATE;
   }
@@ -495,6 +517,7 @@ int cup2d_amr_adapt_tags(cup2d_amr *a, double rtol, int level_max, double *block
   }
   CUP2D_CUDA(cudaSetDevice(a->device));
   int rc;
+  if ((rc = amr_dist_refresh(a, CUP2D_VEL)) || (rc = amr_dist_refresh(a, CUP2D_CHI))) return rc;
   if ((rc = gather(a, 1, a->f[CUP2D_VEL], a->lab[1])) || (rc = gather(a, 3, a->f[CUP2D_CHI], a->lab[3]))) return rc;
   amr_vorticity_kernel<<<grid_for(a->nb * 64), 256, 0, a->stream>>>(a->lab[1], a->f[CUP2D_TMP], a->d_h, a->nb * 64);
   amr_tag_block_kernel<<<grid_for(a->nb), 256, 0, a->stream>>>(a->lab[3], a->f[CUP2D_TMP], a->d_h,
@@ -667,8 +690,8 @@ int cup2d_amr_create_ranks(int64_t nblocks, const int32_t *level_ij, int32_t bpd
   const int64_t nirr_g = cup2d_amr_plan_irregular(plan, nullptr);
   std::vector<int32_t> irr(std::max<int64_t>(nirr_g, 1));
   cup2d_amr_plan_irregular(plan, irr.data());
-  const int ncell[3] = {14 * 14 * 2, 10 * 10 * 2, 10 * 10};
-  for (int which = 0; which < 3; which++) {
+  const int ncell[4] = {14 * 14 * 2, 10 * 10 * 2, 10 * 10, 16 * 16}; // (3: the chi lab of the tagging rule)
+  for (int which = 0; which < 4; which++) {
     int64_t nrows = 0;
     const int64_t nnz = cup2d_amr_plan_ghosts(plan, which, &nrows, nullptr, nullptr, nullptr, nullptr, nullptr);
     if (nnz < 0) return fail(CUP2D_EINVAL);
@@ -712,6 +735,7 @@ int cup2d_amr_create_ranks(int64_t nblocks, const int32_t *level_ij, int32_t bpd
   std::vector<int32_t> slot_of(nblocks, -1);
   for (int64_t k = 0; k < nloc; k++) slot_of[b0 + k] = (int32_t)k;
   for (int64_t k = 0; k < ps->nhalo; k++) slot_of[ps->halo_gid[k]] = (int32_t)(nloc + k);
+  a->slot_of = slot_of;
   // cell size: own blocks and halo slots; the time step uses the smallest cell of the WHOLE mesh
   std::vector<double> h(ps->nslots, h0);
   a->hmin = h0;

@@ -208,7 +208,8 @@ def test_distributed_multi_level_mesh_on_three_ranks_emulated(emulated_library):
     sides of its coarse faces, Poisson columns), refreshed by whole-block peer pulls; face fluxes cross rank boundaries inside a
     field array; dt and the pressure means are all-reduced in a kernel.  Three ranks (uneven ranges) as threads of one process:
     (1) on the reference's 7-level run.sh mesh the body sums / blend / u_def assembly against the one-rank context and the
-    flux-corrected operators against the reference's own outputs; (2) two full steps on a three-level mesh against the one-rank run."""
+    flux-corrected operators and adapt()'s tagging field against the reference's own outputs; (2) two full steps on a
+    three-level mesh against the one-rank run."""
     code = r'''
 import sys, threading, numpy as np
 sys.path.insert(0, %r); sys.path.insert(0, %r)
@@ -263,6 +264,21 @@ worst = 0.0
 for i, name in enumerate(("adv", "rhs1", "gradp")):
     got = np.concatenate([res[r][i] for r in range(W)])
     worst = max(worst, np.abs(got - d[name]).max() / np.abs(d[name]).max())
+# (1b) adapt()'s tagging field on the reference's mesh with its fish
+g = dict(np.load(%r))
+def tags(rank):
+    sl = slice(rb[rank], rb[rank + 1])
+    sim = AmrSimulation.distributed(blocks, int(g["bpdx"]), int(g["bpdy"]), float(g["h0"]), 4e-5, rank, rb, Dist(rank))
+    sim.upload("vel", g["vel"][sl]); sim.upload("chi", g["chi"][sl])
+    out = (sim.adapt_tags(float(g["rtol"]), int(g["level_max"])), sim.download("tmp"))
+    bar.wait(); sim.close()
+    return out
+assert np.array_equal(g["blocks"], d["blocks"])
+res = on_ranks(tags)
+field = np.concatenate([res[r][1] for r in range(W)]).reshape(nb, 8, 8); linf = np.concatenate([res[r][0] for r in range(W)])
+wl = np.abs(g["tagfield"]).reshape(nb, -1).max(axis=1)
+worst = max(worst, np.abs(field - g["tagfield"]).max() / np.abs(g["tagfield"]).max())
+assert np.array_equal(linf > g["rtol"], wl > g["rtol"]) and np.array_equal(linf < g["ctol"], wl < g["ctol"])
 # (2) full steps
 mb = bench_amr.three_level_mesh(3, r1=0.3, r2=0.15, centre=(0.45, 0.55)); mn = len(mb); h0 = 1 / 8
 rng = np.random.default_rng(3)
@@ -290,7 +306,8 @@ for s in range(2):
     assert all(res[r][s][0] == res[0][s][0] for r in range(W)) and res[0][s][0][1] == ref[s][0][1] == 5
 print("WORST", worst)
 assert worst < 1e-11
-''' % (ROOT, os.path.join(ROOT, "tools"), os.path.join(ROOT, "tests", "golden", "amrlab_lmax8.npz"))
+''' % (ROOT, os.path.join(ROOT, "tools"), os.path.join(ROOT, "tests", "golden", "amrlab_lmax8.npz"),
+       os.path.join(ROOT, "tests", "golden", "amrtags_lmax8.npz"))
     r = subprocess.run([sys.executable, "-c", code], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300,  # a rank that dies leaves the others spinning on its flags
                       
                        env=dict(os.environ, CUP2D_B200_LIB=emulated_library))
