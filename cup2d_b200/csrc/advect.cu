@@ -63,12 +63,15 @@ __host__ __device__ __forceinline__ int adv_src_slot(int cx, int cy) {
 // MODE 0: out = tot (raw K, undivided)   1: old == in (stage 1)   2: old is a separate field (stage 2)
 // Both passes run through ONE copy of the fully unrolled line code (a 2-trip loop with run-time strides)
 // instead of two specialised copies: halves the instruction footprint (I-cache), profiles/r01g.
-template <int MODE>
+// DEVFAC: the dt-dependent factors come from device memory (StepFactors, written by k_step_factors) instead of the
+// by-value arguments, so that a time step captured in a CUDA graph needs no host-supplied dt.
+template <int MODE, bool DEVFAC>
 __global__ void __launch_bounds__(NT_ADV, 4)
 advect_stage_kernel(const double *__restrict__ in, const double *__restrict__ old,
                     double *__restrict__ out, const int *__restrict__ tiles,
                     const int *__restrict__ tile_org, const unsigned *__restrict__ lut, int nbx, int nby,
-                    int nloc, double afac, double dfac, double ofac) {
+                    int nloc, double afac_arg, double dfac_arg, double ofac, const StepFactors *__restrict__ sf) {
+  const double afac = DEVFAC ? sf->afac : afac_arg, dfac = DEVFAC ? sf->dfac : dfac_arg;
   extern __shared__ __align__(128) unsigned char smem[];
   double2 *stg = reinterpret_cast<double2 *>(smem);
   double *su = reinterpret_cast<double *>(smem + OFF_SU);
@@ -208,10 +211,11 @@ advect_stage_kernel(const double *__restrict__ in, const double *__restrict__ ol
 }
 
 typedef void (*adv_fn)(const double *, const double *, double *, const int *, const int *, const unsigned *, int,
-                       int, int, double, double, double);
+                       int, int, double, double, double, const StepFactors *);
 
+// dev: null (factors from dt) or the device-resident factors of the current step
 int launch_advect(cup2d_sim *s, const double *in, const double *old, double *out, double coef,
-                  double dt, bool raw) {
+                  double dt, bool raw, const StepFactors *dev) {
   static PerDeviceOnce constants;
   int rc = constants.run(s->device, []() -> int {
     CUP2D_CUDA(cudaMemcpyToSymbol(cW, hW, sizeof hW));
@@ -230,9 +234,10 @@ int launch_advect(cup2d_sim *s, const double *in, const double *old, double *out
     CUP2D_CUDA(cudaMemcpy(s->d_adv_lut, lut.data(), lut.size() * sizeof(unsigned), cudaMemcpyHostToDevice));
   }
   const int mode = raw ? 0 : (old == in ? 1 : 2);
-  const adv_fn fn = mode == 0 ? advect_stage_kernel<0> : mode == 1 ? advect_stage_kernel<1> : advect_stage_kernel<2>;
-  static PerDeviceOnce configured[3];
-  rc = configured[mode].run(s->device, [fn]() -> int {
+  const adv_fn fn = dev ? (mode == 0 ? advect_stage_kernel<0, true> : mode == 1 ? advect_stage_kernel<1, true> : advect_stage_kernel<2, true>)
+                        : (mode == 0 ? advect_stage_kernel<0, false> : mode == 1 ? advect_stage_kernel<1, false> : advect_stage_kernel<2, false>);
+  static PerDeviceOnce configured[6];
+  rc = configured[mode + (dev ? 3 : 0)].run(s->device, [fn]() -> int {
     CUP2D_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, ADV_SMEM));
     return (int)CUP2D_OK;
   });
@@ -242,7 +247,7 @@ int launch_advect(cup2d_sim *s, const double *in, const double *old, double *out
   const double ofac = coef / (s->h * s->h);
   ProfScope prof(s, KC_ADVECT);
   fn<<<s->ntiles, NT_ADV, ADV_SMEM, s->stream>>>(in, old, out, s->d_tiles, s->d_tile_org, s->d_adv_lut, s->nbx,
-                                                 s->nby, (int)s->nloc, afac, dfac, ofac);
+                                                 s->nby, (int)s->nloc, afac, dfac, ofac, dev);
   s->launches++;
   CUP2D_CUDA(cudaGetLastError());
   return CUP2D_OK;

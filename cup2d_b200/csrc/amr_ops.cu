@@ -1,8 +1,7 @@
 // Stencil operators on multi-level (block-AMR) meshes — FIRST, CORRECTNESS-ORIENTED DEVICE PATH.
 //
-// STATUS: compiled and wired to the C ABI (cup2d_amr_*), NOT YET RUN ON HARDWARE: written after the round's GPU budget was
-// spent.  Its GPU tests (tests/test_gpu_amr.py) are skipped unless CUP2D_TEST_UNVALIDATED=1; nothing in bench.py or the
-// validated paths calls into this file.  See DESIGN.md 7.1 for the plan this is step 0 of.
+// STATUS: validated on hardware in round 2 (tests/test_gpu_amr.py green on a B200, compute-sanitizer memcheck / racecheck
+// clean: profiles/r02a_first_contact.md).  See DESIGN.md 7.1 for the plan this is step 0 of.
 //
 // Shape (deliberately the simplest thing that can be compared with the reference, not the fast design):
 //   1. lab = T . field : the ghost-stencil tables of the host plan (csrc/amr_plan.cpp) applied as a CSR gather into a

@@ -529,10 +529,20 @@ static int alloc_device_state(cup2d_sim *s) {
   CUP2D_CUDA(cudaMemset(s->d_counter, 0, sizeof(unsigned int)));
   CUP2D_CUDA(cudaMalloc(&s->d_scal, 16 * sizeof(double)));
   CUP2D_CUDA(cudaMallocHost(&s->h_scal, 16 * sizeof(double)));
+  CUP2D_CUDA(cudaMalloc(&s->d_fac, sizeof(StepFactors)));
+  CUP2D_CUDA(cudaMemset(s->d_fac, 0, sizeof(StepFactors)));
+  CUP2D_CUDA(cudaMallocHost(&s->h_fac, sizeof(StepFactors)));
+  memset(s->h_fac, 0, sizeof(StepFactors));
   CUP2D_CUDA(cudaMalloc(&s->d_mailbox, 4096));
   CUP2D_CUDA(cudaMemset(s->d_mailbox, 0, 4096));
   s->comm.rank = s->rank;
   s->comm.nranks = 1; // raised to nranks by cup2d_peer_attach
+  s->comm.timeout_ns = 30ull * 1000000000ull; // bound of every cross-GPU wait (CUP2D_COMM_TIMEOUT_MS overrides at attach)
+  {
+    std::vector<int> gid(s->halo_gid.begin(), s->halo_gid.end());
+    CUP2D_CUDA(cudaMalloc(&s->d_halo_gid, std::max<size_t>(gid.size(), 4) * sizeof(int)));
+    if (!gid.empty()) CUP2D_CUDA(cudaMemcpy(s->d_halo_gid, gid.data(), gid.size() * sizeof(int), cudaMemcpyHostToDevice));
+  }
   s->comm.mb[s->rank] = s->d_mailbox;
   CUP2D_CUDA(cudaDeviceSynchronize());
   return CUP2D_OK;
@@ -569,9 +579,18 @@ void cup2d_destroy(cup2d_sim *s) {
   cudaFree(s->d_adv_lut); cudaFree(s->d_linf); cudaFree(s->d_ij);
   cudaFree(s->d_state); cudaFree(s->d_partials); cudaFree(s->d_counter); cudaFree(s->d_scal);
   cudaFree(s->d_mailbox);
+  cudaFree(s->d_halo_gid); cudaFree(s->d_push_first); cudaFree(s->d_push_ent);
   cudaFree(s->d_irr_blk); cudaFree(s->d_irr_tab); cudaFree(s->d_irr_rowptr); cudaFree(s->d_irr_col); cudaFree(s->d_irr_val);
   if (s->h_state) cudaFreeHost(s->h_state);
   if (s->h_scal) cudaFreeHost(s->h_scal);
+  cudaFree(s->d_fac);
+  if (s->h_fac) cudaFreeHost(s->h_fac);
+  for (auto &g : s->graphs) {
+    if (g.exec) cudaGraphExecDestroy(g.exec);
+    if (g.graph) cudaGraphDestroy(g.graph);
+  }
+  if (s->body_stream) cudaStreamDestroy(s->body_stream);
+  for (auto e : s->prof_pool) cudaEventDestroy(e);
   if (s->stream) cudaStreamDestroy(s->stream);
   delete s;
 }
@@ -585,8 +604,8 @@ static const char *kclass_name[KC_COUNT] = {"advect_stage_kernel", "umax_kernel"
     "halo_pull_kernel", "vorticity_tag_kernel"};
 int cup2d_profile_enable(cup2d_sim *s, int on) {
   if (!s) return CUP2D_EINVAL;
-  for (auto &r : s->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
-  s->prof.clear();
+  s->prof.clear(); // the events stay in the pool and are reused
+  s->prof_pool_used = 0;
   s->prof_on = on != 0;
   return CUP2D_OK;
 }
@@ -692,23 +711,28 @@ int cup2d_advect_diffuse_rhs(cup2d_sim *s, int in_f, int out_f, double dt) {
   if (s->nranks > 1 && (rc = halo_exchange_ptr(s, s->f[in_f], 2, in_f))) return rc;
   return launch_advect(s, s->f[in_f], s->f[in_f], s->f[out_f], 1.0, dt, true);
 }
+static int rk2(cup2d_sim *s, double dt, const StepFactors *dev);
 int cup2d_advect_diffuse_rk2(cup2d_sim *s, double dt) {
   CHECK_SIM(s);
   CUP2D_REQUIRE(!s->poisson_only, "advect: Poisson-only context (cup2d_poisson_create) has no grid geometry");
   CUP2D_CUDA(cudaSetDevice(s->device));
   int rc = need_peers(s);
   if (rc) return rc;
+  return rk2(s, dt, nullptr);
+}
+static int rk2(cup2d_sim *s, double dt, const StepFactors *dev) {
+  int rc;
   // vold <- vel is a pointer swap (main.cpp:6607-6610 copies); stage 1 reads vold, writes tmpV-as-V1;
   // stage 2 reads V1, adds to vold, writes vel.  No copy kernel: 80 B/cell/step -> 64 B/cell/step.
   swap_fields(s, CUP2D_VEL, CUP2D_VOLD);
   if (s->nranks > 1) {
     if ((rc = halo_exchange_ptr(s, s->f[CUP2D_VOLD], 2, CUP2D_VOLD))) return rc;
   }
-  if ((rc = launch_advect(s, s->f[CUP2D_VOLD], s->f[CUP2D_VOLD], s->f[CUP2D_TMPV], 0.5, dt, false))) return rc;
+  if ((rc = launch_advect(s, s->f[CUP2D_VOLD], s->f[CUP2D_VOLD], s->f[CUP2D_TMPV], 0.5, dt, false, dev))) return rc;
   if (s->nranks > 1) {
     if ((rc = halo_exchange_ptr(s, s->f[CUP2D_TMPV], 2, CUP2D_TMPV))) return rc;
   }
-  return launch_advect(s, s->f[CUP2D_TMPV], s->f[CUP2D_VOLD], s->f[CUP2D_VEL], 1.0, dt, false);
+  return launch_advect(s, s->f[CUP2D_TMPV], s->f[CUP2D_VOLD], s->f[CUP2D_VEL], 1.0, dt, false, dev);
 }
 int cup2d_pressure_rhs(cup2d_sim *s, double dt) {
   CHECK_SIM(s);
@@ -790,26 +814,182 @@ int cup2d_pressure_correct(cup2d_sim *s, double dt) {
   return launch_pressure_correct(s, dt);
 }
 
-int cup2d_step(cup2d_sim *s, double dt_in, int keep_udef, double tol_abs, double tol_rel,
-               int max_restarts, int max_iter, double *dt_out, int *iters_out, double *err_out) {
-  CHECK_SIM(s);
-  CUP2D_CUDA(cudaSetDevice(s->device));
-  int rc = need_peers(s);
-  if (rc) return rc;
-  double dt = dt_in;
-  if (!(dt > 0)) {
-    double umax;
-    if ((rc = cup2d_compute_dt(s, &umax, &dt))) return rc;
+// ---- one time step, enqueued without any host synchronisation --------------------------------------------------------
+// The body: [umax + dt rule on the device] -> RK2 -> Poisson right-hand side -> BiCGSTAB -> correction.  Every dt-dependent
+// kernel reads the device-resident StepFactors, the correction picks the best Krylov iterate through the device-side state,
+// cross-GPU epochs are device counters: nothing in the body depends on a host value that changes from step to step, so the
+// body can be captured ONCE per buffer assignment into a CUDA graph and replayed with a single cudaGraphLaunch (the
+// reference needs ~25 launches + 4 host synchronisations per Krylov iteration, cuda.cu:403-548).  A tolerance-driven solve
+// is a WHILE node whose condition the last CTA of the iteration's final kernel sets (cudaGraphSetConditional): the data-
+// dependent loop runs on the device too.
+static int step_body(cup2d_sim *s, bool dev_dt, int keep_udef, double tol_abs, double tol_rel, int max_restarts, int max_iter,
+                     bool capturing) {
+  int rc;
+  if (dev_dt) {
+    if ((rc = launch_umax_async(s))) return rc;
+    if ((rc = launch_step_factors(s, 0.0))) return rc;
   }
-  if ((rc = cup2d_advect_diffuse_rk2(s, dt))) return rc;
+  if ((rc = rk2(s, 0.0, s->d_fac))) return rc;
   // keep_udef = 0: no bodies, the sum of u_def is identically zero (main.cpp:6980-6983), so the RHS
   // kernel skips the chi*div(u_def) term instead of reading a zeroed field (tmpV keeps RK scratch).
   // keep_udef = 1: the caller uploaded chi and the summed u_def into tmpV after the RK2 stages.
-  if ((rc = launch_pressure_rhs(s, dt, keep_udef != 0))) return rc;
-  if ((rc = poisson_solve(s, tol_abs, tol_rel, max_restarts, max_iter, iters_out, err_out))) return rc;
-  if ((rc = launch_pressure_correct(s, dt))) return rc;
-  if (dt_out) *dt_out = dt;
+  if ((rc = launch_pressure_rhs(s, 1.0, keep_udef != 0, s->d_fac, true))) return rc;
+  const bool tol = tol_abs > 0 || tol_rel > 0;
+#ifndef CUP2D_FULL_EMU
+  cudaGraph_t cap_graph = nullptr;
+  if (capturing && tol && max_iter > 0) {
+    // tolerance-driven solve inside a graph: a WHILE node whose body is one iteration.  Its condition starts at 1 on
+    // every launch; the last CTA of k_init and of every k_final sets it to !done (cudaGraphSetConditional).
+    cudaStreamCaptureStatus st;
+    CUP2D_CUDA(cudaStreamGetCaptureInfo(s->stream, &st, nullptr, &cap_graph, nullptr, nullptr));
+    cudaGraphConditionalHandle handle;
+    CUP2D_CUDA(cudaGraphConditionalHandleCreate(&handle, cap_graph, 1, cudaGraphCondAssignDefault));
+    s->cond_handle = (unsigned long long)handle;
+  }
+#endif
+  rc = poisson_begin(s, tol_abs, tol_rel, max_restarts, max_iter, true);
+  if (rc) {
+    s->cond_handle = 0;
+    return rc;
+  }
+  if (max_iter > 0) {
+    if (!tol) {
+      if ((rc = poisson_iterations(s, max_iter, s->stream))) return rc;
+    } else if (capturing) {
+#ifndef CUP2D_FULL_EMU
+      cudaStreamCaptureStatus st;
+      const cudaGraphNode_t *deps = nullptr;
+      size_t ndeps = 0;
+      cudaError_t e = cudaStreamGetCaptureInfo(s->stream, &st, nullptr, &cap_graph, &deps, &ndeps);
+      cudaGraphNodeParams np = {cudaGraphNodeTypeConditional};
+      np.type = cudaGraphNodeTypeConditional;
+      np.conditional.handle = (cudaGraphConditionalHandle)s->cond_handle;
+      np.conditional.type = cudaGraphCondTypeWhile;
+      np.conditional.size = 1;
+      cudaGraphNode_t loop = nullptr;
+      if (e == cudaSuccess) e = cudaGraphAddNode(&loop, cap_graph, deps, ndeps, &np);
+      if (e == cudaSuccess && !s->body_stream) e = cudaStreamCreateWithFlags(&s->body_stream, cudaStreamNonBlocking);
+      if (e == cudaSuccess)
+        e = cudaStreamBeginCaptureToGraph(s->body_stream, np.conditional.phGraph_out[0], nullptr, nullptr, 0, cudaStreamCaptureModeRelaxed);
+      if (e != cudaSuccess) {
+        s->cond_handle = 0;
+        CUP2D_CUDA(e);
+      }
+      rc = poisson_iterations(s, 1, s->body_stream);
+      s->cond_handle = 0;
+      cudaGraph_t body = nullptr;
+      e = cudaStreamEndCapture(s->body_stream, &body);
+      if (rc) return rc;
+      CUP2D_CUDA(e);
+      CUP2D_CUDA(cudaStreamUpdateCaptureDependencies(s->stream, &loop, 1, cudaStreamSetCaptureDependencies));
+#endif
+    } else {
+      // direct launches (profiling, first step of a context): the host looks at the `done` flag every 8 iterations
+      int launched = 0;
+      while (launched < max_iter) {
+        const int batch = max_iter - launched < 8 ? max_iter - launched : 8;
+        if ((rc = poisson_iterations(s, batch, s->stream))) return rc;
+        launched += batch;
+        if ((rc = poisson_result(s, nullptr, nullptr))) return rc;
+        if (s->h_state->done) break;
+      }
+    }
+  }
+  return launch_pressure_correct(s, 1.0, s->d_fac);
+}
+
+int cup2d_set_graph(cup2d_sim *s, int on) {
+  CHECK_SIM(s);
+  s->use_graph = on != 0;
   return CUP2D_OK;
+}
+
+int cup2d_step_enqueue(cup2d_sim *s, double dt_in, int keep_udef, double tol_abs, double tol_rel, int max_restarts,
+                       int max_iter) {
+  CHECK_SIM(s);
+  CUP2D_REQUIRE(!s->poisson_only, "cup2d_step: Poisson-only context");
+  CUP2D_CUDA(cudaSetDevice(s->device));
+  int rc = need_peers(s);
+  if (rc) return rc;
+  const bool dev_dt = !(dt_in > 0);
+  if (!dev_dt && (rc = launch_step_factors(s, dt_in))) return rc; // by-value dt: outside the graph
+  s->step_pending = true;
+  bool graph = s->use_graph && !s->prof_on && s->warmed;
+#ifdef CUP2D_FULL_EMU
+  graph = false;
+#endif
+  if (!graph) {
+    s->warmed = true; // the first step of a context runs directly: one-time tables and kernel attributes are set up in it
+    return step_body(s, dev_dt, keep_udef, tol_abs, tol_rel, max_restarts, max_iter, false);
+  }
+#ifndef CUP2D_FULL_EMU
+  // one executable graph per assignment of buffers to roles (the body swaps vel<->vold and pres<->pold, so successive
+  // steps alternate between two assignments; the host-buffer pipeline adds its staging sets) and per argument set
+  std::vector<unsigned long long> key;
+  for (int f = 0; f < CUP2D_NFIELDS; f++) key.push_back((unsigned long long)(uintptr_t)s->f[f]);
+  auto bits = [](double v) { unsigned long long u; memcpy(&u, &v, 8); return u; };
+  key.insert(key.end(), {(unsigned long long)dev_dt, (unsigned long long)(keep_udef != 0), bits(tol_abs), bits(tol_rel),
+                         (unsigned long long)max_restarts, (unsigned long long)max_iter, (unsigned long long)s->n_irr_rows});
+  cup2d_sim::StepGraph *hit = nullptr;
+  for (auto &g : s->graphs)
+    if (g.key == key) hit = &g;
+  if (!hit) {
+    if (s->graphs.size() >= 32) { // a caller cycling through many buffer sets: drop the oldest
+      cudaGraphExecDestroy(s->graphs.front().exec);
+      cudaGraphDestroy(s->graphs.front().graph);
+      s->graphs.erase(s->graphs.begin());
+    }
+    const int64_t l0 = s->launches;
+    double *f0[CUP2D_NFIELDS];
+    void *pb0[MAX_RANKS][CUP2D_NFIELDS + 5];
+    memcpy(f0, s->f, sizeof f0);
+    memcpy(pb0, s->peer_base, sizeof pb0);
+    CUP2D_CUDA(cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeRelaxed));
+    rc = step_body(s, dev_dt, keep_udef, tol_abs, tol_rel, max_restarts, max_iter, true);
+    cudaGraph_t g = nullptr;
+    const cudaError_t e = cudaStreamEndCapture(s->stream, &g);
+    // capturing applied the body's buffer swaps to the context; undo them, the launch below applies them again
+    memcpy(s->f, f0, sizeof f0);
+    memcpy(s->peer_base, pb0, sizeof pb0);
+    const int64_t nl = s->launches - l0;
+    s->launches = l0;
+    if (rc) {
+      if (g) cudaGraphDestroy(g);
+      return rc;
+    }
+    CUP2D_CUDA(e);
+    cup2d_sim::StepGraph sg;
+    sg.key = key;
+    sg.graph = g;
+    sg.launches = nl;
+    CUP2D_CUDA(cudaGraphInstantiate(&sg.exec, g, 0));
+    s->graphs.push_back(sg);
+    hit = &s->graphs.back();
+  }
+  CUP2D_CUDA(cudaGraphLaunch(hit->exec, s->stream));
+  s->launches += hit->launches;
+  // the buffer swaps the body makes on the host side (rk2: vel <-> vold; right-hand side: pres <-> pold)
+  swap_fields(s, CUP2D_VEL, CUP2D_VOLD);
+  swap_fields(s, CUP2D_PRES, CUP2D_POLD);
+#endif
+  return CUP2D_OK;
+}
+
+int cup2d_step_result(cup2d_sim *s, double *dt_out, int *iters_out, double *err_out) {
+  CHECK_SIM(s);
+  CUP2D_CUDA(cudaSetDevice(s->device));
+  CUP2D_CUDA(cudaMemcpyAsync(s->h_fac, s->d_fac, sizeof(StepFactors), cudaMemcpyDeviceToHost, s->stream));
+  const int rc = poisson_result(s, iters_out, err_out); // synchronises the stream
+  if (dt_out) *dt_out = s->h_fac->dt;
+  s->step_pending = false;
+  return rc;
+}
+
+int cup2d_step(cup2d_sim *s, double dt_in, int keep_udef, double tol_abs, double tol_rel,
+               int max_restarts, int max_iter, double *dt_out, int *iters_out, double *err_out) {
+  const int rc = cup2d_step_enqueue(s, dt_in, keep_udef, tol_abs, tol_rel, max_restarts, max_iter);
+  if (rc) return rc;
+  return cup2d_step_result(s, dt_out, iters_out, err_out);
 }
 
 /* ---- host-buffer pipeline: upload(n+1) || step(n) || download(n-1) on three streams (include/cup2d_b200.h) ---- */

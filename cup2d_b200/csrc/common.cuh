@@ -76,14 +76,21 @@ __device__ __forceinline__ double fast_rcp_pos(double x) {
 
 // ---- cross-GPU plumbing over NVLink peer memory ---------------------------------------------------
 // One process per GPU; every rank maps every peer's mailbox (CUDA IPC).  Mailbox layout (u64 words):
-//   [0..8)   halo READY epochs, one per source rank      [8..16) halo DONE epochs
-//   [16 + (src*2 + parity)*8 ...]  reduction slot: flag(epoch), v0..v5
-//   [496]    this rank's reduction epoch counter (local use only)
-constexpr int MB_READY = 0, MB_DONE = 8, MB_RED = 16, MB_RED_STRIDE = 8, MB_EPOCH = 496, MB_WORDS = 512;
+//   [0..8)     halo-pull READY epochs, one per source rank     [8..16) halo-pull DONE epochs
+//   [16 + (src*2 + parity)*8 ...]  reduction slot: flag(epoch), v0..v5          (16 .. 144)
+//   [144..152) PUSHED epochs, one per source rank (halo rows pushed by the producing Krylov kernel)
+//   [496] reduction epoch   [497] halo-pull epoch   [498] push epoch   (this rank's counters; device-side, so that a
+//         step captured in a CUDA graph carries no host-supplied epoch)
+//   [499] error word: first failed wait of this rank (0 = none); the host reads it at its synchronisation points
+constexpr int MB_READY = 0, MB_DONE = 8, MB_RED = 16, MB_RED_STRIDE = 8, MB_PUSHED = 144, MB_EPOCH = 496,
+              MB_HEPOCH = 497, MB_PEPOCH = 498, MB_ERR = 499, MB_WORDS = 512;
 constexpr int COMM_MAX_RANKS = 8;
+constexpr unsigned long long COMM_ERR_TIMEOUT = 1; // codes in the error word: (code << 32) | (what << 8) | peer
+enum CommWait { CW_REDUCE = 1, CW_HALO_READY = 2, CW_HALO_DONE = 3, CW_PUSHED = 4 };
 struct Comm {
   int rank, nranks;
   unsigned long long *mb[COMM_MAX_RANKS]; // mb[r] = rank r's mailbox (mb[rank] is local memory)
+  unsigned long long timeout_ns;          // bound of every cross-GPU wait (0 = wait for ever)
 };
 __device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
   asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
@@ -100,6 +107,44 @@ __device__ __forceinline__ unsigned long long ld_relaxed_sys(const unsigned long
   unsigned long long v;
   asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
+}
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)::"memory");
+  return t;
+}
+// coherent (never the non-coherent/texture path, never a stale L1 line) loads of data another GPU wrote into this
+// GPU's memory during the running kernel; used after an acquire of the flag that announces the data
+__device__ __forceinline__ double ld_coherent(const double *p) {
+  double v;
+  asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ double2 ld_coherent2(const double2 *p) {
+  double2 v;
+  asm volatile("ld.relaxed.sys.global.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p) : "memory");
+  return v;
+}
+// Bounded wait for *flag >= target (a peer's release store).  Returns false when the wait was given up: either this
+// one ran into the time limit (the error word is set: code, what, peer) or an earlier one did (then nothing waits any
+// more, so a step with a dead peer drains in milliseconds and the host finds the error word at its next
+// synchronisation point — CUP2D_ECOMM — instead of eight GPUs spinning for ever; the reference aborts through MPI).
+__device__ __forceinline__ bool wait_flag(const unsigned long long *flag, unsigned long long target, const Comm &c,
+                                          int what, int peer) {
+  if (ld_acquire_sys(flag) >= target) return true;
+  unsigned long long *err = c.mb[c.rank] + MB_ERR;
+  if (ld_relaxed_sys(err) != 0) return false;
+  const unsigned long long t0 = global_timer_ns();
+  for (unsigned n = 1;; n++) {
+    if (ld_acquire_sys(flag) >= target) return true;
+    if ((n & 255u) == 0) {
+      if (ld_relaxed_sys(err) != 0) return false;
+      if (c.timeout_ns && global_timer_ns() - t0 > c.timeout_ns) {
+        st_relaxed_sys(err, (COMM_ERR_TIMEOUT << 32) | ((unsigned long long)what << 8) | (unsigned long long)peer);
+        return false;
+      }
+    }
+  }
 }
 // All-reduce of NS sums + 1 max across ranks, executed by ONE WARP per rank (warp 0 of the last CTA of a
 // grid reduction; every lane enters with the same local totals).  Lane r < nranks writes this rank's
@@ -131,7 +176,7 @@ __device__ __forceinline__ void peer_allreduce(const Comm &c, double (&tot)[NS],
   for (int k = 0; k <= NS; k++) v[k] = 0.0;
   if (lane < c.nranks) {
     const unsigned long long *src = mine + MB_RED + (lane * 2 + par) * MB_RED_STRIDE;
-    while (ld_acquire_sys(src) < ep) { }
+    wait_flag(src, ep, c, CW_REDUCE, lane);
 #pragma unroll
     for (int k = 0; k <= NS; k++) v[k] = __longlong_as_double((long long)ld_relaxed_sys(src + 1 + k));
   }

@@ -22,6 +22,7 @@
 #include "sim.h"
 #include <cmath>
 #include <cstdlib>
+#include <type_traits>
 
 namespace cup2d {
 
@@ -98,6 +99,12 @@ __device__ __forceinline__ void precond_row(double (&v)[8], double *sw, int lane
   dst8(a, v, sa, sb_, sc, sd); // back along x
 }
 
+__device__ __forceinline__ void set_gate(NoGate &, unsigned, const Comm &) {}
+__device__ __forceinline__ void set_gate(HaloGate &g, unsigned src_mask, const Comm &comm) {
+  g.mask = src_mask;
+  g.comm = comm;
+  g.target = ld_relaxed_sys(comm.mb[comm.rank] + MB_PEPOCH); // this rank's own producer has run: every rank is at this epoch
+}
 __device__ __forceinline__ int next_buf(int cur, int opt) { return cur != opt ? 3 - cur - opt : (cur + 1) % 3; }
 
 // decisions taken at the top of the reference loop (cuda.cu:440-477), given rho' = rhat.r and |r|^2
@@ -123,6 +130,95 @@ __device__ void prepare_iteration(KrylovState *st, double rho_new, double nr2) {
   }
 }
 
+// ---- halo rows of the Krylov operands, pushed by their producer (multi-rank contexts) --------------------------------
+// z = M p and z_r = M r are consumed by the next kernel's stencil, which needs the face-neighbour blocks other ranks
+// own.  Instead of a separate halo kernel between producer and consumer (launch + all-rank handshake + NVLink round
+// trip on the critical path, twice per iteration), the producer writes every row of a block that some peer holds as a
+// halo slot straight into that slot (plain remote stores: fire and forget) and its last CTA raises this rank's PUSHED
+// flag in those peers' mailboxes; the consumer waits for the flags only in the lanes that touch a halo slot
+// (rows.cuh: HaloGate).  Write-after-read safety: a peer pushes the next version of a slot only after the all-reduce of
+// the consuming SpMV, which completes on no rank before every rank has finished that SpMV.
+struct PushView {
+  const int *first;        // [nloc]: first entry of the block's destinations, -1 = none
+  const int2 *ent;         // (peer rank, halo slot on the peer) ..., (-1,-1)
+  double *peer[MAX_RANKS]; // the vector's base address on every peer
+  unsigned dst_mask;       // peers that hold halo slots of this rank's blocks
+};
+__device__ __forceinline__ void push_rows(const PushView &pv, int slot, int y, const double (&v)[8]) {
+  const int pf = pv.first[slot];
+  if (pf < 0) return;
+  for (int e = pf;; e++) {
+    const int2 d = pv.ent[e];
+    if (d.x < 0) break;
+    double2 *dst = reinterpret_cast<double2 *>(pv.peer[d.x] + (size_t)d.y * 64 + y * 8);
+#pragma unroll
+    for (int k = 0; k < 4; k++) dst[k] = make_double2(v[2 * k], v[2 * k + 1]);
+  }
+  __threadfence_system();
+}
+// end of a pushing kernel: the CTA that finishes last publishes the new push epoch to the destination ranks
+__device__ __forceinline__ void push_finish(const PushView &pv, const Comm &comm, unsigned int *counter) {
+  __shared__ bool s_push_last;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    s_push_last = atomicAdd(counter, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (!s_push_last) return;
+  unsigned long long *mine = comm.mb[comm.rank];
+  const unsigned long long e = ld_relaxed_sys(mine + MB_PEPOCH) + 1;
+  if ((int)threadIdx.x < comm.nranks && ((pv.dst_mask >> threadIdx.x) & 1u)) {
+    __threadfence_system();
+    st_release_sys(comm.mb[threadIdx.x] + MB_PUSHED + comm.rank, e);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    *counter = 0;
+    st_relaxed_sys(mine + MB_PEPOCH, e);
+  }
+}
+
+// Krylov state of a new solve, written on the device from by-value arguments (a host-to-device copy of a staging
+// struct would be read when the copy executes, i.e. possibly after the host has prepared the next solve)
+__global__ void k_state_init(KrylovState *st, double tol_abs, double tol_rel, int max_restarts, int max_iter) {
+  KrylovState z = KrylovState{};
+  z.alpha = z.omega = z.rho_prev = z.rho_curr = 1.0; // cuda.cu:409
+  z.tol_abs = tol_abs;
+  z.tol_rel = tol_rel;
+  z.max_restarts = max_restarts;
+  z.max_iter = max_iter;
+  *st = z;
+}
+
+// end-of-iteration logic of the reference loop (cuda.cu:525-541, 438), run by one thread with the global sums
+__device__ void end_of_iteration(KrylovState *st, const double *tsum, double m, int nxt) {
+  st->iter++;
+  st->err = m;
+  st->cur = nxt;
+  if (m < st->err_opt) { // cuda.cu:535-541
+    st->err_opt = m;
+    st->opt = nxt;
+    st->xsum = tsum[2];
+    if (m <= st->tol_abs || m / st->err_init <= st->tol_rel) {
+      st->done = 1;
+      return;
+    }
+  }
+  st->rho_prev = st->rho_curr; // set_rho
+  if (st->iter >= st->max_iter) { // cuda.cu:438
+    st->done = 1;
+    return;
+  }
+  prepare_iteration(st, tsum[0], tsum[1]);
+}
+// a solve captured as the body of a graph WHILE node keeps iterating while its condition is non-zero
+__device__ __forceinline__ void set_loop_condition(unsigned long long handle, const KrylovState *st) {
+#ifndef CUP2D_FULL_EMU
+  if (handle) cudaGraphSetConditional((cudaGraphConditionalHandle)handle, st->done ? 0u : 1u);
+#endif
+}
+
 #define CHUNK_LOOP()                                                                              \
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;                                     \
   double *sw = s_scr + warp * SCR1;                                                               \
@@ -134,7 +230,7 @@ __global__ void __launch_bounds__(NT)
 k_init(const double *__restrict__ b, const double *__restrict__ x0, double *__restrict__ x,
        double *__restrict__ r, double *__restrict__ rhat, double *__restrict__ p,
        double *__restrict__ nu, const int4 *__restrict__ nbr, int nrows, KrylovState *st,
-       double *partials, unsigned int *counter, Comm comm, IrrView irr) {
+       double *partials, unsigned int *counter, Comm comm, IrrView irr, unsigned long long loop_handle) {
   __shared__ __align__(16) double s_scr[WPB * SCR1];
   double sums[2] = {0, 0}; // |r|^2, sum x0
   double mx = 0;
@@ -167,14 +263,16 @@ k_init(const double *__restrict__ b, const double *__restrict__ x0, double *__re
     st->iter = 0;
     if (st->max_iter <= 0) st->done = 1;
     prepare_iteration(st, t[0], t[0]);
+    set_loop_condition(loop_handle, st);
   });
 }
 
 // ---- K1: p = r + beta (p - omega nu) ; z = M p    (cuda.cu:478-486) -------------------------------
+template <bool MULTI>
 __global__ void __launch_bounds__(NT, PRECOND_CTAS)
 k_pupdate(const double *__restrict__ r, double *__restrict__ rhat, double *__restrict__ p,
           const double *__restrict__ nu, double *__restrict__ z, int nrows,
-          const KrylovState *__restrict__ st) {
+          const KrylovState *__restrict__ st, PushView pv, Comm comm, unsigned int *counter) {
   __shared__ __align__(16) double s_scr[WPB * SCR1];
   if (st->done) return;
   const double beta = st->beta, nomega = -st->omega;
@@ -204,19 +302,31 @@ k_pupdate(const double *__restrict__ r, double *__restrict__ rhat, double *__res
     chunk_to_rows(sw, lane, cp, pp);
     precond_row(pp, sw, lane);
     rows_store1(z, row0, nv, sw, lane, pp);
+    if (MULTI && lane < nv) push_rows(pv, (row0 + lane) >> 3, lane & 7, pp);
   }
+  if (MULTI) push_finish(pv, comm, counter);
 }
 
 // ---- K2 / K4: y = A z with one or two dots against `d` and y -------------------------------------
 //   MODE 0 (K2): nu = A z ; rhat.nu             -> alpha = rho/(rhat.nu + eps)   (cuda.cu:487-496)
 //   MODE 1 (K4): t  = A z ; t.r, t.t            -> omega = t.r/(t.t + eps)       (cuda.cu:506-518)
-template <int MODE, bool IRR>
+//   MULTI: the halo rows of z were pushed by the peers' producing kernels; lanes that touch them wait for the flags
+template <int MODE, bool IRR, bool MULTI>
 __global__ void __launch_bounds__(NT, SPMV_CTAS)
 k_spmv(const double *__restrict__ z, const double *__restrict__ d, double *__restrict__ yout,
        const int4 *__restrict__ nbr, int nrows, KrylovState *st, double *partials,
-       unsigned int *counter, Comm comm, IrrView irr) {
+       unsigned int *counter, Comm comm, IrrView irr, unsigned src_mask) {
   __shared__ __align__(16) double s_scr[WPB * SCR1];
   if (st->done) return;
+  typename std::conditional<MULTI, HaloGate, NoGate>::type gate;
+  if (MULTI) {
+    gate.nloc = nrows >> 3;
+    set_gate(gate, src_mask, comm);
+    if (IRR) { // general rows may name any halo slot: every CTA waits before it starts
+      if (threadIdx.x == 0) gate.wait();
+      __syncthreads();
+    }
+  }
   double sums[2] = {0, 0};
   CHUNK_LOOP() {
     const int nv = min(32, nrows - row0);
@@ -227,7 +337,7 @@ k_spmv(const double *__restrict__ z, const double *__restrict__ d, double *__res
     chunk_ld(z, row0, nv, lane, cz);
     if (HOIST) chunk_ld(d, row0, nv, lane, cd);
     double zz[8], az[8];
-    rows_lap_c(cz, z, row0, nv, nbr, sw, lane, zz, az, IRR ? irr : IrrView());
+    rows_lap_c(cz, z, row0, nv, nbr, sw, lane, zz, az, IRR ? irr : IrrView(), gate);
     // back to chunk layout: the dots and the store are element-wise
     if (!HOIST) chunk_ld(d, row0, nv, lane, cd);
     rows_to_chunk(sw, lane, az, ca);
@@ -256,9 +366,10 @@ k_spmv(const double *__restrict__ z, const double *__restrict__ d, double *__res
 }
 
 // ---- K3: r -= alpha nu ; z_r = M r     (cuda.cu:499-505; the x half-step of cuda.cu:498 happens in K5) ----------
+template <bool MULTI>
 __global__ void __launch_bounds__(NT, PRECOND_CTAS)
 k_r_update(double *__restrict__ r, const double *__restrict__ nu, double *__restrict__ zr, int nrows,
-           const KrylovState *__restrict__ st) {
+           const KrylovState *__restrict__ st, PushView pv, Comm comm, unsigned int *counter) {
   __shared__ __align__(16) double s_scr[WPB * SCR1];
   if (st->done) return;
   const double alpha = st->alpha;
@@ -279,7 +390,9 @@ k_r_update(double *__restrict__ r, const double *__restrict__ nu, double *__rest
     chunk_to_rows(sw, lane, cr, rr);
     precond_row(rr, sw, lane);
     rows_store1(zr, row0, nv, sw, lane, rr);
+    if (MULTI && lane < nv) push_rows(pv, (row0 + lane) >> 3, lane & 7, rr);
   }
+  if (MULTI) push_finish(pv, comm, counter);
 }
 
 // ---- K5: x = (x + alpha z_p) + omega z_r ; r -= omega t ; err, rhat.r, |r|^2, sum(x) ; end-of-iteration logic ----
@@ -288,7 +401,7 @@ k_r_update(double *__restrict__ r, const double *__restrict__ nu, double *__rest
 __global__ void __launch_bounds__(NT)
 k_final(double *x0, double *x1, double *x2, const double *__restrict__ zp, const double *__restrict__ zr,
         double *__restrict__ r, const double *__restrict__ t, const double *__restrict__ rhat, int nrows,
-        KrylovState *st, double *partials, unsigned int *counter, Comm comm) {
+        KrylovState *st, double *partials, unsigned int *counter, Comm comm, unsigned long long loop_handle) {
   if (st->done) return;
   const double alpha = st->alpha, omega = st->omega;
   const int cur = st->cur, nxt = next_buf(st->cur, st->opt);
@@ -324,24 +437,8 @@ k_final(double *x0, double *x1, double *x2, const double *__restrict__ zp, const
     chunk_st(r, row0, nv, lane, cr);
   }
   grid_reduce<3, NT>(sums, mx, partials, counter, comm, [=](const double *tsum, double m) {
-    st->iter++;
-    st->err = m;
-    st->cur = nxt;
-    if (m < st->err_opt) { // cuda.cu:535-541
-      st->err_opt = m;
-      st->opt = nxt;
-      st->xsum = tsum[2];
-      if (m <= st->tol_abs || m / st->err_init <= st->tol_rel) {
-        st->done = 1;
-        return;
-      }
-    }
-    st->rho_prev = st->rho_curr; // set_rho
-    if (st->iter >= st->max_iter) { // cuda.cu:438
-      st->done = 1;
-      return;
-    }
-    prepare_iteration(st, tsum[0], tsum[1]);
+    end_of_iteration(st, tsum, m, nxt);
+    set_loop_condition(loop_handle, st);
   });
 }
 
@@ -352,90 +449,126 @@ static inline int red_grid(const cup2d_sim *s, int nrows) {
   return g < cap ? g : cap;
 }
 
-int poisson_solve(cup2d_sim *s, double tol_abs, double tol_rel, int max_restarts, int max_iter,
-                  int *iters, double *err) {
+static PushView make_push(const cup2d_sim *s, int peer_index) {
+  PushView pv;
+  pv.first = s->d_push_first;
+  pv.ent = s->d_push_ent;
+  for (int r = 0; r < MAX_RANKS; r++) pv.peer[r] = r < s->nranks ? (double *)s->peer_base[r][peer_index] : nullptr;
+  pv.dst_mask = s->dst_mask;
+  return pv;
+}
+
+// Start of a solve: Krylov state, r = b - A x0 (b = tmp, x0 = pres).  x0_halo_current: the halo slots of pres already
+// hold what the neighbours have (the step's right-hand-side kernel zeroes pres, halo slots included), so no refresh.
+int poisson_begin(cup2d_sim *s, double tol_abs, double tol_rel, int max_restarts, int max_iter, bool x0_halo_current) {
   int rc = g_consts.run(s->device, upload_consts);
   if (rc) return rc;
   const int nrows = (int)s->nloc * 8;
   const int grid = red_grid(s, nrows);
   const int4 *nbr = reinterpret_cast<const int4 *>(s->d_nbr);
   const bool has_irr = s->n_irr_rows > 0; // general rows present: kernels with the CSR override compiled in
-  KrylovState *h = s->h_state;
-  *h = KrylovState{};
-  h->alpha = h->omega = h->rho_prev = h->rho_curr = 1.0; // cuda.cu:409
-  h->tol_abs = tol_abs;
-  h->tol_rel = tol_rel;
-  h->max_restarts = max_restarts;
-  h->max_iter = max_iter;
-  CUP2D_CUDA(cudaMemcpyAsync(s->d_state, h, sizeof *h, cudaMemcpyHostToDevice, s->stream));
-  if (s->nranks > 1 && (rc = halo_exchange_ptr(s, s->f[CUP2D_PRES], 1, CUP2D_PRES))) return rc;
+  k_state_init<<<1, 1, 0, s->stream>>>(s->d_state, tol_abs, tol_rel, max_restarts, max_iter);
+  if (s->nranks > 1 && !x0_halo_current && (rc = halo_exchange_ptr(s, s->f[CUP2D_PRES], 1, CUP2D_PRES))) return rc;
   {
     ProfScope prof(s, KC_KINIT);
     if (has_irr)
       k_init<true><<<grid, NT, 0, s->stream>>>(s->f[CUP2D_TMP], s->f[CUP2D_PRES], s->kx[0], s->kr, s->krhat, s->kp,
                                                s->knu, nbr, nrows, s->d_state, s->d_partials, s->d_counter,
-                                               s->comm, irr_view(s));
+                                               s->comm, irr_view(s), s->cond_handle);
     else
       k_init<false><<<grid, NT, 0, s->stream>>>(s->f[CUP2D_TMP], s->f[CUP2D_PRES], s->kx[0], s->kr, s->krhat, s->kp,
                                                 s->knu, nbr, nrows, s->d_state, s->d_partials, s->d_counter,
-                                                s->comm, irr_view(s));
+                                                s->comm, irr_view(s), s->cond_handle);
   }
-  s->launches++;
-  const int check_every = (tol_abs > 0 || tol_rel > 0) ? 8 : 64;
+  s->launches += 2;
+  CUP2D_CUDA(cudaGetLastError());
+  return CUP2D_OK;
+}
+
+// n BiCGSTAB iterations: 5 kernels each, no host involvement (a converged solve turns them into no-ops)
+int poisson_iterations(cup2d_sim *s, int n, cudaStream_t stream) {
+  const int nrows = (int)s->nloc * 8;
+  const int grid = red_grid(s, nrows);
+  const int4 *nbr = reinterpret_cast<const int4 *>(s->d_nbr);
+  const bool has_irr = s->n_irr_rows > 0;
+  const bool multi = s->nranks > 1;
+  const PushView pz = make_push(s, CUP2D_NFIELDS), pzr = make_push(s, CUP2D_NFIELDS + 4);
+  const IrrView irr = irr_view(s);
+  for (int k = 0; k < n; k++) {
+    {
+      ProfScope prof(s, KC_PUPDATE);
+      if (multi)
+        k_pupdate<true><<<grid, NT, 0, stream>>>(s->kr, s->krhat, s->kp, s->knu, s->kz, nrows, s->d_state, pz, s->comm, s->d_counter);
+      else
+        k_pupdate<false><<<grid, NT, 0, stream>>>(s->kr, s->krhat, s->kp, s->knu, s->kz, nrows, s->d_state, pz, s->comm, s->d_counter);
+    }
+    {
+      ProfScope prof(s, KC_SPMV_NU);
+      if (has_irr && multi)
+        k_spmv<0, true, true><<<grid, NT, 0, stream>>>(s->kz, s->krhat, s->knu, nbr, nrows, s->d_state, s->d_partials, s->d_counter, s->comm, irr, s->src_mask);
+      else if (has_irr)
+        k_spmv<0, true, false><<<grid, NT, 0, stream>>>(s->kz, s->krhat, s->knu, nbr, nrows, s->d_state, s->d_partials, s->d_counter, s->comm, irr, s->src_mask);
+      else if (multi)
+        k_spmv<0, false, true><<<grid, NT, 0, stream>>>(s->kz, s->krhat, s->knu, nbr, nrows, s->d_state, s->d_partials, s->d_counter, s->comm, irr, s->src_mask);
+      else
+        k_spmv<0, false, false><<<grid, NT, 0, stream>>>(s->kz, s->krhat, s->knu, nbr, nrows, s->d_state, s->d_partials, s->d_counter, s->comm, irr, s->src_mask);
+    }
+    {
+      ProfScope prof(s, KC_XRUPDATE);
+      if (multi)
+        k_r_update<true><<<grid, NT, 0, stream>>>(s->kr, s->knu, s->kzr, nrows, s->d_state, pzr, s->comm, s->d_counter);
+      else
+        k_r_update<false><<<grid, NT, 0, stream>>>(s->kr, s->knu, s->kzr, nrows, s->d_state, pzr, s->comm, s->d_counter);
+    }
+    {
+      ProfScope prof(s, KC_SPMV_T);
+      if (has_irr && multi)
+        k_spmv<1, true, true><<<grid, NT, 0, stream>>>(s->kzr, s->kr, s->kt, nbr, nrows, s->d_state, s->d_partials, s->d_counter, s->comm, irr, s->src_mask);
+      else if (has_irr)
+        k_spmv<1, true, false><<<grid, NT, 0, stream>>>(s->kzr, s->kr, s->kt, nbr, nrows, s->d_state, s->d_partials, s->d_counter, s->comm, irr, s->src_mask);
+      else if (multi)
+        k_spmv<1, false, true><<<grid, NT, 0, stream>>>(s->kzr, s->kr, s->kt, nbr, nrows, s->d_state, s->d_partials, s->d_counter, s->comm, irr, s->src_mask);
+      else
+        k_spmv<1, false, false><<<grid, NT, 0, stream>>>(s->kzr, s->kr, s->kt, nbr, nrows, s->d_state, s->d_partials, s->d_counter, s->comm, irr, s->src_mask);
+    }
+    {
+      ProfScope prof(s, KC_FINAL);
+      k_final<<<grid, NT, 0, stream>>>(s->kx[0], s->kx[1], s->kx[2], s->kz, s->kzr, s->kr, s->kt, s->krhat, nrows, s->d_state,
+                                       s->d_partials, s->d_counter, s->comm, s->cond_handle);
+    }
+    s->launches += 5;
+  }
+  CUP2D_CUDA(cudaGetLastError());
+  return CUP2D_OK;
+}
+
+// state of the last solve -> host (synchronises the stream); a cross-GPU wait that was given up surfaces here
+int poisson_result(cup2d_sim *s, int *iters, double *err) {
+  KrylovState *h = s->h_state;
+  CUP2D_CUDA(cudaMemcpyAsync(h, s->d_state, sizeof *h, cudaMemcpyDeviceToHost, s->stream));
+  CUP2D_CUDA(cudaStreamSynchronize(s->stream));
+  if (iters) *iters = h->iter;
+  if (err) *err = h->err_opt;
+  return comm_check(s);
+}
+
+int poisson_solve(cup2d_sim *s, double tol_abs, double tol_rel, int max_restarts, int max_iter,
+                  int *iters, double *err, bool x0_halo_current) {
+  int rc = poisson_begin(s, tol_abs, tol_rel, max_restarts, max_iter, x0_halo_current);
+  if (rc) return rc;
+  // fixed work (tolerances 0: the reference's first ten steps, main.cpp:7028-7030): everything is queued at once;
+  // tolerance-driven: the host looks at the device's `done` flag every 8 iterations
+  const int check_every = (tol_abs > 0 || tol_rel > 0) ? 8 : (max_iter > 0 ? max_iter : 1);
   int launched = 0;
   bool done = max_iter <= 0;
   while (!done) {
-    int batch = max_iter - launched < check_every ? max_iter - launched : check_every;
-    for (int k = 0; k < batch; k++) {
-      {
-        ProfScope prof(s, KC_PUPDATE);
-        k_pupdate<<<grid, NT, 0, s->stream>>>(s->kr, s->krhat, s->kp, s->knu, s->kz, nrows, s->d_state);
-      }
-      if (s->nranks > 1 && (rc = halo_exchange_ptr(s, s->kz, 1, CUP2D_NFIELDS, false))) return rc;
-      {
-        ProfScope prof(s, KC_SPMV_NU);
-        if (has_irr)
-          k_spmv<0, true><<<grid, NT, 0, s->stream>>>(s->kz, s->krhat, s->knu, nbr, nrows, s->d_state,
-                                                      s->d_partials, s->d_counter, s->comm, irr_view(s));
-        else
-          k_spmv<0, false><<<grid, NT, 0, s->stream>>>(
-              s->kz, s->krhat, s->knu, nbr, nrows, s->d_state, s->d_partials, s->d_counter, s->comm, irr_view(s));
-      }
-      {
-        ProfScope prof(s, KC_XRUPDATE);
-        k_r_update<<<grid, NT, 0, s->stream>>>(s->kr, s->knu, s->kzr, nrows, s->d_state);
-      }
-      if (s->nranks > 1 && (rc = halo_exchange_ptr(s, s->kzr, 1, CUP2D_NFIELDS + 4, false))) return rc;
-      {
-        ProfScope prof(s, KC_SPMV_T);
-        if (has_irr)
-          k_spmv<1, true><<<grid, NT, 0, s->stream>>>(s->kzr, s->kr, s->kt, nbr, nrows, s->d_state,
-                                                      s->d_partials, s->d_counter, s->comm, irr_view(s));
-        else
-          k_spmv<1, false><<<grid, NT, 0, s->stream>>>(
-              s->kzr, s->kr, s->kt, nbr, nrows, s->d_state, s->d_partials, s->d_counter, s->comm, irr_view(s));
-      }
-      {
-        ProfScope prof(s, KC_FINAL);
-        k_final<<<grid, NT, 0, s->stream>>>(s->kx[0], s->kx[1], s->kx[2], s->kz, s->kzr, s->kr, s->kt,
-                                            s->krhat, nrows, s->d_state, s->d_partials, s->d_counter,
-                                            s->comm);
-      }
-      s->launches += 5;
-    }
+    const int batch = max_iter - launched < check_every ? max_iter - launched : check_every;
+    if ((rc = poisson_iterations(s, batch, s->stream))) return rc;
     launched += batch;
-    CUP2D_CUDA(cudaGetLastError());
-    CUP2D_CUDA(cudaMemcpyAsync(h, s->d_state, sizeof *h, cudaMemcpyDeviceToHost, s->stream));
-    CUP2D_CUDA(cudaStreamSynchronize(s->stream));
-    done = h->done || launched >= max_iter;
+    if ((rc = poisson_result(s, nullptr, nullptr))) return rc;
+    done = s->h_state->done || launched >= max_iter;
   }
-  if (max_iter <= 0) {
-    CUP2D_CUDA(cudaMemcpyAsync(h, s->d_state, sizeof *h, cudaMemcpyDeviceToHost, s->stream));
-    CUP2D_CUDA(cudaStreamSynchronize(s->stream));
-  }
-  if (iters) *iters = h->iter;
-  if (err) *err = h->err_opt;
-  return CUP2D_OK;
+  return poisson_result(s, iters, err);
 }
 
 } // namespace cup2d

@@ -30,7 +30,7 @@ __global__ void __launch_bounds__(NT) umax_kernel(const double *__restrict__ vel
   grid_reduce<1, NT>(dummy, m, partials, counter, comm, [=](const double *, double mx) { out[0] = mx; });
 }
 
-int launch_umax(cup2d_sim *s, double *umax_out) {
+int launch_umax_async(cup2d_sim *s) {
   const size_t n2 = (size_t)s->nloc * 64;
   int grid = s->num_sms * 8;
   {
@@ -39,6 +39,36 @@ int launch_umax(cup2d_sim *s, double *umax_out) {
   }
   s->launches++;
   CUP2D_CUDA(cudaGetLastError());
+  return CUP2D_OK;
+}
+
+// dt rule (main.cpp:6593-6595) and everything derived from dt, on the device, in the host code's operation order
+// (explicit round-to-nearest operations: no FMA contraction, so dt is bitwise what cup2d_compute_dt returns)
+__global__ void k_step_factors(StepFactors *f, const double *umax_in, double dt_host, double h, double nu, double cfl) {
+  double dt = dt_host, umax = 0.0;
+  if (umax_in) {
+    umax = *umax_in;
+    const double dt_diff = __ddiv_rn(__dmul_rn(__dmul_rn(0.25, h), h), __dadd_rn(nu, __dmul_rn(__dmul_rn(0.25, h), umax)));
+    const double dt_adv = __ddiv_rn(h, __dadd_rn(umax, 1e-8));
+    dt = fmin(dt_diff, __dmul_rn(cfl, dt_adv));
+  }
+  f->dt = dt;
+  f->umax = umax;
+  f->afac = __dmul_rn(-dt, h);                                             // launch_advect: -dt * h
+  f->dfac = __dmul_rn(nu, dt);                                             //                nu * dt
+  f->rhs_fac = __ddiv_rn(__dmul_rn(0.5, h), dt);                           // launch_pressure_rhs: 0.5 * h / dt
+  f->corr_fac = __dmul_rn(__dmul_rn(__dmul_rn(-0.5, dt), h), __ddiv_rn(__ddiv_rn(1.0, h), h)); // (-0.5 dt h) * (1/h/h)
+}
+int launch_step_factors(cup2d_sim *s, double dt_host) {
+  k_step_factors<<<1, 1, 0, s->stream>>>(s->d_fac, dt_host > 0 ? nullptr : s->d_scal, dt_host, s->h, s->nu, s->cfl);
+  s->launches++;
+  CUP2D_CUDA(cudaGetLastError());
+  return CUP2D_OK;
+}
+
+int launch_umax(cup2d_sim *s, double *umax_out) {
+  int rc = launch_umax_async(s);
+  if (rc) return rc;
   CUP2D_CUDA(cudaMemcpyAsync(s->h_scal, s->d_scal, sizeof(double), cudaMemcpyDeviceToHost, s->stream));
   CUP2D_CUDA(cudaStreamSynchronize(s->stream));
   *umax_out = s->h_scal[0];
@@ -105,10 +135,15 @@ __global__ void __launch_bounds__(NT)
 pressure_rhs_kernel(const double *__restrict__ vel, const double *__restrict__ udef,
                     const double *__restrict__ chi, const double *__restrict__ pold,
                     double *__restrict__ tmp, double *__restrict__ pres, const int4 *__restrict__ nbr,
-                    int nrows, double fac) {
+                    int nrows, double fac_arg, const StepFactors *__restrict__ sf, int nrows_zero) {
   __shared__ __align__(16) double s_scr[WPB * ROWS_SCRATCH];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   double *sw = s_scr + warp * ROWS_SCRATCH;
+  const double fac = sf ? sf->rhs_fac : fac_arg;
+  // pres = 0 on the halo slots as well (rows nrows .. nrows_zero): the solve that follows starts from x0 = pres and
+  // then needs no halo refresh of it
+  for (int i = nrows * 4 + blockIdx.x * NT + threadIdx.x; i < nrows_zero * 4; i += gridDim.x * NT)
+    reinterpret_cast<double2 *>(pres)[i] = make_double2(0.0, 0.0);
   for (int row0 = (blockIdx.x * WPB + warp) * 32; row0 < nrows; row0 += gridDim.x * WPB * 32) {
     const int nv = min(32, nrows - row0);
     const int row = row0 + lane, slot = row >> 3, y = row & 7;
@@ -140,7 +175,7 @@ pressure_rhs_kernel(const double *__restrict__ vel, const double *__restrict__ u
   }
 }
 
-int launch_pressure_rhs(cup2d_sim *s, double dt, bool has_udef) {
+int launch_pressure_rhs(cup2d_sim *s, double dt, bool has_udef, const StepFactors *dev, bool zero_pres_halo) {
   // pold <- pres is a pointer swap; the kernel then zeroes the new pres (main.cpp:7016-7021)
   swap_fields(s, CUP2D_PRES, CUP2D_POLD);
   if (s->nranks > 1) {
@@ -152,15 +187,16 @@ int launch_pressure_rhs(cup2d_sim *s, double dt, bool has_udef) {
   const int nrows = (int)s->nloc * 8;
   const int grid = min((nrows + NT - 1) / NT, s->num_sms * 8);
   const double fac = 0.5 * s->h / dt; // main.cpp:6119
+  const int nrows_zero = zero_pres_halo ? (int)s->nslots * 8 : nrows;
   ProfScope prof(s, KC_RHS);
   if (has_udef)
     pressure_rhs_kernel<true><<<grid, NT, 0, s->stream>>>(s->f[CUP2D_VEL], s->f[CUP2D_TMPV], s->f[CUP2D_CHI],
                                                           s->f[CUP2D_POLD], s->f[CUP2D_TMP], s->f[CUP2D_PRES],
-                                                          reinterpret_cast<const int4 *>(s->d_nbr), nrows, fac);
+                                                          reinterpret_cast<const int4 *>(s->d_nbr), nrows, fac, dev, nrows_zero);
   else // no bodies: chi * div(udef) is identically zero (main.cpp:6980-6983 leaves tmpV = 0)
     pressure_rhs_kernel<false><<<grid, NT, 0, s->stream>>>(s->f[CUP2D_VEL], s->f[CUP2D_TMPV], s->f[CUP2D_CHI],
                                                            s->f[CUP2D_POLD], s->f[CUP2D_TMP], s->f[CUP2D_PRES],
-                                                           reinterpret_cast<const int4 *>(s->d_nbr), nrows, fac);
+                                                           reinterpret_cast<const int4 *>(s->d_nbr), nrows, fac, dev, nrows_zero);
   s->launches++;
   CUP2D_CUDA(cudaGetLastError());
   return CUP2D_OK;
@@ -216,14 +252,18 @@ __device__ __forceinline__ void rows_P(const double *__restrict__ x, const doubl
 // x = Poisson solution (lives in a Krylov buffer), avg = its volume-weighted mean.  The reference's
 // second mean (of the already mean-free field, main.cpp:7149-7166) is rounding noise and is dropped.
 __global__ void __launch_bounds__(NT)
-pressure_correct_kernel(const double *__restrict__ x, const double *__restrict__ pold,
+pressure_correct_kernel(const double *x0, const double *x1, const double *x2, const double *__restrict__ pold,
                         double *__restrict__ pres, double *__restrict__ vel,
-                        const int4 *__restrict__ nbr, int nrows, const double *__restrict__ xsum,
-                        double inv_ncells, double pfac_ih2) {
+                        const int4 *__restrict__ nbr, int nrows, const KrylovState *__restrict__ st,
+                        double inv_ncells, double pfac_ih2_arg, const StepFactors *__restrict__ sf) {
   __shared__ __align__(16) double s_scr[WPB * ROWS_SCRATCH];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   double *sw = s_scr + warp * ROWS_SCRATCH;
-  const double avg = xsum[0] * inv_ncells;
+  // the best iterate is in the x buffer the device-side Krylov state names (no host copy of the state is needed)
+  const int opt = st->opt;
+  const double *__restrict__ x = opt == 0 ? x0 : (opt == 1 ? x1 : x2);
+  const double avg = st->xsum * inv_ncells;
+  const double pfac_ih2 = sf ? sf->corr_fac : pfac_ih2_arg;
   for (int row0 = (blockIdx.x * WPB + warp) * 32; row0 < nrows; row0 += gridDim.x * WPB * 32) {
     const int nv = min(32, nrows - row0);
     const int row = row0 + lane, slot = row >> 3, y = row & 7;
@@ -243,11 +283,10 @@ pressure_correct_kernel(const double *__restrict__ x, const double *__restrict__
   }
 }
 
-int launch_pressure_correct(cup2d_sim *s, double dt) {
-  const double *x = s->kx[s->h_state->opt];
+int launch_pressure_correct(cup2d_sim *s, double dt, const StepFactors *dev) {
   if (s->nranks > 1) {
     int rc;
-    if ((rc = halo_exchange_ptr(s, s->kx[s->h_state->opt], 1, CUP2D_NFIELDS + 1 + s->h_state->opt))) return rc;
+    if ((rc = halo_exchange_xopt(s))) return rc;
     if ((rc = halo_exchange_ptr(s, s->f[CUP2D_POLD], 1, CUP2D_POLD))) return rc;
   }
   const int nrows = (int)s->nloc * 8;
@@ -256,8 +295,8 @@ int launch_pressure_correct(cup2d_sim *s, double dt) {
   const double ih2 = 1.0 / s->h / s->h; // main.cpp:7182
   ProfScope prof(s, KC_CORRECT);
   pressure_correct_kernel<<<grid, NT, 0, s->stream>>>(
-      x, s->f[CUP2D_POLD], s->f[CUP2D_PRES], s->f[CUP2D_VEL], reinterpret_cast<const int4 *>(s->d_nbr),
-      nrows, &s->d_state->xsum, 1.0 / ((double)s->nglobal * 64.0), pfac * ih2);
+      s->kx[0], s->kx[1], s->kx[2], s->f[CUP2D_POLD], s->f[CUP2D_PRES], s->f[CUP2D_VEL], reinterpret_cast<const int4 *>(s->d_nbr),
+      nrows, s->d_state, 1.0 / ((double)s->nglobal * 64.0), pfac * ih2, dev);
   s->launches++;
   CUP2D_CUDA(cudaGetLastError());
   return CUP2D_OK;

@@ -210,13 +210,53 @@ struct IrrView {
   const double *val = nullptr;
 };
 
+// Neighbour rows that live in HALO slots (slot >= nloc) of a multi-rank context.  In the Krylov loop the producing
+// kernel of a vector pushes its perimeter rows straight into the neighbours' halo slots over NVLink and raises a flag
+// (poisson.cu: push_rows / push_finish); the consuming stencil kernel waits for the flags of the ranks it has halo
+// blocks of — lazily, only in the lanes that touch a halo slot, so that interior rows never wait — and then reads the
+// slots with coherent loads (the data arrived while this kernel was running).
+struct NoGate {
+  static constexpr bool on = false;
+  int nloc = 0;
+  __device__ __forceinline__ void wait() const {}
+};
+struct HaloGate {
+  static constexpr bool on = true;
+  int nloc;                  // slots >= nloc are halo slots
+  unsigned mask;             // ranks this rank has halo blocks of
+  unsigned long long target; // push epoch the flags must have reached
+  Comm comm;
+  __device__ __forceinline__ void wait() const {
+    const unsigned long long *mine = comm.mb[comm.rank];
+    for (int r = 0; r < comm.nranks; r++)
+      if ((mask >> r) & 1u) wait_flag(mine + MB_PUSHED + r, target, comm, CW_PUSHED, r);
+  }
+};
+template <class G> __device__ __forceinline__ double nb_ld1(const double *z, int slot, int off, const G &g) {
+  const double *p = z + (size_t)slot * 64 + off;
+  if (G::on && slot >= g.nloc) return ld_coherent(p);
+  return *p;
+}
+template <class G> __device__ __forceinline__ void nb_row1(const double *z, int slot, int y, double (&c)[8], const G &g) {
+  const double2 *p = reinterpret_cast<const double2 *>(z + (size_t)slot * 64 + y * 8);
+  const bool halo = G::on && slot >= g.nloc;
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    const double2 v = halo ? ld_coherent2(p + k) : p[k];
+    c[2 * k] = v.x;
+    c[2 * k + 1] = v.y;
+  }
+}
+
 // Undivided 5-point Laplacian rows of a scalar field for the warp's 32 rows, ghost = the cell itself at
 // a domain wall (Neumann rows of main.cpp:7100-7107 / ScalarLab::Neumann2D main.cpp:3210-3245).
 // Returns the own row in c and the Laplacian in out.  Summation order S,W,E,N then -4C.
 // rows_lap_c: the caller already holds the chunk of z (so that other global loads can be in flight too)
+template <class G = NoGate>
 __device__ __forceinline__ void rows_lap_c(const double2 (&cz)[4], const double *__restrict__ z, int row0,
                                            int nvalid, const int4 *__restrict__ nbr, double *sw, int lane,
-                                           double (&c)[8], double (&out)[8], const IrrView irr = IrrView());
+                                           double (&c)[8], double (&out)[8], const IrrView irr = IrrView(),
+                                           const G gate = G());
 __device__ __forceinline__ void rows_lap(const double *__restrict__ z, int row0, int nvalid,
                                          const int4 *__restrict__ nbr, double *sw, int lane,
                                          double (&c)[8], double (&out)[8], const IrrView irr = IrrView()) {
@@ -224,28 +264,32 @@ __device__ __forceinline__ void rows_lap(const double *__restrict__ z, int row0,
   chunk_ld(z, row0, nvalid, lane, cz);
   rows_lap_c(cz, z, row0, nvalid, nbr, sw, lane, c, out, irr);
 }
+template <class G>
 __device__ __forceinline__ void rows_lap_c(const double2 (&cz)[4], const double *__restrict__ z, int row0,
                                            int nvalid, const int4 *__restrict__ nbr, double *sw, int lane,
-                                           double (&c)[8], double (&out)[8], const IrrView irr) {
+                                           double (&c)[8], double (&out)[8], const IrrView irr, const G gate) {
   chunk_to_rows(sw, lane, cz, c);
   const int row = row0 + lane, slot = row >> 3, y = row & 7;
   if (lane < nvalid) {
     const int4 nb = nbr[slot];
+    if (G::on) { // pushed halo rows: wait (once, only here) for the ranks that own them
+      if (nb.x >= gate.nloc || nb.y >= gate.nloc || (y == 7 && nb.w >= gate.nloc) || (y == 0 && nb.z >= gate.nloc)) gate.wait();
+    }
     double up[8], dn[8];
     if (y < 7) rows_peek1(sw, lane + 1, up);
-    else if (nb.w >= 0) grow_load1(z, nb.w, 0, up);
+    else if (nb.w >= 0) nb_row1(z, nb.w, 0, up, gate);
     else {
 #pragma unroll
       for (int i = 0; i < 8; i++) up[i] = c[i];
     }
     if (y > 0) rows_peek1(sw, lane - 1, dn);
-    else if (nb.z >= 0) grow_load1(z, nb.z, 7, dn);
+    else if (nb.z >= 0) nb_row1(z, nb.z, 7, dn, gate);
     else {
 #pragma unroll
       for (int i = 0; i < 8; i++) dn[i] = c[i];
     }
-    const double gW = nb.x >= 0 ? z[(size_t)nb.x * 64 + y * 8 + 7] : c[0];
-    const double gE = nb.y >= 0 ? z[(size_t)nb.y * 64 + y * 8 + 0] : c[7];
+    const double gW = nb.x >= 0 ? nb_ld1(z, nb.x, y * 8 + 7, gate) : c[0];
+    const double gE = nb.y >= 0 ? nb_ld1(z, nb.y, y * 8 + 0, gate) : c[7];
 #pragma unroll
     for (int i = 0; i < 8; i++) {
       const double e = i < 7 ? c[i + 1] : gE;
@@ -260,7 +304,10 @@ __device__ __forceinline__ void rows_lap_c(const double2 (&cz)[4], const double 
           const int idx = irr.tab[k * 64 + y * 8 + i];
           if (idx >= 0) {
             double acc = 0.0;
-            for (int j = irr.rowptr[idx]; j < irr.rowptr[idx + 1]; j++) acc = fma(irr.val[j], z[irr.col[j]], acc);
+            for (int j = irr.rowptr[idx]; j < irr.rowptr[idx + 1]; j++) {
+              const int cj = irr.col[j];
+              acc = fma(irr.val[j], (G::on && cj >= gate.nloc * 64) ? ld_coherent(z + cj) : z[cj], acc);
+            }
             out[i] = acc;
           }
         }

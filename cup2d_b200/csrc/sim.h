@@ -36,11 +36,21 @@ struct KrylovState {
   int pad;
 };
 
+// dt-dependent factors of the current time step, device-resident (k_step_factors): a step captured in a CUDA graph
+// reads them from here, so neither dt nor anything derived from it is baked into the graph
+struct StepFactors {
+  double dt, umax;
+  double afac, dfac;   // advect-diffuse: -dt h, nu dt                     (main.cpp:5446-5447)
+  double rhs_fac;      // Poisson right-hand side: 0.5 h / dt               (main.cpp:6119)
+  double corr_fac;     // pressure correction: (-0.5 dt h) / h^2            (main.cpp:6028, 7182)
+};
+
 struct PeerBlob { // what every rank publishes to the others (cup2d_peer_export)
   cudaIpcMemHandle_t field[CUP2D_NFIELDS];
   cudaIpcMemHandle_t kz, kx[3], kzr;
   cudaIpcMemHandle_t mailbox;
-  int64_t nloc;
+  cudaIpcMemHandle_t halo_gid; // global ids of this rank's halo slots (read once by the peers at attach time)
+  int64_t nloc, nhalo;
   int32_t rank, device;
 };
 
@@ -93,11 +103,17 @@ struct cup2d_sim {
   double *d_partials = nullptr;
   unsigned int *d_counter = nullptr;
   double *d_scal = nullptr, *h_scal = nullptr; // small scalar mailbox (umax, sums)
+  cup2d::StepFactors *d_fac = nullptr, *h_fac = nullptr; // factors of the current step (device) / pinned read-back
   int num_sms = 0;
   // multi-GPU (peer memory over NVLink)
   bool peers_attached = false;
   void *peer_base[cup2d::MAX_RANKS][CUP2D_NFIELDS + 5] = {}; // fields, kz, kx[3], kzr
   int *d_halo_src = nullptr;           // [nhalo][2] = (owner rank, slot on owner)
+  int *d_halo_gid = nullptr;           // [nhalo] global block id of every halo slot (exported to the peers)
+  unsigned src_mask = 0, dst_mask = 0; // ranks this rank pulls halo blocks from / ranks that pull from this rank
+  int *d_push_first = nullptr;         // [nloc] first entry of the block in d_push_ent, -1: no peer has it as a halo slot
+  int2 *d_push_ent = nullptr;          // (peer rank, halo slot on that peer) ..., (-1,-1) ends a block's list
+  int64_t n_push = 0;
   unsigned long long *d_mailbox = nullptr;       // this rank's flag/scalar mailbox (peer-writable)
   unsigned long long *peer_mailbox[cup2d::MAX_RANKS] = {};
   unsigned long long epoch = 0;
@@ -117,7 +133,16 @@ struct cup2d_sim {
   // optional per-kernel-class CUDA-event instrumentation (cup2d_profile_*)
   bool prof_on = false;
   struct ProfRec { int cls; cudaEvent_t a, b; };
-  std::vector<ProfRec> prof;
+  std::vector<ProfRec> prof;          // records since cup2d_profile_enable(1)
+  std::vector<cudaEvent_t> prof_pool; // events are created once and reused: no cudaEventCreate inside a timed region
+  size_t prof_pool_used = 0;
+  // whole-step CUDA graphs (cup2d_step_enqueue): one executable graph per (buffer assignment, arguments)
+  struct StepGraph { std::vector<unsigned long long> key; cudaGraphExec_t exec = nullptr; cudaGraph_t graph = nullptr; int64_t launches = 0; };
+  std::vector<StepGraph> graphs;
+  bool use_graph = true, warmed = false;
+  cudaStream_t body_stream = nullptr;             // captures the body of the Krylov WHILE node
+  unsigned long long cond_handle = 0;             // cudaGraphConditionalHandle of the loop being captured (0: none)
+  bool step_pending = false;                      // a step was enqueued whose result has not been read
 };
 
 namespace cup2d {
@@ -131,8 +156,13 @@ struct ProfScope {
     if (!s->prof_on) return;
     cup2d_sim::ProfRec r;
     r.cls = cls;
-    cudaEventCreate(&r.a);
-    cudaEventCreate(&r.b);
+    while (s->prof_pool.size() < s->prof_pool_used + 2) {
+      cudaEvent_t e;
+      cudaEventCreate(&e);
+      s->prof_pool.push_back(e);
+    }
+    r.a = s->prof_pool[s->prof_pool_used++];
+    r.b = s->prof_pool[s->prof_pool_used++];
     cudaEventRecord(r.a, s->stream);
     s->prof.push_back(r);
     idx = (int)s->prof.size() - 1;
@@ -151,10 +181,12 @@ inline IrrView irr_view(const cup2d_sim *s) {
 }
 // operators (host-side launchers; all on s->stream)
 int launch_advect(cup2d_sim *s, const double *in, const double *old, double *out, double coef,
-                  double dt, bool raw);
+                  double dt, bool raw, const StepFactors *dev = nullptr);
 int launch_umax(cup2d_sim *s, double *umax_out);
-int launch_pressure_rhs(cup2d_sim *s, double dt, bool has_udef);
-int launch_pressure_correct(cup2d_sim *s, double dt);
+int launch_umax_async(cup2d_sim *s);                      // umax -> d_scal[0], no host synchronisation
+int launch_step_factors(cup2d_sim *s, double dt_host);    // d_fac from dt_host (> 0) or from d_scal[0] (the dt rule on the device)
+int launch_pressure_rhs(cup2d_sim *s, double dt, bool has_udef, const StepFactors *dev = nullptr, bool zero_pres_halo = false);
+int launch_pressure_correct(cup2d_sim *s, double dt, const StepFactors *dev = nullptr);
 int launch_adapt_tags(cup2d_sim *s, double rtol, int chi_cells, double *linf_host);
 int dump_fields(cup2d_sim *s, double time, const char *path);
 int ensure_block_ij(cup2d_sim *s);
@@ -165,8 +197,13 @@ int shape_penalize(cup2d_sim *s, int shape, double lambda, double dt, double cx,
                    double omega);
 int udef_assemble(cup2d_sim *s);
 int poisson_solve(cup2d_sim *s, double tol_abs, double tol_rel, int max_restarts, int max_iter,
-                  int *iters, double *err);
+                  int *iters, double *err, bool x0_halo_current = false);
+int poisson_begin(cup2d_sim *s, double tol_abs, double tol_rel, int max_restarts, int max_iter, bool x0_halo_current);
+int poisson_iterations(cup2d_sim *s, int n, cudaStream_t stream);
+int poisson_result(cup2d_sim *s, int *iters, double *err);
 int halo_exchange_ptr(cup2d_sim *s, double *base, int dim, int peer_index, bool done_barrier = true);
+int halo_exchange_xopt(cup2d_sim *s); // halo of the x buffer KrylovState::opt names (chosen on the device)
+int comm_check(cup2d_sim *s);         // CUP2D_ECOMM if a cross-GPU wait of this rank was given up
 void swap_fields(cup2d_sim *s, int a, int b); // pointer swap, mirrored on the peer mappings
 int poisson_create_general_ranks_ex(int64_t nblocks_global, int32_t rank, int32_t nranks, const int64_t *rank_begin,
                                     const int32_t *nbr, int64_t n_irr, const int32_t *irr_rows, const int32_t *irr_rowptr,

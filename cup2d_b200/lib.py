@@ -15,6 +15,7 @@ SYMBOLS = [
     "cup2d_field_fill", "cup2d_field_device_ptr", "cup2d_sync", "cup2d_stream", "cup2d_compute_dt",
     "cup2d_advect_diffuse_stage", "cup2d_advect_diffuse_rhs", "cup2d_advect_diffuse_rk2",
     "cup2d_pressure_rhs", "cup2d_poisson_solve", "cup2d_pressure_correct", "cup2d_step",
+    "cup2d_step_enqueue", "cup2d_step_result", "cup2d_set_graph",
     "cup2d_pipe_upload", "cup2d_pipe_step", "cup2d_pipe_download", "cup2d_pipe_wait",
     "cup2d_peer_blob_size", "cup2d_peer_export", "cup2d_peer_attach", "cup2d_halo_exchange",
     "cup2d_launch_count", "cup2d_profile_enable", "cup2d_profile_read",
@@ -86,6 +87,9 @@ def load_library():
     lib.cup2d_poisson_solve.argtypes = [P, D, D, I, I, C.POINTER(I), C.POINTER(D)]
     lib.cup2d_pressure_correct.argtypes = [P, D]
     lib.cup2d_step.argtypes = [P, D, I, D, D, I, I, C.POINTER(D), C.POINTER(I), C.POINTER(D)]
+    lib.cup2d_step_enqueue.argtypes = [P, D, I, D, D, I, I]
+    lib.cup2d_step_result.argtypes = [P, C.POINTER(D), C.POINTER(I), C.POINTER(D)]
+    lib.cup2d_set_graph.argtypes = [P, I]
     lib.cup2d_pipe_upload.argtypes = [P, I, P, P]
     lib.cup2d_pipe_step.argtypes = [P, I, D, D, D, I, I, C.POINTER(D), C.POINTER(I), C.POINTER(D)]
     lib.cup2d_pipe_download.argtypes = [P, I, P, P]

@@ -188,6 +188,20 @@ class Simulation:
                                      C.byref(dto), C.byref(it), C.byref(err)))
         return dto.value, it.value, err.value
 
+    def step_enqueue(self, dt=0.0, keep_udef=False, tol_abs=0.0, tol_rel=0.0, max_restarts=100, max_iter=1000):
+        """the same step without waiting for the device (one CUDA graph launch from the second step on);
+        dt <= 0: dt control runs on the device inside the step"""
+        _l.check(self.lib.cup2d_step_enqueue(self._h, dt, int(keep_udef), tol_abs, tol_rel, max_restarts, max_iter))
+
+    def step_result(self):
+        """waits for the enqueued steps; (dt, iterations, residual) of the last one"""
+        dto, it, err = C.c_double(), C.c_int(), C.c_double()
+        _l.check(self.lib.cup2d_step_result(self._h, C.byref(dto), C.byref(it), C.byref(err)))
+        return dto.value, it.value, err.value
+
+    def set_graph(self, on):
+        _l.check(self.lib.cup2d_set_graph(self._h, int(on)))
+
     # ---- host-buffer pipeline (cup2d_pipe_*): independent steps with inputs and results in host memory ----
     PIPE_SLOTS = 4
 

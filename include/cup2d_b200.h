@@ -34,7 +34,9 @@ enum {
   CUP2D_EINVAL = -1,  /* bad argument / unsupported topology */
   CUP2D_ECUDA = -2,   /* CUDA runtime error (message in cup2d_last_error) */
   CUP2D_ENOGPU = -3,  /* no usable sm_100 device: there is NO CPU fallback */
-  CUP2D_ESTATE = -4   /* call made in the wrong state (e.g. multi-rank step before peers attached) */
+  CUP2D_ESTATE = -4,  /* call made in the wrong state (e.g. multi-rank step before peers attached) */
+  CUP2D_ECOMM = -5    /* a cross-GPU wait ran into its time limit (peer dead, or ranks issued different call sequences);
+                         the reference aborts through MPI in that situation (SURVEY.md 8(b) error convention) */
 };
 
 /* field ids (var.* of main.cpp:3264-3278) */
@@ -137,6 +139,19 @@ int cup2d_udef_assemble(cup2d_sim *s);
  * (or kept if keep_udef), pressure_rhs, poisson_solve, pressure_correct.  Returns dt used. */
 int cup2d_step(cup2d_sim *s, double dt_in, int keep_udef, double tol_abs, double tol_rel,
                int max_restarts, int max_iter, double *dt_out, int *iters_out, double *err_out);
+/* The same step, asynchronously: cup2d_step_enqueue puts the whole step on the context's stream and returns without
+ * waiting for the device; cup2d_step_result waits for it and returns dt, iteration count and residual
+ * (cup2d_step == enqueue + result).  dt_in <= 0: the dt rule (main.cpp:6579-6595) runs on the device inside the step.
+ * From the second step of a context on, the step is ONE cudaGraphLaunch of a graph captured once per buffer assignment
+ * (vel/vold and pres/pold swap every step) and argument set; with tolerances the Krylov loop is a graph WHILE node whose
+ * condition the device sets, so a tolerance-driven solve needs no host polling either.  Replaces the reference's
+ * ~25 launches + 4 host synchronisations + 4 MPI_Allreduce per Krylov iteration (cuda.cu:403-548) and its per-operator
+ * OpenMP loops (main.cpp:6607-6642, 7011-7027, 7120-7187).  Several steps may be enqueued before a result is read.
+ * cup2d_set_graph(s, 0) makes every step use direct kernel launches (what profiling with cup2d_profile_enable does). */
+int cup2d_step_enqueue(cup2d_sim *s, double dt_in, int keep_udef, double tol_abs, double tol_rel, int max_restarts,
+                       int max_iter);
+int cup2d_step_result(cup2d_sim *s, double *dt_out, int *iters_out, double *err_out);
+int cup2d_set_graph(cup2d_sim *s, int on);
 
 /* ---- host-buffer pipeline (single rank): independent steps whose inputs and results live in HOST memory ----
  * What the reference does around every solve is upload, compute, download, one after the other (cuda.cu:298-301,

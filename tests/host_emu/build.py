@@ -91,7 +91,9 @@ ASM_REWRITES = [  # (regex over the source text, replacement): the PTX of common
     (r'asm volatile\("st\.relaxed\.sys.*?: "memory"\);', "*(volatile unsigned long long *)p = v;"),
     (r'asm volatile\("ld\.acquire\.sys.*?: "memory"\);', "v = *(volatile const unsigned long long *)p; __threadfence();"),
     (r'asm volatile\("ld\.relaxed\.sys\.global\.u64.*?: "memory"\);', "v = *(volatile const unsigned long long *)p;"),
-    (r'asm volatile\("ld\.relaxed\.sys\.global\.v2\.f64.*?: "memory"\);', "v = from[i];"),
+    (r'asm volatile\("ld\.relaxed\.sys\.global\.v2\.f64.*?: "memory"\);', "v = *p;"),
+    (r'asm volatile\("ld\.relaxed\.sys\.global\.f64.*?: "memory"\);', "v = *(volatile const double *)p;"),
+    (r'asm volatile\("mov\.u64 %0, %globaltimer;".*?"memory"\);', "t = emu_now_ns();"),
 ]
 LAUNCH_ANY = re.compile(r"(\b\w+)((?:<[^<>;]*>)?)<<<(.*?)>>>\((.*?)\);", re.S)
 

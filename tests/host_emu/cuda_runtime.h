@@ -29,6 +29,17 @@ inline cudaError_t cudaDeviceSynchronize() { return 0; }
 inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t *s, unsigned) { *s = nullptr; return 0; }
 enum { cudaStreamNonBlocking = 1 };
 
+// graphs do not exist here: the product code takes its direct-launch path under CUP2D_FULL_EMU; only the types and the
+// destructors it names unconditionally are provided
+typedef struct EmuGraph *cudaGraph_t;
+typedef struct EmuGraphExec *cudaGraphExec_t;
+inline cudaError_t cudaGraphExecDestroy(cudaGraphExec_t) { return 0; }
+inline cudaError_t cudaGraphDestroy(cudaGraph_t) { return 0; }
+#include <chrono>
+inline unsigned long long emu_now_ns() {
+  return (unsigned long long)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+inline double __ddiv_rn(double a, double b) { volatile double r = a / b; return r; }
 inline unsigned atomicAdd(unsigned *p, unsigned v) { return std::atomic_ref<unsigned>(*p).fetch_add(v); }
 inline void __threadfence() { std::atomic_thread_fence(std::memory_order_seq_cst); }
 inline void __threadfence_system() { std::atomic_thread_fence(std::memory_order_seq_cst); }

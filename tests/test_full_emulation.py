@@ -31,7 +31,7 @@ def emulated_library():
 
 
 def test_gpu_parity_subset_on_the_emulated_library(emulated_library):
-    env = dict(os.environ, CUP2D_B200_LIB=emulated_library, CUP2D_TEST_UNVALIDATED="1")
+    env = dict(os.environ, CUP2D_B200_LIB=emulated_library)
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(HERE, "test_gpu_parity.py"),
                         os.path.join(HERE, "test_gpu_amr.py"), "-m", "gpu", "-q", "-x", "-k", SUBSET, "-p", "no:cacheprovider"],
                        stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=env, timeout=900, cwd=ROOT)

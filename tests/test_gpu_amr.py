@@ -3,17 +3,15 @@ tagging of cup2d_amr_adapt_tags) against the reference's own outputs on its 7-le
 amrtags_lmax8.npz), against the reference restatement on a second mesh family, and in situ (the reference's run.sh case
 with its hot path spliced onto this path).
 
-This path was written after round 1's GPU budget was spent and has NOT been run on hardware yet: the tests are skipped
-unless CUP2D_TEST_UNVALIDATED=1, so that the suite reports only what has actually been validated.  All of them pass on
-the CPU against the emulated build of the same sources (tools/run_emulated_gpu_tests.sh, tests/test_full_emulation.py)."""
+First run on hardware in round 2 (profiles/r02a_first_contact.md: all green on a B200, compute-sanitizer memcheck and
+racecheck clean); they also pass on the CPU against the emulated build of the same sources
+(tools/run_emulated_gpu_tests.sh, tests/test_full_emulation.py)."""
 import os
 
 import numpy as np
 import pytest
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("CUP2D_TEST_UNVALIDATED") != "1",
-                                 reason="the multi-level device path has not been run on hardware yet (set CUP2D_TEST_UNVALIDATED=1)")]
+pytestmark = [pytest.mark.gpu]
 
 
 @pytest.fixture(scope="module")
@@ -362,7 +360,7 @@ def test_two_ranks_on_two_gpus_multi_level():
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
                         "--master-addr", "127.0.0.1", "--master-port", "29578", os.path.join(root, "tools", "multi_gpu_check.py")],
                        stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=400,
-                       env=dict(os.environ, CUP2D_TEST_UNVALIDATED="1"))
+                       env=dict(os.environ))
     assert r.returncode == 0, r.stdout[-2000:]
     for check in ("amr_poisson_ranks", "amr_step_ranks", "amr_distributed_ranks"):
         assert f'"check": "{check}"' in r.stdout

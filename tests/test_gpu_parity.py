@@ -588,9 +588,6 @@ def test_shape_calls_reject_bad_arguments():
     sim.close()
 
 
-@pytest.mark.skipif(os.environ.get("CUP2D_TEST_UNVALIDATED") != "1",
-                    reason="cup2d_pipe_* was written after the GPU budget was spent: opt-in until it has run on hardware "
-                           "(bench.py verifies it bit for bit against the blocking calls before using its figure)")
 def test_host_pipeline_matches_blocking_calls():
     """cup2d_pipe_*: independent steps with host inputs and results, upload(n+1) || step(n) || download(n-1) on three
     streams with buffer trading — bit-identical to cup2d_field_upload + cup2d_step + cup2d_field_download, for more jobs
@@ -626,10 +623,7 @@ def test_host_pipeline_matches_blocking_calls():
         sim.pipe_upload(sim.PIPE_SLOTS, vin[0].data_ptr(), pin_[0].data_ptr())
 
 
-@pytest.mark.parametrize("case", ["all_zero", "constant_pressure", "uniform_flow",
-                                  pytest.param("tiny_values", marks=pytest.mark.skipif(
-                                      os.environ.get("CUP2D_TEST_UNVALIDATED") != "1",
-                                      reason="underflow corner added after the last GPU run: opt-in until seen on hardware"))])
+@pytest.mark.parametrize("case", ["all_zero", "constant_pressure", "uniform_flow", "tiny_values"])
 def test_degenerate_inputs_vs_oracle(case):
     """inputs on which the Krylov recurrences divide by (almost) nothing — zero right-hand side, zero residual after the
     first half-step — and the dt rule has umax = 0: the eps = 1e-21 guards of the reference (cuda.cu:315-326) and its

@@ -15,12 +15,12 @@ echo "== 1. validated suite"
 tail -5 $OUT/pytest_gpu_$TAG.log
 
 echo "== 2. multi-level device path, first contact"
-(time CUP2D_TEST_UNVALIDATED=1 timeout 900 python -m pytest tests/test_gpu_amr.py tests/test_gpu_parity.py -m gpu -q --durations=0 -p no:cacheprovider \
+(time timeout 900 python -m pytest tests/test_gpu_amr.py tests/test_gpu_parity.py -m gpu -q --durations=0 -p no:cacheprovider \
     -k "test_gpu_amr or host_pipeline or tiny_values") \
     > $OUT/pytest_amr_$TAG.log 2>&1
 tail -25 $OUT/pytest_amr_$TAG.log
 for tool in memcheck racecheck; do
-    CUP2D_TEST_UNVALIDATED=1 timeout 400 compute-sanitizer --tool $tool --error-exitcode 9 --print-limit 20 \
+    timeout 400 compute-sanitizer --tool $tool --error-exitcode 9 --print-limit 20 \
         python -m pytest tests/test_gpu_amr.py -m gpu -q -x -k "advect or fast or full_step or bodies or adapt_tags or amr_dump" > $OUT/sanitizer_${tool}_amr_$TAG.log 2>&1
     echo "sanitizer $tool rc=$?"; grep -E "ERROR SUMMARY|RACECHECK SUMMARY|passed|failed" $OUT/sanitizer_${tool}_amr_$TAG.log | tail -3
 done

@@ -10,7 +10,7 @@ OUT=gpurun_out
 mkdir -p $OUT
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1"
 echo "== 1. parity under torchrun, $N ranks"
-CUP2D_TEST_UNVALIDATED=1 timeout 400 $TR --master-port 29571 tools/multi_gpu_check.py > $OUT/multi_gpu_check_${N}gpu_$TAG.jsonl 2> $OUT/multi_gpu_check_${N}gpu_$TAG.err
+timeout 400 $TR --master-port 29571 tools/multi_gpu_check.py > $OUT/multi_gpu_check_${N}gpu_$TAG.jsonl 2> $OUT/multi_gpu_check_${N}gpu_$TAG.err
 echo "rc=$?"; cat $OUT/multi_gpu_check_${N}gpu_$TAG.jsonl; tail -c 400 $OUT/multi_gpu_check_${N}gpu_$TAG.err
 echo "== 2. bench.py at $N GPUs"
 timeout 300 $TR --master-port 29572 bench.py --gpus $N --steps 10 --warmup 3 > $OUT/bench_${N}gpu_$TAG.json 2> $OUT/bench_${N}gpu_$TAG.err

@@ -124,11 +124,6 @@ if rank == 0:
     print(json.dumps({"check": "penalisation", "ranks": world, "integrals_rel_err": pen_err, "blend_udef_bit_exact": bool(pen_exact)}), flush=True)
 assert pen_err < 1e-12 and pen_exact
 sim.close()
-if os.environ.get("CUP2D_TEST_UNVALIDATED") != "1":   # what follows has not been run on hardware yet: opt-in
-    dist.barrier()
-    dist.destroy_process_group()
-    sys.exit(0)
-
 # ---- the Poisson matrix of the reference's 7-level run.sh mesh (neighbour table + coarse-fine rows from the plan),
 #      distributed over the ranks by block ranges, vs the same solve on one GPU (rank 0) ----
 from cup2d_b200.amr import AmrPlan, DistributedPoisson
