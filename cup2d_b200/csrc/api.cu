@@ -664,7 +664,7 @@ void *cup2d_field_device_ptr(cup2d_sim *s, int field) {
 int cup2d_sync(cup2d_sim *s) {
   CHECK_SIM(s);
   CUP2D_CUDA(cudaStreamSynchronize(s->stream));
-  return CUP2D_OK;
+  return comm_check(s); // CUP2D_ECOMM if a cross-GPU wait of this rank was given up
 }
 
 static int need_peers(cup2d_sim *s) {

@@ -225,6 +225,8 @@ void seed_taylor_green() {
       g_input[2 * n2 + (size_t)iy * g_N + ix] = cos(2 * M_PI * x) * cos(2 * M_PI * y);
     }
 }
+struct TimeStat { double min, med, max; };
+static TimeStat g_last_stat;
 template <class F> double median_time(int reps, F f) {
   std::vector<double> t;
   f(); // warm-up (also builds the cached sync plan, excluded as BASELINE.md §3 says)
@@ -234,6 +236,7 @@ template <class F> double median_time(int reps, F f) {
     t.push_back(now() - t0);
   }
   std::sort(t.begin(), t.end());
+  g_last_stat = {t.front(), t[t.size() / 2], t.back()};
   return t[t.size() / 2];
 }
 
@@ -308,15 +311,19 @@ void do_time() {
   sim.nu = 1e-3;
   sim.dt = std::min(0.25 * h * h / (sim.nu + 0.25 * h * umax), 0.5 * h / (umax + 1e-8));
   double t_stage = median_time(g_reps, [] { call_advect(); rk_update(0.5); scatter(var.vel, 2, g_input.data(), g_input.data() + (size_t)g_N * g_NY); });
+  TimeStat s_stage = g_last_stat;
   double t_scatter = median_time(g_reps, [] { scatter(var.vel, 2, g_input.data(), g_input.data() + (size_t)g_N * g_NY); });
   t_stage -= t_scatter;
+  s_stage.min -= t_scatter, s_stage.med -= t_scatter, s_stage.max -= t_scatter;
   double t_rhs = median_time(g_reps, [] { call_rhs(); call_rhs1(); });
+  const TimeStat s_rhs = g_last_stat;
   double t_corr = median_time(g_reps, [] { call_gradp(); corr_update(); });
+  const TimeStat s_corr = g_last_stat;
   // Poisson: the reference has no CPU solver (cuda.cu is its only implementation); this times the CPU
   // restatement of cuda.cu:403-548 (oracle/ref_spmat_cpu.cpp) over the COO the reference's own assembly
   // loop built during step 0, exactly g_kiter iterations per solve (secondary, clearly-labelled figure).
   cup2d_ref_force_iters = g_kiter;
-  double t_solve = median_time(std::max(1, g_reps / 2), [] {
+  double t_solve = median_time(g_reps, [] {
     std::fill(sim.mat->get_x().begin(), sim.mat->get_x().end(), 0.0);
     sim.mat->solveNoUpdate(0, 0, 0);
   });
@@ -325,10 +332,16 @@ void do_time() {
 #ifdef _OPENMP
   nthreads = omp_get_max_threads();
 #endif
-  printf("{\"L\": %d, \"N\": %d, \"cells\": %zu, \"threads\": %d, \"t_stage\": %.6e, \"t_rhs\": %.6e, "
-         "\"t_correct\": %.6e, \"kiter\": %d, \"t_poisson_iter\": %.6e, \"poisson_solver\": \"%s\"}\n",
-         g_L, g_N, n2, nthreads, t_stage, t_rhs, t_corr, iters_run, iters_run > 0 ? t_solve / iters_run : 0.0,
-         cup2d_ref_fixed_iters > 0 ? "reference cuda.cu (GPU)" : "CPU restatement of cuda.cu");
+  const TimeStat s_solve = g_last_stat;
+  const double it = iters_run > 0 ? 1.0 / iters_run : 0.0;
+  printf("{\"L\": %d, \"N\": %d, \"cells\": %zu, \"threads\": %d, \"reps\": %d, \"t_stage\": %.6e, \"t_rhs\": %.6e, "
+         "\"t_correct\": %.6e, \"kiter\": %d, \"t_poisson_iter\": %.6e, \"poisson_solver\": \"%s\", "
+         "\"min_med_max\": {\"t_stage\": [%.6e, %.6e, %.6e], \"t_rhs\": [%.6e, %.6e, %.6e], \"t_correct\": [%.6e, %.6e, %.6e], "
+         "\"t_poisson_iter\": [%.6e, %.6e, %.6e]}}\n",
+         g_L, g_N, n2, nthreads, g_reps, t_stage, t_rhs, t_corr, iters_run, t_solve * it,
+         cup2d_ref_fixed_iters > 0 ? "reference cuda.cu (GPU)" : "CPU restatement of cuda.cu",
+         s_stage.min, s_stage.med, s_stage.max, s_rhs.min, s_rhs.med, s_rhs.max, s_corr.min, s_corr.med, s_corr.max,
+         s_solve.min * it, s_solve.med * it, s_solve.max * it);
 }
 } // namespace
 

@@ -99,6 +99,47 @@ assert worst < 1e-12
     assert r.returncode == 0 and "WORST" in r.stdout, r.stdout[-1500:]
 
 
+def test_a_rank_that_never_arrives_fails_the_call_instead_of_hanging(emulated_library):
+    """bounded cross-GPU waits: rank 1 attaches but never issues its step; rank 0's first halo wait runs into the time limit
+    (CUP2D_COMM_TIMEOUT_MS), every later wait is skipped, and the call that synchronises reports CUP2D_ECOMM — the reference
+    aborts through MPI in that situation, an unbounded spin would hang the GPU"""
+    code = r'''
+import sys, threading, time, numpy as np
+sys.path.insert(0, %r)
+import cup2d_b200
+from cup2d_b200.lib import Cup2dError
+W, L = 2, 3
+N = 8 << L
+u = np.random.default_rng(1).uniform(-1, 1, (N, N))
+bar, slots, msg = threading.Barrier(W), [None] * W, []
+class Dist:
+    def __init__(self, rank): self.rank = rank
+    def all_gather_object(self, out, obj):
+        slots[self.rank] = obj; bar.wait()
+        out[:] = slots; bar.wait()
+    def barrier(self): bar.wait()
+def run(rank):
+    sim = cup2d_b200.Simulation(L, rank=rank, nranks=W)
+    sim.attach_peers(Dist(rank))
+    sim.upload("vel", u, u); sim.upload("pres", u)
+    if rank == 0:
+        t0 = time.time()
+        try:
+            sim.step(max_iter=4)
+            msg.append("no error")
+        except Cup2dError as e:
+            msg.append(str(e)); msg.append(time.time() - t0)
+    bar.wait()
+ths = [threading.Thread(target=run, args=(r,)) for r in range(W)]
+[t.start() for t in ths]; [t.join() for t in ths]
+print("MSG", msg)
+assert "timed out" in msg[0] and "-5" in msg[0] and msg[1] < 60
+''' % (ROOT,)
+    r = subprocess.run([sys.executable, "-c", code], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600,
+                       env=dict(os.environ, CUP2D_B200_LIB=emulated_library, CUP2D_COMM_TIMEOUT_MS="300"))
+    assert r.returncode == 0 and "MSG" in r.stdout, r.stdout[-1500:]
+
+
 @pytest.mark.skipif(os.environ.get("CUP2D_TEST_SLOW") != "1",
                     reason="35 s; test_multi_level_steps_on_three_ranks_emulated runs the same constructor inside whole time steps")
 def test_amr_poisson_matrix_distributed_over_three_ranks_emulated(emulated_library):

@@ -647,3 +647,68 @@ def test_degenerate_inputs_vs_oracle(case):
     assert np.abs(gu - ref["u"]).max() <= 1e-9 * scale and np.abs(gv - ref["v"]).max() <= 1e-9 * scale
     assert np.abs(gp - ref["p"]).max() <= 1e-8 * max(np.abs(ref["p"]).max(), 1e-300)
     sim.close()
+
+
+def _run_steps(L, nsteps, graph, seed=11, **kw):
+    """nsteps time steps through cup2d_step_enqueue (graph replay from the second step on) or, with graph=False, through
+    direct launches with the dt rule on the host; returns fields and the per-step (dt, iterations, residual)"""
+    N = 8 << L
+    u, v, p, *_ = make_fields(N, seed)
+    sim = cup2d_b200.Simulation(L, nu=1e-3, cfl=0.4)
+    sim.set_graph(graph)
+    sim.upload("vel", u, v)
+    sim.upload("pres", p)
+    info = []
+    for _ in range(nsteps):
+        if graph:
+            sim.step_enqueue(**kw)          # dt <= 0: dt control on the device, inside the graph
+            info.append(sim.step_result())
+        else:
+            _, dt = sim.compute_dt()        # the reference's order: umax -> host -> dt (main.cpp:6579-6595)
+            info.append(sim.step(dt=dt, **kw))
+    out = (sim.download("vel"), sim.download("pres"), info, sim.launch_count())
+    sim.close()
+    return out
+
+
+@pytest.mark.parametrize("L", [2, 5])
+def test_graph_replayed_steps_are_bitwise_the_directly_launched_steps(L):
+    """cup2d_step_enqueue replays one captured CUDA graph per buffer assignment (dt rule on the device, correction picking
+    the best iterate through the device-side Krylov state): five steps must reproduce, bit for bit, five steps launched
+    kernel by kernel with dt computed on the host — same dt, same fields"""
+    (gu, gv), gp, ginfo, _ = _run_steps(L, 5, True, max_iter=12, max_restarts=0)
+    (du, dv), dp, dinfo, _ = _run_steps(L, 5, False, max_iter=12, max_restarts=0)
+    assert [i[0] for i in ginfo] == [i[0] for i in dinfo], "dt computed on the device differs from the host rule"
+    assert [i[1] for i in ginfo] == [i[1] for i in dinfo] == [12] * 5
+    assert np.array_equal(gu, du) and np.array_equal(gv, dv) and np.array_equal(gp, dp)
+
+
+def test_graph_while_node_stops_where_the_host_polled_solve_stops():
+    """tolerance-driven solve inside the step graph: the Krylov loop is a WHILE node whose condition the device sets;
+    iteration counts, residuals and fields equal those of the host-polled solve (cuda.cu:535-541 stopping rule)"""
+    kw = dict(tol_abs=1e-7, tol_rel=0.0, max_restarts=100, max_iter=400)
+    (gu, gv), gp, ginfo, _ = _run_steps(4, 4, True, **kw)
+    (du, dv), dp, dinfo, _ = _run_steps(4, 4, False, **kw)
+    assert [i[1] for i in ginfo] == [i[1] for i in dinfo]
+    assert all(0 < i[1] < 400 and i[2] <= 1e-7 for i in ginfo), ginfo
+    assert np.array_equal(gu, du) and np.array_equal(gv, dv) and np.array_equal(gp, dp)
+
+
+def test_enqueued_steps_need_no_host_round_trip():
+    """several steps enqueued back to back, one result read at the end == the same steps read one by one"""
+    L, N = 4, 128
+    u, v, p, *_ = make_fields(N, 3)
+    outs = []
+    for batch in (True, False):
+        sim = cup2d_b200.Simulation(L, nu=1e-3, cfl=0.4)
+        sim.upload("vel", u, v)
+        sim.upload("pres", p)
+        for k in range(6):
+            sim.step_enqueue(max_iter=8, max_restarts=0)
+            if not batch:
+                sim.step_result()
+        last = sim.step_result()
+        outs.append((sim.download("vel"), sim.download("pres"), last))
+        sim.close()
+    assert outs[0][2] == outs[1][2]
+    assert np.array_equal(outs[0][0][0], outs[1][0][0]) and np.array_equal(outs[0][1], outs[1][1])
