@@ -895,7 +895,7 @@ static int step_body(cup2d_sim *s, bool dev_dt, int keep_udef, double tol_abs, d
       }
     }
   }
-  return launch_pressure_correct(s, 1.0, s->d_fac);
+  return launch_pressure_correct(s, 1.0, s->d_fac, true);
 }
 
 int cup2d_set_graph(cup2d_sim *s, int on) {

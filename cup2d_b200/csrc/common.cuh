@@ -77,12 +77,12 @@ __device__ __forceinline__ double fast_rcp_pos(double x) {
 // ---- cross-GPU plumbing over NVLink peer memory ---------------------------------------------------
 // One process per GPU; every rank maps every peer's mailbox (CUDA IPC).  Mailbox layout (u64 words):
 //   [0..8)     halo-pull READY epochs, one per source rank     [8..16) halo-pull DONE epochs
-//   [16 + (src*2 + parity)*8 ...]  reduction slot: flag(epoch), v0..v5          (16 .. 144)
-//   [144..152) PUSHED epochs, one per source rank (halo rows pushed by the producing Krylov kernel)
+//   [16 + (src*2 + parity)*16 ...]  reduction slot: up to 7 doubles, each as two words (32 data bits | epoch << 32)   (16 .. 272)
+//   [288..296) PUSHED epochs, one per source rank (halo rows pushed by the producing Krylov kernel)
 //   [496] reduction epoch   [497] halo-pull epoch   [498] push epoch   (this rank's counters; device-side, so that a
 //         step captured in a CUDA graph carries no host-supplied epoch)
 //   [499] error word: first failed wait of this rank (0 = none); the host reads it at its synchronisation points
-constexpr int MB_READY = 0, MB_DONE = 8, MB_RED = 16, MB_RED_STRIDE = 8, MB_PUSHED = 144, MB_EPOCH = 496,
+constexpr int MB_READY = 0, MB_DONE = 8, MB_RED = 16, MB_RED_STRIDE = 16, MB_PUSHED = 288, MB_EPOCH = 496,
               MB_HEPOCH = 497, MB_PEPOCH = 498, MB_ERR = 499, MB_WORDS = 512;
 constexpr int COMM_MAX_RANKS = 8;
 constexpr unsigned long long COMM_ERR_TIMEOUT = 1; // codes in the error word: (code << 32) | (what << 8) | peer
@@ -146,6 +146,26 @@ __device__ __forceinline__ bool wait_flag(const unsigned long long *flag, unsign
     }
   }
 }
+// Same bound for a "low-latency" word: 32 data bits in the low half, the epoch in the high half (the flag travels WITH
+// the data in one 8-byte store, which is single-copy atomic, so neither fences nor a separate flag round trip are needed)
+__device__ __forceinline__ unsigned long long wait_ll_word(const unsigned long long *w, unsigned ep32, const Comm &c, int peer) {
+  unsigned long long v = ld_relaxed_sys(w);
+  if ((unsigned)(v >> 32) == ep32) return v;
+  unsigned long long *err = c.mb[c.rank] + MB_ERR;
+  if (ld_relaxed_sys(err) != 0) return v;
+  const unsigned long long t0 = global_timer_ns();
+  for (unsigned n = 1;; n++) {
+    v = ld_relaxed_sys(w);
+    if ((unsigned)(v >> 32) == ep32) return v;
+    if ((n & 255u) == 0) {
+      if (ld_relaxed_sys(err) != 0) return v;
+      if (c.timeout_ns && global_timer_ns() - t0 > c.timeout_ns) {
+        st_relaxed_sys(err, (COMM_ERR_TIMEOUT << 32) | ((unsigned long long)CW_REDUCE << 8) | (unsigned long long)peer);
+        return v;
+      }
+    }
+  }
+}
 // All-reduce of NS sums + 1 max across ranks, executed by ONE WARP per rank (warp 0 of the last CTA of a
 // grid reduction; every lane enters with the same local totals).  Lane r < nranks writes this rank's
 // values into rank r's mailbox over NVLink (one peer per lane: one NVLink round trip in total, not one
@@ -153,7 +173,7 @@ __device__ __forceinline__ bool wait_flag(const unsigned long long *flag, unsign
 // in rank order with shuffles, so the result is bitwise identical on every lane and on every rank.
 template <int NS>
 __device__ __forceinline__ void peer_allreduce(const Comm &c, double (&tot)[NS], double &mx, int lane) {
-  static_assert(NS + 1 <= MB_RED_STRIDE - 1, "reduction slot too small");
+  static_assert(2 * (NS + 1) <= MB_RED_STRIDE, "reduction slot too small");
   if (c.nranks <= 1) return;
   unsigned long long *mine = c.mb[c.rank];
   unsigned long long ep = 0;
@@ -163,22 +183,30 @@ __device__ __forceinline__ void peer_allreduce(const Comm &c, double (&tot)[NS],
   }
   ep = __shfl_sync(0xffffffffu, ep, 0);
   const int par = (int)(ep & 1);
+  const unsigned ep32 = (unsigned)ep; // never 0 within 2^32 - 1 reductions of a context (the mailbox starts zeroed)
+  // Every value goes out as two 8-byte words, each carrying 32 bits of the double and the epoch: a word is valid the
+  // moment its epoch matches, whatever order the stores arrive in.  A slot of parity p is rewritten two reductions
+  // later, which the writer can only reach after the reader contributed to the reduction in between, i.e. after it
+  // finished reading.
   if (lane < c.nranks) {
     unsigned long long *dst = c.mb[lane] + MB_RED + (c.rank * 2 + par) * MB_RED_STRIDE;
 #pragma unroll
-    for (int k = 0; k < NS; k++) st_relaxed_sys(dst + 1 + k, (unsigned long long)__double_as_longlong(tot[k]));
-    st_relaxed_sys(dst + 1 + NS, (unsigned long long)__double_as_longlong(mx));
-    __threadfence_system();
-    st_release_sys(dst, ep);
+    for (int k = 0; k <= NS; k++) {
+      const unsigned long long b = (unsigned long long)__double_as_longlong(k < NS ? tot[k] : mx);
+      st_relaxed_sys(dst + 2 * k, (b & 0xffffffffull) | ((unsigned long long)ep32 << 32));
+      st_relaxed_sys(dst + 2 * k + 1, (b >> 32) | ((unsigned long long)ep32 << 32));
+    }
   }
   double v[NS + 1];
 #pragma unroll
   for (int k = 0; k <= NS; k++) v[k] = 0.0;
   if (lane < c.nranks) {
     const unsigned long long *src = mine + MB_RED + (lane * 2 + par) * MB_RED_STRIDE;
-    wait_flag(src, ep, c, CW_REDUCE, lane);
 #pragma unroll
-    for (int k = 0; k <= NS; k++) v[k] = __longlong_as_double((long long)ld_relaxed_sys(src + 1 + k));
+    for (int k = 0; k <= NS; k++) {
+      const unsigned long long lo = wait_ll_word(src + 2 * k, ep32, c, lane), hi = wait_ll_word(src + 2 * k + 1, ep32, c, lane);
+      v[k] = __longlong_as_double((long long)((lo & 0xffffffffull) | (hi << 32)));
+    }
   }
   double acc[NS];
 #pragma unroll

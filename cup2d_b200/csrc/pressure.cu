@@ -283,11 +283,13 @@ pressure_correct_kernel(const double *x0, const double *x1, const double *x2, co
   }
 }
 
-int launch_pressure_correct(cup2d_sim *s, double dt, const StepFactors *dev) {
+// pold_halo_current: the halo slots of pold are still those the right-hand-side kernel's refresh brought (inside one step
+// nothing writes pold in between), so only the solution's halo is pulled
+int launch_pressure_correct(cup2d_sim *s, double dt, const StepFactors *dev, bool pold_halo_current) {
   if (s->nranks > 1) {
     int rc;
     if ((rc = halo_exchange_xopt(s))) return rc;
-    if ((rc = halo_exchange_ptr(s, s->f[CUP2D_POLD], 1, CUP2D_POLD))) return rc;
+    if (!pold_halo_current && (rc = halo_exchange_ptr(s, s->f[CUP2D_POLD], 1, CUP2D_POLD))) return rc;
   }
   const int nrows = (int)s->nloc * 8;
   const int grid = min((nrows + NT - 1) / NT, s->num_sms * 8);

@@ -186,7 +186,7 @@ int launch_umax(cup2d_sim *s, double *umax_out);
 int launch_umax_async(cup2d_sim *s);                      // umax -> d_scal[0], no host synchronisation
 int launch_step_factors(cup2d_sim *s, double dt_host);    // d_fac from dt_host (> 0) or from d_scal[0] (the dt rule on the device)
 int launch_pressure_rhs(cup2d_sim *s, double dt, bool has_udef, const StepFactors *dev = nullptr, bool zero_pres_halo = false);
-int launch_pressure_correct(cup2d_sim *s, double dt, const StepFactors *dev = nullptr);
+int launch_pressure_correct(cup2d_sim *s, double dt, const StepFactors *dev = nullptr, bool pold_halo_current = false);
 int launch_adapt_tags(cup2d_sim *s, double rtol, int chi_cells, double *linf_host);
 int dump_fields(cup2d_sim *s, double time, const char *path);
 int ensure_block_ij(cup2d_sim *s);
