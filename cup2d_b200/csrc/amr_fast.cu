@@ -106,7 +106,7 @@ amr_advect_fast_kernel(const double *__restrict__ vel, double *__restrict__ out,
   const bool live = k < nb;
   double *su = base + q * AF_BLK, *sv = su + AF_PLANE, *Ru = sv + AF_PLANE, *Rv = Ru + 8 * AF_RS;
   const double h = live ? hb[k] : 1.0;
-  const double dfac = nu * dt, afac = -dt * h; // main.cpp:5446-5447
+  const double dfac = nu * dt, afac3 = -dt * h * (1.0 / 3.0); // main.cpp:5446-5447; weno_line delivers 3 x the differences
   // ---- face fluxes of the blocks with a coarse-fine face: lane = (face q', position r) of block qq ----
   for (int qq = 0; qq < AF_BPW; qq++) {
     const int kk = b0 + qq;
@@ -126,8 +126,8 @@ amr_advect_fast_kernel(const double *__restrict__ vel, double *__restrict__ out,
   // (lanes of a partial last warp keep running on their unused planes and simply do not store)
   // ---- x pass: lane = row r of block q ----
   weno_line(su + (r + 3) * AF_PS, sv + (r + 3) * AF_PS, 1,
-            [&](int c, double U, double, double du, double dv, double D2u, double D2v) {
-              const double aU = afac * U;
+            [&](int c, double U, double, double du, double dv, double D2u, double D2v) { // du, dv: 3 x the differences
+              const double aU = afac3 * U;
               Ru[r * AF_RS + c] = fma(aU, du, dfac * D2u);
               Rv[r * AF_RS + c] = fma(aU, dv, dfac * D2v);
             });
@@ -135,7 +135,7 @@ amr_advect_fast_kernel(const double *__restrict__ vel, double *__restrict__ out,
   // ---- y pass: lane = column r of block q; advecting component is v ----
   double2 *outp = reinterpret_cast<double2 *>(out) + (size_t)(live ? k : 0) * 64 + r;
   weno_line(sv + (r + 3), su + (r + 3), AF_PS, [&](int c, double V, double, double dv, double du, double D2v, double D2u) {
-    const double aV = afac * V;
+    const double aV = afac3 * V;
     double2 o;
     o.x = Ru[c * AF_RS + r] + fma(aV, du, dfac * D2u);
     o.y = Rv[c * AF_RS + r] + fma(aV, dv, dfac * D2v);

@@ -576,7 +576,7 @@ void cup2d_destroy(cup2d_sim *s) {
   for (auto p : s->kx) cudaFree(p);
   cudaFree(s->kr); cudaFree(s->krhat); cudaFree(s->kp); cudaFree(s->knu); cudaFree(s->kt); cudaFree(s->kz); cudaFree(s->kzr);
   cudaFree(s->d_nbr); cudaFree(s->d_tiles); cudaFree(s->d_tile_org); cudaFree(s->d_halo_src); shapes_free(s);
-  cudaFree(s->d_adv_lut); cudaFree(s->d_linf); cudaFree(s->d_ij);
+  cudaFree(s->d_linf); cudaFree(s->d_ij);
   cudaFree(s->d_state); cudaFree(s->d_partials); cudaFree(s->d_counter); cudaFree(s->d_scal);
   cudaFree(s->d_mailbox);
   cudaFree(s->d_halo_gid); cudaFree(s->d_push_first); cudaFree(s->d_push_ent);

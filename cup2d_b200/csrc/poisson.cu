@@ -154,7 +154,10 @@ __device__ __forceinline__ void push_rows(const PushView &pv, int slot, int y, c
 #pragma unroll
     for (int k = 0; k < 4; k++) dst[k] = make_double2(v[2 * k], v[2 * k + 1]);
   }
-  __threadfence_system();
+  // no fence here: push_finish orders these stores before the flag for the whole CTA (CTA barrier, then ONE system-scope
+  // fence by the thread that takes part in the release chain — fences are cumulative over what the barrier made visible
+  // to that thread, the same pattern a cooperative grid barrier relies on).  A fence per pushing lane stalled every
+  // perimeter warp for an NVLink round trip.
 }
 // end of a pushing kernel: the CTA that finishes last publishes the new push epoch to the destination ranks
 __device__ __forceinline__ void push_finish(const PushView &pv, const Comm &comm, unsigned int *counter) {

@@ -92,7 +92,6 @@ struct cup2d_sim {
   int ntiles = 0;
   double *d_linf = nullptr;            // per-block L-inf of the tagging field (cup2d_adapt_tags)
   int *d_ij = nullptr;                 // (i,j) of the local blocks (cup2d_dump)
-  unsigned *d_adv_lut = nullptr;       // repack table of the advect kernel (interior tiles)
   // fields (dim*64*nslots doubles each)
   double *f[CUP2D_NFIELDS] = {};
   // Krylov vectors (64*nslots)

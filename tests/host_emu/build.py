@@ -87,6 +87,8 @@ ASM_REWRITES = [  # (regex over the source text, replacement): the PTX of common
     (r'asm volatile\("\{\\n".*?: "memory"\);', "(void)bar; (void)parity; /* copies are synchronous here */"),
     (r'asm volatile\("cp\.async\.bulk\.shared.*?: "memory"\);', "emu_bulk_copy(smem_dst, gmem_src, bytes); (void)bar;"),
     (r'asm\("rcp\.approx\.ftz\.f64 %0, %1;" : "=d"\(r\) : "d"\(x\)\);', "r = (double)(1.0f / (float)x);"),
+    (r'asm volatile\("cp\.async\.cg\.shared\.global.*?: "memory"\);', "emu_bulk_copy(smem_dst, gmem_src, 16);"),
+    (r'asm volatile\("cp\.async\.wait_all;" ::: "memory"\);', ";"),
     (r'asm volatile\("st\.release\.sys.*?: "memory"\);', "__threadfence(); *(volatile unsigned long long *)p = v;"),
     (r'asm volatile\("st\.relaxed\.sys.*?: "memory"\);', "*(volatile unsigned long long *)p = v;"),
     (r'asm volatile\("ld\.acquire\.sys.*?: "memory"\);', "v = *(volatile const unsigned long long *)p; __threadfence();"),

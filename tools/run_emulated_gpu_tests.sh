@@ -5,4 +5,4 @@ set -e
 cd "$(dirname "$0")/.."
 LIB=$(python -c "import sys; sys.path.insert(0, 'tests/host_emu'); import build; print(build.build_full())")
 CUP2D_B200_LIB=$LIB python -m pytest tests/test_gpu_parity.py tests/test_gpu_amr.py -m gpu -q \
-  -k "not 1024 and not large_grid and not reference_driver and not reference_amr and not two_ranks and not multi_chunk" "$@"
+  -k "not 1024 and not tolerance_driven and not large_grid and not reference_driver and not reference_amr and not two_ranks and not multi_chunk" "$@"
