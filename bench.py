@@ -238,6 +238,10 @@ def multi_gpu_parity(cup2d_b200, np, torch, dist, rank, world, local_rank, K):
     return out[0]
 
 
+# FP64 instructions the advect stage executes per cell (DFMA + DMUL + DADD of the ncu instruction mix; round 1: 189)
+ADVECT_FP64_PER_CELL = 152.4
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -502,11 +506,11 @@ def main():
         # the north-star kernel: HBM fraction and the FP64-pipe bound it actually sits under
         gcell = cells_loc / (adv["ms_per_launch"] * 1e-3) / 1e9
         sm_mhz = (clocks or {}).get("sm_mhz") or 1920.0
-        fp64_floor_ms = cells_loc * 191.0 / 32.0 / (148 * 2 * sm_mhz * 1e6) * 1e3   # 191 FP64 instr/cell (ncu), 2 warp-instr/clk/SM
+        fp64_floor_ms = cells_loc * ADVECT_FP64_PER_CELL / 32.0 / (148 * 2 * sm_mhz * 1e6) * 1e3   # 2 FP64 warp-instr/clk/SM
         extra["advect_stage"] = {"Gcell_per_s": gcell, "achieved_GBs": adv["achieved_GBs"], "frac_hbm": adv["frac_hbm"],
                                  "ms_per_launch": adv["ms_per_launch"], "alg_bytes_per_cell": 48.0,
                                  "fp64_floor_ms": fp64_floor_ms, "frac_fp64_floor": fp64_floor_ms / adv["ms_per_launch"],
-                                 "note": "bound by the FP64 pipe, not HBM: 191 FP64 instr/cell (ncu) at 64 lanes/clk/SM; see DESIGN.md 3.1"}
+                                 "note": f"bound by the FP64 pipe, not HBM: {ADVECT_FP64_PER_CELL:g} FP64 instr/cell (ncu, profiles/r02g_advect_ncu.md) at 64 lanes/clk/SM; see DESIGN.md 3.1"}
         # one full RK2 step = the two fused stages (vold = vel is a pointer swap, not a copy)
         try:
             rk2_ms = adv["ms_per_launch"] * adv["launches_per_step"]

@@ -27,7 +27,17 @@ namespace cup2d {
 #define CUP2D_ADV_CTAS 4 // resident CTAs per SM the register allocation is bounded for (shared memory allows 5)
 #endif
 #ifndef CUP2D_ADV_LDGSTS
-#define CUP2D_ADV_LDGSTS 0 // 1: the tile is filled by 16-byte cp.async (LDGSTS) of all threads instead of per-row bulk copies
+// 1: the tile is filled by 16-byte cp.async (SASS LDGSTS) issued by all threads, 13 per thread;  0: by per-row bulk copies
+// (SASS UBLKCP + mbarrier).  A bulk copy issued by a divergent thread costs ~8 warp instructions (ELECT/R2UR loop over the
+// lanes) and a tile needs 216 of them: 0.914 ms per stage against 0.846 ms with cp.async at 8192^2 (profiles/r02e_variants.jsonl).
+#define CUP2D_ADV_LDGSTS 1
+#endif
+
+#ifndef CUP2D_ADV_SPECIALIZE
+#define CUP2D_ADV_SPECIALIZE 1 // 1: the x and the y pass get their own copy of the line code; 0: one copy with run-time strides
+#endif
+#ifndef CUP2D_ADV_FASTPATH
+#define CUP2D_ADV_FASTPATH 1 // 0: every line goes through the general core (measurement variant)
 #endif
 
 constexpr int TC = 32;          // tile cells per side
@@ -177,23 +187,25 @@ advect_stage_kernel(const double *__restrict__ in, const double *__restrict__ ol
   // y pass: lane = column, thread = 8 consecutive cells of one column = one block column (v advects)
   // 16-byte bank groups: P row stride 39 = 7 (mod 8), R row stride 33 = 1 (mod 8): the 8 rows of a quarter warp never collide.
   const int xrow = 8 * warp + (lane & 7), xseg = lane >> 3;
-#pragma unroll 1
-  for (int pass = 0; pass < 2; pass++) {
+  auto run_pass = [&](const int pass) {
     const double2 *q = pass == 0 ? P + (xrow + GH) * PS + 8 * xseg : P + (8 * ys) * PS + (yx + GH);
     const int es = pass == 0 ? 1 : PS;
     double2 *r = pass == 0 ? R + xrow * RS + 8 * xseg : R + (8 * ys) * RS + yx;
     const int rs = pass == 0 ? 1 : RS;
-    weno_line_core([&](int k, double &x, double &y) {
-      const double2 v = q[k * es];
-      x = v.x;
-      y = v.y;
-    }, pass != 0, [&](int c, double du3, double dv3, double Eu, double Ev) {
-      const double2 cell = q[(c + 3) * es];
-      const double aU = afac3 * (pass == 0 ? cell.x : cell.y);
+    // which way the eight cells of this line are advected: sign of the advecting component (high words only)
+    unsigned pos = 0;
+    {
+      const int *qh = reinterpret_cast<const int *>(q) + 2 * pass + 1;
+#pragma unroll
+      for (int c = 0; c < 8; c++) pos |= qh[4 * (c + 3) * es] >= 0 ? (8u << c) : 0u;
+    }
+    // One result per cell, in the order the line core delivers them (c = 0..7 along the direction of traversal):
+    //   x pass: partial sums to R;  y pass: + partial sums, RK update, store.  ci = cell index along the line.
+    auto finish = [&](const int ci, const double2 cell, const double2 oldc, const double aU, double du3, double dv3, double Eu, double Ev) {
       if (pass == 0) { // afac*u*dudx + dfac*(u_E + u_W - 2u)
-        r[c * rs] = make_double2(fma(aU, du3, dfac * Eu), fma(aU, dv3, dfac * Ev));
+        r[ci * rs] = make_double2(fma(aU, du3, dfac * Eu), fma(aU, dv3, dfac * Ev));
       } else {
-        const double2 p = r[c * rs];
+        const double2 p = r[ci * rs];
         const double tu = fma(aU, du3, fma(dfac, Eu, p.x));
         const double tv = fma(aU, dv3, fma(dfac, Ev, p.y));
         if (store) {
@@ -205,15 +217,50 @@ advect_stage_kernel(const double *__restrict__ in, const double *__restrict__ ol
             o.x = fma(ofac, tu, cell.x);
             o.y = fma(ofac, tv, cell.y);
           } else {
-            o.x = fma(ofac, tu, oldv[c].x); // V = Vold + coef*tmpV/h^2, main.cpp:6618-6626
-            o.y = fma(ofac, tv, oldv[c].y);
+            o.x = fma(ofac, tu, oldc.x); // V = Vold + coef*tmpV/h^2, main.cpp:6618-6626
+            o.y = fma(ofac, tv, oldc.y);
           }
-          outp[c * 8] = o;
+          outp[ci * 8] = o;
         }
       }
-    });
+    };
+    if (CUP2D_ADV_FASTPATH && (pos == 0x7f8u || pos == 0u)) {
+      // the whole line is advected one way (the rule away from stagnation lines): straight-line upwind core; from the
+      // right = the mirrored line (weno.cuh): window index k -> 13-k, cell c -> 7-c, differences negated
+      const bool rev = pos == 0u;
+      const double2 *qq = rev ? q + 13 * es : q;
+      const int ee = rev ? -es : es;
+      const double af = rev ? -afac3 : afac3;
+      weno_line_upwind([&](int k, double &x, double &y) {
+        const double2 v = qq[k * ee];
+        x = v.x;
+        y = v.y;
+      }, [&](int c, double du3, double dv3, double Eu, double Ev) {
+        const double2 cell = qq[(c + 3) * ee];
+        const int ci = rev ? 7 - c : c;
+        // `old` sits in registers in cell order: picked by a select, not by a run-time register index
+        const double2 oldc = MODE == 2 ? (rev ? oldv[7 - c] : oldv[c]) : cell;
+        finish(ci, cell, oldc, af * (pass == 0 ? cell.x : cell.y), du3, dv3, Eu, Ev);
+      });
+    } else {
+      weno_line_core([&](int k, double &x, double &y) {
+        const double2 v = q[k * es];
+        x = v.x;
+        y = v.y;
+      }, pos, [&](int c, double du3, double dv3, double Eu, double Ev) {
+        const double2 cell = q[(c + 3) * es];
+        finish(c, cell, MODE == 2 ? oldv[c] : cell, afac3 * (pass == 0 ? cell.x : cell.y), du3, dv3, Eu, Ev);
+      });
+    }
     __syncwarp(); // the y pass of a warp reads the R rows its own x pass wrote
-  }
+  };
+#if CUP2D_ADV_SPECIALIZE
+  run_pass(0); // two copies of the line code, each with its pass folded in (immediate shared-memory offsets, no selects)
+  run_pass(1);
+#else
+#pragma unroll 1
+  for (int pass = 0; pass < 2; pass++) run_pass(pass); // one copy, run-time strides
+#endif
 }
 
 typedef void (*adv_fn)(const double *, const double *, double *, const int *, const int *, int,

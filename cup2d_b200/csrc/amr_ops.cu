@@ -652,11 +652,20 @@ int cup2d_amr_pressure_correct(cup2d_amr *a, double dt) {
  * fillcases travel the same way, stored per block in a field that is free at that point; dt and the pressure means are
  * all-reduced by the in-kernel peer all-reduce.  Fast kernels only.  Then cup2d_amr_peer_export / _attach; field upload and
  * download move this rank's blocks. */
+// rank_begin[0..nranks] must be strictly increasing from 0 to nblocks (every rank owns blocks), and a field must keep
+// its cell indices in 31 bits: checked before anything indexes by these ranges
+static bool valid_partition(int64_t nblocks, int32_t nranks, const int64_t *rank_begin) {
+  if (!rank_begin || nranks < 1 || nranks > MAX_RANKS || nblocks <= 0 || nblocks * 64 >= (1LL << 31)) return false;
+  if (rank_begin[0] != 0 || rank_begin[nranks] != nblocks) return false;
+  for (int r = 0; r < nranks; r++)
+    if (rank_begin[r + 1] <= rank_begin[r]) return false;
+  return true;
+}
+
 int cup2d_amr_create_ranks(int64_t nblocks, const int32_t *level_ij, int32_t bpdx, int32_t bpdy, double h0, double nu, int32_t rank,
                            int32_t nranks, const int64_t *rank_begin, int32_t device, cup2d_amr **out) {
-  if (!out || !level_ij || !rank_begin || nblocks <= 0 || !(h0 > 0) || nranks < 1 || rank < 0 || rank >= nranks ||
-      rank_begin[0] != 0 || rank_begin[nranks] != nblocks) {
-    set_error("cup2d_amr_create_ranks: bad arguments");
+  if (!out || !level_ij || !(h0 > 0) || rank < 0 || rank >= nranks || !valid_partition(nblocks, nranks, rank_begin)) {
+    set_error("cup2d_amr_create_ranks: bad arguments (rank_begin must increase strictly from 0 to nblocks, 1..8 ranks, fewer than 2^31 cells)");
     return CUP2D_EINVAL;
   }
   cup2d_amr_plan *plan = nullptr;
@@ -760,8 +769,8 @@ int cup2d_amr_create_ranks(int64_t nblocks, const int32_t *level_ij, int32_t bpd
  * list.  Then cup2d_amr_peer_export / cup2d_amr_peer_attach like the cup2d_peer_* pair. */
 int cup2d_amr_set_ranks(cup2d_amr *a, int32_t rank, int32_t nranks, const int64_t *rank_begin) {
   CHECK_AMR(a);
-  if (a->poisson || !rank_begin || nranks < 1 || rank < 0 || rank >= nranks || rank_begin[0] != 0 || rank_begin[nranks] != a->nb) {
-    set_error("cup2d_amr_set_ranks: bad arguments (or called after the first solve)");
+  if (a->poisson || rank < 0 || rank >= nranks || !valid_partition(a->nb, nranks, rank_begin)) {
+    set_error("cup2d_amr_set_ranks: bad arguments (rank_begin must increase strictly from 0 to the block count) or called after the first solve");
     return CUP2D_EINVAL;
   }
   CUP2D_CUDA(cudaSetDevice(a->device));

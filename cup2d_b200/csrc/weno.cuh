@@ -107,36 +107,68 @@ __device__ __forceinline__ void line_advance(LineState &s, double qn, double T3,
   s.T1 = T3;
 }
 
-// The line core.  ld(k, x, y): both components at window index k (0..13; cell c is index c+3), called once per index;
-// sel: which of them ADVECTS (false: x, true: y) — its sign picks the upwind side of both components.
-// emit(c, dx3, dy3, Ex, Ey) is called once per cell c = 0..7 with 3 x the undivided upwind differences (reference
-// `derivative`, main.cpp:202-208) of the two components and their second differences (diffusion term).  The two
-// components are treated alike — the line direction and which of them advects only enter through ld and sel — so one copy
-// of this code serves both passes of a kernel.
-// The sign is taken from the high word as the values stream in (no second pass over the line, no FP64 pipe): +0 counts as
-// positive where the reference's `U > 0` sends it to the other side, which only changes a term that is multiplied by U = 0.
+// ---- the line cores -----------------------------------------------------------------------------------------------------
+// ld(k, x, y): both components at window index k (0..13; cell c is index c+3).  emit(c, dx3, dy3, Ex, Ey) is called once
+// per cell c = 0..7 with 3 x the undivided upwind differences (reference `derivative`, main.cpp:202-208) of the two
+// components and their second differences (diffusion term).  The two components are treated alike: the line direction and
+// which of them advects enter only through ld and the sign bits, so one copy of this code can serve both passes.
+//
+// weno_line_upwind: all eight cells are advected from the left (index 0 side).  Straight-line code — nine left-biased
+// fluxes, no branch, nothing evaluated that is not used — which the scheduler can interleave across window positions.
+// A line whose eight cells are all advected from the RIGHT is the same computation on the mirrored line: the caller hands
+// in ld(k) = q[13-k], writes cell 7-c where emit says c, and negates the differences (flux^-(c+1/2) of q is
+// flux^+(c'-1/2) of the mirrored line, c' = 7-c, so D^-(c) = -D'^+(c'); second differences are symmetric).
 template <class Ld, class Emit>
-__device__ __forceinline__ void weno_line_core(Ld ld, const bool sel, Emit emit) {
-  unsigned pos = 0; // bit k <-> advecting component positive at window index k (2..12)
-  auto lds = [&](int k, double &x, double &y) {
-    ld(k, x, y);
-    if (k >= 2 && k <= 12) pos |= (sel ? __double2hiint(y) : __double2hiint(x)) >= 0 ? (1u << k) : 0u;
-  };
+__device__ __forceinline__ void weno_line_upwind(Ld ld, Emit emit) {
   LineState A, B;
   {
     double x0, x1, x2, x3, x4, y0, y1, y2, y3, y4;
-    lds(0, x0, y0);
-    lds(1, x1, y1);
-    lds(2, x2, y2);
-    lds(3, x3, y3);
-    lds(4, x4, y4);
+    ld(0, x0, y0);
+    ld(1, x1, y1);
+    ld(2, x2, y2);
+    ld(3, x3, y3);
+    ld(4, x4, y4);
+    line_init(A, x0, x1, x2, x3, x4);
+    line_init(B, y0, y1, y2, y3, y4);
+  }
+#pragma unroll
+  for (int w = 2; w <= 10; ++w) {
+    if (w >= 4) // finalize cell c = w-4 (window index w-1): flux(w-1) - flux(w-2) + D[w-2]
+      emit(w - 4, fma(3.0, A.dm2, A.rP1 - A.rP2), fma(3.0, B.dm2, B.rP1 - B.rP2), A.Em1, B.Em1);
+    const double T3a = A.Ep1 - A.E0, T3b = B.Ep1 - B.E0;
+    double a1, a2, a3, b1, b2, b3;
+    line_betas(A, a1, a2, a3);
+    line_betas(B, b1, b2, b3);
+    const double rPa = ratio_plus(A, a1, a2, a3, a1 * A.T1, a3 * T3a);
+    const double rPb = ratio_plus(B, b1, b2, b3, b1 * B.T1, b3 * T3b);
+    double qna = 0.0, qnb = 0.0;
+    if (w < 10) ld(w + 3, qna, qnb); // index 13 only enters right-biased fluxes
+    line_advance(A, qna, T3a, rPa, 0.0);
+    line_advance(B, qnb, T3b, rPb, 0.0);
+  }
+  emit(7, fma(3.0, A.dm2, A.rP1 - A.rP2), fma(3.0, B.dm2, B.rP1 - B.rP2), A.Em1, B.Em1); // window position 11
+}
+
+// weno_line_core: any sign pattern.  pos: bit k set <-> the advecting component is positive at window index k; only the
+// bits of the eight cells (k = 3..10) are looked at.  (+0 may be reported either way: the term it selects is multiplied
+// by U = 0; the reference's `U > 0` sends it to the right-biased side.)
+template <class Ld, class Emit>
+__device__ __forceinline__ void weno_line_core(Ld ld, const unsigned pos, Emit emit) {
+  LineState A, B;
+  {
+    double x0, x1, x2, x3, x4, y0, y1, y2, y3, y4;
+    ld(0, x0, y0);
+    ld(1, x1, y1);
+    ld(2, x2, y2);
+    ld(3, x3, y3);
+    ld(4, x4, y4);
     line_init(A, x0, x1, x2, x3, x4);
     line_init(B, y0, y1, y2, y3, y4);
   }
 #pragma unroll
   for (int w = 2; w <= 11; ++w) {
     const bool vc = (unsigned)(w - 3) < 8u, vn = (unsigned)(w - 2) < 8u, vp = (unsigned)(w - 4) < 8u;
-    const unsigned pw = pos >> (w - 1); // bit 0: cell w-1, bit 1: cell w, bit 2: cell w+1 (index w+1 was loaded at position w-2)
+    const unsigned pw = pos >> (w - 1); // bit 0: cell w-1, bit 1: cell w, bit 2: cell w+1
     const bool posp = pw & 1u;
     // flux families needed at this window position (masks are compile-time after unrolling)
     const bool needP = (pw & ((vc ? 2u : 0u) | (vn ? 4u : 0u))) != 0u;
@@ -168,7 +200,7 @@ __device__ __forceinline__ void weno_line_core(Ld ld, const bool sel, Emit emit)
     }
     if (w < 11) {
       double qna, qnb;
-      lds(w + 3, qna, qnb);
+      ld(w + 3, qna, qnb);
       line_advance(A, qna, T3a, rPa, rMa);
       line_advance(B, qnb, T3b, rPb, rMb);
     }
@@ -176,14 +208,30 @@ __device__ __forceinline__ void weno_line_core(Ld ld, const bool sel, Emit emit)
 }
 
 // Separate component planes (amr_fast.cu): qa = advecting component, qb = the other one, element stride es.
-// emit(c, Ua, Ub, da3, db3, D2a, D2b): cell values, 3 x the undivided upwind differences, second differences.
+// emit(c, Ua, Ub, da3, db3, D2a, D2b): cell values, 3 x the undivided upwind differences, second differences; c may be a
+// run-time value (lines advected from the right are walked backwards).
 template <class Emit>
 __device__ __forceinline__ void weno_line(const double *__restrict__ qa, const double *__restrict__ qb,
                                           const int es, Emit emit) {
-  weno_line_core([&](int k, double &x, double &y) { x = qa[k * es]; y = qb[k * es]; }, false,
-                 [&](int c, double da3, double db3, double Ea, double Eb) {
-                   emit(c, qa[(c + 3) * es], qb[(c + 3) * es], da3, db3, Ea, Eb);
-                 });
+  unsigned pos = 0;
+#pragma unroll
+  for (int k = 3; k <= 10; k++) pos |= __double2hiint(qa[k * es]) >= 0 ? (1u << k) : 0u;
+  if (pos == 0x7f8u || pos == 0u) {
+    const bool rev = pos == 0u;
+    const double *pa = rev ? qa + 13 * es : qa, *pb = rev ? qb + 13 * es : qb;
+    const int ee = rev ? -es : es;
+    const double sg = rev ? -1.0 : 1.0;
+    weno_line_upwind([&](int k, double &x, double &y) { x = pa[k * ee]; y = pb[k * ee]; },
+                     [&](int c, double da3, double db3, double Ea, double Eb) {
+                       // U, da3 enter the callers only through the product U * d3: the mirror's sign goes to U's copy
+                       emit(rev ? 7 - c : c, pa[(c + 3) * ee], pb[(c + 3) * ee], sg * da3, sg * db3, Ea, Eb);
+                     });
+  } else {
+    weno_line_core([&](int k, double &x, double &y) { x = qa[k * es]; y = qb[k * es]; }, pos,
+                   [&](int c, double da3, double db3, double Ea, double Eb) {
+                     emit(c, qa[(c + 3) * es], qb[(c + 3) * es], da3, db3, Ea, Eb);
+                   });
+  }
 }
 
 } // namespace cup2d

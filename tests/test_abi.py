@@ -105,3 +105,9 @@ def test_multi_rank_constructors_reject_bad_partitions_before_touching_a_device(
         rb_a = np.array(rb, dtype=np.int64)
         rc = lib.cup2d_amr_create_ranks(1, blocks.ctypes.data_as(I32), 1, 1, 0.125, 1e-3, rank, nranks, rb_a.ctypes.data_as(I64), 0, C.byref(a))
         assert rc != 0 and not a.value, (rank, nranks, rb)
+    # a partition that is not increasing ({0, 100, 50} with 50 blocks) is refused before any table is indexed by it
+    four = np.array([[1, i, j] for j in range(2) for i in range(2)], dtype=np.int32)
+    for nb, rank, nranks, rb in ((4, 0, 2, [0, 8, 4]), (4, 1, 2, [0, 8, 4]), (4, 0, 3, [0, 2, 2, 4])):
+        rb_a = np.array(rb, dtype=np.int64)
+        rc = lib.cup2d_amr_create_ranks(nb, four.ctypes.data_as(I32), 1, 1, 0.125, 1e-3, rank, nranks, rb_a.ctypes.data_as(I64), 0, C.byref(a))
+        assert rc == -1 and lib.cup2d_last_error() and not a.value, (rank, nranks, rb)

@@ -12,6 +12,6 @@ build() { # tag, defines
   echo "$1: $(grep -c 'bytes spill' advect_$1.ptxas.log) kernels, max regs $(grep -o 'Used [0-9]* registers' advect_$1.ptxas.log | sort -k2 -n | tail -1)"
   rm -f advect_v_$1.o
 }
-build ctas5 "-DCUP2D_ADV_CTAS=5"
-build ldgsts "-DCUP2D_ADV_LDGSTS=1"
-build ldgsts5 "-DCUP2D_ADV_LDGSTS=1 -DCUP2D_ADV_CTAS=5"
+build fast_onecopy "-DCUP2D_ADV_SPECIALIZE=0"
+build nofast "-DCUP2D_ADV_FASTPATH=0"
+build nofast_onecopy "-DCUP2D_ADV_FASTPATH=0 -DCUP2D_ADV_SPECIALIZE=0"
