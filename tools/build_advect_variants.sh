@@ -12,6 +12,9 @@ build() { # tag, defines
   echo "$1: $(grep -c 'bytes spill' advect_$1.ptxas.log) kernels, max regs $(grep -o 'Used [0-9]* registers' advect_$1.ptxas.log | sort -k2 -n | tail -1)"
   rm -f advect_v_$1.o
 }
-build fast_onecopy "-DCUP2D_ADV_SPECIALIZE=0"
-build nofast "-DCUP2D_ADV_FASTPATH=0"
-build nofast_onecopy "-DCUP2D_ADV_FASTPATH=0 -DCUP2D_ADV_SPECIALIZE=0"
+build tma "-DCUP2D_ADV_LDGSTS=0"
+# the Krylov stencil kernels without the in-chunk neighbour reads (rows.cuh)
+$NV -DCUP2D_ROWS_INCHUNK=0 -c poisson.cu -o poisson_v_noinchunk.o 2> poisson_noinchunk.ptxas.log
+$NV -DCUP2D_ROWS_INCHUNK=0 -c pressure.cu -o pressure_v_noinchunk.o 2> pressure_noinchunk.ptxas.log
+nvcc -gencode arch=compute_100a,code=sm_100a -shared -o ../libcup2d_b200_noinchunk.so api.o advect.o pressure_v_noinchunk.o poisson_v_noinchunk.o halo.o regrid.o penalize.o amr_ops.o amr_fast.o amr_penalize.o amr_plan.o -ccbin /usr/bin/g++
+rm -f poisson_v_noinchunk.o pressure_v_noinchunk.o
