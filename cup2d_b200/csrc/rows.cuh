@@ -16,10 +16,6 @@
 
 namespace cup2d {
 
-#ifndef CUP2D_ROWS_INCHUNK
-#define CUP2D_ROWS_INCHUNK 1 // 0: neighbour blocks are always read from global memory (measurement variant)
-#endif
-
 constexpr int RS2 = 9;                     // vector row stride in double2 (8 used + 1 pad = 144 B)
 constexpr int ROWS_SCRATCH = 32 * RS2 * 2; // doubles per warp for kernels that touch vector fields
 constexpr int SCR1 = 288;                  // doubles per warp for scalar-only kernels (preconditioner: 4*72)
@@ -279,29 +275,21 @@ __device__ __forceinline__ void rows_lap_c(const double2 (&cz)[4], const double 
     if (G::on) { // pushed halo rows: wait (once, only here) for the ranks that own them
       if (nb.x >= gate.nloc || nb.y >= gate.nloc || (y == 7 && nb.w >= gate.nloc) || (y == 0 && nb.z >= gate.nloc)) gate.wait();
     }
-    // A neighbour block that belongs to this warp's own chunk (in Hilbert order four consecutive, 4-aligned blocks form a
-    // 2x2 square, so two of a block's four neighbours do) is already parked in the scratch: read it there, not in memory.
-    const int s0 = row0 >> 3;
-    const unsigned lW = (unsigned)(nb.x - s0), lE = (unsigned)(nb.y - s0), lS = (unsigned)(nb.z - s0), lN = (unsigned)(nb.w - s0);
-    const unsigned nblk = CUP2D_ROWS_INCHUNK ? (unsigned)((nvalid + 7) >> 3) : 0u;
-    const double2 *s2 = reinterpret_cast<const double2 *>(sw);
     double up[8], dn[8];
     if (y < 7) rows_peek1(sw, lane + 1, up);
-    else if (lN < nblk) rows_peek1(sw, (int)lN * 8, up);
     else if (nb.w >= 0) nb_row1(z, nb.w, 0, up, gate);
     else {
 #pragma unroll
       for (int i = 0; i < 8; i++) up[i] = c[i];
     }
     if (y > 0) rows_peek1(sw, lane - 1, dn);
-    else if (lS < nblk) rows_peek1(sw, (int)lS * 8 + 7, dn);
     else if (nb.z >= 0) nb_row1(z, nb.z, 7, dn, gate);
     else {
 #pragma unroll
       for (int i = 0; i < 8; i++) dn[i] = c[i];
     }
-    const double gW = lW < nblk ? s2[swz((int)lW * 8 + y, 3)].y : (nb.x >= 0 ? nb_ld1(z, nb.x, y * 8 + 7, gate) : c[0]);
-    const double gE = lE < nblk ? s2[swz((int)lE * 8 + y, 0)].x : (nb.y >= 0 ? nb_ld1(z, nb.y, y * 8 + 0, gate) : c[7]);
+    const double gW = nb.x >= 0 ? nb_ld1(z, nb.x, y * 8 + 7, gate) : c[0];
+    const double gE = nb.y >= 0 ? nb_ld1(z, nb.y, y * 8 + 0, gate) : c[7];
 #pragma unroll
     for (int i = 0; i < 8; i++) {
       const double e = i < 7 ? c[i + 1] : gE;

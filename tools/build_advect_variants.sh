@@ -13,8 +13,3 @@ build() { # tag, defines
   rm -f advect_v_$1.o
 }
 build tma "-DCUP2D_ADV_LDGSTS=0"
-# the Krylov stencil kernels without the in-chunk neighbour reads (rows.cuh)
-$NV -DCUP2D_ROWS_INCHUNK=0 -c poisson.cu -o poisson_v_noinchunk.o 2> poisson_noinchunk.ptxas.log
-$NV -DCUP2D_ROWS_INCHUNK=0 -c pressure.cu -o pressure_v_noinchunk.o 2> pressure_noinchunk.ptxas.log
-nvcc -gencode arch=compute_100a,code=sm_100a -shared -o ../libcup2d_b200_noinchunk.so api.o advect.o pressure_v_noinchunk.o poisson_v_noinchunk.o halo.o regrid.o penalize.o amr_ops.o amr_fast.o amr_penalize.o amr_plan.o -ccbin /usr/bin/g++
-rm -f poisson_v_noinchunk.o pressure_v_noinchunk.o
