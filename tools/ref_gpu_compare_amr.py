@@ -34,13 +34,13 @@ def read_records(path):
 def compare(nsteps=12, level_max=8, names=("ref_harness_gpu", "ref_harness_b200"), timeout=None):
     out = {}
     with tempfile.TemporaryDirectory() as tmp:
-        recs = {}
-        for n in names:
-            f = os.path.join(tmp, n + ".bin")
+        recs = []
+        for i, n in enumerate(names):   # the same name twice = two runs of one program (run-to-run variation)
+            f = os.path.join(tmp, f"{i}_{n}.bin")
             subprocess.run([os.path.join(ROOT, "oracle", "_ref", n), "amr", str(level_max), str(nsteps), "1000", f],
                            check=True, stderr=subprocess.DEVNULL, env=dict(os.environ, OMP_NUM_THREADS="8"), timeout=timeout)
-            recs[n] = read_records(f)
-    a, b = recs[names[0]], recs[names[1]]
+            recs.append(read_records(f))
+    a, b = recs
     rows = []
     for s in range(min(len(a), len(b))):
         same_grid = a[s]["lij"].shape == b[s]["lij"].shape and bool((a[s]["lij"] == b[s]["lij"]).all())
@@ -66,4 +66,7 @@ def compare(nsteps=12, level_max=8, names=("ref_harness_gpu", "ref_harness_b200"
 
 if __name__ == "__main__":
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 12
-    print(json.dumps(compare(n)))
+    if len(sys.argv) > 2 and sys.argv[2] == "self":   # the reference against itself: how reproducible is the comparison's yardstick
+        print(json.dumps({"pair": "ref_harness_gpu twice", **compare(n, names=("ref_harness_gpu", "ref_harness_gpu"))}))
+    else:
+        print(json.dumps(compare(n)))
