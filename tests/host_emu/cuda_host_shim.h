@@ -162,6 +162,7 @@ template <class T, class U> cudaError_t cudaMemcpyToSymbol(T &sym, const U &src,
 #ifndef CUP2D_FULL_EMU
 namespace cup2d {
 inline bool is_pos(double x) { return !(x <= 0); } // U > 0, NaN counted as positive (common.cuh)
+inline int __double2hiint(double x) { long long b; memcpy(&b, &x, 8); return (int)(b >> 32); } // (the full build gets it from cuda_runtime.h)
 }
 #endif
 struct cup2d_sim;

@@ -154,29 +154,3 @@ def test_emulated_fast_pressure_kernels(emu):
     up("pres", d["pres"])
     assert lib.cup2d_amr_pressure_gradient_fast(h, dt) == 0
     assert rel(down("tmpV", 2), d["gradp"]) < 1e-12
-
-
-def test_emulated_weno_variants_keep_the_result(golden_dir):
-    """the two arithmetic variants prepared in csrc/weno.cuh (cubic reciprocal step, lazy smoothness indicators; off in the
-    validated build) change the advect result by rounding only"""
-    sys.path.insert(0, os.path.join(HERE, "host_emu"))
-    import build
-    lib = C.CDLL(build.build(defines=("CUP2D_WENO_CUBIC_RCP=1", "CUP2D_WENO_LAZY_BETAS=1"), tag="_variants"))
-    P, D, I, L = C.c_void_p, C.c_double, C.c_int, C.c_int64
-    lib.cup2d_amr_create.argtypes = [L, C.POINTER(C.c_int32), C.c_int32, C.c_int32, D, D, C.c_int32, C.POINTER(P)]
-    lib.cup2d_amr_destroy.argtypes = [P]
-    lib.cup2d_amr_field_upload.argtypes = [P, I, P]
-    lib.cup2d_amr_field_download.argtypes = [P, I, P]
-    lib.cup2d_amr_advect_diffuse_rhs_fast.argtypes = [P, D]
-    d = np.load(os.path.join(golden_dir, "amrlab_lmax8.npz"))
-    blocks = np.ascontiguousarray(d["blocks"], dtype=np.int32)
-    h = P()
-    assert lib.cup2d_amr_create(len(blocks), blocks.ctypes.data_as(C.POINTER(C.c_int32)), int(d["bpdx"]), int(d["bpdy"]),
-                                float(d["h0"]), float(d["nu"]), 0, C.byref(h)) == 0
-    vel = np.ascontiguousarray(d["vel"])
-    assert lib.cup2d_amr_field_upload(h, 0, vel.ctypes.data) == 0
-    assert lib.cup2d_amr_advect_diffuse_rhs_fast(h, float(d["dt"])) == 0
-    out = np.empty_like(vel)
-    assert lib.cup2d_amr_field_download(h, 2, out.ctypes.data) == 0
-    lib.cup2d_amr_destroy(h)
-    assert rel(out, d["adv"]) < 1e-12

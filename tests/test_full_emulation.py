@@ -18,7 +18,7 @@ import pytest
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 
-SUBSET = ("(operators_vs_reference_golden or vorticity_tagging or adapt_tags or dump_files or penalisation_phase or shape_calls "
+SUBSET = ("(operators_vs_reference_golden or uniformly_advected or vorticity_tagging or adapt_tags or dump_files or penalisation_phase or shape_calls "
           "or steps_L2_random_k8 or rectangular_domain or host_pipeline or degenerate or amr_bodies or amr_adapt_tags or amr_dump or (uniform_mesh_equals and True) or synthetic_three_level or amr_fast or amr_advect_diffuse or amr_pressure_gradient) "
           "and not reference_driver")
 
@@ -355,6 +355,13 @@ assert worst < 1e-11
     assert r.returncode == 0 and "WORST" in r.stdout, r.stdout[-1500:]
 
 
+# The two sanitizer builds recompile every product source with -fsanitize and take 4-6 minutes on 8 cores: they run when asked
+# for (CUP2D_TEST_SANITIZERS=1, as tools/run_emulated_gpu_tests.sh does); the hardware counterpart is compute-sanitizer
+# memcheck/racecheck on the GPU box (profiles/r02a_sanitizer_*).
+sanitizers = pytest.mark.skipif(os.environ.get("CUP2D_TEST_SANITIZERS") != "1", reason="sanitizer builds are opt-in: CUP2D_TEST_SANITIZERS=1")
+
+
+@sanitizers
 def test_no_data_races_under_thread_sanitizer():
     """race hunt: the emulated product sources rebuilt with -fsanitize=thread run a uniform-grid time step (advect with its
     staged loads, pressure kernels, the Krylov kernels with their grid reductions, the chi-mask tags) and the multi-level step
@@ -374,6 +381,7 @@ def test_no_data_races_under_thread_sanitizer():
     assert r.stdout.count("multi-level step") == 2 and "uniform step" in r.stdout and "bodies / tags / dump" in r.stdout
 
 
+@sanitizers
 def test_no_out_of_bounds_or_misaligned_access_under_address_sanitizer(golden_dir, tmp_path):
     """memcheck stand-in: the same driver built with -fsanitize=address,alignment,bounds.  Every emulated device buffer and
     every __shared__ array is its own exact-size allocation filled with 0xFF bytes (cudaMalloc does not zero), the vector
@@ -403,16 +411,17 @@ def test_no_out_of_bounds_or_misaligned_access_under_address_sanitizer(golden_di
 
 
 def test_measurement_variants_keep_parity():
-    """the default-off variants prepared for round-2 measurements (advect.cu: CUP2D_ADV_WARP_ROWS — warp-local rows, the CTA
-    barrier between the passes becomes a __syncwarp; weno.cuh: cubic reciprocal step, lazy smoothness indicators) built
-    together into an emulated library: the operator / time-step parity tests still pass.  (Their race check:
-    build.build_tsan(defines, tag) + the resulting executable; clean when this was written.)"""
+    """the build switches of the advect stage that are OFF in the default build (advect.cu: CUP2D_ADV_LDGSTS=0 — the tile
+    filled by per-row bulk copies on one mbarrier instead of cp.async; CUP2D_ADV_SPECIALIZE=0 — one copy of the line code with
+    run-time strides for both passes; CUP2D_ADV_FASTPATH=0 — every line through the general core) built together into an
+    emulated library: the operator / advect / time-step parity tests still pass.  (Each was also run on hardware:
+    profiles/r02e_variants.jsonl, r02g_variants.jsonl.)"""
     sys.path.insert(0, os.path.join(HERE, "host_emu"))
     import build
-    lib = build.build_full(("CUP2D_ADV_WARP_ROWS=1", "CUP2D_WENO_CUBIC_RCP=1", "CUP2D_WENO_LAZY_BETAS=1"), "_variants")
+    lib = build.build_full(("CUP2D_ADV_LDGSTS=0", "CUP2D_ADV_SPECIALIZE=0", "CUP2D_ADV_FASTPATH=0"), "_variants")
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(HERE, "test_gpu_parity.py"), "-m", "gpu", "-q", "-x", "-k",
-                        "(operators_vs_reference_golden or steps_L2_random_k8 or rectangular_domain) and not reference_driver",
-                        "-p", "no:cacheprovider"],
+                        "(operators_vs_reference_golden or steps_L2_random_k8 or rectangular_domain or advect_stage_vs_oracle or uniformly_advected) "
+                        "and not reference_driver", "-p", "no:cacheprovider"],
                        stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=dict(os.environ, CUP2D_B200_LIB=lib),
                        timeout=900, cwd=ROOT)
     assert r.returncode == 0 and " passed" in r.stdout, r.stdout[-1500:]

@@ -1,4 +1,7 @@
 #!/bin/bash
+# RECORD of the first GPU call of round 2 (r02a).  The three advect variants it A/B-tested (CUP2D_ADV_WARP_ROWS,
+# CUP2D_WENO_CUBIC_RCP, CUP2D_WENO_LAZY_BETAS) no longer exist as switches: warp-local rows and the cubic reciprocal step
+# are the default since the rewrite of the advect stage (r02e), the lazy indicators are subsumed by the upwind core.
 # First GPU-box call of round 2, ≈ 20 min of box time on one GPU:
 #   gpurun --timeout 1500 -- 'bash tools/gpu_round2_first.sh r02a'
 # 1. the validated parity suite; 2. the never-run multi-level device path (every test, no -x) + compute-sanitizer on its
