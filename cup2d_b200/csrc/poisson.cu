@@ -340,7 +340,11 @@ k_spmv(const double *__restrict__ z, const double *__restrict__ d, double *__res
     chunk_ld(z, row0, nv, lane, cz);
     if (HOIST) chunk_ld(d, row0, nv, lane, cd);
     double zz[8], az[8];
+#if CUP2D_ROWS_COOP
+    rows_lap_coop(cz, z, row0, nv, nbr, sw, lane, zz, az, IRR ? irr : IrrView(), gate);
+#else
     rows_lap_c(cz, z, row0, nv, nbr, sw, lane, zz, az, IRR ? irr : IrrView(), gate);
+#endif
     // back to chunk layout: the dots and the store are element-wise
     if (!HOIST) chunk_ld(d, row0, nv, lane, cd);
     rows_to_chunk(sw, lane, az, ca);

@@ -18,7 +18,10 @@ namespace cup2d {
 
 constexpr int RS2 = 9;                     // vector row stride in double2 (8 used + 1 pad = 144 B)
 constexpr int ROWS_SCRATCH = 32 * RS2 * 2; // doubles per warp for kernels that touch vector fields
-constexpr int SCR1 = 288;                  // doubles per warp for scalar-only kernels (preconditioner: 4*72)
+constexpr int SCR1 = 320;                  // doubles per warp for scalar-only kernels: 256 chunk + 64 edge-row staging (rows_lap_c); the preconditioner uses 4*72
+#ifndef CUP2D_ROWS_COOP
+#define CUP2D_ROWS_COOP 1 // 0: the SpMV kernels use the plain rows_lap_c as well (measurement variant)
+#endif
 
 __device__ __forceinline__ int swz(int r, int p) { return r * 4 + (p ^ ((r >> 1) & 3)); }
 
@@ -264,6 +267,89 @@ __device__ __forceinline__ void rows_lap(const double *__restrict__ z, int row0,
   chunk_ld(z, row0, nvalid, lane, cz);
   rows_lap_c(cz, z, row0, nvalid, nbr, sw, lane, c, out, irr);
 }
+// ---- rows_lap_coop: the variant the SpMV kernels use (measured there: 0.291 vs 0.302 ms at 8192^2; k_init and the
+// right-hand-side kernel, with their higher register pressure, are 4 % faster on the plain form below, profiles/r02k) ----
+// The L1 data pipe (shared-memory and global-load wavefronts together) is what bounds the stencil kernels, not DRAM
+// (profiles/r02i_krylov_ncu.md: 75 % against 70 %), and the neighbour accesses were 60 % of its global part.  So:
+//  * the edge rows of the S/N neighbour blocks come in with ONE warp-wide 128-bit load: lanes 0..15 fetch the four 16-byte
+//    pieces of row 0 of the N neighbour of each of the warp's four blocks, lanes 16..31 row 7 of the S neighbours (8 wavefronts
+//    instead of 32 for eight quarter-empty per-lane loads); the pieces are staged behind the chunk in the scratch;
+//  * every lane then reads the rows above and below through (base, swizzle key) pairs — the neighbouring lane's row of the
+//    chunk, a staged edge row, or its own row at a wall (Neumann: ghost = own cell) — piece by piece, with no arrays and
+//    no branches in the stencil loop;
+//  * a W/E ghost cell whose block belongs to the warp's own chunk (in Hilbert order four consecutive, 4-aligned blocks form
+//    a 2x2 square, so one of the two does) is read from the scratch.
+template <class G>
+__device__ __forceinline__ void rows_lap_coop(const double2 (&cz)[4], const double *__restrict__ z, int row0,
+                                              int nvalid, const int4 *__restrict__ nbr, double *sw, int lane,
+                                              double (&c)[8], double (&out)[8], const IrrView irr, const G gate) {
+  const int row = row0 + lane, slot = row >> 3, y = row & 7;
+  const int4 nb = lane < nvalid ? nbr[slot] : make_int4(-1, -1, -1, -1);
+  // staging rows behind the chunk: row 2b = N edge row of block b (pieces in place), row 2b+1 = S edge row of block b
+  // (piece p at p ^ 3): exactly the 16-byte bank groups the chunk rows 8b+8 / 8b-1 would occupy, so an edge lane's reads
+  // stay conflict-free with the reads of the seven other lanes of its quarter warp
+  double2 *stage = reinterpret_cast<double2 *>(sw + 256);
+  {
+    const int b = (lane >> 2) & 3, piece = lane & 3;
+    const int nbN = __shfl_sync(0xffffffffu, nb.w, 8 * b), nbS = __shfl_sync(0xffffffffu, nb.z, 8 * b);
+    const int src = lane < 16 ? nbN : nbS;
+    double2 v = make_double2(0.0, 0.0);
+    if (src >= 0) {
+      const bool halo = G::on && src >= gate.nloc;
+      if (halo) gate.wait();
+      const double2 *p = reinterpret_cast<const double2 *>(z + (size_t)src * 64 + (lane < 16 ? 0 : 56)) + piece;
+      v = halo ? ld_coherent2(p) : *p;
+    }
+    __syncwarp(); // the previous user of the scratch is done with it
+    stage[lane < 16 ? 8 * b + piece : 8 * b + 4 + (piece ^ 3)] = v;
+  }
+  chunk_to_rows(sw, lane, cz, c); // (its barriers also publish the staged rows)
+  if (lane < nvalid) {
+    if (G::on) { // pushed halo rows: wait (once, only here) for the ranks that own them
+      if (nb.x >= gate.nloc || nb.y >= gate.nloc) gate.wait();
+    }
+    const double2 *s2 = reinterpret_cast<const double2 *>(sw);
+    const int own_key = (lane >> 1) & 3;
+    // rows above / below: (base, key) with piece k at base[k ^ key]
+    const double2 *bu = y < 7 ? s2 + (lane + 1) * 4 : (nb.w >= 0 ? stage + (lane >> 3) * 8 : s2 + lane * 4);
+    const int ku = y < 7 ? ((lane + 1) >> 1) & 3 : (nb.w >= 0 ? 0 : own_key);
+    const double2 *bd = y > 0 ? s2 + (lane - 1) * 4 : (nb.z >= 0 ? stage + (lane >> 3) * 8 + 4 : s2 + lane * 4);
+    const int kd = y > 0 ? ((lane - 1) >> 1) & 3 : (nb.z >= 0 ? 3 : own_key);
+    const int s0 = row0 >> 3;
+    const unsigned nblk = (unsigned)((nvalid + 7) >> 3), lW = (unsigned)(nb.x - s0), lE = (unsigned)(nb.y - s0);
+    const double gW = lW < nblk ? s2[swz((int)lW * 8 + y, 3)].y : (nb.x >= 0 ? nb_ld1(z, nb.x, y * 8 + 7, gate) : c[0]);
+    const double gE = lE < nblk ? s2[swz((int)lE * 8 + y, 0)].x : (nb.y >= 0 ? nb_ld1(z, nb.y, y * 8 + 0, gate) : c[7]);
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const double2 u = bu[k ^ ku], d = bd[k ^ kd];
+      const int i = 2 * k;
+      const double w0 = i > 0 ? c[i - 1] : gW, e1 = i + 1 < 7 ? c[i + 2] : gE;
+      out[i] = (((d.x + w0) + c[i + 1]) + u.x) - 4.0 * c[i];         // summation order S,W,E,N then -4C
+      out[i + 1] = (((d.y + c[i]) + e1) + u.y) - 4.0 * c[i + 1];
+    }
+    if (irr.blk) { // general rows override the stencil (rare: block faces at coarse-fine interfaces)
+      const int k = irr.blk[slot];
+      if (k >= 0) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+          const int idx = irr.tab[k * 64 + y * 8 + i];
+          if (idx >= 0) {
+            double acc = 0.0;
+            for (int j = irr.rowptr[idx]; j < irr.rowptr[idx + 1]; j++) {
+              const int cj = irr.col[j];
+              acc = fma(irr.val[j], (G::on && cj >= gate.nloc * 64) ? ld_coherent(z + cj) : z[cj], acc);
+            }
+            out[i] = acc;
+          }
+        }
+      }
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; i++) out[i] = 0.0;
+  }
+}
+
 template <class G>
 __device__ __forceinline__ void rows_lap_c(const double2 (&cz)[4], const double *__restrict__ z, int row0,
                                            int nvalid, const int4 *__restrict__ nbr, double *sw, int lane,
@@ -318,5 +404,4 @@ __device__ __forceinline__ void rows_lap_c(const double2 (&cz)[4], const double 
     for (int i = 0; i < 8; i++) out[i] = 0.0;
   }
 }
-
 } // namespace cup2d

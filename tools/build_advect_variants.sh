@@ -13,3 +13,8 @@ build() { # tag, defines
   rm -f advect_v_$1.o
 }
 build tma "-DCUP2D_ADV_LDGSTS=0"
+# the row-mapped stencil kernels with per-lane edge-row loads and all ghost cells from global memory (rows.cuh, round-1 form)
+$NV -DCUP2D_ROWS_COOP=0 -c poisson.cu -o poisson_v_nocoop.o 2> poisson_nocoop.ptxas.log
+$NV -DCUP2D_ROWS_COOP=0 -c pressure.cu -o pressure_v_nocoop.o 2> pressure_nocoop.ptxas.log
+nvcc -gencode arch=compute_100a,code=sm_100a -shared -o ../libcup2d_b200_nocoop.so api.o advect.o pressure_v_nocoop.o poisson_v_nocoop.o halo.o regrid.o penalize.o amr_ops.o amr_fast.o amr_penalize.o amr_plan.o -ccbin /usr/bin/g++
+rm -f poisson_v_nocoop.o pressure_v_nocoop.o
