@@ -319,7 +319,9 @@ __global__ void __launch_bounds__(NT, SPMV_CTAS)
 k_spmv(const double *__restrict__ z, const double *__restrict__ d, double *__restrict__ yout,
        const int4 *__restrict__ nbr, int nrows, KrylovState *st, double *partials,
        unsigned int *counter, Comm comm, IrrView irr, unsigned src_mask) {
-  __shared__ __align__(16) double s_scr[WPB * SCR1];
+  constexpr bool COOP = CUP2D_ROWS_COOP && !MULTI; // see the call below
+  constexpr int SCRW = COOP ? SCR_COOP : SCR1;
+  __shared__ __align__(16) double s_scr[WPB * SCRW];
   if (st->done) return;
   typename std::conditional<MULTI, HaloGate, NoGate>::type gate;
   if (MULTI) {
@@ -331,7 +333,9 @@ k_spmv(const double *__restrict__ z, const double *__restrict__ d, double *__res
     }
   }
   double sums[2] = {0, 0};
-  CHUNK_LOOP() {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double *sw = s_scr + warp * SCRW;
+  for (int row0 = (blockIdx.x * WPB + warp) * 32; row0 < nrows; row0 += gridDim.x * WPB * 32) {
     const int nv = min(32, nrows - row0);
     // uniform grids: both global loads are issued before any shared-memory work (memory-level parallelism,
     // -4 % per iteration in profiles/r01h); with general rows the extra live registers cost more than that
@@ -340,11 +344,11 @@ k_spmv(const double *__restrict__ z, const double *__restrict__ d, double *__res
     chunk_ld(z, row0, nv, lane, cz);
     if (HOIST) chunk_ld(d, row0, nv, lane, cd);
     double zz[8], az[8];
-#if CUP2D_ROWS_COOP
-    rows_lap_coop(cz, z, row0, nv, nbr, sw, lane, zz, az, IRR ? irr : IrrView(), gate);
-#else
-    rows_lap_c(cz, z, row0, nv, nbr, sw, lane, zz, az, IRR ? irr : IrrView(), gate);
-#endif
+    // one GPU: the cooperative form (rows.cuh; measured r02k/r02l).  Several ranks keep the plain form, which is the code
+    // that ran on 2, 4 and 8 GPUs (r02i/r02j); the cooperative form handles halo slots too (emulated 2-rank tests) but has
+    // not been timed or run on more than one GPU
+    if (COOP) rows_lap_coop(cz, z, row0, nv, nbr, sw, lane, zz, az, IRR ? irr : IrrView(), gate);
+    else rows_lap_c(cz, z, row0, nv, nbr, sw, lane, zz, az, IRR ? irr : IrrView(), gate);
     // back to chunk layout: the dots and the store are element-wise
     if (!HOIST) chunk_ld(d, row0, nv, lane, cd);
     rows_to_chunk(sw, lane, az, ca);

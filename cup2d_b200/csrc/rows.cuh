@@ -18,7 +18,8 @@ namespace cup2d {
 
 constexpr int RS2 = 9;                     // vector row stride in double2 (8 used + 1 pad = 144 B)
 constexpr int ROWS_SCRATCH = 32 * RS2 * 2; // doubles per warp for kernels that touch vector fields
-constexpr int SCR1 = 320;                  // doubles per warp for scalar-only kernels: 256 chunk + 64 edge-row staging (rows_lap_c); the preconditioner uses 4*72
+constexpr int SCR1 = 288;                  // doubles per warp for scalar-only kernels (preconditioner: 4*72)
+constexpr int SCR_COOP = 320;              // rows_lap_coop: 256 for the chunk + 64 for the staged edge rows
 #ifndef CUP2D_ROWS_COOP
 #define CUP2D_ROWS_COOP 1 // 0: the SpMV kernels use the plain rows_lap_c as well (measurement variant)
 #endif
