@@ -7,12 +7,14 @@
 // (main.cpp:6618-6626, 6634-6642) are fused into the store.
 //
 // One CTA = one tile of 4x4 blocks (32x32 cells), 128 threads.  Data path (round 2: no staging buffer, no repack):
-//   HBM --cp.async.bulk (1-D TMA), one copy per 8-cell ROW of a block (128 B; 48 B for the three ghost columns of the W/E
-//        neighbours), every thread issues at most two and arrives on one mbarrier with its own byte count--> the padded
-//        (u,v)-interleaved plane P[38][39] (3-cell ghost ring, row stride odd in 16-byte units) exactly where the stencil reads it
+//   HBM --16-byte cp.async (SASS LDGSTS), one per cell, lanes along the 8 cells = 128 contiguous bytes of a block row; 11-13
+//        per thread, no registers in between (build option: one cp.async.bulk per block row on an mbarrier, CUP2D_ADV_LDGSTS=0)-->
+//        the padded (u,v)-interleaved plane P[38][39] (3-cell ghost ring, row stride odd in 16-byte units), every cell exactly
+//        where the stencil reads it
 //   x pass: warp = the 8 rows of its block row, lane = (8-cell segment, row): 128-bit conflict-free LDS -> partial results R
 //   y pass: lane = column, warp = the same block row: reads only what ITS OWN warp wrote to R (__syncwarp, no CTA barrier
 //        between the passes), + old, 128-bit coalesced stores
+//   per line of 8 cells: all advected one way -> branch-free upwind core (mirrored line if from the right), else general core
 // Wall ghosts exist only in the perimeter tiles of the domain and are synthesised there after the copies landed.
 //
 // Arithmetic: all FP64; this kernel is bound by the FP64 pipe, not by HBM — see weno.cuh for the algebra that brings a
